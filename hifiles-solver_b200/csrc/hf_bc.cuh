@@ -1,0 +1,335 @@
+// Boundary ghost states and boundary gradients: restatement of bdy_inters::set_boundary_conditions and
+// bdy_inters::set_boundary_gradients (reference src/bdy_inters.cpp:340-1019, 1138-1189) as device functions.
+// Wall-model (use_wm), pressure-ramp and synthetic-eddy inlet branches are not part of this build; the host
+// rejects inputs that ask for them.
+#pragma once
+#include "hf_physics.cuh"
+#include "../../include/hifiles_b200.h"
+
+enum
+{
+  HF_SUB_IN_SIMP = 0, HF_SUB_OUT_SIMP = 1, HF_SUB_IN_CHAR = 2, HF_SUB_OUT_CHAR = 3, HF_SUP_IN = 4, HF_SUP_OUT = 5,
+  HF_SLIP_WALL = 6, HF_CYCLIC = 7, HF_ISOTHERM_WALL = 8, HF_ADIABAT_WALL = 9, HF_CHAR = 10, HF_SLIP_WALL_DUAL = 11,
+  HF_AD_WALL = 12
+};
+
+__device__ __forceinline__ bool hf_is_wall(int f)
+{
+  return f == HF_SLIP_WALL || f == HF_ISOTHERM_WALL || f == HF_ADIABAT_WALL || f == HF_AD_WALL || f == HF_SLIP_WALL_DUAL;
+}
+
+template <int ND, int NF>
+__device__ void set_boundary_conditions(int sol_spec, const hf_bc &B, const double *u_l, double *u_r, const double *norm, double gamma, double R_ref)
+{
+  if (NF == 1)
+  {
+    if (B.bc_flag == HF_AD_WALL) u_r[0] = 0.0;
+    return;
+  }
+  const int bc_flag = B.bc_flag;
+  double rho_l = u_l[0], rho_r = 0., e_l = u_l[ND + 1], e_r = 0., p_l, p_r, T_r, vn_l, v_sq;
+  double v_l[ND], v_r[ND];
+#pragma unroll
+  for (int i = 0; i < ND; i++) { v_l[i] = u_l[i + 1] / u_l[0]; v_r[i] = 0.; }
+  v_sq = 0.;
+#pragma unroll
+  for (int i = 0; i < ND; i++) v_sq += (v_l[i] * v_l[i]);
+  p_l = (gamma - 1.0) * (e_l - 0.5 * rho_l * v_sq);
+
+  if (bc_flag == HF_SUB_IN_SIMP)
+  {
+    rho_r = B.rho;
+#pragma unroll
+    for (int i = 0; i < ND; i++) v_r[i] = B.velocity[i];
+    v_sq = 0.;
+#pragma unroll
+    for (int i = 0; i < ND; i++) v_sq += (v_r[i] * v_r[i]);
+    e_r = p_l / (gamma - 1.0) + 0.5 * rho_r * v_sq;
+  }
+  else if (bc_flag == HF_SUB_OUT_SIMP)
+  {
+    vn_l = 0.;
+#pragma unroll
+    for (int i = 0; i < ND; i++) vn_l += v_l[i] * norm[i];
+    double machn_l = fabs(vn_l) / sqrt(gamma * p_l / rho_l);
+    if (vn_l < 0)
+    {
+#pragma unroll
+      for (int i = 0; i < ND; i++) v_r[i] = vn_l * norm[i];
+      v_sq = 0.;
+#pragma unroll
+      for (int i = 0; i < ND; i++) v_sq += (v_r[i] * v_r[i]);
+      T_r = B.T_total - 0.5 * v_sq * (gamma - 1.0) / (R_ref * gamma);
+      p_r = B.p_static * pow((1.0 + 0.5 * (gamma - 1.0) * (v_sq / (gamma * R_ref * T_r))), -gamma / (gamma - 1.0));
+      rho_r = p_r / (R_ref * T_r);
+      e_r = (p_r / (gamma - 1.0)) + 0.5 * rho_r * v_sq;
+    }
+    else if (vn_l >= 0 && machn_l >= 1)
+    {
+      rho_r = rho_l;
+#pragma unroll
+      for (int i = 0; i < ND; i++) v_r[i] = v_l[i];
+      e_r = e_l;
+    }
+    else
+    {
+#pragma unroll
+      for (int i = 0; i < ND; i++) v_r[i] = v_l[i];
+      rho_r = rho_l;
+      p_r = B.p_static;
+      v_sq = 0.;
+#pragma unroll
+      for (int i = 0; i < ND; i++) v_sq += (v_r[i] * v_r[i]);
+      e_r = (p_r / (gamma - 1.0)) + 0.5 * rho_r * v_sq;
+    }
+  }
+  else if (bc_flag == HF_SUB_IN_CHAR)
+  {
+    double p_total_temp = B.p_total, T_total_temp = B.T_total;
+    double n_free_stream[3] = {B.nx, B.ny, B.nz};
+    vn_l = 0.;
+#pragma unroll
+    for (int i = 0; i < ND; i++) vn_l += v_l[i] * norm[i];
+    double c_l = sqrt(gamma * p_l / rho_l);
+    double R_plus = vn_l + 2.0 * c_l / (gamma - 1.0);
+    double c_total_sq = gamma * R_ref * T_total_temp;
+    double alpha = 0.;
+#pragma unroll
+    for (int i = 0; i < ND; i++) alpha += norm[i] * n_free_stream[i];
+    double aa = 1.0 + 0.5 * (gamma - 1.0) * alpha * alpha;
+    double bb = -(gamma - 1.0) * alpha * R_plus;
+    double cc = 0.5 * (gamma - 1.0) * R_plus * R_plus - 2.0 * c_total_sq / (gamma - 1.0);
+    double dd = bb * bb - 4.0 * aa * cc;
+    dd = sqrt(fmax(dd, 0.0));
+    double V_r = (-bb + dd) / (2.0 * aa);
+    V_r = fmax(V_r, 0.0);
+    v_sq = V_r * V_r;
+    double c_r_sq = c_total_sq - 0.5 * (gamma - 1.0) * v_sq;
+    double Mach_sq = v_sq / (c_r_sq);
+    Mach_sq = fmin(Mach_sq, 1.0);
+    v_sq = Mach_sq * c_r_sq;
+    V_r = sqrt(v_sq);
+    c_r_sq = c_total_sq - 0.5 * (gamma - 1.0) * v_sq;
+#pragma unroll
+    for (int i = 0; i < ND; i++) v_r[i] = V_r * n_free_stream[i];
+    T_r = c_r_sq / (gamma * R_ref);
+    p_r = p_total_temp * pow(T_r / T_total_temp, gamma / (gamma - 1.0));
+    rho_r = p_r / (R_ref * T_r);
+    e_r = (p_r / (gamma - 1.0)) + 0.5 * rho_r * v_sq;
+  }
+  else if (bc_flag == HF_SUB_OUT_CHAR)
+  {
+    vn_l = 0.;
+#pragma unroll
+    for (int i = 0; i < ND; i++) vn_l += v_l[i] * norm[i];
+    double c_l = sqrt(gamma * p_l / rho_l);
+    double R_plus = vn_l + 2.0 * c_l / (gamma - 1.0);
+    double s = p_l / pow(rho_l, gamma);
+    p_r = B.p_static;
+    rho_r = pow(p_r / s, 1.0 / gamma);
+    double c_r = sqrt(gamma * p_r / rho_r);
+    double vn_r = R_plus - 2.0 * c_r / (gamma - 1.0);
+    v_sq = 0.;
+#pragma unroll
+    for (int i = 0; i < ND; i++)
+    {
+      v_r[i] = v_l[i] + (vn_r - vn_l) * norm[i];
+      v_sq += (v_r[i] * v_r[i]);
+    }
+    e_r = (p_r / (gamma - 1.0)) + 0.5 * rho_r * v_sq;
+  }
+  else if (bc_flag == HF_SUP_IN)
+  {
+    rho_r = B.rho;
+#pragma unroll
+    for (int i = 0; i < ND; i++) v_r[i] = B.velocity[i];
+    p_r = B.p_static;
+    v_sq = 0.;
+#pragma unroll
+    for (int i = 0; i < ND; i++) v_sq += (v_r[i] * v_r[i]);
+    e_r = (p_r / (gamma - 1.0)) + 0.5 * rho_r * v_sq;
+  }
+  else if (bc_flag == HF_SUP_OUT)
+  {
+    rho_r = rho_l;
+#pragma unroll
+    for (int i = 0; i < ND; i++) v_r[i] = v_l[i];
+    e_r = e_l;
+  }
+  else if (bc_flag == HF_SLIP_WALL)
+  {
+    rho_r = rho_l;
+    vn_l = 0.;
+#pragma unroll
+    for (int i = 0; i < ND; i++) vn_l += v_l[i] * norm[i];
+    if (sol_spec == 0)
+    {
+#pragma unroll
+      for (int i = 0; i < ND; i++) v_r[i] = v_l[i] - 2 * vn_l * norm[i];
+    }
+    else
+    {
+#pragma unroll
+      for (int i = 0; i < ND; i++) v_r[i] = v_l[i] - vn_l * norm[i];
+    }
+    v_sq = 0.;
+#pragma unroll
+    for (int i = 0; i < ND; i++) v_sq += (v_r[i] * v_r[i]);
+    e_r = p_l / (gamma - 1.0) + 0.5 * rho_r * v_sq;
+  }
+  else if (bc_flag == HF_ISOTHERM_WALL)
+  {
+    T_r = B.T_static;
+    rho_r = rho_l;
+    if (sol_spec == 0)
+    {
+#pragma unroll
+      for (int i = 0; i < ND; i++) v_r[i] = 2 * B.velocity[i] - v_l[i];
+    }
+    else
+    {
+#pragma unroll
+      for (int i = 0; i < ND; i++) v_r[i] = B.velocity[i];
+    }
+    v_sq = 0.;
+#pragma unroll
+    for (int i = 0; i < ND; i++) v_sq += (v_r[i] * v_r[i]);
+    e_r = rho_r * (R_ref / (gamma - 1.0) * T_r) + 0.5 * rho_r * v_sq;
+  }
+  else if (bc_flag == HF_ADIABAT_WALL)
+  {
+    rho_r = rho_l;
+    if (sol_spec == 0)
+    {
+#pragma unroll
+      for (int i = 0; i < ND; i++) v_r[i] = 2 * B.velocity[i] - v_l[i];
+    }
+    else
+    {
+#pragma unroll
+      for (int i = 0; i < ND; i++) v_r[i] = B.velocity[i];
+    }
+    v_sq = 0.;
+#pragma unroll
+    for (int i = 0; i < ND; i++) v_sq += (v_r[i] * v_r[i]);
+    e_r = p_l / (gamma - 1.0) + 0.5 * rho_r * v_sq;
+  }
+  else if (bc_flag == HF_CHAR)
+  {
+    double r_plus, r_minus;
+    vn_l = 0.;
+#pragma unroll
+    for (int i = 0; i < ND; i++) vn_l += v_l[i] * norm[i];
+    double vn_r = 0;
+#pragma unroll
+    for (int i = 0; i < ND; i++) vn_r += B.velocity[i] * norm[i];
+    double c_l = sqrt(gamma * p_l / rho_l);
+    double c_r = sqrt(gamma * B.p_static / B.rho);
+    double mach = fabs(vn_l) / c_l;
+    if (vn_l < 0)
+    {
+      if (mach >= 1)
+      {
+        r_minus = vn_r - 2. / (gamma - 1.) * c_r;
+        r_plus = vn_r + 2. / (gamma - 1.) * c_r;
+      }
+      else
+      {
+        r_plus = vn_l + 2. / (gamma - 1.) * c_l;
+        r_minus = vn_r - 2. / (gamma - 1.) * c_r;
+      }
+      double c_star = 0.25 * (gamma - 1.) * (r_plus - r_minus);
+      double vn_star = 0.5 * (r_plus + r_minus);
+      double one_over_s = pow(B.rho, gamma) / B.p_static;
+      rho_r = pow(1. / gamma * (one_over_s * c_star * c_star), 1. / (gamma - 1.));
+#pragma unroll
+      for (int i = 0; i < ND; i++) v_r[i] = vn_star * norm[i] + (B.velocity[i] - vn_r * norm[i]);
+      v_sq = 0.;
+#pragma unroll
+      for (int i = 0; i < ND; i++) v_sq += (v_r[i] * v_r[i]);
+      p_r = rho_r / gamma * c_star * c_star;
+      e_r = (p_r / (gamma - 1.0)) + 0.5 * rho_r * v_sq;
+    }
+    else
+    {
+      if (mach >= 1)
+      {
+        r_minus = vn_l - 2. / (gamma - 1.) * c_l;
+        r_plus = vn_l + 2. / (gamma - 1.) * c_l;
+      }
+      else
+      {
+        r_plus = vn_l + 2. / (gamma - 1.) * c_l;
+        r_minus = vn_r - 2. / (gamma - 1.) * c_r;
+      }
+      double c_star = 0.25 * (gamma - 1.) * (r_plus - r_minus);
+      double vn_star = 0.5 * (r_plus + r_minus);
+      double one_over_s = pow(rho_l, gamma) / p_l;
+      rho_r = pow(1. / gamma * (one_over_s * c_star * c_star), 1. / (gamma - 1.));
+#pragma unroll
+      for (int i = 0; i < ND; i++) v_r[i] = vn_star * norm[i] + (v_l[i] - vn_l * norm[i]);
+      v_sq = 0.;
+#pragma unroll
+      for (int i = 0; i < ND; i++) v_sq += (v_r[i] * v_r[i]);
+      p_r = rho_r / gamma * c_star * c_star;
+      e_r = (p_r / (gamma - 1.0)) + 0.5 * rho_r * v_sq;
+    }
+  }
+  else if (bc_flag == HF_SLIP_WALL_DUAL)
+  {
+    rho_r = rho_l;
+    vn_l = 0.;
+#pragma unroll
+    for (int i = 0; i < ND; i++) vn_l += v_l[i] * norm[i];
+#pragma unroll
+    for (int i = 0; i < ND; i++) v_r[i] = v_l[i] - 2 * vn_l * norm[i];
+    e_r = e_l;
+  }
+  u_r[0] = rho_r;
+#pragma unroll
+  for (int i = 0; i < ND; i++) u_r[i + 1] = rho_r * v_r[i];
+  u_r[ND + 1] = e_r;
+}
+
+// grad arrays: g[k + NF*d]
+template <int ND, int NF>
+__device__ void set_boundary_gradients(int bc_flag, const double *u_r, const double *grad_ul, double *grad_ur, const double *norm)
+{
+  if (bc_flag == HF_CHAR || bc_flag == HF_SUP_IN || bc_flag == HF_SUB_IN_SIMP || bc_flag == HF_SUB_OUT_SIMP)
+  {
+#pragma unroll
+    for (int q = 0; q < NF * ND; q++) grad_ur[q] = 0.;
+  }
+  else
+  {
+#pragma unroll
+    for (int q = 0; q < NF * ND; q++) grad_ur[q] = grad_ul[q];
+  }
+  if (NF > 1 && bc_flag == HF_ADIABAT_WALL)
+  {
+    double v_sq = 0.;
+#pragma unroll
+    for (int i = 0; i < ND; i++) v_sq += (u_r[i + 1] * u_r[i + 1]);
+    double inte = (u_r[ND + 1] - 0.5 * v_sq / u_r[0]) / u_r[0];
+    double grad_vel[ND][ND];
+#pragma unroll
+    for (int j = 0; j < ND; j++)
+#pragma unroll
+      for (int i = 0; i < ND; i++)
+        grad_vel[i][j] = (grad_ur[(i + 1) + NF * j] - grad_ur[0 + NF * j] * u_r[i + 1] / u_r[0]) / u_r[0];
+    double grad_inte[ND];
+#pragma unroll
+    for (int i = 0; i < ND; i++)
+    {
+      double s = inte * grad_ur[0 + NF * i] + 0.5 * v_sq / (u_r[0] * u_r[0]) * grad_ur[0 + NF * i];
+#pragma unroll
+      for (int q = 0; q < ND; q++) s += u_r[q + 1] * grad_vel[q][i];
+      grad_inte[i] = grad_ur[(ND + 1) + NF * i] - s;
+    }
+    double dn = 0.;
+#pragma unroll
+    for (int i = 0; i < ND; i++) dn += grad_inte[i] * norm[i];
+#pragma unroll
+    for (int i = 0; i < ND; i++) grad_ur[(ND + 1) + NF * i] -= dn * norm[i];
+  }
+}

@@ -1,0 +1,1318 @@
+// Device layer, part 1: context life cycle, uploads, the staged (one kernel per reference method) path, RK update,
+// residual norms and CFL time step.  The staged kernels reproduce the reference's operation order method by
+// method and work for every element type; the fused tensor-product kernels live in hf_fused.cu.
+//   CalcResidual sequence           reference src/solver.cpp:50-223
+//   operator products (dgemm order) reference src/funcs.cpp:49-124
+//   pointwise flux + transform      reference src/eles.cpp:1415-1478, 2285-2392
+//   gradient correction/transform   reference src/eles.cpp:1890-2052
+//   interface loops                 reference src/int_inters.cpp:160-343, src/bdy_inters.cpp:213-338, 1024-1136,
+//                                   src/mpi_inters.cpp:218-575
+//   RK update                       reference src/eles.cpp:1080-1265
+#include "hf_device.h"
+#include "hf_bc.cuh"
+#include <cstring>
+#include <cstdlib>
+#include <cmath>
+#include <algorithm>
+
+static thread_local std::string g_err;
+void hf_set_error(const std::string &msg) { g_err = msg; }
+
+#define HF_FAIL(msg)            \
+  do {                          \
+    hf_set_error(msg);          \
+    return 1;                   \
+  } while (0)
+
+#define HF_LAUNCH_CHECK(c)                                                                              \
+  do {                                                                                                  \
+    (c)->launches++;                                                                                    \
+    cudaError_t e_ = cudaGetLastError();                                                                \
+    if (e_ != cudaSuccess) { hf_set_error(std::string("kernel launch: ") + cudaGetErrorString(e_)); return 1; } \
+  } while (0)
+
+#define HF_DISPATCH(nd, nf, ...)                                                      \
+  do {                                                                                \
+    if ((nd) == 3 && (nf) == 5) { constexpr int ND = 3, NF = 5; __VA_ARGS__; }         \
+    else if ((nd) == 2 && (nf) == 4) { constexpr int ND = 2, NF = 4; __VA_ARGS__; }    \
+    else if ((nd) == 2 && (nf) == 1) { constexpr int ND = 2, NF = 1; __VA_ARGS__; }    \
+    else if ((nd) == 3 && (nf) == 1) { constexpr int ND = 3, NF = 1; __VA_ARGS__; }    \
+    else HF_FAIL("unsupported (n_dims, n_fields) combination");                       \
+  } while (0)
+
+static inline unsigned hf_blocks(long long n, int bs) { return (unsigned)((n + bs - 1) / bs); }
+
+// ---------------------------------------------------------------------------------------------------------------------
+// kernels: small-operator products
+// ---------------------------------------------------------------------------------------------------------------------
+struct hf_ell3
+{
+  int n, rows, cols;
+  int nnz[3];
+  const double *val[3];
+  const int *col[3];
+};
+
+// out(row, c) = [out(row, c)] + sum_d sum_k E_d(row, k) * in_d(col_d(row,k), c): one running sum in ascending column
+// order, i.e. the order of the reference's column-by-column dgemm with beta = 0 / 1.
+template <bool ACC>
+__global__ void k_op_apply(hf_ell3 E, const double *__restrict__ in, size_t in_dim_stride, double *__restrict__ out, long long n_cols)
+{
+  long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (idx >= (long long)E.rows * n_cols) return;
+  int row = (int)(idx % E.rows);
+  long long cg = idx / E.rows;
+  double acc = ACC ? out[idx] : 0.0;
+  for (int d = 0; d < E.n; d++)
+  {
+    const double *src = in + d * in_dim_stride + cg * E.cols;
+    const double *val = E.val[d] + row;
+    const int *col = E.col[d] + row;
+    for (int k = 0; k < E.nnz[d]; k++) acc += val[(size_t)k * E.rows] * src[col[(size_t)k * E.rows]];
+  }
+  out[idx] = acc;
+}
+
+// y -= x  (the daxpy of calculate_corrected_divergence, reference src/eles.cpp:1746-1750)
+__global__ void k_sub(double *__restrict__ y, const double *__restrict__ x, long long n)
+{
+  long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (idx < n) y[idx] -= x[idx];
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// kernels: pointwise work at solution / flux points
+// ---------------------------------------------------------------------------------------------------------------------
+template <int ND, int NF, bool VISC>
+__global__ void k_point_flux(long long n_pts, const double *__restrict__ u, const double *__restrict__ grad, const double *__restrict__ JGinv,
+                             double *__restrict__ tdisf, hf_phys P)
+{
+  long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (p >= n_pts) return;
+  double uu[NF], f[NF * ND], J[ND * ND];
+#pragma unroll
+  for (int k = 0; k < NF; k++) uu[k] = u[p + k * n_pts];
+#pragma unroll
+  for (int q = 0; q < ND * ND; q++) J[q] = JGinv[p * (ND * ND) + q];
+  if (VISC)
+  {
+    double g[NF * ND];
+#pragma unroll
+    for (int q = 0; q < NF * ND; q++) g[q] = grad[p + q * n_pts];
+    vis_flux<ND, NF>(uu, g, f, P);
+  }
+  else
+    inv_flux<ND, NF>(uu, f, P);
+#pragma unroll
+  for (int k = 0; k < NF; k++)
+#pragma unroll
+    for (int l = 0; l < ND; l++)
+    {
+      double acc = VISC ? tdisf[p + (k + NF * l) * n_pts] : 0.0;
+#pragma unroll
+      for (int m = 0; m < ND; m++) acc += J[l + ND * m] * f[k + NF * m];
+      tdisf[p + (k + NF * l) * n_pts] = acc;
+    }
+}
+
+// reference-space gradient -> physical gradient: g(d,k) = sum_l (1/detJ * gt(l,k)) * JGinv(l,d)
+template <int ND, int NF>
+__global__ void k_transform_grad(long long n_pts, double *__restrict__ grad, const double *__restrict__ detjac, const double *__restrict__ JGinv)
+{
+  long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (p >= n_pts) return;
+  double J[ND * ND];
+#pragma unroll
+  for (int q = 0; q < ND * ND; q++) J[q] = JGinv[p * (ND * ND) + q];
+  double inv_detjac = 1.0 / detjac[p];
+#pragma unroll
+  for (int k = 0; k < NF; k++)
+  {
+    double gt[ND], g[ND];
+#pragma unroll
+    for (int l = 0; l < ND; l++) gt[l] = grad[p + (k + NF * l) * n_pts];
+#pragma unroll
+    for (int d = 0; d < ND; d++)
+    {
+      double acc = 0.0;
+#pragma unroll
+      for (int l = 0; l < ND; l++) acc += (inv_detjac * gt[l]) * J[l + ND * d];
+      g[d] = acc;
+    }
+#pragma unroll
+    for (int d = 0; d < ND; d++) grad[p + (k + NF * d) * n_pts] = g[d];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// kernels: interfaces (one thread per flux-point pair)
+// ---------------------------------------------------------------------------------------------------------------------
+template <int ND, int NF>
+__device__ __forceinline__ void load_fpt(const hf_ele_view &V, int idx, double *u)
+{
+  size_t s = (size_t)V.n_fpts * V.n_eles;
+#pragma unroll
+  for (int k = 0; k < NF; k++) u[k] = V.disu_fpts[idx + k * s];
+}
+template <int ND, int NF>
+__device__ __forceinline__ void load_grad_fpt(const hf_ele_view &V, int idx, double *g)
+{
+  size_t s = (size_t)V.n_fpts * V.n_eles;
+#pragma unroll
+  for (int q = 0; q < NF * ND; q++) g[q] = V.grad_disu_fpts[idx + q * s];
+}
+template <int ND>
+__device__ __forceinline__ void load_norm(const hf_ele_view &V, int idx, double *n)
+{
+  size_t s = (size_t)V.n_fpts * V.n_eles;
+#pragma unroll
+  for (int d = 0; d < ND; d++) n[d] = V.norm_fpts[idx + d * s];
+}
+
+template <int ND, int NF>
+__global__ void k_int_invflux(hf_views W, int n_pairs, int nf, const int *__restrict__ idx_l, const int *__restrict__ idx_r,
+                              const int8_t *__restrict__ type_l, const int8_t *__restrict__ type_r, hf_phys P, int viscous)
+{
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_pairs) return;
+  int i = t / nf;
+  const hf_ele_view &L = W.v[type_l[i]];
+  const hf_ele_view &R = W.v[type_r[i]];
+  int il = idx_l[t], ir = idx_r[t];
+  double u_l[NF], u_r[NF], n[ND], fn[NF];
+  load_fpt<ND, NF>(L, il, u_l);
+  load_fpt<ND, NF>(R, ir, u_r);
+  load_norm<ND>(L, il, n);
+  riemann<ND, NF>(u_l, u_r, n, fn, P);
+  double tdA_l = L.tdA_fpts[il], tdA_r = R.tdA_fpts[ir];
+  size_t sl = (size_t)L.n_fpts * L.n_eles, sr = (size_t)R.n_fpts * R.n_eles;
+#pragma unroll
+  for (int k = 0; k < NF; k++)
+  {
+    L.norm_tconf_fpts[il + k * sl] = fn[k] * tdA_l;
+    R.norm_tconf_fpts[ir + k * sr] = -fn[k] * tdA_r;
+  }
+  if (viscous)
+  {
+    double beta = ldg_switched_beta<ND>(P.ldg_beta, n);
+    double u_c[NF];
+    ldg_solution_int<NF>(u_l, u_r, u_c, beta);
+#pragma unroll
+    for (int k = 0; k < NF; k++)
+    {
+      L.delta_disu_fpts[il + k * sl] = (u_c[k] - u_l[k]);
+      R.delta_disu_fpts[ir + k * sr] = (u_c[k] - u_r[k]);
+    }
+  }
+}
+
+template <int ND, int NF>
+__global__ void k_int_viscflux(hf_views W, int n_pairs, int nf, const int *__restrict__ idx_l, const int *__restrict__ idx_r,
+                               const int8_t *__restrict__ type_l, const int8_t *__restrict__ type_r, hf_phys P)
+{
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_pairs) return;
+  int i = t / nf;
+  const hf_ele_view &L = W.v[type_l[i]];
+  const hf_ele_view &R = W.v[type_r[i]];
+  int il = idx_l[t], ir = idx_r[t];
+  double u_l[NF], u_r[NF], g[NF * ND], f_l[NF * ND], f_r[NF * ND], n[ND], fn[NF];
+  load_fpt<ND, NF>(L, il, u_l);
+  load_fpt<ND, NF>(R, ir, u_r);
+  load_grad_fpt<ND, NF>(L, il, g);
+  vis_flux<ND, NF>(u_l, g, f_l, P);
+  load_grad_fpt<ND, NF>(R, ir, g);
+  vis_flux<ND, NF>(u_r, g, f_r, P);
+  load_norm<ND>(L, il, n);
+  double beta = ldg_switched_beta<ND>(P.ldg_beta, n);
+  ldg_flux<ND, NF>(0, u_l, u_r, f_l, f_r, n, fn, beta, P.ldg_tau);
+  double tdA_l = L.tdA_fpts[il], tdA_r = R.tdA_fpts[ir];
+  size_t sl = (size_t)L.n_fpts * L.n_eles, sr = (size_t)R.n_fpts * R.n_eles;
+#pragma unroll
+  for (int k = 0; k < NF; k++)
+  {
+    L.norm_tconf_fpts[il + k * sl] += fn[k] * tdA_l;
+    R.norm_tconf_fpts[ir + k * sr] += -fn[k] * tdA_r;
+  }
+}
+
+template <int ND, int NF>
+__global__ void k_bdy_invflux(hf_views W, int n_pairs, int nf, const int *__restrict__ idx_l, const int8_t *__restrict__ type_l,
+                              const int *__restrict__ bc_id, const hf_bc *__restrict__ bcs, hf_phys P, double R_ref, int viscous)
+{
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_pairs) return;
+  int i = t / nf;
+  const hf_ele_view &L = W.v[type_l[i]];
+  int il = idx_l[t];
+  const hf_bc B = bcs[bc_id[i]];
+  double u_l[NF], u_r[NF], n[ND], fn[NF];
+  load_fpt<ND, NF>(L, il, u_l);
+  load_norm<ND>(L, il, n);
+#pragma unroll
+  for (int k = 0; k < NF; k++) u_r[k] = 0.;
+  set_boundary_conditions<ND, NF>(0, B, u_l, u_r, n, P.gamma, R_ref);
+  if (NF > 1 && B.bc_flag == HF_SLIP_WALL_DUAL)
+  {
+    double f_l[NF * ND];
+    inv_flux<ND, NF>(u_l, f_l, P);
+    normal_flux<ND, NF>(f_l, n, fn);
+  }
+  else
+    riemann<ND, NF>(u_l, u_r, n, fn, P);
+  double tdA_l = L.tdA_fpts[il];
+  size_t sl = (size_t)L.n_fpts * L.n_eles;
+#pragma unroll
+  for (int k = 0; k < NF; k++) L.norm_tconf_fpts[il + k * sl] = fn[k] * tdA_l;
+  if (viscous)
+  {
+    if (hf_is_wall(B.bc_flag)) set_boundary_conditions<ND, NF>(1, B, u_l, u_r, n, P.gamma, R_ref);
+#pragma unroll
+    for (int k = 0; k < NF; k++) L.delta_disu_fpts[il + k * sl] = (u_r[k] - u_l[k]);
+  }
+}
+
+template <int ND, int NF>
+__global__ void k_bdy_viscflux(hf_views W, int n_pairs, int nf, const int *__restrict__ idx_l, const int8_t *__restrict__ type_l,
+                               const int *__restrict__ bc_id, const hf_bc *__restrict__ bcs, hf_phys P, double R_ref)
+{
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_pairs) return;
+  int i = t / nf;
+  const hf_ele_view &L = W.v[type_l[i]];
+  int il = idx_l[t];
+  const hf_bc B = bcs[bc_id[i]];
+  if (B.bc_flag == HF_SLIP_WALL) return;
+  double u_l[NF], u_r[NF], g_l[NF * ND], g_r[NF * ND], f_r[NF * ND], n[ND], fn[NF];
+  load_fpt<ND, NF>(L, il, u_l);
+  load_norm<ND>(L, il, n);
+  load_grad_fpt<ND, NF>(L, il, g_l);
+#pragma unroll
+  for (int k = 0; k < NF; k++) u_r[k] = 0.;
+  set_boundary_conditions<ND, NF>(1, B, u_l, u_r, n, P.gamma, R_ref);
+  set_boundary_gradients<ND, NF>(B.bc_flag, u_r, g_l, g_r, n);
+  vis_flux<ND, NF>(u_r, g_r, f_r, P);
+  ldg_flux<ND, NF>(1, u_l, u_r, f_r, f_r, n, fn, 0.0, P.ldg_tau);
+  double tdA_l = L.tdA_fpts[il];
+  size_t sl = (size_t)L.n_fpts * L.n_eles;
+#pragma unroll
+  for (int k = 0; k < NF; k++) L.norm_tconf_fpts[il + k * sl] += fn[k] * tdA_l;
+}
+
+// partition ("mpi") faces: right state from the receive buffer, left side only is written
+// in_disu(j_rhs, field, inter), in_grad(j_rhs, field, dim, inter)     (reference src/mpi_inters.cpp:154-215)
+template <int ND, int NF>
+__global__ void k_mpi_invflux(hf_views W, int n_pairs, int nf, const int *__restrict__ idx_l, const int8_t *__restrict__ type_l,
+                              const int *__restrict__ lut, const double *__restrict__ in_disu, hf_phys P, int viscous)
+{
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_pairs) return;
+  int i = t / nf;
+  const hf_ele_view &L = W.v[type_l[i]];
+  int il = idx_l[t];
+  double u_l[NF], u_r[NF], n[ND], fn[NF];
+  load_fpt<ND, NF>(L, il, u_l);
+#pragma unroll
+  for (int k = 0; k < NF; k++) u_r[k] = in_disu[lut[t] + (size_t)nf * (k + NF * (size_t)i)];
+  load_norm<ND>(L, il, n);
+  riemann<ND, NF>(u_l, u_r, n, fn, P);
+  double tdA_l = L.tdA_fpts[il];
+  size_t sl = (size_t)L.n_fpts * L.n_eles;
+#pragma unroll
+  for (int k = 0; k < NF; k++) L.norm_tconf_fpts[il + k * sl] = fn[k] * tdA_l;
+  if (viscous)
+  {
+    double beta = ldg_switched_beta<ND>(P.ldg_beta, n);
+    double u_c[NF];
+    ldg_solution_int<NF>(u_l, u_r, u_c, beta);
+#pragma unroll
+    for (int k = 0; k < NF; k++) L.delta_disu_fpts[il + k * sl] = (u_c[k] - u_l[k]);
+  }
+}
+
+template <int ND, int NF>
+__global__ void k_mpi_viscflux(hf_views W, int n_pairs, int nf, const int *__restrict__ idx_l, const int8_t *__restrict__ type_l,
+                               const int *__restrict__ lut, const double *__restrict__ in_disu, const double *__restrict__ in_grad, hf_phys P)
+{
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_pairs) return;
+  int i = t / nf;
+  const hf_ele_view &L = W.v[type_l[i]];
+  int il = idx_l[t];
+  double u_l[NF], u_r[NF], g[NF * ND], f_l[NF * ND], f_r[NF * ND], n[ND], fn[NF];
+  load_fpt<ND, NF>(L, il, u_l);
+  load_grad_fpt<ND, NF>(L, il, g);
+  vis_flux<ND, NF>(u_l, g, f_l, P);
+#pragma unroll
+  for (int k = 0; k < NF; k++) u_r[k] = in_disu[lut[t] + (size_t)nf * (k + NF * (size_t)i)];
+#pragma unroll
+  for (int d = 0; d < ND; d++)
+#pragma unroll
+    for (int k = 0; k < NF; k++) g[k + NF * d] = in_grad[lut[t] + (size_t)nf * (k + NF * (d + ND * (size_t)i))];
+  vis_flux<ND, NF>(u_r, g, f_r, P);
+  load_norm<ND>(L, il, n);
+  double beta = ldg_switched_beta<ND>(P.ldg_beta, n);
+  ldg_flux<ND, NF>(0, u_l, u_r, f_l, f_r, n, fn, beta, P.ldg_tau);
+  double tdA_l = L.tdA_fpts[il];
+  size_t sl = (size_t)L.n_fpts * L.n_eles;
+#pragma unroll
+  for (int k = 0; k < NF; k++) L.norm_tconf_fpts[il + k * sl] += fn[k] * tdA_l;
+}
+
+// out_disu[inter][field][fpt], out_grad[inter][dim][field][fpt]  (reference src/mpi_inters.cpp:226-229, 285-289)
+__global__ void k_pack_disu(hf_views W, int n_pairs, int nf, int NF, const int *__restrict__ idx_l, const int8_t *__restrict__ type_l, double *__restrict__ out)
+{
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_pairs) return;
+  int i = t / nf, j = t - i * nf;
+  const hf_ele_view &L = W.v[type_l[i]];
+  size_t sl = (size_t)L.n_fpts * L.n_eles;
+  for (int k = 0; k < NF; k++) out[j + (size_t)nf * (k + NF * (size_t)i)] = L.disu_fpts[idx_l[t] + k * sl];
+}
+__global__ void k_pack_grad(hf_views W, int n_pairs, int nf, int NF, int ND, const int *__restrict__ idx_l, const int8_t *__restrict__ type_l, double *__restrict__ out)
+{
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_pairs) return;
+  int i = t / nf, j = t - i * nf;
+  const hf_ele_view &L = W.v[type_l[i]];
+  size_t sl = (size_t)L.n_fpts * L.n_eles;
+  for (int d = 0; d < ND; d++)
+    for (int k = 0; k < NF; k++) out[j + (size_t)nf * (k + NF * (d + ND * (size_t)i))] = L.grad_disu_fpts[idx_l[t] + (k + NF * d) * sl];
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// kernels: time integration, norms, time step
+// ---------------------------------------------------------------------------------------------------------------------
+// mode 0: u -= c0 * (div/detjac)                      (forward Euler, RK24 stages 0-2, RK34 stages 0,1,3)
+// mode 1: u = c1*u + c2*u1 + c0*(-div/detjac)         (RK24 last stage, RK34 stage 2)
+// mode 2: r = a*r + dt*(-div/detjac); u += b*r        (RK45 / RK414), c1 = a, c2 = b
+__global__ void k_rk_update(long long n, long long n_pts, int n_upts, double *__restrict__ u0, double *__restrict__ u1, const double *__restrict__ div,
+                            const double *__restrict__ detjac, const double *__restrict__ dt_local, double dt, double fac, double c1, double c2,
+                            int mode, int copy_u1)
+{
+  long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (idx >= n) return;
+  long long p = idx % n_pts;
+  double dtl = dt_local ? dt_local[p / n_upts] : dt;
+  double u = u0[idx];
+  if (copy_u1) u1[idx] = u;
+  double r = div[idx] / detjac[p];
+  if (mode == 0)
+    u -= dtl / fac * (r - 0.0);
+  else if (mode == 1)
+  {
+    double rhs = -r + 0.0;
+    double uo = copy_u1 ? u : u1[idx];
+    u = c1 * u + c2 * uo + dtl / fac * rhs;
+  }
+  else
+  {
+    double rhs = -r + 0.0;
+    double d = c1 * u1[idx] + dtl * rhs;
+    u1[idx] = d;
+    u += c2 * d;
+  }
+  u0[idx] = u;
+}
+
+// per-block partial norms of div/detjac for one field; partial[block]
+template <int NORM>
+__global__ void k_res_norm(long long n_pts, const double *__restrict__ div, const double *__restrict__ detjac, double *__restrict__ partial)
+{
+  __shared__ double sh[256];
+  double acc = 0.;
+  for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < n_pts; p += (long long)gridDim.x * blockDim.x)
+  {
+    double r = div[p] / detjac[p] - 0.0;
+    if (NORM == 0) acc = fmax(acc, fabs(r));
+    else if (NORM == 1) acc += fabs(r);
+    else acc += r * r;
+  }
+  sh[threadIdx.x] = acc;
+  __syncthreads();
+  for (int s = blockDim.x / 2; s > 0; s >>= 1)
+  {
+    if (threadIdx.x < s) sh[threadIdx.x] = (NORM == 0) ? fmax(sh[threadIdx.x], sh[threadIdx.x + s]) : sh[threadIdx.x] + sh[threadIdx.x + s];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) partial[blockIdx.x] = sh[0];
+}
+
+// eles::calc_dt_local (reference src/eles.cpp:1267-1356): one thread per element
+template <int ND>
+__global__ void k_dt_local(int n_eles, int n_upts, const double *__restrict__ u, const double *__restrict__ h_ref, double *__restrict__ dt_out, hf_phys P,
+                           double CFL, int order, int viscous)
+{
+  int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n_eles) return;
+  size_t s = (size_t)n_upts * n_eles;
+  double lam_inv = 0, lam_visc = 0;
+  for (int i = 0; i < n_upts; i++)
+  {
+    size_t p = i + (size_t)n_upts * e;
+    double rho = u[p];
+    double vsq = 0.;
+#pragma unroll
+    for (int d = 0; d < ND; d++)
+    {
+      double v = u[p + (d + 1) * s] / rho;
+      vsq += v * v;
+    }
+    double pr = (P.gamma - 1.0) * (u[p + (ND + 1) * s] - 0.5 * rho * vsq);
+    double c = sqrt(P.gamma * pr / rho);
+    double inte = pr / ((P.gamma - 1.0) * rho);
+    double rt_ratio = (P.gamma - 1.0) * inte / (P.rt_inf);
+    double mu = (P.mu_inf) * pow(rt_ratio, 1.5) * (1. + (P.c_sth)) / (rt_ratio + (P.c_sth));
+    mu = mu + P.fix_vis * (P.mu_inf - mu);
+    double li = sqrt(vsq) + c;
+    double lv = fmax(4.0 / 3.0, P.gamma / P.prandtl) * mu / rho;
+    if (lam_inv < li) lam_inv = li;
+    if (lam_visc < lv) lam_visc = lv;
+  }
+  double h = h_ref[e];
+  double dt_inv = CFL * h / lam_inv * 1.0 / (2.0 * order + 1.0);
+  double dt_visc = viscous ? (CFL * 0.25 * h * h) / (lam_visc) * 1.0 / (2.0 * order + 1.0) : 1e16;
+  dt_out[e] = fmin(dt_visc, dt_inv);
+}
+
+__global__ void k_min_reduce(int n, const double *__restrict__ x, double *__restrict__ partial)
+{
+  __shared__ double sh[256];
+  double acc = 1e300;
+  for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < n; p += gridDim.x * blockDim.x) acc = fmin(acc, x[p]);
+  sh[threadIdx.x] = acc;
+  __syncthreads();
+  for (int s = blockDim.x / 2; s > 0; s >>= 1)
+  {
+    if (threadIdx.x < s) sh[threadIdx.x] = fmin(sh[threadIdx.x], sh[threadIdx.x + s]);
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) partial[blockIdx.x] = sh[0];
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------------------------
+void hf_ktimer_begin(hf_ctx *c)
+{
+  if (!c->ktimer_on) return;
+  if (c->kt_used + 2 > c->kt_ev.size())
+  {
+    cudaEvent_t a, b;
+    cudaEventCreate(&a);
+    cudaEventCreate(&b);
+    c->kt_ev.push_back(a);
+    c->kt_ev.push_back(b);
+  }
+  cudaEventRecord(c->kt_ev[c->kt_used], c->stream);
+}
+void hf_ktimer_end(hf_ctx *c)
+{
+  if (!c->ktimer_on) return;
+  cudaEventRecord(c->kt_ev[c->kt_used + 1], c->stream);
+  c->kt_used += 2;
+}
+
+hf_views hf_make_views(hf_ctx *c)
+{
+  hf_views W;
+  memset(&W, 0, sizeof(W));
+  for (int t = 0; t < HF_N_ELE_TYPES; t++)
+  {
+    hf_eles_dev &e = c->eles[t];
+    if (!e.present) continue;
+    hf_ele_view &v = W.v[t];
+    v.n_eles = e.n_eles; v.n_upts = e.n_upts; v.n_fpts = e.n_fpts; v.n_dims = e.n_dims; v.n_fields = e.n_fields;
+    v.disu_fpts = e.disu_fpts;
+    v.norm_tconf_fpts = e.norm_tconf_fpts;
+    v.delta_disu_fpts = e.delta_disu_fpts;
+    v.grad_disu_fpts = e.grad_disu_fpts;
+    v.tdA_fpts = e.tdA_fpts;
+    v.norm_fpts = e.norm_fpts;
+  }
+  return W;
+}
+
+static int build_ell(hf_ctx *c, hf_ell &E, const double *dense, int rows, int cols)
+{
+  int nnz = 1;
+  for (int r = 0; r < rows; r++)
+  {
+    int cnt = 0;
+    for (int k = 0; k < cols; k++) if (dense[r + (size_t)rows * k] != 0.0) cnt++;
+    nnz = std::max(nnz, cnt);
+  }
+  std::vector<double> val((size_t)nnz * rows, 0.0);
+  std::vector<int> col((size_t)nnz * rows, 0);
+  for (int r = 0; r < rows; r++)
+  {
+    int cnt = 0, last = 0;
+    for (int k = 0; k < cols; k++)
+      if (dense[r + (size_t)rows * k] != 0.0)
+      {
+        val[(size_t)cnt * rows + r] = dense[r + (size_t)rows * k];
+        col[(size_t)cnt * rows + r] = k;
+        last = k;
+        cnt++;
+      }
+    for (; cnt < nnz; cnt++) col[(size_t)cnt * rows + r] = last;
+  }
+  E.rows = rows; E.cols = cols; E.nnz = nnz;
+  if (hf_alloc_copy(c, &E.val, val.data(), val.size())) return 1;
+  if (hf_alloc_copy(c, &E.col, col.data(), col.size())) return 1;
+  return 0;
+}
+
+extern "C" {
+
+const char *hf_dev_last_error(void) { return g_err.c_str(); }
+
+int hf_dev_create(hf_ctx **out, int device, int rank, int nproc)
+{
+  int n_dev = 0;
+  cudaError_t e = cudaGetDeviceCount(&n_dev);
+  if (e != cudaSuccess || n_dev == 0)
+    HF_FAIL(std::string("no CUDA device available: the HiFiLES B200 hot path has no CPU fallback (") + cudaGetErrorString(e) + ")");
+  if (device < 0)
+  {
+    const char *lr = getenv("LOCAL_RANK");
+    device = lr ? atoi(lr) % n_dev : rank % n_dev;
+  }
+  HF_CUDA(cudaSetDevice(device));
+  hf_ctx *c = new hf_ctx();
+  c->device = device; c->rank = rank; c->nproc = nproc;
+  HF_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  HF_CUDA(cudaStreamCreateWithFlags(&c->comm_stream, cudaStreamNonBlocking));
+  c->own_stream = true;
+  HF_CUDA(cudaEventCreateWithFlags(&c->ev_a, cudaEventDisableTiming));
+  HF_CUDA(cudaEventCreateWithFlags(&c->ev_b, cudaEventDisableTiming));
+  HF_CUDA(cudaEventCreate(&c->ev_t0));
+  HF_CUDA(cudaEventCreate(&c->ev_t1));
+  c->scratch_bytes = 1 << 20;
+  if (hf_alloc_zero(c, &c->scratch, c->scratch_bytes / sizeof(double))) return 1;
+  memset(&c->prm, 0, sizeof(c->prm));
+  *out = c;
+  return 0;
+}
+
+int hf_dev_destroy(hf_ctx *c)
+{
+  if (!c) return 0;
+  cudaSetDevice(c->device);
+  cudaDeviceSynchronize();
+  hf_halo_destroy(c);
+  for (void *p : c->allocs) cudaFree(p);
+  for (cudaEvent_t ev : c->kt_ev) cudaEventDestroy(ev);
+  if (c->ev_a) cudaEventDestroy(c->ev_a);
+  if (c->ev_b) cudaEventDestroy(c->ev_b);
+  if (c->ev_t0) cudaEventDestroy(c->ev_t0);
+  if (c->ev_t1) cudaEventDestroy(c->ev_t1);
+  if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+  if (c->comm_stream) cudaStreamDestroy(c->comm_stream);
+  delete c;
+  return 0;
+}
+
+int hf_dev_set_stream(hf_ctx *c, void *cuda_stream)
+{
+  if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+  c->stream = (cudaStream_t)cuda_stream;
+  c->own_stream = false;
+  return 0;
+}
+
+int hf_dev_set_params(hf_ctx *c, const hf_params *p)
+{
+  c->prm = *p;
+  hf_phys &P = c->phys;
+  P.gamma = p->gamma; P.prandtl = p->prandtl; P.mu_inf = p->mu_inf; P.rt_inf = p->rt_inf; P.c_sth = p->c_sth;
+  P.fix_vis = (double)p->fix_vis;
+  P.ldg_beta = p->ldg_beta; P.ldg_tau = p->ldg_tau;
+  for (int i = 0; i < 3; i++) P.wave_speed[i] = p->wave_speed[i];
+  P.diff_coeff = p->diff_coeff; P.lambda = p->lambda;
+  P.riemann_solve_type = p->riemann_solve_type;
+  if (p->equation == 0 && !(p->riemann_solve_type == 0 || p->riemann_solve_type == 2 || p->riemann_solve_type == 3))
+    HF_FAIL("Riemann solver not implemented");
+  if (p->viscous && p->vis_riemann_solve_type != 0) HF_FAIL("Viscous Riemann solver not implemented");
+  c->have_params = true;
+  return 0;
+}
+
+int hf_dev_upload_eles(hf_ctx *c, const hf_eles_desc *d)
+{
+  if (!c->have_params) HF_FAIL("hf_dev_set_params must be called before hf_dev_upload_eles");
+  if (d->ele_type < 0 || d->ele_type >= HF_N_ELE_TYPES) HF_FAIL("bad element type");
+  HF_CUDA(cudaSetDevice(c->device));
+  hf_eles_dev &e = c->eles[d->ele_type];
+  if (e.present) HF_FAIL("element type uploaded twice");
+  e.present = true;
+  e.ele_type = d->ele_type; e.n_eles = d->n_eles; e.n_upts = d->n_upts_per_ele; e.n_fpts = d->n_fpts_per_ele;
+  e.n_dims = d->n_dims; e.n_fields = d->n_fields; e.order = d->order; e.n_inters = d->n_inters_per_ele;
+  if (e.n_inters > 6) HF_FAIL("too many faces per element");
+  e.fpt_offset[0] = 0;
+  for (int f = 0; f < e.n_inters; f++)
+  {
+    e.n_fpts_per_inter[f] = d->n_fpts_per_inter[f];
+    e.fpt_offset[f + 1] = e.fpt_offset[f] + d->n_fpts_per_inter[f];
+  }
+  const int nu = e.n_upts, nf = e.n_fpts, nd = e.n_dims;
+  const size_t NU = (size_t)nu * e.n_eles, NFP = (size_t)nf * e.n_eles, F = e.n_fields;
+  const bool visc = c->prm.viscous != 0;
+  auto keep = [&](int slot, const double *src, size_t n) { if (src) e.h_op[slot].assign(src, src + n); };
+  if (build_ell(c, e.opp_0, d->opp_0, nf, nu)) return 1;
+  keep(0, d->opp_0, (size_t)nf * nu);
+  if (build_ell(c, e.opp_3, d->opp_3, nu, nf)) return 1;
+  keep(3, d->opp_3, (size_t)nu * nf);
+  for (int i = 0; i < nd; i++)
+  {
+    if (build_ell(c, e.opp_1[i], d->opp_1[i], nf, nu)) return 1;
+    if (build_ell(c, e.opp_2[i], d->opp_2[i], nu, nu)) return 1;
+    keep(4 + i, d->opp_2[i], (size_t)nu * nu);
+    keep(7 + i, d->opp_1[i], (size_t)nf * nu);
+    if (visc)
+    {
+      if (!d->opp_4[i] || !d->opp_5[i] || !d->opp_6) HF_FAIL("viscous run needs opp_4, opp_5, opp_6");
+      if (build_ell(c, e.opp_4[i], d->opp_4[i], nu, nu)) return 1;
+      if (build_ell(c, e.opp_5[i], d->opp_5[i], nu, nf)) return 1;
+      keep(10 + i, d->opp_5[i], (size_t)nu * nf);
+    }
+  }
+  if (visc && build_ell(c, e.opp_6, d->opp_6, nf, nu)) return 1;
+  if (hf_alloc_copy(c, &e.detjac_upts, d->detjac_upts, NU)) return 1;
+  if (hf_alloc_copy(c, &e.JGinv_upts, d->JGinv_upts, NU * nd * nd)) return 1;
+  if (hf_alloc_copy(c, &e.detjac_fpts, d->detjac_fpts, NFP)) return 1;
+  if (hf_alloc_copy(c, &e.JGinv_fpts, d->JGinv_fpts, NFP * nd * nd)) return 1;
+  if (hf_alloc_copy(c, &e.tdA_fpts, d->tdA_fpts, NFP)) return 1;
+  if (hf_alloc_copy(c, &e.norm_fpts, d->norm_fpts, NFP * nd)) return 1;
+  if (d->h_ref && hf_alloc_copy(c, &e.h_ref, d->h_ref, (size_t)e.n_eles)) return 1;
+  if (c->prm.dt_type != 0 && hf_alloc_zero(c, &e.dt_local, (size_t)e.n_eles)) return 1;
+  if (d->disu_upts0) { if (hf_alloc_copy(c, &e.disu_upts[0], d->disu_upts0, NU * F)) return 1; }
+  else if (hf_alloc_zero(c, &e.disu_upts[0], NU * F)) return 1;
+  if (c->prm.adv_type != 0 && hf_alloc_zero(c, &e.disu_upts[1], NU * F)) return 1;
+  if (hf_alloc_zero(c, &e.div_tconf_upts, NU * F)) return 1;
+  if (hf_alloc_zero(c, &e.disu_fpts, NFP * F)) return 1;
+  if (hf_alloc_zero(c, &e.norm_tconf_fpts, NFP * F)) return 1;
+  if (visc)
+  {
+    if (hf_alloc_zero(c, &e.delta_disu_fpts, NFP * F)) return 1;
+    if (hf_alloc_zero(c, &e.grad_disu_fpts, NFP * F * nd)) return 1;
+  }
+  // tdisf_upts, norm_tdisf_fpts, grad_disu_upts are only needed by the staged path: allocated lazily
+  return 0;
+}
+
+static int ensure_staged_buffers(hf_ctx *c, hf_eles_dev &e)
+{
+  const size_t NU = (size_t)e.n_upts * e.n_eles, NFP = (size_t)e.n_fpts * e.n_eles, F = e.n_fields;
+  if (!e.tdisf_upts && hf_alloc_zero(c, &e.tdisf_upts, NU * F * e.n_dims)) return 1;
+  if (!e.norm_tdisf_fpts && hf_alloc_zero(c, &e.norm_tdisf_fpts, NFP * F)) return 1;
+  if (c->prm.viscous && !e.grad_disu_upts && hf_alloc_zero(c, &e.grad_disu_upts, NU * F * e.n_dims)) return 1;
+  return 0;
+}
+
+// flat flux-point index (fpt + n_fpts*ele) of face-local point j on local face `loc` of element `ele`
+static inline int flat_fpt(const hf_eles_dev &e, int ele, int loc, int j) { return e.fpt_offset[loc] + j + e.n_fpts * ele; }
+
+// right-side permutation (reference src/inters.cpp:153-262)
+static int fill_lut(int inter_type, int order, int nfp, int rot, std::vector<int> &lut)
+{
+  int n = order + 1;
+  lut.assign(nfp, 0);
+  if (inter_type == 0)
+    for (int i = 0; i < nfp; i++) lut[i] = nfp - i - 1;
+  else if (inter_type == 1)
+  {
+    for (int j = 0; j < n; j++)
+      for (int i = 0; i < n - j; i++)
+      {
+        int i0 = j * n - (j - 1) * j / 2 + i, i1;
+        if (rot == 0) i1 = i * n - (i - 1) * i / 2 + j;
+        else if (rot == 1) i1 = n * (order + 2) / 2 - 1 - (i + j) * (i + j + 1) / 2 - j;
+        else if (rot == 2) i1 = j * n - (j - 1) * j / 2 + (order - j - i);
+        else HF_FAIL("ERROR: Unknown rotation of triangular face...");
+        lut[i0] = i1;
+      }
+  }
+  else
+  {
+    for (int i = 0; i < n; i++)
+      for (int j = 0; j < n; j++)
+      {
+        int v;
+        if (rot == 0) v = (n - 1 - j) + n * i;
+        else if (rot == 1) v = nfp - (n - 1 - j) - n * i - 1;
+        else if (rot == 2) v = n * j + i;
+        else if (rot == 3) v = nfp - n * j - i - 1;
+        else HF_FAIL("ERROR: Unknown rotation tag ... ");
+        lut[i * n + j] = v;
+      }
+  }
+  return 0;
+}
+
+int hf_dev_upload_int_inters(hf_ctx *c, const hf_int_inters_desc *d)
+{
+  HF_CUDA(cudaSetDevice(c->device));
+  hf_int_inters_dev &I = c->ints[d->inter_type];
+  I.n_inters = d->n_inters; I.nf = d->n_fpts_per_inter;
+  const int nf = I.nf, ni = I.n_inters;
+  std::vector<int> il((size_t)nf * ni), ir((size_t)nf * ni), lut;
+  std::vector<int8_t> tl(ni), tr(ni);
+  for (int i = 0; i < ni; i++)
+  {
+    const hf_eles_dev &L = c->eles[d->ele_type_l[i]], &R = c->eles[d->ele_type_r[i]];
+    if (!L.present || !R.present) HF_FAIL("interface refers to an element type that was not uploaded");
+    if (fill_lut(d->inter_type, c->prm.order, nf, d->rot_tag[i], lut)) return 1;
+    tl[i] = (int8_t)d->ele_type_l[i]; tr[i] = (int8_t)d->ele_type_r[i];
+    for (int j = 0; j < nf; j++)
+    {
+      il[j + (size_t)nf * i] = flat_fpt(L, d->ele_l[i], d->local_inter_l[i], j);
+      ir[j + (size_t)nf * i] = flat_fpt(R, d->ele_r[i], d->local_inter_r[i], lut[j]);
+    }
+  }
+  if (hf_alloc_copy(c, &I.idx_l, il.data(), il.size())) return 1;
+  if (hf_alloc_copy(c, &I.idx_r, ir.data(), ir.size())) return 1;
+  if (hf_alloc_copy(c, &I.type_l, tl.data(), tl.size())) return 1;
+  if (hf_alloc_copy(c, &I.type_r, tr.data(), tr.size())) return 1;
+  I.h_ele_type_l.assign(d->ele_type_l, d->ele_type_l + ni); I.h_ele_l.assign(d->ele_l, d->ele_l + ni);
+  I.h_loc_l.assign(d->local_inter_l, d->local_inter_l + ni);
+  I.h_ele_type_r.assign(d->ele_type_r, d->ele_type_r + ni); I.h_ele_r.assign(d->ele_r, d->ele_r + ni);
+  I.h_loc_r.assign(d->local_inter_r, d->local_inter_r + ni);
+  I.h_rot.assign(d->rot_tag, d->rot_tag + ni);
+  return 0;
+}
+
+int hf_dev_set_bc_table(hf_ctx *c, int n_bc, const hf_bc *table)
+{
+  HF_CUDA(cudaSetDevice(c->device));
+  c->n_bc = n_bc;
+  if (n_bc > 0 && hf_alloc_copy(c, &c->bc_table, table, (size_t)n_bc)) return 1;
+  c->h_bc.assign(table, table + n_bc);
+  return 0;
+}
+
+int hf_dev_upload_bdy_inters(hf_ctx *c, const hf_bdy_inters_desc *d)
+{
+  HF_CUDA(cudaSetDevice(c->device));
+  hf_bdy_inters_dev &I = c->bdys[d->inter_type];
+  I.n_inters = d->n_inters; I.nf = d->n_fpts_per_inter;
+  const int nf = I.nf, ni = I.n_inters;
+  std::vector<int> il((size_t)nf * ni);
+  std::vector<int8_t> tl(ni);
+  for (int i = 0; i < ni; i++)
+  {
+    const hf_eles_dev &L = c->eles[d->ele_type_l[i]];
+    if (!L.present) HF_FAIL("interface refers to an element type that was not uploaded");
+    if (d->bc_id[i] < 0 || d->bc_id[i] >= c->n_bc) HF_FAIL("boundary interface refers to an unknown bc id");
+    tl[i] = (int8_t)d->ele_type_l[i];
+    for (int j = 0; j < nf; j++) il[j + (size_t)nf * i] = flat_fpt(L, d->ele_l[i], d->local_inter_l[i], j);
+  }
+  if (hf_alloc_copy(c, &I.idx_l, il.data(), il.size())) return 1;
+  if (hf_alloc_copy(c, &I.type_l, tl.data(), tl.size())) return 1;
+  if (hf_alloc_copy(c, &I.bc_id, d->bc_id, (size_t)ni)) return 1;
+  I.h_ele_type_l.assign(d->ele_type_l, d->ele_type_l + ni); I.h_ele_l.assign(d->ele_l, d->ele_l + ni);
+  I.h_loc_l.assign(d->local_inter_l, d->local_inter_l + ni);
+  I.h_bc_id.assign(d->bc_id, d->bc_id + ni);
+  return 0;
+}
+
+int hf_dev_upload_mpi_inters(hf_ctx *c, const hf_mpi_inters_desc *d)
+{
+  HF_CUDA(cudaSetDevice(c->device));
+  hf_mpi_inters_dev &I = c->mpis[d->inter_type];
+  I.n_inters = d->n_inters; I.nf = d->n_fpts_per_inter;
+  const int nf = I.nf, ni = I.n_inters;
+  std::vector<int> il((size_t)nf * ni), lt((size_t)nf * ni), lut;
+  std::vector<int8_t> tl(ni);
+  int nfields = c->prm.n_fields, nd = c->prm.n_dims;
+  for (int i = 0; i < ni; i++)
+  {
+    const hf_eles_dev &L = c->eles[d->ele_type_l[i]];
+    if (!L.present) HF_FAIL("interface refers to an element type that was not uploaded");
+    if (fill_lut(d->inter_type, c->prm.order, nf, d->rot_tag[i], lut)) return 1;
+    tl[i] = (int8_t)d->ele_type_l[i];
+    for (int j = 0; j < nf; j++)
+    {
+      il[j + (size_t)nf * i] = flat_fpt(L, d->ele_l[i], d->local_inter_l[i], j);
+      lt[j + (size_t)nf * i] = lut[j];
+    }
+  }
+  if (hf_alloc_copy(c, &I.idx_l, il.data(), il.size())) return 1;
+  if (hf_alloc_copy(c, &I.lut, lt.data(), lt.size())) return 1;
+  if (hf_alloc_copy(c, &I.type_l, tl.data(), tl.size())) return 1;
+  I.nb_rank.assign(d->neighbour_rank, d->neighbour_rank + d->n_neighbours);
+  I.nb_count.assign(d->neighbour_count, d->neighbour_count + d->n_neighbours);
+  size_t nb = (size_t)ni * nf * nfields;
+  if (hf_alloc_zero(c, &I.out_disu, nb)) return 1;
+  if (hf_alloc_zero(c, &I.in_disu, nb)) return 1;
+  if (c->prm.viscous)
+  {
+    if (hf_alloc_zero(c, &I.out_grad, nb * nd)) return 1;
+    if (hf_alloc_zero(c, &I.in_grad, nb * nd)) return 1;
+  }
+  I.h_ele_type_l.assign(d->ele_type_l, d->ele_type_l + ni); I.h_ele_l.assign(d->ele_l, d->ele_l + ni);
+  I.h_loc_l.assign(d->local_inter_l, d->local_inter_l + ni);
+  I.h_rot.assign(d->rot_tag, d->rot_tag + ni);
+  return 0;
+}
+
+int hf_dev_finalize_setup(hf_ctx *c)
+{
+  HF_CUDA(cudaSetDevice(c->device));
+  if (c->fused && hf_fused_prepare(c)) return 1;
+  c->finalized = true;
+  HF_CUDA(cudaDeviceSynchronize());
+  return 0;
+}
+
+int hf_dev_set_mode(hf_ctx *c, int fused)
+{
+  c->fused = fused;
+  return 0;
+}
+
+// ---- the staged element methods ----------------------------------------------------------------------------------------
+static hf_ell3 ell1(const hf_ell &E)
+{
+  hf_ell3 r;
+  memset(&r, 0, sizeof(r));
+  r.n = 1; r.rows = E.rows; r.cols = E.cols; r.nnz[0] = E.nnz; r.val[0] = E.val; r.col[0] = E.col;
+  return r;
+}
+static hf_ell3 elln(const hf_ell *E, int n)
+{
+  hf_ell3 r;
+  memset(&r, 0, sizeof(r));
+  r.n = n; r.rows = E[0].rows; r.cols = E[0].cols;
+  for (int d = 0; d < n; d++) { r.nnz[d] = E[d].nnz; r.val[d] = E[d].val; r.col[d] = E[d].col; }
+  return r;
+}
+
+static int op_apply(hf_ctx *c, const hf_ell3 &E, const double *in, size_t in_dim_stride, double *out, long long n_cols, bool acc)
+{
+  long long n = (long long)E.rows * n_cols;
+  if (acc) k_op_apply<true><<<hf_blocks(n, 256), 256, 0, c->stream>>>(E, in, in_dim_stride, out, n_cols);
+  else k_op_apply<false><<<hf_blocks(n, 256), 256, 0, c->stream>>>(E, in, in_dim_stride, out, n_cols);
+  HF_LAUNCH_CHECK(c);
+  return 0;
+}
+
+int hf_dev_eles_op(hf_ctx *c, int ele_type, int op)
+{
+  if (!c->finalized) HF_FAIL("hf_dev_finalize_setup has not been called");
+  hf_eles_dev &e = c->eles[ele_type];
+  if (!e.present) return 0;
+  HF_CUDA(cudaSetDevice(c->device));
+  if (ensure_staged_buffers(c, e)) return 1;
+  const int nd = e.n_dims, nfl = e.n_fields;
+  const long long ncols = (long long)e.n_eles * nfl;
+  const size_t NU = (size_t)e.n_upts * e.n_eles, NFP = (size_t)e.n_fpts * e.n_eles;
+  const bool visc = c->prm.viscous != 0;
+  switch (op)
+  {
+  case HF_EXTRAPOLATE_SOLUTION:
+    return op_apply(c, ell1(e.opp_0), e.disu_upts[0], 0, e.disu_fpts, ncols, false);
+  case HF_CALCULATE_GRADIENT:
+    if (!visc) HF_FAIL("calculate_gradient called on an inviscid run");
+    for (int d = 0; d < nd; d++)
+      if (op_apply(c, ell1(e.opp_4[d]), e.disu_upts[0], 0, e.grad_disu_upts + d * NU * nfl, ncols, false)) return 1;
+    return 0;
+  case HF_EVALUATE_INVFLUX:
+    HF_DISPATCH(nd, nfl, (k_point_flux<ND, NF, false><<<hf_blocks(NU, 128), 128, 0, c->stream>>>((long long)NU, e.disu_upts[0], nullptr, e.JGinv_upts, e.tdisf_upts, c->phys)));
+    HF_LAUNCH_CHECK(c);
+    return 0;
+  case HF_CORRECT_GRADIENT:
+    if (!visc) HF_FAIL("correct_gradient called on an inviscid run");
+    for (int d = 0; d < nd; d++)
+      if (op_apply(c, ell1(e.opp_5[d]), e.delta_disu_fpts, 0, e.grad_disu_upts + d * NU * nfl, ncols, true)) return 1;
+    for (int d = 0; d < nd; d++)
+      if (op_apply(c, ell1(e.opp_6), e.grad_disu_upts + d * NU * nfl, 0, e.grad_disu_fpts + d * NFP * nfl, ncols, false)) return 1;
+    HF_DISPATCH(nd, nfl, (k_transform_grad<ND, NF><<<hf_blocks(NU, 128), 128, 0, c->stream>>>((long long)NU, e.grad_disu_upts, e.detjac_upts, e.JGinv_upts)));
+    HF_LAUNCH_CHECK(c);
+    HF_DISPATCH(nd, nfl, (k_transform_grad<ND, NF><<<hf_blocks(NFP, 128), 128, 0, c->stream>>>((long long)NFP, e.grad_disu_fpts, e.detjac_fpts, e.JGinv_fpts)));
+    HF_LAUNCH_CHECK(c);
+    return 0;
+  case HF_EVALUATE_VISCFLUX:
+    if (!visc) HF_FAIL("evaluate_viscFlux called on an inviscid run");
+    HF_DISPATCH(nd, nfl, (k_point_flux<ND, NF, true><<<hf_blocks(NU, 128), 128, 0, c->stream>>>((long long)NU, e.disu_upts[0], e.grad_disu_upts, e.JGinv_upts, e.tdisf_upts, c->phys)));
+    HF_LAUNCH_CHECK(c);
+    return 0;
+  case HF_EXTRAPOLATE_TOTALFLUX:
+    return op_apply(c, elln(e.opp_1, nd), e.tdisf_upts, NU * nfl, e.norm_tdisf_fpts, ncols, false);
+  case HF_CALCULATE_DIVERGENCE:
+    return op_apply(c, elln(e.opp_2, nd), e.tdisf_upts, NU * nfl, e.div_tconf_upts, ncols, false);
+  case HF_CALCULATE_CORRECTED_DIVERGENCE:
+  {
+    long long n = (long long)NFP * nfl;
+    k_sub<<<hf_blocks(n, 256), 256, 0, c->stream>>>(e.norm_tconf_fpts, e.norm_tdisf_fpts, n);
+    HF_LAUNCH_CHECK(c);
+    c->ufpts_valid = false;
+    return op_apply(c, ell1(e.opp_3), e.norm_tconf_fpts, 0, e.div_tconf_upts, ncols, true);
+  }
+  default:
+    HF_FAIL("unknown element operation");
+  }
+}
+
+int hf_dev_int_inters_op(hf_ctx *c, int inter_type, int op)
+{
+  if (!c->finalized) HF_FAIL("hf_dev_finalize_setup has not been called");
+  hf_int_inters_dev &I = c->ints[inter_type];
+  if (I.n_inters == 0) return 0;
+  HF_CUDA(cudaSetDevice(c->device));
+  hf_views W = hf_make_views(c);
+  int n = I.n_inters * I.nf;
+  const int nd = c->prm.n_dims, nfl = c->prm.n_fields;
+  if (op == HF_COMMON_INVFLUX)
+    HF_DISPATCH(nd, nfl, (k_int_invflux<ND, NF><<<hf_blocks(n, 128), 128, 0, c->stream>>>(W, n, I.nf, I.idx_l, I.idx_r, I.type_l, I.type_r, c->phys, c->prm.viscous)));
+  else if (op == HF_COMMON_VISCFLUX)
+    HF_DISPATCH(nd, nfl, (k_int_viscflux<ND, NF><<<hf_blocks(n, 128), 128, 0, c->stream>>>(W, n, I.nf, I.idx_l, I.idx_r, I.type_l, I.type_r, c->phys)));
+  else
+    HF_FAIL("unknown interface operation");
+  HF_LAUNCH_CHECK(c);
+  return 0;
+}
+
+int hf_dev_bdy_inters_op(hf_ctx *c, int inter_type, int op, double time)
+{
+  (void)time; // the reference passes FlowSol->time; only the (out-of-scope) pressure ramp and turbulent inlet read it
+  if (!c->finalized) HF_FAIL("hf_dev_finalize_setup has not been called");
+  hf_bdy_inters_dev &I = c->bdys[inter_type];
+  if (I.n_inters == 0) return 0;
+  HF_CUDA(cudaSetDevice(c->device));
+  hf_views W = hf_make_views(c);
+  int n = I.n_inters * I.nf;
+  const int nd = c->prm.n_dims, nfl = c->prm.n_fields;
+  if (op == HF_COMMON_INVFLUX)
+    HF_DISPATCH(nd, nfl, (k_bdy_invflux<ND, NF><<<hf_blocks(n, 128), 128, 0, c->stream>>>(W, n, I.nf, I.idx_l, I.type_l, I.bc_id, c->bc_table, c->phys, c->prm.R_ref, c->prm.viscous)));
+  else if (op == HF_COMMON_VISCFLUX)
+    HF_DISPATCH(nd, nfl, (k_bdy_viscflux<ND, NF><<<hf_blocks(n, 128), 128, 0, c->stream>>>(W, n, I.nf, I.idx_l, I.type_l, I.bc_id, c->bc_table, c->phys, c->prm.R_ref)));
+  else
+    HF_FAIL("unknown interface operation");
+  HF_LAUNCH_CHECK(c);
+  return 0;
+}
+
+int hf_dev_mpi_inters_op(hf_ctx *c, int inter_type, int op)
+{
+  if (!c->finalized) HF_FAIL("hf_dev_finalize_setup has not been called");
+  hf_mpi_inters_dev &I = c->mpis[inter_type];
+  if (I.n_inters == 0) return 0;
+  HF_CUDA(cudaSetDevice(c->device));
+  hf_views W = hf_make_views(c);
+  int n = I.n_inters * I.nf;
+  const int nd = c->prm.n_dims, nfl = c->prm.n_fields;
+  switch (op)
+  {
+  case HF_COMMON_INVFLUX:
+    HF_DISPATCH(nd, nfl, (k_mpi_invflux<ND, NF><<<hf_blocks(n, 128), 128, 0, c->stream>>>(W, n, I.nf, I.idx_l, I.type_l, I.lut, I.in_disu, c->phys, c->prm.viscous)));
+    HF_LAUNCH_CHECK(c);
+    return 0;
+  case HF_COMMON_VISCFLUX:
+    HF_DISPATCH(nd, nfl, (k_mpi_viscflux<ND, NF><<<hf_blocks(n, 128), 128, 0, c->stream>>>(W, n, I.nf, I.idx_l, I.type_l, I.lut, I.in_disu, I.in_grad, c->phys)));
+    HF_LAUNCH_CHECK(c);
+    return 0;
+  case 2: // send_solution: pack, then post the exchange on the comm stream
+    k_pack_disu<<<hf_blocks(n, 128), 128, 0, c->stream>>>(W, n, I.nf, nfl, I.idx_l, I.type_l, I.out_disu);
+    HF_LAUNCH_CHECK(c);
+    return hf_halo_post(c, I, I.out_disu, I.in_disu, (size_t)I.nf * nfl);
+  case 3: // receive_solution
+    return hf_halo_wait(c);
+  case 4: // send_corrected_gradient
+    k_pack_grad<<<hf_blocks(n, 128), 128, 0, c->stream>>>(W, n, I.nf, nfl, nd, I.idx_l, I.type_l, I.out_grad);
+    HF_LAUNCH_CHECK(c);
+    return hf_halo_post(c, I, I.out_grad, I.in_grad, (size_t)I.nf * nfl * nd);
+  case 5: // receive_corrected_gradient
+    return hf_halo_wait(c);
+  default:
+    HF_FAIL("unknown partition-interface operation");
+  }
+}
+
+// ---- CalcResidual / AdvanceSolution --------------------------------------------------------------------------------------
+static int staged_residual(hf_ctx *c, double time)
+{
+  const bool visc = c->prm.viscous != 0;
+  const bool par = c->nproc > 1;
+#define EACH_ELE(OP) for (int t = 0; t < HF_N_ELE_TYPES; t++) if (c->eles[t].present && hf_dev_eles_op(c, t, OP)) return 1
+#define EACH_INT(OP) for (int t = 0; t < HF_N_INTER_TYPES; t++) if (hf_dev_int_inters_op(c, t, OP)) return 1
+#define EACH_BDY(OP) for (int t = 0; t < HF_N_INTER_TYPES; t++) if (hf_dev_bdy_inters_op(c, t, OP, time)) return 1
+#define EACH_MPI(OP) for (int t = 0; t < HF_N_INTER_TYPES; t++) if (hf_dev_mpi_inters_op(c, t, OP)) return 1
+  EACH_ELE(HF_EXTRAPOLATE_SOLUTION);
+  if (par) EACH_MPI(2);
+  if (visc) EACH_ELE(HF_CALCULATE_GRADIENT);
+  EACH_ELE(HF_EVALUATE_INVFLUX);
+  EACH_INT(HF_COMMON_INVFLUX);
+  EACH_BDY(HF_COMMON_INVFLUX);
+  if (par) { EACH_MPI(3); EACH_MPI(HF_COMMON_INVFLUX); }
+  if (visc)
+  {
+    EACH_ELE(HF_CORRECT_GRADIENT);
+    if (par) EACH_MPI(4);
+    EACH_ELE(HF_EVALUATE_VISCFLUX);
+  }
+  EACH_ELE(HF_EXTRAPOLATE_TOTALFLUX);
+  EACH_ELE(HF_CALCULATE_DIVERGENCE);
+  if (visc)
+  {
+    EACH_INT(HF_COMMON_VISCFLUX);
+    EACH_BDY(HF_COMMON_VISCFLUX);
+    if (par) { EACH_MPI(5); EACH_MPI(HF_COMMON_VISCFLUX); }
+  }
+  EACH_ELE(HF_CALCULATE_CORRECTED_DIVERGENCE);
+  return 0;
+}
+
+int hf_dev_calc_residual(hf_ctx *c, int rk_stage, double time)
+{
+  if (!c->finalized) HF_FAIL("hf_dev_finalize_setup has not been called");
+  if (c->fused && hf_fused_available(c)) return hf_fused_stage(c, rk_stage, time, 1, 0);
+  return staged_residual(c, time);
+}
+
+static int advance_one(hf_ctx *c, hf_eles_dev &e, int stage)
+{
+  const hf_params &p = c->prm;
+  long long n_pts = (long long)e.n_upts * e.n_eles, n = n_pts * e.n_fields;
+  int mode = 0, copy = 0;
+  double fac = 1.0, c1 = 0., c2 = 0.;
+  if (p.adv_type == 0) { mode = 0; fac = 1.0; }
+  else if (p.adv_type == 1)
+  {
+    copy = stage == 0;
+    if (stage < 3) { mode = 0; fac = 3.0; }
+    else { mode = 1; fac = 4.0; c1 = 3.0 / 4.0; c2 = 1.0 / 4.0; }
+  }
+  else if (p.adv_type == 2)
+  {
+    copy = stage == 0;
+    if (stage < 2 || stage == 3) { mode = 0; fac = 2.0; }
+    else { mode = 1; fac = 6.0; c1 = 1.0 / 3.0; c2 = 2.0 / 3.0; }
+  }
+  else if (p.adv_type == 3 || p.adv_type == 4)
+  {
+    if (stage < 0 || stage >= HF_MAX_RK) HF_FAIL("RK stage out of range");
+    mode = 2; c1 = p.RK_a[stage]; c2 = p.RK_b[stage];
+  }
+  else
+    HF_FAIL("ERROR: Time integration type not recognised ... ");
+  const double *dtl = (p.dt_type == 2) ? e.dt_local : nullptr;
+  k_rk_update<<<hf_blocks(n, 256), 256, 0, c->stream>>>(n, n_pts, e.n_upts, e.disu_upts[0], e.disu_upts[1], e.div_tconf_upts, e.detjac_upts, dtl,
+                                                        p.dt, fac, c1, c2, mode, copy);
+  HF_LAUNCH_CHECK(c);
+  c->ufpts_valid = false;
+  return 0;
+}
+
+// rk_stage: bits 0-7 the stage; bits 8.. = 1 + element type to advance one type only (0 = all types)
+int hf_dev_advance_solution(hf_ctx *c, int rk_stage)
+{
+  if (!c->finalized) HF_FAIL("hf_dev_finalize_setup has not been called");
+  HF_CUDA(cudaSetDevice(c->device));
+  int stage = rk_stage & 0xff, only = (rk_stage >> 8) - 1;
+  for (int t = 0; t < HF_N_ELE_TYPES; t++)
+  {
+    if (!c->eles[t].present) continue;
+    if (only >= 0 && t != only) continue;
+    if (advance_one(c, c->eles[t], stage)) return 1;
+  }
+  return 0;
+}
+
+int hf_dev_rk_stage(hf_ctx *c, int rk_stage, double time, int keep_residual)
+{
+  if (!c->finalized) HF_FAIL("hf_dev_finalize_setup has not been called");
+  if (c->fused && hf_fused_available(c)) return hf_fused_stage(c, rk_stage, time, keep_residual, 1);
+  if (staged_residual(c, time)) return 1;
+  return hf_dev_advance_solution(c, rk_stage);
+}
+
+int hf_dev_run_steps(hf_ctx *c, int n_steps, double time0)
+{
+  if (c->prm.dt_type != 0) HF_FAIL("hf_dev_run_steps needs a fixed time step (dt_type 0)");
+  double t = time0;
+  for (int s = 0; s < n_steps; s++)
+  {
+    for (int i = 0; i < c->prm.n_rk; i++)
+      if (hf_dev_rk_stage(c, i, t, (s == n_steps - 1 && i == c->prm.n_rk - 1) ? 1 : 0)) return 1;
+    t += c->prm.dt;
+  }
+  return 0;
+}
+
+int hf_dev_set_dt(hf_ctx *c, double dt)
+{
+  c->prm.dt = dt;
+  return 0;
+}
+
+int hf_dev_calc_dt(hf_ctx *c, double *dt_out)
+{
+  if (!c->finalized) HF_FAIL("hf_dev_finalize_setup has not been called");
+  HF_CUDA(cudaSetDevice(c->device));
+  if (c->prm.dt_type == 0) { *dt_out = c->prm.dt; return 0; }
+  if (c->prm.equation != 0) HF_FAIL("CFL time step is only defined for the Euler / Navier-Stokes equations");
+  double dt_min = 1e12;
+  for (int t = 0; t < HF_N_ELE_TYPES; t++)
+  {
+    hf_eles_dev &e = c->eles[t];
+    if (!e.present) continue;
+    if (!e.h_ref || !e.dt_local) HF_FAIL("h_ref was not uploaded: dt_type != 0 needs it");
+    if (e.n_dims == 2)
+      k_dt_local<2><<<hf_blocks(e.n_eles, 128), 128, 0, c->stream>>>(e.n_eles, e.n_upts, e.disu_upts[0], e.h_ref, e.dt_local, c->phys, c->prm.CFL, c->prm.order, c->prm.viscous);
+    else
+      k_dt_local<3><<<hf_blocks(e.n_eles, 128), 128, 0, c->stream>>>(e.n_eles, e.n_upts, e.disu_upts[0], e.h_ref, e.dt_local, c->phys, c->prm.CFL, c->prm.order, c->prm.viscous);
+    HF_LAUNCH_CHECK(c);
+    int nb = std::min(1024, (int)hf_blocks(e.n_eles, 256));
+    k_min_reduce<<<nb, 256, 0, c->stream>>>(e.n_eles, e.dt_local, c->scratch);
+    HF_LAUNCH_CHECK(c);
+    std::vector<double> part(nb);
+    HF_CUDA(cudaMemcpyAsync(part.data(), c->scratch, nb * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    HF_CUDA(cudaStreamSynchronize(c->stream));
+    for (double v : part) if (v < dt_min) dt_min = v;
+  }
+  if (c->nproc > 1 && hf_halo_allreduce_min(c, &dt_min)) return 1;
+  c->prm.dt = dt_min;
+  *dt_out = dt_min;
+  return 0;
+}
+
+// ---- data movement -------------------------------------------------------------------------------------------------------
+static int locate_array(hf_ctx *c, hf_eles_dev &e, int which, double **p, size_t *n)
+{
+  const size_t NU = (size_t)e.n_upts * e.n_eles, NFP = (size_t)e.n_fpts * e.n_eles, F = e.n_fields, D = e.n_dims;
+  switch (which)
+  {
+  case HF_DISU_UPTS0: *p = e.disu_upts[0]; *n = NU * F; break;
+  case HF_DISU_UPTS1: *p = e.disu_upts[1]; *n = NU * F; break;
+  case HF_DIV_TCONF_UPTS: *p = e.div_tconf_upts; *n = NU * F; break;
+  case HF_DISU_FPTS: *p = e.disu_fpts; *n = NFP * F; break;
+  case HF_TDISF_UPTS: *p = e.tdisf_upts; *n = NU * F * D; break;
+  case HF_NORM_TDISF_FPTS: *p = e.norm_tdisf_fpts; *n = NFP * F; break;
+  case HF_NORM_TCONF_FPTS: *p = e.norm_tconf_fpts; *n = NFP * F; break;
+  case HF_DELTA_DISU_FPTS: *p = e.delta_disu_fpts; *n = NFP * F; break;
+  case HF_GRAD_DISU_UPTS: *p = e.grad_disu_upts; *n = NU * F * D; break;
+  case HF_GRAD_DISU_FPTS: *p = e.grad_disu_fpts; *n = NFP * F * D; break;
+  case HF_SRC_UPTS: *p = nullptr; *n = NU * F; break;
+  case HF_DT_LOCAL: *p = e.dt_local; *n = e.n_eles; break;
+  default: HF_FAIL("unknown array id");
+  }
+  (void)c;
+  return 0;
+}
+
+int hf_dev_download(hf_ctx *c, int ele_type, int which, double *host, size_t n_doubles)
+{
+  HF_CUDA(cudaSetDevice(c->device));
+  hf_eles_dev &e = c->eles[ele_type];
+  if (!e.present) HF_FAIL("element type not present on the device");
+  double *p; size_t n;
+  if (locate_array(c, e, which, &p, &n)) return 1;
+  if (n_doubles != n) HF_FAIL("download: size mismatch");
+  if (which == HF_SRC_UPTS) { memset(host, 0, n * sizeof(double)); return 0; } // no source terms on the in-scope path
+  if (!p) HF_FAIL("download: array is not materialised on the device in the current mode");
+  if (which == HF_DISU_FPTS && c->fused && hf_fused_available(c) && !c->ufpts_valid && hf_fused_extrapolate(c)) return 1;
+  HF_CUDA(cudaMemcpyAsync(host, p, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  HF_CUDA(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+int hf_dev_upload(hf_ctx *c, int ele_type, int which, const double *host, size_t n_doubles)
+{
+  HF_CUDA(cudaSetDevice(c->device));
+  hf_eles_dev &e = c->eles[ele_type];
+  if (!e.present) HF_FAIL("element type not present on the device");
+  double *p; size_t n;
+  if (locate_array(c, e, which, &p, &n)) return 1;
+  if (n_doubles != n) HF_FAIL("upload: size mismatch");
+  if (!p)
+  {
+    if (ensure_staged_buffers(c, e) || locate_array(c, e, which, &p, &n)) return 1;
+    if (!p) HF_FAIL("upload: array is not materialised on the device");
+  }
+  HF_CUDA(cudaMemcpyAsync(p, host, n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  HF_CUDA(cudaStreamSynchronize(c->stream));
+  c->ufpts_valid = false;
+  return 0;
+}
+
+int hf_dev_residual_norm(hf_ctx *c, int norm_type, double *out)
+{
+  HF_CUDA(cudaSetDevice(c->device));
+  if (norm_type < 0 || norm_type > 2) HF_FAIL("norm_type not recognized");
+  const int nb = 512;
+  for (int f = 0; f < c->prm.n_fields; f++) out[f] = 0.;
+  for (int t = 0; t < HF_N_ELE_TYPES; t++)
+  {
+    hf_eles_dev &e = c->eles[t];
+    if (!e.present) continue;
+    long long n_pts = (long long)e.n_upts * e.n_eles;
+    for (int f = 0; f < e.n_fields; f++)
+    {
+      const double *div = e.div_tconf_upts + (size_t)f * n_pts;
+      double *part = c->scratch + (size_t)f * nb;
+      if (norm_type == 0) k_res_norm<0><<<nb, 256, 0, c->stream>>>(n_pts, div, e.detjac_upts, part);
+      else if (norm_type == 1) k_res_norm<1><<<nb, 256, 0, c->stream>>>(n_pts, div, e.detjac_upts, part);
+      else k_res_norm<2><<<nb, 256, 0, c->stream>>>(n_pts, div, e.detjac_upts, part);
+      HF_LAUNCH_CHECK(c);
+    }
+    std::vector<double> h((size_t)nb * e.n_fields);
+    HF_CUDA(cudaMemcpyAsync(h.data(), c->scratch, h.size() * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    HF_CUDA(cudaStreamSynchronize(c->stream));
+    for (int f = 0; f < e.n_fields; f++)
+    {
+      double s = 0.;
+      for (int b = 0; b < nb; b++) s = (norm_type == 0) ? std::max(s, h[(size_t)f * nb + b]) : s + h[(size_t)f * nb + b];
+      out[f] = (norm_type == 0) ? std::max(out[f], s) : out[f] + s;
+    }
+  }
+  return 0;
+}
+
+int hf_dev_sync(hf_ctx *c)
+{
+  if (!c) HF_FAIL("no device context");
+  HF_CUDA(cudaSetDevice(c->device));
+  HF_CUDA(cudaStreamSynchronize(c->stream));
+  HF_CUDA(cudaStreamSynchronize(c->comm_stream));
+  HF_CUDA(cudaGetLastError());
+  return 0;
+}
+
+long long hf_dev_launch_count(hf_ctx *c) { return c ? c->launches : 0; }
+
+int hf_dev_kernel_timer(hf_ctx *c, int mode, double *ms_total, long long *n_launches)
+{
+  HF_CUDA(cudaSetDevice(c->device));
+  if (mode == 1) { c->ktimer_on = true; c->kt_used = 0; }
+  else if (mode == 0) c->ktimer_on = false;
+  double tot = 0.;
+  if (mode == -1 || mode == 0)
+  {
+    HF_CUDA(cudaStreamSynchronize(c->stream));
+    for (size_t i = 0; i + 1 < c->kt_used; i += 2)
+    {
+      float ms = 0.f;
+      HF_CUDA(cudaEventElapsedTime(&ms, c->kt_ev[i], c->kt_ev[i + 1]));
+      tot += ms;
+    }
+  }
+  if (ms_total) *ms_total = tot;
+  if (n_launches) *n_launches = (long long)(c->kt_used / 2);
+  return 0;
+}
+
+int hf_dev_timer_start(hf_ctx *c)
+{
+  HF_CUDA(cudaEventRecord(c->ev_t0, c->stream));
+  return 0;
+}
+int hf_dev_timer_stop(hf_ctx *c, float *ms)
+{
+  HF_CUDA(cudaEventRecord(c->ev_t1, c->stream));
+  HF_CUDA(cudaEventSynchronize(c->ev_t1));
+  HF_CUDA(cudaEventElapsedTime(ms, c->ev_t0, c->ev_t1));
+  return 0;
+}
+
+} // extern "C"

@@ -1,0 +1,613 @@
+// Element base class: storage, operator construction, metric terms, initial conditions on the host; every
+// per-stage method is a single call into the device layer.
+//   storage         reference src/eles.cpp:58-228
+//   set_ics         reference src/eles.cpp:237-531
+//   set_opp_0..6    reference src/eles.cpp:3074-3596
+//   set_transforms  reference src/eles.cpp:4015-4393   (arithmetic order kept: the LDG beta switch tests the sign
+//                   of rounding-level normal components, reference src/inters.cpp:570-581, so the metrics have to
+//                   be bit-identical, not merely close)
+#include "hifiles.h"
+
+using namespace std;
+
+void hf_check(int status)
+{
+  if (status != 0) FatalError(string("device layer: ") + hf_dev_last_error());
+}
+
+eles::eles()
+{
+  ctx = nullptr;
+  rank = 0;
+  ele_type = -1;
+  n_eles = 0;
+  n_dims = n_fields = order = viscous = n_inters_per_ele = 0;
+  n_upts_per_ele = n_fpts_per_ele = max_n_spts_per_ele = n_adv_levels = upts_type = 0;
+}
+
+void eles::setup(int in_n_eles, int in_max_n_spts_per_ele)
+{
+  n_eles = in_n_eles;
+  max_n_spts_per_ele = in_max_n_spts_per_ele;
+  if (n_eles == 0) return;
+
+  order = run_input.order;
+  viscous = run_input.viscous;
+  setup_ele_type_specific();
+
+  if (run_input.adv_type == 0) n_adv_levels = 1;
+  else if (run_input.adv_type >= 1 && run_input.adv_type <= 4) n_adv_levels = 2;
+  else FatalError("ERROR: Type of time integration scheme not recongized ... ");
+
+  disu_upts.setup(n_adv_levels);
+  for (int i = 0; i < n_adv_levels; i++) disu_upts(i).setup(n_upts_per_ele, n_eles, n_fields); // zero-initialised
+  if (run_input.dt_type == 2) dt_local.setup(n_eles);
+  src_upts.setup(n_upts_per_ele, n_eles, n_fields);
+  set_shape(in_max_n_spts_per_ele);
+  d_nodal_s_basis.setup(max_n_spts_per_ele, n_dims);
+  ele2global_ele.setup(n_eles);
+  bcid.setup(n_eles, n_inters_per_ele);
+  div_tconf_upts.setup(1);
+  div_tconf_upts(0).setup(n_upts_per_ele, n_eles, n_fields);
+}
+
+void eles::set_shape(int in_max_n_spts_per_ele)
+{
+  shape.setup(n_dims, in_max_n_spts_per_ele, n_eles);
+  n_spts_per_ele.setup(n_eles);
+}
+
+void eles::set_shape_node(int in_spt, int in_ele, hf_array<double> &in_pos)
+{
+  for (int i = 0; i < n_dims; i++) shape(i, in_spt, in_ele) = in_pos(i);
+}
+
+int eles::get_fpt_index(int in_inter_local_fpt, int in_ele_local_inter)
+{
+  int fpt = in_inter_local_fpt;
+  for (int i = 0; i < in_ele_local_inter; i++) fpt += n_fpts_per_inter(i);
+  return fpt;
+}
+
+// ---- initial conditions --------------------------------------------------------------------------------------
+void eles::set_ics(double &time)
+{
+  double rho, vx, vy, vz, p;
+  double gamma = run_input.gamma;
+  time = 0.;
+  hf_array<double> pos(n_dims), ics(n_fields);
+
+  for (int i = 0; i < n_eles; i++)
+  {
+    for (int j = 0; j < n_upts_per_ele; j++)
+    {
+      for (int k = 0; k < n_dims; k++) pos(k) = pos_upts(j, i, k);
+
+      if (run_input.ic_form == 0) // isentropic vortex
+      {
+        eval_isentropic_vortex(pos, time, rho, vx, vy, vz, p, n_dims);
+        ics(0) = rho;
+        ics(1) = rho * vx;
+        ics(2) = rho * vy;
+        if (n_dims == 2)
+          ics(3) = (p / (gamma - 1.0)) + (0.5 * rho * ((vx * vx) + (vy * vy)));
+        else
+        {
+          ics(3) = rho * vz;
+          ics(4) = (p / (gamma - 1.0)) + (0.5 * rho * ((vx * vx) + (vy * vy) + (vz * vz)));
+        }
+      }
+      else if (run_input.ic_form == 1) // uniform flow
+      {
+        rho = run_input.rho_c_ic;
+        vx = run_input.u_c_ic;
+        vy = run_input.v_c_ic;
+        vz = run_input.w_c_ic;
+        p = run_input.p_c_ic;
+        ics(0) = rho;
+        ics(1) = rho * vx;
+        ics(2) = rho * vy;
+        if (n_dims == 2)
+          ics(3) = (p / (gamma - 1.0)) + (0.5 * rho * ((vx * vx) + (vy * vy)));
+        else
+        {
+          ics(3) = rho * vz;
+          ics(4) = (p / (gamma - 1.0)) + (0.5 * rho * ((vx * vx) + (vy * vy) + (vz * vz)));
+        }
+      }
+      else if (run_input.ic_form == 7) // Taylor-Green vortex
+      {
+        double V_0 = run_input.uvw_c_ic / run_input.uvw_ref;
+        if (n_dims == 2)
+        {
+          p = run_input.p_c_ic + run_input.rho_c_ic * pow(V_0, 2) / 4.0 * (cos(2.0 * pos(0)) + cos(2.0 * pos(1)));
+          ics(0) = p / (run_input.R_ref * run_input.T_c_ic);
+          ics(1) = ics(0) * V_0 * sin(pos(0)) * cos(pos(1));
+          ics(2) = -ics(0) * V_0 * cos(pos(0)) * sin(pos(1));
+          ics(3) = p / (gamma - 1.0) + 0.5 * (ics(1) * ics(1) + ics(2) * ics(2)) / ics(0);
+        }
+        else
+        {
+          p = run_input.p_c_ic + run_input.rho_c_ic * pow(V_0, 2) / 16.0 * (cos(2.0 * pos(0)) + cos(2.0 * pos(1))) * (cos(2.0 * pos(2)) + 2.0);
+          ics(0) = p / (run_input.R_ref * run_input.T_c_ic);
+          ics(1) = ics(0) * V_0 * sin(pos(0)) * cos(pos(1)) * cos(pos(2));
+          ics(2) = -ics(0) * V_0 * cos(pos(0)) * sin(pos(1)) * cos(pos(2));
+          ics(3) = 0.0;
+          ics(4) = p / (gamma - 1.0) + 0.5 * (ics(1) * ics(1) + ics(2) * ics(2) + ics(3) * ics(3)) / ics(0);
+        }
+      }
+      else if (run_input.ic_form == 9) // stationary shock
+      {
+        int found = 0;
+        for (size_t k = 0; k < run_input.bc_list.size(); k++)
+        {
+          bc &b = run_input.bc_list[k];
+          if (b.get_bc_flag() == SUP_IN || b.get_bc_flag() == CHAR)
+          {
+            if (pos(0) <= run_input.x_shock_ic)
+            {
+              rho = b.rho; vx = b.velocity(0); vy = b.velocity(1); vz = b.velocity(2); p = b.p_static;
+            }
+            else
+            {
+              rho = run_input.rho_c_ic; vx = run_input.u_c_ic; vy = run_input.v_c_ic; vz = run_input.w_c_ic; p = run_input.p_c_ic;
+            }
+            found = 1;
+            break;
+          }
+        }
+        if (found == 0) FatalError("Must have a Sup_In or Char boundary condition");
+        ics(0) = rho;
+        ics(1) = rho * vx;
+        ics(2) = rho * vy;
+        if (n_dims == 2)
+          ics(3) = (p / (gamma - 1.0)) + (0.5 * rho * ((vx * vx) + (vy * vy)));
+        else
+        {
+          ics(3) = rho * vz;
+          ics(4) = (p / (gamma - 1.0)) + (0.5 * rho * ((vx * vx) + (vy * vy) + (vz * vz)));
+        }
+      }
+      else if (run_input.ic_form == 10) // shock tube
+      {
+        vx = vy = vz = 0.;
+        if (pos(0) <= run_input.x_shock_ic)
+        {
+          if (run_input.viscous) { p = 100000. / run_input.p_ref; rho = 1.0 / run_input.rho_ref; }
+          else { p = 100000.; rho = 1.0; }
+        }
+        else
+        {
+          if (run_input.viscous) { p = 10000. / run_input.p_ref; rho = 0.125 / run_input.rho_ref; }
+          else { p = 10000.; rho = 0.125; }
+        }
+        ics(0) = rho;
+        ics(1) = rho * vx;
+        ics(2) = rho * vy;
+        if (n_dims == 2)
+          ics(3) = (p / (gamma - 1.0)) + (0.5 * rho * ((vx * vx) + (vy * vy)));
+        else
+        {
+          ics(3) = rho * vz;
+          ics(4) = (p / (gamma - 1.0)) + (0.5 * rho * ((vx * vx) + (vy * vy) + (vz * vz)));
+        }
+      }
+      else
+        FatalError("ERROR: Invalid form of initial condition ...");
+
+      if (run_input.perturb_ic == 1 && n_dims == 3)
+      {
+        double alpha = 0.1, L_x = 2. * pi, L_y = pi, L_z = 2.;
+        ics(3) += alpha * exp(-pow((pos(0) - L_x / 2.) / L_x, 2)) * exp(-pow(pos(1) / L_y, 2)) * cos(4. * pi * pos(2) / L_z);
+      }
+
+      for (int k = 0; k < n_fields; k++) disu_upts(0)(j, i, k) = ics(k);
+    }
+  }
+
+  if (run_input.dt_type > 0)
+  {
+    h_ref.setup(n_eles);
+    for (int i = 0; i < n_eles; i++) h_ref(i) = calc_h_ref_specific(i);
+  }
+  else
+    h_ref.setup(1);
+}
+
+double eles::calc_h_ref_specific(int e)
+{
+  // minimum corner-to-corner edge length (reference src/eles_quads.cpp:1287-1301, src/eles_hexas.cpp:1551-1571);
+  // the shape slots of a linear element are in tensor order, so the edges are the slot pairs below.
+  auto len = [&](int a, int b) {
+    double s = 0.;
+    for (int d = 0; d < n_dims; d++) s += pow(shape(d, a, e) - shape(d, b, e), 2.0);
+    return sqrt(s);
+  };
+  double h = 1e300;
+  if (ele_type == QUAD)
+  {
+    const int ed[4][2] = {{0, 1}, {1, 3}, {3, 2}, {2, 0}};
+    for (auto &p : ed) h = min(h, len(p[0], p[1]));
+  }
+  else if (ele_type == HEX)
+  {
+    const int ed[12][2] = {{0, 1}, {1, 3}, {3, 2}, {2, 0}, {4, 5}, {5, 7}, {7, 6}, {6, 4}, {1, 5}, {3, 7}, {0, 4}, {2, 6}};
+    for (auto &p : ed) h = min(h, len(p[0], p[1]));
+  }
+  else
+    FatalError("h_ref not available for this element type");
+  return h;
+}
+
+// ---- operators -------------------------------------------------------------------------------------------------
+void eles::set_opp_0(int)
+{
+  hf_array<double> loc(n_dims);
+  opp_0.setup(n_fpts_per_ele, n_upts_per_ele);
+  for (int i = 0; i < n_upts_per_ele; i++)
+    for (int j = 0; j < n_fpts_per_ele; j++)
+    {
+      for (int k = 0; k < n_dims; k++) loc(k) = tloc_fpts(k, j);
+      opp_0(j, i) = eval_nodal_basis(i, loc);
+    }
+}
+
+void eles::set_opp_1(int)
+{
+  hf_array<double> loc(n_dims);
+  opp_1.setup(n_dims);
+  for (int i = 0; i < n_dims; i++) opp_1(i).setup(n_fpts_per_ele, n_upts_per_ele);
+  for (int i = 0; i < n_dims; i++)
+    for (int j = 0; j < n_upts_per_ele; j++)
+      for (int k = 0; k < n_fpts_per_ele; k++)
+      {
+        for (int l = 0; l < n_dims; l++) loc(l) = tloc_fpts(l, k);
+        opp_1(i)(k, j) = eval_nodal_basis(j, loc) * tnorm_fpts(i, k);
+      }
+}
+
+void eles::set_opp_2(int)
+{
+  hf_array<double> loc(n_dims);
+  opp_2.setup(n_dims);
+  for (int i = 0; i < n_dims; i++) opp_2(i).setup(n_upts_per_ele, n_upts_per_ele);
+  for (int i = 0; i < n_dims; i++)
+    for (int j = 0; j < n_upts_per_ele; j++)
+      for (int k = 0; k < n_upts_per_ele; k++)
+      {
+        for (int l = 0; l < n_dims; l++) loc(l) = loc_upts(l, k);
+        opp_2(i)(k, j) = eval_d_nodal_basis(j, i, loc);
+      }
+}
+
+void eles::set_opp_3(int)
+{
+  opp_3.setup(n_upts_per_ele, n_fpts_per_ele);
+  fill_opp_3(opp_3);
+}
+
+void eles::set_opp_4(int)
+{
+  hf_array<double> loc(n_dims);
+  opp_4.setup(n_dims);
+  for (int i = 0; i < n_dims; i++) opp_4(i).setup(n_upts_per_ele, n_upts_per_ele);
+  for (int i = 0; i < n_dims; i++)
+    for (int j = 0; j < n_upts_per_ele; j++)
+      for (int k = 0; k < n_upts_per_ele; k++)
+      {
+        for (int l = 0; l < n_dims; l++) loc(l) = loc_upts(l, k);
+        opp_4(i)(k, j) = eval_d_nodal_basis(j, i, loc);
+      }
+}
+
+void eles::set_opp_5(int)
+{
+  opp_5.setup(n_dims);
+  for (int i = 0; i < n_dims; i++) opp_5(i).setup(n_upts_per_ele, n_fpts_per_ele);
+  for (int i = 0; i < n_dims; i++)
+    for (int j = 0; j < n_fpts_per_ele; j++)
+      for (int k = 0; k < n_upts_per_ele; k++)
+        opp_5(i)(k, j) = opp_3(k, j) * tnorm_fpts(i, j);
+}
+
+void eles::set_opp_6(int)
+{
+  hf_array<double> loc(n_dims);
+  opp_6.setup(n_fpts_per_ele, n_upts_per_ele);
+  for (int j = 0; j < n_upts_per_ele; j++)
+    for (int l = 0; l < n_fpts_per_ele; l++)
+    {
+      for (int m = 0; m < n_dims; m++) loc(m) = tloc_fpts(m, l);
+      opp_6(l, j) = eval_nodal_basis(j, loc);
+    }
+}
+
+// ---- metrics ---------------------------------------------------------------------------------------------------
+void eles::calc_pos(hf_array<double> &in_loc, int in_ele, hf_array<double> &out_pos)
+{
+  for (int i = 0; i < n_dims; i++)
+  {
+    out_pos(i) = 0.0;
+    for (int j = 0; j < n_spts_per_ele(in_ele); j++)
+      out_pos(i) += eval_nodal_s_basis(j, in_loc, n_spts_per_ele(in_ele)) * shape(i, j, in_ele);
+  }
+}
+
+void eles::calc_d_pos(hf_array<double> &in_loc, int in_ele, hf_array<double> &out_d_pos)
+{
+  eval_d_nodal_s_basis(d_nodal_s_basis, in_loc, n_spts_per_ele(in_ele));
+  for (int j = 0; j < n_dims; j++)
+    for (int k = 0; k < n_dims; k++)
+    {
+      out_d_pos(j, k) = 0.0;
+      for (int i = 0; i < n_spts_per_ele(in_ele); i++)
+        out_d_pos(j, k) += d_nodal_s_basis(i, k) * shape(j, i, in_ele);
+    }
+}
+
+void eles::set_transforms()
+{
+  if (n_eles == 0) return;
+  set_transforms_upts();
+  set_transforms_fpts();
+}
+
+namespace
+{
+// The shape-basis values depend only on the reference location and the number of shape nodes; the reference
+// re-evaluates them for every element (the start-up bottleneck at 64^3).  Cache them per
+// (point, n_spts): the sums below then use the very same factors in the very same order.
+struct basis_cache
+{
+  int n_spts = -1;
+  vector<double> s;  // [pt][spt]
+  vector<double> ds; // [pt][spt][dim]
+};
+} // namespace
+
+static void fill_basis_cache(eles *e, hf_array<double> &locs, int n_pts, int n_spts, basis_cache &c)
+{
+  int nd = e->n_dims;
+  c.n_spts = n_spts;
+  c.s.assign((size_t)n_pts * n_spts, 0.);
+  c.ds.assign((size_t)n_pts * n_spts * nd, 0.);
+  hf_array<double> loc(nd), d(e->max_n_spts_per_ele, nd);
+  for (int p = 0; p < n_pts; p++)
+  {
+    for (int k = 0; k < nd; k++) loc(k) = locs(k, p);
+    for (int j = 0; j < n_spts; j++) c.s[(size_t)p * n_spts + j] = e->eval_nodal_s_basis(j, loc, n_spts);
+    e->eval_d_nodal_s_basis(d, loc, n_spts);
+    for (int j = 0; j < n_spts; j++)
+      for (int k = 0; k < nd; k++) c.ds[((size_t)p * n_spts + j) * nd + k] = d(j, k);
+  }
+}
+
+void eles::set_transforms_upts()
+{
+  detjac_upts.setup(n_upts_per_ele, n_eles);
+  JGinv_upts.setup(n_dims, n_dims, n_upts_per_ele, n_eles);
+  pos_upts.setup(n_upts_per_ele, n_eles, n_dims);
+  basis_cache c;
+  double dp[3][3];
+  for (int i = 0; i < n_eles; i++)
+  {
+    int ns = n_spts_per_ele(i);
+    if (ns != c.n_spts) fill_basis_cache(this, loc_upts, n_upts_per_ele, ns, c);
+    for (int j = 0; j < n_upts_per_ele; j++)
+    {
+      const double *s = &c.s[(size_t)j * ns];
+      const double *ds = &c.ds[(size_t)j * ns * n_dims];
+      for (int d = 0; d < n_dims; d++)
+      {
+        double acc = 0.0;
+        for (int q = 0; q < ns; q++) acc += s[q] * shape(d, q, i);
+        pos_upts(j, i, d) = acc;
+      }
+      for (int a = 0; a < n_dims; a++)
+        for (int b = 0; b < n_dims; b++)
+        {
+          double acc = 0.0;
+          for (int q = 0; q < ns; q++) acc += ds[q * n_dims + b] * shape(a, q, i);
+          dp[a][b] = acc;
+        }
+      if (n_dims == 2)
+      {
+        double xr = dp[0][0], xs = dp[0][1], yr = dp[1][0], ys = dp[1][1];
+        detjac_upts(j, i) = xr * ys - xs * yr;
+        if (detjac_upts(j, i) < 0) FatalError("Negative Jacobian at solution points");
+        JGinv_upts(0, 0, j, i) = ys;
+        JGinv_upts(0, 1, j, i) = -xs;
+        JGinv_upts(1, 0, j, i) = -yr;
+        JGinv_upts(1, 1, j, i) = xr;
+      }
+      else
+      {
+        double xr = dp[0][0], xs = dp[0][1], xt = dp[0][2];
+        double yr = dp[1][0], ys = dp[1][1], yt = dp[1][2];
+        double zr = dp[2][0], zs = dp[2][1], zt = dp[2][2];
+        detjac_upts(j, i) = xr * (ys * zt - yt * zs) - xs * (yr * zt - yt * zr) + xt * (yr * zs - ys * zr);
+        JGinv_upts(0, 0, j, i) = ys * zt - yt * zs;
+        JGinv_upts(0, 1, j, i) = xt * zs - xs * zt;
+        JGinv_upts(0, 2, j, i) = xs * yt - xt * ys;
+        JGinv_upts(1, 0, j, i) = yt * zr - yr * zt;
+        JGinv_upts(1, 1, j, i) = xr * zt - xt * zr;
+        JGinv_upts(1, 2, j, i) = xt * yr - xr * yt;
+        JGinv_upts(2, 0, j, i) = yr * zs - ys * zr;
+        JGinv_upts(2, 1, j, i) = xs * zr - xr * zs;
+        JGinv_upts(2, 2, j, i) = xr * ys - xs * yr;
+      }
+    }
+  }
+}
+
+void eles::set_transforms_fpts()
+{
+  detjac_fpts.setup(n_fpts_per_ele, n_eles);
+  JGinv_fpts.setup(n_dims, n_dims, n_fpts_per_ele, n_eles);
+  tdA_fpts.setup(n_fpts_per_ele, n_eles);
+  norm_fpts.setup(n_fpts_per_ele, n_eles, n_dims);
+  pos_fpts.setup(n_fpts_per_ele, n_eles, n_dims);
+  basis_cache c;
+  double dp[3][3], tn[3];
+  for (int i = 0; i < n_eles; i++)
+  {
+    int ns = n_spts_per_ele(i);
+    if (ns != c.n_spts) fill_basis_cache(this, tloc_fpts, n_fpts_per_ele, ns, c);
+    for (int j = 0; j < n_fpts_per_ele; j++)
+    {
+      const double *s = &c.s[(size_t)j * ns];
+      const double *ds = &c.ds[(size_t)j * ns * n_dims];
+      for (int d = 0; d < n_dims; d++)
+      {
+        double acc = 0.0;
+        for (int q = 0; q < ns; q++) acc += s[q] * shape(d, q, i);
+        pos_fpts(j, i, d) = acc;
+      }
+      for (int a = 0; a < n_dims; a++)
+        for (int b = 0; b < n_dims; b++)
+        {
+          double acc = 0.0;
+          for (int q = 0; q < ns; q++) acc += ds[q * n_dims + b] * shape(a, q, i);
+          dp[a][b] = acc;
+        }
+      if (n_dims == 2)
+      {
+        double xr = dp[0][0], xs = dp[0][1], yr = dp[1][0], ys = dp[1][1];
+        detjac_fpts(j, i) = xr * ys - xs * yr;
+        if (detjac_fpts(j, i) < 0) FatalError("Negative Jacobian at flux points");
+        JGinv_fpts(0, 0, j, i) = ys;
+        JGinv_fpts(0, 1, j, i) = -xs;
+        JGinv_fpts(1, 0, j, i) = -yr;
+        JGinv_fpts(1, 1, j, i) = xr;
+        tn[0] = (tnorm_fpts(0, j) * dp[1][1]) - (tnorm_fpts(1, j) * dp[1][0]);
+        tn[1] = -(tnorm_fpts(0, j) * dp[0][1]) + (tnorm_fpts(1, j) * dp[0][0]);
+        tdA_fpts(j, i) = sqrt(tn[0] * tn[0] + tn[1] * tn[1]);
+        norm_fpts(j, i, 0) = tn[0] / tdA_fpts(j, i);
+        norm_fpts(j, i, 1) = tn[1] / tdA_fpts(j, i);
+      }
+      else
+      {
+        double xr = dp[0][0], xs = dp[0][1], xt = dp[0][2];
+        double yr = dp[1][0], ys = dp[1][1], yt = dp[1][2];
+        double zr = dp[2][0], zs = dp[2][1], zt = dp[2][2];
+        detjac_fpts(j, i) = xr * (ys * zt - yt * zs) - xs * (yr * zt - yt * zr) + xt * (yr * zs - ys * zr);
+        JGinv_fpts(0, 0, j, i) = ys * zt - yt * zs;
+        JGinv_fpts(0, 1, j, i) = xt * zs - xs * zt;
+        JGinv_fpts(0, 2, j, i) = xs * yt - xt * ys;
+        JGinv_fpts(1, 0, j, i) = yt * zr - yr * zt;
+        JGinv_fpts(1, 1, j, i) = xr * zt - xt * zr;
+        JGinv_fpts(1, 2, j, i) = xt * yr - xr * yt;
+        JGinv_fpts(2, 0, j, i) = yr * zs - ys * zr;
+        JGinv_fpts(2, 1, j, i) = xs * zr - xr * zs;
+        JGinv_fpts(2, 2, j, i) = xr * ys - xs * yr;
+        double t0 = tnorm_fpts(0, j), t1 = tnorm_fpts(1, j), t2 = tnorm_fpts(2, j);
+        tn[0] = ((t0 * (dp[1][1] * dp[2][2] - dp[1][2] * dp[2][1])) + (t1 * (dp[1][2] * dp[2][0] - dp[1][0] * dp[2][2])) + (t2 * (dp[1][0] * dp[2][1] - dp[1][1] * dp[2][0])));
+        tn[1] = ((t0 * (dp[0][2] * dp[2][1] - dp[0][1] * dp[2][2])) + (t1 * (dp[0][0] * dp[2][2] - dp[0][2] * dp[2][0])) + (t2 * (dp[0][1] * dp[2][0] - dp[0][0] * dp[2][1])));
+        tn[2] = ((t0 * (dp[0][1] * dp[1][2] - dp[0][2] * dp[1][1])) + (t1 * (dp[0][2] * dp[1][0] - dp[0][0] * dp[1][2])) + (t2 * (dp[0][0] * dp[1][1] - dp[0][1] * dp[1][0])));
+        tdA_fpts(j, i) = sqrt(tn[0] * tn[0] + tn[1] * tn[1] + tn[2] * tn[2]);
+        norm_fpts(j, i, 0) = tn[0] / tdA_fpts(j, i);
+        norm_fpts(j, i, 1) = tn[1] / tdA_fpts(j, i);
+        norm_fpts(j, i, 2) = tn[2] / tdA_fpts(j, i);
+      }
+    }
+  }
+}
+
+// ---- device mirror ---------------------------------------------------------------------------------------------
+void eles::mv_all_cpu_gpu()
+{
+  if (n_eles == 0) return;
+  hf_eles_desc d;
+  memset(&d, 0, sizeof(d));
+  d.ele_type = ele_type;
+  d.n_eles = n_eles;
+  d.n_upts_per_ele = n_upts_per_ele;
+  d.n_fpts_per_ele = n_fpts_per_ele;
+  d.n_dims = n_dims;
+  d.n_fields = n_fields;
+  d.order = order;
+  d.n_inters_per_ele = n_inters_per_ele;
+  d.n_fpts_per_inter = n_fpts_per_inter.get_ptr_cpu();
+  d.opp_0 = opp_0.get_ptr_cpu();
+  d.opp_3 = opp_3.get_ptr_cpu();
+  for (int i = 0; i < n_dims; i++)
+  {
+    d.opp_1[i] = opp_1(i).get_ptr_cpu();
+    d.opp_2[i] = opp_2(i).get_ptr_cpu();
+    if (viscous)
+    {
+      d.opp_4[i] = opp_4(i).get_ptr_cpu();
+      d.opp_5[i] = opp_5(i).get_ptr_cpu();
+    }
+  }
+  if (viscous) d.opp_6 = opp_6.get_ptr_cpu();
+  d.detjac_upts = detjac_upts.get_ptr_cpu();
+  d.JGinv_upts = JGinv_upts.get_ptr_cpu();
+  d.detjac_fpts = detjac_fpts.get_ptr_cpu();
+  d.JGinv_fpts = JGinv_fpts.get_ptr_cpu();
+  d.tdA_fpts = tdA_fpts.get_ptr_cpu();
+  d.norm_fpts = norm_fpts.get_ptr_cpu();
+  d.h_ref = (run_input.dt_type > 0) ? h_ref.get_ptr_cpu() : nullptr;
+  d.disu_upts0 = disu_upts(0).get_ptr_cpu();
+  hf_check(hf_dev_upload_eles(ctx, &d));
+}
+
+void eles::cp_disu_upts_cpu_gpu()
+{
+  if (n_eles) hf_check(hf_dev_upload(ctx, ele_type, HF_DISU_UPTS0, disu_upts(0).get_ptr_cpu(), disu_upts(0).size()));
+}
+void eles::cp_disu_upts_gpu_cpu()
+{
+  if (n_eles) hf_check(hf_dev_download(ctx, ele_type, HF_DISU_UPTS0, disu_upts(0).get_ptr_cpu(), disu_upts(0).size()));
+}
+void eles::cp_div_tconf_upts_gpu_cpu()
+{
+  if (n_eles) hf_check(hf_dev_download(ctx, ele_type, HF_DIV_TCONF_UPTS, div_tconf_upts(0).get_ptr_cpu(), div_tconf_upts(0).size()));
+}
+void eles::cp_grad_disu_upts_gpu_cpu()
+{
+  if (!n_eles || !viscous) return;
+  if (grad_disu_upts.size() == 0) grad_disu_upts.setup(n_upts_per_ele, n_eles, n_fields, n_dims);
+  hf_check(hf_dev_download(ctx, ele_type, HF_GRAD_DISU_UPTS, grad_disu_upts.get_ptr_cpu(), grad_disu_upts.size()));
+}
+void eles::cp_src_upts_gpu_cpu()
+{
+  if (n_eles) hf_check(hf_dev_download(ctx, ele_type, HF_SRC_UPTS, src_upts.get_ptr_cpu(), src_upts.size()));
+}
+void eles::cp_array_gpu_cpu(int which, hf_array<double> &dst)
+{
+  if (n_eles) hf_check(hf_dev_download(ctx, ele_type, which, dst.get_ptr_cpu(), dst.size()));
+}
+
+void eles::extrapolate_solution() { if (n_eles) hf_check(hf_dev_eles_op(ctx, ele_type, HF_EXTRAPOLATE_SOLUTION)); }
+void eles::calculate_gradient() { if (n_eles) hf_check(hf_dev_eles_op(ctx, ele_type, HF_CALCULATE_GRADIENT)); }
+void eles::evaluate_invFlux() { if (n_eles) hf_check(hf_dev_eles_op(ctx, ele_type, HF_EVALUATE_INVFLUX)); }
+void eles::correct_gradient() { if (n_eles) hf_check(hf_dev_eles_op(ctx, ele_type, HF_CORRECT_GRADIENT)); }
+void eles::evaluate_viscFlux() { if (n_eles) hf_check(hf_dev_eles_op(ctx, ele_type, HF_EVALUATE_VISCFLUX)); }
+void eles::extrapolate_totalFlux() { if (n_eles) hf_check(hf_dev_eles_op(ctx, ele_type, HF_EXTRAPOLATE_TOTALFLUX)); }
+void eles::calculate_divergence() { if (n_eles) hf_check(hf_dev_eles_op(ctx, ele_type, HF_CALCULATE_DIVERGENCE)); }
+void eles::calculate_corrected_divergence() { if (n_eles) hf_check(hf_dev_eles_op(ctx, ele_type, HF_CALCULATE_CORRECTED_DIVERGENCE)); }
+
+void eles::AdvanceSolution(int in_step, int adv_type)
+{
+  // the device advances every element type in one call; issue it from the first non-empty type only so the
+  // reference's "for every element type" loop (src/HiFiLES.cpp:209-210) advances exactly once
+  (void)adv_type;
+  if (n_eles == 0) return;
+  hf_check(hf_dev_advance_solution(ctx, in_step | ((ele_type + 1) << 8)));
+}
+
+double eles::compute_res_upts(int in_norm_type, int in_field)
+{
+  // host-side restatement for callers that already copied div_tconf_upts back (reference src/eles.cpp:5045-5074)
+  double sum = 0.;
+  for (int i = 0; i < n_eles; i++)
+    for (int j = 0; j < n_upts_per_ele; j++)
+    {
+      double r = div_tconf_upts(0)(j, i, in_field) / detjac_upts(j, i) - src_upts(j, i, in_field);
+      if (in_norm_type == 0) sum = max(sum, fabs(r));
+      else if (in_norm_type == 1) sum += fabs(r);
+      else if (in_norm_type == 2) sum += r * r;
+    }
+  return sum;
+}

@@ -1,0 +1,167 @@
+// Residual orchestration: the same fixed sequence of element / interface method calls as the reference's
+// CalcResidual (src/solver.cpp:50-223), InitSolution (:321-375), calc_time_step (:484-549) and
+// output::CalcNormResidual (src/output.cpp:2166-2248).  Each call below is one asynchronous device call.
+#include "hifiles.h"
+
+using namespace std;
+
+int get_n_rk_steps(int adv_type)
+{
+  if (adv_type == 0) return 1;
+  if (adv_type == 1 || adv_type == 2) return 4;
+  if (adv_type == 3) return 5;
+  if (adv_type == 4) return 14;
+  FatalError("ERROR: Time integration type not recognised ... ");
+  return 0;
+}
+
+static void upload_params(struct solution *FlowSol)
+{
+  hf_params p;
+  memset(&p, 0, sizeof(p));
+  p.equation = run_input.equation;
+  p.viscous = run_input.viscous;
+  p.n_dims = FlowSol->n_dims;
+  p.n_fields = (run_input.equation == 0) ? FlowSol->n_dims + 2 : 1;
+  p.riemann_solve_type = run_input.riemann_solve_type;
+  p.vis_riemann_solve_type = run_input.vis_riemann_solve_type;
+  p.adv_type = run_input.adv_type;
+  p.dt_type = run_input.dt_type;
+  p.fix_vis = run_input.fix_vis;
+  p.order = run_input.order;
+  p.gamma = run_input.gamma;
+  p.prandtl = run_input.prandtl;
+  p.mu_inf = run_input.mu_inf;
+  p.rt_inf = run_input.rt_inf;
+  p.c_sth = run_input.c_sth;
+  p.ldg_beta = run_input.ldg_beta;
+  p.ldg_tau = run_input.ldg_tau;
+  p.dt = run_input.dt;
+  p.CFL = run_input.CFL;
+  // boundary conditions use the dimensional gas constant when the run is inviscid (reference src/bdy_inters.cpp:368-369)
+  p.R_ref = run_input.viscous ? run_input.R_ref : run_input.R_gas;
+  for (int i = 0; i < 3; i++) p.wave_speed[i] = run_input.wave_speed.size() ? run_input.wave_speed(i) : 0.;
+  p.diff_coeff = run_input.diff_coeff;
+  p.lambda = run_input.lambda;
+  p.n_rk = get_n_rk_steps(run_input.adv_type);
+  for (int i = 0; i < run_input.RK_a.get_dim(0) && i < HF_MAX_RK; i++) p.RK_a[i] = run_input.RK_a(i);
+  for (int i = 0; i < run_input.RK_b.get_dim(0) && i < HF_MAX_RK; i++) p.RK_b[i] = run_input.RK_b(i);
+  hf_check(hf_dev_set_params(FlowSol->ctx, &p));
+
+  vector<hf_bc> table(run_input.bc_list.size());
+  for (size_t i = 0; i < table.size(); i++)
+  {
+    bc &b = run_input.bc_list[i];
+    hf_bc &t = table[i];
+    memset(&t, 0, sizeof(t));
+    t.bc_flag = b.get_bc_flag();
+    t.rho = b.rho;
+    for (int k = 0; k < 3; k++) t.velocity[k] = b.velocity.size() == 3 ? b.velocity(k) : 0.;
+    t.p_static = b.p_static;
+    t.T_static = b.T_static;
+    t.p_total = b.p_total;
+    t.T_total = b.T_total;
+    t.mach = b.mach;
+    t.nx = b.nx; t.ny = b.ny; t.nz = b.nz;
+  }
+  hf_check(hf_dev_set_bc_table(FlowSol->ctx, (int)table.size(), table.empty() ? nullptr : table.data()));
+}
+
+/*! Move everything to the device (the reference did this piecemeal with mv_all_cpu_gpu calls inside
+ *  GeoPreprocess, src/geometry.cpp:310-321, 553-557). */
+static void upload_all(struct solution *FlowSol)
+{
+  upload_params(FlowSol);
+  for (int i = 0; i < FlowSol->n_ele_types; i++) FlowSol->mesh_eles(i)->mv_all_cpu_gpu();
+  for (int i = 0; i < FlowSol->n_int_inter_types; i++) FlowSol->mesh_int_inters[i].mv_all_cpu_gpu();
+  for (int i = 0; i < FlowSol->n_bdy_inter_types; i++) FlowSol->mesh_bdy_inters[i].mv_all_cpu_gpu();
+  for (int i = 0; i < FlowSol->n_mpi_inter_types; i++) FlowSol->mesh_mpi_inters[i].mv_all_cpu_gpu();
+  hf_check(hf_dev_set_mode(FlowSol->ctx, run_input.device_fused));
+  hf_check(hf_dev_finalize_setup(FlowSol->ctx));
+}
+
+void InitSolution(struct solution *FlowSol)
+{
+  if (run_input.restart_flag != 0)
+    FatalError("restart files are outside the hot-path scope of this build");
+  FlowSol->ini_iter = 0;
+  for (int i = 0; i < FlowSol->n_ele_types; i++)
+    if (FlowSol->mesh_eles(i)->get_n_eles() != 0) FlowSol->mesh_eles(i)->set_ics(FlowSol->time);
+  if (!FlowSol->no_device) upload_all(FlowSol);
+}
+
+void CalcResidual(int in_file_num, int in_rk_stage, struct solution *FlowSol)
+{
+  (void)in_file_num;
+  (void)in_rk_stage;
+  int n = FlowSol->n_ele_types;
+  for (int i = 0; i < n; i++) FlowSol->mesh_eles(i)->extrapolate_solution();
+  if (FlowSol->nproc > 1)
+    for (int i = 0; i < FlowSol->n_mpi_inter_types; i++) FlowSol->mesh_mpi_inters[i].send_solution();
+  if (run_input.viscous)
+    for (int i = 0; i < n; i++) FlowSol->mesh_eles(i)->calculate_gradient();
+  for (int i = 0; i < n; i++) FlowSol->mesh_eles(i)->evaluate_invFlux();
+  for (int i = 0; i < FlowSol->n_int_inter_types; i++) FlowSol->mesh_int_inters[i].calculate_common_invFlux();
+  for (int i = 0; i < FlowSol->n_bdy_inter_types; i++) FlowSol->mesh_bdy_inters[i].evaluate_boundaryConditions_invFlux(FlowSol, FlowSol->time);
+  if (FlowSol->nproc > 1)
+  {
+    for (int i = 0; i < FlowSol->n_mpi_inter_types; i++) FlowSol->mesh_mpi_inters[i].receive_solution();
+    for (int i = 0; i < FlowSol->n_mpi_inter_types; i++) FlowSol->mesh_mpi_inters[i].calculate_common_invFlux();
+  }
+  if (run_input.viscous)
+  {
+    for (int i = 0; i < n; i++) FlowSol->mesh_eles(i)->correct_gradient();
+    if (FlowSol->nproc > 1)
+      for (int i = 0; i < FlowSol->n_mpi_inter_types; i++) FlowSol->mesh_mpi_inters[i].send_corrected_gradient();
+    for (int i = 0; i < n; i++) FlowSol->mesh_eles(i)->evaluate_viscFlux();
+  }
+  for (int i = 0; i < n; i++) FlowSol->mesh_eles(i)->extrapolate_totalFlux();
+  for (int i = 0; i < n; i++) FlowSol->mesh_eles(i)->calculate_divergence();
+  if (run_input.viscous)
+  {
+    for (int i = 0; i < FlowSol->n_int_inter_types; i++) FlowSol->mesh_int_inters[i].calculate_common_viscFlux();
+    for (int i = 0; i < FlowSol->n_bdy_inter_types; i++) FlowSol->mesh_bdy_inters[i].evaluate_boundaryConditions_viscFlux(FlowSol->time);
+    if (FlowSol->nproc > 1)
+    {
+      for (int i = 0; i < FlowSol->n_mpi_inter_types; i++) FlowSol->mesh_mpi_inters[i].receive_corrected_gradient();
+      for (int i = 0; i < FlowSol->n_mpi_inter_types; i++) FlowSol->mesh_mpi_inters[i].calculate_common_viscFlux();
+    }
+  }
+  for (int i = 0; i < n; i++) FlowSol->mesh_eles(i)->calculate_corrected_divergence();
+}
+
+void calc_time_step(struct solution *FlowSol)
+{
+  if (run_input.dt_type == 0) return;
+  double dt = 0.;
+  hf_check(hf_dev_calc_dt(FlowSol->ctx, &dt));
+  run_input.dt = dt;
+}
+
+void AdvanceSteps(struct solution *FlowSol, int n_steps)
+{
+  hf_check(hf_dev_run_steps(FlowSol->ctx, n_steps, FlowSol->time));
+  FlowSol->time += n_steps * run_input.dt;
+  run_input.time = FlowSol->time;
+}
+
+void CalcNormResidual(struct solution *FlowSol)
+{
+  int n_fields = (run_input.equation == 0) ? FlowSol->n_dims + 2 : 1;
+  FlowSol->norm_residual.setup(6);
+  double sums[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  hf_check(hf_dev_residual_norm(FlowSol->ctx, run_input.res_norm_type, sums));
+  long long n_upts_global = 0;
+  for (int i = 0; i < FlowSol->n_ele_types; i++)
+    if (FlowSol->mesh_eles(i)->get_n_eles() != 0)
+      n_upts_global += (long long)FlowSol->mesh_eles(i)->get_n_eles() * FlowSol->mesh_eles(i)->get_n_upts_per_ele();
+  for (int f = 0; f < n_fields; f++)
+  {
+    double s = sums[f];
+    if (run_input.res_norm_type == 1) s = s / n_upts_global;
+    else if (run_input.res_norm_type == 2) s = sqrt(s) / n_upts_global;
+    else if (run_input.res_norm_type != 0) FatalError("norm_type not recognized");
+    if (std::isnan(s)) FatalError("NaN residual encountered. Exiting");
+    FlowSol->norm_residual(f) = s;
+  }
+}

@@ -1,0 +1,202 @@
+/* hifiles_b200.h -- C ABI of the B200 device layer for the HiFiLES per-RK-stage residual hot path.
+ *
+ * This is the drop-in seam.  In the reference the host classes reach the device through
+ *   (1) hf_array<T>::{mv_cpu_gpu,cp_cpu_gpu,cp_gpu_cpu,get_ptr_gpu}   (reference include/hf_array.h:341-355,493-594)
+ *   (2) the *_gpu_kernel_wrapper free functions and bespoke_SPMV      (reference include/cuda_kernels.h:30-120)
+ *   (3) legacy cublasDgemm / cublasDaxpy                              (e.g. reference src/eles.cpp:1397,1800)
+ * none of which is compiled any more (SURVEY.md "Five facts" #1).  The entry points below replace all three.
+ * Plain pointers and sizes only; no C++ or torch types.  Every function returns 0 on success, non-zero on
+ * failure with the text available from hf_dev_last_error(); the C++ shim maps non-zero to the reference's
+ * FatalError behaviour (reference include/error.h:31-43).  All device work is enqueued on the context's
+ * compute stream; only download / residual_norm / calc_dt / sync block the host.
+ *
+ * Array layouts are the reference's: column-major hf_array, first index fastest (Appendix A of SURVEY.md):
+ *   disu_upts(upt,ele,field)  disu_fpts(fpt,ele,field)  grad_disu_*(pt,ele,field,dim)  tdisf_upts(upt,ele,field,dim)
+ *   detjac_*(pt,ele)  JGinv_*(l,m,pt,ele)  tdA_fpts(fpt,ele)  norm_fpts(fpt,ele,dim)  opp_k(row,col)
+ */
+#ifndef HIFILES_B200_H
+#define HIFILES_B200_H
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct hf_ctx hf_ctx;
+
+#define HF_MAX_RK 16
+#define HF_N_ELE_TYPES 5   /* 0 tri, 1 quad, 2 tet, 3 prism, 4 hex (reference include/global.h:44-51) */
+#define HF_N_INTER_TYPES 3 /* 0 segment, 1 triangle, 2 quad face (reference src/inters.cpp:58-98) */
+
+/* run_input fields the hot path reads (reference include/input.h; set in src/input.cpp:75-324,527-720). */
+typedef struct hf_params
+{
+  int equation;               /* 0 Euler/Navier-Stokes, 1 advection-diffusion */
+  int viscous;
+  int n_dims;
+  int n_fields;
+  int riemann_solve_type;     /* 0 Rusanov, 1 Lax-Friedrichs, 2 RoeM, 3 HLLC (reference src/int_inters.cpp:187-214) */
+  int vis_riemann_solve_type; /* 0 LDG */
+  int adv_type;               /* 0 Euler, 1 SSP-RK24, 2 SSP-RK34, 3 RK45, 4 RK414 (reference src/eles.cpp:1080-1265) */
+  int dt_type;                /* 0 fixed, 1 global CFL, 2 local CFL */
+  int fix_vis;
+  int order;
+  double gamma, prandtl, mu_inf, rt_inf, c_sth;
+  double ldg_beta, ldg_tau;
+  double dt, CFL;
+  double R_ref, T_ref_placeholder;
+  double wave_speed[3], diff_coeff, lambda;
+  int n_rk;
+  double RK_a[HF_MAX_RK], RK_b[HF_MAX_RK];
+} hf_params;
+
+/* One element type (mirror of class eles, reference include/eles.h; storage src/eles.cpp:100-213). */
+typedef struct hf_eles_desc
+{
+  int ele_type, n_eles, n_upts_per_ele, n_fpts_per_ele, n_dims, n_fields, order, n_inters_per_ele;
+  const int *n_fpts_per_inter; /* [n_inters_per_ele] */
+  /* dense operators, column-major (reference src/eles.cpp:3074-3596); opp_4..6 may be NULL when !viscous */
+  const double *opp_0;    /* [n_fpts x n_upts] */
+  const double *opp_1[3]; /* [n_fpts x n_upts] per dim */
+  const double *opp_2[3]; /* [n_upts x n_upts] per dim */
+  const double *opp_3;    /* [n_upts x n_fpts] */
+  const double *opp_4[3]; /* [n_upts x n_upts] per dim */
+  const double *opp_5[3]; /* [n_upts x n_fpts] per dim */
+  const double *opp_6;    /* [n_fpts x n_upts] */
+  /* metrics (reference src/eles.cpp:4035-4393) */
+  const double *detjac_upts; /* (upt,ele) */
+  const double *JGinv_upts;  /* (l,m,upt,ele) */
+  const double *detjac_fpts; /* (fpt,ele) */
+  const double *JGinv_fpts;  /* (l,m,fpt,ele) */
+  const double *tdA_fpts;    /* (fpt,ele) */
+  const double *norm_fpts;   /* (fpt,ele,dim) */
+  const double *h_ref;       /* (ele) or NULL; only for dt_type != 0 */
+  const double *disu_upts0;  /* (upt,ele,field) initial solution, or NULL (zero) */
+} hf_eles_desc;
+
+/* Interior interfaces of one face type (mirror of int_inters::set_interior, reference src/int_inters.cpp:67-121).
+ * The reference bakes double* tables; here the same getter arithmetic (reference src/eles.cpp:4638-4871) is
+ * done on the device side from these per-interface integers. */
+typedef struct hf_int_inters_desc
+{
+  int inter_type, n_inters, n_fpts_per_inter;
+  const int *ele_type_l, *ele_l, *local_inter_l;
+  const int *ele_type_r, *ele_r, *local_inter_r;
+  const int *rot_tag;
+} hf_int_inters_desc;
+
+/* Boundary parameter table entry (mirror of class bc after non-dimensionalisation, reference include/bc.h,
+ * src/input.cpp:329-525).  bc_flag follows enum BCFLAG (reference include/global.h:55-69). */
+typedef struct hf_bc
+{
+  int bc_flag;
+  double rho, velocity[3], p_static, T_static, p_total, T_total, mach, nx, ny, nz;
+} hf_bc;
+
+/* Boundary interfaces of one face type (mirror of bdy_inters::set_boundary, reference src/bdy_inters.cpp:75-178). */
+typedef struct hf_bdy_inters_desc
+{
+  int inter_type, n_inters, n_fpts_per_inter;
+  const int *ele_type_l, *ele_l, *local_inter_l;
+  const int *bc_id;         /* index into the hf_bc table, per interface */
+  const double *pos_fpts;   /* (fpt,inter,dim) physical flux-point coordinates, or NULL */
+} hf_bdy_inters_desc;
+
+/* Partition ("MPI") interfaces of one face type (mirror of mpi_inters::set_mpi + set_nout_proc, reference
+ * src/mpi_inters.cpp:154-215; ordering per neighbour as built by match_mpifaces, reference src/geometry.cpp:1132-1251). */
+typedef struct hf_mpi_inters_desc
+{
+  int inter_type, n_inters, n_fpts_per_inter;
+  const int *ele_type_l, *ele_l, *local_inter_l, *rot_tag;
+  int n_neighbours;
+  const int *neighbour_rank;  /* [n_neighbours] */
+  const int *neighbour_count; /* [n_neighbours] interfaces exchanged with that rank, contiguous slices */
+} hf_mpi_inters_desc;
+
+/* which-array selectors for hf_dev_download / hf_dev_upload */
+enum hf_array_id
+{
+  HF_DISU_UPTS0 = 0, HF_DISU_UPTS1 = 1, HF_DIV_TCONF_UPTS = 2, HF_DISU_FPTS = 3, HF_TDISF_UPTS = 4,
+  HF_NORM_TDISF_FPTS = 5, HF_NORM_TCONF_FPTS = 6, HF_DELTA_DISU_FPTS = 7, HF_GRAD_DISU_UPTS = 8,
+  HF_GRAD_DISU_FPTS = 9, HF_SRC_UPTS = 10, HF_DT_LOCAL = 11
+};
+
+/* element operations = the eles methods CalcResidual calls (reference src/solver.cpp:65-216) */
+enum hf_eles_op
+{
+  HF_EXTRAPOLATE_SOLUTION = 0,       /* eles::extrapolate_solution          reference src/eles.cpp:1360 */
+  HF_CALCULATE_GRADIENT = 1,         /* eles::calculate_gradient            reference src/eles.cpp:1823 */
+  HF_EVALUATE_INVFLUX = 2,           /* eles::evaluate_invFlux              reference src/eles.cpp:1415 */
+  HF_CORRECT_GRADIENT = 3,           /* eles::correct_gradient              reference src/eles.cpp:1890 */
+  HF_EVALUATE_VISCFLUX = 4,          /* eles::evaluate_viscFlux             reference src/eles.cpp:2285 */
+  HF_EXTRAPOLATE_TOTALFLUX = 5,      /* eles::extrapolate_totalFlux         reference src/eles.cpp:1549 */
+  HF_CALCULATE_DIVERGENCE = 6,       /* eles::calculate_divergence          reference src/eles.cpp:1651 */
+  HF_CALCULATE_CORRECTED_DIVERGENCE = 7 /* eles::calculate_corrected_divergence reference src/eles.cpp:1738 */
+};
+enum hf_inters_op
+{
+  HF_COMMON_INVFLUX = 0, /* int_inters::calculate_common_invFlux / bdy_inters::evaluate_boundaryConditions_invFlux */
+  HF_COMMON_VISCFLUX = 1 /* int_inters::calculate_common_viscFlux / bdy_inters::evaluate_boundaryConditions_viscFlux */
+};
+
+/* ---- life cycle -------------------------------------------------------------------------------------- */
+int hf_dev_create(hf_ctx **out, int device, int rank, int nproc);
+int hf_dev_destroy(hf_ctx *ctx);
+const char *hf_dev_last_error(void);
+/* Use an externally created CUDA stream (cudaStream_t passed as void*) as the compute stream. */
+int hf_dev_set_stream(hf_ctx *ctx, void *cuda_stream);
+/* Join an NCCL communicator: unique_id is the 128-byte ncclUniqueId produced on rank 0 by hf_dev_nccl_unique_id. */
+int hf_dev_nccl_unique_id(void *unique_id_128_bytes);
+int hf_dev_nccl_init(hf_ctx *ctx, const void *unique_id_128_bytes);
+
+/* ---- setup (replaces eles::mv_all_cpu_gpu, int_inters::mv_all_cpu_gpu, ...) ---------------------------- */
+int hf_dev_set_params(hf_ctx *ctx, const hf_params *p);
+int hf_dev_upload_eles(hf_ctx *ctx, const hf_eles_desc *d);
+int hf_dev_upload_int_inters(hf_ctx *ctx, const hf_int_inters_desc *d);
+int hf_dev_set_bc_table(hf_ctx *ctx, int n_bc, const hf_bc *table);
+int hf_dev_upload_bdy_inters(hf_ctx *ctx, const hf_bdy_inters_desc *d);
+int hf_dev_upload_mpi_inters(hf_ctx *ctx, const hf_mpi_inters_desc *d);
+/* Call once after all uploads: builds element-face neighbour tables, tensor-product operator tables, buffers. */
+int hf_dev_finalize_setup(hf_ctx *ctx);
+
+/* ---- the hot path --------------------------------------------------------------------------------------- */
+/* CalcResidual(in_file_num, in_rk_stage, FlowSol)  (reference src/solver.cpp:50-223): result in div_tconf_upts. */
+int hf_dev_calc_residual(hf_ctx *ctx, int rk_stage, double time);
+/* eles::AdvanceSolution(in_step, adv_type) for every element type (reference src/eles.cpp:1080-1265). */
+int hf_dev_advance_solution(hf_ctx *ctx, int rk_stage);
+/* CalcResidual + AdvanceSolution of one stage as fused kernels (no div_tconf_upts round trip unless keep_residual). */
+int hf_dev_rk_stage(hf_ctx *ctx, int rk_stage, double time, int keep_residual);
+/* n_steps full time steps (all RK stages each), fused path, no host synchronisation inside. */
+int hf_dev_run_steps(hf_ctx *ctx, int n_steps, double time0);
+/* Individual methods, for per-operator parity tests and for hosts that keep the reference's call sequence. */
+int hf_dev_eles_op(hf_ctx *ctx, int ele_type, int op);
+int hf_dev_int_inters_op(hf_ctx *ctx, int inter_type, int op);
+int hf_dev_bdy_inters_op(hf_ctx *ctx, int inter_type, int op, double time);
+int hf_dev_mpi_inters_op(hf_ctx *ctx, int inter_type, int op);
+/* calc_time_step (reference src/solver.cpp:484-549): returns the global dt (dt_type 1) or fills dt_local (2). */
+int hf_dev_calc_dt(hf_ctx *ctx, double *dt_out);
+int hf_dev_set_dt(hf_ctx *ctx, double dt);
+
+/* ---- data movement (replaces hf_array::cp_gpu_cpu / cp_cpu_gpu and eles::cp_*_gpu_cpu) ------------------- */
+int hf_dev_download(hf_ctx *ctx, int ele_type, int which, double *host, size_t n_doubles);
+int hf_dev_upload(hf_ctx *ctx, int ele_type, int which, const double *host, size_t n_doubles);
+/* eles::compute_res_upts summed over element types as output::CalcNormResidual does (reference
+ * src/eles.cpp:5045-5074, src/output.cpp:2166-2248); out[n_fields]. Local to this rank (no collective). */
+int hf_dev_residual_norm(hf_ctx *ctx, int norm_type, double *out);
+int hf_dev_sync(hf_ctx *ctx);
+/* kernels launched by this context since creation (bench.py reports the delta as gpu_launches) */
+long long hf_dev_launch_count(hf_ctx *ctx);
+/* select kernel family: 0 = staged reference-order kernels for every element type, 1 = fused tensor-product
+ * kernels where available (default 1). */
+int hf_dev_set_mode(hf_ctx *ctx, int fused);
+/* CUDA-event timing on the compute stream: start/stop bracket, elapsed in milliseconds. */
+int hf_dev_timer_start(hf_ctx *ctx);
+int hf_dev_timer_stop(hf_ctx *ctx, float *ms);
+/* Per-launch CUDA-event timing of the dominant kernel (the fused residual kernel; in staged mode the operator
+ * kernel): mode 1 = start collecting, 0 = stop, -1 = read. ms_total / n_launches cover the launches since mode 1. */
+int hf_dev_kernel_timer(hf_ctx *ctx, int mode, double *ms_total, long long *n_launches);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
