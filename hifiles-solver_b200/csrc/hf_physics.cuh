@@ -329,7 +329,9 @@ template <int NF>
 __device__ __forceinline__ void ldg_solution_int(const double *u_l, const double *u_r, double *u_c, double beta)
 {
 #pragma unroll
-  for (int k = 0; k < NF; k++) u_c[k] = 0.5 * (u_l[k] + u_r[k]) - beta * (u_l[k] - u_r[k]);
+  // no FMA contraction here: delta = u_c - u_l is a difference of nearly equal numbers, and with |beta| = 1/2 the
+  // reference's separately rounded product makes u_c equal one of the two states to the last bit
+  for (int k = 0; k < NF; k++) u_c[k] = __dsub_rn(__dmul_rn(0.5, __dadd_rn(u_l[k], u_r[k])), __dmul_rn(beta, __dsub_rn(u_l[k], u_r[k])));
 }
 
 // flux_spec 0 (interior / partition): f_c = (1/2+beta) f_l + (1/2-beta) f_r ; flux_spec 1 (boundary): f_c = f_r

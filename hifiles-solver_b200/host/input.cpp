@@ -141,6 +141,17 @@ void input::setup(const char *fileNameC, int rank)
 {
   fileNameS.assign(fileNameC);
   read_input_file(fileNameS, rank);
+  // The reference opens mesh_file relative to the working directory.  Embedding hosts (tests, bench) do not chdir:
+  // when that path does not exist, fall back to the directory of the input file.
+  if (!mesh_file.empty() && mesh_file[0] != '/' && !std::ifstream(mesh_file.c_str()).good())
+  {
+    size_t slash = fileNameS.find_last_of('/');
+    if (slash != string::npos)
+    {
+      string alt = fileNameS.substr(0, slash + 1) + mesh_file;
+      if (std::ifstream(alt.c_str()).good()) mesh_file = alt;
+    }
+  }
   setup_params(rank);
 }
 

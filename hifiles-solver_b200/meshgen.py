@@ -1,0 +1,192 @@
+"""Synthetic structured meshes in the Gambit neutral (.neu) format the reference reads (reference
+src/mesh_reader.cpp:105-393), and matching input files.  Used by the tests, smoke() and bench.py: the reference's own
+64^3 / 32^3 Taylor-Green meshes are not shipped (testcases/.../.MISSING_LARGE_BLOBS), only the 15^3 one.
+
+Record formats follow the shipped Taylor-Green-Vortex-hex.neu: 6-line header + counts line, `id x y z` node lines,
+`id 4 8 n1..n7 \\n n8` brick records (node order -> internal shape slots 0,2,4,6,1,3,5,7, mesh_reader.cpp:240-241),
+`id 2 4 n1..n4` quad records (slots 0,1,3,2, :205-206), and boundary sets of `cell type face` triples with Gambit face
+ids (hex: 1..6 -> local faces 0,3,5,1,4,2, :336-350; quad: k-1, :333-334)."""
+import io
+import os
+
+import numpy as np
+
+
+def _header(name, n_nodes, n_cells, n_bsets, ndim):
+    return ("        CONTROL INFO 2.3.16\n** GAMBIT NEUTRAL FILE\n%s\nPROGRAM:                Gambit     VERSION:  2.3.16\n\n"
+            "     NUMNP     NELEM     NGRPS    NBSETS     NDFCD     NDFVL\n%10d%10d%10d%10d%10d%10d\nENDOFSECTION\n"
+            % (name, n_nodes, n_cells, 1, n_bsets, ndim, ndim))
+
+
+def _write_rows(f, arr, fmt):
+    buf = io.StringIO()
+    np.savetxt(buf, arr, fmt=fmt)
+    f.write(buf.getvalue())
+
+
+def _group(f, n_cells):
+    f.write("       ELEMENT GROUP 2.3.16\nGROUP:          1 ELEMENTS: %10d MATERIAL:          2 NFLAGS:          1\n"
+            "                           fluid\n       0\n" % n_cells)
+    ids = np.arange(1, n_cells + 1)
+    pad = (-n_cells) % 10
+    rows = np.concatenate([ids, np.zeros(pad, dtype=ids.dtype)]).reshape(-1, 10)
+    buf = io.StringIO()
+    np.savetxt(buf, rows[:-1] if pad else rows, fmt="%8d")
+    f.write(buf.getvalue())
+    if pad:
+        f.write("".join("%8d" % v for v in rows[-1][:10 - pad]) + "\n")
+    f.write("ENDOFSECTION\n")
+
+
+def hex_box(path, n, lengths=(2 * np.pi, 2 * np.pi, 2 * np.pi), bcs=None, origin=(0., 0., 0.), warp=0.0):
+    """n = N or (Nx,Ny,Nz) linear bricks on a box.  bcs maps side ('x-','x+','y-','y+','z-','z+') -> boundary-group
+    name; default: every side in one group 'Cyclic'.  warp > 0 displaces interior nodes smoothly (non-affine elements;
+    boundary nodes stay put so periodic pairing still holds)."""
+    if np.isscalar(n):
+        n = (n, n, n)
+    nx, ny, nz = n
+    if bcs is None:
+        bcs = {s: "Cyclic" for s in ("x-", "x+", "y-", "y+", "z-", "z+")}
+    px, py, pz = nx + 1, ny + 1, nz + 1
+    gx, gy, gz = np.meshgrid(np.arange(px), np.arange(py), np.arange(pz), indexing="ij")
+    x = origin[0] + lengths[0] * gx / nx
+    y = origin[1] + lengths[1] * gy / ny
+    z = origin[2] + lengths[2] * gz / nz
+    if warp:
+        sx, sy, sz = np.sin(np.pi * gx / nx), np.sin(np.pi * gy / ny), np.sin(np.pi * gz / nz)
+        bump = warp * sx * sy * sz
+        x = x + bump * lengths[0] / nx * np.sin(2 * np.pi * gy / ny + 0.3)
+        y = y + bump * lengths[1] / ny * np.sin(2 * np.pi * gz / nz + 0.7)
+        z = z + bump * lengths[2] / nz * np.sin(2 * np.pi * gx / nx + 1.1)
+    nid = 1 + gx + px * (gy + py * gz)  # node id (1-based), x fastest
+    order = np.argsort(nid.ravel())
+    nodes = np.column_stack([nid.ravel()[order], x.ravel()[order], y.ravel()[order], z.ravel()[order]])
+
+    cx, cy, cz = np.meshgrid(np.arange(nx), np.arange(ny), np.arange(nz), indexing="ij")
+    cid = 1 + cx + nx * (cy + ny * cz)  # cell id (1-based), x fastest
+    corner = lambda dx, dy, dz: nid[cx + dx, cy + dy, cz + dz]
+    # file node m -> internal slot [0,2,4,6,1,3,5,7][m]; slot = ix + 2*iy + 4*iz
+    conn = np.stack([cid, np.full_like(cid, 4), np.full_like(cid, 8),
+                     corner(0, 0, 0), corner(0, 1, 0), corner(0, 0, 1), corner(0, 1, 1),
+                     corner(1, 0, 0), corner(1, 1, 0), corner(1, 0, 1), corner(1, 1, 1)], axis=-1).reshape(-1, 11)
+    conn = conn[np.argsort(conn[:, 0])]
+
+    side_faces = {
+        "z-": (cid[:, :, 0], 1), "y+": (cid[:, ny - 1, :], 2), "z+": (cid[:, :, nz - 1], 3),
+        "y-": (cid[:, 0, :], 4), "x-": (cid[0, :, :], 5), "x+": (cid[nx - 1, :, :], 6)}
+    groups = {}
+    for side, name in bcs.items():
+        cells, k = side_faces[side]
+        rows = np.column_stack([np.sort(cells.ravel()), np.full(cells.size, 4), np.full(cells.size, k)])
+        groups.setdefault(name, []).append(rows)
+
+    with open(path, "w") as f:
+        f.write(_header(os.path.basename(path), nodes.shape[0], conn.shape[0], len(groups), 3))
+        f.write("   NODAL COORDINATES 2.3.16\n")
+        _write_rows(f, nodes, "%10d %19.16e %19.16e %19.16e")
+        f.write("ENDOFSECTION\n      ELEMENTS/CELLS 2.3.16\n")
+        buf = io.StringIO()
+        np.savetxt(buf, conn, fmt="%8d %2d %2d %8d%8d%8d%8d%8d%8d%8d\n               %8d")
+        f.write(buf.getvalue())
+        f.write("ENDOFSECTION\n")
+        _group(f, conn.shape[0])
+        for name, parts in groups.items():
+            rows = np.concatenate(parts)
+            f.write(" BOUNDARY CONDITIONS 2.3.16\n%32s%8d%8d%8d%8d\n" % (name, 1, rows.shape[0], 0, 6))
+            _write_rows(f, rows, "%10d%5d%5d")
+            f.write("ENDOFSECTION\n")
+    return dict(n_cells=conn.shape[0], n_nodes=nodes.shape[0])
+
+
+def quad_box(path, n, lengths=(20., 20.), bcs=None, origin=(-10., -10.), warp=0.0):
+    """n = N or (Nx,Ny) linear quads.  bcs maps side ('x-','x+','y-','y+') -> boundary-group name (default 'Cyclic')."""
+    if np.isscalar(n):
+        n = (n, n)
+    nx, ny = n
+    if bcs is None:
+        bcs = {s: "Cyclic" for s in ("x-", "x+", "y-", "y+")}
+    px, py = nx + 1, ny + 1
+    gx, gy = np.meshgrid(np.arange(px), np.arange(py), indexing="ij")
+    x = origin[0] + lengths[0] * gx / nx
+    y = origin[1] + lengths[1] * gy / ny
+    if warp:
+        bump = warp * np.sin(np.pi * gx / nx) * np.sin(np.pi * gy / ny)
+        x = x + bump * lengths[0] / nx * np.sin(2 * np.pi * gy / ny + 0.3)
+        y = y + bump * lengths[1] / ny * np.sin(2 * np.pi * gx / nx + 0.7)
+    nid = 1 + gx + px * gy
+    order = np.argsort(nid.ravel())
+    nodes = np.column_stack([nid.ravel()[order], x.ravel()[order], y.ravel()[order]])
+    cx, cy = np.meshgrid(np.arange(nx), np.arange(ny), indexing="ij")
+    cid = 1 + cx + nx * cy
+    corner = lambda dx, dy: nid[cx + dx, cy + dy]
+    conn = np.stack([cid, np.full_like(cid, 2), np.full_like(cid, 4), corner(0, 0), corner(1, 0), corner(1, 1), corner(0, 1)], axis=-1).reshape(-1, 7)
+    conn = conn[np.argsort(conn[:, 0])]
+    side_faces = {"y-": (cid[:, 0], 1), "x+": (cid[nx - 1, :], 2), "y+": (cid[:, ny - 1], 3), "x-": (cid[0, :], 4)}
+    groups = {}
+    for side, name in bcs.items():
+        cells, k = side_faces[side]
+        rows = np.column_stack([np.sort(cells.ravel()), np.full(cells.size, 2), np.full(cells.size, k)])
+        groups.setdefault(name, []).append(rows)
+    with open(path, "w") as f:
+        f.write(_header(os.path.basename(path), nodes.shape[0], conn.shape[0], len(groups), 2))
+        f.write("   NODAL COORDINATES 2.3.16\n")
+        _write_rows(f, nodes, "%10d %19.16e %19.16e")
+        f.write("ENDOFSECTION\n      ELEMENTS/CELLS 2.3.16\n")
+        _write_rows(f, conn, "%8d %2d %2d %8d%8d%8d%8d")
+        f.write("ENDOFSECTION\n")
+        _group(f, conn.shape[0])
+        for name, parts in groups.items():
+            rows = np.concatenate(parts)
+            f.write(" BOUNDARY CONDITIONS 2.3.16\n%32s%8d%8d%8d%8d\n" % (name, 1, rows.shape[0], 0, 6))
+            _write_rows(f, rows, "%10d%5d%5d")
+            f.write("ENDOFSECTION\n")
+    return dict(n_cells=conn.shape[0], n_nodes=nodes.shape[0])
+
+
+# ---- input files -------------------------------------------------------------------------------------------------------
+_TGV_DEFAULTS = dict(
+    equation=0, viscous=1, riemann_solve_type=3, vis_riemann_solve_type=0, ic_form=7, test_case=0, order=4, dt_type=0,
+    dt=1.0e-5, n_steps=1, adv_type=2, LES=0, over_int=0, restart_flag=0, dx_cyclic=6.2831853071795862,
+    dy_cyclic=6.2831853071795862, dz_cyclic=6.2831853071795862, p_res=2, write_type=0, monitor_res_freq=1000000,
+    plot_freq=1000000, restart_dump_freq=1000000, data_file_name="run", res_norm_type=1, error_norm_type=1, res_norm_field=0,
+    upts_type_hexa=0, vcjh_scheme_hexa=1, eta_hexa=0., sparse_hexa=0, upts_type_quad=0, vcjh_scheme_quad=1, eta_quad=0.,
+    sparse_quad=0, upts_type_tri=0, fpts_type_tri=0, vcjh_scheme_tri=1, c_tri=0.0, sparse_tri=0, upts_type_tet=0,
+    fpts_type_tet=0, vcjh_scheme_tet=1, eta_tet=0.0, sparse_tet=0, upts_type_pri_tri=0, upts_type_pri_1d=0,
+    vcjh_scheme_pri_1d=1, eta_pri=0.0, sparse_pri=0, bc_Cyclic_type="cyclic", gamma=1.4, prandtl=0.72, S_gas=120., T_gas=291.15, R_gas=286.9, mu_gas=1.827e-5, fix_vis=1,
+    Mach_free_stream=0.1, L_free_stream=1.0, T_free_stream=300., rho_free_stream=0.0008421095852102401,
+    Mach_c_ic=0.1, nx_c_ic=1., ny_c_ic=0., nz_c_ic=0., T_c_ic=300., rho_c_ic=0.0008421095852102401, ldg_beta=0.5, ldg_tau=0.)
+
+
+def write_input(path, mesh_file, **overrides):
+    """Input file in the reference's `key value` format (reference src/input.cpp:62-327).  Defaults are the shipped
+    Taylor-Green input (testcases/navier-stokes/Taylor_Green_vortex/input_TGV_SD_hex) with BASELINE config 3's changes
+    (order 4, adv_type 2); overrides replace or add keys.  A value of None removes a key."""
+    opts = dict(_TGV_DEFAULTS)
+    opts["mesh_file"] = mesh_file
+    opts.update(overrides)
+    with open(path, "w") as f:
+        for k, v in opts.items():
+            if v is None:
+                continue
+            if isinstance(v, float):
+                f.write("%s %.17g\n" % (k, v))
+            else:
+                f.write("%s %s\n" % (k, v))
+    return path
+
+
+def block_partition(n, blocks):
+    """part[global cell] for an n^3 (or (nx,ny,nz)) hex_box split into blocks=(bx,by,bz) equal bricks: the partition a
+    k-way graph partitioner converges to on a uniform periodic cube."""
+    if np.isscalar(n):
+        n = (n, n, n)
+    cx, cy, cz = np.meshgrid(np.arange(n[0]), np.arange(n[1]), np.arange(n[2]), indexing="ij")
+    cid = cx + n[0] * (cy + n[1] * cz)
+    r = (cx * blocks[0] // n[0]) + blocks[0] * ((cy * blocks[1] // n[1]) + blocks[1] * (cz * blocks[2] // n[2]))
+    part = np.zeros(cid.size, dtype=np.int32)
+    part[cid.ravel()] = r.ravel()
+    return part
+
+
+def blocks_for(nproc):
+    return {1: (1, 1, 1), 2: (2, 1, 1), 4: (2, 2, 1), 8: (2, 2, 2)}[nproc]
