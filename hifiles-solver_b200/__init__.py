@@ -79,6 +79,8 @@ def lib():
     L.hf_dev_set_dt.argtypes = [C.c_void_p, C.c_double]
     L.hf_dev_timer_start.argtypes = [C.c_void_p]
     L.hf_dev_timer_stop.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
+    L.hf_dev_fused_status.argtypes = [C.c_void_p]
+    L.hf_dev_fused_status.restype = C.c_char_p
     L.hf_dev_kernel_timer.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_longlong)]
     _lib = L
     return L
@@ -221,6 +223,9 @@ class Run:
 
     def set_mode(self, fused):
         self._ckd(lib().hf_dev_set_mode(self.ctx, 1 if fused else 0))
+
+    def fused_status(self):
+        return lib().hf_dev_fused_status(self.ctx).decode()
 
     def rk_stage(self, stage, time=0.0, keep_residual=False):
         self._ckd(lib().hf_dev_rk_stage(self.ctx, stage, time, 1 if keep_residual else 0))

@@ -601,6 +601,7 @@ int hf_dev_destroy(hf_ctx *c)
   cudaSetDevice(c->device);
   cudaDeviceSynchronize();
   hf_halo_destroy(c);
+  hf_fused_destroy(c);
   for (void *p : c->allocs) cudaFree(p);
   for (cudaEvent_t ev : c->kt_ev) cudaEventDestroy(ev);
   if (c->ev_a) cudaEventDestroy(c->ev_a);
@@ -698,6 +699,7 @@ int hf_dev_upload_eles(hf_ctx *c, const hf_eles_desc *d)
     if (hf_alloc_zero(c, &e.grad_disu_fpts, NFP * F * nd)) return 1;
   }
   // tdisf_upts, norm_tdisf_fpts, grad_disu_upts are only needed by the staged path: allocated lazily
+  if (c->fused && hf_fused_on_upload(c, e, d)) return 1;
   return 0;
 }
 
@@ -1211,7 +1213,9 @@ int hf_dev_download(hf_ctx *c, int ele_type, int which, double *host, size_t n_d
   if (n_doubles != n) HF_FAIL("download: size mismatch");
   if (which == HF_SRC_UPTS) { memset(host, 0, n * sizeof(double)); return 0; } // no source terms on the in-scope path
   if (!p) HF_FAIL("download: array is not materialised on the device in the current mode");
-  if (which == HF_DISU_FPTS && c->fused && hf_fused_available(c) && !c->ufpts_valid && hf_fused_extrapolate(c)) return 1;
+  // the fused path keeps face values in its own per-face layout: materialise the reference-layout array on request
+  if (which == HF_DISU_FPTS && c->fused && hf_fused_available(c) &&
+      op_apply(c, ell1(e.opp_0), e.disu_upts[0], 0, e.disu_fpts, (long long)e.n_eles * e.n_fields, false)) return 1;
   HF_CUDA(cudaMemcpyAsync(host, p, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
   HF_CUDA(cudaStreamSynchronize(c->stream));
   return 0;

@@ -62,6 +62,11 @@ struct hf_eles_dev
   int8_t *face_info = nullptr;  // (face,ele): bits 0-2 rot tag, bit 3 = this element is the right side, bit 4 = boundary/partition
   int8_t *beta_sign = nullptr;  // (fpt,ele): +1 / -1 sign applied to ldg_beta at this flux point (from the LEFT normal)
   std::vector<double> h_op[16]; // host copies of dense operators (kept for table extraction)
+  // host-side extracts made at upload time for the fused path (hf_fused.cu)
+  std::vector<double> h_em;        // per element: JGinv(l,m) at point 0 (ND*ND), detjac
+  std::vector<double> h_face_geo;  // per (ele, face): tdA, unit normal[3] at the face's first flux point
+  std::vector<int8_t> h_own_sign;  // (fpt,ele): sign of ldg_beta if this element is the left side of the face
+  double affine_defect = 0.;       // max relative variation of the metrics inside an element
 };
 
 struct hf_int_inters_dev
@@ -119,6 +124,7 @@ struct hf_ctx
   long long launches = 0;
   void *nccl_comm = nullptr;
   bool halo_pending = false;
+  struct hf_fused_state *fz = nullptr; // fused-path state (hf_fused.cu)
   // per-launch timing of the dominant kernel (bench roofline): event pairs recorded around its launches
   bool ktimer_on = false;
   std::vector<cudaEvent_t> kt_ev; // pool, pairs
@@ -131,6 +137,8 @@ int hf_fused_available(hf_ctx *c);
 int hf_fused_prepare(hf_ctx *c);
 int hf_fused_stage(hf_ctx *c, int rk_stage, double time, int keep_residual, int do_update);
 int hf_fused_extrapolate(hf_ctx *c);
+int hf_fused_on_upload(hf_ctx *c, hf_eles_dev &e, const hf_eles_desc *d);
+void hf_fused_destroy(hf_ctx *c);
 // halo exchange over NCCL (hf_halo.cu): buffers are [inter][...] with `per_inter` doubles per interface, the message
 // to neighbour p is the contiguous slice of its nb_count interfaces (reference src/mpi_inters.cpp:244-255)
 int hf_halo_post(hf_ctx *c, hf_mpi_inters_dev &I, const double *out, double *in, size_t per_inter);

@@ -72,11 +72,11 @@ static void upload_params(struct solution *FlowSol)
 static void upload_all(struct solution *FlowSol)
 {
   upload_params(FlowSol);
+  hf_check(hf_dev_set_mode(FlowSol->ctx, run_input.device_fused));
   for (int i = 0; i < FlowSol->n_ele_types; i++) FlowSol->mesh_eles(i)->mv_all_cpu_gpu();
   for (int i = 0; i < FlowSol->n_int_inter_types; i++) FlowSol->mesh_int_inters[i].mv_all_cpu_gpu();
   for (int i = 0; i < FlowSol->n_bdy_inter_types; i++) FlowSol->mesh_bdy_inters[i].mv_all_cpu_gpu();
   for (int i = 0; i < FlowSol->n_mpi_inter_types; i++) FlowSol->mesh_mpi_inters[i].mv_all_cpu_gpu();
-  hf_check(hf_dev_set_mode(FlowSol->ctx, run_input.device_fused));
   hf_check(hf_dev_finalize_setup(FlowSol->ctx));
 }
 

@@ -189,6 +189,8 @@ long long hf_dev_launch_count(hf_ctx *ctx);
 /* select kernel family: 0 = staged reference-order kernels for every element type, 1 = fused tensor-product
  * kernels where available (default 1). */
 int hf_dev_set_mode(hf_ctx *ctx, int fused);
+/* "available", or the reason the fused kernels cannot be used for this mesh / input (the staged kernels then run) */
+const char *hf_dev_fused_status(hf_ctx *ctx);
 /* CUDA-event timing on the compute stream: start/stop bracket, elapsed in milliseconds. */
 int hf_dev_timer_start(hf_ctx *ctx);
 int hf_dev_timer_stop(hf_ctx *ctx, float *ms);
