@@ -1,0 +1,336 @@
+#!/usr/bin/env python
+"""Benchmark of the HiFiLES per-RK-stage residual hot path on B200 (BASELINE.json config 3).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--n 64] [--order 4] [--impl ours|reference]
+
+One "step" is one full time step of the low-storage SSP-RK34 scheme = 4 passes of the hot path (CalcResidual +
+AdvanceSolution) over the whole mesh; the metric counts scalar DOF-RK-stage updates per second over all GPUs.
+Workload at N = 1: 3-D Taylor-Green vortex, Re 1600, 64^3 linear hexahedra, P = 4, HLLC + LDG, periodic (synthetic mesh
+from hifiles-solver_b200/meshgen.py, analytic initial condition: no dataset involved).  N > 1: the same 64^3 mesh split
+into N bricks (strong scaling), halo exchange over NCCL.
+See DESIGN.md "Measurement" for the definition of every key of the JSON line."""
+import argparse
+import ctypes
+import json
+import os
+import shutil
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+BYTES_PER_DOF_STAGE = {  # algorithmic bytes per DOF-RK-stage (DESIGN.md "Measurement")
+    # a_RK words of state traffic + (Nf/Nu) * (2 + 2*n_dims) face words, 8 bytes each
+    "stage": lambda a_rk, nf_nu, nd, visc: 8.0 * (a_rk + nf_nu * (2 + (2 * nd if visc else 0))),
+    # share of the dominant kernel k_resid: state traffic + write own face u + read neighbour face u + read neighbour grad
+    "k_resid": lambda a_rk, nf_nu, nd, visc: 8.0 * (a_rk + nf_nu * (2 + (nd if visc else 0))),
+}
+A_RK = {0: 2.0, 1: 2.5, 2: 2.5, 3: 4.0, 4: 4.0}
+
+
+def load_package():
+    import conftest
+    return conftest.load_package()
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs"
+        except Exception:
+            pass
+    return 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clock / throttle-reason samples during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx = float(r[1])
+                for nm, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                pass
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_case(workdir, n, order, blocks=(1, 1, 1), **over):
+    hb = load_package()
+    import importlib
+    mg = importlib.import_module("hifiles_solver_b200.meshgen")
+    mesh = os.path.join(workdir, "tgv_%d.neu" % n)
+    if not os.path.exists(mesh):
+        mg.hex_box(mesh, n)
+    # dt: the shipped input's 1.440389e-5 (15^3, P = 1) scaled to stay CFL-stable
+    dt = 1.440389e-5 * (15.0 / n) * (3.0 / (2 * order + 1))
+    opts = dict(order=order, adv_type=2, dt=dt, riemann_solve_type=3, viscous=1)
+    opts.update(over)
+    inp = mg.write_input(os.path.join(workdir, "input_tgv_%d_p%d" % (n, order)), os.path.basename(mesh), **opts)
+    return hb, mg, inp
+
+
+def cpu_reference_rate(order, n_ref, budget_note=""):
+    """Times the UNMODIFIED reference CPU solver (oracle/_ref, serial: the reference has no threading and its MPI build
+    needs MPI + ParMETIS, absent here) on a bounded sample: TGV n_ref^3 hexes, same order and options; rate from the
+    difference between a 3-step and a 1-step run so that setup is excluded."""
+    import util
+    if not util.have_reference():
+        return None
+    work = tempfile.mkdtemp(prefix="hf_cpu_")
+    try:
+        _, _, inp = make_case(work, n_ref, order)
+        env = dict(os.environ, HIFILES_HOME=util.REF_DIR)
+        times = {}
+        for steps in (1, 3):
+            t0 = time.time()
+            r = subprocess.run([util.REF_DUMP, os.path.basename(inp), os.path.join(work, "o.hfd"), str(steps), "0"], cwd=work, env=env,
+                               capture_output=True, text=True)
+            times[steps] = time.time() - t0
+            if r.returncode != 0:
+                return None
+        dof = n_ref ** 3 * (order + 1) ** 3 * 5
+        sec = max(times[3] - times[1], 1e-9)
+        return dict(value=dof * 4 * 2 / sec / 1e9, seconds=sec, sample="TGV %d^3 hex P=%d, 2 time steps (8 RK stages) of the unmodified reference, serial%s"
+                    % (n_ref, order, budget_note), dof=dof)
+    finally:
+        shutil.rmtree(work, ignore_errors=True)
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    res = cpu_reference_rate(args.order, args.cpu_n)
+    n = args.n
+    cfg = {"workload": "3-D Taylor-Green vortex Re=1600, %d^3 hexahedra, P=%d, HLLC+LDG, SSP-RK34" % (n, args.order),
+           "sample": None}
+    if res is None:
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref (compiled reference) is not present"}))
+        return
+    cfg["sample"] = res["sample"]
+    line = {"impl": "reference", "metric": "GDOF-RK-stage updates/s (TGV hex P=%d)" % args.order, "value": res["value"], "unit": "GDOF-stage/s",
+            "n_gpus": args.gpus, "steps": 2, "warmup": 0, "ms_per_step": res["seconds"] / 2 * 1e3, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg,
+            "cpu_baseline": {"value": res["value"], "unit": "GDOF-stage/s", "cores": 1, "kind": "reference", "sample": res["sample"]},
+            "e2e": {"value": res["value"], "unit": "GDOF-stage/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--n", type=int, default=64, help="elements per direction of the global mesh")
+    ap.add_argument("--order", type=int, default=4)
+    ap.add_argument("--impl", default="ours")
+    ap.add_argument("--cpu-n", type=int, default=10, help="elements per direction of the CPU baseline sample")
+    ap.add_argument("--staged", action="store_true", help="time the staged (reference-order) kernels instead of the fused ones")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+
+    import numpy as np
+    import torch
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("--gpus %d needs torchrun with %d ranks" % (args.gpus, args.gpus))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the hot path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    work = os.environ.get("HF_BENCH_DIR") or tempfile.mkdtemp(prefix="hf_bench_")
+    if world > 1:
+        # all ranks must read the same files: rank 0 creates the directory, the others receive its name
+        obj = [work if rank == 0 else None]
+        dist.broadcast_object_list(obj, src=0)
+        work = obj[0]
+    hb = mg = inp = None
+    if rank == 0:
+        hb, mg, inp = make_case(work, args.n, args.order)
+    if world > 1:
+        dist.barrier()
+        if rank != 0:
+            hb, mg, inp = make_case(work, args.n, args.order)
+    part, nccl_id = None, None
+    if world > 1:
+        part = mg.block_partition(args.n, mg.blocks_for(world))
+        idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            idt = torch.tensor(list(hb.nccl_unique_id()), dtype=torch.uint8, device="cuda")
+        dist.broadcast(idt, src=0)
+        nccl_id = bytes(idt.cpu().tolist())
+
+    t_setup = time.time()
+    run = hb.Run(inp, rank=rank, nproc=world, part=part, nccl_id=nccl_id)
+    t_setup = time.time() - t_setup
+    if args.staged:
+        run.set_mode(False)
+    fused = (not args.staged) and run.fused_status() == "available"
+    n_eles = run.n_eles("hex")
+    nu = (args.order + 1) ** 3
+    dof_local = n_eles * nu * 5
+    n_rk = int(run.scalar("n_rk"))
+    adv_type = int(run.scalar("adv_type"))
+
+    def barrier():
+        run.sync()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing ("value") ---------------------------------------------------------------------------
+    for _ in range(args.warmup):
+        run.run(1, fused=True)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    l0 = run.launch_count()
+    barrier()
+    run.timer_start()
+    run.run(args.steps, fused=True)
+    ms = run.timer_stop()
+    barrier()
+    launches = run.launch_count() - l0
+    clocks = sampler.stop() if rank == 0 else None
+    if dist is not None:
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        d = torch.tensor([float(dof_local)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(d)
+        dof_total = float(d.item())
+    else:
+        dof_total = float(dof_local)
+    value = dof_total * n_rk * args.steps / (ms * 1e-3) / 1e9
+
+    # ---- dominant kernel, timed launch by launch with CUDA events on its stream ------------------------------------------
+    roofline = None
+    peak, peak_src = measured_peak()
+    if fused:
+        run.kernel_timer(True)
+        run.run(max(2, args.steps // 2), fused=True)
+        kms, kn = run.kernel_timer(False)
+        per_launch_s = kms * 1e-3 / max(kn, 1)
+        bpd = BYTES_PER_DOF_STAGE["k_resid"](A_RK[adv_type], 6.0 / (args.order + 1), 3, True)
+        ach = dof_local * bpd / per_launch_s / 1e9
+        stage_b = BYTES_PER_DOF_STAGE["stage"](A_RK[adv_type], 6.0 / (args.order + 1), 3, True)
+        roofline = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                    "kernel": "k_resid (fused residual + RK update + next-stage face values)", "launch_ms": per_launch_s * 1e3,
+                    "algorithmic_bytes_per_dof_stage": bpd, "peak_source": peak_src,
+                    "whole_stage": {"algorithmic_bytes_per_dof_stage": stage_b,
+                                    "achieved": (dof_total / world) * n_rk * args.steps / (ms * 1e-3) * stage_b / 1e9,
+                                    "frac": (dof_total / world) * n_rk * args.steps / (ms * 1e-3) * stage_b / 1e9 / peak}}
+        tr = os.path.join(ROOT, "profiles", "traffic_r01.json")
+        if os.path.exists(tr):
+            try:
+                roofline["traffic"] = json.load(open(tr)).get("k_resid_dram_bytes_per_launch")
+            except Exception:
+                pass
+
+    # ---- end to end through the reference-facing API with HOST buffers -----------------------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        lib = hb.lib()
+        shape = (nu, n_eles, 5)
+        nbytes = int(np.prod(shape)) * 8
+        host = torch.empty(int(np.prod(shape)), dtype=torch.float64, pin_memory=True)
+        ctx = run.ctx
+        ck = lambda st: (_ for _ in ()).throw(RuntimeError(lib.hf_dev_last_error().decode())) if st != 0 else None
+        ck(lib.hf_dev_download(ctx, 4, 0, ctypes.c_void_p(host.data_ptr()), host.numel()))
+        e2e_steps = max(2, min(args.steps, 5))
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            ck(lib.hf_dev_upload(ctx, 4, 0, ctypes.c_void_p(host.data_ptr()), host.numel()))  # eles::cp_disu_upts_cpu_gpu
+            run.run(1, fused=True)                                                             # CalcResidual + AdvanceSolution x 4
+            ck(lib.hf_dev_download(ctx, 4, 0, ctypes.c_void_p(host.data_ptr()), host.numel()))  # eles::cp_disu_upts_gpu_cpu
+        barrier()
+        sec = time.perf_counter() - t0
+        if dist is not None:
+            t = torch.tensor([sec], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            sec = float(t.item())
+        e2e = {"value": dof_total * n_rk * e2e_steps / sec / 1e9, "unit": "GDOF-stage/s", "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes,
+               "steps": e2e_steps, "note": "per step: solution host->device from pinned memory, 4 RK stages, solution device->host"}
+
+    res_norm = run.norm_residual()
+    finite = bool(np.all(np.isfinite(res_norm)))
+    run.close()
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        r = cpu_reference_rate(args.order, args.cpu_n)
+        if r is not None:
+            cpu = {"value": r["value"], "unit": "GDOF-stage/s", "cores": 1, "kind": "reference", "sample": r["sample"]}
+
+    if rank == 0:
+        line = {
+            "metric": "GDOF-RK-stage updates/s (TGV hex P=%d)" % args.order, "value": value, "unit": "GDOF-stage/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "3-D Taylor-Green vortex Re=1600, %d^3 hexahedra (global), P=%d, HLLC + LDG(beta=0.5), SSP-RK34, periodic; "
+                                   "1 step = 1 time step = %d RK stages" % (args.n, args.order, n_rk),
+                       "kernels": "fused" if fused else "staged", "elements_per_gpu": n_eles, "dof_total": dof_total,
+                       "l2": "no flush needed: state per GPU %.2f GB >> 126 MB L2" % (dof_local * 8 / 1e9), "setup_s": round(t_setup, 1),
+                       "partition": "bricks %s" % (mg.blocks_for(world),) if world > 1 else "none"},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
+            "residual_finite": finite,
+        }
+        print(json.dumps(line))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    if not os.environ.get("HF_BENCH_DIR") and rank == 0:
+        shutil.rmtree(work, ignore_errors=True)
+
+
+if __name__ == "__main__":
+    main()

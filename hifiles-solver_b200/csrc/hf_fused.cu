@@ -7,9 +7,12 @@
 // reference's numbers):
 //
 //   k_grad   (viscous only)   u -> own face values, LDG common solution with the neighbour's face values, corrected
-//                             physical gradient at solution points, extrapolated to the faces -> fg
+//                             physical gradient at solution points, extrapolated to the faces, and there the element's
+//                             own viscous flux dotted with the face's LEFT normal -> fv (4 values per flux point: the
+//                             LDG common flux is linear in the two one-sided fluxes, so a side only ever needs
+//                             F_vis(u,grad u).n of its neighbour, not the 15 gradient components)
 //                             = eles::calculate_gradient + the LDG half of int_inters::calculate_common_invFlux +
-//                               eles::correct_gradient
+//                               eles::correct_gradient + the one-sided half of calculate_common_viscFlux
 //   k_resid                   the same gradient again (cheaper than storing it), inviscid + viscous flux at solution
 //                             points, common fluxes on all six faces (Riemann + LDG, both sides of a face evaluate the
 //                             same expression with the LEFT element's normal), divergence + correction, RK update,
@@ -18,9 +21,9 @@
 //                               extrapolate_totalFlux + calculate_divergence + calculate_corrected_divergence +
 //                               AdvanceSolution + extrapolate_solution of the next stage
 //
-// Only face data crosses kernels: fu = u at flux points, fg = grad u at flux points, stored per face block
-// [ele][face][(dim)][field][fpt] so that a neighbour's face is one contiguous run and a partition face's receive
-// buffer is simply an extra block behind the last element (message layout = the reference's
+// Only face data crosses kernels: fu = u at flux points (5 fields), fv = one-sided viscous normal flux (4 fields),
+// stored per face block [ele][face][field][fpt] so that a neighbour's face is one contiguous run and a partition
+// face's receive buffer is simply an extra block behind the last element (message layout of fu = the reference's
 // out_buffer_disu[inter][field][fpt], src/mpi_inters.cpp:226-229).
 // Algorithmic traffic per element-stage, P = 4, RK34: see DESIGN.md (about 9 k doubles vs 56 k for the staged path).
 #include "hf_device.h"
@@ -82,6 +85,7 @@ struct fused_tables // small per-order tables, copied to shared memory by every 
   double Lm[6], Lp[6]; // l_i(-1), l_i(+1)                        (from opp_0)
   double c3[36];     // c3[f*N+m]: opp_3 entry of face f at directional index m
   double c5[36];     // c5[f*N+m]: opp_5(dir f) entry
+  unsigned short lbase[216];  // [f*N*N + j]: first solution point of the line behind flux point j of face f
   unsigned char perm[8 * 36]; // [rot + 4*is_right][j] -> neighbour's face-local flux point
 };
 
@@ -100,10 +104,10 @@ struct fused_args
   double *div;            // written when keep_residual
   const double *fu_cur;   // face u, read (neighbours)
   double *fu_next;        // face u of the updated solution, written (own faces)
-  double *fg;             // face gradients: written by k_grad, read by k_resid
+  double *fv;             // one-sided viscous normal flux at flux points: written by k_grad, read by k_resid
   const double *em;       // [ele][EM]
   const int *nbr;         // [ele][6] neighbour face block
-  const signed char *finfo; // [ele][6] rot + 4*is_right
+  const signed char *finfo; // [ele][6] rot + 4*is_right + 8*partition face
   const signed char *bsign; // [ele][6*N*N] sign of ldg_beta
   const double *dt_local;
   const fused_tables *tab;
@@ -125,6 +129,177 @@ struct smem_layout
   int finfo[E][6];
 };
 
+template <int N>
+__device__ __forceinline__ int face_stride(int f)
+{
+  return (f == 0 || f == 5) ? N * N : ((f == 1 || f == 3) ? N : 1);
+}
+
+// ---- pointwise physics of the fused path ------------------------------------------------------------------------------
+// Same formulas as hf_physics.cuh (= reference src/flux.cpp, src/inters.cpp) with the divisions by rho replaced by one
+// reciprocal per state and pow(x,1.5) by x*sqrt(x): results differ from the reference in the last bits only.
+__device__ __forceinline__ void inv_flux_fast(const double *__restrict__ u, double *__restrict__ f, double gm1)
+{
+  const double ir = 1.0 / u[0];
+  const double v0 = u[1] * ir, v1 = u[2] * ir, v2 = u[3] * ir;
+  const double p = gm1 * (u[4] - 0.5 * u[0] * (v0 * v0 + v1 * v1 + v2 * v2));
+  const double ep = u[4] + p;
+  f[0] = u[1];       f[1] = p + u[1] * v0;  f[2] = u[2] * v0;      f[3] = u[3] * v0;      f[4] = v0 * ep;
+  f[5] = u[2];       f[6] = u[1] * v1;      f[7] = p + u[2] * v1;  f[8] = u[3] * v1;      f[9] = v1 * ep;
+  f[10] = u[3];      f[11] = u[1] * v2;     f[12] = u[2] * v2;     f[13] = p + u[3] * v2; f[14] = v2 * ep;
+}
+
+// viscous flux F(k,d) = f[k + 5 d] for k = 1..4 (the mass equation has none); g(k,d) = g[k + 5 d]
+__device__ __forceinline__ void vis_flux_fast(const double *__restrict__ u, const double *__restrict__ g, double *__restrict__ f, const hf_phys &P)
+{
+  const double rho = u[0], ir = 1.0 / u[0];
+  const double v0 = u[1] * ir, v1 = u[2] * ir, v2 = u[3] * ir;
+  const double vsq = v0 * v0 + v1 * v1 + v2 * v2;
+  const double inte = u[4] * ir - 0.5 * vsq;
+  double mu = P.mu_inf;
+  if (P.fix_vis != 1.0)
+  {
+    double rt = (P.gamma - 1.0) * inte / P.rt_inf;
+    mu = P.mu_inf * (rt * sqrt(rt)) * (1. + P.c_sth) / (rt + P.c_sth);
+    mu = mu + P.fix_vis * (P.mu_inf - mu);
+  }
+  double dv[3][3], de[3];
+#pragma unroll
+  for (int d = 0; d < 3; d++)
+  {
+    const double r_d = g[5 * d];
+    dv[0][d] = (g[1 + 5 * d] - r_d * v0) * ir;
+    dv[1][d] = (g[2 + 5 * d] - r_d * v1) * ir;
+    dv[2][d] = (g[3 + 5 * d] - r_d * v2) * ir;
+    const double dke = 0.5 * vsq * r_d + rho * (v0 * dv[0][d] + v1 * dv[1][d] + v2 * dv[2][d]);
+    de[d] = (g[4 + 5 * d] - dke - r_d * inte) * ir;
+  }
+  const double diag = (dv[0][0] + dv[1][1] + dv[2][2]) / 3.0;
+  const double txx = 2.0 * mu * (dv[0][0] - diag), tyy = 2.0 * mu * (dv[1][1] - diag), tzz = 2.0 * mu * (dv[2][2] - diag);
+  const double txy = mu * (dv[0][1] + dv[1][0]), txz = mu * (dv[0][2] + dv[2][0]), tyz = mu * (dv[1][2] + dv[2][1]);
+  const double kap = (mu / P.prandtl) * P.gamma;
+  f[0] = 0.;  f[1] = -txx; f[2] = -txy; f[3] = -txz; f[4] = -(v0 * txx + v1 * txy + v2 * txz + kap * de[0]);
+  f[5] = 0.;  f[6] = -txy; f[7] = -tyy; f[8] = -tyz; f[9] = -(v0 * txy + v1 * tyy + v2 * tyz + kap * de[1]);
+  f[10] = 0.; f[11] = -txz; f[12] = -tyz; f[13] = -tzz; f[14] = -(v0 * txz + v1 * tyz + v2 * tzz + kap * de[2]);
+}
+
+struct side_state
+{
+  double rho, ir, v[3], vn, vsq, p, h, fn[5];
+};
+__device__ __forceinline__ void make_side(const double *__restrict__ u, const double *__restrict__ n, double gm1, side_state &s)
+{
+  s.rho = u[0];
+  s.ir = 1.0 / u[0];
+  s.v[0] = u[1] * s.ir; s.v[1] = u[2] * s.ir; s.v[2] = u[3] * s.ir;
+  s.vn = s.v[0] * n[0] + s.v[1] * n[1] + s.v[2] * n[2];
+  s.vsq = s.v[0] * s.v[0] + s.v[1] * s.v[1] + s.v[2] * s.v[2];
+  s.p = gm1 * (u[4] - 0.5 * u[0] * s.vsq);
+  s.h = (u[4] + s.p) * s.ir;
+  // normal inviscid flux F(u).n
+  s.fn[0] = u[1] * n[0] + u[2] * n[1] + u[3] * n[2];
+  s.fn[1] = u[1] * s.vn + s.p * n[0];
+  s.fn[2] = u[2] * s.vn + s.p * n[1];
+  s.fn[3] = u[3] * s.vn + s.p * n[2];
+  s.fn[4] = s.vn * (u[4] + s.p);
+}
+
+// common inviscid normal flux (reference src/inters.cpp:277-532: rusanov_flux, roeM_flux, hllc_flux)
+__device__ __forceinline__ void riemann_fast(const double *__restrict__ u_l, const double *__restrict__ u_r, const double *__restrict__ n,
+                                             double *__restrict__ fn, const hf_phys &P)
+{
+  const double gamma = P.gamma, gm1 = P.gamma - 1.0;
+  side_state L, R;
+  make_side(u_l, n, gm1, L);
+  make_side(u_r, n, gm1, R);
+  if (P.riemann_solve_type == 3) // HLLC
+  {
+    const double sq_rho = sqrt(R.rho * L.ir);
+    const double rrho = 1. / (sq_rho + 1.);
+    const double vn_m = rrho * (L.vn + sq_rho * R.vn);
+    const double h_m = rrho * (L.h + sq_rho * R.h);
+    const double a_m = sqrt(gm1 * (h_m - 0.5 * vn_m * vn_m));
+    const double S_R = vn_m + a_m, S_L = vn_m - a_m;
+    const double ml = L.rho * (S_L - L.vn), mr = R.rho * (S_R - R.vn);
+    const double S_star = (R.p - L.p + ml * L.vn - mr * R.vn) / (ml - mr);
+    if (S_L >= 0)
+    {
+#pragma unroll
+      for (int k = 0; k < 5; k++) fn[k] = L.fn[k];
+    }
+    else if (S_star >= 0)
+    {
+      const double inv = 1.0 / (S_L - S_star);
+      const double pst = (L.p + ml * (S_star - L.vn));
+      fn[0] = S_star * (S_L * u_l[0] - L.fn[0]) * inv;
+#pragma unroll
+      for (int i = 0; i < 3; i++) fn[i + 1] = (S_star * (S_L * u_l[i + 1] - L.fn[i + 1]) + S_L * pst * n[i]) * inv;
+      fn[4] = (S_star * (S_L * u_l[4] - L.fn[4]) + S_L * pst * S_star) * inv;
+    }
+    else if (S_R >= 0)
+    {
+      const double inv = 1.0 / (S_R - S_star);
+      const double pst = (R.p + mr * (S_star - R.vn));
+      fn[0] = S_star * (S_R * u_r[0] - R.fn[0]) * inv;
+#pragma unroll
+      for (int i = 0; i < 3; i++) fn[i + 1] = (S_star * (S_R * u_r[i + 1] - R.fn[i + 1]) + S_R * pst * n[i]) * inv;
+      fn[4] = (S_star * (S_R * u_r[4] - R.fn[4]) + S_R * pst * S_star) * inv;
+    }
+    else
+    {
+#pragma unroll
+      for (int k = 0; k < 5; k++) fn[k] = R.fn[k];
+    }
+  }
+  else if (P.riemann_solve_type == 0) // Rusanov
+  {
+    const double eig = sqrt(gamma * (L.p + R.p) / (L.rho + R.rho)) + 0.5 * fabs(L.vn + R.vn);
+#pragma unroll
+    for (int k = 0; k < 5; k++) fn[k] = 0.5 * ((L.fn[k] + R.fn[k]) - eig * (u_r[k] - u_l[k]));
+  }
+  else // RoeM
+  {
+    double va[3], dv[3], du[5], bdq[5];
+    const double drho = R.rho - L.rho, dp = R.p - L.p, dh = R.h - L.h, dvn = R.vn - L.vn;
+    const double sq_rho = sqrt(R.rho * L.ir);
+    const double rrho = 1.0 / (1.0 + sq_rho);
+    const double ratr = sq_rho * rrho;
+    const double ra = sq_rho * L.rho;
+    const double ha = L.h * rrho + R.h * ratr;
+    double qq = 0., va_n = 0.;
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+    {
+      dv[i] = R.v[i] - L.v[i];
+      va[i] = L.v[i] * rrho + R.v[i] * ratr;
+      qq += va[i] * va[i];
+      va_n += n[i] * va[i];
+    }
+    const double aa = sqrt(gm1 * (ha - 0.5 * qq));
+    const double rcp_aa = 1.0 / aa;
+    const double abs_ma = fabs(va_n * rcp_aa);
+    double b1 = fmax(0.0, fmax(va_n + aa, R.vn + aa));
+    double b2 = fmin(0.0, fmin(va_n - aa, L.vn - aa));
+    double b1b2 = b1 * b2;
+    const double rcp_b1_b2 = 1.0 / (b1 - b2);
+    b1 = b1 * rcp_b1_b2;
+    b2 = b2 * rcp_b1_b2;
+    b1b2 = b1b2 * rcp_b1_b2;
+    const double hh = 1.0 - ((L.p < R.p) ? (L.p / R.p) : (R.p / L.p));
+    const double ff = ((abs_ma != 0) ? pow(abs_ma, hh) : 1.);
+    const double gg = ff / (1.0 + abs_ma);
+#pragma unroll
+    for (int i = 0; i < 4; i++) du[i] = u_r[i] - u_l[i];
+    du[4] = R.rho * R.h - L.rho * L.h;
+    bdq[0] = drho - ff * dp * rcp_aa * rcp_aa;
+    bdq[4] = bdq[0] * ha + ra * dh;
+#pragma unroll
+    for (int i = 0; i < 3; i++) bdq[i + 1] = bdq[0] * va[i] + ra * (dv[i] - n[i] * dvn);
+#pragma unroll
+    for (int i = 0; i < 5; i++) fn[i] = (b1 * L.fn[i] - b2 * R.fn[i]) + b1b2 * (du[i] - gg * bdq[i]);
+  }
+}
+
 // ---- shared phases ----------------------------------------------------------------------------------------------------
 template <int N, int E, int NT>
 __device__ __forceinline__ void load_block(smem_layout<N, E> &S, const fused_args &A, int e0, int ne)
@@ -139,6 +314,7 @@ __device__ __forceinline__ void load_block(smem_layout<N, E> &S, const fused_arg
     for (int i = tid; i < nd; i += NT) dst[i] = src[i];
   }
   // solution: for a field, the ne elements of this block are contiguous in (upt, ele)
+#pragma unroll
   for (int k = 0; k < NF; k++)
   {
     const double *src = A.u0 + (size_t)NU * (e0 + (size_t)A.n_eles * k);
@@ -170,20 +346,23 @@ __device__ __forceinline__ void phase_delta(smem_layout<N, E> &S, const fused_ar
   for (int q = threadIdx.x; q < ne * NFP; q += NT)
   {
     int e = q / NFP, r = q - e * NFP, f = r / NN, j = r - f * NN;
-    int base, stride;
-    line_of_fpt<N>(f, j, base, stride);
-    const double *L = face_sgn(f) > 0 ? S.tab.Lp : S.tab.Lm;
+    const int base = S.tab.lbase[r], stride = face_stride<N>(f);
+    double L[N];
+#pragma unroll
+    for (int i = 0; i < N; i++) L[i] = face_sgn(f) > 0 ? S.tab.Lp[i] : S.tab.Lm[i];
     int info = S.finfo[e][f];
-    int pj = S.tab.perm[info * 36 + j];
+    int pj = S.tab.perm[(info & 7) * 36 + j];
     const double *nb = A.fu_cur + (size_t)S.nbr[e][f] * (NF * NN) + pj;
     double beta = A.P.ldg_beta * (double)A.bsign[(size_t)(e0 + e) * NFP + r];
-    bool is_right = info >= 4;
+    bool is_right = (info & 4) != 0;
+    double un[NF];
+#pragma unroll
+    for (int k = 0; k < NF; k++) un[k] = nb[k * NN];
 #pragma unroll
     for (int k = 0; k < NF; k++)
     {
       double uo = face_value<N>(S.su[e][k], L, base, stride);
-      double un = nb[k * NN];
-      double ul = is_right ? un : uo, ur = is_right ? uo : un;
+      double ul = is_right ? un[k] : uo, ur = is_right ? uo : un[k];
       double uc = __dsub_rn(__dmul_rn(0.5, __dadd_rn(ul, ur)), __dmul_rn(beta, __dsub_rn(ul, ur)));
       S.sx[e][k][r] = uc - uo;
     }
@@ -199,54 +378,44 @@ __device__ __forceinline__ void phase_gradient(smem_layout<N, E> &S, int ne)
   {
     int e = q / NU, p = q - e * NU;
     int a = p % N, b = (p / N) % N, c = p / NN;
-    const double *J = S.em[e];
-    double inv_detjac = 1.0 / J[9];
+    double J[9];
+#pragma unroll
+    for (int i = 0; i < 9; i++) J[i] = S.em[e][i];
+    const double inv_detjac = 1.0 / S.em[e][9];
+    double Da[N], Db[N], Dc[N];
+#pragma unroll
+    for (int i = 0; i < N; i++) { Da[i] = S.tab.D[a * N + i]; Db[i] = S.tab.D[b * N + i]; Dc[i] = S.tab.D[c * N + i]; }
+    const double c52 = S.tab.c5[2 * N + a], c54 = S.tab.c5[4 * N + a], c51 = S.tab.c5[1 * N + b], c53 = S.tab.c5[3 * N + b],
+                 c50 = S.tab.c5[0 * N + c], c55 = S.tab.c5[5 * N + c];
+    const int f0 = 0 * NN + fpt_of_upt<N>(0, a, b, c), f1 = 1 * NN + fpt_of_upt<N>(1, a, b, c), f2 = 2 * NN + fpt_of_upt<N>(2, a, b, c),
+              f3 = 3 * NN + fpt_of_upt<N>(3, a, b, c), f4 = 4 * NN + fpt_of_upt<N>(4, a, b, c), f5 = 5 * NN + fpt_of_upt<N>(5, a, b, c);
 #pragma unroll
     for (int k = 0; k < NF; k++)
     {
       const double *u = S.su[e][k];
       const double *dl = S.sx[e][k];
-      double gt[3];
-      {
-        double acc = 0.0;
+      double g0 = 0.0, g1 = 0.0, g2 = 0.0;
 #pragma unroll
-        for (int i = 0; i < N; i++) acc += S.tab.D[a * N + i] * u[i + N * b + NN * c];
-        acc += S.tab.c5[2 * N + a] * dl[2 * NN + fpt_of_upt<N>(2, a, b, c)];
-        acc += S.tab.c5[4 * N + a] * dl[4 * NN + fpt_of_upt<N>(4, a, b, c)];
-        gt[0] = acc;
-      }
-      {
-        double acc = 0.0;
+      for (int i = 0; i < N; i++) g0 += Da[i] * u[i + N * b + NN * c];
 #pragma unroll
-        for (int i = 0; i < N; i++) acc += S.tab.D[b * N + i] * u[a + N * i + NN * c];
-        acc += S.tab.c5[1 * N + b] * dl[1 * NN + fpt_of_upt<N>(1, a, b, c)];
-        acc += S.tab.c5[3 * N + b] * dl[3 * NN + fpt_of_upt<N>(3, a, b, c)];
-        gt[1] = acc;
-      }
-      {
-        double acc = 0.0;
+      for (int i = 0; i < N; i++) g1 += Db[i] * u[a + N * i + NN * c];
 #pragma unroll
-        for (int i = 0; i < N; i++) acc += S.tab.D[c * N + i] * u[a + N * b + NN * i];
-        acc += S.tab.c5[0 * N + c] * dl[0 * NN + fpt_of_upt<N>(0, a, b, c)];
-        acc += S.tab.c5[5 * N + c] * dl[5 * NN + fpt_of_upt<N>(5, a, b, c)];
-        gt[2] = acc;
-      }
+      for (int i = 0; i < N; i++) g2 += Dc[i] * u[a + N * b + NN * i];
+      g0 += c52 * dl[f2]; g0 += c54 * dl[f4];
+      g1 += c51 * dl[f1]; g1 += c53 * dl[f3];
+      g2 += c50 * dl[f0]; g2 += c55 * dl[f5];
+      g0 *= inv_detjac; g1 *= inv_detjac; g2 *= inv_detjac;
       // physical gradient: g(d) = sum_l (1/detJ * gt(l)) * JGinv(l,d)    (reference src/eles.cpp:1955-2011)
-#pragma unroll
-      for (int d = 0; d < 3; d++)
-      {
-        double acc = 0.0;
-#pragma unroll
-        for (int l = 0; l < 3; l++) acc += (inv_detjac * gt[l]) * J[l + 3 * d];
-        S.sg[e][d][k][p] = acc;
-      }
+      S.sg[e][0][k][p] = g0 * J[0] + g1 * J[1] + g2 * J[2];
+      S.sg[e][1][k][p] = g0 * J[3] + g1 * J[4] + g2 * J[5];
+      S.sg[e][2][k][p] = g0 * J[6] + g1 * J[7] + g2 * J[8];
     }
   }
 }
 
-// ---- kernel 1: face gradients ------------------------------------------------------------------------------------------
-template <int N, int E, int NT>
-__global__ void __launch_bounds__(NT) k_grad(fused_args A)
+// ---- kernel 1: one-sided viscous normal flux at the faces ---------------------------------------------------------------
+template <int N, int E, int NT, int MINB>
+__global__ void __launch_bounds__(NT, MINB) k_grad(fused_args A)
 {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   smem_layout<N, E> &S = *reinterpret_cast<smem_layout<N, E> *>(smem_raw);
@@ -259,24 +428,34 @@ __global__ void __launch_bounds__(NT) k_grad(fused_args A)
   __syncthreads();
   phase_gradient<N, E, NT>(S, ne);
   __syncthreads();
-  // gradient at the own flux points (opp_6 then the transform; for an affine element the two commute)
+  // u and grad u at the own flux points (opp_0, opp_6; for an affine element extrapolation and the transform to
+  // physical space commute), viscous flux there, dotted with the face's left normal
   for (int q = threadIdx.x; q < ne * NFP; q += NT)
   {
     int e = q / NFP, r = q - e * NFP, f = r / NN, j = r - f * NN;
-    int base, stride;
-    line_of_fpt<N>(f, j, base, stride);
-    const double *L = face_sgn(f) > 0 ? S.tab.Lp : S.tab.Lm;
-    double *out = A.fg + ((size_t)(e0 + e) * 6 + f) * (ND * NF * NN) + j;
+    const int base = S.tab.lbase[r], stride = face_stride<N>(f);
+    double L[N];
+#pragma unroll
+    for (int i = 0; i < N; i++) L[i] = face_sgn(f) > 0 ? S.tab.Lp[i] : S.tab.Lm[i];
+    double u[NF], g[NF * ND], fv[NF * ND];
+#pragma unroll
+    for (int k = 0; k < NF; k++) u[k] = face_value<N>(S.su[e][k], L, base, stride);
 #pragma unroll
     for (int d = 0; d < ND; d++)
 #pragma unroll
-      for (int k = 0; k < NF; k++) out[(d * NF + k) * NN] = face_value<N>(S.sg[e][d][k], L, base, stride);
+      for (int k = 0; k < NF; k++) g[k + NF * d] = face_value<N>(S.sg[e][d][k], L, base, stride);
+    vis_flux_fast(u, g, fv, A.P);
+    const double *n = &S.em[e][10 + 4 * f + 1];
+    const double n0 = n[0], n1 = n[1], n2 = n[2];
+    double *out = A.fv + ((size_t)(e0 + e) * 6 + f) * (4 * NN) + j;
+#pragma unroll
+    for (int k = 1; k < NF; k++) out[(k - 1) * NN] = fv[k] * n0 + fv[k + 5] * n1 + fv[k + 10] * n2;
   }
 }
 
 // ---- kernel 2: residual + RK update + next face values --------------------------------------------------------------------
-template <int N, int E, int NT, bool VISC>
-__global__ void __launch_bounds__(NT) k_resid(fused_args A)
+template <int N, int E, int NT, int MINB, bool VISC>
+__global__ void __launch_bounds__(NT, MINB) k_resid(fused_args A)
 {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   smem_layout<N, E> &S = *reinterpret_cast<smem_layout<N, E> *>(smem_raw);
@@ -291,121 +470,91 @@ __global__ void __launch_bounds__(NT) k_resid(fused_args A)
     __syncthreads();
     phase_gradient<N, E, NT>(S, ne);
     __syncthreads();
-    // own-side viscous normal flux F_vis(u_own, grad_own) . n_left at every own flux point -> S.sx
-    for (int q = threadIdx.x; q < ne * NFP; q += NT)
-    {
-      int e = q / NFP, r = q - e * NFP, f = r / NN, j = r - f * NN;
-      int base, stride;
-      line_of_fpt<N>(f, j, base, stride);
-      const double *L = face_sgn(f) > 0 ? S.tab.Lp : S.tab.Lm;
-      double u[NF], g[NF * ND], fv[NF * ND], fn[NF];
-#pragma unroll
-      for (int k = 0; k < NF; k++) u[k] = face_value<N>(S.su[e][k], L, base, stride);
-#pragma unroll
-      for (int d = 0; d < ND; d++)
-#pragma unroll
-        for (int k = 0; k < NF; k++) g[k + NF * d] = face_value<N>(S.sg[e][d][k], L, base, stride);
-      vis_flux<ND, NF>(u, g, fv, A.P);
-      normal_flux<ND, NF>(fv, &S.em[e][10 + 4 * f + 1], fn);
-#pragma unroll
-      for (int k = 0; k < NF; k++) S.sx[e][k][r] = fn[k];
-    }
-    __syncthreads();
   }
   // transformed total flux at the solution points -> S.sg (overwrites the gradient point by point)
   for (int q = threadIdx.x; q < ne * NU; q += NT)
   {
     int e = q / NU, p = q - e * NU;
-    const double *J = S.em[e];
+    double J[9];
+#pragma unroll
+    for (int i = 0; i < 9; i++) J[i] = S.em[e][i];
     double u[NF], f[NF * ND];
 #pragma unroll
     for (int k = 0; k < NF; k++) u[k] = S.su[e][k][p];
-    inv_flux<ND, NF>(u, f, A.P);
-    double t[NF * ND];
-#pragma unroll
-    for (int k = 0; k < NF; k++)
-#pragma unroll
-      for (int l = 0; l < ND; l++)
-      {
-        double acc = 0.0;
-#pragma unroll
-        for (int m = 0; m < ND; m++) acc += J[l + 3 * m] * f[k + NF * m];
-        t[k + NF * l] = acc;
-      }
+    inv_flux_fast(u, f, A.P.gamma - 1.0);
     if (VISC)
     {
-      double g[NF * ND];
+      double g[NF * ND], fv[NF * ND];
 #pragma unroll
       for (int d = 0; d < ND; d++)
 #pragma unroll
         for (int k = 0; k < NF; k++) g[k + NF * d] = S.sg[e][d][k][p];
-      vis_flux<ND, NF>(u, g, f, A.P);
+      vis_flux_fast(u, g, fv, A.P);
 #pragma unroll
-      for (int k = 0; k < NF; k++)
+      for (int d = 0; d < ND; d++)
 #pragma unroll
-        for (int l = 0; l < ND; l++)
-        {
-          double acc = t[k + NF * l];
-#pragma unroll
-          for (int m = 0; m < ND; m++) acc += J[l + 3 * m] * f[k + NF * m];
-          t[k + NF * l] = acc;
-        }
+        for (int k = 1; k < NF; k++) f[k + NF * d] += fv[k + NF * d];
     }
+    // tdisf(k,l) = sum_m JGinv(l,m) f(k,m)
 #pragma unroll
-    for (int l = 0; l < ND; l++)
+    for (int k = 0; k < NF; k++)
 #pragma unroll
-      for (int k = 0; k < NF; k++) S.sg[e][l][k][p] = t[k + NF * l];
+      for (int l = 0; l < ND; l++) S.sg[e][l][k][p] = J[l] * f[k] + J[l + 3] * f[k + 5] + J[l + 6] * f[k + 10];
   }
   __syncthreads();
   // common flux minus own normal flux at every own flux point -> S.sx
   for (int q = threadIdx.x; q < ne * NFP; q += NT)
   {
     int e = q / NFP, r = q - e * NFP, f = r / NN, j = r - f * NN;
-    int base, stride;
-    line_of_fpt<N>(f, j, base, stride);
+    const int base = S.tab.lbase[r], stride = face_stride<N>(f);
     const int sgn = face_sgn(f), dir = face_dir(f);
-    const double *L = sgn > 0 ? S.tab.Lp : S.tab.Lm;
-    int info = S.finfo[e][f];
-    bool is_right = info >= 4;
-    int pj = S.tab.perm[info * 36 + j];
-    size_t nblk = (size_t)S.nbr[e][f];
+    double L[N];
+#pragma unroll
+    for (int i = 0; i < N; i++) L[i] = sgn > 0 ? S.tab.Lp[i] : S.tab.Lm[i];
+    const int info = S.finfo[e][f];
+    const bool is_right = (info & 4) != 0;
+    const int pj = S.tab.perm[(info & 7) * 36 + j];
+    const size_t nblk = (size_t)S.nbr[e][f];
     const double *geo = &S.em[e][10 + 4 * f];
     const double tdA = geo[0];
     const double n[3] = {geo[1], geo[2], geo[3]};
     double uo[NF], un[NF], fn[NF];
     const double *nb = A.fu_cur + nblk * (NF * NN) + pj;
 #pragma unroll
-    for (int k = 0; k < NF; k++)
-    {
-      uo[k] = face_value<N>(S.su[e][k], L, base, stride);
-      un[k] = nb[k * NN];
-    }
-    if (is_right) riemann<ND, NF>(un, uo, n, fn, A.P);
-    else riemann<ND, NF>(uo, un, n, fn, A.P);
+    for (int k = 0; k < NF; k++) un[k] = nb[k * NN];
+    double fvo[4], fvn[4];
     if (VISC)
     {
-      double g[NF * ND], fv[NF * ND], fvn[NF];
-      const double *ng = A.fg + nblk * (ND * NF * NN) + pj;
+      const double *po = A.fv + ((size_t)(e0 + e) * 6 + f) * (4 * NN) + j;
+      const double *pn = A.fv + nblk * (4 * NN) + pj;
+      const double flip = (info & 8) ? -1.0 : 1.0; // a partition neighbour used its own (opposite) normal
 #pragma unroll
-      for (int q2 = 0; q2 < NF * ND; q2++) g[q2] = ng[q2 * NN];
-      vis_flux<ND, NF>(un, g, fv, A.P);
-      normal_flux<ND, NF>(fv, n, fvn);
-      double beta = A.P.ldg_beta * (double)A.bsign[(size_t)(e0 + e) * NFP + r];
+      for (int k = 0; k < 4; k++) { fvo[k] = po[k * NN]; fvn[k] = flip * pn[k * NN]; }
+    }
 #pragma unroll
-      for (int k = 0; k < NF; k++)
+    for (int k = 0; k < NF; k++) uo[k] = face_value<N>(S.su[e][k], L, base, stride);
+    if (is_right) riemann_fast(un, uo, n, fn, A.P);
+    else riemann_fast(uo, un, n, fn, A.P);
+    if (VISC)
+    {
+      const double beta = A.P.ldg_beta * (double)A.bsign[(size_t)(e0 + e) * NFP + r];
+      const double wl = 0.5 + beta, wr = 0.5 - beta, tau = A.P.ldg_tau;
+      fn[0] -= tau * (is_right ? uo[0] - un[0] : un[0] - uo[0]);
+#pragma unroll
+      for (int k = 1; k < NF; k++)
       {
-        double fo = S.sx[e][k][r];
-        double fl = is_right ? fvn[k] : fo, fr = is_right ? fo : fvn[k];
-        double ul = is_right ? un[k] : uo[k], ur = is_right ? uo[k] : un[k];
-        fn[k] += ((0.5 + beta) * fl + (0.5 - beta) * fr) - A.P.ldg_tau * (ur - ul);
+        const double fl = is_right ? fvn[k - 1] : fvo[k - 1], fr = is_right ? fvo[k - 1] : fvn[k - 1];
+        const double du = is_right ? uo[k] - un[k] : un[k] - uo[k];
+        fn[k] += (wl * fl + wr * fr) - tau * du;
       }
     }
     const double s_side = is_right ? -tdA : tdA;
+    const double s_ntd = sgn > 0 ? 1.0 : -1.0;
 #pragma unroll
     for (int k = 0; k < NF; k++)
     {
       double ntd = face_value<N>(S.sg[e][dir][k], L, base, stride);
-      S.sx[e][k][r] = fn[k] * s_side - (sgn > 0 ? ntd : -ntd);
+      S.sx[e][k][r] = fn[k] * s_side - s_ntd * ntd;
     }
   }
   __syncthreads();
@@ -415,31 +564,34 @@ __global__ void __launch_bounds__(NT) k_resid(fused_args A)
     int e = q / NU, p = q - e * NU;
     int a = p % N, b = (p / N) % N, c = p / NN;
     const int ge = e0 + e;
-    const double detjac = S.em[e][9];
+    const double inv_detjac = 1.0 / S.em[e][9];
     const double dtl = A.dt_local ? A.dt_local[ge] : A.rk.dt;
+    double Da[N], Db[N], Dc[N];
+#pragma unroll
+    for (int i = 0; i < N; i++) { Da[i] = S.tab.D[a * N + i]; Db[i] = S.tab.D[b * N + i]; Dc[i] = S.tab.D[c * N + i]; }
+    const double c30 = S.tab.c3[0 * N + c], c31 = S.tab.c3[1 * N + b], c32 = S.tab.c3[2 * N + a], c33 = S.tab.c3[3 * N + b],
+                 c34 = S.tab.c3[4 * N + a], c35 = S.tab.c3[5 * N + c];
+    const int f0 = 0 * NN + fpt_of_upt<N>(0, a, b, c), f1 = 1 * NN + fpt_of_upt<N>(1, a, b, c), f2 = 2 * NN + fpt_of_upt<N>(2, a, b, c),
+              f3 = 3 * NN + fpt_of_upt<N>(3, a, b, c), f4 = 4 * NN + fpt_of_upt<N>(4, a, b, c), f5 = 5 * NN + fpt_of_upt<N>(5, a, b, c);
 #pragma unroll
     for (int k = 0; k < NF; k++)
     {
       double acc = 0.0;
 #pragma unroll
-      for (int i = 0; i < N; i++) acc += S.tab.D[a * N + i] * S.sg[e][0][k][i + N * b + NN * c];
+      for (int i = 0; i < N; i++) acc += Da[i] * S.sg[e][0][k][i + N * b + NN * c];
 #pragma unroll
-      for (int i = 0; i < N; i++) acc += S.tab.D[b * N + i] * S.sg[e][1][k][a + N * i + NN * c];
+      for (int i = 0; i < N; i++) acc += Db[i] * S.sg[e][1][k][a + N * i + NN * c];
 #pragma unroll
-      for (int i = 0; i < N; i++) acc += S.tab.D[c * N + i] * S.sg[e][2][k][a + N * b + NN * i];
+      for (int i = 0; i < N; i++) acc += Dc[i] * S.sg[e][2][k][a + N * b + NN * i];
       const double *dfl = S.sx[e][k];
-      acc += S.tab.c3[0 * N + c] * dfl[0 * NN + fpt_of_upt<N>(0, a, b, c)];
-      acc += S.tab.c3[1 * N + b] * dfl[1 * NN + fpt_of_upt<N>(1, a, b, c)];
-      acc += S.tab.c3[2 * N + a] * dfl[2 * NN + fpt_of_upt<N>(2, a, b, c)];
-      acc += S.tab.c3[3 * N + b] * dfl[3 * NN + fpt_of_upt<N>(3, a, b, c)];
-      acc += S.tab.c3[4 * N + a] * dfl[4 * NN + fpt_of_upt<N>(4, a, b, c)];
-      acc += S.tab.c3[5 * N + c] * dfl[5 * NN + fpt_of_upt<N>(5, a, b, c)];
+      acc += c30 * dfl[f0]; acc += c31 * dfl[f1]; acc += c32 * dfl[f2];
+      acc += c33 * dfl[f3]; acc += c34 * dfl[f4]; acc += c35 * dfl[f5];
       size_t gi = p + (size_t)NU * (ge + (size_t)A.n_eles * k);
       if (A.keep_residual) A.div[gi] = acc;
       if (A.do_update)
       {
         double u = S.su[e][k][p];
-        double rr = acc / detjac;
+        double rr = acc * inv_detjac;
         if (A.rk.copy_u1) A.u1[gi] = u;
         if (A.rk.mode == 0)
           u -= dtl / A.rk.fac * rr;
@@ -462,9 +614,10 @@ __global__ void __launch_bounds__(NT) k_resid(fused_args A)
   for (int q = threadIdx.x; q < ne * NFP; q += NT)
   {
     int e = q / NFP, r = q - e * NFP, f = r / NN, j = r - f * NN;
-    int base, stride;
-    line_of_fpt<N>(f, j, base, stride);
-    const double *L = face_sgn(f) > 0 ? S.tab.Lp : S.tab.Lm;
+    const int base = S.tab.lbase[r], stride = face_stride<N>(f);
+    double L[N];
+#pragma unroll
+    for (int i = 0; i < N; i++) L[i] = face_sgn(f) > 0 ? S.tab.Lp[i] : S.tab.Lm[i];
     double *out = A.fu_next + ((size_t)(e0 + e) * 6 + f) * (NF * NN) + j;
 #pragma unroll
     for (int k = 0; k < NF; k++) out[k * NN] = face_value<N>(S.su[e][k], L, base, stride);
@@ -485,8 +638,7 @@ __global__ void __launch_bounds__(NT) k_face_values(fused_args A)
   for (int q = threadIdx.x; q < ne * NFP; q += NT)
   {
     int e = q / NFP, r = q - e * NFP, f = r / NN, j = r - f * NN;
-    int base, stride;
-    line_of_fpt<N>(f, j, base, stride);
+    const int base = S.tab.lbase[r], stride = face_stride<N>(f);
     const double *L = face_sgn(f) > 0 ? S.tab.Lp : S.tab.Lm;
     double *out = A.fu_next + ((size_t)(e0 + e) * 6 + f) * (NF * NN) + j;
 #pragma unroll
@@ -512,7 +664,7 @@ struct hf_fused_state
   int order = 0, n_eles = 0, n_mpi = 0;
   double *fu[2] = {nullptr, nullptr};
   int cur = 0;
-  double *fg = nullptr;
+  double *fv = nullptr;
   double *em = nullptr;
   int *nbr = nullptr;
   signed char *finfo = nullptr, *bsign = nullptr;
@@ -659,6 +811,13 @@ static bool extract_tables(hf_eles_dev &e, bool visc, fused_tables &T, std::stri
         T.perm[rot * 36 + (i * N + j)] = (unsigned char)v;
         T.perm[(rot + 4) * 36 + v] = (unsigned char)(i * N + j);
       }
+  for (int f = 0; f < 6; f++)
+    for (int j = 0; j < NN; j++)
+    {
+      int base, stride;
+      line_of_fpt<N>(f, j, base, stride);
+      T.lbase[f * NN + j] = (unsigned short)base;
+    }
   return true;
 }
 
@@ -727,7 +886,7 @@ int hf_fused_prepare(hf_ctx *c)
   {
     int el = M.h_ele_l[i], fl = M.h_loc_l[i];
     nbr[(size_t)el * 6 + fl] = ne * 6 + i; // receive block behind the last element
-    finfo[(size_t)el * 6 + fl] = (signed char)M.h_rot[i];
+    finfo[(size_t)el * 6 + fl] = (signed char)(M.h_rot[i] + 8);
     mpi_blk[i] = el * 6 + fl;
     for (int j = 0; j < NN; j++) bsign[(size_t)el * NFP + fl * NN + j] = e.h_own_sign[(size_t)el * NFP + fl * NN + j];
   }
@@ -738,7 +897,7 @@ int hf_fused_prepare(hf_ctx *c)
   const size_t nblk = (size_t)ne * 6 + M.n_inters;
   if (hf_alloc_zero(c, &Z->fu[0], nblk * NF * NN)) return 1;
   if (hf_alloc_zero(c, &Z->fu[1], nblk * NF * NN)) return 1;
-  if (visc && hf_alloc_zero(c, &Z->fg, nblk * ND * NF * NN)) return 1;
+  if (visc && hf_alloc_zero(c, &Z->fv, nblk * 4 * NN)) return 1;
   if (hf_alloc_copy(c, &Z->em, em.data(), em.size())) return 1;
   if (hf_alloc_copy(c, &Z->nbr, nbr.data(), nbr.size())) return 1;
   if (hf_alloc_copy(c, &Z->finfo, finfo.data(), finfo.size())) return 1;
@@ -748,7 +907,7 @@ int hf_fused_prepare(hf_ctx *c)
   if (M.n_inters)
   {
     if (hf_alloc_zero(c, &Z->out_u, (size_t)M.n_inters * NF * NN)) return 1;
-    if (visc && hf_alloc_zero(c, &Z->out_g, (size_t)M.n_inters * ND * NF * NN)) return 1;
+    if (visc && hf_alloc_zero(c, &Z->out_g, (size_t)M.n_inters * 4 * NN)) return 1;
   }
   // host-side extracts are no longer needed
   std::vector<double>().swap(e.h_em);
@@ -760,34 +919,34 @@ int hf_fused_prepare(hf_ctx *c)
 
 namespace
 {
-template <int N, int E, int NT>
+template <int N, int E, int NT, int MINB>
 int launch_all(hf_ctx *c, hf_fused_state *Z, fused_args &A, int what)
 {
   // what: 0 face values, 1 gradient kernel, 2 residual kernel
   const size_t smem = sizeof(smem_layout<N, E>);
   const int grid = (Z->n_eles + E - 1) / E;
-  static bool attr_done[3] = {false, false, false};
+  static bool attr_done = false;
+  if (!attr_done)
+  {
+    HF_CUDA(cudaFuncSetAttribute(k_face_values<N, E, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    HF_CUDA(cudaFuncSetAttribute(k_grad<N, E, NT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    HF_CUDA(cudaFuncSetAttribute(k_resid<N, E, NT, MINB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    HF_CUDA(cudaFuncSetAttribute(k_resid<N, E, NT, MINB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // ask for the largest shared-memory carve-out so that MINB blocks fit on an SM
+    HF_CUDA(cudaFuncSetAttribute(k_grad<N, E, NT, MINB>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    HF_CUDA(cudaFuncSetAttribute(k_resid<N, E, NT, MINB, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    HF_CUDA(cudaFuncSetAttribute(k_resid<N, E, NT, MINB, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    attr_done = true;
+  }
   if (what == 0)
-  {
-    if (!attr_done[0]) { HF_CUDA(cudaFuncSetAttribute(k_face_values<N, E, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_done[0] = true; }
     k_face_values<N, E, NT><<<grid, NT, smem, c->stream>>>(A);
-  }
   else if (what == 1)
-  {
-    if (!attr_done[1]) { HF_CUDA(cudaFuncSetAttribute(k_grad<N, E, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_done[1] = true; }
-    k_grad<N, E, NT><<<grid, NT, smem, c->stream>>>(A);
-  }
+    k_grad<N, E, NT, MINB><<<grid, NT, smem, c->stream>>>(A);
   else
   {
-    if (!attr_done[2])
-    {
-      HF_CUDA(cudaFuncSetAttribute(k_resid<N, E, NT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      HF_CUDA(cudaFuncSetAttribute(k_resid<N, E, NT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      attr_done[2] = true;
-    }
     hf_ktimer_begin(c);
-    if (A.viscous) k_resid<N, E, NT, true><<<grid, NT, smem, c->stream>>>(A);
-    else k_resid<N, E, NT, false><<<grid, NT, smem, c->stream>>>(A);
+    if (A.viscous) k_resid<N, E, NT, MINB, true><<<grid, NT, smem, c->stream>>>(A);
+    else k_resid<N, E, NT, MINB, false><<<grid, NT, smem, c->stream>>>(A);
     hf_ktimer_end(c);
   }
   c->launches++;
@@ -800,11 +959,11 @@ int launch(hf_ctx *c, hf_fused_state *Z, fused_args &A, int what)
 {
   switch (Z->order)
   {
-  case 1: return launch_all<2, 8, 128>(c, Z, A, what);
-  case 2: return launch_all<3, 4, 128>(c, Z, A, what);
-  case 3: return launch_all<4, 2, 128>(c, Z, A, what);
-  case 4: return launch_all<5, 2, 128>(c, Z, A, what);
-  case 5: return launch_all<6, 1, 128>(c, Z, A, what);
+  case 1: return launch_all<2, 8, 128, 4>(c, Z, A, what);
+  case 2: return launch_all<3, 4, 128, 4>(c, Z, A, what);
+  case 3: return launch_all<4, 2, 128, 4>(c, Z, A, what);
+  case 4: return launch_all<5, 2, 128, 4>(c, Z, A, what);
+  case 5: return launch_all<6, 1, 128, 4>(c, Z, A, what);
   }
   hf_set_error("fused path: unsupported order");
   return 1;
@@ -821,7 +980,7 @@ void base_args(hf_ctx *c, hf_fused_state *Z, fused_args &A)
   A.div = e.div_tconf_upts;
   A.fu_cur = Z->fu[Z->cur];
   A.fu_next = Z->fu[Z->cur ^ 1];
-  A.fg = Z->fg;
+  A.fv = Z->fv;
   A.em = Z->em;
   A.nbr = Z->nbr;
   A.finfo = Z->finfo;
@@ -898,7 +1057,7 @@ int hf_fused_stage(hf_ctx *c, int rk_stage, double time, int keep_residual, int 
   if (p.viscous)
   {
     if (launch(c, Z, A, 1)) return 1;
-    if (exchange(c, Z, Z->fg, Z->out_g, ND * NF * NN)) return 1;
+    if (exchange(c, Z, Z->fv, Z->out_g, 4 * NN)) return 1;
   }
   if (launch(c, Z, A, 2)) return 1;
   if (do_update)

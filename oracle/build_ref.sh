@@ -23,7 +23,7 @@ for f in $SRCS HiFiLES; do
   pids+=($!)
 done
 for p in "${pids[@]}"; do wait $p; done
-g++ "$OUT"/obj/*.o -o "$OUT/HiFiLES_ref"
+g++ $(ls "$OUT"/obj/*.o | grep -v '/ref_dump.o$') -o "$OUT/HiFiLES_ref"
 # instrumented dumper (our own TU, oracle/ref_dump.cpp) linked against the reference objects minus its main()
 if [ -f "$HERE/ref_dump.cpp" ]; then
   objs=$(ls "$OUT"/obj/*.o | grep -v '/HiFiLES.o$' | grep -v '/ref_dump.o$')
