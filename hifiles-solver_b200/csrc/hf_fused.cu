@@ -28,6 +28,7 @@
 // Algorithmic traffic per element-stage, P = 4, RK34: see DESIGN.md (about 9 k doubles vs 56 k for the staged path).
 #include "hf_device.h"
 #include <cstring>
+#include <cstdlib>
 #include <cmath>
 #include <algorithm>
 
@@ -962,7 +963,15 @@ int launch(hf_ctx *c, hf_fused_state *Z, fused_args &A, int what)
   case 1: return launch_all<2, 8, 128, 4>(c, Z, A, what);
   case 2: return launch_all<3, 4, 128, 4>(c, Z, A, what);
   case 3: return launch_all<4, 2, 128, 4>(c, Z, A, what);
-  case 4: return launch_all<5, 2, 128, 4>(c, Z, A, what);
+  case 4:
+  {
+    static int cfg = getenv("HF_FUSED_CFG") ? atoi(getenv("HF_FUSED_CFG")) : 0;
+    if (cfg == 1) return launch_all<5, 1, 64, 8>(c, Z, A, what);
+    if (cfg == 2) return launch_all<5, 2, 160, 3>(c, Z, A, what);
+    if (cfg == 3) return launch_all<5, 4, 256, 2>(c, Z, A, what);
+    if (cfg == 4) return launch_all<5, 1, 128, 8>(c, Z, A, what);
+    return launch_all<5, 2, 128, 4>(c, Z, A, what);
+  }
   case 5: return launch_all<6, 1, 128, 4>(c, Z, A, what);
   }
   hf_set_error("fused path: unsupported order");

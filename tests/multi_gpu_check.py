@@ -1,0 +1,83 @@
+"""Run under torchrun (one rank per GPU): the TGV case split into bricks over the ranks must reproduce the
+single-domain result.  Rank 0 also runs the whole mesh on its own GPU (staged kernels = bit-exact reference order) and
+compares element by element through ele2global_ele.  Usage:
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port 29511 \
+        tests/multi_gpu_check.py [n] [order] [steps] [fused|staged]"""
+import os
+import pathlib
+import sys
+import tempfile
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, str(pathlib.Path(__file__).parent))
+import conftest  # noqa: E402
+
+
+def main():
+    n = int(sys.argv[1]) if len(sys.argv) > 1 else 8
+    order = int(sys.argv[2]) if len(sys.argv) > 2 else 3
+    steps = int(sys.argv[3]) if len(sys.argv) > 3 else 2
+    mode = sys.argv[4] if len(sys.argv) > 4 else "fused"
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    hb = conftest.load_package()
+    import importlib
+    mg = importlib.import_module("hifiles_solver_b200.meshgen")
+    obj = [tempfile.mkdtemp(prefix="hf_mgpu_") if rank == 0 else None]
+    dist.broadcast_object_list(obj, src=0)
+    work = obj[0]
+    mesh = os.path.join(work, "tgv.neu")
+    inp = os.path.join(work, "input")
+    if rank == 0:
+        mg.hex_box(mesh, n)
+        mg.write_input(inp, "tgv.neu", order=order, adv_type=2, dt=1e-5, riemann_solve_type=3, viscous=1)
+    dist.barrier()
+    part = mg.block_partition(n, mg.blocks_for(world))
+    idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
+    if rank == 0:
+        idt = torch.tensor(list(hb.nccl_unique_id()), dtype=torch.uint8, device="cuda")
+    dist.broadcast(idt, src=0)
+    run = hb.Run(inp, rank=rank, nproc=world, part=part, nccl_id=bytes(idt.cpu().tolist()))
+    if mode == "staged":
+        run.set_mode(False)
+    else:
+        assert run.fused_status() == "available", run.fused_status()
+    run.run(steps, fused=True)
+    u = run.download("hex", "disu_upts")
+    gid = run.host_array("hex.ele2global_ele")
+    n_mpi = run.n_inters("mpi", 2)
+    run.close()
+    # gather on rank 0
+    nu = u.shape[0]
+    full = torch.zeros((n ** 3, nu, 5), dtype=torch.float64, device="cuda")
+    full[torch.from_numpy(gid.astype(np.int64)).cuda()] = torch.from_numpy(np.ascontiguousarray(u.transpose(1, 0, 2))).cuda()
+    dist.all_reduce(full)
+    ok = True
+    if rank == 0:
+        with hb.Run(inp) as single:
+            single.set_mode(False)
+            single.run(steps, fused=True)
+            us = single.download("hex", "disu_upts")
+            gs = single.host_array("hex.ele2global_ele")
+        ref = np.zeros((n ** 3, nu, 5))
+        ref[gs] = us.transpose(1, 0, 2)
+        got = full.cpu().numpy()
+        sc = np.abs(ref).reshape(-1, 5).max(0)
+        sc[1:4] = sc[1:4].max()
+        err = (np.abs(got - ref).reshape(-1, 5).max(0) / sc).max()
+        ok = bool(err < 1e-12)
+        print("multi_gpu_check: world=%d n=%d order=%d steps=%d mode=%s partition faces on rank 0: %d  max rel err vs single domain %.3e  %s"
+              % (world, n, order, steps, mode, n_mpi, err, "OK" if ok else "FAIL"))
+    flag = torch.tensor([1 if ok else 0], device="cuda")
+    dist.broadcast(flag, src=0)
+    dist.barrier()
+    dist.destroy_process_group()
+    sys.exit(0 if int(flag.item()) == 1 else 1)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,29 @@
+"""Multi-GPU parity (runs only where >= 2 CUDA devices are visible): the partitioned run over NCCL must reproduce the
+single-domain run.  The host-side partition logic is covered on CPU by test_partition_cpu.py (gloo, world_size 2)."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def n_gpus():
+    try:
+        import torch
+        return torch.cuda.device_count()
+    except Exception:
+        return 0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", ["staged", "fused"])
+def test_two_ranks_match_single_domain(mode):
+    if n_gpus() < 2:
+        pytest.skip("needs 2 GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29533", os.path.join(ROOT, "tests", "multi_gpu_check.py"), "6", "2", "2", mode]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "OK" in r.stdout
