@@ -1,0 +1,292 @@
+"""TEST INFRASTRUCTURE -- CPU restatement (numpy) of the reference's per-RK-stage residual path.  Never imported by the
+product: only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg may use anything under oracle/.
+
+Pinned: tests/test_oracle_cpu.py checks this file against golden dumps of the UNMODIFIED reference solver
+(tests/golden/*.npz, produced by tests/golden/make_golden.py from oracle/_ref/ref_dump, i.e. the reference's own
+sources compiled where they lie under /root/reference).  The reference's own regression goldens are stale
+(SURVEY.md section 4), so reference runs are the pin.
+
+Every function cites the reference routine it restates.  Arrays keep the reference's column-major hf_array index order
+(first index fastest): disu_upts(upt,ele,field), disu_fpts(fpt,ele,field), grad(pt,ele,field,dim),
+tdisf_upts(upt,ele,field,dim), JGinv(l,m,pt,ele), detjac(pt,ele), tdA(fpt,ele), norm_fpts(fpt,ele,dim), opp(row,col).
+Scope: Euler / Navier-Stokes on one element type with interior (incl. periodic) interfaces -- what BASELINE configs
+1 and 3 exercise.  Operator products use numpy's BLAS, so sums are not in the reference's order: agreement is to
+rounding (1e-13), not bit-exact."""
+import numpy as np
+
+
+class Params:
+    def __init__(self, gamma, prandtl, mu_inf, rt_inf, c_sth, fix_vis, ldg_beta, ldg_tau, dt, viscous, riemann_solve_type, adv_type,
+                 RK_a=None, RK_b=None):
+        self.__dict__.update(locals())
+        del self.__dict__["self"]
+
+
+# ---- pointwise physics -------------------------------------------------------------------------------------------------
+def calc_invf(u, gamma):
+    """calc_invf_2d / calc_invf_3d (reference src/flux.cpp:33-125).  u[..., field] -> f[..., field, dim]"""
+    nd = u.shape[-1] - 2
+    rho, E = u[..., 0], u[..., nd + 1]
+    v = u[..., 1:nd + 1] / rho[..., None]
+    p = (gamma - 1.0) * (E - 0.5 * rho * np.sum(v * v, axis=-1))
+    f = np.empty(u.shape + (nd,))
+    for d in range(nd):
+        f[..., 0, d] = u[..., d + 1]
+        for k in range(nd):
+            f[..., k + 1, d] = u[..., k + 1] * v[..., d] + (p if k == d else 0.0)
+        f[..., nd + 1, d] = v[..., d] * (E + p)
+    return f
+
+
+def calc_visf(u, g, P):
+    """calc_visf_2d / calc_visf_3d (reference src/flux.cpp:129-422), no RANS.  g[..., field, dim]"""
+    nd = u.shape[-1] - 2
+    rho, ene = u[..., 0], u[..., nd + 1]
+    v = u[..., 1:nd + 1] / rho[..., None]
+    vsq = np.sum(v * v, axis=-1)
+    inte = ene / rho - 0.5 * vsq
+    rt_ratio = (P.gamma - 1.0) * inte / P.rt_inf
+    mu = P.mu_inf * rt_ratio ** 1.5 * (1 + P.c_sth) / (rt_ratio + P.c_sth)
+    mu = mu + P.fix_vis * (P.mu_inf - mu)
+    drho = g[..., 0, :]                                             # (..., dim)
+    dv = (g[..., 1:nd + 1, :] - drho[..., None, :] * v[..., :, None]) / rho[..., None, None]  # dv[i, d]
+    dke = 0.5 * vsq[..., None] * drho + rho[..., None] * np.einsum("...i,...id->...d", v, dv)
+    de = (g[..., nd + 1, :] - dke - drho * inte[..., None]) / rho[..., None]
+    diag = np.einsum("...ii->...", dv) / 3.0
+    tau = mu[..., None, None] * (dv + np.swapaxes(dv, -1, -2))
+    for i in range(nd):
+        tau[..., i, i] = 2.0 * mu * (dv[..., i, i] - diag)
+    f = np.zeros(u.shape + (nd,))
+    f[..., 1:nd + 1, :] = -tau
+    f[..., nd + 1, :] = -(np.einsum("...i,...id->...d", v, tau) + (mu / P.prandtl)[..., None] * P.gamma * de)
+    return f
+
+
+def _sides(u_l, u_r, n, gamma):
+    nd = n.shape[-1]
+    out = []
+    for u in (u_l, u_r):
+        v = u[..., 1:nd + 1] / u[..., :1]
+        vn = np.sum(v * n, axis=-1)
+        vsq = np.sum(v * v, axis=-1)
+        p = (gamma - 1.0) * (u[..., nd + 1] - 0.5 * u[..., 0] * vsq)
+        h = (u[..., nd + 1] + p) / u[..., 0]
+        fn = np.einsum("...kd,...d->...k", calc_invf(u, gamma), n)
+        out.append((v, vn, vsq, p, h, fn))
+    return out
+
+
+def rusanov_flux(u_l, u_r, n, gamma):
+    """inters::rusanov_flux (reference src/inters.cpp:277-324)"""
+    (_, vn_l, _, p_l, _, fn_l), (_, vn_r, _, p_r, _, fn_r) = _sides(u_l, u_r, n, gamma)
+    eig = np.sqrt(gamma * (p_l + p_r) / (u_l[..., 0] + u_r[..., 0])) + 0.5 * np.abs(vn_l + vn_r)
+    return 0.5 * ((fn_l + fn_r) - eig[..., None] * (u_r - u_l))
+
+
+def hllc_flux(u_l, u_r, n, gamma):
+    """inters::hllc_flux (reference src/inters.cpp:439-532)"""
+    nd = n.shape[-1]
+    (_, vn_l, _, p_l, h_l, fn_l), (_, vn_r, _, p_r, h_r, fn_r) = _sides(u_l, u_r, n, gamma)
+    rl, rr = u_l[..., 0], u_r[..., 0]
+    sq_rho = np.sqrt(rr / rl)
+    rrho = 1. / (sq_rho + 1.)
+    vn_m = rrho * (vn_l + sq_rho * vn_r)
+    h_m = rrho * (h_l + sq_rho * h_r)
+    a_m = np.sqrt((gamma - 1.) * (h_m - 0.5 * vn_m * vn_m))
+    S_R, S_L = vn_m + a_m, vn_m - a_m
+    S_star = (p_r - p_l + rl * vn_l * (S_L - vn_l) - rr * vn_r * (S_R - vn_r)) / (rl * (S_L - vn_l) - rr * (S_R - vn_r))
+
+    def star(u, fn, p, vn, S):
+        rcp = S - S_star
+        pst = p + u[..., 0] * (S - vn) * (S_star - vn)
+        out = np.empty_like(u)
+        out[..., 0] = S_star * (S * u[..., 0] - fn[..., 0]) / rcp
+        for i in range(nd):
+            out[..., i + 1] = (S_star * (S * u[..., i + 1] - fn[..., i + 1]) + S * pst * n[..., i]) / rcp
+        out[..., nd + 1] = (S_star * (S * u[..., nd + 1] - fn[..., nd + 1]) + S * pst * S_star) / rcp
+        return out
+    fl_star, fr_star = star(u_l, fn_l, p_l, vn_l, S_L), star(u_r, fn_r, p_r, vn_r, S_R)
+    c0, c1, c2 = (S_L >= 0)[..., None], (S_star >= 0)[..., None], (S_R >= 0)[..., None]
+    return np.where(c0, fn_l, np.where(c1, fl_star, np.where(c2, fr_star, fn_r)))
+
+
+def roeM_flux(u_l, u_r, n, gamma):
+    """inters::roeM_flux (reference src/inters.cpp:327-437)"""
+    nd = n.shape[-1]
+    (v_l, vn_l, _, p_l, h_l, fn_l), (v_r, vn_r, _, p_r, h_r, fn_r) = _sides(u_l, u_r, n, gamma)
+    rl, rr = u_l[..., 0], u_r[..., 0]
+    drho, dp, dh, dvn = rr - rl, p_r - p_l, h_r - h_l, vn_r - vn_l
+    dv = v_r - v_l
+    sq_rho = np.sqrt(rr / rl)
+    rrho = 1.0 / (1.0 + sq_rho)
+    ratr = sq_rho * rrho
+    ra = sq_rho * rl
+    ha = h_l * rrho + h_r * ratr
+    va = v_l * rrho[..., None] + v_r * ratr[..., None]
+    qq = np.sum(va * va, axis=-1)
+    va_n = np.sum(n * va, axis=-1)
+    aa = np.sqrt((gamma - 1) * (ha - 0.5 * qq))
+    rcp_aa = 1.0 / aa
+    abs_ma = np.abs(va_n * rcp_aa)
+    b1 = np.maximum(0.0, np.maximum(va_n + aa, vn_r + aa))
+    b2 = np.minimum(0.0, np.minimum(va_n - aa, vn_l - aa))
+    b1b2 = b1 * b2
+    rcp = 1.0 / (b1 - b2)
+    b1, b2, b1b2 = b1 * rcp, b2 * rcp, b1b2 * rcp
+    h = 1.0 - np.where(p_l < p_r, p_l / p_r, p_r / p_l)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        f = np.where(abs_ma != 0, abs_ma ** h, 1.)
+    g = f / (1.0 + abs_ma)
+    du = u_r - u_l
+    du[..., nd + 1] = rr * h_r - rl * h_l
+    bdq = np.empty_like(u_l)
+    bdq[..., 0] = drho - f * dp * rcp_aa * rcp_aa
+    bdq[..., nd + 1] = bdq[..., 0] * ha + ra * dh
+    for i in range(nd):
+        bdq[..., i + 1] = bdq[..., 0] * va[..., i] + ra * (dv[..., i] - n[..., i] * dvn)
+    return (b1[..., None] * fn_l - b2[..., None] * fn_r) + b1b2[..., None] * (du - g[..., None] * bdq)
+
+
+def ldg_switched_beta(beta, n):
+    """the 'consistent switch' of inters::ldg_flux / ldg_solution (reference src/inters.cpp:566-581, 620-634)"""
+    nd = n.shape[-1]
+    b = np.full(n.shape[:-1], float(beta))
+    if beta == 0.:
+        return b
+    n0 = n[..., 0]
+    s01 = n[..., 0] + n[..., 1]
+    flip = n0 < 0.
+    z0 = n0 == 0.
+    flip |= z0 & (s01 < 0.)
+    if nd == 3:
+        flip |= z0 & (s01 == 0) & ((n[..., 0] + n[..., 2]) < 0.)
+    return np.where(flip, -b, b)
+
+
+# ---- the per-stage sequence (reference src/solver.cpp:50-223) for one element type, interior interfaces -------------------
+class Oracle:
+    def __init__(self, setup, prefix, inter_prefix, P):
+        """setup: dict with the reference dump's names (oracle/ref_dump.cpp dump_setup): '<prefix>.opp_0', ... and
+        '<inter_prefix>.idx_l' / '.idx_r' (flat fpt + n_fpts*ele of each flux-point pair, right side already permuted by
+        inters::get_lut, reference src/int_inters.cpp:76-95)."""
+        g = lambda k: np.asarray(setup[prefix + "." + k])
+        self.P = P
+        self.ne, self.nu, self.nfp, self.nf, self.nd = [int(x) for x in g("sizes")[:5]]
+        nd = self.nd
+        self.opp_0, self.opp_3 = g("opp_0"), g("opp_3")
+        self.opp_1 = [g("opp_1_%d" % d) for d in range(nd)]
+        self.opp_2 = [g("opp_2_%d" % d) for d in range(nd)]
+        if P.viscous:
+            self.opp_4 = [g("opp_4_%d" % d) for d in range(nd)]
+            self.opp_5 = [g("opp_5_%d" % d) for d in range(nd)]
+            self.opp_6 = g("opp_6")
+        self.detjac_upts, self.JGinv_upts = g("detjac_upts"), g("JGinv_upts")
+        self.detjac_fpts, self.JGinv_fpts = g("detjac_fpts"), g("JGinv_fpts")
+        self.tdA_fpts, self.norm_fpts = g("tdA_fpts"), g("norm_fpts")
+        self.idx_l = np.asarray(setup[inter_prefix + ".idx_l"]).ravel(order="F")
+        self.idx_r = np.asarray(setup[inter_prefix + ".idx_r"]).ravel(order="F")
+        self.u = [np.array(g("disu_upts_ic"), order="F"), np.zeros((self.nu, self.ne, self.nf), order="F")]
+        self.div = np.zeros((self.nu, self.ne, self.nf), order="F")
+
+    # operator product over all (ele, field) columns: the reference's column-major dgemm (src/funcs.cpp:49-124)
+    @staticmethod
+    def _apply(op, x):
+        return np.einsum("rc,cef->ref", op, x)
+
+    def _flat(self, a):  # (fpt, ele, field[...]) -> (fpt*ele, field[...]) in flat (fpt + n_fpts*ele) order
+        return a.reshape((self.nfp * self.ne,) + a.shape[2:], order="F")
+
+    def calc_residual(self):
+        P, nd = self.P, self.nd
+        u = self.u[0]
+        disu_fpts = self._apply(self.opp_0, u)                                   # eles::extrapolate_solution :1360
+        if P.viscous:
+            grad_upts = np.stack([self._apply(self.opp_4[d], u) for d in range(nd)], axis=-1)   # calculate_gradient :1823
+        # eles::evaluate_invFlux (:1415): tdisf(j,i,k,l) = sum_m JGinv(l,m,j,i) f(k,m)
+        f = calc_invf(u, P.gamma)
+        tdisf = np.einsum("lmje,jekm->jekl", self.JGinv_upts, f)
+        # int_inters::calculate_common_invFlux (src/int_inters.cpp:160-249)
+        uf = self._flat(disu_fpts)
+        nrm = self._flat(self.norm_fpts)
+        tdA = self.tdA_fpts.ravel(order="F")
+        u_l, u_r, n = uf[self.idx_l], uf[self.idx_r], nrm[self.idx_l]
+        fn = {0: rusanov_flux, 2: roeM_flux, 3: hllc_flux}[P.riemann_solve_type](u_l, u_r, n, P.gamma)
+        ntconf = np.zeros_like(uf)
+        ntconf[self.idx_l] = fn * tdA[self.idx_l][:, None]
+        ntconf[self.idx_r] = -fn * tdA[self.idx_r][:, None]
+        if P.viscous:
+            beta = ldg_switched_beta(P.ldg_beta, n)[:, None]
+            u_c = 0.5 * (u_l + u_r) - beta * (u_l - u_r)                          # inters::ldg_solution :615
+            delta = np.zeros_like(uf)
+            delta[self.idx_l] = u_c - u_l
+            delta[self.idx_r] = u_c - u_r
+            delta = delta.reshape((self.nfp, self.ne, self.nf), order="F")
+            # eles::correct_gradient (:1890-2052)
+            for d in range(nd):
+                grad_upts[..., d] += self._apply(self.opp_5[d], delta)
+            grad_fpts = np.stack([self._apply(self.opp_6, grad_upts[..., d]) for d in range(nd)], axis=-1)
+            grad_upts = np.einsum("ldje,jekl->jekd", self.JGinv_upts, grad_upts) / self.detjac_upts[:, :, None, None]
+            grad_fpts = np.einsum("ldje,jekl->jekd", self.JGinv_fpts, grad_fpts) / self.detjac_fpts[:, :, None, None]
+            # eles::evaluate_viscFlux (:2285)
+            tdisf = tdisf + np.einsum("lmje,jekm->jekl", self.JGinv_upts, calc_visf(u, grad_upts, P))
+        # extrapolate_totalFlux (:1549), calculate_divergence (:1651)
+        ntdisf = sum(self._apply(self.opp_1[d], tdisf[..., d]) for d in range(nd))
+        div = sum(self._apply(self.opp_2[d], tdisf[..., d]) for d in range(nd))
+        if P.viscous:
+            # int_inters::calculate_common_viscFlux (src/int_inters.cpp:254-343) + inters::ldg_flux (:561-611)
+            gf = self._flat(grad_fpts)
+            f_l, f_r = calc_visf(u_l, gf[self.idx_l], P), calc_visf(u_r, gf[self.idx_r], P)
+            b = ldg_switched_beta(P.ldg_beta, n)[:, None, None]
+            f_c = (0.5 + b) * f_l + (0.5 - b) * f_r
+            fnv = np.einsum("qkd,qd->qk", f_c, n) - P.ldg_tau * (u_r - u_l)
+            ntconf[self.idx_l] += fnv * tdA[self.idx_l][:, None]
+            ntconf[self.idx_r] += -fnv * tdA[self.idx_r][:, None]
+        ntconf = ntconf.reshape((self.nfp, self.ne, self.nf), order="F")
+        # calculate_corrected_divergence (:1738)
+        self.div = div + self._apply(self.opp_3, ntconf - ntdisf)
+        return self.div
+
+    def advance_solution(self, stage):
+        """eles::AdvanceSolution (reference src/eles.cpp:1080-1265), fixed time step, no source term"""
+        P = self.P
+        res = self.div / self.detjac_upts[:, :, None]
+        rhs = -res
+        u0, u1 = self.u
+        a = P.adv_type
+        if a == 0:
+            u0 -= P.dt * res
+        elif a == 1:
+            if stage == 0:
+                u1[...] = u0
+            if stage < 3:
+                u0 -= P.dt / 3.0 * res
+            else:
+                u0[...] = 3.0 / 4.0 * u0 + 1.0 / 4.0 * u1 + P.dt / 4.0 * rhs
+        elif a == 2:
+            if stage == 0:
+                u1[...] = u0
+            if stage < 2 or stage == 3:
+                u0 -= P.dt / 2.0 * res
+            else:
+                u0[...] = 1.0 / 3.0 * u0 + 2.0 / 3.0 * u1 + P.dt / 6.0 * rhs
+        else:
+            u1[...] = P.RK_a[stage] * u1 + P.dt * rhs
+            u0 += P.RK_b[stage] * u1
+
+    def n_stages(self):
+        return {0: 1, 1: 4, 2: 4, 3: 5, 4: 14}[self.P.adv_type]
+
+    def step(self):
+        for s in range(self.n_stages()):
+            self.calc_residual()
+            self.advance_solution(s)
+
+    def norm_residual(self, norm_type=1):
+        """eles::compute_res_upts + output::CalcNormResidual (reference src/eles.cpp:5045-5074, src/output.cpp:2166-2248)"""
+        r = self.div / self.detjac_upts[:, :, None]
+        n = self.nu * self.ne
+        if norm_type == 0:
+            return np.abs(r).max(axis=(0, 1))
+        if norm_type == 1:
+            return np.abs(r).sum(axis=(0, 1)) / n
+        return np.sqrt((r * r).sum(axis=(0, 1))) / n

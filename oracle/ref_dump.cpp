@@ -121,6 +121,11 @@ static void dump_setup(struct solution *S)
                         (double)run_input.fix_vis, run_input.ldg_beta, run_input.ldg_tau, run_input.dt,
                         run_input.R_ref, run_input.p_c_ic, run_input.rho_c_ic, run_input.T_c_ic, run_input.uvw_c_ic, run_input.uvw_ref};
   put_dvec("params", par);
+  if (run_input.adv_type == 3 || run_input.adv_type == 4)
+  {
+    put("rk_a", run_input.RK_a);
+    put("rk_b", run_input.RK_b);
+  }
   for (int t = 0; t < S->n_ele_types; t++)
   {
     eles *e = S->mesh_eles(t);

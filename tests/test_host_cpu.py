@@ -1,0 +1,87 @@
+"""CPU: host mirror (mesh reader, connectivity, operator and metric setup, initial condition) against the golden dumps
+of the unmodified reference -- bit-exact -- plus the C-ABI surface of the shared library (no compute without a GPU)."""
+import glob
+import os
+import re
+
+import numpy as np
+import pytest
+
+import util
+
+GOLDEN = sorted(glob.glob(os.path.join(util.ROOT, "tests", "golden", "*.npz")))
+
+
+def unpack_case(path, tmp_path):
+    z = np.load(path)
+    g = {k.replace("__", "."): z[k] for k in z.files}
+    name = os.path.basename(path)[:-4]
+    mesh = tmp_path / (name + ".neu")
+    inp = tmp_path / ("input_" + name)
+    mesh.write_bytes(g["case.mesh_text"].tobytes())
+    inp.write_bytes(g["case.input_text"].tobytes())
+    return g, str(inp), str(mesh)
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[:-4] for p in GOLDEN])
+def test_host_setup_is_bit_identical_to_reference(path, tmp_path, hb):
+    g, inp, _ = unpack_case(path, tmp_path)
+    skip = ("step", "final", "history", "mesh", "meta", "params", "rk_", "case")
+    checked = 0
+    with hb.Run(inp, host_only=True) as run:
+        for k, v in g.items():
+            if k.startswith(skip) or k.endswith(("tdA_idx_l", "tdA_idx_r", "norm_idx", "bc_flags")):
+                continue
+            a = run.host_array(k.replace("disu_upts_ic", "disu_upts"))
+            assert a.shape == v.shape, k
+            assert np.array_equal(a, v), "%s differs from the reference (max abs %.3e)" % (k, np.abs(a.astype(float) - v).max())
+            checked += 1
+        p = g["params"]
+        for i, nm in enumerate(["gamma", "prandtl", "mu_inf", "rt_inf", "c_sth", "fix_vis", "ldg_beta", "ldg_tau", "dt", "R_ref"]):
+            assert run.scalar(nm) == p[i] or (np.isnan(p[i]) and np.isnan(run.scalar(nm))), nm  # Euler runs keep NaN reference scales
+        if "rk_a" in g:
+            for i in range(len(g["rk_a"])):
+                assert run.scalar("RK_a%d" % i) == g["rk_a"][i] and run.scalar("RK_b%d" % i) == g["rk_b"][i]
+    assert checked > 25
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[:-4] for p in GOLDEN])
+def test_mesh_generator_reproduces_fixture_mesh(path, tmp_path, meshgen):
+    from tests_golden_cases import GOLDEN_CASES
+    g, _, mesh = unpack_case(path, tmp_path)
+    kind, n, mkw = GOLDEN_CASES[os.path.basename(path)[:-4]]
+    out = tmp_path / "regen.neu"
+    (meshgen.hex_box if kind == "hex" else meshgen.quad_box)(str(out), n, **mkw)
+    a, b = open(mesh).read().split("\n"), out.read_text().split("\n")
+    assert a[3:] == b[3:]  # line 3 holds the file name
+
+
+def test_library_exports_every_declared_symbol(hb):
+    import ctypes
+    lib = ctypes.CDLL(hb.LIB_PATH)
+    header = open(os.path.join(util.ROOT, "include", "hifiles_b200.h")).read()
+    names = sorted(set(re.findall(r"\b(hf_dev_\w+)\s*\(", header)))
+    assert len(names) >= 30
+    for nm in names:
+        assert hasattr(lib, nm), "symbol %s declared in include/hifiles_b200.h is not exported" % nm
+
+
+def test_no_cpu_fallback(tmp_path, hb, meshgen):
+    """Without a CUDA device the product must fail loudly, not fall back to any CPU path."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    meshgen.hex_box(str(tmp_path / "m.neu"), 2)
+    inp = meshgen.write_input(str(tmp_path / "input"), "m.neu", order=1)
+    with pytest.raises(hb.HiFiLESError, match="no CUDA device|CUDA"):
+        hb.Run(inp)
+
+
+def test_input_errors_match_reference_behaviour(tmp_path, hb, meshgen):
+    meshgen.hex_box(str(tmp_path / "m.neu"), 2)
+    inp = meshgen.write_input(str(tmp_path / "input"), "m.neu", order=1, riemann_solve_type=None)
+    with pytest.raises(hb.HiFiLESError, match="Required option not found: riemann_solve_type"):
+        hb.Run(inp, host_only=True)
+    inp = meshgen.write_input(str(tmp_path / "input2"), "does_not_exist.neu", order=1)
+    with pytest.raises(hb.HiFiLESError, match="Unable to open mesh file"):
+        hb.Run(inp, host_only=True)

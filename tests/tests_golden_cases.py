@@ -1,0 +1,8 @@
+"""Mesh parameters of the golden fixtures (kept apart from make_golden.py so that CPU tests need no reference)."""
+GOLDEN_CASES = {
+    "hex3_p2_ns_hllc_rk34": ("hex", 3, {}),
+    "hex2_p3_ns_rusanov_rk45": ("hex", 2, {}),
+    "hex3_p1_ns_roem_sutherland_rk24": ("hex", 3, {}),
+    "quad4_p3_euler_vortex_hllc_rk45": ("quad", 4, {}),
+    "quad4_p2_ns_rusanov_euler": ("quad", 4, dict(lengths=(6.2831853071795862,) * 2, origin=(0., 0.))),
+}
