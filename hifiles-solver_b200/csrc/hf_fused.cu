@@ -28,6 +28,7 @@
 // Algorithmic traffic per element-stage, P = 4, RK34: see DESIGN.md (about 9 k doubles vs 56 k for the staged path).
 #include "hf_device.h"
 #include <cstring>
+#include <type_traits>
 #include <cstdlib>
 #include <cmath>
 #include <algorithm>
@@ -108,8 +109,8 @@ struct fused_args
   double *fv;             // one-sided viscous normal flux at flux points: written by k_grad, read by k_resid
   const double *em;       // [ele][EM]
   const int *nbr;         // [ele][6] neighbour face block
-  const signed char *finfo; // [ele][6] rot + 4*is_right + 8*partition face
-  const signed char *bsign; // [ele][6*N*N] sign of ldg_beta
+  const int *finfo;       // [ele][6] rot + 4*is_right + 8*partition face
+  const unsigned long long *bmask; // [ele][6] per face: bit j = ldg_beta switched to -beta at flux point j
   const double *dt_local;
   const fused_tables *tab;
   hf_phys P;
@@ -117,18 +118,34 @@ struct fused_args
   int viscous, keep_residual, do_update;
 };
 
+// shared memory of one CTA: E elements, arrays indexed [field][ele][point] so that an element-item index
+// q = ele*points + point addresses them without divisions
 template <int N, int E>
 struct smem_layout
 {
   static constexpr int NU = N * N * N, NFP = 6 * N * N;
   fused_tables tab;
-  double su[E][NF][NU];
-  double sg[E][ND][NF][NU];
-  double sx[E][NF][NFP];
+  double su[NF][E * NU];          // solution at solution points
+  double sg[ND][NF][E * NU];      // physical gradient, later the transformed total flux
+  double sx[NF][E * NFP];         // neighbour face values -> LDG delta -> (neighbour face values) -> common minus own normal flux
   double em[E][EM];
+  unsigned long long bs[E][6];    // per face: bit j set = ldg_beta is switched to -beta at flux point j
   int nbr[E][6];
   int finfo[E][6];
 };
+template <int N, int E>
+struct smem_layout_visc : smem_layout<N, E>
+{
+  double sv[2][4][E * 6 * N * N]; // one-sided viscous normal fluxes: [own | neighbour][field 1..4][ele*NFP + fpt]
+};
+
+__device__ __forceinline__ void cp_async8(void *smem, const void *gmem)
+{
+  unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(sa), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
 
 template <int N>
 __device__ __forceinline__ int face_stride(int f)
@@ -302,34 +319,50 @@ __device__ __forceinline__ void riemann_fast(const double *__restrict__ u_l, con
 }
 
 // ---- shared phases ----------------------------------------------------------------------------------------------------
-template <int N, int E, int NT>
-__device__ __forceinline__ void load_block(smem_layout<N, E> &S, const fused_args &A, int e0, int ne)
+// All global reads of a CTA are cp.async copies into shared memory issued as early as possible; the compute phases
+// touch shared memory and registers only.
+template <int N, int E, int NT, typename SM>
+__device__ __forceinline__ void stage_inputs(SM &S, const fused_args &A, int e0, int ne, bool with_neighbours)
 {
-  constexpr int NU = N * N * N;
+  constexpr int NU = N * N * N, NFP = 6 * N * N, NN = N * N;
   const int tid = threadIdx.x;
-  // tables
-  {
-    const double *src = (const double *)A.tab;
-    double *dst = (double *)&S.tab;
-    constexpr int nd = sizeof(fused_tables) / sizeof(double);
-    for (int i = tid; i < nd; i += NT) dst[i] = src[i];
-  }
-  // solution: for a field, the ne elements of this block are contiguous in (upt, ele)
+  // solution: for a field, the ne elements of this CTA are contiguous in (upt, ele)
 #pragma unroll
   for (int k = 0; k < NF; k++)
   {
     const double *src = A.u0 + (size_t)NU * (e0 + (size_t)A.n_eles * k);
-    for (int i = tid; i < ne * NU; i += NT) S.su[i / NU][k][i % NU] = src[i];
+    for (int i = tid; i < ne * NU; i += NT) cp_async8(&S.su[k][i], src + i);
   }
-  for (int i = tid; i < ne * EM; i += NT) S.em[i / EM][i % EM] = A.em[(size_t)e0 * EM + i];
+  {
+    const double *src = (const double *)A.tab;
+    double *dst = (double *)&S.tab;
+    constexpr int nd = sizeof(fused_tables) / sizeof(double);
+    for (int i = tid; i < nd; i += NT) cp_async8(dst + i, src + i);
+  }
+  for (int i = tid; i < ne * EM; i += NT) cp_async8(&S.em[0][0] + i, A.em + (size_t)e0 * EM + i);
+  for (int i = tid; i < ne * 6; i += NT) cp_async8(&S.bs[0][0] + i, A.bmask + (size_t)e0 * 6 + i);
+  if (with_neighbours)
+  {
+    // neighbour face values, gathered through the rotation permutation straight into sx
+    for (int q = tid; q < ne * NFP; q += NT)
+    {
+      int e = q / NFP, r = q - e * NFP, f = r / NN, j = r - f * NN;
+      int info = A.finfo[(size_t)(e0 + e) * 6 + f];
+      int pj = A.tab->perm[(info & 7) * 36 + j];
+      const double *nb = A.fu_cur + (size_t)A.nbr[(size_t)(e0 + e) * 6 + f] * (NF * NN) + pj;
+#pragma unroll
+      for (int k = 0; k < NF; k++) cp_async8(&S.sx[k][q], nb + k * NN);
+    }
+  }
   for (int i = tid; i < ne * 6; i += NT)
   {
-    S.nbr[i / 6][i % 6] = A.nbr[(size_t)e0 * 6 + i];
-    S.finfo[i / 6][i % 6] = A.finfo[(size_t)e0 * 6 + i];
+    S.nbr[0][i] = A.nbr[(size_t)e0 * 6 + i];
+    S.finfo[0][i] = A.finfo[(size_t)e0 * 6 + i];
   }
+  cp_async_commit();
 }
 
-// own face value of field k at face-local flux point j of face f: sum_i L[i] * su[line]
+// own face value of one field at a flux point: sum_i L[i] * field[line]
 template <int N>
 __device__ __forceinline__ double face_value(const double *field_upts, const double *L, int base, int stride)
 {
@@ -339,78 +372,72 @@ __device__ __forceinline__ double face_value(const double *field_upts, const dou
   return acc;
 }
 
-// LDG common solution minus own value at every own flux point -> S.sx   (delta_disu_fpts of the reference)
-template <int N, int E, int NT>
-__device__ __forceinline__ void phase_delta(smem_layout<N, E> &S, const fused_args &A, int e0, int ne)
+// LDG common solution minus own value at every own flux point, in place over the staged neighbour values in S.sx
+// (delta_disu_fpts of the reference)
+template <int N, int E, int NT, typename SM>
+__device__ __forceinline__ void phase_delta(SM &S, const fused_args &A, int ne)
 {
-  constexpr int NFP = 6 * N * N, NN = N * N;
+  constexpr int NU = N * N * N, NFP = 6 * N * N, NN = N * N;
   for (int q = threadIdx.x; q < ne * NFP; q += NT)
   {
     int e = q / NFP, r = q - e * NFP, f = r / NN, j = r - f * NN;
-    const int base = S.tab.lbase[r], stride = face_stride<N>(f);
+    const int base = e * NU + S.tab.lbase[r], stride = face_stride<N>(f);
     double L[N];
 #pragma unroll
     for (int i = 0; i < N; i++) L[i] = face_sgn(f) > 0 ? S.tab.Lp[i] : S.tab.Lm[i];
-    int info = S.finfo[e][f];
-    int pj = S.tab.perm[(info & 7) * 36 + j];
-    const double *nb = A.fu_cur + (size_t)S.nbr[e][f] * (NF * NN) + pj;
-    double beta = A.P.ldg_beta * (double)A.bsign[(size_t)(e0 + e) * NFP + r];
-    bool is_right = (info & 4) != 0;
-    double un[NF];
-#pragma unroll
-    for (int k = 0; k < NF; k++) un[k] = nb[k * NN];
+    const bool is_right = (S.finfo[e][f] & 4) != 0;
+    const double beta = ((S.bs[e][f] >> j) & 1ull) ? -A.P.ldg_beta : A.P.ldg_beta;
 #pragma unroll
     for (int k = 0; k < NF; k++)
     {
-      double uo = face_value<N>(S.su[e][k], L, base, stride);
-      double ul = is_right ? un[k] : uo, ur = is_right ? uo : un[k];
+      double uo = face_value<N>(S.su[k], L, base, stride);
+      double un = S.sx[k][q];
+      double ul = is_right ? un : uo, ur = is_right ? uo : un;
       double uc = __dsub_rn(__dmul_rn(0.5, __dadd_rn(ul, ur)), __dmul_rn(beta, __dsub_rn(ul, ur)));
-      S.sx[e][k][r] = uc - uo;
+      S.sx[k][q] = uc - uo;
     }
   }
 }
 
-// corrected physical gradient at the solution points -> S.sg
-template <int N, int E, int NT>
-__device__ __forceinline__ void phase_gradient(smem_layout<N, E> &S, int ne)
+// corrected physical gradient of the five fields at one solution point, in registers: g[k + 5 d]
+template <int N, int E, typename SM>
+__device__ __forceinline__ void point_gradient(const SM &S, int e, int p, double *__restrict__ g)
 {
-  constexpr int NU = N * N * N, NN = N * N;
-  for (int q = threadIdx.x; q < ne * NU; q += NT)
+  constexpr int NU = N * N * N, NFP = 6 * N * N, NN = N * N;
+  const int a = p % N, b = (p / N) % N, c = p / NN;
+  double J[9];
+#pragma unroll
+  for (int i = 0; i < 9; i++) J[i] = S.em[e][i];
+  const double inv_detjac = 1.0 / S.em[e][9];
+  double Da[N], Db[N], Dc[N];
+#pragma unroll
+  for (int i = 0; i < N; i++) { Da[i] = S.tab.D[a * N + i]; Db[i] = S.tab.D[b * N + i]; Dc[i] = S.tab.D[c * N + i]; }
+  const double c52 = S.tab.c5[2 * N + a], c54 = S.tab.c5[4 * N + a], c51 = S.tab.c5[1 * N + b], c53 = S.tab.c5[3 * N + b],
+               c50 = S.tab.c5[0 * N + c], c55 = S.tab.c5[5 * N + c];
+  const int fb = e * NFP;
+  const int f0 = fb + 0 * NN + fpt_of_upt<N>(0, a, b, c), f1 = fb + 1 * NN + fpt_of_upt<N>(1, a, b, c), f2 = fb + 2 * NN + fpt_of_upt<N>(2, a, b, c),
+            f3 = fb + 3 * NN + fpt_of_upt<N>(3, a, b, c), f4 = fb + 4 * NN + fpt_of_upt<N>(4, a, b, c), f5 = fb + 5 * NN + fpt_of_upt<N>(5, a, b, c);
+  const int ub = e * NU;
+#pragma unroll
+  for (int k = 0; k < NF; k++)
   {
-    int e = q / NU, p = q - e * NU;
-    int a = p % N, b = (p / N) % N, c = p / NN;
-    double J[9];
+    const double *u = S.su[k] + ub;
+    const double *dl = S.sx[k];
+    double g0 = 0.0, g1 = 0.0, g2 = 0.0;
 #pragma unroll
-    for (int i = 0; i < 9; i++) J[i] = S.em[e][i];
-    const double inv_detjac = 1.0 / S.em[e][9];
-    double Da[N], Db[N], Dc[N];
+    for (int i = 0; i < N; i++) g0 += Da[i] * u[i + N * b + NN * c];
 #pragma unroll
-    for (int i = 0; i < N; i++) { Da[i] = S.tab.D[a * N + i]; Db[i] = S.tab.D[b * N + i]; Dc[i] = S.tab.D[c * N + i]; }
-    const double c52 = S.tab.c5[2 * N + a], c54 = S.tab.c5[4 * N + a], c51 = S.tab.c5[1 * N + b], c53 = S.tab.c5[3 * N + b],
-                 c50 = S.tab.c5[0 * N + c], c55 = S.tab.c5[5 * N + c];
-    const int f0 = 0 * NN + fpt_of_upt<N>(0, a, b, c), f1 = 1 * NN + fpt_of_upt<N>(1, a, b, c), f2 = 2 * NN + fpt_of_upt<N>(2, a, b, c),
-              f3 = 3 * NN + fpt_of_upt<N>(3, a, b, c), f4 = 4 * NN + fpt_of_upt<N>(4, a, b, c), f5 = 5 * NN + fpt_of_upt<N>(5, a, b, c);
+    for (int i = 0; i < N; i++) g1 += Db[i] * u[a + N * i + NN * c];
 #pragma unroll
-    for (int k = 0; k < NF; k++)
-    {
-      const double *u = S.su[e][k];
-      const double *dl = S.sx[e][k];
-      double g0 = 0.0, g1 = 0.0, g2 = 0.0;
-#pragma unroll
-      for (int i = 0; i < N; i++) g0 += Da[i] * u[i + N * b + NN * c];
-#pragma unroll
-      for (int i = 0; i < N; i++) g1 += Db[i] * u[a + N * i + NN * c];
-#pragma unroll
-      for (int i = 0; i < N; i++) g2 += Dc[i] * u[a + N * b + NN * i];
-      g0 += c52 * dl[f2]; g0 += c54 * dl[f4];
-      g1 += c51 * dl[f1]; g1 += c53 * dl[f3];
-      g2 += c50 * dl[f0]; g2 += c55 * dl[f5];
-      g0 *= inv_detjac; g1 *= inv_detjac; g2 *= inv_detjac;
-      // physical gradient: g(d) = sum_l (1/detJ * gt(l)) * JGinv(l,d)    (reference src/eles.cpp:1955-2011)
-      S.sg[e][0][k][p] = g0 * J[0] + g1 * J[1] + g2 * J[2];
-      S.sg[e][1][k][p] = g0 * J[3] + g1 * J[4] + g2 * J[5];
-      S.sg[e][2][k][p] = g0 * J[6] + g1 * J[7] + g2 * J[8];
-    }
+    for (int i = 0; i < N; i++) g2 += Dc[i] * u[a + N * b + NN * i];
+    g0 += c52 * dl[f2]; g0 += c54 * dl[f4];
+    g1 += c51 * dl[f1]; g1 += c53 * dl[f3];
+    g2 += c50 * dl[f0]; g2 += c55 * dl[f5];
+    g0 *= inv_detjac; g1 *= inv_detjac; g2 *= inv_detjac;
+    // physical gradient: g(d) = sum_l (1/detJ * gt(l)) * JGinv(l,d)    (reference src/eles.cpp:1955-2011)
+    g[k] = g0 * J[0] + g1 * J[1] + g2 * J[2];
+    g[k + 5] = g0 * J[3] + g1 * J[4] + g2 * J[5];
+    g[k + 10] = g0 * J[6] + g1 * J[7] + g2 * J[8];
   }
 }
 
@@ -419,32 +446,42 @@ template <int N, int E, int NT, int MINB>
 __global__ void __launch_bounds__(NT, MINB) k_grad(fused_args A)
 {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  smem_layout<N, E> &S = *reinterpret_cast<smem_layout<N, E> *>(smem_raw);
-  constexpr int NFP = 6 * N * N, NN = N * N;
+  typedef smem_layout<N, E> SM;
+  SM &S = *reinterpret_cast<SM *>(smem_raw);
+  constexpr int NU = N * N * N, NFP = 6 * N * N, NN = N * N;
   const int e0 = blockIdx.x * E;
   const int ne = min(E, A.n_eles - e0);
-  load_block<N, E, NT>(S, A, e0, ne);
+  stage_inputs<N, E, NT>(S, A, e0, ne, true);
+  cp_async_wait_all();
   __syncthreads();
-  phase_delta<N, E, NT>(S, A, e0, ne);
+  phase_delta<N, E, NT>(S, A, ne);
   __syncthreads();
-  phase_gradient<N, E, NT>(S, ne);
+  for (int q = threadIdx.x; q < ne * NU; q += NT)
+  {
+    double g[NF * ND];
+    point_gradient<N, E>(S, q / NU, q % NU, g);
+#pragma unroll
+    for (int d = 0; d < ND; d++)
+#pragma unroll
+      for (int k = 0; k < NF; k++) S.sg[d][k][q] = g[k + NF * d];
+  }
   __syncthreads();
   // u and grad u at the own flux points (opp_0, opp_6; for an affine element extrapolation and the transform to
   // physical space commute), viscous flux there, dotted with the face's left normal
   for (int q = threadIdx.x; q < ne * NFP; q += NT)
   {
     int e = q / NFP, r = q - e * NFP, f = r / NN, j = r - f * NN;
-    const int base = S.tab.lbase[r], stride = face_stride<N>(f);
+    const int base = e * NU + S.tab.lbase[r], stride = face_stride<N>(f);
     double L[N];
 #pragma unroll
     for (int i = 0; i < N; i++) L[i] = face_sgn(f) > 0 ? S.tab.Lp[i] : S.tab.Lm[i];
     double u[NF], g[NF * ND], fv[NF * ND];
 #pragma unroll
-    for (int k = 0; k < NF; k++) u[k] = face_value<N>(S.su[e][k], L, base, stride);
+    for (int k = 0; k < NF; k++) u[k] = face_value<N>(S.su[k], L, base, stride);
 #pragma unroll
     for (int d = 0; d < ND; d++)
 #pragma unroll
-      for (int k = 0; k < NF; k++) g[k + NF * d] = face_value<N>(S.sg[e][d][k], L, base, stride);
+      for (int k = 0; k < NF; k++) g[k + NF * d] = face_value<N>(S.sg[d][k], L, base, stride);
     vis_flux_fast(u, g, fv, A.P);
     const double *n = &S.em[e][10 + 4 * f + 1];
     const double n0 = n[0], n1 = n[1], n2 = n[2];
@@ -459,37 +496,50 @@ template <int N, int E, int NT, int MINB, bool VISC>
 __global__ void __launch_bounds__(NT, MINB) k_resid(fused_args A)
 {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  smem_layout<N, E> &S = *reinterpret_cast<smem_layout<N, E> *>(smem_raw);
+  typedef typename std::conditional<VISC, smem_layout_visc<N, E>, smem_layout<N, E>>::type SM;
+  SM &S = *reinterpret_cast<SM *>(smem_raw);
   constexpr int NU = N * N * N, NFP = 6 * N * N, NN = N * N;
+  const int tid = threadIdx.x;
   const int e0 = blockIdx.x * E;
   const int ne = min(E, A.n_eles - e0);
-  load_block<N, E, NT>(S, A, e0, ne);
-  __syncthreads();
-  if (VISC)
+  stage_inputs<N, E, NT>(S, A, e0, ne, true);
+  if constexpr (VISC)
   {
-    phase_delta<N, E, NT>(S, A, e0, ne);
-    __syncthreads();
-    phase_gradient<N, E, NT>(S, ne);
+    // own and neighbour one-sided viscous normal fluxes: needed only for the common flux, staged now
+    for (int q = tid; q < ne * NFP; q += NT)
+    {
+      int e = q / NFP, r = q - e * NFP, f = r / NN, j = r - f * NN;
+      int info = A.finfo[(size_t)(e0 + e) * 6 + f];
+      int pj = A.tab->perm[(info & 7) * 36 + j];
+      const double *po = A.fv + ((size_t)(e0 + e) * 6 + f) * (4 * NN) + j;
+      const double *pn = A.fv + (size_t)A.nbr[(size_t)(e0 + e) * 6 + f] * (4 * NN) + pj;
+#pragma unroll
+      for (int k = 0; k < 4; k++) { cp_async8(&S.sv[0][k][q], po + k * NN); cp_async8(&S.sv[1][k][q], pn + k * NN); }
+    }
+    cp_async_commit();
+  }
+  cp_async_wait_all();
+  __syncthreads();
+  if constexpr (VISC)
+  {
+    phase_delta<N, E, NT>(S, A, ne);
     __syncthreads();
   }
-  // transformed total flux at the solution points -> S.sg (overwrites the gradient point by point)
-  for (int q = threadIdx.x; q < ne * NU; q += NT)
+  // transformed total flux at the solution points -> S.sg
+  for (int q = tid; q < ne * NU; q += NT)
   {
-    int e = q / NU, p = q - e * NU;
+    const int e = q / NU;
     double J[9];
 #pragma unroll
     for (int i = 0; i < 9; i++) J[i] = S.em[e][i];
     double u[NF], f[NF * ND];
 #pragma unroll
-    for (int k = 0; k < NF; k++) u[k] = S.su[e][k][p];
+    for (int k = 0; k < NF; k++) u[k] = S.su[k][q];
     inv_flux_fast(u, f, A.P.gamma - 1.0);
-    if (VISC)
+    if constexpr (VISC)
     {
       double g[NF * ND], fv[NF * ND];
-#pragma unroll
-      for (int d = 0; d < ND; d++)
-#pragma unroll
-        for (int k = 0; k < NF; k++) g[k + NF * d] = S.sg[e][d][k][p];
+      point_gradient<N, E>(S, e, q - e * NU, g);
       vis_flux_fast(u, g, fv, A.P);
 #pragma unroll
       for (int d = 0; d < ND; d++)
@@ -500,51 +550,58 @@ __global__ void __launch_bounds__(NT, MINB) k_resid(fused_args A)
 #pragma unroll
     for (int k = 0; k < NF; k++)
 #pragma unroll
-      for (int l = 0; l < ND; l++) S.sg[e][l][k][p] = J[l] * f[k] + J[l + 3] * f[k + 5] + J[l + 6] * f[k + 10];
+      for (int l = 0; l < ND; l++) S.sg[l][k][q] = J[l] * f[k] + J[l + 3] * f[k + 5] + J[l + 6] * f[k + 10];
   }
   __syncthreads();
-  // common flux minus own normal flux at every own flux point -> S.sx
-  for (int q = threadIdx.x; q < ne * NFP; q += NT)
+  if constexpr (VISC)
+  {
+    // the LDG deltas are consumed: fetch the neighbour face values again (L2) for the Riemann solver
+    for (int q = tid; q < ne * NFP; q += NT)
+    {
+      int e = q / NFP, r = q - e * NFP, f = r / NN, j = r - f * NN;
+      int pj = S.tab.perm[(S.finfo[e][f] & 7) * 36 + j];
+      const double *nb = A.fu_cur + (size_t)S.nbr[e][f] * (NF * NN) + pj;
+#pragma unroll
+      for (int k = 0; k < NF; k++) cp_async8(&S.sx[k][q], nb + k * NN);
+    }
+    cp_async_commit();
+    cp_async_wait_all();
+    __syncthreads();
+  }
+  // common flux minus own normal flux at every own flux point, in place over the neighbour values in S.sx
+  for (int q = tid; q < ne * NFP; q += NT)
   {
     int e = q / NFP, r = q - e * NFP, f = r / NN, j = r - f * NN;
-    const int base = S.tab.lbase[r], stride = face_stride<N>(f);
+    const int base = e * NU + S.tab.lbase[r], stride = face_stride<N>(f);
     const int sgn = face_sgn(f), dir = face_dir(f);
     double L[N];
 #pragma unroll
     for (int i = 0; i < N; i++) L[i] = sgn > 0 ? S.tab.Lp[i] : S.tab.Lm[i];
     const int info = S.finfo[e][f];
     const bool is_right = (info & 4) != 0;
-    const int pj = S.tab.perm[(info & 7) * 36 + j];
-    const size_t nblk = (size_t)S.nbr[e][f];
     const double *geo = &S.em[e][10 + 4 * f];
     const double tdA = geo[0];
     const double n[3] = {geo[1], geo[2], geo[3]};
     double uo[NF], un[NF], fn[NF];
-    const double *nb = A.fu_cur + nblk * (NF * NN) + pj;
 #pragma unroll
-    for (int k = 0; k < NF; k++) un[k] = nb[k * NN];
-    double fvo[4], fvn[4];
-    if (VISC)
+    for (int k = 0; k < NF; k++)
     {
-      const double *po = A.fv + ((size_t)(e0 + e) * 6 + f) * (4 * NN) + j;
-      const double *pn = A.fv + nblk * (4 * NN) + pj;
-      const double flip = (info & 8) ? -1.0 : 1.0; // a partition neighbour used its own (opposite) normal
-#pragma unroll
-      for (int k = 0; k < 4; k++) { fvo[k] = po[k * NN]; fvn[k] = flip * pn[k * NN]; }
+      un[k] = S.sx[k][q];
+      uo[k] = face_value<N>(S.su[k], L, base, stride);
     }
-#pragma unroll
-    for (int k = 0; k < NF; k++) uo[k] = face_value<N>(S.su[e][k], L, base, stride);
     if (is_right) riemann_fast(un, uo, n, fn, A.P);
     else riemann_fast(uo, un, n, fn, A.P);
-    if (VISC)
+    if constexpr (VISC)
     {
-      const double beta = A.P.ldg_beta * (double)A.bsign[(size_t)(e0 + e) * NFP + r];
+      const double beta = ((S.bs[e][f] >> j) & 1ull) ? -A.P.ldg_beta : A.P.ldg_beta;
       const double wl = 0.5 + beta, wr = 0.5 - beta, tau = A.P.ldg_tau;
+      const double flip = (info & 8) ? -1.0 : 1.0; // a partition neighbour used its own (opposite) normal
       fn[0] -= tau * (is_right ? uo[0] - un[0] : un[0] - uo[0]);
 #pragma unroll
       for (int k = 1; k < NF; k++)
       {
-        const double fl = is_right ? fvn[k - 1] : fvo[k - 1], fr = is_right ? fvo[k - 1] : fvn[k - 1];
+        const double fo = S.sv[0][k - 1][q], fnb = flip * S.sv[1][k - 1][q];
+        const double fl = is_right ? fnb : fo, fr = is_right ? fo : fnb;
         const double du = is_right ? uo[k] - un[k] : un[k] - uo[k];
         fn[k] += (wl * fl + wr * fr) - tau * du;
       }
@@ -554,74 +611,83 @@ __global__ void __launch_bounds__(NT, MINB) k_resid(fused_args A)
 #pragma unroll
     for (int k = 0; k < NF; k++)
     {
-      double ntd = face_value<N>(S.sg[e][dir][k], L, base, stride);
-      S.sx[e][k][r] = fn[k] * s_side - s_ntd * ntd;
+      double ntd = face_value<N>(S.sg[dir][k], L, base, stride);
+      S.sx[k][q] = fn[k] * s_side - s_ntd * ntd;
     }
   }
   __syncthreads();
   // divergence + correction, RK update
-  for (int q = threadIdx.x; q < ne * NU; q += NT)
+  for (int q = tid; q < ne * NU; q += NT)
   {
-    int e = q / NU, p = q - e * NU;
-    int a = p % N, b = (p / N) % N, c = p / NN;
+    const int e = q / NU, p = q - e * NU;
+    const int a = p % N, b = (p / N) % N, c = p / NN;
     const int ge = e0 + e;
     const double inv_detjac = 1.0 / S.em[e][9];
     const double dtl = A.dt_local ? A.dt_local[ge] : A.rk.dt;
+    const size_t gi0 = p + (size_t)NU * ge, gstride = (size_t)NU * A.n_eles;
+    double u1v[NF];
+    if (A.do_update && A.rk.mode != 0)
+    {
+#pragma unroll
+      for (int k = 0; k < NF; k++) u1v[k] = A.u1[gi0 + k * gstride];
+    }
     double Da[N], Db[N], Dc[N];
 #pragma unroll
     for (int i = 0; i < N; i++) { Da[i] = S.tab.D[a * N + i]; Db[i] = S.tab.D[b * N + i]; Dc[i] = S.tab.D[c * N + i]; }
     const double c30 = S.tab.c3[0 * N + c], c31 = S.tab.c3[1 * N + b], c32 = S.tab.c3[2 * N + a], c33 = S.tab.c3[3 * N + b],
                  c34 = S.tab.c3[4 * N + a], c35 = S.tab.c3[5 * N + c];
-    const int f0 = 0 * NN + fpt_of_upt<N>(0, a, b, c), f1 = 1 * NN + fpt_of_upt<N>(1, a, b, c), f2 = 2 * NN + fpt_of_upt<N>(2, a, b, c),
-              f3 = 3 * NN + fpt_of_upt<N>(3, a, b, c), f4 = 4 * NN + fpt_of_upt<N>(4, a, b, c), f5 = 5 * NN + fpt_of_upt<N>(5, a, b, c);
+    const int fb = e * NFP;
+    const int f0 = fb + 0 * NN + fpt_of_upt<N>(0, a, b, c), f1 = fb + 1 * NN + fpt_of_upt<N>(1, a, b, c), f2 = fb + 2 * NN + fpt_of_upt<N>(2, a, b, c),
+              f3 = fb + 3 * NN + fpt_of_upt<N>(3, a, b, c), f4 = fb + 4 * NN + fpt_of_upt<N>(4, a, b, c), f5 = fb + 5 * NN + fpt_of_upt<N>(5, a, b, c);
+    const int ub = e * NU;
 #pragma unroll
     for (int k = 0; k < NF; k++)
     {
       double acc = 0.0;
 #pragma unroll
-      for (int i = 0; i < N; i++) acc += Da[i] * S.sg[e][0][k][i + N * b + NN * c];
+      for (int i = 0; i < N; i++) acc += Da[i] * S.sg[0][k][ub + i + N * b + NN * c];
 #pragma unroll
-      for (int i = 0; i < N; i++) acc += Db[i] * S.sg[e][1][k][a + N * i + NN * c];
+      for (int i = 0; i < N; i++) acc += Db[i] * S.sg[1][k][ub + a + N * i + NN * c];
 #pragma unroll
-      for (int i = 0; i < N; i++) acc += Dc[i] * S.sg[e][2][k][a + N * b + NN * i];
-      const double *dfl = S.sx[e][k];
+      for (int i = 0; i < N; i++) acc += Dc[i] * S.sg[2][k][ub + a + N * b + NN * i];
+      const double *dfl = S.sx[k];
       acc += c30 * dfl[f0]; acc += c31 * dfl[f1]; acc += c32 * dfl[f2];
       acc += c33 * dfl[f3]; acc += c34 * dfl[f4]; acc += c35 * dfl[f5];
-      size_t gi = p + (size_t)NU * (ge + (size_t)A.n_eles * k);
+      const size_t gi = gi0 + k * gstride;
       if (A.keep_residual) A.div[gi] = acc;
       if (A.do_update)
       {
-        double u = S.su[e][k][p];
-        double rr = acc * inv_detjac;
+        double u = S.su[k][q];
+        const double rr = acc * inv_detjac;
         if (A.rk.copy_u1) A.u1[gi] = u;
         if (A.rk.mode == 0)
           u -= dtl / A.rk.fac * rr;
         else if (A.rk.mode == 1)
-          u = A.rk.c1 * u + A.rk.c2 * A.u1[gi] + dtl / A.rk.fac * (-rr);
+          u = A.rk.c1 * u + A.rk.c2 * u1v[k] + dtl / A.rk.fac * (-rr);
         else
         {
-          double dlt = A.rk.c1 * A.u1[gi] + dtl * (-rr);
+          const double dlt = A.rk.c1 * u1v[k] + dtl * (-rr);
           A.u1[gi] = dlt;
           u += A.rk.c2 * dlt;
         }
         A.u0_out[gi] = u;
-        S.su[e][k][p] = u;
+        S.su[k][q] = u;
       }
     }
   }
   if (!A.do_update) return;
   __syncthreads();
   // face values of the updated solution for the next stage (extrapolate_solution)
-  for (int q = threadIdx.x; q < ne * NFP; q += NT)
+  for (int q = tid; q < ne * NFP; q += NT)
   {
     int e = q / NFP, r = q - e * NFP, f = r / NN, j = r - f * NN;
-    const int base = S.tab.lbase[r], stride = face_stride<N>(f);
+    const int base = e * NU + S.tab.lbase[r], stride = face_stride<N>(f);
     double L[N];
 #pragma unroll
     for (int i = 0; i < N; i++) L[i] = face_sgn(f) > 0 ? S.tab.Lp[i] : S.tab.Lm[i];
     double *out = A.fu_next + ((size_t)(e0 + e) * 6 + f) * (NF * NN) + j;
 #pragma unroll
-    for (int k = 0; k < NF; k++) out[k * NN] = face_value<N>(S.su[e][k], L, base, stride);
+    for (int k = 0; k < NF; k++) out[k * NN] = face_value<N>(S.su[k], L, base, stride);
   }
 }
 
@@ -630,20 +696,22 @@ template <int N, int E, int NT>
 __global__ void __launch_bounds__(NT) k_face_values(fused_args A)
 {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  smem_layout<N, E> &S = *reinterpret_cast<smem_layout<N, E> *>(smem_raw);
-  constexpr int NFP = 6 * N * N, NN = N * N;
+  typedef smem_layout<N, E> SM;
+  SM &S = *reinterpret_cast<SM *>(smem_raw);
+  constexpr int NU = N * N * N, NFP = 6 * N * N, NN = N * N;
   const int e0 = blockIdx.x * E;
   const int ne = min(E, A.n_eles - e0);
-  load_block<N, E, NT>(S, A, e0, ne);
+  stage_inputs<N, E, NT>(S, A, e0, ne, false);
+  cp_async_wait_all();
   __syncthreads();
   for (int q = threadIdx.x; q < ne * NFP; q += NT)
   {
     int e = q / NFP, r = q - e * NFP, f = r / NN, j = r - f * NN;
-    const int base = S.tab.lbase[r], stride = face_stride<N>(f);
+    const int base = e * NU + S.tab.lbase[r], stride = face_stride<N>(f);
     const double *L = face_sgn(f) > 0 ? S.tab.Lp : S.tab.Lm;
     double *out = A.fu_next + ((size_t)(e0 + e) * 6 + f) * (NF * NN) + j;
 #pragma unroll
-    for (int k = 0; k < NF; k++) out[k * NN] = face_value<N>(S.su[e][k], L, base, stride);
+    for (int k = 0; k < NF; k++) out[k * NN] = face_value<N>(S.su[k], L, base, stride);
   }
 }
 
@@ -668,7 +736,8 @@ struct hf_fused_state
   double *fv = nullptr;
   double *em = nullptr;
   int *nbr = nullptr;
-  signed char *finfo = nullptr, *bsign = nullptr;
+  int *finfo = nullptr;
+  unsigned long long *bmask = nullptr;
   fused_tables *tab = nullptr;
   int *mpi_blk = nullptr; // [n_mpi] own face block of every partition interface
   double *out_u = nullptr, *out_g = nullptr;
@@ -854,7 +923,8 @@ int hf_fused_prepare(hf_ctx *c)
   if (!ok) return no(Z->why);
   // connectivity per (ele, face)
   std::vector<int> nbr((size_t)ne * 6, -1);
-  std::vector<signed char> finfo((size_t)ne * 6, 0), bsign((size_t)ne * NFP, 1);
+  std::vector<int> finfo((size_t)ne * 6, 0);
+  std::vector<unsigned long long> bmask((size_t)ne * 6, 0ull);
   std::vector<double> em((size_t)ne * EM, 0.);
   for (int i = 0; i < ne; i++)
   {
@@ -868,15 +938,18 @@ int hf_fused_prepare(hf_ctx *c)
     int el = I.h_ele_l[i], fl = I.h_loc_l[i], er = I.h_ele_r[i], fr = I.h_loc_r[i], rot = I.h_rot[i];
     nbr[(size_t)el * 6 + fl] = er * 6 + fr;
     nbr[(size_t)er * 6 + fr] = el * 6 + fl;
-    finfo[(size_t)el * 6 + fl] = (signed char)rot;
-    finfo[(size_t)er * 6 + fr] = (signed char)(rot + 4);
+    finfo[(size_t)el * 6 + fl] = rot;
+    finfo[(size_t)er * 6 + fr] = rot + 4;
     // the right element uses the left element's normal; its own tdA stays
     for (int q = 1; q < 4; q++) em[(size_t)er * EM + 10 + 4 * fr + q] = e.h_face_geo[(size_t)el * 24 + 4 * fl + q];
     for (int j = 0; j < NN; j++)
     {
       signed char s = e.h_own_sign[(size_t)el * NFP + fl * NN + j];
-      bsign[(size_t)el * NFP + fl * NN + j] = s;
-      bsign[(size_t)er * NFP + fr * NN + T.perm[rot * 36 + j]] = s;
+      if (s < 0)
+      {
+        bmask[(size_t)el * 6 + fl] |= 1ull << j;
+        bmask[(size_t)er * 6 + fr] |= 1ull << T.perm[rot * 36 + j];
+      }
     }
   }
   hf_mpi_inters_dev &M = c->mpis[2];
@@ -887,9 +960,10 @@ int hf_fused_prepare(hf_ctx *c)
   {
     int el = M.h_ele_l[i], fl = M.h_loc_l[i];
     nbr[(size_t)el * 6 + fl] = ne * 6 + i; // receive block behind the last element
-    finfo[(size_t)el * 6 + fl] = (signed char)(M.h_rot[i] + 8);
+    finfo[(size_t)el * 6 + fl] = M.h_rot[i] + 8;
     mpi_blk[i] = el * 6 + fl;
-    for (int j = 0; j < NN; j++) bsign[(size_t)el * NFP + fl * NN + j] = e.h_own_sign[(size_t)el * NFP + fl * NN + j];
+    for (int j = 0; j < NN; j++)
+      if (e.h_own_sign[(size_t)el * NFP + fl * NN + j] < 0) bmask[(size_t)el * 6 + fl] |= 1ull << j;
   }
   for (size_t q = 0; q < nbr.size(); q++)
     if (nbr[q] < 0) return no("an element face has no neighbour");
@@ -902,7 +976,7 @@ int hf_fused_prepare(hf_ctx *c)
   if (hf_alloc_copy(c, &Z->em, em.data(), em.size())) return 1;
   if (hf_alloc_copy(c, &Z->nbr, nbr.data(), nbr.size())) return 1;
   if (hf_alloc_copy(c, &Z->finfo, finfo.data(), finfo.size())) return 1;
-  if (hf_alloc_copy(c, &Z->bsign, bsign.data(), bsign.size())) return 1;
+  if (hf_alloc_copy(c, &Z->bmask, bmask.data(), bmask.size())) return 1;
   if (hf_alloc_copy(c, &Z->tab, &T, 1)) return 1;
   if (hf_alloc_copy(c, &Z->mpi_blk, mpi_blk.data(), mpi_blk.size())) return 1;
   if (M.n_inters)
@@ -924,14 +998,14 @@ template <int N, int E, int NT, int MINB>
 int launch_all(hf_ctx *c, hf_fused_state *Z, fused_args &A, int what)
 {
   // what: 0 face values, 1 gradient kernel, 2 residual kernel
-  const size_t smem = sizeof(smem_layout<N, E>);
+  const size_t smem = sizeof(smem_layout<N, E>), smem_v = sizeof(smem_layout_visc<N, E>);
   const int grid = (Z->n_eles + E - 1) / E;
   static bool attr_done = false;
   if (!attr_done)
   {
     HF_CUDA(cudaFuncSetAttribute(k_face_values<N, E, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     HF_CUDA(cudaFuncSetAttribute(k_grad<N, E, NT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    HF_CUDA(cudaFuncSetAttribute(k_resid<N, E, NT, MINB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    HF_CUDA(cudaFuncSetAttribute(k_resid<N, E, NT, MINB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_v));
     HF_CUDA(cudaFuncSetAttribute(k_resid<N, E, NT, MINB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     // ask for the largest shared-memory carve-out so that MINB blocks fit on an SM
     HF_CUDA(cudaFuncSetAttribute(k_grad<N, E, NT, MINB>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
@@ -946,7 +1020,7 @@ int launch_all(hf_ctx *c, hf_fused_state *Z, fused_args &A, int what)
   else
   {
     hf_ktimer_begin(c);
-    if (A.viscous) k_resid<N, E, NT, MINB, true><<<grid, NT, smem, c->stream>>>(A);
+    if (A.viscous) k_resid<N, E, NT, MINB, true><<<grid, NT, smem_v, c->stream>>>(A);
     else k_resid<N, E, NT, MINB, false><<<grid, NT, smem, c->stream>>>(A);
     hf_ktimer_end(c);
   }
@@ -993,7 +1067,7 @@ void base_args(hf_ctx *c, hf_fused_state *Z, fused_args &A)
   A.em = Z->em;
   A.nbr = Z->nbr;
   A.finfo = Z->finfo;
-  A.bsign = Z->bsign;
+  A.bmask = Z->bmask;
   A.dt_local = (c->prm.dt_type == 2) ? e.dt_local : nullptr;
   A.tab = Z->tab;
   A.P = c->phys;
