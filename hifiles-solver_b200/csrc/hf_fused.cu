@@ -643,16 +643,19 @@ __global__ void __launch_bounds__(NT, MINB) k_resid(fused_args A)
 #pragma unroll
     for (int k = 0; k < NF; k++)
     {
-      double acc = 0.0;
+      // four independent partial sums (the three directional derivatives and the correction): short dependency chains
+      double a0 = 0.0, a1 = 0.0, a2 = 0.0;
 #pragma unroll
-      for (int i = 0; i < N; i++) acc += Da[i] * S.sg[0][k][ub + i + N * b + NN * c];
-#pragma unroll
-      for (int i = 0; i < N; i++) acc += Db[i] * S.sg[1][k][ub + a + N * i + NN * c];
-#pragma unroll
-      for (int i = 0; i < N; i++) acc += Dc[i] * S.sg[2][k][ub + a + N * b + NN * i];
+      for (int i = 0; i < N; i++)
+      {
+        a0 += Da[i] * S.sg[0][k][ub + i + N * b + NN * c];
+        a1 += Db[i] * S.sg[1][k][ub + a + N * i + NN * c];
+        a2 += Dc[i] * S.sg[2][k][ub + a + N * b + NN * i];
+      }
       const double *dfl = S.sx[k];
-      acc += c30 * dfl[f0]; acc += c31 * dfl[f1]; acc += c32 * dfl[f2];
-      acc += c33 * dfl[f3]; acc += c34 * dfl[f4]; acc += c35 * dfl[f5];
+      double a3 = c30 * dfl[f0] + c31 * dfl[f1] + c32 * dfl[f2];
+      double a4 = c33 * dfl[f3] + c34 * dfl[f4] + c35 * dfl[f5];
+      const double acc = ((a0 + a1) + a2) + (a3 + a4);
       const size_t gi = gi0 + k * gstride;
       if (A.keep_residual) A.div[gi] = acc;
       if (A.do_update)
@@ -1040,10 +1043,10 @@ int launch(hf_ctx *c, hf_fused_state *Z, fused_args &A, int what)
   case 4:
   {
     static int cfg = getenv("HF_FUSED_CFG") ? atoi(getenv("HF_FUSED_CFG")) : 0;
-    if (cfg == 1) return launch_all<5, 1, 64, 8>(c, Z, A, what);
-    if (cfg == 2) return launch_all<5, 2, 160, 3>(c, Z, A, what);
-    if (cfg == 3) return launch_all<5, 4, 256, 2>(c, Z, A, what);
-    if (cfg == 4) return launch_all<5, 1, 128, 8>(c, Z, A, what);
+    if (cfg == 1) return launch_all<5, 1, 64, 6>(c, Z, A, what);
+    if (cfg == 2) return launch_all<5, 2, 192, 3>(c, Z, A, what);
+    if (cfg == 3) return launch_all<5, 2, 256, 3>(c, Z, A, what);
+    if (cfg == 4) return launch_all<5, 2, 160, 3>(c, Z, A, what);
     return launch_all<5, 2, 128, 4>(c, Z, A, what);
   }
   case 5: return launch_all<6, 1, 128, 4>(c, Z, A, what);
