@@ -1,0 +1,54 @@
+"""GPU: the drop-in command line.  `HiFiLES <input_file>` of this repository (host mirror + device layer) and the
+reference's own binary (oracle/_ref/HiFiLES_ref) are run on the same input; the residual table printed on stdout and
+the log10-residual columns of history.plt (15 digits, reference src/output.cpp:2298-2378) must agree."""
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+import util
+
+OURS = os.path.join(util.ROOT, "hifiles-solver_b200", "bin", "HiFiLES")
+REF = os.path.join(util.REF_DIR, "HiFiLES_ref")
+
+
+def residual_rows(text):
+    rows = []
+    for line in text.splitlines():
+        t = line.split()
+        if len(t) >= 5 and re.fullmatch(r"\d+", t[0]):
+            try:
+                rows.append([float(x) for x in t[1:6]])
+            except ValueError:
+                pass
+    return np.array(rows)
+
+
+def history_rows(path, n_fields):
+    rows = []
+    for line in open(path):
+        t = [x.strip() for x in line.split(",")]
+        if len(t) > n_fields and re.fullmatch(r"\d+", t[0]):
+            rows.append([float(x) for x in t[1:1 + n_fields]])
+    return np.array(rows)
+
+
+@pytest.mark.gpu
+def test_command_line_matches_reference_binary(tmp_path, hb, meshgen):
+    if not (os.path.exists(REF) and os.path.exists(OURS)):
+        pytest.skip("driver binaries not built")
+    out = {}
+    for who, exe in (("ref", REF), ("ours", OURS)):
+        d = tmp_path / who
+        d.mkdir()
+        meshgen.hex_box(str(d / "tgv.neu"), 4)
+        meshgen.write_input(str(d / "input"), "tgv.neu", order=3, adv_type=2, dt=1e-5, riemann_solve_type=3, viscous=1, n_steps=4, monitor_res_freq=1)
+        env = dict(os.environ, HIFILES_HOME=util.REF_DIR if who == "ref" else os.path.join(util.ROOT, "hifiles-solver_b200"))
+        r = subprocess.run([exe, "input"], cwd=str(d), env=env, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+        out[who] = (residual_rows(r.stdout), history_rows(str(d / "history.plt"), 5))
+    assert out["ref"][0].shape == out["ours"][0].shape and out["ref"][0].shape[0] == 4
+    assert np.abs(out["ours"][0] - out["ref"][0]).max() <= 1e-8          # printed with 8 decimals
+    assert np.abs(out["ours"][1] - out["ref"][1]).max() <= 1e-11         # log10 of the residual norms, 15 digits

@@ -28,6 +28,10 @@ CASES = {
                                                     dx_cyclic=20., dy_cyclic=20., dz_cyclic=None, **EULER_IC)),
     "quad_p2_ns_hllc_rk34": ("quad", 6, dict(lengths=(6.2831853071795862,) * 2, origin=(0., 0.)),
                              dict(order=2, adv_type=2, riemann_solve_type=3, viscous=1, dt=2e-5, dz_cyclic=None)),
+    # CFL-based time steps: calc_time_step + eles::calc_dt_local (reference src/solver.cpp:484-549, src/eles.cpp:1267-1356)
+    "quad_p2_ns_cfl_global_dt": ("quad", 6, dict(lengths=(6.2831853071795862,) * 2, origin=(0., 0.), warp=0.2),
+                                 dict(order=2, adv_type=3, riemann_solve_type=0, viscous=1, dt_type=1, CFL=0.4, dt=None, dz_cyclic=None)),
+    "hex_p2_ns_cfl_local_dt": ("hex", 3, dict(warp=0.2), dict(order=2, adv_type=2, riemann_solve_type=3, viscous=1, dt_type=2, CFL=0.4, dt=None)),
     # boundary conditions (reference src/bdy_inters.cpp:213-1189): staged kernels only
     "quad_p2_ns_walls_char_out": ("quad", (8, 6), dict(lengths=(4., 2.), origin=(0., 0.), bcs={"x-": "In", "x+": "Out", "y-": "Wall", "y+": "Top"}),
                                   dict(order=2, adv_type=3, riemann_solve_type=0, viscous=1, ic_form=1, dt=1e-4, fix_vis=0, Mach_c_ic=0.3, nx_c_ic=1.,
@@ -79,6 +83,9 @@ def test_methods_one_by_one(tmp_path, hb, meshgen, name):
         run.set_mode(False)
         types = run.ele_types()
         pre = "step0.stage0."
+        if "dt_type" in CASES[name][3]:
+            dt = run.calc_time_step()  # calc_time_step precedes the RK loop (reference src/HiFiLES.cpp:199)
+            assert abs(dt / ref["step0.dt_time"][0] - 1.0) < 1e-14
 
         def each(op, arr, key):
             for t in types:
@@ -133,6 +140,9 @@ def test_time_steps_reference_call_sequence(tmp_path, hb, meshgen, name):
     with hb.Run(inp) as run:
         run.set_mode(False)
         run.run(n_steps, fused=False)
+        if "dt_type" in CASES[name][3]:
+            ref_dt = ref["step%d.dt_time" % (n_steps - 1)][0]
+            assert abs(run.scalar("dt") / ref_dt - 1.0) < 1e-14, (run.scalar("dt"), ref_dt)
         hist = run.norm_residual()
         check("residual norm", hist, ref["history.norm_residual"][:, -1], 1e-13)
         for t in run.ele_types():
