@@ -589,8 +589,13 @@ __global__ void __launch_bounds__(NT, MINB) k_resid(fused_args A)
       un[k] = S.sx[k][q];
       uo[k] = face_value<N>(S.su[k], L, base, stride);
     }
-    if (is_right) riemann_fast(un, uo, n, fn, A.P);
-    else riemann_fast(uo, un, n, fn, A.P);
+    {
+      // one solver call on (left, right) selected per thread: no divergent duplicate of the solver body
+      double ul[NF], ur[NF];
+#pragma unroll
+      for (int k = 0; k < NF; k++) { ul[k] = is_right ? un[k] : uo[k]; ur[k] = is_right ? uo[k] : un[k]; }
+      riemann_fast(ul, ur, n, fn, A.P);
+    }
     if constexpr (VISC)
     {
       const double beta = ((S.bs[e][f] >> j) & 1ull) ? -A.P.ldg_beta : A.P.ldg_beta;
@@ -624,6 +629,7 @@ __global__ void __launch_bounds__(NT, MINB) k_resid(fused_args A)
     const int ge = e0 + e;
     const double inv_detjac = 1.0 / S.em[e][9];
     const double dtl = A.dt_local ? A.dt_local[ge] : A.rk.dt;
+    const double dt_fac = dtl / A.rk.fac; // (dt / fac) * r, the reference's evaluation order (src/eles.cpp:1141, 1191)
     const size_t gi0 = p + (size_t)NU * ge, gstride = (size_t)NU * A.n_eles;
     double u1v[NF];
     if (A.do_update && A.rk.mode != 0)
@@ -664,9 +670,9 @@ __global__ void __launch_bounds__(NT, MINB) k_resid(fused_args A)
         const double rr = acc * inv_detjac;
         if (A.rk.copy_u1) A.u1[gi] = u;
         if (A.rk.mode == 0)
-          u -= dtl / A.rk.fac * rr;
+          u -= dt_fac * rr;
         else if (A.rk.mode == 1)
-          u = A.rk.c1 * u + A.rk.c2 * u1v[k] + dtl / A.rk.fac * (-rr);
+          u = A.rk.c1 * u + A.rk.c2 * u1v[k] + dt_fac * (-rr);
         else
         {
           const double dlt = A.rk.c1 * u1v[k] + dtl * (-rr);
