@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Benchmark of the HiFiLES per-RK-stage residual hot path on B200 (BASELINE.json config 3).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--n 64] [--order 4] [--impl ours|reference]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--size 64] [--order 4] [--impl ours|reference]
 
 One "step" is one full time step of the low-storage SSP-RK34 scheme = 4 passes of the hot path (CalcResidual +
 AdvanceSolution) over the whole mesh; the metric counts scalar DOF-RK-stage updates per second over all GPUs.
@@ -158,7 +158,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--n", type=int, default=64, help="elements per direction of the global mesh")
+    ap.add_argument("--size", dest="n", type=int, default=64, help="elements per direction of the global mesh")
     ap.add_argument("--order", type=int, default=4)
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--cpu-n", type=int, default=10, help="elements per direction of the CPU baseline sample")
@@ -256,9 +256,12 @@ def main():
     peak, peak_src = measured_peak()
     if fused:
         run.kernel_timer(True)
-        run.run(max(2, args.steps // 2), fused=True)
+        ksteps = max(2, args.steps // 2)
+        run.run(ksteps, fused=True)
         kms, kn = run.kernel_timer(False)
-        per_launch_s = kms * 1e-3 / max(kn, 1)
+        # one k_resid pass over all elements of the rank per RK stage (two launches when the rank has partition faces:
+        # interior elements, then partition-adjacent ones); the time below is the sum of the launches of one stage
+        per_launch_s = kms * 1e-3 / (ksteps * n_rk)
         bpd = BYTES_PER_DOF_STAGE["k_resid"](A_RK[adv_type], 6.0 / (args.order + 1), 3, True)
         ach = dof_local * bpd / per_launch_s / 1e9
         stage_b = BYTES_PER_DOF_STAGE["stage"](A_RK[adv_type], 6.0 / (args.order + 1), 3, True)

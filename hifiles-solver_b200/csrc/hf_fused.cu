@@ -100,6 +100,8 @@ struct rk_args
 struct fused_args
 {
   int n_eles;
+  const int *elist;       // element order of this launch: interior elements first, partition-adjacent ones last
+  int lo, hi;             // the launch covers elist[lo .. hi)
   const double *u0;
   double *u0_out;
   double *u1;
@@ -132,6 +134,7 @@ struct smem_layout
   unsigned long long bs[E][6];    // per face: bit j set = ldg_beta is switched to -beta at flux point j
   int nbr[E][6];
   int finfo[E][6];
+  int ge[E];                      // global (rank-local) element ids of this CTA
 };
 template <int N, int E>
 struct smem_layout_visc : smem_layout<N, E>
@@ -321,17 +324,34 @@ __device__ __forceinline__ void riemann_fast(const double *__restrict__ u_l, con
 // ---- shared phases ----------------------------------------------------------------------------------------------------
 // All global reads of a CTA are cp.async copies into shared memory issued as early as possible; the compute phases
 // touch shared memory and registers only.
+// element id at a position of the launch order (identity when the rank has no partition faces)
+__device__ __forceinline__ int elem_id(const fused_args &A, int pos) { return A.elist ? A.elist[pos] : pos; }
+
 template <int N, int E, int NT, typename SM>
-__device__ __forceinline__ void stage_inputs(SM &S, const fused_args &A, int e0, int ne, bool with_neighbours)
+__device__ __forceinline__ void stage_inputs(SM &S, const fused_args &A, int l0, int ne, bool with_neighbours)
 {
   constexpr int NU = N * N * N, NFP = 6 * N * N, NN = N * N;
   const int tid = threadIdx.x;
-  // solution: for a field, the ne elements of this CTA are contiguous in (upt, ele)
-#pragma unroll
-  for (int k = 0; k < NF; k++)
+  // solution: one contiguous run of NU doubles per (element, field)
+  if (!A.elist)
   {
-    const double *src = A.u0 + (size_t)NU * (e0 + (size_t)A.n_eles * k);
-    for (int i = tid; i < ne * NU; i += NT) cp_async8(&S.su[k][i], src + i);
+    // identity order: the ne elements of this CTA are contiguous in (upt, ele) for every field
+#pragma unroll
+    for (int k = 0; k < NF; k++)
+    {
+      const double *src = A.u0 + (size_t)NU * (l0 + (size_t)A.n_eles * k);
+      for (int i = tid; i < ne * NU; i += NT) cp_async8(&S.su[k][i], src + i);
+    }
+  }
+  else
+  {
+#pragma unroll
+    for (int k = 0; k < NF; k++)
+      for (int i = tid; i < ne * NU; i += NT)
+      {
+        int e = i / NU, p = i - e * NU;
+        cp_async8(&S.su[k][i], A.u0 + p + (size_t)NU * (A.elist[l0 + e] + (size_t)A.n_eles * k));
+      }
   }
   {
     const double *src = (const double *)A.tab;
@@ -339,26 +359,29 @@ __device__ __forceinline__ void stage_inputs(SM &S, const fused_args &A, int e0,
     constexpr int nd = sizeof(fused_tables) / sizeof(double);
     for (int i = tid; i < nd; i += NT) cp_async8(dst + i, src + i);
   }
-  for (int i = tid; i < ne * EM; i += NT) cp_async8(&S.em[0][0] + i, A.em + (size_t)e0 * EM + i);
-  for (int i = tid; i < ne * 6; i += NT) cp_async8(&S.bs[0][0] + i, A.bmask + (size_t)e0 * 6 + i);
+  for (int i = tid; i < ne * EM; i += NT) cp_async8(&S.em[0][0] + i, A.em + (size_t)elem_id(A, l0 + i / EM) * EM + i % EM);
+  for (int i = tid; i < ne * 6; i += NT) cp_async8(&S.bs[0][0] + i, A.bmask + (size_t)elem_id(A, l0 + i / 6) * 6 + i % 6);
   if (with_neighbours)
   {
     // neighbour face values, gathered through the rotation permutation straight into sx
     for (int q = tid; q < ne * NFP; q += NT)
     {
       int e = q / NFP, r = q - e * NFP, f = r / NN, j = r - f * NN;
-      int info = A.finfo[(size_t)(e0 + e) * 6 + f];
+      const size_t gf = (size_t)elem_id(A, l0 + e) * 6 + f;
+      int info = A.finfo[gf];
       int pj = A.tab->perm[(info & 7) * 36 + j];
-      const double *nb = A.fu_cur + (size_t)A.nbr[(size_t)(e0 + e) * 6 + f] * (NF * NN) + pj;
+      const double *nb = A.fu_cur + (size_t)A.nbr[gf] * (NF * NN) + pj;
 #pragma unroll
       for (int k = 0; k < NF; k++) cp_async8(&S.sx[k][q], nb + k * NN);
     }
   }
   for (int i = tid; i < ne * 6; i += NT)
   {
-    S.nbr[0][i] = A.nbr[(size_t)e0 * 6 + i];
-    S.finfo[0][i] = A.finfo[(size_t)e0 * 6 + i];
+    const size_t gf = (size_t)elem_id(A, l0 + i / 6) * 6 + i % 6;
+    S.nbr[0][i] = A.nbr[gf];
+    S.finfo[0][i] = A.finfo[gf];
   }
+  if (tid < ne) S.ge[tid] = elem_id(A, l0 + tid);
   cp_async_commit();
 }
 
@@ -449,9 +472,9 @@ __global__ void __launch_bounds__(NT, MINB) k_grad(fused_args A)
   typedef smem_layout<N, E> SM;
   SM &S = *reinterpret_cast<SM *>(smem_raw);
   constexpr int NU = N * N * N, NFP = 6 * N * N, NN = N * N;
-  const int e0 = blockIdx.x * E;
-  const int ne = min(E, A.n_eles - e0);
-  stage_inputs<N, E, NT>(S, A, e0, ne, true);
+  const int l0 = A.lo + blockIdx.x * E;
+  const int ne = min(E, A.hi - l0);
+  stage_inputs<N, E, NT>(S, A, l0, ne, true);
   cp_async_wait_all();
   __syncthreads();
   phase_delta<N, E, NT>(S, A, ne);
@@ -485,7 +508,7 @@ __global__ void __launch_bounds__(NT, MINB) k_grad(fused_args A)
     vis_flux_fast(u, g, fv, A.P);
     const double *n = &S.em[e][10 + 4 * f + 1];
     const double n0 = n[0], n1 = n[1], n2 = n[2];
-    double *out = A.fv + ((size_t)(e0 + e) * 6 + f) * (4 * NN) + j;
+    double *out = A.fv + ((size_t)S.ge[e] * 6 + f) * (4 * NN) + j;
 #pragma unroll
     for (int k = 1; k < NF; k++) out[(k - 1) * NN] = fv[k] * n0 + fv[k + 5] * n1 + fv[k + 10] * n2;
   }
@@ -500,19 +523,20 @@ __global__ void __launch_bounds__(NT, MINB) k_resid(fused_args A)
   SM &S = *reinterpret_cast<SM *>(smem_raw);
   constexpr int NU = N * N * N, NFP = 6 * N * N, NN = N * N;
   const int tid = threadIdx.x;
-  const int e0 = blockIdx.x * E;
-  const int ne = min(E, A.n_eles - e0);
-  stage_inputs<N, E, NT>(S, A, e0, ne, true);
+  const int l0 = A.lo + blockIdx.x * E;
+  const int ne = min(E, A.hi - l0);
+  stage_inputs<N, E, NT>(S, A, l0, ne, true);
   if constexpr (VISC)
   {
     // own and neighbour one-sided viscous normal fluxes: needed only for the common flux, staged now
     for (int q = tid; q < ne * NFP; q += NT)
     {
       int e = q / NFP, r = q - e * NFP, f = r / NN, j = r - f * NN;
-      int info = A.finfo[(size_t)(e0 + e) * 6 + f];
+      const size_t gf = (size_t)elem_id(A, l0 + e) * 6 + f;
+      int info = A.finfo[gf];
       int pj = A.tab->perm[(info & 7) * 36 + j];
-      const double *po = A.fv + ((size_t)(e0 + e) * 6 + f) * (4 * NN) + j;
-      const double *pn = A.fv + (size_t)A.nbr[(size_t)(e0 + e) * 6 + f] * (4 * NN) + pj;
+      const double *po = A.fv + gf * (4 * NN) + j;
+      const double *pn = A.fv + (size_t)A.nbr[gf] * (4 * NN) + pj;
 #pragma unroll
       for (int k = 0; k < 4; k++) { cp_async8(&S.sv[0][k][q], po + k * NN); cp_async8(&S.sv[1][k][q], pn + k * NN); }
     }
@@ -626,7 +650,7 @@ __global__ void __launch_bounds__(NT, MINB) k_resid(fused_args A)
   {
     const int e = q / NU, p = q - e * NU;
     const int a = p % N, b = (p / N) % N, c = p / NN;
-    const int ge = e0 + e;
+    const int ge = S.ge[e];
     const double inv_detjac = 1.0 / S.em[e][9];
     const double dtl = A.dt_local ? A.dt_local[ge] : A.rk.dt;
     const double dt_fac = dtl / A.rk.fac; // (dt / fac) * r, the reference's evaluation order (src/eles.cpp:1141, 1191)
@@ -694,7 +718,7 @@ __global__ void __launch_bounds__(NT, MINB) k_resid(fused_args A)
     double L[N];
 #pragma unroll
     for (int i = 0; i < N; i++) L[i] = face_sgn(f) > 0 ? S.tab.Lp[i] : S.tab.Lm[i];
-    double *out = A.fu_next + ((size_t)(e0 + e) * 6 + f) * (NF * NN) + j;
+    double *out = A.fu_next + ((size_t)S.ge[e] * 6 + f) * (NF * NN) + j;
 #pragma unroll
     for (int k = 0; k < NF; k++) out[k * NN] = face_value<N>(S.su[k], L, base, stride);
   }
@@ -708,9 +732,9 @@ __global__ void __launch_bounds__(NT) k_face_values(fused_args A)
   typedef smem_layout<N, E> SM;
   SM &S = *reinterpret_cast<SM *>(smem_raw);
   constexpr int NU = N * N * N, NFP = 6 * N * N, NN = N * N;
-  const int e0 = blockIdx.x * E;
-  const int ne = min(E, A.n_eles - e0);
-  stage_inputs<N, E, NT>(S, A, e0, ne, false);
+  const int l0 = A.lo + blockIdx.x * E;
+  const int ne = min(E, A.hi - l0);
+  stage_inputs<N, E, NT>(S, A, l0, ne, false);
   cp_async_wait_all();
   __syncthreads();
   for (int q = threadIdx.x; q < ne * NFP; q += NT)
@@ -718,7 +742,7 @@ __global__ void __launch_bounds__(NT) k_face_values(fused_args A)
     int e = q / NFP, r = q - e * NFP, f = r / NN, j = r - f * NN;
     const int base = e * NU + S.tab.lbase[r], stride = face_stride<N>(f);
     const double *L = face_sgn(f) > 0 ? S.tab.Lp : S.tab.Lm;
-    double *out = A.fu_next + ((size_t)(e0 + e) * 6 + f) * (NF * NN) + j;
+    double *out = A.fu_next + ((size_t)S.ge[e] * 6 + f) * (NF * NN) + j;
 #pragma unroll
     for (int k = 0; k < NF; k++) out[k * NN] = face_value<N>(S.su[k], L, base, stride);
   }
@@ -749,6 +773,8 @@ struct hf_fused_state
   unsigned long long *bmask = nullptr;
   fused_tables *tab = nullptr;
   int *mpi_blk = nullptr; // [n_mpi] own face block of every partition interface
+  int *elist = nullptr;   // interior elements (ascending), then elements with a partition face (ascending)
+  int n_interior = 0;
   double *out_u = nullptr, *out_g = nullptr;
   int E = 2, NT = 128;
 };
@@ -976,6 +1002,14 @@ int hf_fused_prepare(hf_ctx *c)
   }
   for (size_t q = 0; q < nbr.size(); q++)
     if (nbr[q] < 0) return no("an element face has no neighbour");
+  // launch order: elements without a partition face first, so their work overlaps the halo exchange
+  std::vector<char> is_halo(ne, 0);
+  for (int i = 0; i < M.n_inters; i++) is_halo[M.h_ele_l[i]] = 1;
+  std::vector<int> elist;
+  elist.reserve(ne);
+  for (int i = 0; i < ne; i++) if (!is_halo[i]) elist.push_back(i);
+  Z->n_interior = (int)elist.size();
+  for (int i = 0; i < ne; i++) if (is_halo[i]) elist.push_back(i);
   Z->order = e.order;
   Z->n_eles = ne;
   const size_t nblk = (size_t)ne * 6 + M.n_inters;
@@ -988,6 +1022,7 @@ int hf_fused_prepare(hf_ctx *c)
   if (hf_alloc_copy(c, &Z->bmask, bmask.data(), bmask.size())) return 1;
   if (hf_alloc_copy(c, &Z->tab, &T, 1)) return 1;
   if (hf_alloc_copy(c, &Z->mpi_blk, mpi_blk.data(), mpi_blk.size())) return 1;
+  if (hf_alloc_copy(c, &Z->elist, elist.data(), elist.size())) return 1;
   if (M.n_inters)
   {
     if (hf_alloc_zero(c, &Z->out_u, (size_t)M.n_inters * NF * NN)) return 1;
@@ -1004,11 +1039,14 @@ int hf_fused_prepare(hf_ctx *c)
 namespace
 {
 template <int N, int E, int NT, int MINB>
-int launch_all(hf_ctx *c, hf_fused_state *Z, fused_args &A, int what)
+int launch_all(hf_ctx *c, hf_fused_state *Z, fused_args &A, int what, int lo, int hi)
 {
+  if (hi <= lo) return 0;
+  A.lo = lo;
+  A.hi = hi;
   // what: 0 face values, 1 gradient kernel, 2 residual kernel
   const size_t smem = sizeof(smem_layout<N, E>), smem_v = sizeof(smem_layout_visc<N, E>);
-  const int grid = (Z->n_eles + E - 1) / E;
+  const int grid = (hi - lo + E - 1) / E;
   static bool attr_done = false;
   if (!attr_done)
   {
@@ -1039,23 +1077,23 @@ int launch_all(hf_ctx *c, hf_fused_state *Z, fused_args &A, int what)
   return 0;
 }
 
-int launch(hf_ctx *c, hf_fused_state *Z, fused_args &A, int what)
+int launch(hf_ctx *c, hf_fused_state *Z, fused_args &A, int what, int lo, int hi)
 {
   switch (Z->order)
   {
-  case 1: return launch_all<2, 8, 128, 4>(c, Z, A, what);
-  case 2: return launch_all<3, 4, 128, 4>(c, Z, A, what);
-  case 3: return launch_all<4, 2, 128, 4>(c, Z, A, what);
+  case 1: return launch_all<2, 8, 128, 4>(c, Z, A, what, lo, hi);
+  case 2: return launch_all<3, 4, 128, 4>(c, Z, A, what, lo, hi);
+  case 3: return launch_all<4, 2, 128, 4>(c, Z, A, what, lo, hi);
   case 4:
   {
     static int cfg = getenv("HF_FUSED_CFG") ? atoi(getenv("HF_FUSED_CFG")) : 0;
-    if (cfg == 1) return launch_all<5, 1, 64, 6>(c, Z, A, what);
-    if (cfg == 2) return launch_all<5, 2, 192, 3>(c, Z, A, what);
-    if (cfg == 3) return launch_all<5, 2, 256, 3>(c, Z, A, what);
-    if (cfg == 4) return launch_all<5, 2, 160, 3>(c, Z, A, what);
-    return launch_all<5, 2, 128, 4>(c, Z, A, what);
+    if (cfg == 1) return launch_all<5, 1, 64, 6>(c, Z, A, what, lo, hi);
+    if (cfg == 2) return launch_all<5, 2, 192, 3>(c, Z, A, what, lo, hi);
+    if (cfg == 3) return launch_all<5, 2, 256, 3>(c, Z, A, what, lo, hi);
+    if (cfg == 4) return launch_all<5, 2, 160, 3>(c, Z, A, what, lo, hi);
+    return launch_all<5, 2, 128, 4>(c, Z, A, what, lo, hi);
   }
-  case 5: return launch_all<6, 1, 128, 4>(c, Z, A, what);
+  case 5: return launch_all<6, 1, 128, 4>(c, Z, A, what, lo, hi);
   }
   hf_set_error("fused path: unsupported order");
   return 1;
@@ -1066,6 +1104,7 @@ void base_args(hf_ctx *c, hf_fused_state *Z, fused_args &A)
   hf_eles_dev &e = c->eles[4];
   memset(&A, 0, sizeof(A));
   A.n_eles = e.n_eles;
+  A.elist = Z->n_mpi ? Z->elist : nullptr;
   A.u0 = e.disu_upts[0];
   A.u0_out = e.disu_upts[0];
   A.u1 = e.disu_upts[1];
@@ -1083,17 +1122,18 @@ void base_args(hf_ctx *c, hf_fused_state *Z, fused_args &A)
   A.viscous = c->prm.viscous;
 }
 
-// exchange the partition-face blocks of arr (blk_doubles each): pack -> ncclSend/Recv into the tail of arr
-int exchange(hf_ctx *c, hf_fused_state *Z, double *arr, double *out, int blk_doubles)
+// exchange the partition-face blocks of arr (blk_doubles each): pack -> ncclSend/Recv into the tail of arr, on the
+// communication stream; the compute stream carries on and calls exchange_wait before it touches the received blocks
+int exchange_post(hf_ctx *c, hf_fused_state *Z, double *arr, double *out, int blk_doubles)
 {
   if (Z->n_mpi == 0) return 0;
   hf_mpi_inters_dev &M = c->mpis[2];
   long long n = (long long)Z->n_mpi * blk_doubles;
   k_pack_blocks<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(arr, Z->mpi_blk, out, Z->n_mpi, blk_doubles);
   c->launches++;
-  if (hf_halo_post(c, M, out, arr + (size_t)Z->n_eles * 6 * blk_doubles, (size_t)blk_doubles)) return 1;
-  return hf_halo_wait(c);
+  return hf_halo_post(c, M, out, arr + (size_t)Z->n_eles * 6 * blk_doubles, (size_t)blk_doubles);
 }
+int exchange_wait(hf_ctx *c) { return hf_halo_wait(c); }
 } // namespace
 
 int hf_fused_extrapolate(hf_ctx *c)
@@ -1104,9 +1144,10 @@ int hf_fused_extrapolate(hf_ctx *c)
   fused_args A;
   base_args(c, Z, A);
   A.fu_next = Z->fu[Z->cur]; // fill the current buffer
-  if (launch(c, Z, A, 0)) return 1;
+  if (exchange_wait(c)) return 1; // an exchange into this buffer may still be in flight
+  if (launch(c, Z, A, 0, 0, Z->n_eles)) return 1;
   const int NN = (Z->order + 1) * (Z->order + 1);
-  if (exchange(c, Z, Z->fu[Z->cur], Z->out_u, NF * NN)) return 1;
+  if (exchange_post(c, Z, Z->fu[Z->cur], Z->out_u, NF * NN)) return 1;
   c->ufpts_valid = true;
   return 0;
 }
@@ -1146,16 +1187,28 @@ int hf_fused_stage(hf_ctx *c, int rk_stage, double time, int keep_residual, int 
   }
   else if (p.adv_type != 0)
     HF_FAIL("ERROR: Time integration type not recognised ... ");
+  // Overlap: the exchange of the face values (posted at the end of the previous stage) runs while the elements
+  // without a partition face are processed; the partition-adjacent elements follow once it has arrived.  The same
+  // for the viscous normal fluxes between k_grad and k_resid (reference windows: src/solver.cpp:68-73/131-140 and
+  // :148-155/199-201).
+  const int ni = Z->n_interior, n = Z->n_eles;
+  static const bool no_overlap = getenv("HF_NO_OVERLAP") != nullptr; // measurement aid: serialise exchange and compute
+  if (no_overlap && exchange_wait(c)) return 1;
   if (p.viscous)
   {
-    if (launch(c, Z, A, 1)) return 1;
-    if (exchange(c, Z, Z->fv, Z->out_g, 4 * NN)) return 1;
+    if (launch(c, Z, A, 1, 0, ni)) return 1;
+    if (exchange_wait(c)) return 1;
+    if (launch(c, Z, A, 1, ni, n)) return 1;
+    if (exchange_post(c, Z, Z->fv, Z->out_g, 4 * NN)) return 1;
+    if (no_overlap && exchange_wait(c)) return 1;
   }
-  if (launch(c, Z, A, 2)) return 1;
+  if (launch(c, Z, A, 2, 0, ni)) return 1;
+  if (exchange_wait(c)) return 1;
+  if (launch(c, Z, A, 2, ni, n)) return 1;
   if (do_update)
   {
     Z->cur ^= 1;
-    if (exchange(c, Z, Z->fu[Z->cur], Z->out_u, NF * NN)) return 1;
+    if (exchange_post(c, Z, Z->fu[Z->cur], Z->out_u, NF * NN)) return 1; // waited for by the next stage
     c->ufpts_valid = true;
   }
   return 0;
