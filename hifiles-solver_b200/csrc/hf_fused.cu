@@ -130,6 +130,7 @@ struct smem_layout
   double su[NF][E * NU];          // solution at solution points
   double sg[ND][NF][E * NU];      // physical gradient, later the transformed total flux
   double sx[NF][E * NFP];         // neighbour face values -> LDG delta -> (neighbour face values) -> common minus own normal flux
+  double sf[NF][E * NFP];         // own face values of the solution
   double em[E][EM];
   unsigned long long bs[E][6];    // per face: bit j set = ldg_beta is switched to -beta at flux point j
   int nbr[E][6];
@@ -395,69 +396,124 @@ __device__ __forceinline__ double face_value(const double *field_upts, const dou
   return acc;
 }
 
+// ---- line tasks ----------------------------------------------------------------------------------------------------------
+// The kernels are bound by shared-memory bandwidth (ncu: 80-90 % of the LSU wavefront rate with one LDS per FMA), so every
+// 1-D operator is applied by a thread that owns a whole line of N solution points: N loads feed N derivative outputs
+// and both face values (register tiling of the sum-factorised operators).
+// Task t -> (direction, field, element, line); geometry of a line: first solution point, stride, and the face-local
+// flux points (with face offset) at its minus / plus end (reference src/eles_hexas.cpp:224-282).
+template <int N>
+__device__ __forceinline__ void line_geom(int dir, int l, int &base, int &stride, int &fm, int &fp)
+{
+  constexpr int P = N - 1, NN = N * N;
+  const int x = l % N, y = l / N;
+  if (dir == 0) { base = N * x + NN * y; stride = 1; fm = 4 * NN + (P - x) + N * y; fp = 2 * NN + x + N * y; }
+  else if (dir == 1) { base = x + NN * y; stride = N; fm = 1 * NN + x + N * y; fp = 3 * NN + (P - x) + N * y; }
+  else { base = x + N * y; stride = NN; fm = 0 * NN + (P - x) + N * y; fp = 5 * NN + x + N * y; }
+}
+__device__ __forceinline__ int face_minus(int dir) { return dir == 0 ? 4 : (dir == 1 ? 1 : 0); }
+__device__ __forceinline__ int face_plus(int dir) { return dir == 0 ? 2 : (dir == 1 ? 3 : 5); }
+
+// values of every field at the flux points of the own faces: sf[k][e*NFP + fpt]  (opp_0)
+template <int N, int E, int NT, typename SM>
+__device__ __forceinline__ void pass_face_values(SM &S, int ne)
+{
+  constexpr int NU = N * N * N, NFP = 6 * N * N, NN = N * N;
+  double Lm[N], Lp[N];
+#pragma unroll
+  for (int i = 0; i < N; i++) { Lm[i] = S.tab.Lm[i]; Lp[i] = S.tab.Lp[i]; }
+  for (int t = threadIdx.x; t < 3 * NF * E * NN; t += NT)
+  {
+    const int dir = t / (NF * E * NN), r1 = t - dir * (NF * E * NN), k = r1 / (E * NN), r2 = r1 - k * (E * NN), e = r2 / NN, l = r2 - e * NN;
+    if (e >= ne) continue;
+    int base, stride, fm, fp;
+    line_geom<N>(dir, l, base, stride, fm, fp);
+    const double *x = S.su[k] + e * NU + base;
+    double um = 0.0, up = 0.0;
+#pragma unroll
+    for (int i = 0; i < N; i++)
+    {
+      const double v = x[i * stride];
+      um += Lm[i] * v;
+      up += Lp[i] * v;
+    }
+    S.sf[k][e * NFP + fm] = um;
+    S.sf[k][e * NFP + fp] = up;
+  }
+}
+
 // LDG common solution minus own value at every own flux point, in place over the staged neighbour values in S.sx
 // (delta_disu_fpts of the reference)
 template <int N, int E, int NT, typename SM>
 __device__ __forceinline__ void phase_delta(SM &S, const fused_args &A, int ne)
 {
-  constexpr int NU = N * N * N, NFP = 6 * N * N, NN = N * N;
+  constexpr int NFP = 6 * N * N, NN = N * N;
   for (int q = threadIdx.x; q < ne * NFP; q += NT)
   {
-    int e = q / NFP, r = q - e * NFP, f = r / NN, j = r - f * NN;
-    const int base = e * NU + S.tab.lbase[r], stride = face_stride<N>(f);
-    double L[N];
-#pragma unroll
-    for (int i = 0; i < N; i++) L[i] = face_sgn(f) > 0 ? S.tab.Lp[i] : S.tab.Lm[i];
+    const int e = q / NFP, r = q - e * NFP, f = r / NN, j = r - f * NN;
     const bool is_right = (S.finfo[e][f] & 4) != 0;
     const double beta = ((S.bs[e][f] >> j) & 1ull) ? -A.P.ldg_beta : A.P.ldg_beta;
 #pragma unroll
     for (int k = 0; k < NF; k++)
     {
-      double uo = face_value<N>(S.su[k], L, base, stride);
-      double un = S.sx[k][q];
-      double ul = is_right ? un : uo, ur = is_right ? uo : un;
-      double uc = __dsub_rn(__dmul_rn(0.5, __dadd_rn(ul, ur)), __dmul_rn(beta, __dsub_rn(ul, ur)));
+      const double uo = S.sf[k][q], un = S.sx[k][q];
+      const double ul = is_right ? un : uo, ur = is_right ? uo : un;
+      const double uc = __dsub_rn(__dmul_rn(0.5, __dadd_rn(ul, ur)), __dmul_rn(beta, __dsub_rn(ul, ur)));
       S.sx[k][q] = uc - uo;
     }
   }
 }
 
-// corrected physical gradient of the five fields at one solution point, in registers: g[k + 5 d]
-template <int N, int E, typename SM>
-__device__ __forceinline__ void point_gradient(const SM &S, int e, int p, double *__restrict__ g)
+// corrected reference-space gradient: sg[dir][k][pt] = sum_j D[i][j] u_j + c5(plus face) delta_plus + c5(minus face) delta_minus
+// (opp_4 and opp_5 of the reference)
+template <int N, int E, int NT, typename SM>
+__device__ __forceinline__ void pass_gradient(SM &S, int ne)
 {
   constexpr int NU = N * N * N, NFP = 6 * N * N, NN = N * N;
-  const int a = p % N, b = (p / N) % N, c = p / NN;
+  double D[N][N];
+#pragma unroll
+  for (int i = 0; i < N; i++)
+#pragma unroll
+    for (int j = 0; j < N; j++) D[i][j] = S.tab.D[i * N + j];
+  for (int t = threadIdx.x; t < 3 * NF * E * NN; t += NT)
+  {
+    const int dir = t / (NF * E * NN), r1 = t - dir * (NF * E * NN), k = r1 / (E * NN), r2 = r1 - k * (E * NN), e = r2 / NN, l = r2 - e * NN;
+    if (e >= ne) continue;
+    int base, stride, fm, fp;
+    line_geom<N>(dir, l, base, stride, fm, fp);
+    const double *x = S.su[k] + e * NU + base;
+    double *o = S.sg[dir][k] + e * NU + base;
+    const double dm = S.sx[k][e * NFP + fm], dp = S.sx[k][e * NFP + fp];
+    const double *c5m = S.tab.c5 + face_minus(dir) * N, *c5p = S.tab.c5 + face_plus(dir) * N;
+    double v[N];
+#pragma unroll
+    for (int j = 0; j < N; j++) v[j] = x[j * stride];
+#pragma unroll
+    for (int i = 0; i < N; i++)
+    {
+      double acc = 0.0;
+#pragma unroll
+      for (int j = 0; j < N; j++) acc += D[i][j] * v[j];
+      acc += c5p[i] * dp;
+      acc += c5m[i] * dm;
+      o[i * stride] = acc;
+    }
+  }
+}
+
+// physical gradient of the five fields at one solution point from the reference-space gradient in sg:
+// g(d) = sum_l (1/detJ * gt(l)) * JGinv(l,d)    (reference src/eles.cpp:1955-2011)
+template <typename SM>
+__device__ __forceinline__ void point_gradient(const SM &S, int e, int q, double *__restrict__ g)
+{
   double J[9];
 #pragma unroll
   for (int i = 0; i < 9; i++) J[i] = S.em[e][i];
   const double inv_detjac = 1.0 / S.em[e][9];
-  double Da[N], Db[N], Dc[N];
-#pragma unroll
-  for (int i = 0; i < N; i++) { Da[i] = S.tab.D[a * N + i]; Db[i] = S.tab.D[b * N + i]; Dc[i] = S.tab.D[c * N + i]; }
-  const double c52 = S.tab.c5[2 * N + a], c54 = S.tab.c5[4 * N + a], c51 = S.tab.c5[1 * N + b], c53 = S.tab.c5[3 * N + b],
-               c50 = S.tab.c5[0 * N + c], c55 = S.tab.c5[5 * N + c];
-  const int fb = e * NFP;
-  const int f0 = fb + 0 * NN + fpt_of_upt<N>(0, a, b, c), f1 = fb + 1 * NN + fpt_of_upt<N>(1, a, b, c), f2 = fb + 2 * NN + fpt_of_upt<N>(2, a, b, c),
-            f3 = fb + 3 * NN + fpt_of_upt<N>(3, a, b, c), f4 = fb + 4 * NN + fpt_of_upt<N>(4, a, b, c), f5 = fb + 5 * NN + fpt_of_upt<N>(5, a, b, c);
-  const int ub = e * NU;
 #pragma unroll
   for (int k = 0; k < NF; k++)
   {
-    const double *u = S.su[k] + ub;
-    const double *dl = S.sx[k];
-    double g0 = 0.0, g1 = 0.0, g2 = 0.0;
-#pragma unroll
-    for (int i = 0; i < N; i++) g0 += Da[i] * u[i + N * b + NN * c];
-#pragma unroll
-    for (int i = 0; i < N; i++) g1 += Db[i] * u[a + N * i + NN * c];
-#pragma unroll
-    for (int i = 0; i < N; i++) g2 += Dc[i] * u[a + N * b + NN * i];
-    g0 += c52 * dl[f2]; g0 += c54 * dl[f4];
-    g1 += c51 * dl[f1]; g1 += c53 * dl[f3];
-    g2 += c50 * dl[f0]; g2 += c55 * dl[f5];
-    g0 *= inv_detjac; g1 *= inv_detjac; g2 *= inv_detjac;
-    // physical gradient: g(d) = sum_l (1/detJ * gt(l)) * JGinv(l,d)    (reference src/eles.cpp:1955-2011)
+    const double g0 = S.sg[0][k][q] * inv_detjac, g1 = S.sg[1][k][q] * inv_detjac, g2 = S.sg[2][k][q] * inv_detjac;
     g[k] = g0 * J[0] + g1 * J[1] + g2 * J[2];
     g[k + 5] = g0 * J[3] + g1 * J[4] + g2 * J[5];
     g[k + 10] = g0 * J[6] + g1 * J[7] + g2 * J[8];
@@ -477,34 +533,37 @@ __global__ void __launch_bounds__(NT, MINB) k_grad(fused_args A)
   stage_inputs<N, E, NT>(S, A, l0, ne, true);
   cp_async_wait_all();
   __syncthreads();
+  pass_face_values<N, E, NT>(S, ne);
+  __syncthreads();
   phase_delta<N, E, NT>(S, A, ne);
   __syncthreads();
-  for (int q = threadIdx.x; q < ne * NU; q += NT)
-  {
-    double g[NF * ND];
-    point_gradient<N, E>(S, q / NU, q % NU, g);
-#pragma unroll
-    for (int d = 0; d < ND; d++)
-#pragma unroll
-      for (int k = 0; k < NF; k++) S.sg[d][k][q] = g[k + NF * d];
-  }
+  pass_gradient<N, E, NT>(S, ne);
   __syncthreads();
-  // u and grad u at the own flux points (opp_0, opp_6; for an affine element extrapolation and the transform to
-  // physical space commute), viscous flux there, dotted with the face's left normal
+  // reference-space gradient at the own flux points (opp_6), transformed there (as the reference does), viscous flux,
+  // dotted with the face's left normal
   for (int q = threadIdx.x; q < ne * NFP; q += NT)
   {
-    int e = q / NFP, r = q - e * NFP, f = r / NN, j = r - f * NN;
+    const int e = q / NFP, r = q - e * NFP, f = r / NN, j = r - f * NN;
     const int base = e * NU + S.tab.lbase[r], stride = face_stride<N>(f);
     double L[N];
 #pragma unroll
     for (int i = 0; i < N; i++) L[i] = face_sgn(f) > 0 ? S.tab.Lp[i] : S.tab.Lm[i];
+    double J[9];
+#pragma unroll
+    for (int i = 0; i < 9; i++) J[i] = S.em[e][i];
+    const double inv_detjac = 1.0 / S.em[e][9];
     double u[NF], g[NF * ND], fv[NF * ND];
 #pragma unroll
-    for (int k = 0; k < NF; k++) u[k] = face_value<N>(S.su[k], L, base, stride);
-#pragma unroll
-    for (int d = 0; d < ND; d++)
-#pragma unroll
-      for (int k = 0; k < NF; k++) g[k + NF * d] = face_value<N>(S.sg[d][k], L, base, stride);
+    for (int k = 0; k < NF; k++)
+    {
+      u[k] = S.sf[k][q];
+      const double g0 = face_value<N>(S.sg[0][k], L, base, stride) * inv_detjac;
+      const double g1 = face_value<N>(S.sg[1][k], L, base, stride) * inv_detjac;
+      const double g2 = face_value<N>(S.sg[2][k], L, base, stride) * inv_detjac;
+      g[k] = g0 * J[0] + g1 * J[1] + g2 * J[2];
+      g[k + 5] = g0 * J[3] + g1 * J[4] + g2 * J[5];
+      g[k + 10] = g0 * J[6] + g1 * J[7] + g2 * J[8];
+    }
     vis_flux_fast(u, g, fv, A.P);
     const double *n = &S.em[e][10 + 4 * f + 1];
     const double n0 = n[0], n1 = n[1], n2 = n[2];
@@ -519,37 +578,36 @@ template <int N, int E, int NT, int MINB, bool VISC>
 __global__ void __launch_bounds__(NT, MINB) k_resid(fused_args A)
 {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  typedef typename std::conditional<VISC, smem_layout_visc<N, E>, smem_layout<N, E>>::type SM;
+  typedef smem_layout<N, E> SM;
   SM &S = *reinterpret_cast<SM *>(smem_raw);
   constexpr int NU = N * N * N, NFP = 6 * N * N, NN = N * N;
   const int tid = threadIdx.x;
   const int l0 = A.lo + blockIdx.x * E;
   const int ne = min(E, A.hi - l0);
   stage_inputs<N, E, NT>(S, A, l0, ne, true);
-  if constexpr (VISC)
-  {
-    // own and neighbour one-sided viscous normal fluxes: needed only for the common flux, staged now
-    for (int q = tid; q < ne * NFP; q += NT)
-    {
-      int e = q / NFP, r = q - e * NFP, f = r / NN, j = r - f * NN;
-      const size_t gf = (size_t)elem_id(A, l0 + e) * 6 + f;
-      int info = A.finfo[gf];
-      int pj = A.tab->perm[(info & 7) * 36 + j];
-      const double *po = A.fv + gf * (4 * NN) + j;
-      const double *pn = A.fv + (size_t)A.nbr[gf] * (4 * NN) + pj;
-#pragma unroll
-      for (int k = 0; k < 4; k++) { cp_async8(&S.sv[0][k][q], po + k * NN); cp_async8(&S.sv[1][k][q], pn + k * NN); }
-    }
-    cp_async_commit();
-  }
   cp_async_wait_all();
+  __syncthreads();
+  pass_face_values<N, E, NT>(S, ne);
   __syncthreads();
   if constexpr (VISC)
   {
     phase_delta<N, E, NT>(S, A, ne);
     __syncthreads();
+    pass_gradient<N, E, NT>(S, ne);
+    __syncthreads();
+    // the LDG deltas are consumed: fetch the neighbour face values again (L2) for the Riemann solver; the copy
+    // overlaps the flux evaluation below
+    for (int q = tid; q < ne * NFP; q += NT)
+    {
+      const int e = q / NFP, r = q - e * NFP, f = r / NN, j = r - f * NN;
+      const int pj = S.tab.perm[(S.finfo[e][f] & 7) * 36 + j];
+      const double *nb = A.fu_cur + (size_t)S.nbr[e][f] * (NF * NN) + pj;
+#pragma unroll
+      for (int k = 0; k < NF; k++) cp_async8(&S.sx[k][q], nb + k * NN);
+    }
+    cp_async_commit();
   }
-  // transformed total flux at the solution points -> S.sg
+  // transformed total flux at the solution points -> S.sg (over the gradient, point by point)
   for (int q = tid; q < ne * NU; q += NT)
   {
     const int e = q / NU;
@@ -563,7 +621,7 @@ __global__ void __launch_bounds__(NT, MINB) k_resid(fused_args A)
     if constexpr (VISC)
     {
       double g[NF * ND], fv[NF * ND];
-      point_gradient<N, E>(S, e, q - e * NU, g);
+      point_gradient(S, e, q, g);
       vis_flux_fast(u, g, fv, A.P);
 #pragma unroll
       for (int d = 0; d < ND; d++)
@@ -576,43 +634,30 @@ __global__ void __launch_bounds__(NT, MINB) k_resid(fused_args A)
 #pragma unroll
       for (int l = 0; l < ND; l++) S.sg[l][k][q] = J[l] * f[k] + J[l + 3] * f[k + 5] + J[l + 6] * f[k + 10];
   }
+  cp_async_wait_all();
   __syncthreads();
-  if constexpr (VISC)
-  {
-    // the LDG deltas are consumed: fetch the neighbour face values again (L2) for the Riemann solver
-    for (int q = tid; q < ne * NFP; q += NT)
-    {
-      int e = q / NFP, r = q - e * NFP, f = r / NN, j = r - f * NN;
-      int pj = S.tab.perm[(S.finfo[e][f] & 7) * 36 + j];
-      const double *nb = A.fu_cur + (size_t)S.nbr[e][f] * (NF * NN) + pj;
-#pragma unroll
-      for (int k = 0; k < NF; k++) cp_async8(&S.sx[k][q], nb + k * NN);
-    }
-    cp_async_commit();
-    cp_async_wait_all();
-    __syncthreads();
-  }
-  // common flux minus own normal flux at every own flux point, in place over the neighbour values in S.sx
+  // common normal flux (Riemann + LDG) at every own flux point, in the element's own orientation and scaled by its
+  // tdA, in place over the neighbour values in S.sx; the own normal flux is subtracted by the line pass below
   for (int q = tid; q < ne * NFP; q += NT)
   {
-    int e = q / NFP, r = q - e * NFP, f = r / NN, j = r - f * NN;
-    const int base = e * NU + S.tab.lbase[r], stride = face_stride<N>(f);
-    const int sgn = face_sgn(f), dir = face_dir(f);
-    double L[N];
-#pragma unroll
-    for (int i = 0; i < N; i++) L[i] = sgn > 0 ? S.tab.Lp[i] : S.tab.Lm[i];
+    const int e = q / NFP, r = q - e * NFP, f = r / NN, j = r - f * NN;
     const int info = S.finfo[e][f];
     const bool is_right = (info & 4) != 0;
     const double *geo = &S.em[e][10 + 4 * f];
     const double tdA = geo[0];
     const double n[3] = {geo[1], geo[2], geo[3]};
+    double fvo[4], fvn[4];
+    if constexpr (VISC)
+    {
+      const int pj = S.tab.perm[(info & 7) * 36 + j];
+      const double *po = A.fv + ((size_t)S.ge[e] * 6 + f) * (4 * NN) + j;
+      const double *pn = A.fv + (size_t)S.nbr[e][f] * (4 * NN) + pj;
+#pragma unroll
+      for (int k = 0; k < 4; k++) { fvo[k] = po[k * NN]; fvn[k] = pn[k * NN]; }
+    }
     double uo[NF], un[NF], fn[NF];
 #pragma unroll
-    for (int k = 0; k < NF; k++)
-    {
-      un[k] = S.sx[k][q];
-      uo[k] = face_value<N>(S.su[k], L, base, stride);
-    }
+    for (int k = 0; k < NF; k++) { un[k] = S.sx[k][q]; uo[k] = S.sf[k][q]; }
     {
       // one solver call on (left, right) selected per thread: no divergent duplicate of the solver body
       double ul[NF], ur[NF];
@@ -629,23 +674,61 @@ __global__ void __launch_bounds__(NT, MINB) k_resid(fused_args A)
 #pragma unroll
       for (int k = 1; k < NF; k++)
       {
-        const double fo = S.sv[0][k - 1][q], fnb = flip * S.sv[1][k - 1][q];
+        const double fo = fvo[k - 1], fnb = flip * fvn[k - 1];
         const double fl = is_right ? fnb : fo, fr = is_right ? fo : fnb;
         const double du = is_right ? uo[k] - un[k] : un[k] - uo[k];
         fn[k] += (wl * fl + wr * fr) - tau * du;
       }
     }
     const double s_side = is_right ? -tdA : tdA;
-    const double s_ntd = sgn > 0 ? 1.0 : -1.0;
 #pragma unroll
-    for (int k = 0; k < NF; k++)
-    {
-      double ntd = face_value<N>(S.sg[dir][k], L, base, stride);
-      S.sx[k][q] = fn[k] * s_side - s_ntd * ntd;
-    }
+    for (int k = 0; k < NF; k++) S.sx[k][q] = fn[k] * s_side;
   }
   __syncthreads();
-  // divergence + correction, RK update
+  // divergence of the transformed flux, accumulated in sg[0], and own normal flux at the line ends subtracted from the
+  // common flux (extrapolate_totalFlux + calculate_divergence); one direction at a time
+  {
+    double D[N][N], Lm[N], Lp[N];
+#pragma unroll
+    for (int i = 0; i < N; i++)
+    {
+      Lm[i] = S.tab.Lm[i]; Lp[i] = S.tab.Lp[i];
+#pragma unroll
+      for (int j = 0; j < N; j++) D[i][j] = S.tab.D[i * N + j];
+    }
+#pragma unroll 1
+    for (int dir = 0; dir < 3; dir++)
+    {
+      for (int t = tid; t < NF * E * NN; t += NT)
+      {
+        const int k = t / (E * NN), r2 = t - k * (E * NN), e = r2 / NN, l = r2 - e * NN;
+        if (e >= ne) continue;
+        int base, stride, fm, fp;
+        line_geom<N>(dir, l, base, stride, fm, fp);
+        const double *x = S.sg[dir][k] + e * NU + base;
+        double *o = S.sg[0][k] + e * NU + base;
+        double v[N];
+#pragma unroll
+        for (int j = 0; j < N; j++) v[j] = x[j * stride];
+        double nm = 0.0, np = 0.0;
+#pragma unroll
+        for (int j = 0; j < N; j++) { nm += Lm[j] * v[j]; np += Lp[j] * v[j]; }
+        S.sx[k][e * NFP + fm] += nm; // norm_tdisf = -(L . tdisf) on a minus face
+        S.sx[k][e * NFP + fp] -= np;
+#pragma unroll
+        for (int i = 0; i < N; i++)
+        {
+          double acc = 0.0;
+#pragma unroll
+          for (int j = 0; j < N; j++) acc += D[i][j] * v[j];
+          if (dir == 0) o[i * stride] = acc;
+          else o[i * stride] += acc;
+        }
+      }
+      __syncthreads();
+    }
+  }
+  // correction (opp_3 on common minus own normal flux), RK update
   for (int q = tid; q < ne * NU; q += NT)
   {
     const int e = q / NU, p = q - e * NU;
@@ -661,31 +744,18 @@ __global__ void __launch_bounds__(NT, MINB) k_resid(fused_args A)
 #pragma unroll
       for (int k = 0; k < NF; k++) u1v[k] = A.u1[gi0 + k * gstride];
     }
-    double Da[N], Db[N], Dc[N];
-#pragma unroll
-    for (int i = 0; i < N; i++) { Da[i] = S.tab.D[a * N + i]; Db[i] = S.tab.D[b * N + i]; Dc[i] = S.tab.D[c * N + i]; }
     const double c30 = S.tab.c3[0 * N + c], c31 = S.tab.c3[1 * N + b], c32 = S.tab.c3[2 * N + a], c33 = S.tab.c3[3 * N + b],
                  c34 = S.tab.c3[4 * N + a], c35 = S.tab.c3[5 * N + c];
     const int fb = e * NFP;
     const int f0 = fb + 0 * NN + fpt_of_upt<N>(0, a, b, c), f1 = fb + 1 * NN + fpt_of_upt<N>(1, a, b, c), f2 = fb + 2 * NN + fpt_of_upt<N>(2, a, b, c),
               f3 = fb + 3 * NN + fpt_of_upt<N>(3, a, b, c), f4 = fb + 4 * NN + fpt_of_upt<N>(4, a, b, c), f5 = fb + 5 * NN + fpt_of_upt<N>(5, a, b, c);
-    const int ub = e * NU;
 #pragma unroll
     for (int k = 0; k < NF; k++)
     {
-      // four independent partial sums (the three directional derivatives and the correction): short dependency chains
-      double a0 = 0.0, a1 = 0.0, a2 = 0.0;
-#pragma unroll
-      for (int i = 0; i < N; i++)
-      {
-        a0 += Da[i] * S.sg[0][k][ub + i + N * b + NN * c];
-        a1 += Db[i] * S.sg[1][k][ub + a + N * i + NN * c];
-        a2 += Dc[i] * S.sg[2][k][ub + a + N * b + NN * i];
-      }
       const double *dfl = S.sx[k];
-      double a3 = c30 * dfl[f0] + c31 * dfl[f1] + c32 * dfl[f2];
-      double a4 = c33 * dfl[f3] + c34 * dfl[f4] + c35 * dfl[f5];
-      const double acc = ((a0 + a1) + a2) + (a3 + a4);
+      const double a3 = c30 * dfl[f0] + c31 * dfl[f1] + c32 * dfl[f2];
+      const double a4 = c33 * dfl[f3] + c34 * dfl[f4] + c35 * dfl[f5];
+      const double acc = S.sg[0][k][q] + (a3 + a4);
       const size_t gi = gi0 + k * gstride;
       if (A.keep_residual) A.div[gi] = acc;
       if (A.do_update)
@@ -710,17 +780,32 @@ __global__ void __launch_bounds__(NT, MINB) k_resid(fused_args A)
   }
   if (!A.do_update) return;
   __syncthreads();
-  // face values of the updated solution for the next stage (extrapolate_solution)
-  for (int q = tid; q < ne * NFP; q += NT)
+  // face values of the updated solution for the next stage (extrapolate_solution), line by line
   {
-    int e = q / NFP, r = q - e * NFP, f = r / NN, j = r - f * NN;
-    const int base = e * NU + S.tab.lbase[r], stride = face_stride<N>(f);
-    double L[N];
+    double Lm[N], Lp[N];
 #pragma unroll
-    for (int i = 0; i < N; i++) L[i] = face_sgn(f) > 0 ? S.tab.Lp[i] : S.tab.Lm[i];
-    double *out = A.fu_next + ((size_t)S.ge[e] * 6 + f) * (NF * NN) + j;
+    for (int i = 0; i < N; i++) { Lm[i] = S.tab.Lm[i]; Lp[i] = S.tab.Lp[i]; }
+    for (int t = tid; t < 3 * NF * E * NN; t += NT)
+    {
+      const int dir = t / (NF * E * NN), r1 = t - dir * (NF * E * NN), k = r1 / (E * NN), r2 = r1 - k * (E * NN), e = r2 / NN, l = r2 - e * NN;
+      if (e >= ne) continue;
+      int base, stride, fm, fp;
+      line_geom<N>(dir, l, base, stride, fm, fp);
+      const double *x = S.su[k] + e * NU + base;
+      double um = 0.0, up = 0.0;
 #pragma unroll
-    for (int k = 0; k < NF; k++) out[k * NN] = face_value<N>(S.su[k], L, base, stride);
+      for (int i = 0; i < N; i++)
+      {
+        const double v = x[i * stride];
+        um += Lm[i] * v;
+        up += Lp[i] * v;
+      }
+      // fm / fp carry the face offset f*NN: block layout [face][field][fpt]
+      double *blk = A.fu_next + (size_t)S.ge[e] * 6 * (NF * NN);
+      const int fmf = fm / NN, fpf = fp / NN;
+      blk[(fmf * NF + k) * NN + (fm - fmf * NN)] = um;
+      blk[(fpf * NF + k) * NN + (fp - fpf * NN)] = up;
+    }
   }
 }
 
@@ -1045,7 +1130,7 @@ int launch_all(hf_ctx *c, hf_fused_state *Z, fused_args &A, int what, int lo, in
   A.lo = lo;
   A.hi = hi;
   // what: 0 face values, 1 gradient kernel, 2 residual kernel
-  const size_t smem = sizeof(smem_layout<N, E>), smem_v = sizeof(smem_layout_visc<N, E>);
+  const size_t smem = sizeof(smem_layout<N, E>), smem_v = smem;
   const int grid = (hi - lo + E - 1) / E;
   static bool attr_done = false;
   if (!attr_done)
