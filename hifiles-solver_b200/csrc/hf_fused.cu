@@ -402,32 +402,44 @@ __device__ __forceinline__ double face_value(const double *field_upts, const dou
 // and both face values (register tiling of the sum-factorised operators).
 // Task t -> (direction, field, element, line); geometry of a line: first solution point, stride, and the face-local
 // flux points (with face offset) at its minus / plus end (reference src/eles_hexas.cpp:224-282).
-template <int N>
-__device__ __forceinline__ void line_geom(int dir, int l, int &base, int &stride, int &fm, int &fp)
+template <int N, int DIR>
+__device__ __forceinline__ void line_geom(int l, int &base, int &fm, int &fp)
 {
   constexpr int P = N - 1, NN = N * N;
   const int x = l % N, y = l / N;
-  if (dir == 0) { base = N * x + NN * y; stride = 1; fm = 4 * NN + (P - x) + N * y; fp = 2 * NN + x + N * y; }
-  else if (dir == 1) { base = x + NN * y; stride = N; fm = 1 * NN + x + N * y; fp = 3 * NN + (P - x) + N * y; }
-  else { base = x + N * y; stride = NN; fm = 0 * NN + (P - x) + N * y; fp = 5 * NN + x + N * y; }
+  if (DIR == 0) { base = N * x + NN * y; fm = 4 * NN + (P - x) + N * y; fp = 2 * NN + x + N * y; }
+  else if (DIR == 1) { base = x + NN * y; fm = 1 * NN + x + N * y; fp = 3 * NN + (P - x) + N * y; }
+  else { base = x + N * y; fm = 0 * NN + (P - x) + N * y; fp = 5 * NN + x + N * y; }
 }
-__device__ __forceinline__ int face_minus(int dir) { return dir == 0 ? 4 : (dir == 1 ? 1 : 0); }
-__device__ __forceinline__ int face_plus(int dir) { return dir == 0 ? 2 : (dir == 1 ? 3 : 5); }
+template <int N, int DIR>
+struct line_dir
+{
+  static constexpr int stride = DIR == 0 ? 1 : (DIR == 1 ? N : N * N);
+  static constexpr int fminus = DIR == 0 ? 4 : (DIR == 1 ? 1 : 0);
+  static constexpr int fplus = DIR == 0 ? 2 : (DIR == 1 ? 3 : 5);
+};
+// task t of one direction -> (field k, element e, line l)
+template <int N, int E>
+__device__ __forceinline__ void line_task(int t, int &k, int &e, int &l)
+{
+  constexpr int NN = N * N;
+  k = t / (E * NN);
+  const int r = t - k * (E * NN);
+  e = r / NN;
+  l = r - e * NN;
+}
 
 // values of every field at the flux points of the own faces: sf[k][e*NFP + fpt]  (opp_0)
-template <int N, int E, int NT, typename SM>
-__device__ __forceinline__ void pass_face_values(SM &S, int ne)
+template <int N, int E, int NT, int DIR, typename SM>
+__device__ __forceinline__ void pass_face_values_dir(SM &S, int ne, const double *Lm, const double *Lp)
 {
-  constexpr int NU = N * N * N, NFP = 6 * N * N, NN = N * N;
-  double Lm[N], Lp[N];
-#pragma unroll
-  for (int i = 0; i < N; i++) { Lm[i] = S.tab.Lm[i]; Lp[i] = S.tab.Lp[i]; }
-  for (int t = threadIdx.x; t < 3 * NF * E * NN; t += NT)
+  constexpr int NU = N * N * N, NFP = 6 * N * N, NN = N * N, stride = line_dir<N, DIR>::stride;
+  for (int t = threadIdx.x; t < NF * E * NN; t += NT)
   {
-    const int dir = t / (NF * E * NN), r1 = t - dir * (NF * E * NN), k = r1 / (E * NN), r2 = r1 - k * (E * NN), e = r2 / NN, l = r2 - e * NN;
+    int k, e, l, base, fm, fp;
+    line_task<N, E>(t, k, e, l);
     if (e >= ne) continue;
-    int base, stride, fm, fp;
-    line_geom<N>(dir, l, base, stride, fm, fp);
+    line_geom<N, DIR>(l, base, fm, fp);
     const double *x = S.su[k] + e * NU + base;
     double um = 0.0, up = 0.0;
 #pragma unroll
@@ -440,6 +452,16 @@ __device__ __forceinline__ void pass_face_values(SM &S, int ne)
     S.sf[k][e * NFP + fm] = um;
     S.sf[k][e * NFP + fp] = up;
   }
+}
+template <int N, int E, int NT, typename SM>
+__device__ __forceinline__ void pass_face_values(SM &S, int ne)
+{
+  double Lm[N], Lp[N];
+#pragma unroll
+  for (int i = 0; i < N; i++) { Lm[i] = S.tab.Lm[i]; Lp[i] = S.tab.Lp[i]; }
+  pass_face_values_dir<N, E, NT, 0>(S, ne, Lm, Lp);
+  pass_face_values_dir<N, E, NT, 1>(S, ne, Lm, Lp);
+  pass_face_values_dir<N, E, NT, 2>(S, ne, Lm, Lp);
 }
 
 // LDG common solution minus own value at every own flux point, in place over the staged neighbour values in S.sx
@@ -466,25 +488,22 @@ __device__ __forceinline__ void phase_delta(SM &S, const fused_args &A, int ne)
 
 // corrected reference-space gradient: sg[dir][k][pt] = sum_j D[i][j] u_j + c5(plus face) delta_plus + c5(minus face) delta_minus
 // (opp_4 and opp_5 of the reference)
-template <int N, int E, int NT, typename SM>
-__device__ __forceinline__ void pass_gradient(SM &S, int ne)
+template <int N, int E, int NT, int DIR, typename SM>
+__device__ __forceinline__ void pass_gradient_dir(SM &S, int ne, const double (&D)[N][N])
 {
-  constexpr int NU = N * N * N, NFP = 6 * N * N, NN = N * N;
-  double D[N][N];
+  constexpr int NU = N * N * N, NFP = 6 * N * N, NN = N * N, stride = line_dir<N, DIR>::stride;
+  double c5m[N], c5p[N];
 #pragma unroll
-  for (int i = 0; i < N; i++)
-#pragma unroll
-    for (int j = 0; j < N; j++) D[i][j] = S.tab.D[i * N + j];
-  for (int t = threadIdx.x; t < 3 * NF * E * NN; t += NT)
+  for (int i = 0; i < N; i++) { c5m[i] = S.tab.c5[line_dir<N, DIR>::fminus * N + i]; c5p[i] = S.tab.c5[line_dir<N, DIR>::fplus * N + i]; }
+  for (int t = threadIdx.x; t < NF * E * NN; t += NT)
   {
-    const int dir = t / (NF * E * NN), r1 = t - dir * (NF * E * NN), k = r1 / (E * NN), r2 = r1 - k * (E * NN), e = r2 / NN, l = r2 - e * NN;
+    int k, e, l, base, fm, fp;
+    line_task<N, E>(t, k, e, l);
     if (e >= ne) continue;
-    int base, stride, fm, fp;
-    line_geom<N>(dir, l, base, stride, fm, fp);
+    line_geom<N, DIR>(l, base, fm, fp);
     const double *x = S.su[k] + e * NU + base;
-    double *o = S.sg[dir][k] + e * NU + base;
+    double *o = S.sg[DIR][k] + e * NU + base;
     const double dm = S.sx[k][e * NFP + fm], dp = S.sx[k][e * NFP + fp];
-    const double *c5m = S.tab.c5 + face_minus(dir) * N, *c5p = S.tab.c5 + face_plus(dir) * N;
     double v[N];
 #pragma unroll
     for (int j = 0; j < N; j++) v[j] = x[j * stride];
@@ -499,6 +518,18 @@ __device__ __forceinline__ void pass_gradient(SM &S, int ne)
       o[i * stride] = acc;
     }
   }
+}
+template <int N, int E, int NT, typename SM>
+__device__ __forceinline__ void pass_gradient(SM &S, int ne)
+{
+  double D[N][N];
+#pragma unroll
+  for (int i = 0; i < N; i++)
+#pragma unroll
+    for (int j = 0; j < N; j++) D[i][j] = S.tab.D[i * N + j];
+  pass_gradient_dir<N, E, NT, 0>(S, ne, D);
+  pass_gradient_dir<N, E, NT, 1>(S, ne, D);
+  pass_gradient_dir<N, E, NT, 2>(S, ne, D);
 }
 
 // physical gradient of the five fields at one solution point from the reference-space gradient in sg:
@@ -517,6 +548,67 @@ __device__ __forceinline__ void point_gradient(const SM &S, int e, int q, double
     g[k] = g0 * J[0] + g1 * J[1] + g2 * J[2];
     g[k + 5] = g0 * J[3] + g1 * J[4] + g2 * J[5];
     g[k + 10] = g0 * J[6] + g1 * J[7] + g2 * J[8];
+  }
+}
+
+// one direction of the flux divergence: out(i) = sum_j D[i][j] F_dir(j) accumulated in sg[0]; own normal flux at both
+// line ends folded into the common flux in sx
+template <int N, int E, int NT, int DIR, typename SM>
+__device__ __forceinline__ void pass_divergence_dir(SM &S, int ne, const double (&D)[N][N], const double *Lm, const double *Lp)
+{
+  constexpr int NU = N * N * N, NFP = 6 * N * N, NN = N * N, stride = line_dir<N, DIR>::stride;
+  for (int t = threadIdx.x; t < NF * E * NN; t += NT)
+  {
+    int k, e, l, base, fm, fp;
+    line_task<N, E>(t, k, e, l);
+    if (e >= ne) continue;
+    line_geom<N, DIR>(l, base, fm, fp);
+    const double *x = S.sg[DIR][k] + e * NU + base;
+    double *o = S.sg[0][k] + e * NU + base;
+    double v[N];
+#pragma unroll
+    for (int j = 0; j < N; j++) v[j] = x[j * stride];
+    double nm = 0.0, np = 0.0;
+#pragma unroll
+    for (int j = 0; j < N; j++) { nm += Lm[j] * v[j]; np += Lp[j] * v[j]; }
+    S.sx[k][e * NFP + fm] += nm; // norm_tdisf = -(L . tdisf) on a minus face
+    S.sx[k][e * NFP + fp] -= np;
+#pragma unroll
+    for (int i = 0; i < N; i++)
+    {
+      double acc = 0.0;
+#pragma unroll
+      for (int j = 0; j < N; j++) acc += D[i][j] * v[j];
+      if (DIR == 0) o[i * stride] = acc;
+      else o[i * stride] += acc;
+    }
+  }
+}
+
+// face values of the (updated) solution written to the element's own face blocks in global memory
+template <int N, int E, int NT, int DIR, typename SM>
+__device__ __forceinline__ void pass_face_out_dir(SM &S, int ne, const double *Lm, const double *Lp, double *__restrict__ fu_out)
+{
+  constexpr int NU = N * N * N, NN = N * N, stride = line_dir<N, DIR>::stride;
+  for (int t = threadIdx.x; t < NF * E * NN; t += NT)
+  {
+    int k, e, l, base, fm, fp;
+    line_task<N, E>(t, k, e, l);
+    if (e >= ne) continue;
+    line_geom<N, DIR>(l, base, fm, fp);
+    const double *x = S.su[k] + e * NU + base;
+    double um = 0.0, up = 0.0;
+#pragma unroll
+    for (int i = 0; i < N; i++)
+    {
+      const double v = x[i * stride];
+      um += Lm[i] * v;
+      up += Lp[i] * v;
+    }
+    // block layout [face][field][fpt]; fm / fp carry the face offset face*NN
+    double *blk = fu_out + (size_t)S.ge[e] * 6 * (NF * NN);
+    blk[(line_dir<N, DIR>::fminus * NF + k) * NN + (fm - line_dir<N, DIR>::fminus * NN)] = um;
+    blk[(line_dir<N, DIR>::fplus * NF + k) * NN + (fp - line_dir<N, DIR>::fplus * NN)] = up;
   }
 }
 
@@ -696,37 +788,12 @@ __global__ void __launch_bounds__(NT, MINB) k_resid(fused_args A)
 #pragma unroll
       for (int j = 0; j < N; j++) D[i][j] = S.tab.D[i * N + j];
     }
-#pragma unroll 1
-    for (int dir = 0; dir < 3; dir++)
-    {
-      for (int t = tid; t < NF * E * NN; t += NT)
-      {
-        const int k = t / (E * NN), r2 = t - k * (E * NN), e = r2 / NN, l = r2 - e * NN;
-        if (e >= ne) continue;
-        int base, stride, fm, fp;
-        line_geom<N>(dir, l, base, stride, fm, fp);
-        const double *x = S.sg[dir][k] + e * NU + base;
-        double *o = S.sg[0][k] + e * NU + base;
-        double v[N];
-#pragma unroll
-        for (int j = 0; j < N; j++) v[j] = x[j * stride];
-        double nm = 0.0, np = 0.0;
-#pragma unroll
-        for (int j = 0; j < N; j++) { nm += Lm[j] * v[j]; np += Lp[j] * v[j]; }
-        S.sx[k][e * NFP + fm] += nm; // norm_tdisf = -(L . tdisf) on a minus face
-        S.sx[k][e * NFP + fp] -= np;
-#pragma unroll
-        for (int i = 0; i < N; i++)
-        {
-          double acc = 0.0;
-#pragma unroll
-          for (int j = 0; j < N; j++) acc += D[i][j] * v[j];
-          if (dir == 0) o[i * stride] = acc;
-          else o[i * stride] += acc;
-        }
-      }
-      __syncthreads();
-    }
+    pass_divergence_dir<N, E, NT, 0>(S, ne, D, Lm, Lp);
+    __syncthreads();
+    pass_divergence_dir<N, E, NT, 1>(S, ne, D, Lm, Lp);
+    __syncthreads();
+    pass_divergence_dir<N, E, NT, 2>(S, ne, D, Lm, Lp);
+    __syncthreads();
   }
   // correction (opp_3 on common minus own normal flux), RK update
   for (int q = tid; q < ne * NU; q += NT)
@@ -785,27 +852,9 @@ __global__ void __launch_bounds__(NT, MINB) k_resid(fused_args A)
     double Lm[N], Lp[N];
 #pragma unroll
     for (int i = 0; i < N; i++) { Lm[i] = S.tab.Lm[i]; Lp[i] = S.tab.Lp[i]; }
-    for (int t = tid; t < 3 * NF * E * NN; t += NT)
-    {
-      const int dir = t / (NF * E * NN), r1 = t - dir * (NF * E * NN), k = r1 / (E * NN), r2 = r1 - k * (E * NN), e = r2 / NN, l = r2 - e * NN;
-      if (e >= ne) continue;
-      int base, stride, fm, fp;
-      line_geom<N>(dir, l, base, stride, fm, fp);
-      const double *x = S.su[k] + e * NU + base;
-      double um = 0.0, up = 0.0;
-#pragma unroll
-      for (int i = 0; i < N; i++)
-      {
-        const double v = x[i * stride];
-        um += Lm[i] * v;
-        up += Lp[i] * v;
-      }
-      // fm / fp carry the face offset f*NN: block layout [face][field][fpt]
-      double *blk = A.fu_next + (size_t)S.ge[e] * 6 * (NF * NN);
-      const int fmf = fm / NN, fpf = fp / NN;
-      blk[(fmf * NF + k) * NN + (fm - fmf * NN)] = um;
-      blk[(fpf * NF + k) * NN + (fp - fpf * NN)] = up;
-    }
+    pass_face_out_dir<N, E, NT, 0>(S, ne, Lm, Lp, A.fu_next);
+    pass_face_out_dir<N, E, NT, 1>(S, ne, Lm, Lp, A.fu_next);
+    pass_face_out_dir<N, E, NT, 2>(S, ne, Lm, Lp, A.fu_next);
   }
 }
 
@@ -816,21 +865,17 @@ __global__ void __launch_bounds__(NT) k_face_values(fused_args A)
   extern __shared__ __align__(16) unsigned char smem_raw[];
   typedef smem_layout<N, E> SM;
   SM &S = *reinterpret_cast<SM *>(smem_raw);
-  constexpr int NU = N * N * N, NFP = 6 * N * N, NN = N * N;
   const int l0 = A.lo + blockIdx.x * E;
   const int ne = min(E, A.hi - l0);
   stage_inputs<N, E, NT>(S, A, l0, ne, false);
   cp_async_wait_all();
   __syncthreads();
-  for (int q = threadIdx.x; q < ne * NFP; q += NT)
-  {
-    int e = q / NFP, r = q - e * NFP, f = r / NN, j = r - f * NN;
-    const int base = e * NU + S.tab.lbase[r], stride = face_stride<N>(f);
-    const double *L = face_sgn(f) > 0 ? S.tab.Lp : S.tab.Lm;
-    double *out = A.fu_next + ((size_t)S.ge[e] * 6 + f) * (NF * NN) + j;
+  double Lm[N], Lp[N];
 #pragma unroll
-    for (int k = 0; k < NF; k++) out[k * NN] = face_value<N>(S.su[k], L, base, stride);
-  }
+  for (int i = 0; i < N; i++) { Lm[i] = S.tab.Lm[i]; Lp[i] = S.tab.Lp[i]; }
+  pass_face_out_dir<N, E, NT, 0>(S, ne, Lm, Lp, A.fu_next);
+  pass_face_out_dir<N, E, NT, 1>(S, ne, Lm, Lp, A.fu_next);
+  pass_face_out_dir<N, E, NT, 2>(S, ne, Lm, Lp, A.fu_next);
 }
 
 // gather partition-face blocks into the send buffer: out[inter][block] = arr[block_of(inter)]
