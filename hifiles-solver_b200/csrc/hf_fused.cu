@@ -89,6 +89,7 @@ struct fused_tables // small per-order tables, copied to shared memory by every 
   double c5[36];     // c5[f*N+m]: opp_5(dir f) entry
   unsigned short lbase[216];  // [f*N*N + j]: first solution point of the line behind flux point j of face f
   unsigned char perm[8 * 36]; // [rot + 4*is_right][j] -> neighbour's face-local flux point
+  unsigned char uptab[216][8]; // per solution point: the face-local flux point (with face offset) it meets on faces 0..5, a | b<<4, c
 };
 
 struct rk_args
@@ -115,6 +116,8 @@ struct fused_args
   const unsigned long long *bmask; // [ele][6] per face: bit j = ldg_beta switched to -beta at flux point j
   const double *dt_local;
   const fused_tables *tab;
+  const unsigned long long *ltab; // [3][NF*E*NN] line tasks: k | e<<8, e*NU+base, e*NFP+fm, e*NFP+fp as 4 x uint16
+  const int *nidx;        // [ele][NFP] index into fu (field 0) of the neighbour's value facing each own flux point
   hf_phys P;
   rk_args rk;
   int viscous, keep_residual, do_update;
@@ -136,6 +139,7 @@ struct smem_layout
   int nbr[E][6];
   int finfo[E][6];
   int ge[E];                      // global (rank-local) element ids of this CTA
+  unsigned long long ltab[3][NF * E * N * N]; // line-task table (same for every CTA)
 };
 template <int N, int E>
 struct smem_layout_visc : smem_layout<N, E>
@@ -360,18 +364,16 @@ __device__ __forceinline__ void stage_inputs(SM &S, const fused_args &A, int l0,
     constexpr int nd = sizeof(fused_tables) / sizeof(double);
     for (int i = tid; i < nd; i += NT) cp_async8(dst + i, src + i);
   }
+  for (int i = tid; i < 3 * NF * E * NN; i += NT) cp_async8(&S.ltab[0][0] + i, A.ltab + i);
   for (int i = tid; i < ne * EM; i += NT) cp_async8(&S.em[0][0] + i, A.em + (size_t)elem_id(A, l0 + i / EM) * EM + i % EM);
   for (int i = tid; i < ne * 6; i += NT) cp_async8(&S.bs[0][0] + i, A.bmask + (size_t)elem_id(A, l0 + i / 6) * 6 + i % 6);
   if (with_neighbours)
   {
-    // neighbour face values, gathered through the rotation permutation straight into sx
+    // neighbour face values, gathered through the (precomputed) rotation permutation straight into sx
     for (int q = tid; q < ne * NFP; q += NT)
     {
-      int e = q / NFP, r = q - e * NFP, f = r / NN, j = r - f * NN;
-      const size_t gf = (size_t)elem_id(A, l0 + e) * 6 + f;
-      int info = A.finfo[gf];
-      int pj = A.tab->perm[(info & 7) * 36 + j];
-      const double *nb = A.fu_cur + (size_t)A.nbr[gf] * (NF * NN) + pj;
+      const int e = q / NFP, r = q - e * NFP;
+      const double *nb = A.fu_cur + A.nidx[(size_t)elem_id(A, l0 + e) * NFP + r];
 #pragma unroll
       for (int k = 0; k < NF; k++) cp_async8(&S.sx[k][q], nb + k * NN);
     }
@@ -418,15 +420,17 @@ struct line_dir
   static constexpr int fminus = DIR == 0 ? 4 : (DIR == 1 ? 1 : 0);
   static constexpr int fplus = DIR == 0 ? 2 : (DIR == 1 ? 3 : 5);
 };
-// task t of one direction -> (field k, element e, line l)
-template <int N, int E>
-__device__ __forceinline__ void line_task(int t, int &k, int &e, int &l)
+// task t of direction DIR -> field k, element e, first solution point (with element offset), flux points at both ends
+// (with element offset): one 8-byte entry of the precomputed table
+template <int DIR, typename SM>
+__device__ __forceinline__ void line_task(const SM &S, int t, int &k, int &e, int &ubase, int &fmq, int &fpq)
 {
-  constexpr int NN = N * N;
-  k = t / (E * NN);
-  const int r = t - k * (E * NN);
-  e = r / NN;
-  l = r - e * NN;
+  const unsigned long long w = S.ltab[DIR][t];
+  k = (int)(w & 0xff);
+  e = (int)((w >> 8) & 0xff);
+  ubase = (int)((w >> 16) & 0xffff);
+  fmq = (int)((w >> 32) & 0xffff);
+  fpq = (int)(w >> 48);
 }
 
 // values of every field at the flux points of the own faces: sf[k][e*NFP + fpt]  (opp_0)
@@ -436,11 +440,10 @@ __device__ __forceinline__ void pass_face_values_dir(SM &S, int ne, const double
   constexpr int NU = N * N * N, NFP = 6 * N * N, NN = N * N, stride = line_dir<N, DIR>::stride;
   for (int t = threadIdx.x; t < NF * E * NN; t += NT)
   {
-    int k, e, l, base, fm, fp;
-    line_task<N, E>(t, k, e, l);
+    int k, e, ubase, fmq, fpq;
+    line_task<DIR>(S, t, k, e, ubase, fmq, fpq);
     if (e >= ne) continue;
-    line_geom<N, DIR>(l, base, fm, fp);
-    const double *x = S.su[k] + e * NU + base;
+    const double *x = S.su[k] + ubase;
     double um = 0.0, up = 0.0;
 #pragma unroll
     for (int i = 0; i < N; i++)
@@ -449,8 +452,8 @@ __device__ __forceinline__ void pass_face_values_dir(SM &S, int ne, const double
       um += Lm[i] * v;
       up += Lp[i] * v;
     }
-    S.sf[k][e * NFP + fm] = um;
-    S.sf[k][e * NFP + fp] = up;
+    S.sf[k][fmq] = um;
+    S.sf[k][fpq] = up;
   }
 }
 template <int N, int E, int NT, typename SM>
@@ -497,13 +500,12 @@ __device__ __forceinline__ void pass_gradient_dir(SM &S, int ne, const double (&
   for (int i = 0; i < N; i++) { c5m[i] = S.tab.c5[line_dir<N, DIR>::fminus * N + i]; c5p[i] = S.tab.c5[line_dir<N, DIR>::fplus * N + i]; }
   for (int t = threadIdx.x; t < NF * E * NN; t += NT)
   {
-    int k, e, l, base, fm, fp;
-    line_task<N, E>(t, k, e, l);
+    int k, e, ubase, fmq, fpq;
+    line_task<DIR>(S, t, k, e, ubase, fmq, fpq);
     if (e >= ne) continue;
-    line_geom<N, DIR>(l, base, fm, fp);
-    const double *x = S.su[k] + e * NU + base;
-    double *o = S.sg[DIR][k] + e * NU + base;
-    const double dm = S.sx[k][e * NFP + fm], dp = S.sx[k][e * NFP + fp];
+    const double *x = S.su[k] + ubase;
+    double *o = S.sg[DIR][k] + ubase;
+    const double dm = S.sx[k][fmq], dp = S.sx[k][fpq];
     double v[N];
 #pragma unroll
     for (int j = 0; j < N; j++) v[j] = x[j * stride];
@@ -559,20 +561,19 @@ __device__ __forceinline__ void pass_divergence_dir(SM &S, int ne, const double 
   constexpr int NU = N * N * N, NFP = 6 * N * N, NN = N * N, stride = line_dir<N, DIR>::stride;
   for (int t = threadIdx.x; t < NF * E * NN; t += NT)
   {
-    int k, e, l, base, fm, fp;
-    line_task<N, E>(t, k, e, l);
+    int k, e, ubase, fmq, fpq;
+    line_task<DIR>(S, t, k, e, ubase, fmq, fpq);
     if (e >= ne) continue;
-    line_geom<N, DIR>(l, base, fm, fp);
-    const double *x = S.sg[DIR][k] + e * NU + base;
-    double *o = S.sg[0][k] + e * NU + base;
+    const double *x = S.sg[DIR][k] + ubase;
+    double *o = S.sg[0][k] + ubase;
     double v[N];
 #pragma unroll
     for (int j = 0; j < N; j++) v[j] = x[j * stride];
     double nm = 0.0, np = 0.0;
 #pragma unroll
     for (int j = 0; j < N; j++) { nm += Lm[j] * v[j]; np += Lp[j] * v[j]; }
-    S.sx[k][e * NFP + fm] += nm; // norm_tdisf = -(L . tdisf) on a minus face
-    S.sx[k][e * NFP + fp] -= np;
+    S.sx[k][fmq] += nm; // norm_tdisf = -(L . tdisf) on a minus face
+    S.sx[k][fpq] -= np;
 #pragma unroll
     for (int i = 0; i < N; i++)
     {
@@ -592,11 +593,10 @@ __device__ __forceinline__ void pass_face_out_dir(SM &S, int ne, const double *L
   constexpr int NU = N * N * N, NN = N * N, stride = line_dir<N, DIR>::stride;
   for (int t = threadIdx.x; t < NF * E * NN; t += NT)
   {
-    int k, e, l, base, fm, fp;
-    line_task<N, E>(t, k, e, l);
+    int k, e, ubase, fmq, fpq;
+    line_task<DIR>(S, t, k, e, ubase, fmq, fpq);
     if (e >= ne) continue;
-    line_geom<N, DIR>(l, base, fm, fp);
-    const double *x = S.su[k] + e * NU + base;
+    const double *x = S.su[k] + ubase;
     double um = 0.0, up = 0.0;
 #pragma unroll
     for (int i = 0; i < N; i++)
@@ -605,10 +605,11 @@ __device__ __forceinline__ void pass_face_out_dir(SM &S, int ne, const double *L
       um += Lm[i] * v;
       up += Lp[i] * v;
     }
-    // block layout [face][field][fpt]; fm / fp carry the face offset face*NN
-    double *blk = fu_out + (size_t)S.ge[e] * 6 * (NF * NN);
-    blk[(line_dir<N, DIR>::fminus * NF + k) * NN + (fm - line_dir<N, DIR>::fminus * NN)] = um;
-    blk[(line_dir<N, DIR>::fplus * NF + k) * NN + (fp - line_dir<N, DIR>::fplus * NN)] = up;
+    // block layout [face][field][fpt]; fmq / fpq = e*NFP + face*NN + fpt
+    constexpr int NFP = 6 * NN;
+    double *blk = fu_out + (size_t)S.ge[e] * 6 * (NF * NN) + k * NN - e * NFP;
+    blk[line_dir<N, DIR>::fminus * ((NF - 1) * NN) + fmq] = um;
+    blk[line_dir<N, DIR>::fplus * ((NF - 1) * NN) + fpq] = up;
   }
 }
 
@@ -799,7 +800,8 @@ __global__ void __launch_bounds__(NT, MINB) k_resid(fused_args A)
   for (int q = tid; q < ne * NU; q += NT)
   {
     const int e = q / NU, p = q - e * NU;
-    const int a = p % N, b = (p / N) % N, c = p / NN;
+    const unsigned long long ut = *reinterpret_cast<const unsigned long long *>(S.tab.uptab[p]);
+    const int a = (int)((ut >> 48) & 15), b = (int)((ut >> 52) & 15), c = (int)(ut >> 56);
     const int ge = S.ge[e];
     const double inv_detjac = 1.0 / S.em[e][9];
     const double dtl = A.dt_local ? A.dt_local[ge] : A.rk.dt;
@@ -814,8 +816,8 @@ __global__ void __launch_bounds__(NT, MINB) k_resid(fused_args A)
     const double c30 = S.tab.c3[0 * N + c], c31 = S.tab.c3[1 * N + b], c32 = S.tab.c3[2 * N + a], c33 = S.tab.c3[3 * N + b],
                  c34 = S.tab.c3[4 * N + a], c35 = S.tab.c3[5 * N + c];
     const int fb = e * NFP;
-    const int f0 = fb + 0 * NN + fpt_of_upt<N>(0, a, b, c), f1 = fb + 1 * NN + fpt_of_upt<N>(1, a, b, c), f2 = fb + 2 * NN + fpt_of_upt<N>(2, a, b, c),
-              f3 = fb + 3 * NN + fpt_of_upt<N>(3, a, b, c), f4 = fb + 4 * NN + fpt_of_upt<N>(4, a, b, c), f5 = fb + 5 * NN + fpt_of_upt<N>(5, a, b, c);
+    const int f0 = fb + (int)(ut & 255), f1 = fb + (int)((ut >> 8) & 255), f2 = fb + (int)((ut >> 16) & 255), f3 = fb + (int)((ut >> 24) & 255),
+              f4 = fb + (int)((ut >> 32) & 255), f5 = fb + (int)((ut >> 40) & 255);
 #pragma unroll
     for (int k = 0; k < NF; k++)
     {
@@ -903,6 +905,9 @@ struct hf_fused_state
   unsigned long long *bmask = nullptr;
   fused_tables *tab = nullptr;
   int *mpi_blk = nullptr; // [n_mpi] own face block of every partition interface
+  int *nidx = nullptr;    // [ele][NFP] neighbour value index into fu
+  unsigned long long *ltab = nullptr; // line-task table of the launch configuration in use
+  int ltab_E = 0;
   int *elist = nullptr;   // interior elements (ascending), then elements with a partition face (ascending)
   int n_interior = 0;
   double *out_u = nullptr, *out_g = nullptr;
@@ -1053,8 +1058,17 @@ static bool extract_tables(hf_eles_dev &e, bool visc, fused_tables &T, std::stri
       line_of_fpt<N>(f, j, base, stride);
       T.lbase[f * NN + j] = (unsigned short)base;
     }
+  for (int p = 0; p < NU; p++)
+  {
+    int a = p % N, b = (p / N) % N, c = p / NN;
+    for (int f = 0; f < 6; f++) T.uptab[p][f] = (unsigned char)(f * NN + fpt_of_upt<N>(f, a, b, c));
+    T.uptab[p][6] = (unsigned char)(a | (b << 4));
+    T.uptab[p][7] = (unsigned char)c;
+  }
   return true;
 }
+
+static inline double nblk_total(int ne, int n_mpi) { return (double)ne * 6 + n_mpi; }
 
 int hf_fused_available(hf_ctx *c) { return c->fz && c->fz->available; }
 
@@ -1132,6 +1146,13 @@ int hf_fused_prepare(hf_ctx *c)
   }
   for (size_t q = 0; q < nbr.size(); q++)
     if (nbr[q] < 0) return no("an element face has no neighbour");
+  // per own flux point: where the neighbour's value of field 0 sits in fu (block * NF*NN + permuted flux point)
+  std::vector<int> nidx((size_t)ne * NFP);
+  if ((double)nblk_total(ne, M.n_inters) * NF * NN > 2.0e9) return no("face arrays exceed int32 indexing");
+  for (int i = 0; i < ne; i++)
+    for (int f = 0; f < 6; f++)
+      for (int j = 0; j < NN; j++)
+        nidx[(size_t)i * NFP + f * NN + j] = nbr[(size_t)i * 6 + f] * (NF * NN) + T.perm[(finfo[(size_t)i * 6 + f] & 7) * 36 + j];
   // launch order: elements without a partition face first, so their work overlaps the halo exchange
   std::vector<char> is_halo(ne, 0);
   for (int i = 0; i < M.n_inters; i++) is_halo[M.h_ele_l[i]] = 1;
@@ -1153,6 +1174,7 @@ int hf_fused_prepare(hf_ctx *c)
   if (hf_alloc_copy(c, &Z->tab, &T, 1)) return 1;
   if (hf_alloc_copy(c, &Z->mpi_blk, mpi_blk.data(), mpi_blk.size())) return 1;
   if (hf_alloc_copy(c, &Z->elist, elist.data(), elist.size())) return 1;
+  if (hf_alloc_copy(c, &Z->nidx, nidx.data(), nidx.size())) return 1;
   if (M.n_inters)
   {
     if (hf_alloc_zero(c, &Z->out_u, (size_t)M.n_inters * NF * NN)) return 1;
@@ -1175,6 +1197,29 @@ int launch_all(hf_ctx *c, hf_fused_state *Z, fused_args &A, int what, int lo, in
   A.lo = lo;
   A.hi = hi;
   // what: 0 face values, 1 gradient kernel, 2 residual kernel
+  if (Z->ltab_E != E)
+  {
+    // line-task table for this (N, E): [dir][k][e][line] -> k | e<<8, e*NU+base, e*NFP+fm, e*NFP+fp
+    constexpr int NN = N * N, NU = N * NN, NFP = 6 * NN, P = N - 1;
+    std::vector<unsigned long long> h((size_t)3 * NF * E * NN);
+    for (int dir = 0; dir < 3; dir++)
+      for (int k = 0; k < NF; k++)
+        for (int e = 0; e < E; e++)
+          for (int l = 0; l < NN; l++)
+          {
+            const int x = l % N, y = l / N;
+            int base, fm, fp;
+            if (dir == 0) { base = N * x + NN * y; fm = 4 * NN + (P - x) + N * y; fp = 2 * NN + x + N * y; }
+            else if (dir == 1) { base = x + NN * y; fm = 1 * NN + x + N * y; fp = 3 * NN + (P - x) + N * y; }
+            else { base = x + N * y; fm = 0 * NN + (P - x) + N * y; fp = 5 * NN + x + N * y; }
+            h[(size_t)dir * NF * E * NN + (size_t)(k * E + e) * NN + l] =
+                (unsigned long long)k | ((unsigned long long)e << 8) | ((unsigned long long)(e * NU + base) << 16) |
+                ((unsigned long long)(e * NFP + fm) << 32) | ((unsigned long long)(e * NFP + fp) << 48);
+          }
+    if (hf_alloc_copy(c, &Z->ltab, h.data(), h.size())) return 1;
+    Z->ltab_E = E;
+  }
+  A.ltab = Z->ltab;
   const size_t smem = sizeof(smem_layout<N, E>), smem_v = smem;
   const int grid = (hi - lo + E - 1) / E;
   static bool attr_done = false;
@@ -1246,6 +1291,7 @@ void base_args(hf_ctx *c, hf_fused_state *Z, fused_args &A)
   A.nbr = Z->nbr;
   A.finfo = Z->finfo;
   A.bmask = Z->bmask;
+  A.nidx = Z->nidx;
   A.dt_local = (c->prm.dt_type == 2) ? e.dt_local : nullptr;
   A.tab = Z->tab;
   A.P = c->phys;
