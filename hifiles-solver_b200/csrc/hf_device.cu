@@ -632,6 +632,7 @@ int hf_dev_set_params(hf_ctx *c, const hf_params *p)
   for (int i = 0; i < 3; i++) P.wave_speed[i] = p->wave_speed[i];
   P.diff_coeff = p->diff_coeff; P.lambda = p->lambda;
   P.riemann_solve_type = p->riemann_solve_type;
+  P.gamma_over_pr = p->gamma / p->prandtl;
   if (p->equation == 0 && !(p->riemann_solve_type == 0 || p->riemann_solve_type == 2 || p->riemann_solve_type == 3))
     HF_FAIL("Riemann solver not implemented");
   if (p->viscous && p->vis_riemann_solve_type != 0) HF_FAIL("Viscous Riemann solver not implemented");

@@ -96,6 +96,7 @@ struct rk_args
 {
   int mode, copy_u1; // as k_rk_update in hf_device.cu
   double dt, fac, c1, c2;
+  double dt_fac;     // dt / fac, formed once on the host (global time step)
 };
 
 struct fused_args
@@ -110,41 +111,20 @@ struct fused_args
   const double *fu_cur;   // face u, read (neighbours)
   double *fu_next;        // face u of the updated solution, written (own faces)
   double *fv;             // one-sided viscous normal flux at flux points: written by k_grad, read by k_resid
-  const double *em;       // [ele][EM]
+  const double *em;       // [ele][EM]: JGinv[9], 1/detjac, 6 x (tdA, left normal[3])
   const int *nbr;         // [ele][6] neighbour face block
   const int *finfo;       // [ele][6] rot + 4*is_right + 8*partition face
-  const unsigned long long *bmask; // [ele][6] per face: bit j = ldg_beta switched to -beta at flux point j
+  const unsigned long long *bmask; // [ele][6] per face: bit j clear = own LDG weight 0.5 + beta, set = 0.5 - beta (see hf_fused_prepare)
   const double *dt_local;
-  const fused_tables *tab;
-  const unsigned long long *ltab; // [3][NF*E*NN] line tasks: k | e<<8, e*NU+base, e*NFP+fm, e*NFP+fp as 4 x uint16
+  // 1-D operator tables of the run's order; kernel parameters live in the constant bank, so the unrolled line passes use
+  // them as immediate constant operands (no registers, no shared memory)
+  double tD[36];          // D[i*N+j] = d l_j / dxi at xi_i
+  double tL[2][6];        // [0]: l_i(-1), [1]: l_i(+1)
+  double tc3[36], tc5[36]; // opp_3 / opp_5 entry of face f at directional index m: [f*N+m]
   const int *nidx;        // [ele][NFP] index into fu (field 0) of the neighbour's value facing each own flux point
   hf_phys P;
   rk_args rk;
   int viscous, keep_residual, do_update;
-};
-
-// shared memory of one CTA: E elements, arrays indexed [field][ele][point] so that an element-item index
-// q = ele*points + point addresses them without divisions
-template <int N, int E>
-struct smem_layout
-{
-  static constexpr int NU = N * N * N, NFP = 6 * N * N;
-  fused_tables tab;
-  double su[NF][E * NU];          // solution at solution points
-  double sg[ND][NF][E * NU];      // physical gradient, later the transformed total flux
-  double sx[NF][E * NFP];         // neighbour face values -> LDG delta -> (neighbour face values) -> common minus own normal flux
-  double sf[NF][E * NFP];         // own face values of the solution
-  double em[E][EM];
-  unsigned long long bs[E][6];    // per face: bit j set = ldg_beta is switched to -beta at flux point j
-  int nbr[E][6];
-  int finfo[E][6];
-  int ge[E];                      // global (rank-local) element ids of this CTA
-  unsigned long long ltab[3][NF * E * N * N]; // line-task table (same for every CTA)
-};
-template <int N, int E>
-struct smem_layout_visc : smem_layout<N, E>
-{
-  double sv[2][4][E * 6 * N * N]; // one-sided viscous normal fluxes: [own | neighbour][field 1..4][ele*NFP + fpt]
 };
 
 __device__ __forceinline__ void cp_async8(void *smem, const void *gmem)
@@ -200,10 +180,10 @@ __device__ __forceinline__ void vis_flux_fast(const double *__restrict__ u, cons
     const double dke = 0.5 * vsq * r_d + rho * (v0 * dv[0][d] + v1 * dv[1][d] + v2 * dv[2][d]);
     de[d] = (g[4 + 5 * d] - dke - r_d * inte) * ir;
   }
-  const double diag = (dv[0][0] + dv[1][1] + dv[2][2]) / 3.0;
+  const double diag = (dv[0][0] + dv[1][1] + dv[2][2]) * (1.0 / 3.0);
   const double txx = 2.0 * mu * (dv[0][0] - diag), tyy = 2.0 * mu * (dv[1][1] - diag), tzz = 2.0 * mu * (dv[2][2] - diag);
   const double txy = mu * (dv[0][1] + dv[1][0]), txz = mu * (dv[0][2] + dv[2][0]), tyz = mu * (dv[1][2] + dv[2][1]);
-  const double kap = (mu / P.prandtl) * P.gamma;
+  const double kap = mu * P.gamma_over_pr; // (mu / Pr) * gamma
   f[0] = 0.;  f[1] = -txx; f[2] = -txy; f[3] = -txz; f[4] = -(v0 * txx + v1 * txy + v2 * txz + kap * de[0]);
   f[5] = 0.;  f[6] = -txy; f[7] = -tyy; f[8] = -tyz; f[9] = -(v0 * txy + v1 * tyy + v2 * tyz + kap * de[1]);
   f[10] = 0.; f[11] = -txz; f[12] = -tyz; f[13] = -tzz; f[14] = -(v0 * txz + v1 * tyz + v2 * tzz + kap * de[2]);
@@ -326,559 +306,10 @@ __device__ __forceinline__ void riemann_fast(const double *__restrict__ u_l, con
   }
 }
 
-// ---- shared phases ----------------------------------------------------------------------------------------------------
-// All global reads of a CTA are cp.async copies into shared memory issued as early as possible; the compute phases
-// touch shared memory and registers only.
 // element id at a position of the launch order (identity when the rank has no partition faces)
 __device__ __forceinline__ int elem_id(const fused_args &A, int pos) { return A.elist ? A.elist[pos] : pos; }
 
-template <int N, int E, int NT, typename SM>
-__device__ __forceinline__ void stage_inputs(SM &S, const fused_args &A, int l0, int ne, bool with_neighbours)
-{
-  constexpr int NU = N * N * N, NFP = 6 * N * N, NN = N * N;
-  const int tid = threadIdx.x;
-  // solution: one contiguous run of NU doubles per (element, field)
-  if (!A.elist)
-  {
-    // identity order: the ne elements of this CTA are contiguous in (upt, ele) for every field
-#pragma unroll
-    for (int k = 0; k < NF; k++)
-    {
-      const double *src = A.u0 + (size_t)NU * (l0 + (size_t)A.n_eles * k);
-      for (int i = tid; i < ne * NU; i += NT) cp_async8(&S.su[k][i], src + i);
-    }
-  }
-  else
-  {
-#pragma unroll
-    for (int k = 0; k < NF; k++)
-      for (int i = tid; i < ne * NU; i += NT)
-      {
-        int e = i / NU, p = i - e * NU;
-        cp_async8(&S.su[k][i], A.u0 + p + (size_t)NU * (A.elist[l0 + e] + (size_t)A.n_eles * k));
-      }
-  }
-  {
-    const double *src = (const double *)A.tab;
-    double *dst = (double *)&S.tab;
-    constexpr int nd = sizeof(fused_tables) / sizeof(double);
-    for (int i = tid; i < nd; i += NT) cp_async8(dst + i, src + i);
-  }
-  for (int i = tid; i < 3 * NF * E * NN; i += NT) cp_async8(&S.ltab[0][0] + i, A.ltab + i);
-  for (int i = tid; i < ne * EM; i += NT) cp_async8(&S.em[0][0] + i, A.em + (size_t)elem_id(A, l0 + i / EM) * EM + i % EM);
-  for (int i = tid; i < ne * 6; i += NT) cp_async8(&S.bs[0][0] + i, A.bmask + (size_t)elem_id(A, l0 + i / 6) * 6 + i % 6);
-  if (with_neighbours)
-  {
-    // neighbour face values, gathered through the (precomputed) rotation permutation straight into sx
-    for (int q = tid; q < ne * NFP; q += NT)
-    {
-      const int e = q / NFP, r = q - e * NFP;
-      const double *nb = A.fu_cur + A.nidx[(size_t)elem_id(A, l0 + e) * NFP + r];
-#pragma unroll
-      for (int k = 0; k < NF; k++) cp_async8(&S.sx[k][q], nb + k * NN);
-    }
-  }
-  for (int i = tid; i < ne * 6; i += NT)
-  {
-    const size_t gf = (size_t)elem_id(A, l0 + i / 6) * 6 + i % 6;
-    S.nbr[0][i] = A.nbr[gf];
-    S.finfo[0][i] = A.finfo[gf];
-  }
-  if (tid < ne) S.ge[tid] = elem_id(A, l0 + tid);
-  cp_async_commit();
-}
-
-// own face value of one field at a flux point: sum_i L[i] * field[line]
-template <int N>
-__device__ __forceinline__ double face_value(const double *field_upts, const double *L, int base, int stride)
-{
-  double acc = 0.0;
-#pragma unroll
-  for (int i = 0; i < N; i++) acc += L[i] * field_upts[base + i * stride];
-  return acc;
-}
-
-// ---- line tasks ----------------------------------------------------------------------------------------------------------
-// The kernels are bound by shared-memory bandwidth (ncu: 80-90 % of the LSU wavefront rate with one LDS per FMA), so every
-// 1-D operator is applied by a thread that owns a whole line of N solution points: N loads feed N derivative outputs
-// and both face values (register tiling of the sum-factorised operators).
-// Task t -> (direction, field, element, line); geometry of a line: first solution point, stride, and the face-local
-// flux points (with face offset) at its minus / plus end (reference src/eles_hexas.cpp:224-282).
-template <int N, int DIR>
-__device__ __forceinline__ void line_geom(int l, int &base, int &fm, int &fp)
-{
-  constexpr int P = N - 1, NN = N * N;
-  const int x = l % N, y = l / N;
-  if (DIR == 0) { base = N * x + NN * y; fm = 4 * NN + (P - x) + N * y; fp = 2 * NN + x + N * y; }
-  else if (DIR == 1) { base = x + NN * y; fm = 1 * NN + x + N * y; fp = 3 * NN + (P - x) + N * y; }
-  else { base = x + N * y; fm = 0 * NN + (P - x) + N * y; fp = 5 * NN + x + N * y; }
-}
-template <int N, int DIR>
-struct line_dir
-{
-  static constexpr int stride = DIR == 0 ? 1 : (DIR == 1 ? N : N * N);
-  static constexpr int fminus = DIR == 0 ? 4 : (DIR == 1 ? 1 : 0);
-  static constexpr int fplus = DIR == 0 ? 2 : (DIR == 1 ? 3 : 5);
-};
-// task t of direction DIR -> field k, element e, first solution point (with element offset), flux points at both ends
-// (with element offset): one 8-byte entry of the precomputed table
-template <int DIR, typename SM>
-__device__ __forceinline__ void line_task(const SM &S, int t, int &k, int &e, int &ubase, int &fmq, int &fpq)
-{
-  const unsigned long long w = S.ltab[DIR][t];
-  k = (int)(w & 0xff);
-  e = (int)((w >> 8) & 0xff);
-  ubase = (int)((w >> 16) & 0xffff);
-  fmq = (int)((w >> 32) & 0xffff);
-  fpq = (int)(w >> 48);
-}
-
-// values of every field at the flux points of the own faces: sf[k][e*NFP + fpt]  (opp_0)
-template <int N, int E, int NT, int DIR, typename SM>
-__device__ __forceinline__ void pass_face_values_dir(SM &S, int ne, const double *Lm, const double *Lp)
-{
-  constexpr int NU = N * N * N, NFP = 6 * N * N, NN = N * N, stride = line_dir<N, DIR>::stride;
-  for (int t = threadIdx.x; t < NF * E * NN; t += NT)
-  {
-    int k, e, ubase, fmq, fpq;
-    line_task<DIR>(S, t, k, e, ubase, fmq, fpq);
-    if (e >= ne) continue;
-    const double *x = S.su[k] + ubase;
-    double um = 0.0, up = 0.0;
-#pragma unroll
-    for (int i = 0; i < N; i++)
-    {
-      const double v = x[i * stride];
-      um += Lm[i] * v;
-      up += Lp[i] * v;
-    }
-    S.sf[k][fmq] = um;
-    S.sf[k][fpq] = up;
-  }
-}
-template <int N, int E, int NT, typename SM>
-__device__ __forceinline__ void pass_face_values(SM &S, int ne)
-{
-  double Lm[N], Lp[N];
-#pragma unroll
-  for (int i = 0; i < N; i++) { Lm[i] = S.tab.Lm[i]; Lp[i] = S.tab.Lp[i]; }
-  pass_face_values_dir<N, E, NT, 0>(S, ne, Lm, Lp);
-  pass_face_values_dir<N, E, NT, 1>(S, ne, Lm, Lp);
-  pass_face_values_dir<N, E, NT, 2>(S, ne, Lm, Lp);
-}
-
-// LDG common solution minus own value at every own flux point, in place over the staged neighbour values in S.sx
-// (delta_disu_fpts of the reference)
-template <int N, int E, int NT, typename SM>
-__device__ __forceinline__ void phase_delta(SM &S, const fused_args &A, int ne)
-{
-  constexpr int NFP = 6 * N * N, NN = N * N;
-  for (int q = threadIdx.x; q < ne * NFP; q += NT)
-  {
-    const int e = q / NFP, r = q - e * NFP, f = r / NN, j = r - f * NN;
-    const bool is_right = (S.finfo[e][f] & 4) != 0;
-    const double beta = ((S.bs[e][f] >> j) & 1ull) ? -A.P.ldg_beta : A.P.ldg_beta;
-#pragma unroll
-    for (int k = 0; k < NF; k++)
-    {
-      const double uo = S.sf[k][q], un = S.sx[k][q];
-      const double ul = is_right ? un : uo, ur = is_right ? uo : un;
-      const double uc = __dsub_rn(__dmul_rn(0.5, __dadd_rn(ul, ur)), __dmul_rn(beta, __dsub_rn(ul, ur)));
-      S.sx[k][q] = uc - uo;
-    }
-  }
-}
-
-// corrected reference-space gradient: sg[dir][k][pt] = sum_j D[i][j] u_j + c5(plus face) delta_plus + c5(minus face) delta_minus
-// (opp_4 and opp_5 of the reference)
-template <int N, int E, int NT, int DIR, typename SM>
-__device__ __forceinline__ void pass_gradient_dir(SM &S, int ne, const double (&D)[N][N])
-{
-  constexpr int NU = N * N * N, NFP = 6 * N * N, NN = N * N, stride = line_dir<N, DIR>::stride;
-  double c5m[N], c5p[N];
-#pragma unroll
-  for (int i = 0; i < N; i++) { c5m[i] = S.tab.c5[line_dir<N, DIR>::fminus * N + i]; c5p[i] = S.tab.c5[line_dir<N, DIR>::fplus * N + i]; }
-  for (int t = threadIdx.x; t < NF * E * NN; t += NT)
-  {
-    int k, e, ubase, fmq, fpq;
-    line_task<DIR>(S, t, k, e, ubase, fmq, fpq);
-    if (e >= ne) continue;
-    const double *x = S.su[k] + ubase;
-    double *o = S.sg[DIR][k] + ubase;
-    const double dm = S.sx[k][fmq], dp = S.sx[k][fpq];
-    double v[N];
-#pragma unroll
-    for (int j = 0; j < N; j++) v[j] = x[j * stride];
-#pragma unroll
-    for (int i = 0; i < N; i++)
-    {
-      double acc = 0.0;
-#pragma unroll
-      for (int j = 0; j < N; j++) acc += D[i][j] * v[j];
-      acc += c5p[i] * dp;
-      acc += c5m[i] * dm;
-      o[i * stride] = acc;
-    }
-  }
-}
-template <int N, int E, int NT, typename SM>
-__device__ __forceinline__ void pass_gradient(SM &S, int ne)
-{
-  double D[N][N];
-#pragma unroll
-  for (int i = 0; i < N; i++)
-#pragma unroll
-    for (int j = 0; j < N; j++) D[i][j] = S.tab.D[i * N + j];
-  pass_gradient_dir<N, E, NT, 0>(S, ne, D);
-  pass_gradient_dir<N, E, NT, 1>(S, ne, D);
-  pass_gradient_dir<N, E, NT, 2>(S, ne, D);
-}
-
-// physical gradient of the five fields at one solution point from the reference-space gradient in sg:
-// g(d) = sum_l (1/detJ * gt(l)) * JGinv(l,d)    (reference src/eles.cpp:1955-2011)
-template <typename SM>
-__device__ __forceinline__ void point_gradient(const SM &S, int e, int q, double *__restrict__ g)
-{
-  double J[9];
-#pragma unroll
-  for (int i = 0; i < 9; i++) J[i] = S.em[e][i];
-  const double inv_detjac = 1.0 / S.em[e][9];
-#pragma unroll
-  for (int k = 0; k < NF; k++)
-  {
-    const double g0 = S.sg[0][k][q] * inv_detjac, g1 = S.sg[1][k][q] * inv_detjac, g2 = S.sg[2][k][q] * inv_detjac;
-    g[k] = g0 * J[0] + g1 * J[1] + g2 * J[2];
-    g[k + 5] = g0 * J[3] + g1 * J[4] + g2 * J[5];
-    g[k + 10] = g0 * J[6] + g1 * J[7] + g2 * J[8];
-  }
-}
-
-// one direction of the flux divergence: out(i) = sum_j D[i][j] F_dir(j) accumulated in sg[0]; own normal flux at both
-// line ends folded into the common flux in sx
-template <int N, int E, int NT, int DIR, typename SM>
-__device__ __forceinline__ void pass_divergence_dir(SM &S, int ne, const double (&D)[N][N], const double *Lm, const double *Lp)
-{
-  constexpr int NU = N * N * N, NFP = 6 * N * N, NN = N * N, stride = line_dir<N, DIR>::stride;
-  for (int t = threadIdx.x; t < NF * E * NN; t += NT)
-  {
-    int k, e, ubase, fmq, fpq;
-    line_task<DIR>(S, t, k, e, ubase, fmq, fpq);
-    if (e >= ne) continue;
-    const double *x = S.sg[DIR][k] + ubase;
-    double *o = S.sg[0][k] + ubase;
-    double v[N];
-#pragma unroll
-    for (int j = 0; j < N; j++) v[j] = x[j * stride];
-    double nm = 0.0, np = 0.0;
-#pragma unroll
-    for (int j = 0; j < N; j++) { nm += Lm[j] * v[j]; np += Lp[j] * v[j]; }
-    S.sx[k][fmq] += nm; // norm_tdisf = -(L . tdisf) on a minus face
-    S.sx[k][fpq] -= np;
-#pragma unroll
-    for (int i = 0; i < N; i++)
-    {
-      double acc = 0.0;
-#pragma unroll
-      for (int j = 0; j < N; j++) acc += D[i][j] * v[j];
-      if (DIR == 0) o[i * stride] = acc;
-      else o[i * stride] += acc;
-    }
-  }
-}
-
-// face values of the (updated) solution written to the element's own face blocks in global memory
-template <int N, int E, int NT, int DIR, typename SM>
-__device__ __forceinline__ void pass_face_out_dir(SM &S, int ne, const double *Lm, const double *Lp, double *__restrict__ fu_out)
-{
-  constexpr int NU = N * N * N, NN = N * N, stride = line_dir<N, DIR>::stride;
-  for (int t = threadIdx.x; t < NF * E * NN; t += NT)
-  {
-    int k, e, ubase, fmq, fpq;
-    line_task<DIR>(S, t, k, e, ubase, fmq, fpq);
-    if (e >= ne) continue;
-    const double *x = S.su[k] + ubase;
-    double um = 0.0, up = 0.0;
-#pragma unroll
-    for (int i = 0; i < N; i++)
-    {
-      const double v = x[i * stride];
-      um += Lm[i] * v;
-      up += Lp[i] * v;
-    }
-    // block layout [face][field][fpt]; fmq / fpq = e*NFP + face*NN + fpt
-    constexpr int NFP = 6 * NN;
-    double *blk = fu_out + (size_t)S.ge[e] * 6 * (NF * NN) + k * NN - e * NFP;
-    blk[line_dir<N, DIR>::fminus * ((NF - 1) * NN) + fmq] = um;
-    blk[line_dir<N, DIR>::fplus * ((NF - 1) * NN) + fpq] = up;
-  }
-}
-
-// ---- kernel 1: one-sided viscous normal flux at the faces ---------------------------------------------------------------
-template <int N, int E, int NT, int MINB>
-__global__ void __launch_bounds__(NT, MINB) k_grad(fused_args A)
-{
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  typedef smem_layout<N, E> SM;
-  SM &S = *reinterpret_cast<SM *>(smem_raw);
-  constexpr int NU = N * N * N, NFP = 6 * N * N, NN = N * N;
-  const int l0 = A.lo + blockIdx.x * E;
-  const int ne = min(E, A.hi - l0);
-  stage_inputs<N, E, NT>(S, A, l0, ne, true);
-  cp_async_wait_all();
-  __syncthreads();
-  pass_face_values<N, E, NT>(S, ne);
-  __syncthreads();
-  phase_delta<N, E, NT>(S, A, ne);
-  __syncthreads();
-  pass_gradient<N, E, NT>(S, ne);
-  __syncthreads();
-  // reference-space gradient at the own flux points (opp_6), transformed there (as the reference does), viscous flux,
-  // dotted with the face's left normal
-  for (int q = threadIdx.x; q < ne * NFP; q += NT)
-  {
-    const int e = q / NFP, r = q - e * NFP, f = r / NN, j = r - f * NN;
-    const int base = e * NU + S.tab.lbase[r], stride = face_stride<N>(f);
-    double L[N];
-#pragma unroll
-    for (int i = 0; i < N; i++) L[i] = face_sgn(f) > 0 ? S.tab.Lp[i] : S.tab.Lm[i];
-    double J[9];
-#pragma unroll
-    for (int i = 0; i < 9; i++) J[i] = S.em[e][i];
-    const double inv_detjac = 1.0 / S.em[e][9];
-    double u[NF], g[NF * ND], fv[NF * ND];
-#pragma unroll
-    for (int k = 0; k < NF; k++)
-    {
-      u[k] = S.sf[k][q];
-      const double g0 = face_value<N>(S.sg[0][k], L, base, stride) * inv_detjac;
-      const double g1 = face_value<N>(S.sg[1][k], L, base, stride) * inv_detjac;
-      const double g2 = face_value<N>(S.sg[2][k], L, base, stride) * inv_detjac;
-      g[k] = g0 * J[0] + g1 * J[1] + g2 * J[2];
-      g[k + 5] = g0 * J[3] + g1 * J[4] + g2 * J[5];
-      g[k + 10] = g0 * J[6] + g1 * J[7] + g2 * J[8];
-    }
-    vis_flux_fast(u, g, fv, A.P);
-    const double *n = &S.em[e][10 + 4 * f + 1];
-    const double n0 = n[0], n1 = n[1], n2 = n[2];
-    double *out = A.fv + ((size_t)S.ge[e] * 6 + f) * (4 * NN) + j;
-#pragma unroll
-    for (int k = 1; k < NF; k++) out[(k - 1) * NN] = fv[k] * n0 + fv[k + 5] * n1 + fv[k + 10] * n2;
-  }
-}
-
-// ---- kernel 2: residual + RK update + next face values --------------------------------------------------------------------
-template <int N, int E, int NT, int MINB, bool VISC>
-__global__ void __launch_bounds__(NT, MINB) k_resid(fused_args A)
-{
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  typedef smem_layout<N, E> SM;
-  SM &S = *reinterpret_cast<SM *>(smem_raw);
-  constexpr int NU = N * N * N, NFP = 6 * N * N, NN = N * N;
-  const int tid = threadIdx.x;
-  const int l0 = A.lo + blockIdx.x * E;
-  const int ne = min(E, A.hi - l0);
-  stage_inputs<N, E, NT>(S, A, l0, ne, true);
-  cp_async_wait_all();
-  __syncthreads();
-  pass_face_values<N, E, NT>(S, ne);
-  __syncthreads();
-  if constexpr (VISC)
-  {
-    phase_delta<N, E, NT>(S, A, ne);
-    __syncthreads();
-    pass_gradient<N, E, NT>(S, ne);
-    __syncthreads();
-    // the LDG deltas are consumed: fetch the neighbour face values again (L2) for the Riemann solver; the copy
-    // overlaps the flux evaluation below
-    for (int q = tid; q < ne * NFP; q += NT)
-    {
-      const int e = q / NFP, r = q - e * NFP, f = r / NN, j = r - f * NN;
-      const int pj = S.tab.perm[(S.finfo[e][f] & 7) * 36 + j];
-      const double *nb = A.fu_cur + (size_t)S.nbr[e][f] * (NF * NN) + pj;
-#pragma unroll
-      for (int k = 0; k < NF; k++) cp_async8(&S.sx[k][q], nb + k * NN);
-    }
-    cp_async_commit();
-  }
-  // transformed total flux at the solution points -> S.sg (over the gradient, point by point)
-  for (int q = tid; q < ne * NU; q += NT)
-  {
-    const int e = q / NU;
-    double J[9];
-#pragma unroll
-    for (int i = 0; i < 9; i++) J[i] = S.em[e][i];
-    double u[NF], f[NF * ND];
-#pragma unroll
-    for (int k = 0; k < NF; k++) u[k] = S.su[k][q];
-    inv_flux_fast(u, f, A.P.gamma - 1.0);
-    if constexpr (VISC)
-    {
-      double g[NF * ND], fv[NF * ND];
-      point_gradient(S, e, q, g);
-      vis_flux_fast(u, g, fv, A.P);
-#pragma unroll
-      for (int d = 0; d < ND; d++)
-#pragma unroll
-        for (int k = 1; k < NF; k++) f[k + NF * d] += fv[k + NF * d];
-    }
-    // tdisf(k,l) = sum_m JGinv(l,m) f(k,m)
-#pragma unroll
-    for (int k = 0; k < NF; k++)
-#pragma unroll
-      for (int l = 0; l < ND; l++) S.sg[l][k][q] = J[l] * f[k] + J[l + 3] * f[k + 5] + J[l + 6] * f[k + 10];
-  }
-  cp_async_wait_all();
-  __syncthreads();
-  // common normal flux (Riemann + LDG) at every own flux point, in the element's own orientation and scaled by its
-  // tdA, in place over the neighbour values in S.sx; the own normal flux is subtracted by the line pass below
-  for (int q = tid; q < ne * NFP; q += NT)
-  {
-    const int e = q / NFP, r = q - e * NFP, f = r / NN, j = r - f * NN;
-    const int info = S.finfo[e][f];
-    const bool is_right = (info & 4) != 0;
-    const double *geo = &S.em[e][10 + 4 * f];
-    const double tdA = geo[0];
-    const double n[3] = {geo[1], geo[2], geo[3]};
-    double fvo[4], fvn[4];
-    if constexpr (VISC)
-    {
-      const int pj = S.tab.perm[(info & 7) * 36 + j];
-      const double *po = A.fv + ((size_t)S.ge[e] * 6 + f) * (4 * NN) + j;
-      const double *pn = A.fv + (size_t)S.nbr[e][f] * (4 * NN) + pj;
-#pragma unroll
-      for (int k = 0; k < 4; k++) { fvo[k] = po[k * NN]; fvn[k] = pn[k * NN]; }
-    }
-    double uo[NF], un[NF], fn[NF];
-#pragma unroll
-    for (int k = 0; k < NF; k++) { un[k] = S.sx[k][q]; uo[k] = S.sf[k][q]; }
-    {
-      // one solver call on (left, right) selected per thread: no divergent duplicate of the solver body
-      double ul[NF], ur[NF];
-#pragma unroll
-      for (int k = 0; k < NF; k++) { ul[k] = is_right ? un[k] : uo[k]; ur[k] = is_right ? uo[k] : un[k]; }
-      riemann_fast(ul, ur, n, fn, A.P);
-    }
-    if constexpr (VISC)
-    {
-      const double beta = ((S.bs[e][f] >> j) & 1ull) ? -A.P.ldg_beta : A.P.ldg_beta;
-      const double wl = 0.5 + beta, wr = 0.5 - beta, tau = A.P.ldg_tau;
-      const double flip = (info & 8) ? -1.0 : 1.0; // a partition neighbour used its own (opposite) normal
-      fn[0] -= tau * (is_right ? uo[0] - un[0] : un[0] - uo[0]);
-#pragma unroll
-      for (int k = 1; k < NF; k++)
-      {
-        const double fo = fvo[k - 1], fnb = flip * fvn[k - 1];
-        const double fl = is_right ? fnb : fo, fr = is_right ? fo : fnb;
-        const double du = is_right ? uo[k] - un[k] : un[k] - uo[k];
-        fn[k] += (wl * fl + wr * fr) - tau * du;
-      }
-    }
-    const double s_side = is_right ? -tdA : tdA;
-#pragma unroll
-    for (int k = 0; k < NF; k++) S.sx[k][q] = fn[k] * s_side;
-  }
-  __syncthreads();
-  // divergence of the transformed flux, accumulated in sg[0], and own normal flux at the line ends subtracted from the
-  // common flux (extrapolate_totalFlux + calculate_divergence); one direction at a time
-  {
-    double D[N][N], Lm[N], Lp[N];
-#pragma unroll
-    for (int i = 0; i < N; i++)
-    {
-      Lm[i] = S.tab.Lm[i]; Lp[i] = S.tab.Lp[i];
-#pragma unroll
-      for (int j = 0; j < N; j++) D[i][j] = S.tab.D[i * N + j];
-    }
-    pass_divergence_dir<N, E, NT, 0>(S, ne, D, Lm, Lp);
-    __syncthreads();
-    pass_divergence_dir<N, E, NT, 1>(S, ne, D, Lm, Lp);
-    __syncthreads();
-    pass_divergence_dir<N, E, NT, 2>(S, ne, D, Lm, Lp);
-    __syncthreads();
-  }
-  // correction (opp_3 on common minus own normal flux), RK update
-  for (int q = tid; q < ne * NU; q += NT)
-  {
-    const int e = q / NU, p = q - e * NU;
-    const unsigned long long ut = *reinterpret_cast<const unsigned long long *>(S.tab.uptab[p]);
-    const int a = (int)((ut >> 48) & 15), b = (int)((ut >> 52) & 15), c = (int)(ut >> 56);
-    const int ge = S.ge[e];
-    const double inv_detjac = 1.0 / S.em[e][9];
-    const double dtl = A.dt_local ? A.dt_local[ge] : A.rk.dt;
-    const double dt_fac = dtl / A.rk.fac; // (dt / fac) * r, the reference's evaluation order (src/eles.cpp:1141, 1191)
-    const size_t gi0 = p + (size_t)NU * ge, gstride = (size_t)NU * A.n_eles;
-    double u1v[NF];
-    if (A.do_update && A.rk.mode != 0)
-    {
-#pragma unroll
-      for (int k = 0; k < NF; k++) u1v[k] = A.u1[gi0 + k * gstride];
-    }
-    const double c30 = S.tab.c3[0 * N + c], c31 = S.tab.c3[1 * N + b], c32 = S.tab.c3[2 * N + a], c33 = S.tab.c3[3 * N + b],
-                 c34 = S.tab.c3[4 * N + a], c35 = S.tab.c3[5 * N + c];
-    const int fb = e * NFP;
-    const int f0 = fb + (int)(ut & 255), f1 = fb + (int)((ut >> 8) & 255), f2 = fb + (int)((ut >> 16) & 255), f3 = fb + (int)((ut >> 24) & 255),
-              f4 = fb + (int)((ut >> 32) & 255), f5 = fb + (int)((ut >> 40) & 255);
-#pragma unroll
-    for (int k = 0; k < NF; k++)
-    {
-      const double *dfl = S.sx[k];
-      const double a3 = c30 * dfl[f0] + c31 * dfl[f1] + c32 * dfl[f2];
-      const double a4 = c33 * dfl[f3] + c34 * dfl[f4] + c35 * dfl[f5];
-      const double acc = S.sg[0][k][q] + (a3 + a4);
-      const size_t gi = gi0 + k * gstride;
-      if (A.keep_residual) A.div[gi] = acc;
-      if (A.do_update)
-      {
-        double u = S.su[k][q];
-        const double rr = acc * inv_detjac;
-        if (A.rk.copy_u1) A.u1[gi] = u;
-        if (A.rk.mode == 0)
-          u -= dt_fac * rr;
-        else if (A.rk.mode == 1)
-          u = A.rk.c1 * u + A.rk.c2 * u1v[k] + dt_fac * (-rr);
-        else
-        {
-          const double dlt = A.rk.c1 * u1v[k] + dtl * (-rr);
-          A.u1[gi] = dlt;
-          u += A.rk.c2 * dlt;
-        }
-        A.u0_out[gi] = u;
-        S.su[k][q] = u;
-      }
-    }
-  }
-  if (!A.do_update) return;
-  __syncthreads();
-  // face values of the updated solution for the next stage (extrapolate_solution), line by line
-  {
-    double Lm[N], Lp[N];
-#pragma unroll
-    for (int i = 0; i < N; i++) { Lm[i] = S.tab.Lm[i]; Lp[i] = S.tab.Lp[i]; }
-    pass_face_out_dir<N, E, NT, 0>(S, ne, Lm, Lp, A.fu_next);
-    pass_face_out_dir<N, E, NT, 1>(S, ne, Lm, Lp, A.fu_next);
-    pass_face_out_dir<N, E, NT, 2>(S, ne, Lm, Lp, A.fu_next);
-  }
-}
-
-// face values of the current solution (first stage, or after an upload)
-template <int N, int E, int NT>
-__global__ void __launch_bounds__(NT) k_face_values(fused_args A)
-{
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  typedef smem_layout<N, E> SM;
-  SM &S = *reinterpret_cast<SM *>(smem_raw);
-  const int l0 = A.lo + blockIdx.x * E;
-  const int ne = min(E, A.hi - l0);
-  stage_inputs<N, E, NT>(S, A, l0, ne, false);
-  cp_async_wait_all();
-  __syncthreads();
-  double Lm[N], Lp[N];
-#pragma unroll
-  for (int i = 0; i < N; i++) { Lm[i] = S.tab.Lm[i]; Lp[i] = S.tab.Lp[i]; }
-  pass_face_out_dir<N, E, NT, 0>(S, ne, Lm, Lp, A.fu_next);
-  pass_face_out_dir<N, E, NT, 1>(S, ne, Lm, Lp, A.fu_next);
-  pass_face_out_dir<N, E, NT, 2>(S, ne, Lm, Lp, A.fu_next);
-}
+#include "hf_fused_kernels.cuh"
 
 // gather partition-face blocks into the send buffer: out[inter][block] = arr[block_of(inter)]
 __global__ void k_pack_blocks(const double *__restrict__ arr, const int *__restrict__ blk, double *__restrict__ out, int n_inters, int blk_doubles)
@@ -903,11 +334,9 @@ struct hf_fused_state
   int *nbr = nullptr;
   int *finfo = nullptr;
   unsigned long long *bmask = nullptr;
-  fused_tables *tab = nullptr;
+  fused_tables T;
   int *mpi_blk = nullptr; // [n_mpi] own face block of every partition interface
   int *nidx = nullptr;    // [ele][NFP] neighbour value index into fu
-  unsigned long long *ltab = nullptr; // line-task table of the launch configuration in use
-  int ltab_E = 0;
   int *elist = nullptr;   // interior elements (ascending), then elements with a partition face (ascending)
   int n_interior = 0;
   double *out_u = nullptr, *out_g = nullptr;
@@ -1107,7 +536,8 @@ int hf_fused_prepare(hf_ctx *c)
   std::vector<double> em((size_t)ne * EM, 0.);
   for (int i = 0; i < ne; i++)
   {
-    for (int q = 0; q < 10; q++) em[(size_t)i * EM + q] = e.h_em[(size_t)i * 10 + q];
+    for (int q = 0; q < 9; q++) em[(size_t)i * EM + q] = e.h_em[(size_t)i * 10 + q];
+    em[(size_t)i * EM + 9] = 1.0 / e.h_em[(size_t)i * 10 + 9]; // the kernels only ever divide by detjac
     for (int f = 0; f < 6; f++)
       for (int q = 0; q < 4; q++) em[(size_t)i * EM + 10 + 4 * f + q] = e.h_face_geo[(size_t)i * 24 + 4 * f + q];
   }
@@ -1123,12 +553,11 @@ int hf_fused_prepare(hf_ctx *c)
     for (int q = 1; q < 4; q++) em[(size_t)er * EM + 10 + 4 * fr + q] = e.h_face_geo[(size_t)el * 24 + 4 * fl + q];
     for (int j = 0; j < NN; j++)
     {
+      // bit = (ldg_beta switched to -beta at this flux point) XOR (this element is the right side): the weight of the
+      // element's OWN value / flux in the LDG common solution / flux is 0.5 + beta when the bit is clear, 0.5 - beta when set
       signed char s = e.h_own_sign[(size_t)el * NFP + fl * NN + j];
-      if (s < 0)
-      {
-        bmask[(size_t)el * 6 + fl] |= 1ull << j;
-        bmask[(size_t)er * 6 + fr] |= 1ull << T.perm[rot * 36 + j];
-      }
+      if (s < 0) bmask[(size_t)el * 6 + fl] |= 1ull << j;
+      else bmask[(size_t)er * 6 + fr] |= 1ull << T.perm[rot * 36 + j];
     }
   }
   hf_mpi_inters_dev &M = c->mpis[2];
@@ -1171,7 +600,7 @@ int hf_fused_prepare(hf_ctx *c)
   if (hf_alloc_copy(c, &Z->nbr, nbr.data(), nbr.size())) return 1;
   if (hf_alloc_copy(c, &Z->finfo, finfo.data(), finfo.size())) return 1;
   if (hf_alloc_copy(c, &Z->bmask, bmask.data(), bmask.size())) return 1;
-  if (hf_alloc_copy(c, &Z->tab, &T, 1)) return 1;
+  Z->T = T;
   if (hf_alloc_copy(c, &Z->mpi_blk, mpi_blk.data(), mpi_blk.size())) return 1;
   if (hf_alloc_copy(c, &Z->elist, elist.data(), elist.size())) return 1;
   if (hf_alloc_copy(c, &Z->nidx, nidx.data(), nidx.size())) return 1;
@@ -1197,53 +626,30 @@ int launch_all(hf_ctx *c, hf_fused_state *Z, fused_args &A, int what, int lo, in
   A.lo = lo;
   A.hi = hi;
   // what: 0 face values, 1 gradient kernel, 2 residual kernel
-  if (Z->ltab_E != E)
-  {
-    // line-task table for this (N, E): [dir][k][e][line] -> k | e<<8, e*NU+base, e*NFP+fm, e*NFP+fp
-    constexpr int NN = N * N, NU = N * NN, NFP = 6 * NN, P = N - 1;
-    std::vector<unsigned long long> h((size_t)3 * NF * E * NN);
-    for (int dir = 0; dir < 3; dir++)
-      for (int k = 0; k < NF; k++)
-        for (int e = 0; e < E; e++)
-          for (int l = 0; l < NN; l++)
-          {
-            const int x = l % N, y = l / N;
-            int base, fm, fp;
-            if (dir == 0) { base = N * x + NN * y; fm = 4 * NN + (P - x) + N * y; fp = 2 * NN + x + N * y; }
-            else if (dir == 1) { base = x + NN * y; fm = 1 * NN + x + N * y; fp = 3 * NN + (P - x) + N * y; }
-            else { base = x + N * y; fm = 0 * NN + (P - x) + N * y; fp = 5 * NN + x + N * y; }
-            h[(size_t)dir * NF * E * NN + (size_t)(k * E + e) * NN + l] =
-                (unsigned long long)k | ((unsigned long long)e << 8) | ((unsigned long long)(e * NU + base) << 16) |
-                ((unsigned long long)(e * NFP + fm) << 32) | ((unsigned long long)(e * NFP + fp) << 48);
-          }
-    if (hf_alloc_copy(c, &Z->ltab, h.data(), h.size())) return 1;
-    Z->ltab_E = E;
-  }
-  A.ltab = Z->ltab;
-  const size_t smem = sizeof(smem_layout<N, E>), smem_v = smem;
+  const size_t smem_g = sizeof(smem6<N, E>), smem_r = smem_g;
   const int grid = (hi - lo + E - 1) / E;
   static bool attr_done = false;
   if (!attr_done)
   {
-    HF_CUDA(cudaFuncSetAttribute(k_face_values<N, E, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    HF_CUDA(cudaFuncSetAttribute(k_grad<N, E, NT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    HF_CUDA(cudaFuncSetAttribute(k_resid<N, E, NT, MINB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_v));
-    HF_CUDA(cudaFuncSetAttribute(k_resid<N, E, NT, MINB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    HF_CUDA(cudaFuncSetAttribute(k_face_values6<N, E, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_g));
+    HF_CUDA(cudaFuncSetAttribute(k_grad6<N, E, NT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_g));
+    HF_CUDA(cudaFuncSetAttribute(k_resid6<N, E, NT, MINB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_r));
+    HF_CUDA(cudaFuncSetAttribute(k_resid6<N, E, NT, MINB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_r));
     // ask for the largest shared-memory carve-out so that MINB blocks fit on an SM
-    HF_CUDA(cudaFuncSetAttribute(k_grad<N, E, NT, MINB>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-    HF_CUDA(cudaFuncSetAttribute(k_resid<N, E, NT, MINB, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-    HF_CUDA(cudaFuncSetAttribute(k_resid<N, E, NT, MINB, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    HF_CUDA(cudaFuncSetAttribute(k_grad6<N, E, NT, MINB>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    HF_CUDA(cudaFuncSetAttribute(k_resid6<N, E, NT, MINB, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    HF_CUDA(cudaFuncSetAttribute(k_resid6<N, E, NT, MINB, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     attr_done = true;
   }
   if (what == 0)
-    k_face_values<N, E, NT><<<grid, NT, smem, c->stream>>>(A);
+    k_face_values6<N, E, NT><<<grid, NT, smem_g, c->stream>>>(A);
   else if (what == 1)
-    k_grad<N, E, NT, MINB><<<grid, NT, smem, c->stream>>>(A);
+    k_grad6<N, E, NT, MINB><<<grid, NT, smem_g, c->stream>>>(A);
   else
   {
     hf_ktimer_begin(c);
-    if (A.viscous) k_resid<N, E, NT, MINB, true><<<grid, NT, smem_v, c->stream>>>(A);
-    else k_resid<N, E, NT, MINB, false><<<grid, NT, smem, c->stream>>>(A);
+    if (A.viscous) k_resid6<N, E, NT, MINB, true><<<grid, NT, smem_r, c->stream>>>(A);
+    else k_resid6<N, E, NT, MINB, false><<<grid, NT, smem_r, c->stream>>>(A);
     hf_ktimer_end(c);
   }
   c->launches++;
@@ -1256,19 +662,20 @@ int launch(hf_ctx *c, hf_fused_state *Z, fused_args &A, int what, int lo, int hi
 {
   switch (Z->order)
   {
-  case 1: return launch_all<2, 8, 128, 4>(c, Z, A, what, lo, hi);
-  case 2: return launch_all<3, 4, 128, 4>(c, Z, A, what, lo, hi);
-  case 3: return launch_all<4, 2, 128, 4>(c, Z, A, what, lo, hi);
+  case 1: return launch_all<2, 8, 128, 3>(c, Z, A, what, lo, hi);
+  case 2: return launch_all<3, 4, 128, 3>(c, Z, A, what, lo, hi);
+  case 3: return launch_all<4, 2, 128, 3>(c, Z, A, what, lo, hi);
   case 4:
   {
     static int cfg = getenv("HF_FUSED_CFG") ? atoi(getenv("HF_FUSED_CFG")) : 0;
     if (cfg == 1) return launch_all<5, 1, 64, 6>(c, Z, A, what, lo, hi);
-    if (cfg == 2) return launch_all<5, 2, 192, 3>(c, Z, A, what, lo, hi);
-    if (cfg == 3) return launch_all<5, 2, 256, 3>(c, Z, A, what, lo, hi);
-    if (cfg == 4) return launch_all<5, 2, 160, 3>(c, Z, A, what, lo, hi);
-    return launch_all<5, 2, 128, 4>(c, Z, A, what, lo, hi);
+    if (cfg == 2) return launch_all<5, 2, 256, 2>(c, Z, A, what, lo, hi);
+    if (cfg == 3) return launch_all<5, 2, 192, 3>(c, Z, A, what, lo, hi);
+    if (cfg == 4) return launch_all<5, 3, 192, 2>(c, Z, A, what, lo, hi);
+    if (cfg == 5) return launch_all<5, 2, 128, 3>(c, Z, A, what, lo, hi);
+    return launch_all<5, 2, 125, 3>(c, Z, A, what, lo, hi);
   }
-  case 5: return launch_all<6, 1, 128, 4>(c, Z, A, what, lo, hi);
+  case 5: return launch_all<6, 1, 128, 3>(c, Z, A, what, lo, hi);
   }
   hf_set_error("fused path: unsupported order");
   return 1;
@@ -1293,7 +700,8 @@ void base_args(hf_ctx *c, hf_fused_state *Z, fused_args &A)
   A.bmask = Z->bmask;
   A.nidx = Z->nidx;
   A.dt_local = (c->prm.dt_type == 2) ? e.dt_local : nullptr;
-  A.tab = Z->tab;
+  for (int i = 0; i < 36; i++) { A.tD[i] = Z->T.D[i]; A.tc3[i] = Z->T.c3[i]; A.tc5[i] = Z->T.c5[i]; }
+  for (int i = 0; i < 6; i++) { A.tL[0][i] = Z->T.Lm[i]; A.tL[1][i] = Z->T.Lp[i]; }
   A.P = c->phys;
   A.viscous = c->prm.viscous;
 }
@@ -1363,6 +771,7 @@ int hf_fused_stage(hf_ctx *c, int rk_stage, double time, int keep_residual, int 
   }
   else if (p.adv_type != 0)
     HF_FAIL("ERROR: Time integration type not recognised ... ");
+  R.dt_fac = R.dt / R.fac;
   // Overlap: the exchange of the face values (posted at the end of the previous stage) runs while the elements
   // without a partition face are processed; the partition-adjacent elements follow once it has arrived.  The same
   // for the viscous normal fluxes between k_grad and k_resid (reference windows: src/solver.cpp:68-73/131-140 and

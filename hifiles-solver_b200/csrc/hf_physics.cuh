@@ -17,6 +17,7 @@ struct hf_phys
   double ldg_beta, ldg_tau;
   double wave_speed[3], diff_coeff, lambda;
   int riemann_solve_type;
+  double gamma_over_pr; // (1 / Pr) * gamma, used by the fused kernels
 };
 
 // F(k,d) stored as f[k + NF*d]
