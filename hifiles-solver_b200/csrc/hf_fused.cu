@@ -125,6 +125,7 @@ struct fused_args
   hf_phys P;
   rk_args rk;
   int viscous, keep_residual, do_update;
+  int pf_dist;            // L2 software-prefetch distance in CTAs (0 = off)
 };
 
 __device__ __forceinline__ void cp_async8(void *smem, const void *gmem)
@@ -704,6 +705,8 @@ void base_args(hf_ctx *c, hf_fused_state *Z, fused_args &A)
   for (int i = 0; i < 6; i++) { A.tL[0][i] = Z->T.Lm[i]; A.tL[1][i] = Z->T.Lp[i]; }
   A.P = c->phys;
   A.viscous = c->prm.viscous;
+  static const int pf = getenv("HF_FUSED_PF") ? atoi(getenv("HF_FUSED_PF")) : 0; // measured: no effect on B200 (the other resident CTAs already cover the staging latency)
+  A.pf_dist = pf;
 }
 
 // exchange the partition-face blocks of arr (blk_doubles each): pack -> ncclSend/Recv into the tail of arr, on the

@@ -90,14 +90,41 @@ __device__ __forceinline__ void stage6(SM &S, const fused_args &A, int l0, int n
     const size_t gf = (size_t)elem_id(A, l0 + e) * 6 + f;
     cp_async8(&S.bs[0][0] + tid, A.bmask + gf);
     S.finfo[0][tid] = A.finfo[gf];
-    if constexpr (PREFETCH_FV)
+  }
+  // Software prefetch into L2 for the CTA that will run in this slot next (A.pf_dist CTAs further on): its solution
+  // rows, neighbour face blocks and (k_resid) viscous-flux blocks, so that its staging copies hit L2 instead of HBM.
+  if constexpr (NEIGHBOURS)
+  {
+    const int p0 = l0 + A.pf_dist * E;
+    if (A.pf_dist > 0 && p0 < A.hi)
     {
-      // the viscous normal fluxes are read (own and neighbour block of every face) by the RM phase: pull their lines
-      // into L2 now so that those loads do not pay the HBM latency
-      const char *po = (const char *)(A.fv + gf * (4 * NN));
-      const char *pn = (const char *)(A.fv + (size_t)A.nbr[gf] * (4 * NN));
-#pragma unroll
-      for (int b = 0; b < 4 * NN * 8; b += 128) { prefetch_l2(po + b); prefetch_l2(pn + b); }
+      const int pn = min(E, A.hi - p0);
+      constexpr int ROW_LINES = (E * NU * 8 + 127) / 128 + 1;
+      if (!A.elist)
+      {
+        for (int i = tid; i < NF * ROW_LINES; i += NT)
+        {
+          const int k = i / ROW_LINES, b = i - k * ROW_LINES;
+          if (b * 128 < pn * NU * 8 + 120) prefetch_l2((const char *)(A.u0 + (size_t)NU * (p0 + (size_t)A.n_eles * k)) + b * 128);
+        }
+      }
+      constexpr int FU_LINES = (NF * NN * 8 + 127) / 128 + 1, FV_LINES = (4 * NN * 8 + 127) / 128 + 1;
+      for (int i = tid; i < pn * 6 * FU_LINES; i += NT)
+      {
+        const int ef = i / FU_LINES, b = i - ef * FU_LINES;
+        const int blk = A.nbr[(size_t)elem_id(A, p0 + ef / 6) * 6 + ef % 6];
+        prefetch_l2((const char *)(A.fu_cur + (size_t)blk * (NF * NN)) + b * 128);
+      }
+      if constexpr (PREFETCH_FV)
+      {
+        for (int i = tid; i < pn * 6 * FV_LINES; i += NT)
+        {
+          const int ef = i / FV_LINES, b = i - ef * FV_LINES;
+          const size_t gf = (size_t)elem_id(A, p0 + ef / 6) * 6 + ef % 6;
+          prefetch_l2((const char *)(A.fv + gf * (4 * NN)) + b * 128);
+          prefetch_l2((const char *)(A.fv + (size_t)A.nbr[gf] * (4 * NN)) + b * 128);
+        }
+      }
     }
   }
   cp_async_commit();
