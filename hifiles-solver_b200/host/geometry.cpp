@@ -14,7 +14,7 @@
 
 using namespace std;
 
-solution::solution() : mesh_eles_tris("tri"), mesh_eles_tets("tet"), mesh_eles_pris("prism")
+solution::solution()
 {
   rank = 0;
   nproc = 1;

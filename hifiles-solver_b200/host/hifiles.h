@@ -163,6 +163,22 @@ void eval_isentropic_vortex(hf_array<double> &pos, double time, double &rho, dou
 /*! 1-D Gauss (rule 0) / Gauss-Lobatto (rule 1) points and weights from the reference's binary tables
  *  (reference src/cubature_1d.cpp:50-85). */
 void cubature_1d(int in_rule, int in_order, hf_array<double> &locs, hf_array<double> &weights);
+/*! simplex point tables of the data directory: locs(point, coordinate); rule 0 = interior (with weights), 1 = alpha-optimised */
+void cubature_tri(int in_rule, int in_order, hf_array<double> &locs, hf_array<double> &weights);
+void cubature_tet(int in_rule, int in_order, hf_array<double> &locs, hf_array<double> &weights);
+// Dubiner bases and small dense algebra (host/simplex_basis.cpp)
+double eval_jacobi(double r, int alpha, int beta, int mode);
+double eval_grad_jacobi(double r, int alpha, int beta, int mode);
+double eval_dubiner_basis_2d(double r, double s, int mode, int order);
+double eval_dr_dubiner_basis_2d(double r, double s, int mode, int order);
+double eval_ds_dubiner_basis_2d(double r, double s, int mode, int order);
+double eval_dubiner_basis_3d(double r, double s, double t, int mode, int order);
+double eval_grad_dubiner_basis_3d(double r, double s, double t, int mode, int order, int component);
+hf_array<double> mult_arrays(hf_array<double> &A, hf_array<double> &B);
+hf_array<double> transpose_array(hf_array<double> &A);
+hf_array<double> inv_array(hf_array<double> &in);
+void get_opp_3_tri(hf_array<double> &opp_3, hf_array<double> &loc_upts_tri, hf_array<double> &loc_1d_fpts, hf_array<double> &vandermonde_tri,
+                   hf_array<double> &inv_vandermonde_tri, int n_upts_per_tri, int order, double c_tri, int vcjh_scheme_tri);
 
 // ---------------------------------------------------------------------------------------------------------
 // mesh (reference include/mesh.h, src/mesh.cpp, src/mesh_reader.cpp)
@@ -280,7 +296,7 @@ public:
   void set_transforms_fpts();
   void calc_pos(hf_array<double> &in_loc, int in_ele, hf_array<double> &out_pos);
   void calc_d_pos(hf_array<double> &in_loc, int in_ele, hf_array<double> &out_d_pos);
-  double calc_h_ref_specific(int in_ele);
+  virtual double calc_h_ref_specific(int in_ele);
 
   /*! flux-point index inside the element from (local face, face-local flux point): the arithmetic of the
    *  reference's eleven pointer getters (reference src/eles.cpp:4638-4871) */
@@ -341,19 +357,52 @@ private:
   void set_tnorm_fpts();
 };
 
-/*! Simplex / prism element types are accepted by the mesh front-end but their operator setup is not built yet
- *  (SURVEY.md §8 "next"): a mesh containing them fails loudly. */
-class eles_unavailable : public eles
+/*! Triangles, tetrahedra, prisms: Dubiner modal basis, dense operators (host/eles_simplex.cpp) */
+class eles_tris : public eles
 {
 public:
-  explicit eles_unavailable(const char *nm) : name(nm) {}
-  void setup_ele_type_specific() override { FatalError(std::string(name) + " elements: operator setup not available in this build"); }
-  double eval_nodal_basis(int, hf_array<double> &) override { return 0.; }
-  double eval_d_nodal_basis(int, int, hf_array<double> &) override { return 0.; }
-  void fill_opp_3(hf_array<double> &) override {}
-  double eval_nodal_s_basis(int, hf_array<double> &, int) override { return 0.; }
-  void eval_d_nodal_s_basis(hf_array<double> &, hf_array<double> &, int) override {}
-  const char *name;
+  void setup_ele_type_specific() override;
+  double eval_nodal_basis(int in_index, hf_array<double> &in_loc) override;
+  double eval_d_nodal_basis(int in_index, int in_cpnt, hf_array<double> &in_loc) override;
+  void fill_opp_3(hf_array<double> &opp_3) override;
+  double eval_nodal_s_basis(int in_index, hf_array<double> &in_loc, int in_n_spts) override;
+  void eval_d_nodal_s_basis(hf_array<double> &d_nodal_s_basis, hf_array<double> &in_loc, int in_n_spts) override;
+  double calc_h_ref_specific(int in_ele) override;
+  hf_array<double> vandermonde, inv_vandermonde, loc_1d_fpts;
+};
+
+class eles_tets : public eles
+{
+public:
+  void setup_ele_type_specific() override;
+  double eval_nodal_basis(int in_index, hf_array<double> &in_loc) override;
+  double eval_d_nodal_basis(int in_index, int in_cpnt, hf_array<double> &in_loc) override;
+  void fill_opp_3(hf_array<double> &opp_3) override;
+  double eval_nodal_s_basis(int in_index, hf_array<double> &in_loc, int in_n_spts) override;
+  void eval_d_nodal_s_basis(hf_array<double> &d_nodal_s_basis, hf_array<double> &in_loc, int in_n_spts) override;
+  double calc_h_ref_specific(int in_ele) override;
+  hf_array<double> vandermonde, inv_vandermonde;
+
+private:
+  double eval_div_dg_tet(int in_index, hf_array<double> &loc, hf_array<double> &cub, hf_array<double> &cub_w);
+};
+
+class eles_pris : public eles
+{
+public:
+  void setup_ele_type_specific() override;
+  double eval_nodal_basis(int in_index, hf_array<double> &in_loc) override;
+  double eval_d_nodal_basis(int in_index, int in_cpnt, hf_array<double> &in_loc) override;
+  void fill_opp_3(hf_array<double> &opp_3) override;
+  double eval_nodal_s_basis(int in_index, hf_array<double> &in_loc, int in_n_spts) override;
+  void eval_d_nodal_s_basis(hf_array<double> &d_nodal_s_basis, hf_array<double> &in_loc, int in_n_spts) override;
+  double calc_h_ref_specific(int in_ele) override;
+  int n_upts_tri, n_upts_1d;
+  hf_array<double> loc_upts_pri_1d, loc_upts_pri_tri, vandermonde_tri, inv_vandermonde_tri, loc_1d_fpts;
+
+private:
+  double tri_part(int index_tri, int cpnt, hf_array<double> &in_loc);
+  int face0_map(int index);
 };
 
 // ---------------------------------------------------------------------------------------------------------
@@ -429,10 +478,10 @@ struct solution
   int n_ele_types, n_dims, num_cells_global, ini_iter;
   hf_array<eles *> mesh_eles;
   eles_quads mesh_eles_quads;
-  eles_unavailable mesh_eles_tris;
+  eles_tris mesh_eles_tris;
   eles_hexas mesh_eles_hexas;
-  eles_unavailable mesh_eles_tets;
-  eles_unavailable mesh_eles_pris;
+  eles_tets mesh_eles_tets;
+  eles_pris mesh_eles_pris;
   int n_int_inter_types, n_bdy_inter_types, n_mpi_inter_types, n_mpi_inters;
   std::vector<int_inters> mesh_int_inters;
   std::vector<bdy_inters> mesh_bdy_inters;

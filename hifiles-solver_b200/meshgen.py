@@ -143,6 +143,179 @@ def quad_box(path, n, lengths=(20., 20.), bcs=None, origin=(-10., -10.), warp=0.
     return dict(n_cells=conn.shape[0], n_nodes=nodes.shape[0])
 
 
+def _write_neu(path, ndim, nodes, cells, groups):
+    """nodes: (id, x, y[, z]) rows; cells: list of (id, ntype, [node ids]) ; groups: {name: rows (cell, ntype, face)}"""
+    with open(path, "w") as f:
+        f.write(_header(os.path.basename(path), nodes.shape[0], len(cells), len(groups), ndim))
+        f.write("   NODAL COORDINATES 2.3.16\n")
+        _write_rows(f, nodes, "%10d " + " ".join(["%19.16e"] * ndim))
+        f.write("ENDOFSECTION\n      ELEMENTS/CELLS 2.3.16\n")
+        out = []
+        for cid, ntype, vs in cells:
+            head = "%8d %2d %2d " % (cid, ntype, len(vs))
+            first, rest = vs[:7], vs[7:]
+            out.append(head + "".join("%8d" % v for v in first) + "\n")
+            while rest:
+                out.append("               " + "".join("%8d" % v for v in rest[:7]) + "\n")
+                rest = rest[7:]
+        f.write("".join(out))
+        f.write("ENDOFSECTION\n")
+        _group(f, len(cells))
+        for name, rows in groups.items():
+            rows = np.asarray(rows)
+            f.write(" BOUNDARY CONDITIONS 2.3.16\n%32s%8d%8d%8d%8d\n" % (name, 1, rows.shape[0], 0, 6))
+            _write_rows(f, rows, "%10d%5d%5d")
+            f.write("ENDOFSECTION\n")
+    return dict(n_cells=len(cells), n_nodes=nodes.shape[0])
+
+
+def mixed_box_2d(path, n, lengths=(20., 20.), bcs=None, origin=(-10., -10.), kind="tri", warp=0.0):
+    """Nx x Ny cells on a rectangle.  kind: 'tri' (every cell split into two triangles along its (0,0)-(1,1) diagonal),
+    'quad', or 'mixed' (quads in the left half, triangles in the right half: BASELINE config 2's element mix).
+    Gambit records: triangles `id 3 3 n1 n2 n3` (counter-clockwise; edge k joins nodes k, k+1: mesh_reader.cpp:192-197,
+    :333-334), quads as in quad_box."""
+    if np.isscalar(n):
+        n = (n, n)
+    nx, ny = n
+    if bcs is None:
+        bcs = {s: "Cyclic" for s in ("x-", "x+", "y-", "y+")}
+    px, py = nx + 1, ny + 1
+    gx, gy = np.meshgrid(np.arange(px), np.arange(py), indexing="ij")
+    x = origin[0] + lengths[0] * gx / nx
+    y = origin[1] + lengths[1] * gy / ny
+    if warp:
+        bump = warp * np.sin(np.pi * gx / nx) * np.sin(np.pi * gy / ny)
+        x = x + bump * lengths[0] / nx * np.sin(2 * np.pi * gy / ny + 0.3)
+        y = y + bump * lengths[1] / ny * np.sin(2 * np.pi * gx / nx + 0.7)
+    nid = 1 + gx + px * gy
+    order = np.argsort(nid.ravel())
+    nodes = np.column_stack([nid.ravel()[order], x.ravel()[order], y.ravel()[order]])
+    cells, groups = [], {}
+
+    def bface(side, cid, ntype, k):
+        if side in bcs:
+            groups.setdefault(bcs[side], []).append((cid, ntype, k))
+
+    cid = 0
+    for j in range(ny):
+        for i in range(nx):
+            v00, v10, v11, v01 = nid[i, j], nid[i + 1, j], nid[i + 1, j + 1], nid[i, j + 1]
+            as_quad = kind == "quad" or (kind == "mixed" and i < nx // 2)
+            if as_quad:
+                cid += 1
+                cells.append((cid, 2, [v00, v10, v11, v01]))
+                if j == 0: bface("y-", cid, 2, 1)
+                if i == nx - 1: bface("x+", cid, 2, 2)
+                if j == ny - 1: bface("y+", cid, 2, 3)
+                if i == 0: bface("x-", cid, 2, 4)
+            else:
+                cid += 1
+                cells.append((cid, 3, [v00, v10, v11]))
+                if j == 0: bface("y-", cid, 3, 1)
+                if i == nx - 1: bface("x+", cid, 3, 2)
+                cid += 1
+                cells.append((cid, 3, [v00, v11, v01]))
+                if j == ny - 1: bface("y+", cid, 3, 2)
+                if i == 0: bface("x-", cid, 3, 3)
+    return _write_neu(path, 2, nodes, cells, groups)
+
+
+def tri_box(path, n, **kw):
+    return mixed_box_2d(path, n, kind="tri", **kw)
+
+
+_KUHN = [(0, 1, 2), (0, 2, 1), (1, 0, 2), (1, 2, 0), (2, 0, 1), (2, 1, 0)]
+# Gambit face number of the local faces (reference src/mesh_reader.cpp:336-350, inverted)
+_TET_GAMBIT_FACE = {3: 1, 2: 2, 0: 3, 1: 4}          # local face f is opposite local vertex f
+_PRI_GAMBIT_FACE = {2: 1, 3: 2, 4: 3, 0: 4, 1: 5}    # local faces: 0 bottom, 1 top triangle, 2..4 the sides over edges 01, 12, 20
+_HEX_GAMBIT_FACE = {"z-": 1, "y+": 2, "z+": 3, "y-": 4, "x-": 5, "x+": 6}
+
+
+def mixed_box_3d(path, n, lengths=(2 * np.pi,) * 3, bcs=None, origin=(0., 0., 0.), kind="tet", warp=0.0):
+    """Nx x Ny x Nz cubes on a box.  kind:
+      'tet'      every cube split into six tetrahedra around its (0,0,0)-(1,1,1) diagonal (Kuhn), which cuts every cube
+                 face along the diagonal from its lowest to its highest corner, so the split is conforming and periodic;
+      'pri'      every cube split into two prisms extruded along y, triangles in the x-z plane cut along the same diagonal;
+      'hex'      bricks;
+      'hexpri'   bricks for z-index < Nz/2, prisms above (they meet through the prisms' quadrilateral z faces);
+      'pritet'   prisms for y-index < Ny/2, tetrahedra above (they meet through triangles in x-z planes).
+    Records: tets `id 6 4 n1..n4` (slots 0..3), prisms `id 5 6 n1..n6` (bottom triangle then top triangle), bricks as in
+    hex_box (mesh_reader.cpp:207-246)."""
+    if np.isscalar(n):
+        n = (n, n, n)
+    nx, ny, nz = n
+    sides = ("x-", "x+", "y-", "y+", "z-", "z+")
+    if bcs is None:
+        bcs = {s: "Cyclic" for s in sides}
+    px, py, pz = nx + 1, ny + 1, nz + 1
+    gx, gy, gz = np.meshgrid(np.arange(px), np.arange(py), np.arange(pz), indexing="ij")
+    x = origin[0] + lengths[0] * gx / nx
+    y = origin[1] + lengths[1] * gy / ny
+    z = origin[2] + lengths[2] * gz / nz
+    if warp:
+        bump = warp * np.sin(np.pi * gx / nx) * np.sin(np.pi * gy / ny) * np.sin(np.pi * gz / nz)
+        x = x + bump * lengths[0] / nx * np.sin(2 * np.pi * gy / ny + 0.3)
+        y = y + bump * lengths[1] / ny * np.sin(2 * np.pi * gz / nz + 0.7)
+        z = z + bump * lengths[2] / nz * np.sin(2 * np.pi * gx / nx + 1.1)
+    nid = 1 + gx + px * (gy + py * gz)
+    order = np.argsort(nid.ravel())
+    nodes = np.column_stack([nid.ravel()[order], x.ravel()[order], y.ravel()[order], z.ravel()[order]])
+    cells, groups = [], {}
+
+    def on_side(ijk_list):
+        """box side all the given lattice points lie on, or None"""
+        a = np.array(ijk_list)
+        for d, (lo, hi) in enumerate((("x-", "x+"), ("y-", "y+"), ("z-", "z+"))):
+            if np.all(a[:, d] == 0): return lo
+            if np.all(a[:, d] == n[d]): return hi
+        return None
+
+    def bface(side, cid, ntype, k):
+        if side is not None and side in bcs:
+            groups.setdefault(bcs[side], []).append((cid, ntype, k))
+
+    tet_faces = [(1, 2, 3), (0, 3, 2), (0, 1, 3), (0, 2, 1)]
+    pri_faces = [(0, 2, 1), (3, 4, 5), (0, 1, 4, 3), (1, 2, 5, 4), (2, 0, 3, 5)]
+    cid = 0
+    for k in range(nz):
+        for j in range(ny):
+            for i in range(nx):
+                if kind == "hexpri": sub = "hex" if k < nz // 2 else "pri"
+                elif kind == "pritet": sub = "pri" if j < ny // 2 else "tet"
+                else: sub = kind
+                P = lambda a, b, c: (i + a, j + b, k + c)
+                if sub == "hex":
+                    cid += 1
+                    pts = [P(0, 0, 0), P(0, 1, 0), P(0, 0, 1), P(0, 1, 1), P(1, 0, 0), P(1, 1, 0), P(1, 0, 1), P(1, 1, 1)]
+                    cells.append((cid, 4, [nid[q] for q in pts]))
+                    for side, cond in (("z-", k == 0), ("y+", j == ny - 1), ("z+", k == nz - 1), ("y-", j == 0), ("x-", i == 0), ("x+", i == nx - 1)):
+                        if cond: bface(side, cid, 4, _HEX_GAMBIT_FACE[side])
+                elif sub == "pri":
+                    # triangles in the x-z plane (counter-clockwise seen from -y, so that bottom -> top points along +y)
+                    for tri in ([P(0, 0, 0), P(1, 0, 1), P(1, 0, 0)], [P(0, 0, 0), P(0, 0, 1), P(1, 0, 1)]):
+                        cid += 1
+                        pts = tri + [(a, b + 1, c) for (a, b, c) in tri]
+                        cells.append((cid, 5, [nid[q] for q in pts]))
+                        for f, vs in enumerate(pri_faces):
+                            bface(on_side([pts[v] for v in vs]), cid, 5, _PRI_GAMBIT_FACE[f])
+                else:
+                    for perm in _KUHN:
+                        cur = [0, 0, 0]
+                        pts = [P(*cur)]
+                        for ax in perm:
+                            cur[ax] = 1
+                            pts.append(P(*cur))
+                        # positive orientation: even permutations as they are, odd ones with two vertices swapped
+                        sign = np.linalg.det(np.array([np.subtract(pts[m], pts[0]) for m in (1, 2, 3)], dtype=float))
+                        if sign < 0:
+                            pts[2], pts[3] = pts[3], pts[2]
+                        cid += 1
+                        cells.append((cid, 6, [nid[q] for q in pts]))
+                        for f, vs in enumerate(tet_faces):
+                            bface(on_side([pts[v] for v in vs]), cid, 6, _TET_GAMBIT_FACE[f])
+    return _write_neu(path, 3, nodes, cells, groups)
+
+
 # ---- input files -------------------------------------------------------------------------------------------------------
 _TGV_DEFAULTS = dict(
     equation=0, viscous=1, riemann_solve_type=3, vis_riemann_solve_type=0, ic_form=7, test_case=0, order=4, dt_type=0,
