@@ -51,13 +51,41 @@ CASES = {
                                           nz_c_ic=0., T_c_ic=300., rho_c_ic=1.17, Mach_free_stream=0.2, rho_free_stream=1.17, T_free_stream=300.,
                                           L_free_stream=1., dx_cyclic=1., dy_cyclic=1., dz_cyclic=None, bc_Wall_type="adiabat_wall",
                                           bc_Far_type="sub_out_char", bc_Far_p_static=100500.)),
+    # simplex / prism element types (dense Dubiner-basis operators) and mixed meshes: BASELINE configs 2 and 4
+    "tri_p3_ns_rusanov_rk34": ("tri", 4, dict(lengths=(6.2831853071795862,) * 2, origin=(0., 0.)),
+                               dict(order=3, adv_type=2, riemann_solve_type=0, viscous=1, dt=2e-5, dz_cyclic=None)),
+    "tri_p2_euler_vortex_hllc_rk45": ("tri", 6, {}, dict(order=2, adv_type=3, riemann_solve_type=3, viscous=0, ic_form=0, test_case=1, dt=1e-3,
+                                                       dx_cyclic=20., dy_cyclic=20., dz_cyclic=None, **EULER_IC)),
+    "mixed_tri_quad_p3_ns_rusanov_walls": ("mixed", (8, 6), dict(lengths=(4., 2.), origin=(0., 0.), bcs={"x-": "In", "x+": "Out", "y-": "Wall", "y+": "Top"}),
+                                           dict(order=3, adv_type=3, riemann_solve_type=0, viscous=1, ic_form=1, dt=5e-5, fix_vis=0, Mach_c_ic=0.3, nx_c_ic=1.,
+                                                ny_c_ic=0., nz_c_ic=0., T_c_ic=300., rho_c_ic=1.17, Mach_free_stream=0.3, rho_free_stream=1.17,
+                                                T_free_stream=300., L_free_stream=1., dx_cyclic=None, dy_cyclic=None, dz_cyclic=None, bc_Cyclic_type=None,
+                                                bc_In_type="char", bc_In_p_static=100747., bc_In_mach=0.3, bc_In_T_static=300., bc_In_nx=1., bc_In_ny=0.,
+                                                bc_Out_type="sub_out_simp", bc_Out_p_static=100000., bc_Wall_type="isotherm_wall", bc_Wall_T_static=310.,
+                                                bc_Top_type="adiabat_wall", bc_Top_u=20.)),
+    "tet_p3_ns_roem_rk34": ("tet", 2, {}, dict(order=3, adv_type=2, riemann_solve_type=2, viscous=1, dt=1e-5)),
+    "tet_p2_ns_hllc_cfl_local_dt": ("tet", 2, dict(warp=0.15), dict(order=2, adv_type=3, riemann_solve_type=3, viscous=1, dt_type=2, CFL=0.3, dt=None)),
+    "pri_p3_ns_roem_rk45": ("pri", 2, {}, dict(order=3, adv_type=3, riemann_solve_type=2, viscous=1, dt=1e-5)),
+    "hexpri_p2_ns_roem_rk34": ("hexpri", (2, 2, 4), {}, dict(order=2, adv_type=2, riemann_solve_type=2, viscous=1, dt=2e-5)),
+    "pritet_p3_ns_roem_rk34": ("pritet", (2, 4, 2), {}, dict(order=3, adv_type=2, riemann_solve_type=2, viscous=1, dt=1e-5)),
 }
+
+
+def make_mesh(meshgen, kind, mesh, n, mkw):
+    if kind == "hex":
+        meshgen.hex_box(mesh, n, **mkw)
+    elif kind == "quad":
+        meshgen.quad_box(mesh, n, **mkw)
+    elif kind in ("tri", "mixed"):
+        meshgen.mixed_box_2d(mesh, n, kind=kind, **mkw)
+    else:
+        meshgen.mixed_box_3d(mesh, n, kind=kind, **mkw)
 
 
 def make_case(tmp_path, meshgen, name):
     kind, n, mkw, opts = CASES[name]
     mesh = str(tmp_path / (name + ".neu"))
-    (meshgen.hex_box if kind == "hex" else meshgen.quad_box)(mesh, n, **mkw)
+    make_mesh(meshgen, kind, mesh, n, mkw)
     inp = str(tmp_path / ("input_" + name))
     meshgen.write_input(inp, name + ".neu", **opts)
     return inp
