@@ -183,8 +183,9 @@ class Oracle:
         self.detjac_upts, self.JGinv_upts = g("detjac_upts"), g("JGinv_upts")
         self.detjac_fpts, self.JGinv_fpts = g("detjac_fpts"), g("JGinv_fpts")
         self.tdA_fpts, self.norm_fpts = g("tdA_fpts"), g("norm_fpts")
-        self.idx_l = np.asarray(setup[inter_prefix + ".idx_l"]).ravel(order="F")
-        self.idx_r = np.asarray(setup[inter_prefix + ".idx_r"]).ravel(order="F")
+        prefixes = [inter_prefix] if isinstance(inter_prefix, str) else list(inter_prefix)  # a prism has triangular and quadrilateral faces
+        self.idx_l = np.concatenate([np.asarray(setup[q + ".idx_l"]).ravel(order="F") for q in prefixes])
+        self.idx_r = np.concatenate([np.asarray(setup[q + ".idx_r"]).ravel(order="F") for q in prefixes])
         self.u = [np.array(g("disu_upts_ic"), order="F"), np.zeros((self.nu, self.ne, self.nf), order="F")]
         self.div = np.zeros((self.nu, self.ne, self.nf), order="F")
 

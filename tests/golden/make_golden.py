@@ -25,24 +25,33 @@ GOLDEN = {
                                                           dx_cyclic=20., dy_cyclic=20., dz_cyclic=None, **EULER_IC), 3),
     "quad4_p2_ns_rusanov_euler": ("quad", 4, dict(lengths=(6.2831853071795862,) * 2, origin=(0., 0.)),
                                   dict(order=2, adv_type=0, riemann_solve_type=0, viscous=1, dt=2e-5, dz_cyclic=None), 3),
+    "tri3_p3_ns_rusanov_rk34": ("tri", 3, dict(lengths=(6.2831853071795862,) * 2, origin=(0., 0.)),
+                                dict(order=3, adv_type=2, riemann_solve_type=0, viscous=1, dt=2e-5, dz_cyclic=None), 2),
+    "tet1_p2_ns_roem_rk34": ("tet", 1, {}, dict(order=2, adv_type=2, riemann_solve_type=2, viscous=1, dt=1e-5), 2),
+    "pri1_p2_ns_hllc_rk45": ("pri", (1, 2, 1), {}, dict(order=2, adv_type=3, riemann_solve_type=3, viscous=1, dt=1e-5), 2),
 }
+KINDS = ["hex", "quad", "tri", "tet", "pri"]
 KEEP_PREFIX = ("meta", "params", "rk_a", "rk_b", "history.", "final.", "mesh.f2c", "mesh.f2loc_f", "mesh.rot_tag", "mesh.c2v", "mesh.xv",
                "step0.stage0.s18_corrected_divergence", "step0.stage0.advanced", "step0.stage0.s09_common_invFlux", "step0.stage0.s11_correct_gradient",
-               "hex.", "quad.", "int_quad.", "int_seg.")
+               "hex.", "quad.", "tri.", "tet.", "pri.", "int_quad.", "int_seg.", "int_tri.")
 
 
 def main():
     hb = conftest.load_package()
     import importlib
     mg = importlib.import_module("hifiles_solver_b200.meshgen")
+    only = sys.argv[1:]
     for name, (kind, n, mkw, opts, steps) in GOLDEN.items():
+        if only and name not in only:
+            continue
         work = pathlib.Path(tempfile.mkdtemp())
         mesh = str(work / (name + ".neu"))
-        (mg.hex_box if kind == "hex" else mg.quad_box)(mesh, n, **mkw)
+        from test_staged_parity import make_mesh
+        make_mesh(mg, kind, mesh, n, mkw)
         inp = mg.write_input(str(work / ("input_" + name)), name + ".neu", **opts)
         ref = util.run_reference(inp, steps, stagewise=True)
         keep = {k.replace(".", "__"): v for k, v in ref.items() if k.startswith(KEEP_PREFIX)}
-        keep["case__kind"] = np.array([0 if kind == "hex" else 1])
+        keep["case__kind"] = np.array([KINDS.index(kind)])
         keep["case__n"] = np.array([n])
         keep["case__steps"] = np.array([steps])
         keep["case__mesh_text"] = np.frombuffer(open(mesh, "rb").read(), dtype=np.uint8)

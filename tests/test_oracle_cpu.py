@@ -22,8 +22,8 @@ def load(path):
 
 
 def make_oracle(g):
-    kind = "hex" if int(g["case.kind"][0]) == 0 else "quad"
-    inter = "int_quad" if kind == "hex" else "int_seg"
+    kind = ["hex", "quad", "tri", "tet", "pri"][int(g["case.kind"][0])]
+    inter = {"hex": ["int_quad"], "quad": ["int_seg"], "tri": ["int_seg"], "tet": ["int_tri"], "pri": ["int_tri", "int_quad"]}[kind]
     n_dims, _, order, viscous, riemann, adv = [int(x) for x in g["meta"]]
     p = g["params"]
     P = ho.Params(gamma=p[0], prandtl=p[1], mu_inf=p[2], rt_inf=p[3], c_sth=p[4], fix_vis=p[5], ldg_beta=p[6], ldg_tau=p[7], dt=p[8],

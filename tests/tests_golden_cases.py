@@ -5,4 +5,7 @@ GOLDEN_CASES = {
     "hex3_p1_ns_roem_sutherland_rk24": ("hex", 3, {}),
     "quad4_p3_euler_vortex_hllc_rk45": ("quad", 4, {}),
     "quad4_p2_ns_rusanov_euler": ("quad", 4, dict(lengths=(6.2831853071795862,) * 2, origin=(0., 0.))),
+    "tri3_p3_ns_rusanov_rk34": ("tri", 3, dict(lengths=(6.2831853071795862,) * 2, origin=(0., 0.))),
+    "tet1_p2_ns_roem_rk34": ("tet", 1, {}),
+    "pri1_p2_ns_hllc_rk45": ("pri", (1, 2, 1), {}),
 }
