@@ -73,6 +73,54 @@ __global__ void k_op_apply(hf_ell3 E, const double *__restrict__ in, size_t in_d
   out[idx] = acc;
 }
 
+// Persson's modal sensor and the exponential filter, one CTA per element (reference src/eles.cpp:2918-2959 and
+// <type>::shock_det_persson): uhat = V^-1 u_field, sensor = sum_top w uhat^2 / sum_all w uhat^2 (both sums in ascending
+// mode order, as the reference's loops); if sensor >= s0 every field of the element is replaced by exp_filter * u.
+__global__ void k_shock_capture(int n_upts, int n_eles, int n_fields, int det_field, double s0, double *__restrict__ u, const double *__restrict__ inv_vdm,
+                                const double *__restrict__ w_top, const double *__restrict__ w_all, const double *__restrict__ filt,
+                                double *__restrict__ sensor)
+{
+  extern __shared__ double sh[]; // [n_upts] squared modal values, then [n_upts * n_fields] the element's solution
+  double *m2 = sh, *us = sh + n_upts;
+  __shared__ int flagged;
+  const int e = blockIdx.x;
+  const size_t fs = (size_t)n_upts * n_eles;
+  for (int q = threadIdx.x; q < n_upts * n_fields; q += blockDim.x)
+  {
+    const int k = q / n_upts, j = q - k * n_upts;
+    us[q] = u[j + (size_t)n_upts * e + k * fs];
+  }
+  __syncthreads();
+  for (int j = threadIdx.x; j < n_upts; j += blockDim.x)
+  {
+    double acc = 0.0;
+    for (int l = 0; l < n_upts; l++) acc += (1.0 * us[l + det_field * n_upts]) * inv_vdm[j + (size_t)n_upts * l];
+    m2[j] = acc * acc;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0)
+  {
+    double top = 0, all = 0.;
+    for (int j = 0; j < n_upts; j++)
+    {
+      if (w_top[j] != 0.) top += m2[j] * w_top[j];
+      all = all + w_all[j] * m2[j];
+    }
+    const double sv = top / all;
+    sensor[e] = sv;
+    flagged = sv >= s0;
+  }
+  __syncthreads();
+  if (!flagged) return;
+  for (int q = threadIdx.x; q < n_upts * n_fields; q += blockDim.x)
+  {
+    const int k = q / n_upts, j = q - k * n_upts;
+    double acc = 0.0;
+    for (int l = 0; l < n_upts; l++) acc += (1.0 * us[l + k * n_upts]) * filt[j + (size_t)n_upts * l];
+    u[j + (size_t)n_upts * e + k * fs] = acc;
+  }
+}
+
 // y -= x  (the daxpy of calculate_corrected_divergence, reference src/eles.cpp:1746-1750)
 __global__ void k_sub(double *__restrict__ y, const double *__restrict__ x, long long n)
 {
@@ -582,7 +630,13 @@ int hf_dev_create(hf_ctx **out, int device, int rank, int nproc)
   hf_ctx *c = new hf_ctx();
   c->device = device; c->rank = rank; c->nproc = nproc;
   HF_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-  HF_CUDA(cudaStreamCreateWithFlags(&c->comm_stream, cudaStreamNonBlocking));
+  {
+    // the halo exchange runs beside a compute kernel that fills every SM with queued CTAs: give its stream the highest
+    // priority so that the NCCL kernel's CTAs are placed as soon as a slot frees up instead of behind the whole grid
+    int prio_lo = 0, prio_hi = 0;
+    HF_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+    HF_CUDA(cudaStreamCreateWithPriority(&c->comm_stream, cudaStreamNonBlocking, prio_hi));
+  }
   c->own_stream = true;
   HF_CUDA(cudaEventCreateWithFlags(&c->ev_a, cudaEventDisableTiming));
   HF_CUDA(cudaEventCreateWithFlags(&c->ev_b, cudaEventDisableTiming));
@@ -633,6 +687,7 @@ int hf_dev_set_params(hf_ctx *c, const hf_params *p)
   P.diff_coeff = p->diff_coeff; P.lambda = p->lambda;
   P.riemann_solve_type = p->riemann_solve_type;
   P.gamma_over_pr = p->gamma / p->prandtl;
+  if (p->shock_cap && p->shock_cap != 1) HF_FAIL("Shock capturing method not implemented.");
   if (p->equation == 0 && !(p->riemann_solve_type == 0 || p->riemann_solve_type == 2 || p->riemann_solve_type == 3))
     HF_FAIL("Riemann solver not implemented");
   if (p->viscous && p->vis_riemann_solve_type != 0) HF_FAIL("Viscous Riemann solver not implemented");
@@ -698,6 +753,26 @@ int hf_dev_upload_eles(hf_ctx *c, const hf_eles_desc *d)
   {
     if (hf_alloc_zero(c, &e.delta_disu_fpts, NFP * F)) return 1;
     if (hf_alloc_zero(c, &e.grad_disu_fpts, NFP * F * nd)) return 1;
+  }
+  if (c->prm.over_int)
+  {
+    if (!d->n_over_int_cubpts || !d->opp_over_int_cubpts || !d->over_int_filter || !d->JGinv_over_int_cubpts) HF_FAIL("over_int needs the over-integration operators");
+    e.n_cub = d->n_over_int_cubpts;
+    const size_t NC = (size_t)e.n_cub * e.n_eles;
+    if (build_ell(c, e.opp_over_int, d->opp_over_int_cubpts, e.n_cub, nu)) return 1;
+    if (build_ell(c, e.over_int_filter, d->over_int_filter, nu, e.n_cub)) return 1;
+    if (hf_alloc_copy(c, &e.JGinv_over_int, d->JGinv_over_int_cubpts, NC * nd * nd)) return 1;
+    if (hf_alloc_zero(c, &e.u_cub, NC * F)) return 1;
+    if (hf_alloc_zero(c, &e.tdisf_cub, NC * F * nd)) return 1;
+  }
+  if (c->prm.shock_cap)
+  {
+    if (!d->inv_vandermonde || !d->exp_filter || !d->sensor_w_top || !d->sensor_w_all) HF_FAIL("shock_cap needs the modal transform, sensor weights and filter");
+    if (hf_alloc_copy(c, &e.inv_vandermonde, d->inv_vandermonde, (size_t)nu * nu)) return 1;
+    if (hf_alloc_copy(c, &e.exp_filter, d->exp_filter, (size_t)nu * nu)) return 1;
+    if (hf_alloc_copy(c, &e.sensor_w_top, d->sensor_w_top, (size_t)nu)) return 1;
+    if (hf_alloc_copy(c, &e.sensor_w_all, d->sensor_w_all, (size_t)nu)) return 1;
+    if (hf_alloc_zero(c, &e.sensor, (size_t)e.n_eles)) return 1;
   }
   // tdisf_upts, norm_tdisf_fpts, grad_disu_upts are only needed by the staged path: allocated lazily
   if (c->fused && hf_fused_on_upload(c, e, d)) return 1;
@@ -952,6 +1027,28 @@ int hf_dev_eles_op(hf_ctx *c, int ele_type, int op)
     c->ufpts_valid = false;
     return op_apply(c, ell1(e.opp_3), e.norm_tconf_fpts, 0, e.div_tconf_upts, ncols, true);
   }
+  case HF_EVALUATE_INVFLUX_OVER_INT:
+  {
+    if (!c->prm.over_int) HF_FAIL("evaluate_invFlux_over_int called without over_int");
+    const size_t NC = (size_t)e.n_cub * e.n_eles;
+    if (op_apply(c, ell1(e.opp_over_int), e.disu_upts[0], 0, e.u_cub, ncols, false)) return 1;
+    HF_DISPATCH(nd, nfl, (k_point_flux<ND, NF, false><<<hf_blocks(NC, 128), 128, 0, c->stream>>>((long long)NC, e.u_cub, nullptr, e.JGinv_over_int, e.tdisf_cub, c->phys)));
+    HF_LAUNCH_CHECK(c);
+    for (int d = 0; d < nd; d++)
+      if (op_apply(c, ell1(e.over_int_filter), e.tdisf_cub + d * NC * nfl, 0, e.tdisf_upts + d * NU * nfl, ncols, false)) return 1;
+    return 0;
+  }
+  case HF_SHOCK_CAPTURE:
+  {
+    if (!c->prm.shock_cap) HF_FAIL("shock_capture called without shock_cap");
+    const int det_field = c->prm.shock_det_field == 0 ? 0 : nd + 1;
+    const size_t smem = sizeof(double) * (size_t)e.n_upts * (1 + nfl);
+    k_shock_capture<<<e.n_eles, 128, smem, c->stream>>>(e.n_upts, e.n_eles, nfl, det_field, c->prm.s0, e.disu_upts[0], e.inv_vandermonde, e.sensor_w_top,
+                                                       e.sensor_w_all, e.exp_filter, e.sensor);
+    HF_LAUNCH_CHECK(c);
+    c->ufpts_valid = false;
+    return 0;
+  }
   default:
     HF_FAIL("unknown element operation");
   }
@@ -1044,7 +1141,7 @@ static int staged_residual(hf_ctx *c, double time)
   EACH_ELE(HF_EXTRAPOLATE_SOLUTION);
   if (par) EACH_MPI(2);
   if (visc) EACH_ELE(HF_CALCULATE_GRADIENT);
-  EACH_ELE(HF_EVALUATE_INVFLUX);
+  EACH_ELE(c->prm.over_int ? HF_EVALUATE_INVFLUX_OVER_INT : HF_EVALUATE_INVFLUX);
   EACH_INT(HF_COMMON_INVFLUX);
   EACH_BDY(HF_COMMON_INVFLUX);
   if (par) { EACH_MPI(3); EACH_MPI(HF_COMMON_INVFLUX); }
@@ -1125,9 +1222,20 @@ int hf_dev_advance_solution(hf_ctx *c, int rk_stage)
 int hf_dev_rk_stage(hf_ctx *c, int rk_stage, double time, int keep_residual)
 {
   if (!c->finalized) HF_FAIL("hf_dev_finalize_setup has not been called");
-  if (c->fused && hf_fused_available(c)) return hf_fused_stage(c, rk_stage, time, keep_residual, 1);
-  if (staged_residual(c, time)) return 1;
-  return hf_dev_advance_solution(c, rk_stage);
+  if (c->fused && hf_fused_available(c))
+  {
+    if (hf_fused_stage(c, rk_stage, time, keep_residual, 1)) return 1;
+  }
+  else
+  {
+    if (staged_residual(c, time)) return 1;
+    if (hf_dev_advance_solution(c, rk_stage)) return 1;
+  }
+  // shock capturing follows the update of every stage (reference src/HiFiLES.cpp:213-217)
+  if (c->prm.shock_cap)
+    for (int t = 0; t < HF_N_ELE_TYPES; t++)
+      if (c->eles[t].present && hf_dev_eles_op(c, t, HF_SHOCK_CAPTURE)) return 1;
+  return 0;
 }
 
 int hf_dev_run_steps(hf_ctx *c, int n_steps, double time0)
@@ -1198,6 +1306,7 @@ static int locate_array(hf_ctx *c, hf_eles_dev &e, int which, double **p, size_t
   case HF_GRAD_DISU_FPTS: *p = e.grad_disu_fpts; *n = NFP * F * D; break;
   case HF_SRC_UPTS: *p = nullptr; *n = NU * F; break;
   case HF_DT_LOCAL: *p = e.dt_local; *n = e.n_eles; break;
+  case HF_SENSOR: *p = e.sensor; *n = e.n_eles; break;
   default: HF_FAIL("unknown array id");
   }
   (void)c;

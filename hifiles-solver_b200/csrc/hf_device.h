@@ -47,6 +47,12 @@ struct hf_eles_dev
   int n_fpts_per_inter[6] = {0, 0, 0, 0, 0, 0};
   int fpt_offset[7] = {0, 0, 0, 0, 0, 0, 0};
   hf_ell opp_0, opp_1[3], opp_2[3], opp_3, opp_4[3], opp_5[3], opp_6;
+  // over-integration
+  int n_cub = 0;
+  hf_ell opp_over_int, over_int_filter;
+  double *JGinv_over_int = nullptr, *u_cub = nullptr, *tdisf_cub = nullptr;
+  // shock capturing (dense, row-major access by mode)
+  double *inv_vandermonde = nullptr, *exp_filter = nullptr, *sensor_w_top = nullptr, *sensor_w_all = nullptr, *sensor = nullptr;
   double *detjac_upts = nullptr, *JGinv_upts = nullptr, *detjac_fpts = nullptr, *JGinv_fpts = nullptr;
   double *tdA_fpts = nullptr, *norm_fpts = nullptr, *h_ref = nullptr, *dt_local = nullptr;
   double *disu_upts[2] = {nullptr, nullptr};

@@ -39,6 +39,8 @@ int main(int argc, char *argv[])
       {
         CalcResidual(FlowSol.ini_iter + i_steps, i, &FlowSol);
         for (int j = 0; j < FlowSol.n_ele_types; j++) FlowSol.mesh_eles(j)->AdvanceSolution(i, run_input.adv_type);
+        if (run_input.shock_cap)
+          for (int j = 0; j < FlowSol.n_ele_types; j++) FlowSol.mesh_eles(j)->shock_capture();
       }
       FlowSol.time += run_input.dt;
       run_input.time = FlowSol.time;

@@ -93,6 +93,8 @@ int hifiles_advance_solution(void *handle, int rk_stage)
   return guard([&]() {
     solution *S = &((run_handle *)handle)->FlowSol;
     for (int j = 0; j < S->n_ele_types; j++) S->mesh_eles(j)->AdvanceSolution(rk_stage, run_input.adv_type);
+    if (run_input.shock_cap)
+      for (int j = 0; j < S->n_ele_types; j++) S->mesh_eles(j)->shock_capture();
   });
 }
 
@@ -114,6 +116,8 @@ int hifiles_run(void *handle, int n_steps, int fused)
       {
         CalcResidual(S->ini_iter + it, i, S);
         for (int j = 0; j < S->n_ele_types; j++) S->mesh_eles(j)->AdvanceSolution(i, run_input.adv_type);
+        if (run_input.shock_cap)
+          for (int j = 0; j < S->n_ele_types; j++) S->mesh_eles(j)->shock_capture();
       }
       S->time += run_input.dt;
       run_input.time = S->time;
@@ -249,6 +253,10 @@ int hifiles_get_array(void *handle, const char *name, const void **ptr, int *dty
         if (arr == "opp_4_" + sd) return set_d(e->opp_4(d));
         if (arr == "opp_5_" + sd) return set_d(e->opp_5(d));
       }
+      if (arr == "opp_over_int_cubpts") return set_d(e->opp_over_int_cubpts);
+      if (arr == "over_int_filter") return set_d(e->over_int_filter);
+      if (arr == "JGinv_over_int_cubpts") return set_d(e->JGinv_over_int_cubpts);
+      if (arr == "exp_filter") return set_d(e->exp_filter);
       if (arr == "shape") return set_d(e->shape);
       if (arr == "n_spts_per_ele") return set_i(e->n_spts_per_ele);
       if (arr == "ele2global_ele") return set_i(e->ele2global_ele);

@@ -34,6 +34,8 @@ void eles::setup(int in_n_eles, int in_max_n_spts_per_ele)
   order = run_input.order;
   viscous = run_input.viscous;
   setup_ele_type_specific();
+  if (run_input.over_int) set_over_int();
+  if (run_input.shock_cap) set_shock_capture();
 
   if (run_input.adv_type == 0) n_adv_levels = 1;
   else if (run_input.adv_type >= 1 && run_input.adv_type <= 4) n_adv_levels = 2;
@@ -349,6 +351,7 @@ void eles::set_transforms()
 {
   if (n_eles == 0) return;
   set_transforms_upts();
+  if (run_input.over_int) set_transforms_over_int_cubpts();
   set_transforms_fpts();
 }
 
@@ -549,6 +552,20 @@ void eles::mv_all_cpu_gpu()
   d.norm_fpts = norm_fpts.get_ptr_cpu();
   d.h_ref = (run_input.dt_type > 0) ? h_ref.get_ptr_cpu() : nullptr;
   d.disu_upts0 = disu_upts(0).get_ptr_cpu();
+  if (run_input.over_int)
+  {
+    d.n_over_int_cubpts = loc_over_int_cubpts.get_dim(1);
+    d.opp_over_int_cubpts = opp_over_int_cubpts.get_ptr_cpu();
+    d.over_int_filter = over_int_filter.get_ptr_cpu();
+    d.JGinv_over_int_cubpts = JGinv_over_int_cubpts.get_ptr_cpu();
+  }
+  if (run_input.shock_cap)
+  {
+    d.inv_vandermonde = modal_inv_vandermonde.get_ptr_cpu();
+    d.sensor_w_top = sensor_w_top.get_ptr_cpu();
+    d.sensor_w_all = sensor_w_all.get_ptr_cpu();
+    d.exp_filter = exp_filter.get_ptr_cpu();
+  }
   hf_check(hf_dev_upload_eles(ctx, &d));
 }
 
@@ -582,6 +599,9 @@ void eles::cp_array_gpu_cpu(int which, hf_array<double> &dst)
 void eles::extrapolate_solution() { if (n_eles) hf_check(hf_dev_eles_op(ctx, ele_type, HF_EXTRAPOLATE_SOLUTION)); }
 void eles::calculate_gradient() { if (n_eles) hf_check(hf_dev_eles_op(ctx, ele_type, HF_CALCULATE_GRADIENT)); }
 void eles::evaluate_invFlux() { if (n_eles) hf_check(hf_dev_eles_op(ctx, ele_type, HF_EVALUATE_INVFLUX)); }
+void eles::evaluate_invFlux_over_int() { if (n_eles) hf_check(hf_dev_eles_op(ctx, ele_type, HF_EVALUATE_INVFLUX_OVER_INT)); }
+void eles::shock_capture() { if (n_eles) hf_check(hf_dev_eles_op(ctx, ele_type, HF_SHOCK_CAPTURE)); }
+void eles::cp_sensor_gpu_cpu() { if (n_eles && run_input.shock_cap) hf_check(hf_dev_download(ctx, ele_type, HF_SENSOR, sensor.get_ptr_cpu(), sensor.size())); }
 void eles::correct_gradient() { if (n_eles) hf_check(hf_dev_eles_op(ctx, ele_type, HF_CORRECT_GRADIENT)); }
 void eles::evaluate_viscFlux() { if (n_eles) hf_check(hf_dev_eles_op(ctx, ele_type, HF_EVALUATE_VISCFLUX)); }
 void eles::extrapolate_totalFlux() { if (n_eles) hf_check(hf_dev_eles_op(ctx, ele_type, HF_EXTRAPOLATE_TOTALFLUX)); }

@@ -259,6 +259,9 @@ public:
   void extrapolate_solution();
   void calculate_gradient();
   void evaluate_invFlux();
+  void evaluate_invFlux_over_int();
+  void shock_capture();
+  void cp_sensor_gpu_cpu();
   void correct_gradient();
   void evaluate_viscFlux();
   void extrapolate_totalFlux();
@@ -292,6 +295,17 @@ public:
   void set_opp_6(int in_sparse);
 
   void set_transforms();
+  // modal bases, over-integration, shock capturing (host/eles_modal.cpp)
+  struct modal_mode { int i, j, k; };
+  void set_modes();
+  double eval_modal_basis(int m, hf_array<double> &loc);
+  double modal_norm(int m);
+  bool mode_is_top(int m);
+  void set_modal_vandermonde();
+  void set_volume_cubpts(int in_order, hf_array<double> &locs, hf_array<double> &weights);
+  void set_over_int();
+  void set_transforms_over_int_cubpts();
+  void set_shock_capture();
   void set_transforms_upts();
   void set_transforms_fpts();
   void calc_pos(hf_array<double> &in_loc, int in_ele, hf_array<double> &out_pos);
@@ -321,6 +335,10 @@ public:
   hf_array<double> detjac_upts, JGinv_upts, detjac_fpts, JGinv_fpts, tdA_fpts, norm_fpts, pos_upts, pos_fpts, h_ref;
   hf_array<hf_array<double>> disu_upts, div_tconf_upts;
   hf_array<double> src_upts, grad_disu_upts, dt_local;
+  std::vector<modal_mode> modes;
+  hf_array<double> modal_vandermonde, modal_inv_vandermonde;
+  hf_array<double> loc_over_int_cubpts, weight_over_int_cubpts, opp_over_int_cubpts, over_int_filter, JGinv_over_int_cubpts;
+  hf_array<double> sensor_w_top, sensor_w_all, exp_filter, sensor;
 };
 
 class eles_hexas : public eles

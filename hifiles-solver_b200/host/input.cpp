@@ -539,8 +539,7 @@ void input::setup_params(int rank)
   }
   if (RANS) FatalError("RANS (Spalart-Allmaras) is outside the hot-path scope of this build (SURVEY.md §2 #12)");
   if (LES) FatalError("LES sub-grid models are outside the hot-path scope of this build (SURVEY.md §8f rank 3)");
-  if (over_int) FatalError("over-integration is outside the hot-path scope of this build (SURVEY.md §8f rank 3)");
-  if (shock_cap) FatalError("shock capturing is outside the hot-path scope of this build (SURVEY.md §8f rank 3)");
+  if (over_int && over_int_order < 0) FatalError("Invalid under sampling order");
   if (riemann_solve_type < 0 || riemann_solve_type > 3) FatalError("Riemann solver not implemented");
 
   set_rk_coeff(*this);

@@ -46,6 +46,10 @@ static void upload_params(struct solution *FlowSol)
   p.n_rk = get_n_rk_steps(run_input.adv_type);
   for (int i = 0; i < run_input.RK_a.get_dim(0) && i < HF_MAX_RK; i++) p.RK_a[i] = run_input.RK_a(i);
   for (int i = 0; i < run_input.RK_b.get_dim(0) && i < HF_MAX_RK; i++) p.RK_b[i] = run_input.RK_b(i);
+  p.over_int = run_input.over_int;
+  p.shock_cap = run_input.shock_cap;
+  p.shock_det_field = run_input.shock_det_field;
+  p.s0 = run_input.s0;
   hf_check(hf_dev_set_params(FlowSol->ctx, &p));
 
   vector<hf_bc> table(run_input.bc_list.size());
@@ -100,7 +104,8 @@ void CalcResidual(int in_file_num, int in_rk_stage, struct solution *FlowSol)
     for (int i = 0; i < FlowSol->n_mpi_inter_types; i++) FlowSol->mesh_mpi_inters[i].send_solution();
   if (run_input.viscous)
     for (int i = 0; i < n; i++) FlowSol->mesh_eles(i)->calculate_gradient();
-  for (int i = 0; i < n; i++) FlowSol->mesh_eles(i)->evaluate_invFlux();
+  if (run_input.over_int) for (int i = 0; i < n; i++) FlowSol->mesh_eles(i)->evaluate_invFlux_over_int();
+  else for (int i = 0; i < n; i++) FlowSol->mesh_eles(i)->evaluate_invFlux();
   for (int i = 0; i < FlowSol->n_int_inter_types; i++) FlowSol->mesh_int_inters[i].calculate_common_invFlux();
   for (int i = 0; i < FlowSol->n_bdy_inter_types; i++) FlowSol->mesh_bdy_inters[i].evaluate_boundaryConditions_invFlux(FlowSol, FlowSol->time);
   if (FlowSol->nproc > 1)

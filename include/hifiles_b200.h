@@ -48,6 +48,11 @@ typedef struct hf_params
   double wave_speed[3], diff_coeff, lambda;
   int n_rk;
   double RK_a[HF_MAX_RK], RK_b[HF_MAX_RK];
+  /* de-aliasing and shock capturing (reference src/input.cpp:248-262) */
+  int over_int;               /* 1: inviscid flux through over-integration (eles::evaluate_invFlux_over_int) */
+  int shock_cap;              /* 1: Persson sensor + exponential modal filter after every RK stage (eles::shock_capture) */
+  int shock_det_field;        /* 0 density, 1 total energy */
+  double s0;                  /* sensor threshold */
 } hf_params;
 
 /* One element type (mirror of class eles, reference include/eles.h; storage src/eles.cpp:100-213). */
@@ -72,6 +77,16 @@ typedef struct hf_eles_desc
   const double *norm_fpts;   /* (fpt,ele,dim) */
   const double *h_ref;       /* (ele) or NULL; only for dt_type != 0 */
   const double *disu_upts0;  /* (upt,ele,field) initial solution, or NULL (zero) */
+  /* over-integration (reference src/eles.cpp:1480-1545, <type>::set_over_int, eles::set_transforms_over_int_cubtps); NULL / 0 when off */
+  int n_over_int_cubpts;
+  const double *opp_over_int_cubpts;   /* [n_cubpts x n_upts] interpolation to the cubature points */
+  const double *over_int_filter;       /* [n_upts x n_cubpts] L2 projection back onto the solution basis */
+  const double *JGinv_over_int_cubpts; /* (l,m,cubpt,ele) */
+  /* shock capturing (reference src/eles.cpp:2918-2959, <type>::shock_det_persson / set_exp_filter); NULL when off */
+  const double *inv_vandermonde;       /* [n_upts x n_upts] nodal -> modal */
+  const double *sensor_w_top;          /* [n_upts] squared norm of the modes of the highest-degree shell, 0 elsewhere */
+  const double *sensor_w_all;          /* [n_upts] squared norm of every mode */
+  const double *exp_filter;            /* [n_upts x n_upts] */
 } hf_eles_desc;
 
 /* Interior interfaces of one face type (mirror of int_inters::set_interior, reference src/int_inters.cpp:67-121).
@@ -118,7 +133,7 @@ enum hf_array_id
 {
   HF_DISU_UPTS0 = 0, HF_DISU_UPTS1 = 1, HF_DIV_TCONF_UPTS = 2, HF_DISU_FPTS = 3, HF_TDISF_UPTS = 4,
   HF_NORM_TDISF_FPTS = 5, HF_NORM_TCONF_FPTS = 6, HF_DELTA_DISU_FPTS = 7, HF_GRAD_DISU_UPTS = 8,
-  HF_GRAD_DISU_FPTS = 9, HF_SRC_UPTS = 10, HF_DT_LOCAL = 11
+  HF_GRAD_DISU_FPTS = 9, HF_SRC_UPTS = 10, HF_DT_LOCAL = 11, HF_SENSOR = 12 /* (ele) Persson sensor of the last shock_capture */
 };
 
 /* element operations = the eles methods CalcResidual calls (reference src/solver.cpp:65-216) */
@@ -131,7 +146,9 @@ enum hf_eles_op
   HF_EVALUATE_VISCFLUX = 4,          /* eles::evaluate_viscFlux             reference src/eles.cpp:2285 */
   HF_EXTRAPOLATE_TOTALFLUX = 5,      /* eles::extrapolate_totalFlux         reference src/eles.cpp:1549 */
   HF_CALCULATE_DIVERGENCE = 6,       /* eles::calculate_divergence          reference src/eles.cpp:1651 */
-  HF_CALCULATE_CORRECTED_DIVERGENCE = 7 /* eles::calculate_corrected_divergence reference src/eles.cpp:1738 */
+  HF_CALCULATE_CORRECTED_DIVERGENCE = 7, /* eles::calculate_corrected_divergence reference src/eles.cpp:1738 */
+  HF_EVALUATE_INVFLUX_OVER_INT = 8,  /* eles::evaluate_invFlux_over_int     reference src/eles.cpp:1480 */
+  HF_SHOCK_CAPTURE = 9               /* eles::shock_capture                 reference src/eles.cpp:2918 */
 };
 enum hf_inters_op
 {

@@ -163,6 +163,13 @@ static void dump_setup(struct solution *S)
     put(p + "pos_upts", e->pos_upts);
     put(p + "pos_fpts", e->pos_fpts);
     put(p + "disu_upts_ic", e->disu_upts(0));
+    if (run_input.over_int)
+    {
+      put(p + "opp_over_int_cubpts", e->opp_over_int_cubpts);
+      put(p + "over_int_filter", e->over_int_filter);
+      put(p + "JGinv_over_int_cubpts", e->JGinv_over_int_cubpts);
+    }
+    if (run_input.shock_cap) put(p + "exp_filter", e->exp_filter);
   }
   const char *iname[3] = {"seg", "tri", "quad"};
   for (int t = 0; t < S->n_int_inter_types; t++)
@@ -221,6 +228,7 @@ static void dump_state(struct solution *S, const string &tag, bool all)
     string p = tag + "." + tname[t] + ".";
     put(p + "disu_upts", e->disu_upts(0));
     put(p + "div_tconf_upts", e->div_tconf_upts(0));
+    if (run_input.shock_cap) put(p + "sensor", e->sensor);
     if (all)
     {
       put(p + "disu_fpts", e->disu_fpts);

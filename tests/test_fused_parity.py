@@ -9,7 +9,8 @@ import pytest
 import util
 from test_staged_parity import CASES, make_case, check
 
-FUSED_CASES = ["hex_p2_ns_hllc_rk34", "hex_p3_ns_rusanov_rk45", "hex_p2_euler_roem_rk24", "hex_p1_ns_sutherland_euler", "hex_p4_ns_hllc_rk34"]
+FUSED_CASES = ["hex_p2_ns_hllc_rk34", "hex_p3_ns_rusanov_rk45", "hex_p2_euler_roem_rk24", "hex_p1_ns_sutherland_euler", "hex_p4_ns_hllc_rk34",
+               "hex_p2_euler_hllc_shockcap"]  # the last one: fused stages + the shock-capturing kernel after each of them
 TOL = 1e-12
 
 

@@ -68,6 +68,22 @@ CASES = {
     "pri_p3_ns_roem_rk45": ("pri", 2, {}, dict(order=3, adv_type=3, riemann_solve_type=2, viscous=1, dt=1e-5)),
     "hexpri_p2_ns_roem_rk34": ("hexpri", (2, 2, 4), {}, dict(order=2, adv_type=2, riemann_solve_type=2, viscous=1, dt=2e-5)),
     "pritet_p3_ns_roem_rk34": ("pritet", (2, 4, 2), {}, dict(order=3, adv_type=2, riemann_solve_type=2, viscous=1, dt=1e-5)),
+    # polynomial de-aliasing by over-integration (eles::evaluate_invFlux_over_int, reference src/eles.cpp:1480-1545): BASELINE config 4
+    "hex_p3_ns_roem_overint": ("hex", 3, dict(warp=0.1), dict(order=3, adv_type=2, riemann_solve_type=2, viscous=1, dt=1e-5, over_int=1, over_int_order=5)),
+    "hexpri_p2_ns_roem_overint": ("hexpri", (2, 2, 4), {}, dict(order=2, adv_type=2, riemann_solve_type=2, viscous=1, dt=2e-5, over_int=1, over_int_order=4)),
+    "pritet_p2_ns_roem_overint": ("pritet", (2, 4, 2), {}, dict(order=2, adv_type=3, riemann_solve_type=2, viscous=1, dt=1e-5, over_int=1, over_int_order=4)),
+    "mixed_tri_quad_p3_euler_overint": ("mixed", 6, {}, dict(order=3, adv_type=3, riemann_solve_type=0, viscous=0, ic_form=0, test_case=1, dt=1e-3,
+                                                            dx_cyclic=20., dy_cyclic=20., dz_cyclic=None, over_int=1, over_int_order=5, **EULER_IC)),
+    # Persson sensor + exponential modal filter after every stage (eles::shock_capture, reference src/eles.cpp:2918-2959): BASELINE config 5;
+    # s0 is set inside the range of the sensor values of these smooth fields so that some elements are filtered and some are not
+    "mixed_tri_quad_p3_euler_shockcap": ("mixed", 6, {}, dict(order=3, adv_type=3, riemann_solve_type=3, viscous=0, ic_form=0, test_case=1, dt=1e-3,
+                                                             dx_cyclic=20., dy_cyclic=20., dz_cyclic=None, shock_cap=1, s0=1e-7, expf_cutoff=1, **EULER_IC)),
+    "hex_p2_euler_hllc_shockcap": ("hex", 4, dict(lengths=(20.,) * 3, origin=(-10.,) * 3),
+                                   dict(order=2, adv_type=2, riemann_solve_type=3, viscous=0, dt=1e-3, ic_form=0, test_case=1, dx_cyclic=20.,
+                                        dy_cyclic=20., dz_cyclic=20., shock_cap=1, s0=1e-7, **EULER_IC)),
+    "hexpri_p2_ns_hllc_shockcap": ("hexpri", (2, 2, 4), {}, dict(order=2, adv_type=2, riemann_solve_type=3, viscous=1, dt=2e-5, shock_cap=1, s0=5e-6,
+                                                              shock_det_field=1)),
+    "pritet_p2_ns_hllc_shockcap": ("pritet", (2, 4, 2), {}, dict(order=2, adv_type=2, riemann_solve_type=3, viscous=1, dt=1e-5, shock_cap=1, s0=1.5e-6)),
 }
 
 
@@ -124,7 +140,7 @@ def test_methods_one_by_one(tmp_path, hb, meshgen, name):
         each("extrapolate_solution", "disu_fpts", "s02_extrapolate_solution")
         if visc:
             each("calculate_gradient", "grad_disu_upts", "s04_calculate_gradient")
-        each("evaluate_invFlux", "tdisf_upts", "s05_evaluate_invFlux")
+        each("evaluate_invFlux_over_int" if CASES[name][3].get("over_int") else "evaluate_invFlux", "tdisf_upts", "s05_evaluate_invFlux")
         for it in range(3):
             run.int_inters_op(it, 0)
         for it in range(3):
@@ -151,9 +167,18 @@ def test_methods_one_by_one(tmp_path, hb, meshgen, name):
             for t in types:
                 check("norm_tconf_fpts visc " + t, run.download(t, "norm_tconf_fpts"), ref[pre + "s17_common_viscFlux." + t + ".norm_tconf_fpts"])
         each("calculate_corrected_divergence", "div_tconf_upts", "s18_corrected_divergence")
-        run.advance_solution(0)
+        run.advance_solution(0)  # AdvanceSolution, then shock_capture when it is on (reference src/HiFiLES.cpp:209-217)
         for t in types:
             check("advanced " + t, run.download(t, "disu_upts"), ref["step0.stage0.advanced." + t + ".disu_upts"])
+        if CASES[name][3].get("shock_cap"):
+            flagged = total = 0
+            for t in types:
+                sensor, want = run.download(t, "sensor"), ref["step0.stage0.advanced." + t + ".sensor"]
+                check("sensor " + t, sensor, want, 1e-11)
+                assert np.array_equal(sensor >= CASES[name][3]["s0"], want >= CASES[name][3]["s0"])
+                flagged += int((want >= CASES[name][3]["s0"]).sum())
+                total += want.size
+            assert 0 < flagged < total, "the case must filter some elements and leave others alone (%d of %d)" % (flagged, total)
 
 
 @pytest.mark.gpu
