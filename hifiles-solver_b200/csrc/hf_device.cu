@@ -695,7 +695,65 @@ int hf_dev_set_params(hf_ctx *c, const hf_params *p)
   return 0;
 }
 
+// Device element order (hf_dev_set_element_order): arrays are (points, element, rest); slot pos[e] holds host element e.
+static std::vector<double> permute_eles(const double *src, size_t pre, int n_eles, size_t post, const std::vector<int> &pos, bool to_device)
+{
+  std::vector<double> out(pre * n_eles * post);
+  for (size_t b = 0; b < post; b++)
+    for (int e = 0; e < n_eles; e++)
+    {
+      const size_t host_off = pre * (e + (size_t)n_eles * b), dev_off = pre * (pos[e] + (size_t)n_eles * b);
+      if (to_device) memcpy(&out[dev_off], src + host_off, pre * sizeof(double));
+      else memcpy(&out[host_off], src + dev_off, pre * sizeof(double));
+    }
+  return out;
+}
+
+int hf_dev_set_element_order(hf_ctx *c, int ele_type, int n_eles, const int *pos)
+{
+  if (ele_type < 0 || ele_type >= HF_N_ELE_TYPES) HF_FAIL("bad element type");
+  hf_eles_dev &e = c->eles[ele_type];
+  if (e.present) HF_FAIL("hf_dev_set_element_order must precede hf_dev_upload_eles");
+  std::vector<char> seen(n_eles, 0);
+  for (int i = 0; i < n_eles; i++)
+  {
+    if (pos[i] < 0 || pos[i] >= n_eles || seen[pos[i]]) HF_FAIL("element order is not a permutation");
+    seen[pos[i]] = 1;
+  }
+  e.pos.assign(pos, pos + n_eles);
+  return 0;
+}
+
+static int upload_eles_impl(hf_ctx *c, const hf_eles_desc *d);
+
 int hf_dev_upload_eles(hf_ctx *c, const hf_eles_desc *d)
+{
+  if (d->ele_type < 0 || d->ele_type >= HF_N_ELE_TYPES) HF_FAIL("bad element type");
+  hf_eles_dev &e = c->eles[d->ele_type];
+  if (e.pos.empty()) return upload_eles_impl(c, d);
+  if ((int)e.pos.size() != d->n_eles) HF_FAIL("element order has the wrong length");
+  // permuted host copies of every per-element array, then the ordinary upload
+  hf_eles_desc q = *d;
+  const int ne = d->n_eles, nu = d->n_upts_per_ele, nf = d->n_fpts_per_ele, nd = d->n_dims;
+  std::vector<std::vector<double>> keep;
+  auto perm = [&](const double *&ptr, size_t pre, size_t post) {
+    if (!ptr) return;
+    keep.push_back(permute_eles(ptr, pre, ne, post, e.pos, true));
+    ptr = keep.back().data();
+  };
+  perm(q.detjac_upts, nu, 1);
+  perm(q.JGinv_upts, (size_t)nd * nd * nu, 1);
+  perm(q.detjac_fpts, nf, 1);
+  perm(q.JGinv_fpts, (size_t)nd * nd * nf, 1);
+  perm(q.tdA_fpts, nf, 1);
+  perm(q.norm_fpts, nf, nd);
+  perm(q.h_ref, 1, 1);
+  perm(q.disu_upts0, nu, d->n_fields);
+  perm(q.JGinv_over_int_cubpts, (size_t)nd * nd * d->n_over_int_cubpts, 1);
+  return upload_eles_impl(c, &q);
+}
+
+static int upload_eles_impl(hf_ctx *c, const hf_eles_desc *d)
 {
   if (!c->have_params) HF_FAIL("hf_dev_set_params must be called before hf_dev_upload_eles");
   if (d->ele_type < 0 || d->ele_type >= HF_N_ELE_TYPES) HF_FAIL("bad element type");
@@ -789,7 +847,8 @@ static int ensure_staged_buffers(hf_ctx *c, hf_eles_dev &e)
 }
 
 // flat flux-point index (fpt + n_fpts*ele) of face-local point j on local face `loc` of element `ele`
-static inline int flat_fpt(const hf_eles_dev &e, int ele, int loc, int j) { return e.fpt_offset[loc] + j + e.n_fpts * ele; }
+static inline int dev_ele(const hf_eles_dev &e, int ele) { return e.pos.empty() ? ele : e.pos[ele]; }
+static inline int flat_fpt(const hf_eles_dev &e, int ele, int loc, int j) { return e.fpt_offset[loc] + j + e.n_fpts * dev_ele(e, ele); }
 
 // right-side permutation (reference src/inters.cpp:153-262)
 static int fill_lut(int inter_type, int order, int nfp, int rot, std::vector<int> &lut)
@@ -853,8 +912,10 @@ int hf_dev_upload_int_inters(hf_ctx *c, const hf_int_inters_desc *d)
   if (hf_alloc_copy(c, &I.type_l, tl.data(), tl.size())) return 1;
   if (hf_alloc_copy(c, &I.type_r, tr.data(), tr.size())) return 1;
   I.h_ele_type_l.assign(d->ele_type_l, d->ele_type_l + ni); I.h_ele_l.assign(d->ele_l, d->ele_l + ni);
+  for (int i = 0; i < ni; i++) I.h_ele_l[i] = dev_ele(c->eles[I.h_ele_type_l[i]], I.h_ele_l[i]);
   I.h_loc_l.assign(d->local_inter_l, d->local_inter_l + ni);
   I.h_ele_type_r.assign(d->ele_type_r, d->ele_type_r + ni); I.h_ele_r.assign(d->ele_r, d->ele_r + ni);
+  for (int i = 0; i < ni; i++) I.h_ele_r[i] = dev_ele(c->eles[I.h_ele_type_r[i]], I.h_ele_r[i]);
   I.h_loc_r.assign(d->local_inter_r, d->local_inter_r + ni);
   I.h_rot.assign(d->rot_tag, d->rot_tag + ni);
   return 0;
@@ -889,6 +950,7 @@ int hf_dev_upload_bdy_inters(hf_ctx *c, const hf_bdy_inters_desc *d)
   if (hf_alloc_copy(c, &I.type_l, tl.data(), tl.size())) return 1;
   if (hf_alloc_copy(c, &I.bc_id, d->bc_id, (size_t)ni)) return 1;
   I.h_ele_type_l.assign(d->ele_type_l, d->ele_type_l + ni); I.h_ele_l.assign(d->ele_l, d->ele_l + ni);
+  for (int i = 0; i < ni; i++) I.h_ele_l[i] = dev_ele(c->eles[I.h_ele_type_l[i]], I.h_ele_l[i]);
   I.h_loc_l.assign(d->local_inter_l, d->local_inter_l + ni);
   I.h_bc_id.assign(d->bc_id, d->bc_id + ni);
   return 0;
@@ -929,6 +991,7 @@ int hf_dev_upload_mpi_inters(hf_ctx *c, const hf_mpi_inters_desc *d)
     if (hf_alloc_zero(c, &I.in_grad, nb * nd)) return 1;
   }
   I.h_ele_type_l.assign(d->ele_type_l, d->ele_type_l + ni); I.h_ele_l.assign(d->ele_l, d->ele_l + ni);
+  for (int i = 0; i < ni; i++) I.h_ele_l[i] = dev_ele(c->eles[I.h_ele_type_l[i]], I.h_ele_l[i]);
   I.h_loc_l.assign(d->local_inter_l, d->local_inter_l + ni);
   I.h_rot.assign(d->rot_tag, d->rot_tag + ni);
   return 0;
@@ -1313,6 +1376,16 @@ static int locate_array(hf_ctx *c, hf_eles_dev &e, int which, double **p, size_t
   return 0;
 }
 
+static size_t pts_per_ele(const hf_eles_dev &e, int which)
+{
+  switch (which)
+  {
+  case HF_DISU_FPTS: case HF_NORM_TDISF_FPTS: case HF_NORM_TCONF_FPTS: case HF_DELTA_DISU_FPTS: case HF_GRAD_DISU_FPTS: return e.n_fpts;
+  case HF_DT_LOCAL: case HF_SENSOR: return 1;
+  default: return e.n_upts;
+  }
+}
+
 int hf_dev_download(hf_ctx *c, int ele_type, int which, double *host, size_t n_doubles)
 {
   HF_CUDA(cudaSetDevice(c->device));
@@ -1328,6 +1401,12 @@ int hf_dev_download(hf_ctx *c, int ele_type, int which, double *host, size_t n_d
       op_apply(c, ell1(e.opp_0), e.disu_upts[0], 0, e.disu_fpts, (long long)e.n_eles * e.n_fields, false)) return 1;
   HF_CUDA(cudaMemcpyAsync(host, p, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
   HF_CUDA(cudaStreamSynchronize(c->stream));
+  if (!e.pos.empty())
+  {
+    const size_t pre = pts_per_ele(e, which);
+    std::vector<double> t = permute_eles(host, pre, e.n_eles, n / (pre * e.n_eles), e.pos, false);
+    memcpy(host, t.data(), n * sizeof(double));
+  }
   return 0;
 }
 
@@ -1343,6 +1422,13 @@ int hf_dev_upload(hf_ctx *c, int ele_type, int which, const double *host, size_t
   {
     if (ensure_staged_buffers(c, e) || locate_array(c, e, which, &p, &n)) return 1;
     if (!p) HF_FAIL("upload: array is not materialised on the device");
+  }
+  std::vector<double> t;
+  if (!e.pos.empty())
+  {
+    const size_t pre = pts_per_ele(e, which);
+    t = permute_eles(host, pre, e.n_eles, n / (pre * e.n_eles), e.pos, true);
+    host = t.data();
   }
   HF_CUDA(cudaMemcpyAsync(p, host, n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
   HF_CUDA(cudaStreamSynchronize(c->stream));

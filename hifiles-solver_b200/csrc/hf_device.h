@@ -73,6 +73,7 @@ struct hf_eles_dev
   std::vector<double> h_face_geo;  // per (ele, face): tdA, unit normal[3] at the face's first flux point
   std::vector<int8_t> h_own_sign;  // (fpt,ele): sign of ldg_beta if this element is the left side of the face
   double affine_defect = 0.;       // max relative variation of the metrics inside an element
+  std::vector<int> pos;            // device element order: slot pos[e] holds host element e (empty = identity), hf_dev_set_element_order
 };
 
 struct hf_int_inters_dev

@@ -340,6 +340,7 @@ struct hf_fused_state
   int *nidx = nullptr;    // [ele][NFP] neighbour value index into fu
   int *elist = nullptr;   // interior elements (ascending), then elements with a partition face (ascending)
   int n_interior = 0;
+  bool elist_identity = false;
   double *out_u = nullptr, *out_g = nullptr;
   int E = 2, NT = 128;
 };
@@ -592,6 +593,8 @@ int hf_fused_prepare(hf_ctx *c)
   for (int i = 0; i < ne; i++) if (!is_halo[i]) elist.push_back(i);
   Z->n_interior = (int)elist.size();
   for (int i = 0; i < ne; i++) if (is_halo[i]) elist.push_back(i);
+  Z->elist_identity = true; // true when the device element order already has the interior elements first (hf_dev_set_element_order)
+  for (int i = 0; i < ne; i++) if (elist[i] != i) Z->elist_identity = false;
   Z->order = e.order;
   Z->n_eles = ne;
   const size_t nblk = (size_t)ne * 6 + M.n_inters;
@@ -688,7 +691,8 @@ void base_args(hf_ctx *c, hf_fused_state *Z, fused_args &A)
   hf_eles_dev &e = c->eles[4];
   memset(&A, 0, sizeof(A));
   A.n_eles = e.n_eles;
-  A.elist = Z->n_mpi ? Z->elist : nullptr;
+  static const bool force_elist = getenv("HF_FORCE_ELIST") != nullptr; // measurement aid: the indirect element order on one GPU
+  A.elist = ((Z->n_mpi && !Z->elist_identity) || force_elist) ? Z->elist : nullptr;
   A.u0 = e.disu_upts[0];
   A.u0_out = e.disu_upts[0];
   A.u1 = e.disu_upts[1];

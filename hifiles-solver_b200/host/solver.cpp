@@ -77,6 +77,30 @@ static void upload_all(struct solution *FlowSol)
 {
   upload_params(FlowSol);
   hf_check(hf_dev_set_mode(FlowSol->ctx, run_input.device_fused));
+  // device element order: elements without a partition face first (ascending), the partition-adjacent ones behind them
+  if (FlowSol->nproc > 1)
+  {
+    for (int t = 0; t < FlowSol->n_ele_types; t++)
+    {
+      eles *e = FlowSol->mesh_eles(t);
+      const int ne = e->get_n_eles();
+      if (ne == 0) continue;
+      vector<char> halo(ne, 0);
+      bool any = false;
+      for (int i = 0; i < FlowSol->n_mpi_inter_types; i++)
+      {
+        mpi_inters &M = FlowSol->mesh_mpi_inters[i];
+        for (int q = 0; q < M.get_n_inters(); q++)
+          if (M.ele_type_l(q) == e->get_ele_type()) { halo[M.ele_l(q)] = 1; any = true; }
+      }
+      if (!any) continue;
+      vector<int> pos(ne);
+      int slot = 0;
+      for (int q = 0; q < ne; q++) if (!halo[q]) pos[q] = slot++;
+      for (int q = 0; q < ne; q++) if (halo[q]) pos[q] = slot++;
+      hf_check(hf_dev_set_element_order(FlowSol->ctx, e->get_ele_type(), ne, pos.data()));
+    }
+  }
   for (int i = 0; i < FlowSol->n_ele_types; i++) FlowSol->mesh_eles(i)->mv_all_cpu_gpu();
   for (int i = 0; i < FlowSol->n_int_inter_types; i++) FlowSol->mesh_int_inters[i].mv_all_cpu_gpu();
   for (int i = 0; i < FlowSol->n_bdy_inter_types; i++) FlowSol->mesh_bdy_inters[i].mv_all_cpu_gpu();

@@ -168,6 +168,12 @@ int hf_dev_nccl_init(hf_ctx *ctx, const void *unique_id_128_bytes);
 
 /* ---- setup (replaces eles::mv_all_cpu_gpu, int_inters::mv_all_cpu_gpu, ...) ---------------------------- */
 int hf_dev_set_params(hf_ctx *ctx, const hf_params *p);
+/* Optional, before hf_dev_upload_eles of that type: device storage order of the elements, pos[e] = device slot of host
+ * element e (a permutation).  Every per-element array is stored in that order and hf_dev_upload / hf_dev_download
+ * translate, so the host keeps the reference's numbering (reference src/mesh.cpp:188-311).  The host mirror puts the
+ * elements without a partition face first, so that the fused kernels launch contiguous ranges: interior elements
+ * while the halo exchange is in flight, partition-adjacent ones after it. */
+int hf_dev_set_element_order(hf_ctx *ctx, int ele_type, int n_eles, const int *pos);
 int hf_dev_upload_eles(hf_ctx *ctx, const hf_eles_desc *d);
 int hf_dev_upload_int_inters(hf_ctx *ctx, const hf_int_inters_desc *d);
 int hf_dev_set_bc_table(hf_ctx *ctx, int n_bc, const hf_bc *table);
