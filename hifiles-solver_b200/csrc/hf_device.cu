@@ -163,6 +163,182 @@ __global__ void k_point_flux(long long n_pts, const double *__restrict__ u, cons
     }
 }
 
+
+// Sub-grid-scale flux of the eddy-viscosity models at one solution point (eles::calc_sgsf_upts, reference
+// src/eles.cpp:2395-2646; Smagorinsky with wall damping, WALE), same operation order.  sf(k,d) = sf[k + NF*d].
+struct hf_les
+{
+  int sgs_model, order;
+  double C_s, Kappa, prandtl_t, filter_ratio, vol_factor, gamma;
+};
+template <int ND, int NF>
+__device__ __forceinline__ void sgs_flux(const double *u, const double *g, double detjac, const double *wd, const hf_les &Q, double *sf)
+{
+  const double rho = u[0];
+  double v[ND], ke = 0.;
+#pragma unroll
+  for (int i = 0; i < ND; i++)
+  {
+    v[i] = u[i + 1] / rho;
+    ke += 0.5 * (v[i] * v[i]);
+  }
+  const double inte = u[NF - 1] / rho - ke;
+  const double vol = detjac * Q.vol_factor;
+  const double delta = Q.filter_ratio * pow(vol, 1. / ND) / (Q.order + 1.);
+  double drho[ND], dene[ND], dke[ND], de[ND], du[ND][ND], S[ND][ND];
+#pragma unroll
+  for (int i = 0; i < ND; i++) { drho[i] = g[0 + NF * i]; dene[i] = g[(NF - 1) + NF * i]; }
+#pragma unroll
+  for (int i = 0; i < ND; i++)
+  {
+    dke[i] = ke * drho[i];
+#pragma unroll
+    for (int j = 0; j < ND; j++)
+    {
+      du[i][j] = (g[(j + 1) + NF * i] - v[j] * drho[i]) / rho; // du_j/dx_i
+      dke[i] += rho * v[j] * du[i][j];
+    }
+    de[i] = (dene[i] - dke[i] - drho[i] * inte) / rho;
+  }
+#pragma unroll
+  for (int i = 0; i < ND; i++)
+#pragma unroll
+    for (int j = 0; j < ND; j++) S[i][j] = (du[i][j] + du[j][i]) / 2.0;
+  double mu_t;
+  if (Q.sgs_model == 0)
+  {
+    double y = 0.0;
+#pragma unroll
+    for (int i = 0; i < ND; i++) y += wd[i] * wd[i];
+    y = sqrt(y);
+    double Smod = 0.0;
+#pragma unroll
+    for (int i = 0; i < ND; i++)
+#pragma unroll
+      for (int j = 0; j < ND; j++) Smod += 2.0 * S[i][j] * S[i][j];
+    Smod = sqrt(Smod);
+    mu_t = rho * fmin(y * y * Q.Kappa * Q.Kappa, Q.C_s * Q.C_s * delta * delta) * Smod;
+  }
+  else
+  {
+    // WALE: square of the velocity-gradient tensor, symmetrised, trace removed
+    double gbt[ND][ND], Sq[ND][ND];
+#pragma unroll
+    for (int j = 0; j < ND; j++)
+#pragma unroll
+      for (int i = 0; i < ND; i++)
+      {
+        double acc = 0.0;
+#pragma unroll
+        for (int l = 0; l < ND; l++) acc += (1.0 * du[j][l]) * du[l][i]; // column-major product of the (i,j) = du_j/dx_i array with itself
+        gbt[j][i] = acc;
+      }
+    // gbt[j][i] holds element (i,j) of the product; its transpose is g_bar
+    double diag = 0.0;
+#pragma unroll
+    for (int i = 0; i < ND; i++)
+#pragma unroll
+      for (int j = 0; j < ND; j++) Sq[i][j] = (0.0 + 0.5 * gbt[i][j]) + 0.5 * gbt[j][i];
+#pragma unroll
+    for (int i = 0; i < ND; i++) diag += gbt[i][i] / 3.0;
+#pragma unroll
+    for (int i = 0; i < ND; i++) Sq[i][i] -= diag;
+    double num = 0.0, denom = 0.0;
+#pragma unroll
+    for (int i = 0; i < ND; i++)
+#pragma unroll
+      for (int j = 0; j < ND; j++)
+      {
+        num += Sq[i][j] * Sq[i][j];
+        denom += S[i][j] * S[i][j];
+      }
+    denom = pow(denom, 2.5) + pow(num, 1.25);
+    num = pow(num, 1.5);
+    mu_t = rho * Q.C_s * Q.C_s * delta * delta * num / (denom + 1.e-12);
+  }
+  double diag = 0.;
+#pragma unroll
+  for (int i = 0; i < ND; i++) diag += S[i][i] / 3.0;
+#pragma unroll
+  for (int i = 0; i < ND; i++) S[i][i] -= diag;
+#pragma unroll
+  for (int j = 0; j < ND; j++)
+  {
+    sf[0 + NF * j] = 0.0;
+    double e = -1.0 * Q.gamma * mu_t / Q.prandtl_t * de[j];
+#pragma unroll
+    for (int k = 0; k < ND; k++) e -= v[k] * 2.0 * mu_t * S[k][j];
+    sf[(NF - 1) + NF * j] = e;
+#pragma unroll
+    for (int i = 1; i < NF - 1; i++) sf[i + NF * j] = -2.0 * mu_t * S[i - 1][j];
+  }
+}
+
+// eles::evaluate_viscFlux with LES (reference src/eles.cpp:2285-2392): viscous + SGS flux, the transformed SGS flux
+// alone goes to sgsf_upts
+template <int ND, int NF>
+__global__ void k_point_flux_les(long long n_pts, int n_upts, const double *__restrict__ u, const double *__restrict__ grad, const double *__restrict__ JGinv,
+                                 const double *__restrict__ detjac, const double *__restrict__ wall_distance, double *__restrict__ tdisf,
+                                 double *__restrict__ sgsf, hf_phys P, hf_les Q)
+{
+  long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (p >= n_pts) return;
+  double uu[NF], f[NF * ND], sf[NF * ND], g[NF * ND], J[ND * ND], wd[ND];
+#pragma unroll
+  for (int k = 0; k < NF; k++) uu[k] = u[p + k * n_pts];
+#pragma unroll
+  for (int q = 0; q < ND * ND; q++) J[q] = JGinv[p * (ND * ND) + q];
+#pragma unroll
+  for (int q = 0; q < NF * ND; q++) g[q] = grad[p + q * n_pts];
+#pragma unroll
+  for (int d = 0; d < ND; d++) wd[d] = wall_distance ? wall_distance[p + d * n_pts] : 1e20;
+  vis_flux<ND, NF>(uu, g, f, P);
+  sgs_flux<ND, NF>(uu, g, detjac[p], wd, Q, sf);
+#pragma unroll
+  for (int q = 0; q < NF * ND; q++) f[q] = f[q] + 1.0 * sf[q];
+#pragma unroll
+  for (int k = 0; k < NF; k++)
+#pragma unroll
+    for (int l = 0; l < ND; l++)
+    {
+      double s = 0.0, acc = tdisf[p + (k + NF * l) * n_pts];
+#pragma unroll
+      for (int m = 0; m < ND; m++)
+      {
+        s += J[l + ND * m] * sf[k + NF * m];
+        acc += J[l + ND * m] * f[k + NF * m];
+      }
+      sgsf[p + (k + NF * l) * n_pts] = s;
+      tdisf[p + (k + NF * l) * n_pts] = acc;
+    }
+  (void)n_upts;
+}
+
+// transformed SGS flux at the flux points back to physical space: f = (1/detJ) J F (eles::extrapolate_sgsFlux, reference
+// src/eles.cpp:2864-2893)
+template <int ND, int NF>
+__global__ void k_sgsf_physical(long long n_pts, double *__restrict__ sgsf, const double *__restrict__ detjac, const double *__restrict__ Jac)
+{
+  long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (p >= n_pts) return;
+  const double inv_detjac = 1.0 / detjac[p];
+  double J[ND * ND], t[NF * ND];
+#pragma unroll
+  for (int q = 0; q < ND * ND; q++) J[q] = Jac[p * (ND * ND) + q]; // (a,b) = a + ND*b
+#pragma unroll
+  for (int q = 0; q < NF * ND; q++) t[q] = sgsf[p + q * n_pts];
+#pragma unroll
+  for (int k = 0; k < NF; k++)
+#pragma unroll
+    for (int d = 0; d < ND; d++)
+    {
+      double acc = 0.0;
+#pragma unroll
+      for (int m = 0; m < ND; m++) acc += (inv_detjac * t[k + NF * m]) * J[d + ND * m];
+      sgsf[p + (k + NF * d) * n_pts] = acc;
+    }
+}
+
 // reference-space gradient -> physical gradient: g(d,k) = sum_l (1/detJ * gt(l,k)) * JGinv(l,d)
 template <int ND, int NF>
 __global__ void k_transform_grad(long long n_pts, double *__restrict__ grad, const double *__restrict__ detjac, const double *__restrict__ JGinv)
@@ -208,6 +384,13 @@ __device__ __forceinline__ void load_grad_fpt(const hf_ele_view &V, int idx, dou
   size_t s = (size_t)V.n_fpts * V.n_eles;
 #pragma unroll
   for (int q = 0; q < NF * ND; q++) g[q] = V.grad_disu_fpts[idx + q * s];
+}
+template <int ND, int NF>
+__device__ __forceinline__ void add_sgsf_fpt(const hf_ele_view &V, int idx, double *f)
+{
+  size_t s = (size_t)V.n_fpts * V.n_eles;
+#pragma unroll
+  for (int q = 0; q < NF * ND; q++) f[q] += V.sgsf_fpts[idx + q * s];
 }
 template <int ND>
 __device__ __forceinline__ void load_norm(const hf_ele_view &V, int idx, double *n)
@@ -256,7 +439,7 @@ __global__ void k_int_invflux(hf_views W, int n_pairs, int nf, const int *__rest
 
 template <int ND, int NF>
 __global__ void k_int_viscflux(hf_views W, int n_pairs, int nf, const int *__restrict__ idx_l, const int *__restrict__ idx_r,
-                               const int8_t *__restrict__ type_l, const int8_t *__restrict__ type_r, hf_phys P)
+                               const int8_t *__restrict__ type_l, const int8_t *__restrict__ type_r, hf_phys P, int les)
 {
   int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= n_pairs) return;
@@ -271,6 +454,11 @@ __global__ void k_int_viscflux(hf_views W, int n_pairs, int nf, const int *__res
   vis_flux<ND, NF>(u_l, g, f_l, P);
   load_grad_fpt<ND, NF>(R, ir, g);
   vis_flux<ND, NF>(u_r, g, f_r, P);
+  if (les) // physical SGS flux of both sides joins the viscous flux (reference src/int_inters.cpp:297-313)
+  {
+    add_sgsf_fpt<ND, NF>(L, il, f_l);
+    add_sgsf_fpt<ND, NF>(R, ir, f_r);
+  }
   load_norm<ND>(L, il, n);
   double beta = ldg_switched_beta<ND>(P.ldg_beta, n);
   ldg_flux<ND, NF>(0, u_l, u_r, f_l, f_r, n, fn, beta, P.ldg_tau);
@@ -575,6 +763,7 @@ hf_views hf_make_views(hf_ctx *c)
     v.norm_tconf_fpts = e.norm_tconf_fpts;
     v.delta_disu_fpts = e.delta_disu_fpts;
     v.grad_disu_fpts = e.grad_disu_fpts;
+    v.sgsf_fpts = e.sgsf_fpts;
     v.tdA_fpts = e.tdA_fpts;
     v.norm_fpts = e.norm_fpts;
   }
@@ -688,6 +877,8 @@ int hf_dev_set_params(hf_ctx *c, const hf_params *p)
   P.riemann_solve_type = p->riemann_solve_type;
   P.gamma_over_pr = p->gamma / p->prandtl;
   if (p->shock_cap && p->shock_cap != 1) HF_FAIL("Shock capturing method not implemented.");
+  if (p->LES && p->SGS_model != 0 && p->SGS_model != 1) HF_FAIL("SGS model not available in this build: the filter-based models (WSM, SVV, similarity) are not built yet");
+  if (p->LES && c->nproc > 1) HF_FAIL("LES on several GPUs is not built yet (the SGS-flux halo exchange of mpi_inters::send_sgsf_fpts)");
   if (p->equation == 0 && !(p->riemann_solve_type == 0 || p->riemann_solve_type == 2 || p->riemann_solve_type == 3))
     HF_FAIL("Riemann solver not implemented");
   if (p->viscous && p->vis_riemann_solve_type != 0) HF_FAIL("Viscous Riemann solver not implemented");
@@ -750,6 +941,8 @@ int hf_dev_upload_eles(hf_ctx *c, const hf_eles_desc *d)
   perm(q.h_ref, 1, 1);
   perm(q.disu_upts0, nu, d->n_fields);
   perm(q.JGinv_over_int_cubpts, (size_t)nd * nd * d->n_over_int_cubpts, 1);
+  perm(q.wall_distance, nu, nd);
+  perm(q.Jacobian_fpts, (size_t)nd * nd * nf, 1);
   return upload_eles_impl(c, &q);
 }
 
@@ -822,6 +1015,17 @@ static int upload_eles_impl(hf_ctx *c, const hf_eles_desc *d)
     if (hf_alloc_copy(c, &e.JGinv_over_int, d->JGinv_over_int_cubpts, NC * nd * nd)) return 1;
     if (hf_alloc_zero(c, &e.u_cub, NC * F)) return 1;
     if (hf_alloc_zero(c, &e.tdisf_cub, NC * F * nd)) return 1;
+  }
+  if (c->prm.LES)
+  {
+    if (!visc) HF_FAIL("LES not supported with inviscid flow");
+    if (!d->Jacobian_fpts || d->ele_vol_factor <= 0.) HF_FAIL("LES needs Jacobian_fpts and the reference-element volume");
+    if (c->prm.SGS_model == 0 && !d->wall_distance) HF_FAIL("the Smagorinsky model needs wall_distance");
+    if (hf_alloc_zero(c, &e.sgsf_upts, NU * F * nd)) return 1;
+    if (hf_alloc_zero(c, &e.sgsf_fpts, NFP * F * nd)) return 1;
+    if (hf_alloc_copy(c, &e.Jacobian_fpts, d->Jacobian_fpts, NFP * nd * nd)) return 1;
+    if (d->wall_distance && hf_alloc_copy(c, &e.wall_distance, d->wall_distance, NU * nd)) return 1;
+    e.ele_vol_factor = d->ele_vol_factor;
   }
   if (c->prm.shock_cap)
   {
@@ -1075,6 +1279,16 @@ int hf_dev_eles_op(hf_ctx *c, int ele_type, int op)
     return 0;
   case HF_EVALUATE_VISCFLUX:
     if (!visc) HF_FAIL("evaluate_viscFlux called on an inviscid run");
+    if (c->prm.LES)
+    {
+      hf_les Q;
+      Q.sgs_model = c->prm.SGS_model; Q.order = e.order; Q.C_s = c->prm.C_s; Q.Kappa = c->prm.Kappa; Q.prandtl_t = c->prm.prandtl_t;
+      Q.filter_ratio = c->prm.filter_ratio; Q.vol_factor = e.ele_vol_factor; Q.gamma = c->prm.gamma;
+      HF_DISPATCH(nd, nfl, (k_point_flux_les<ND, NF><<<hf_blocks(NU, 128), 128, 0, c->stream>>>((long long)NU, e.n_upts, e.disu_upts[0], e.grad_disu_upts, e.JGinv_upts,
+                                                                                          e.detjac_upts, e.wall_distance, e.tdisf_upts, e.sgsf_upts, c->phys, Q)));
+      HF_LAUNCH_CHECK(c);
+      return 0;
+    }
     HF_DISPATCH(nd, nfl, (k_point_flux<ND, NF, true><<<hf_blocks(NU, 128), 128, 0, c->stream>>>((long long)NU, e.disu_upts[0], e.grad_disu_upts, e.JGinv_upts, e.tdisf_upts, c->phys)));
     HF_LAUNCH_CHECK(c);
     return 0;
@@ -1099,6 +1313,15 @@ int hf_dev_eles_op(hf_ctx *c, int ele_type, int op)
     HF_LAUNCH_CHECK(c);
     for (int d = 0; d < nd; d++)
       if (op_apply(c, ell1(e.over_int_filter), e.tdisf_cub + d * NC * nfl, 0, e.tdisf_upts + d * NU * nfl, ncols, false)) return 1;
+    return 0;
+  }
+  case HF_EXTRAPOLATE_SGSFLUX:
+  {
+    if (!c->prm.LES) HF_FAIL("extrapolate_sgsFlux called without LES");
+    for (int d = 0; d < nd; d++)
+      if (op_apply(c, ell1(e.opp_0), e.sgsf_upts + d * NU * nfl, 0, e.sgsf_fpts + d * NFP * nfl, ncols, false)) return 1;
+    HF_DISPATCH(nd, nfl, (k_sgsf_physical<ND, NF><<<hf_blocks(NFP, 128), 128, 0, c->stream>>>((long long)NFP, e.sgsf_fpts, e.detjac_fpts, e.Jacobian_fpts)));
+    HF_LAUNCH_CHECK(c);
     return 0;
   }
   case HF_SHOCK_CAPTURE:
@@ -1129,7 +1352,7 @@ int hf_dev_int_inters_op(hf_ctx *c, int inter_type, int op)
   if (op == HF_COMMON_INVFLUX)
     HF_DISPATCH(nd, nfl, (k_int_invflux<ND, NF><<<hf_blocks(n, 128), 128, 0, c->stream>>>(W, n, I.nf, I.idx_l, I.idx_r, I.type_l, I.type_r, c->phys, c->prm.viscous)));
   else if (op == HF_COMMON_VISCFLUX)
-    HF_DISPATCH(nd, nfl, (k_int_viscflux<ND, NF><<<hf_blocks(n, 128), 128, 0, c->stream>>>(W, n, I.nf, I.idx_l, I.idx_r, I.type_l, I.type_r, c->phys)));
+    HF_DISPATCH(nd, nfl, (k_int_viscflux<ND, NF><<<hf_blocks(n, 128), 128, 0, c->stream>>>(W, n, I.nf, I.idx_l, I.idx_r, I.type_l, I.type_r, c->phys, c->prm.LES)));
   else
     HF_FAIL("unknown interface operation");
   HF_LAUNCH_CHECK(c);
@@ -1213,6 +1436,7 @@ static int staged_residual(hf_ctx *c, double time)
     EACH_ELE(HF_CORRECT_GRADIENT);
     if (par) EACH_MPI(4);
     EACH_ELE(HF_EVALUATE_VISCFLUX);
+    if (c->prm.LES) EACH_ELE(HF_EXTRAPOLATE_SGSFLUX);
   }
   EACH_ELE(HF_EXTRAPOLATE_TOTALFLUX);
   EACH_ELE(HF_CALCULATE_DIVERGENCE);
@@ -1370,6 +1594,8 @@ static int locate_array(hf_ctx *c, hf_eles_dev &e, int which, double **p, size_t
   case HF_SRC_UPTS: *p = nullptr; *n = NU * F; break;
   case HF_DT_LOCAL: *p = e.dt_local; *n = e.n_eles; break;
   case HF_SENSOR: *p = e.sensor; *n = e.n_eles; break;
+  case HF_SGSF_UPTS: *p = e.sgsf_upts; *n = NU * F * D; break;
+  case HF_SGSF_FPTS: *p = e.sgsf_fpts; *n = NFP * F * D; break;
   default: HF_FAIL("unknown array id");
   }
   (void)c;
@@ -1380,7 +1606,7 @@ static size_t pts_per_ele(const hf_eles_dev &e, int which)
 {
   switch (which)
   {
-  case HF_DISU_FPTS: case HF_NORM_TDISF_FPTS: case HF_NORM_TCONF_FPTS: case HF_DELTA_DISU_FPTS: case HF_GRAD_DISU_FPTS: return e.n_fpts;
+  case HF_DISU_FPTS: case HF_NORM_TDISF_FPTS: case HF_NORM_TCONF_FPTS: case HF_DELTA_DISU_FPTS: case HF_GRAD_DISU_FPTS: case HF_SGSF_FPTS: return e.n_fpts;
   case HF_DT_LOCAL: case HF_SENSOR: return 1;
   default: return e.n_upts;
   }

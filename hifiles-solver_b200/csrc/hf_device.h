@@ -32,6 +32,7 @@ struct hf_ele_view
   double *norm_tconf_fpts;  // (fpt,ele,field)
   double *delta_disu_fpts;  // (fpt,ele,field)
   double *grad_disu_fpts;   // (fpt,ele,field,dim)
+  double *sgsf_fpts;        // (fpt,ele,field,dim), LES only
   const double *tdA_fpts;   // (fpt,ele)
   const double *norm_fpts;  // (fpt,ele,dim)
 };
@@ -51,6 +52,9 @@ struct hf_eles_dev
   int n_cub = 0;
   hf_ell opp_over_int, over_int_filter;
   double *JGinv_over_int = nullptr, *u_cub = nullptr, *tdisf_cub = nullptr;
+  // LES
+  double *sgsf_upts = nullptr, *sgsf_fpts = nullptr, *wall_distance = nullptr, *Jacobian_fpts = nullptr;
+  double ele_vol_factor = 0.;
   // shock capturing (dense, row-major access by mode)
   double *inv_vandermonde = nullptr, *exp_filter = nullptr, *sensor_w_top = nullptr, *sensor_w_all = nullptr, *sensor = nullptr;
   double *detjac_upts = nullptr, *JGinv_upts = nullptr, *detjac_fpts = nullptr, *JGinv_fpts = nullptr;

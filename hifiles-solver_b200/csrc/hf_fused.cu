@@ -518,6 +518,7 @@ int hf_fused_prepare(hf_ctx *c)
     if (c->bdys[t].n_inters) return no("boundary interfaces present (fused path handles interior and partition faces)");
   if (!e.affine) return no("elements are not affine (metric variation inside an element)");
   if (c->prm.over_int) return no("over-integration runs through the staged kernels");
+  if (c->prm.LES) return no("LES runs through the staged kernels");
   if (e.order < 1 || e.order > 5) return no("order outside 1..5");
   const bool visc = c->prm.viscous != 0;
   const int N = e.order + 1, NN = N * N, NFP = 6 * NN, ne = e.n_eles;

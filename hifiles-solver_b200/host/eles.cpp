@@ -450,6 +450,7 @@ void eles::set_transforms_fpts()
   tdA_fpts.setup(n_fpts_per_ele, n_eles);
   norm_fpts.setup(n_fpts_per_ele, n_eles, n_dims);
   pos_fpts.setup(n_fpts_per_ele, n_eles, n_dims);
+  if (run_input.LES) Jacobian_fpts.setup(n_dims, n_dims, n_fpts_per_ele, n_eles);
   basis_cache c;
   double dp[3][3], tn[3];
   for (int i = 0; i < n_eles; i++)
@@ -472,6 +473,7 @@ void eles::set_transforms_fpts()
           double acc = 0.0;
           for (int q = 0; q < ns; q++) acc += ds[q * n_dims + b] * shape(a, q, i);
           dp[a][b] = acc;
+          if (run_input.LES) Jacobian_fpts(a, b, j, i) = acc;
         }
       if (n_dims == 2)
       {
@@ -559,6 +561,13 @@ void eles::mv_all_cpu_gpu()
     d.over_int_filter = over_int_filter.get_ptr_cpu();
     d.JGinv_over_int_cubpts = JGinv_over_int_cubpts.get_ptr_cpu();
   }
+  if (run_input.LES)
+  {
+    static const double vol_factor[5] = {2., 4., 8. / 6., 4., 8.}; // tri, quad, tet, prism, hex: <type>::calc_ele_vol
+    d.ele_vol_factor = vol_factor[ele_type];
+    d.Jacobian_fpts = Jacobian_fpts.get_ptr_cpu();
+    d.wall_distance = wall_distance.size() ? wall_distance.get_ptr_cpu() : nullptr;
+  }
   if (run_input.shock_cap)
   {
     d.inv_vandermonde = modal_inv_vandermonde.get_ptr_cpu();
@@ -600,6 +609,7 @@ void eles::extrapolate_solution() { if (n_eles) hf_check(hf_dev_eles_op(ctx, ele
 void eles::calculate_gradient() { if (n_eles) hf_check(hf_dev_eles_op(ctx, ele_type, HF_CALCULATE_GRADIENT)); }
 void eles::evaluate_invFlux() { if (n_eles) hf_check(hf_dev_eles_op(ctx, ele_type, HF_EVALUATE_INVFLUX)); }
 void eles::evaluate_invFlux_over_int() { if (n_eles) hf_check(hf_dev_eles_op(ctx, ele_type, HF_EVALUATE_INVFLUX_OVER_INT)); }
+void eles::extrapolate_sgsFlux() { if (n_eles) hf_check(hf_dev_eles_op(ctx, ele_type, HF_EXTRAPOLATE_SGSFLUX)); }
 void eles::shock_capture() { if (n_eles) hf_check(hf_dev_eles_op(ctx, ele_type, HF_SHOCK_CAPTURE)); }
 void eles::cp_sensor_gpu_cpu() { if (n_eles && run_input.shock_cap) hf_check(hf_dev_download(ctx, ele_type, HF_SENSOR, sensor.get_ptr_cpu(), sensor.size())); }
 void eles::correct_gradient() { if (n_eles) hf_check(hf_dev_eles_op(ctx, ele_type, HF_CORRECT_GRADIENT)); }

@@ -310,3 +310,40 @@ void eles::set_shock_capture()
   exp_filter = mult_arrays(modal_vandermonde, t);
   sensor.setup(n_eles);
 }
+
+// ---- LES: wall distance -----------------------------------------------------------------------------------------------------
+// vector from the nearest no-slip wall flux point to every solution point; the first of equally near points wins;
+// (1e20, ...) when the mesh has no such wall
+void eles::calc_wall_distance(std::vector<hf_array<double>> &loc_noslip_bdy)
+{
+  if (n_eles == 0) return;
+  wall_distance.setup(n_upts_per_ele, n_eles, n_dims);
+  double vec[3], vecmin[3] = {1e20, 1e20, 1e20};
+  for (int i = 0; i < n_eles; ++i)
+    for (int j = 0; j < n_upts_per_ele; ++j)
+    {
+      double distmin = 1e20;
+      for (int t = 0; t < 3; t++)
+      {
+        hf_array<double> &W = loc_noslip_bdy[t];
+        const int nw = (int)(W.size() ? W.get_dim(2) : 0), nfp = W.get_dim(1);
+        for (int k = 0; k < nw; ++k)
+          for (int m = 0; m < nfp; ++m)
+          {
+            double dist = 0.0;
+            for (int n = 0; n < n_dims; ++n)
+            {
+              vec[n] = pos_upts(j, i, n) - W(n, m, k);
+              dist += vec[n] * vec[n];
+            }
+            dist = sqrt(dist);
+            if (dist < distmin)
+            {
+              for (int n = 0; n < n_dims; ++n) vecmin[n] = vec[n];
+              distmin = dist;
+            }
+          }
+      }
+      for (int n = 0; n < n_dims; ++n) wall_distance(j, i, n) = vecmin[n];
+    }
+}

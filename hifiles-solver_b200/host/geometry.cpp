@@ -492,4 +492,29 @@ void GeoPreprocess(struct solution *FlowSol, mesh &mesh_data)
     else if (bcid_f != -3)
       FlowSol->mesh_bdy_inters[t].set_boundary(i_bdy[t]++, bcid_f, mesh_data.ctype(ic_l), local_c[ic_l], mesh_data.f2loc_f(i, 0), FlowSol);
   }
+
+  // wall distance for the Smagorinsky near-wall damping (reference src/geometry.cpp:706-892): flux points of every
+  // isothermal / adiabatic wall face, per face type, in mesh-face order
+  if (run_input.LES && run_input.SGS_model == 0)
+  {
+    if (FlowSol->nproc > 1) FatalError("LES on several GPUs is not built yet");
+    vector<hf_array<double>> loc_noslip_bdy(3);
+    for (int t = 0; t < 3; t++)
+    {
+      bdy_inters &B = FlowSol->mesh_bdy_inters[t];
+      vector<int> walls;
+      for (int q = 0; q < B.get_n_inters(); q++)
+      {
+        int flag = run_input.bc_list[B.boundary_id(q)].get_bc_flag();
+        if (flag == ISOTHERM_WALL || flag == ADIABAT_WALL) walls.push_back(q);
+      }
+      const int nfp = t == 0 ? run_input.order + 1 : (t == 1 ? (run_input.order + 2) * (run_input.order + 1) / 2 : (run_input.order + 1) * (run_input.order + 1));
+      loc_noslip_bdy[t].setup(FlowSol->n_dims, nfp, max((int)walls.size(), 1));
+      loc_noslip_bdy[t].setup(FlowSol->n_dims, nfp, (int)walls.size());
+      for (size_t w = 0; w < walls.size(); w++)
+        for (int j = 0; j < nfp; j++)
+          for (int k = 0; k < FlowSol->n_dims; k++) loc_noslip_bdy[t](k, j, (int)w) = B.pos_fpts(j, walls[w], k);
+    }
+    for (int i = 0; i < FlowSol->n_ele_types; i++) FlowSol->mesh_eles(i)->calc_wall_distance(loc_noslip_bdy);
+  }
 }

@@ -261,6 +261,9 @@ public:
   void evaluate_invFlux();
   void evaluate_invFlux_over_int();
   void shock_capture();
+  void extrapolate_sgsFlux();
+  /*! distance vector of every solution point to the nearest no-slip wall flux point, brute force (reference src/eles.cpp:2698-2813) */
+  void calc_wall_distance(std::vector<hf_array<double>> &loc_noslip_bdy);
   void cp_sensor_gpu_cpu();
   void correct_gradient();
   void evaluate_viscFlux();
@@ -339,6 +342,7 @@ public:
   hf_array<double> modal_vandermonde, modal_inv_vandermonde;
   hf_array<double> loc_over_int_cubpts, weight_over_int_cubpts, opp_over_int_cubpts, over_int_filter, JGinv_over_int_cubpts;
   hf_array<double> sensor_w_top, sensor_w_all, exp_filter, sensor;
+  hf_array<double> wall_distance, Jacobian_fpts;
 };
 
 class eles_hexas : public eles

@@ -46,6 +46,12 @@ static void upload_params(struct solution *FlowSol)
   p.n_rk = get_n_rk_steps(run_input.adv_type);
   for (int i = 0; i < run_input.RK_a.get_dim(0) && i < HF_MAX_RK; i++) p.RK_a[i] = run_input.RK_a(i);
   for (int i = 0; i < run_input.RK_b.get_dim(0) && i < HF_MAX_RK; i++) p.RK_b[i] = run_input.RK_b(i);
+  p.LES = run_input.LES;
+  p.SGS_model = run_input.SGS_model;
+  p.C_s = run_input.C_s;
+  p.Kappa = run_input.Kappa;
+  p.prandtl_t = run_input.prandtl_t;
+  p.filter_ratio = run_input.filter_ratio;
   p.over_int = run_input.over_int;
   p.shock_cap = run_input.shock_cap;
   p.shock_det_field = run_input.shock_det_field;
@@ -143,6 +149,8 @@ void CalcResidual(int in_file_num, int in_rk_stage, struct solution *FlowSol)
     if (FlowSol->nproc > 1)
       for (int i = 0; i < FlowSol->n_mpi_inter_types; i++) FlowSol->mesh_mpi_inters[i].send_corrected_gradient();
     for (int i = 0; i < n; i++) FlowSol->mesh_eles(i)->evaluate_viscFlux();
+    if (run_input.LES)
+      for (int i = 0; i < n; i++) FlowSol->mesh_eles(i)->extrapolate_sgsFlux();
   }
   for (int i = 0; i < n; i++) FlowSol->mesh_eles(i)->extrapolate_totalFlux();
   for (int i = 0; i < n; i++) FlowSol->mesh_eles(i)->calculate_divergence();

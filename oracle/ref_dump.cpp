@@ -170,6 +170,7 @@ static void dump_setup(struct solution *S)
       put(p + "JGinv_over_int_cubpts", e->JGinv_over_int_cubpts);
     }
     if (run_input.shock_cap) put(p + "exp_filter", e->exp_filter);
+    if (run_input.LES && run_input.SGS_model == 0) put(p + "wall_distance", e->wall_distance);
   }
   const char *iname[3] = {"seg", "tri", "quad"};
   for (int t = 0; t < S->n_int_inter_types; t++)
@@ -245,7 +246,7 @@ static void dump_state(struct solution *S, const string &tag, bool all)
   }
 }
 
-// CalcResidual (src/solver.cpp:50-223) unrolled for the serial, non-LES, non-RANS case, with dumps in between.
+// CalcResidual (src/solver.cpp:50-223) unrolled for the serial, non-RANS case (LES: eddy-viscosity models, no filter step), with dumps in between.
 static void calc_residual_stagewise(struct solution *S, const string &tag)
 {
   int n = S->n_ele_types;
@@ -263,6 +264,8 @@ static void calc_residual_stagewise(struct solution *S, const string &tag)
       else if (arr == "delta_disu_fpts") put(p, e->delta_disu_fpts);
       else if (arr == "norm_tdisf_fpts") put(p, e->norm_tdisf_fpts);
       else if (arr == "div_tconf_upts") put(p, e->div_tconf_upts(0));
+      else if (arr == "sgsf_upts") put(p, e->sgsf_upts);
+      else if (arr == "sgsf_fpts") put(p, e->sgsf_fpts);
     }
   };
   for (int i = 0; i < n; i++) S->mesh_eles(i)->extrapolate_solution();
@@ -286,6 +289,12 @@ static void calc_residual_stagewise(struct solution *S, const string &tag)
     dump1("s11_correct_gradient", "grad_disu_fpts");
     for (int i = 0; i < n; i++) S->mesh_eles(i)->evaluate_viscFlux();
     dump1("s13_evaluate_viscFlux", "tdisf_upts");
+    if (run_input.LES)
+    {
+      dump1("s13_evaluate_viscFlux", "sgsf_upts");
+      for (int i = 0; i < n; i++) S->mesh_eles(i)->extrapolate_sgsFlux();
+      dump1("s14_extrapolate_sgsFlux", "sgsf_fpts");
+    }
   }
   for (int i = 0; i < n; i++) S->mesh_eles(i)->extrapolate_totalFlux();
   dump1("s15_extrapolate_totalFlux", "norm_tdisf_fpts");

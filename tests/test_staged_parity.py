@@ -74,6 +74,20 @@ CASES = {
     "pritet_p2_ns_roem_overint": ("pritet", (2, 4, 2), {}, dict(order=2, adv_type=3, riemann_solve_type=2, viscous=1, dt=1e-5, over_int=1, over_int_order=4)),
     "mixed_tri_quad_p3_euler_overint": ("mixed", 6, {}, dict(order=3, adv_type=3, riemann_solve_type=0, viscous=0, ic_form=0, test_case=1, dt=1e-3,
                                                             dx_cyclic=20., dy_cyclic=20., dz_cyclic=None, over_int=1, over_int_order=5, **EULER_IC)),
+    # LES, eddy-viscosity sub-grid models (eles::calc_sgsf_upts, extrapolate_sgsFlux; reference src/eles.cpp:2395-2646, 2817-2914): BASELINE config 5
+    "hex_p3_les_wale_rk34": ("hex", 3, dict(warp=0.1), dict(order=3, adv_type=2, riemann_solve_type=3, viscous=1, dt=1e-5, LES=1, SGS_model=1, C_s=0.325,
+                                                         filter_ratio=2.0)),
+    "pritet_p2_les_wale_rk34": ("pritet", (2, 4, 2), {}, dict(order=2, adv_type=2, riemann_solve_type=2, viscous=1, dt=1e-5, LES=1, SGS_model=1, C_s=0.325,
+                                                            filter_ratio=1.5)),
+    "mixed_tri_quad_p3_les_smagorinsky_walls": ("mixed", (8, 6), dict(lengths=(4., 2.), origin=(0., 0.), bcs={"x-": "In", "x+": "Out", "y-": "Wall", "y+": "Top"}),
+                                                dict(order=3, adv_type=3, riemann_solve_type=0, viscous=1, ic_form=1, dt=5e-5, fix_vis=0, Mach_c_ic=0.3, nx_c_ic=1.,
+                                                     ny_c_ic=0., nz_c_ic=0., T_c_ic=300., rho_c_ic=1.17, Mach_free_stream=0.3, rho_free_stream=1.17,
+                                                     T_free_stream=300., L_free_stream=1., dx_cyclic=None, dy_cyclic=None, dz_cyclic=None, bc_Cyclic_type=None,
+                                                     bc_In_type="char", bc_In_p_static=100747., bc_In_mach=0.3, bc_In_T_static=300., bc_In_nx=1., bc_In_ny=0.,
+                                                     bc_Out_type="sub_out_simp", bc_Out_p_static=100000., bc_Wall_type="isotherm_wall", bc_Wall_T_static=310.,
+                                                     bc_Top_type="adiabat_wall", bc_Top_u=20., LES=1, SGS_model=0, C_s=0.1, filter_ratio=2.0)),
+    "hexpri_p2_les_smagorinsky_periodic": ("hexpri", (2, 2, 4), {}, dict(order=2, adv_type=2, riemann_solve_type=3, viscous=1, dt=2e-5, LES=1, SGS_model=0,
+                                                                       C_s=0.1, filter_ratio=2.0)),
     # Persson sensor + exponential modal filter after every stage (eles::shock_capture, reference src/eles.cpp:2918-2959): BASELINE config 5;
     # s0 is set inside the range of the sensor values of these smooth fields so that some elements are filtered and some are not
     "mixed_tri_quad_p3_euler_shockcap": ("mixed", 6, {}, dict(order=3, adv_type=3, riemann_solve_type=3, viscous=0, ic_form=0, test_case=1, dt=1e-3,
@@ -131,11 +145,15 @@ def test_methods_one_by_one(tmp_path, hb, meshgen, name):
             dt = run.calc_time_step()  # calc_time_step precedes the RK loop (reference src/HiFiLES.cpp:199)
             assert abs(dt / ref["step0.dt_time"][0] - 1.0) < 1e-14
 
-        def each(op, arr, key):
+        # the SGS models evaluate pow(x, 1.25 / 1.5 / 2.5): device and host libm differ by an ulp there, and every array
+        # downstream of the SGS flux (divergence = derivative of the flux) amplifies it: 1e-12 from that point on
+        late = 1e-12 if CASES[name][3].get("LES") else TOL
+
+        def each(op, arr, key, tol=TOL):
             for t in types:
                 run.eles_op(t, op)
             for t in types:
-                check(key + "." + t + "." + arr, run.download(t, arr), ref[pre + key + "." + t + "." + arr])
+                check(key + "." + t + "." + arr, run.download(t, arr), ref[pre + key + "." + t + "." + arr], tol)
 
         each("extrapolate_solution", "disu_fpts", "s02_extrapolate_solution")
         if visc:
@@ -156,20 +174,24 @@ def test_methods_one_by_one(tmp_path, hb, meshgen, name):
             for t in types:
                 check("grad_disu_upts " + t, run.download(t, "grad_disu_upts"), ref[pre + "s11_correct_gradient." + t + ".grad_disu_upts"])
                 check("grad_disu_fpts " + t, run.download(t, "grad_disu_fpts"), ref[pre + "s11_correct_gradient." + t + ".grad_disu_fpts"])
-            each("evaluate_viscFlux", "tdisf_upts", "s13_evaluate_viscFlux")
-        each("extrapolate_totalFlux", "norm_tdisf_fpts", "s15_extrapolate_totalFlux")
-        each("calculate_divergence", "div_tconf_upts", "s16_calculate_divergence")
+            each("evaluate_viscFlux", "tdisf_upts", "s13_evaluate_viscFlux", late)
+            if CASES[name][3].get("LES"):
+                for t in types:
+                    check("sgsf_upts " + t, run.download(t, "sgsf_upts"), ref[pre + "s13_evaluate_viscFlux." + t + ".sgsf_upts"], late)
+                each("extrapolate_sgsFlux", "sgsf_fpts", "s14_extrapolate_sgsFlux", late)
+        each("extrapolate_totalFlux", "norm_tdisf_fpts", "s15_extrapolate_totalFlux", late)
+        each("calculate_divergence", "div_tconf_upts", "s16_calculate_divergence", late)
         if visc:
             for it in range(3):
                 run.int_inters_op(it, 1)
             for it in range(3):
                 run.bdy_inters_op(it, 1)
             for t in types:
-                check("norm_tconf_fpts visc " + t, run.download(t, "norm_tconf_fpts"), ref[pre + "s17_common_viscFlux." + t + ".norm_tconf_fpts"])
-        each("calculate_corrected_divergence", "div_tconf_upts", "s18_corrected_divergence")
+                check("norm_tconf_fpts visc " + t, run.download(t, "norm_tconf_fpts"), ref[pre + "s17_common_viscFlux." + t + ".norm_tconf_fpts"], late)
+        each("calculate_corrected_divergence", "div_tconf_upts", "s18_corrected_divergence", late)
         run.advance_solution(0)  # AdvanceSolution, then shock_capture when it is on (reference src/HiFiLES.cpp:209-217)
         for t in types:
-            check("advanced " + t, run.download(t, "disu_upts"), ref["step0.stage0.advanced." + t + ".disu_upts"])
+            check("advanced " + t, run.download(t, "disu_upts"), ref["step0.stage0.advanced." + t + ".disu_upts"], late)
         if CASES[name][3].get("shock_cap"):
             flagged = total = 0
             for t in types:
@@ -197,9 +219,10 @@ def test_time_steps_reference_call_sequence(tmp_path, hb, meshgen, name):
             ref_dt = ref["step%d.dt_time" % (n_steps - 1)][0]
             assert abs(run.scalar("dt") / ref_dt - 1.0) < 1e-14, (run.scalar("dt"), ref_dt)
         hist = run.norm_residual()
-        check("residual norm", hist, ref["history.norm_residual"][:, -1], 1e-13)
+        loose = 1e-12 if CASES[name][3].get("LES") else 1e-13
+        check("residual norm", hist, ref["history.norm_residual"][:, -1], loose)
         for t in run.ele_types():
-            # after 3 steps the 1-ulp differences of pow() (Sutherland's law, characteristic BCs) have propagated: 1e-13
-            check("final disu_upts " + t, run.download(t, "disu_upts"), ref["final." + t + ".disu_upts"], 1e-13)
-            check("final div_tconf_upts " + t, run.download(t, "div_tconf_upts"), ref["final." + t + ".div_tconf_upts"], 1e-13)
+            # after 3 steps the 1-ulp differences of pow() (Sutherland's law, characteristic BCs, SGS models) have propagated
+            check("final disu_upts " + t, run.download(t, "disu_upts"), ref["final." + t + ".disu_upts"], loose)
+            check("final div_tconf_upts " + t, run.download(t, "div_tconf_upts"), ref["final." + t + ".div_tconf_upts"], loose)
         assert run.launch_count() > 0
