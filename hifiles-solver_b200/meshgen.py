@@ -166,7 +166,18 @@ def _write_neu(path, ndim, nodes, cells, groups):
             f.write(" BOUNDARY CONDITIONS 2.3.16\n%32s%8d%8d%8d%8d\n" % (name, 1, rows.shape[0], 0, 6))
             _write_rows(f, rows, "%10d%5d%5d")
             f.write("ENDOFSECTION\n")
-    return dict(n_cells=len(cells), n_nodes=nodes.shape[0])
+    xyz = {int(r[0]): r[1:] for r in nodes}
+    cent = np.array([np.mean([xyz[v] for v in vs], axis=0) for _, _, vs in cells])
+    return dict(n_cells=len(cells), n_nodes=nodes.shape[0], centroids=cent)
+
+
+def slab_partition(centroids, nproc, axis=0):
+    """part[global cell] for any mesh: nproc slabs of (nearly) equal cell count along one axis, from the cell centroids a
+    generator returned.  A stand-in for the reference's ParMETIS call on the generated test meshes."""
+    order = np.argsort(centroids[:, axis], kind="stable")
+    part = np.zeros(len(order), dtype=np.int32)
+    part[order] = (np.arange(len(order)) * nproc) // len(order)
+    return part
 
 
 def mixed_box_2d(path, n, lengths=(20., 20.), bcs=None, origin=(-10., -10.), kind="tri", warp=0.0):

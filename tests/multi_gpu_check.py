@@ -2,7 +2,8 @@
 single-domain result.  Rank 0 also runs the whole mesh on its own GPU (staged kernels = bit-exact reference order) and
 compares element by element through ele2global_ele.  Usage:
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port 29511 \
-        tests/multi_gpu_check.py [n] [order] [steps] [fused|staged]"""
+        tests/multi_gpu_check.py [n] [order] [steps] [fused|staged] [hex|tet|pri|hexpri|pritet|tri|mixed]
+For the simplex / mixed kinds the mesh is cut into slabs (meshgen.slab_partition) and every element type is compared."""
 import os
 import pathlib
 import sys
@@ -21,6 +22,7 @@ def main():
     order = int(sys.argv[2]) if len(sys.argv) > 2 else 3
     steps = int(sys.argv[3]) if len(sys.argv) > 3 else 2
     mode = sys.argv[4] if len(sys.argv) > 4 else "fused"
+    kind = sys.argv[5] if len(sys.argv) > 5 else "hex"
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -32,6 +34,8 @@ def main():
     work = obj[0]
     mesh = os.path.join(work, "tgv.neu")
     inp = os.path.join(work, "input")
+    if kind != "hex":
+        return general(hb, mg, dist, rank, world, work, kind, n, order, steps)
     if rank == 0:
         mg.hex_box(mesh, n)
         mg.write_input(inp, "tgv.neu", order=order, adv_type=2, dt=1e-5, riemann_solve_type=3, viscous=1)
@@ -72,6 +76,70 @@ def main():
         ok = bool(err < 1e-12)
         print("multi_gpu_check: world=%d n=%d order=%d steps=%d mode=%s partition faces on rank 0: %d  max rel err vs single domain %.3e  %s"
               % (world, n, order, steps, mode, n_mpi, err, "OK" if ok else "FAIL"))
+    flag = torch.tensor([1 if ok else 0], device="cuda")
+    dist.broadcast(flag, src=0)
+    dist.barrier()
+    dist.destroy_process_group()
+    sys.exit(0 if int(flag.item()) == 1 else 1)
+
+
+def general(hb, mg, dist, rank, world, work, kind, n, order, steps):
+    """staged kernels on a partitioned simplex / prism / mixed mesh (triangular, quadrilateral and segment partition faces)"""
+    mesh = os.path.join(work, "m.neu")
+    inp = os.path.join(work, "input")
+    two_d = kind in ("tri", "mixed", "quad")
+    obj = [None]
+    if rank == 0:
+        if two_d:
+            info = mg.mixed_box_2d(mesh, n, kind=kind, lengths=(6.2831853071795862,) * 2, origin=(0., 0.))
+            mg.write_input(inp, "m.neu", order=order, adv_type=2, dt=1e-5, riemann_solve_type=0, viscous=1, dz_cyclic=None)
+        else:
+            info = mg.mixed_box_3d(mesh, n, kind=kind)
+            mg.write_input(inp, "m.neu", order=order, adv_type=2, dt=1e-5, riemann_solve_type=2, viscous=1)
+        obj = [mg.slab_partition(info["centroids"], world, axis=1 if kind == "pritet" else 0)]
+    dist.broadcast_object_list(obj, src=0)
+    part = obj[0]
+    idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
+    if rank == 0:
+        idt = torch.tensor(list(hb.nccl_unique_id()), dtype=torch.uint8, device="cuda")
+    dist.broadcast(idt, src=0)
+    run = hb.Run(inp, rank=rank, nproc=world, part=part, nccl_id=bytes(idt.cpu().tolist()))
+    run.set_mode(False)
+    run.run(steps, fused=False)
+    mine = {t: (run.download(t, "disu_upts"), run.host_array(t + ".ele2global_ele")) for t in run.ele_types()}
+    n_mpi = sum(run.n_inters("mpi", i) for i in range(3))
+    run.close()
+    ok, worst = True, 0.
+    n_cells = len(part)
+    for t in ("tri", "quad", "tet", "pri", "hex"):
+        shape = torch.zeros(2, dtype=torch.int64, device="cuda")
+        if t in mine:
+            shape[0], shape[1] = mine[t][0].shape[0], mine[t][0].shape[2]
+        dist.all_reduce(shape, op=dist.ReduceOp.MAX)
+        nu, nf = int(shape[0]), int(shape[1])
+        if nu == 0:
+            continue
+        full = torch.zeros((n_cells, nu, nf), dtype=torch.float64, device="cuda")
+        if t in mine:
+            u, gid = mine[t]
+            full[torch.from_numpy(gid.astype(np.int64)).cuda()] = torch.from_numpy(np.ascontiguousarray(u.transpose(1, 0, 2))).cuda()
+        dist.all_reduce(full)
+        if rank == 0:
+            with hb.Run(inp) as single:
+                single.set_mode(False)
+                single.run(steps, fused=False)
+                us, gs = single.download(t, "disu_upts"), single.host_array(t + ".ele2global_ele")
+            ref = np.zeros((n_cells, nu, nf))
+            ref[gs] = us.transpose(1, 0, 2)
+            got = full.cpu().numpy()
+            sc = np.abs(ref).reshape(-1, nf).max(0)
+            sc[1:nf - 1] = sc[1:nf - 1].max()
+            err = (np.abs(got - ref).reshape(-1, nf).max(0) / sc).max()
+            worst = max(worst, err)
+            ok = ok and bool(err < 1e-12)
+    if rank == 0:
+        print("multi_gpu_check: world=%d kind=%s n=%s order=%d steps=%d mode=staged partition faces on rank 0: %d  max rel err vs single domain %.3e  %s"
+              % (world, kind, n, order, steps, n_mpi, worst, "OK" if ok else "FAIL"))
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.broadcast(flag, src=0)
     dist.barrier()
