@@ -14,11 +14,11 @@ DATA_DIR = os.path.join(PKG_DIR, "data")
 
 HF_ARRAY_IDS = dict(
     disu_upts=0, disu_upts1=1, div_tconf_upts=2, disu_fpts=3, tdisf_upts=4, norm_tdisf_fpts=5, norm_tconf_fpts=6,
-    delta_disu_fpts=7, grad_disu_upts=8, grad_disu_fpts=9, src_upts=10, dt_local=11, sensor=12, sgsf_upts=13, sgsf_fpts=14)
+    delta_disu_fpts=7, grad_disu_upts=8, grad_disu_fpts=9, src_upts=10, dt_local=11, sensor=12, sgsf_upts=13, sgsf_fpts=14, disuf_upts=15, Lu=16, Le=17)
 ELE_TYPES = dict(tri=0, quad=1, tet=2, pri=3, hex=4)
 ELES_OPS = dict(extrapolate_solution=0, calculate_gradient=1, evaluate_invFlux=2, correct_gradient=3, evaluate_viscFlux=4,
                 extrapolate_totalFlux=5, calculate_divergence=6, calculate_corrected_divergence=7, evaluate_invFlux_over_int=8,
-                shock_capture=9, extrapolate_sgsFlux=10)
+                shock_capture=9, extrapolate_sgsFlux=10, calc_sgs_terms=11)
 
 
 class HiFiLESError(RuntimeError):
@@ -201,7 +201,7 @@ class Run:
             disu_upts=(nu, ne, nfl), disu_upts1=(nu, ne, nfl), div_tconf_upts=(nu, ne, nfl), disu_fpts=(nf, ne, nfl),
             tdisf_upts=(nu, ne, nfl, nd), norm_tdisf_fpts=(nf, ne, nfl), norm_tconf_fpts=(nf, ne, nfl),
             delta_disu_fpts=(nf, ne, nfl), grad_disu_upts=(nu, ne, nfl, nd), grad_disu_fpts=(nf, ne, nfl, nd),
-            src_upts=(nu, ne, nfl), dt_local=(ne,), sensor=(ne,), sgsf_upts=(nu, ne, nfl, nd), sgsf_fpts=(nf, ne, nfl, nd))[which]
+            src_upts=(nu, ne, nfl), dt_local=(ne,), sensor=(ne,), sgsf_upts=(nu, ne, nfl, nd), sgsf_fpts=(nf, ne, nfl, nd), disuf_upts=(nu, ne, nfl), Lu=(nu, ne, 3 if nd == 2 else 6), Le=(nu, ne, nd))[which]
 
     def download(self, ele_type, which):
         shape = self._dev_shape(ele_type, which)

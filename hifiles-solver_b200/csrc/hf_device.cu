@@ -172,7 +172,7 @@ struct hf_les
   double C_s, Kappa, prandtl_t, filter_ratio, vol_factor, gamma;
 };
 template <int ND, int NF>
-__device__ __forceinline__ void sgs_flux(const double *u, const double *g, double detjac, const double *wd, const hf_les &Q, double *sf)
+__device__ __forceinline__ void sgs_flux_eddy(const double *u, const double *g, double detjac, const double *wd, const hf_les &Q, double *sf)
 {
   const double rho = u[0];
   double v[ND], ke = 0.;
@@ -274,12 +274,113 @@ __device__ __forceinline__ void sgs_flux(const double *u, const double *g, doubl
   }
 }
 
+template <int ND, int NF>
+__device__ __forceinline__ void sgs_flux(const double *u, const double *g, double detjac, const double *wd, const hf_les &Q, const double *Lu, const double *Le,
+                                         double *sf)
+{
+  const bool eddy = Q.sgs_model <= 2, sim = Q.sgs_model == 2 || Q.sgs_model == 4;
+#pragma unroll
+  for (int q = 0; q < NF * ND; q++) sf[q] = 0.;
+  if (eddy) sgs_flux_eddy<ND, NF>(u, g, detjac, wd, Q, sf);
+  if (sim)
+  {
+    // scale-similarity term from the Leonard tensors (reference src/eles.cpp:2612-2644)
+    const double rho = u[0];
+#pragma unroll
+    for (int j = 0; j < ND; j++) sf[(NF - 1) + NF * j] += Q.gamma * rho * Le[j];
+    if (ND == 2)
+    {
+      sf[1 + NF * 0] += rho * Lu[0];
+      sf[1 + NF * 1] += rho * Lu[2];
+      sf[2 + NF * 0] += sf[1 + NF * 1];
+      sf[2 + NF * 1] += rho * Lu[1];
+    }
+    else
+    {
+      sf[1 + NF * 0] += rho * Lu[0];
+      sf[1 + NF * 1] += rho * Lu[3];
+      sf[1 + NF * 2] += rho * Lu[4];
+      sf[2 + NF * 0] += sf[1 + NF * 1];
+      sf[2 + NF * 1] += rho * Lu[1];
+      sf[2 + NF * 2] += rho * Lu[5];
+      sf[3 % NF + NF * 0] += sf[1 + NF * 2];
+      sf[3 % NF + NF * 1] += sf[2 + NF * 2];
+      sf[3 % NF + NF * 2] += rho * Lu[2];
+    }
+  }
+}
+
+// eles::calc_sgs_terms (reference src/eles.cpp:2058-2200): products of the unfiltered solution, then Leonard tensors
+template <int ND, int NF>
+__global__ void k_sgs_products(long long n_pts, const double *__restrict__ u, double *__restrict__ uu, double *__restrict__ ue)
+{
+  long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (p >= n_pts) return;
+  double t[NF];
+#pragma unroll
+  for (int k = 0; k < NF; k++) t[k] = u[p + k * n_pts];
+  const double rsq = t[0] * t[0];
+  if (ND == 2)
+  {
+    uu[p] = t[1] * t[1] / rsq;
+    uu[p + n_pts] = t[2] * t[2] / rsq;
+    uu[p + 2 * n_pts] = t[1] * t[2] / rsq;
+    t[NF - 1] -= 0.5 * (t[1] * t[1] + t[2] * t[2]) / t[0];
+  }
+  else
+  {
+    uu[p] = t[1] * t[1] / rsq;
+    uu[p + n_pts] = t[2] * t[2] / rsq;
+    uu[p + 2 * n_pts] = t[3 % NF] * t[3 % NF] / rsq;
+    uu[p + 3 * n_pts] = t[1] * t[2] / rsq;
+    uu[p + 4 * n_pts] = t[1] * t[3 % NF] / rsq;
+    uu[p + 5 * n_pts] = t[2] * t[3 % NF] / rsq;
+    t[NF - 1] -= 0.5 * (t[1] * t[1] + t[2] * t[2] + t[3 % NF] * t[3 % NF]) / t[0];
+  }
+#pragma unroll
+  for (int d = 0; d < ND; d++) ue[p + d * n_pts] = t[d + 1] * t[NF - 1] / rsq;
+}
+template <int ND, int NF>
+__global__ void k_sgs_leonard(long long n_pts, const double *__restrict__ uf, double *__restrict__ Lu, double *__restrict__ Le)
+{
+  long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (p >= n_pts) return;
+  double t[NF];
+#pragma unroll
+  for (int k = 0; k < NF; k++) t[k] = uf[p + k * n_pts];
+  const double rsq = t[0] * t[0];
+  double diag;
+  if (ND == 2)
+  {
+    Lu[p] -= (t[1] * t[1]) / rsq;
+    Lu[p + n_pts] -= (t[2] * t[2]) / rsq;
+    Lu[p + 2 * n_pts] -= (t[1] * t[2]) / rsq;
+    diag = (Lu[p] + Lu[p + n_pts]) / 3.0;
+    t[NF - 1] -= 0.5 * (t[1] * t[1] + t[2] * t[2]) / t[0];
+  }
+  else
+  {
+    Lu[p] -= (t[1] * t[1]) / rsq;
+    Lu[p + n_pts] -= (t[2] * t[2]) / rsq;
+    Lu[p + 2 * n_pts] -= (t[3 % NF] * t[3 % NF]) / rsq;
+    Lu[p + 3 * n_pts] -= (t[1] * t[2]) / rsq;
+    Lu[p + 4 * n_pts] -= (t[1] * t[3 % NF]) / rsq;
+    Lu[p + 5 * n_pts] -= (t[2] * t[3 % NF]) / rsq;
+    diag = (Lu[p] + Lu[p + n_pts] + Lu[p + 2 * n_pts]) / 3.0;
+    t[NF - 1] -= 0.5 * (t[1] * t[1] + t[2] * t[2] + t[3 % NF] * t[3 % NF]) / t[0];
+  }
+#pragma unroll
+  for (int d = 0; d < ND; d++) Le[p + d * n_pts] = (Le[p + d * n_pts] - t[d + 1] * t[NF - 1]) / rsq;
+#pragma unroll
+  for (int d = 0; d < ND; d++) Lu[p + d * n_pts] -= diag;
+}
+
 // eles::evaluate_viscFlux with LES (reference src/eles.cpp:2285-2392): viscous + SGS flux, the transformed SGS flux
 // alone goes to sgsf_upts
 template <int ND, int NF>
 __global__ void k_point_flux_les(long long n_pts, int n_upts, const double *__restrict__ u, const double *__restrict__ grad, const double *__restrict__ JGinv,
-                                 const double *__restrict__ detjac, const double *__restrict__ wall_distance, double *__restrict__ tdisf,
-                                 double *__restrict__ sgsf, hf_phys P, hf_les Q)
+                                 const double *__restrict__ detjac, const double *__restrict__ wall_distance, const double *__restrict__ Lu,
+                                 const double *__restrict__ Le, double *__restrict__ tdisf, double *__restrict__ sgsf, hf_phys P, hf_les Q)
 {
   long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (p >= n_pts) return;
@@ -293,7 +394,15 @@ __global__ void k_point_flux_les(long long n_pts, int n_upts, const double *__re
 #pragma unroll
   for (int d = 0; d < ND; d++) wd[d] = wall_distance ? wall_distance[p + d * n_pts] : 1e20;
   vis_flux<ND, NF>(uu, g, f, P);
-  sgs_flux<ND, NF>(uu, g, detjac[p], wd, Q, sf);
+  double lu[6] = {0, 0, 0, 0, 0, 0}, le[3] = {0, 0, 0};
+  if (Lu)
+  {
+#pragma unroll
+    for (int q = 0; q < (ND == 2 ? 3 : 6); q++) lu[q] = Lu[p + q * n_pts];
+#pragma unroll
+    for (int q = 0; q < ND; q++) le[q] = Le[p + q * n_pts];
+  }
+  sgs_flux<ND, NF>(uu, g, detjac[p], wd, Q, lu, le, sf);
 #pragma unroll
   for (int q = 0; q < NF * ND; q++) f[q] = f[q] + 1.0 * sf[q];
 #pragma unroll
@@ -877,7 +986,7 @@ int hf_dev_set_params(hf_ctx *c, const hf_params *p)
   P.riemann_solve_type = p->riemann_solve_type;
   P.gamma_over_pr = p->gamma / p->prandtl;
   if (p->shock_cap && p->shock_cap != 1) HF_FAIL("Shock capturing method not implemented.");
-  if (p->LES && p->SGS_model != 0 && p->SGS_model != 1) HF_FAIL("SGS model not available in this build: the filter-based models (WSM, SVV, similarity) are not built yet");
+  if (p->LES && (p->SGS_model < 0 || p->SGS_model > 4)) HF_FAIL("SGS model not implemented");
   if (p->LES && c->nproc > 1) HF_FAIL("LES on several GPUs is not built yet (the SGS-flux halo exchange of mpi_inters::send_sgsf_fpts)");
   if (p->equation == 0 && !(p->riemann_solve_type == 0 || p->riemann_solve_type == 2 || p->riemann_solve_type == 3))
     HF_FAIL("Riemann solver not implemented");
@@ -1026,6 +1135,18 @@ static int upload_eles_impl(hf_ctx *c, const hf_eles_desc *d)
     if (hf_alloc_copy(c, &e.Jacobian_fpts, d->Jacobian_fpts, NFP * nd * nd)) return 1;
     if (d->wall_distance && hf_alloc_copy(c, &e.wall_distance, d->wall_distance, NU * nd)) return 1;
     e.ele_vol_factor = d->ele_vol_factor;
+    if (c->prm.SGS_model >= 2)
+    {
+      if (!d->filter_upts) HF_FAIL("the filter-based SGS models need filter_upts");
+      if (build_ell(c, e.filter_upts, d->filter_upts, nu, nu)) return 1;
+      if (hf_alloc_zero(c, &e.disuf_upts, NU * F)) return 1;
+      if (c->prm.SGS_model != 3)
+      {
+        const size_t dim3 = nd == 2 ? 3 : 6;
+        if (hf_alloc_zero(c, &e.uu, NU * dim3) || hf_alloc_zero(c, &e.Lu, NU * dim3)) return 1;
+        if (hf_alloc_zero(c, &e.ue, NU * nd) || hf_alloc_zero(c, &e.Le, NU * nd)) return 1;
+      }
+    }
   }
   if (c->prm.shock_cap)
   {
@@ -1285,7 +1406,7 @@ int hf_dev_eles_op(hf_ctx *c, int ele_type, int op)
       Q.sgs_model = c->prm.SGS_model; Q.order = e.order; Q.C_s = c->prm.C_s; Q.Kappa = c->prm.Kappa; Q.prandtl_t = c->prm.prandtl_t;
       Q.filter_ratio = c->prm.filter_ratio; Q.vol_factor = e.ele_vol_factor; Q.gamma = c->prm.gamma;
       HF_DISPATCH(nd, nfl, (k_point_flux_les<ND, NF><<<hf_blocks(NU, 128), 128, 0, c->stream>>>((long long)NU, e.n_upts, e.disu_upts[0], e.grad_disu_upts, e.JGinv_upts,
-                                                                                          e.detjac_upts, e.wall_distance, e.tdisf_upts, e.sgsf_upts, c->phys, Q)));
+                                                                                          e.detjac_upts, e.wall_distance, e.Lu, e.Le, e.tdisf_upts, e.sgsf_upts, c->phys, Q)));
       HF_LAUNCH_CHECK(c);
       return 0;
     }
@@ -1313,6 +1434,26 @@ int hf_dev_eles_op(hf_ctx *c, int ele_type, int op)
     HF_LAUNCH_CHECK(c);
     for (int d = 0; d < nd; d++)
       if (op_apply(c, ell1(e.over_int_filter), e.tdisf_cub + d * NC * nfl, 0, e.tdisf_upts + d * NU * nfl, ncols, false)) return 1;
+    return 0;
+  }
+  case HF_CALC_SGS_TERMS:
+  {
+    if (!c->prm.LES || c->prm.SGS_model < 2) HF_FAIL("calc_sgs_terms called without a filter-based SGS model");
+    if (op_apply(c, ell1(e.filter_upts), e.disu_upts[0], 0, e.disuf_upts, ncols, false)) return 1;
+    if (c->prm.SGS_model == 3)
+    {
+      // SVV: the filtered solution replaces the solution
+      HF_CUDA(cudaMemcpyAsync(e.disu_upts[0], e.disuf_upts, NU * nfl * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+      c->ufpts_valid = false;
+      return 0;
+    }
+    const long long dim3 = nd == 2 ? 3 : 6;
+    HF_DISPATCH(nd, nfl, (k_sgs_products<ND, NF><<<hf_blocks(NU, 128), 128, 0, c->stream>>>((long long)NU, e.disu_upts[0], e.uu, e.ue)));
+    HF_LAUNCH_CHECK(c);
+    if (op_apply(c, ell1(e.filter_upts), e.uu, 0, e.Lu, (long long)e.n_eles * dim3, false)) return 1;
+    if (op_apply(c, ell1(e.filter_upts), e.ue, 0, e.Le, (long long)e.n_eles * nd, false)) return 1;
+    HF_DISPATCH(nd, nfl, (k_sgs_leonard<ND, NF><<<hf_blocks(NU, 128), 128, 0, c->stream>>>((long long)NU, e.disuf_upts, e.Lu, e.Le)));
+    HF_LAUNCH_CHECK(c);
     return 0;
   }
   case HF_EXTRAPOLATE_SGSFLUX:
@@ -1416,7 +1557,7 @@ int hf_dev_mpi_inters_op(hf_ctx *c, int inter_type, int op)
 }
 
 // ---- CalcResidual / AdvanceSolution --------------------------------------------------------------------------------------
-static int staged_residual(hf_ctx *c, double time)
+static int staged_residual(hf_ctx *c, double time, int rk_stage)
 {
   const bool visc = c->prm.viscous != 0;
   const bool par = c->nproc > 1;
@@ -1424,6 +1565,8 @@ static int staged_residual(hf_ctx *c, double time)
 #define EACH_INT(OP) for (int t = 0; t < HF_N_INTER_TYPES; t++) if (hf_dev_int_inters_op(c, t, OP)) return 1
 #define EACH_BDY(OP) for (int t = 0; t < HF_N_INTER_TYPES; t++) if (hf_dev_bdy_inters_op(c, t, OP, time)) return 1
 #define EACH_MPI(OP) for (int t = 0; t < HF_N_INTER_TYPES; t++) if (hf_dev_mpi_inters_op(c, t, OP)) return 1
+  // first RK stage of a step: filtered solution, Leonard tensors (reference src/solver.cpp:54-62)
+  if (c->prm.LES && c->prm.SGS_model >= 2 && (rk_stage & 0xff) == 0) EACH_ELE(HF_CALC_SGS_TERMS);
   EACH_ELE(HF_EXTRAPOLATE_SOLUTION);
   if (par) EACH_MPI(2);
   if (visc) EACH_ELE(HF_CALCULATE_GRADIENT);
@@ -1454,7 +1597,7 @@ int hf_dev_calc_residual(hf_ctx *c, int rk_stage, double time)
 {
   if (!c->finalized) HF_FAIL("hf_dev_finalize_setup has not been called");
   if (c->fused && hf_fused_available(c)) return hf_fused_stage(c, rk_stage, time, 1, 0);
-  return staged_residual(c, time);
+  return staged_residual(c, time, rk_stage);
 }
 
 static int advance_one(hf_ctx *c, hf_eles_dev &e, int stage)
@@ -1515,7 +1658,7 @@ int hf_dev_rk_stage(hf_ctx *c, int rk_stage, double time, int keep_residual)
   }
   else
   {
-    if (staged_residual(c, time)) return 1;
+    if (staged_residual(c, time, rk_stage)) return 1;
     if (hf_dev_advance_solution(c, rk_stage)) return 1;
   }
   // shock capturing follows the update of every stage (reference src/HiFiLES.cpp:213-217)
@@ -1596,6 +1739,9 @@ static int locate_array(hf_ctx *c, hf_eles_dev &e, int which, double **p, size_t
   case HF_SENSOR: *p = e.sensor; *n = e.n_eles; break;
   case HF_SGSF_UPTS: *p = e.sgsf_upts; *n = NU * F * D; break;
   case HF_SGSF_FPTS: *p = e.sgsf_fpts; *n = NFP * F * D; break;
+  case HF_DISUF_UPTS: *p = e.disuf_upts; *n = NU * F; break;
+  case HF_LU: *p = e.Lu; *n = NU * (D == 2 ? 3 : 6); break;
+  case HF_LE: *p = e.Le; *n = NU * D; break;
   default: HF_FAIL("unknown array id");
   }
   (void)c;

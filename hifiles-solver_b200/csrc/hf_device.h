@@ -55,6 +55,8 @@ struct hf_eles_dev
   // LES
   double *sgsf_upts = nullptr, *sgsf_fpts = nullptr, *wall_distance = nullptr, *Jacobian_fpts = nullptr;
   double ele_vol_factor = 0.;
+  hf_ell filter_upts;
+  double *disuf_upts = nullptr, *uu = nullptr, *ue = nullptr, *Lu = nullptr, *Le = nullptr;
   // shock capturing (dense, row-major access by mode)
   double *inv_vandermonde = nullptr, *exp_filter = nullptr, *sensor_w_top = nullptr, *sensor_w_all = nullptr, *sensor = nullptr;
   double *detjac_upts = nullptr, *JGinv_upts = nullptr, *detjac_fpts = nullptr, *JGinv_fpts = nullptr;

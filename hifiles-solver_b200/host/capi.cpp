@@ -258,6 +258,7 @@ int hifiles_get_array(void *handle, const char *name, const void **ptr, int *dty
       if (arr == "JGinv_over_int_cubpts") return set_d(e->JGinv_over_int_cubpts);
       if (arr == "exp_filter") return set_d(e->exp_filter);
       if (arr == "wall_distance") return set_d(e->wall_distance);
+      if (arr == "filter_upts") return set_d(e->filter_upts);
       if (arr == "shape") return set_d(e->shape);
       if (arr == "n_spts_per_ele") return set_i(e->n_spts_per_ele);
       if (arr == "ele2global_ele") return set_i(e->ele2global_ele);

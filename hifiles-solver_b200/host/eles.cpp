@@ -36,6 +36,7 @@ void eles::setup(int in_n_eles, int in_max_n_spts_per_ele)
   setup_ele_type_specific();
   if (run_input.over_int) set_over_int();
   if (run_input.shock_cap) set_shock_capture();
+  if (run_input.LES && viscous && (run_input.SGS_model == 2 || run_input.SGS_model == 3 || run_input.SGS_model == 4)) compute_filter_upts();
 
   if (run_input.adv_type == 0) n_adv_levels = 1;
   else if (run_input.adv_type >= 1 && run_input.adv_type <= 4) n_adv_levels = 2;
@@ -567,6 +568,7 @@ void eles::mv_all_cpu_gpu()
     d.ele_vol_factor = vol_factor[ele_type];
     d.Jacobian_fpts = Jacobian_fpts.get_ptr_cpu();
     d.wall_distance = wall_distance.size() ? wall_distance.get_ptr_cpu() : nullptr;
+    d.filter_upts = filter_upts.size() ? filter_upts.get_ptr_cpu() : nullptr;
   }
   if (run_input.shock_cap)
   {
@@ -609,6 +611,7 @@ void eles::extrapolate_solution() { if (n_eles) hf_check(hf_dev_eles_op(ctx, ele
 void eles::calculate_gradient() { if (n_eles) hf_check(hf_dev_eles_op(ctx, ele_type, HF_CALCULATE_GRADIENT)); }
 void eles::evaluate_invFlux() { if (n_eles) hf_check(hf_dev_eles_op(ctx, ele_type, HF_EVALUATE_INVFLUX)); }
 void eles::evaluate_invFlux_over_int() { if (n_eles) hf_check(hf_dev_eles_op(ctx, ele_type, HF_EVALUATE_INVFLUX_OVER_INT)); }
+void eles::calc_sgs_terms() { if (n_eles) hf_check(hf_dev_eles_op(ctx, ele_type, HF_CALC_SGS_TERMS)); }
 void eles::extrapolate_sgsFlux() { if (n_eles) hf_check(hf_dev_eles_op(ctx, ele_type, HF_EXTRAPOLATE_SGSFLUX)); }
 void eles::shock_capture() { if (n_eles) hf_check(hf_dev_eles_op(ctx, ele_type, HF_SHOCK_CAPTURE)); }
 void eles::cp_sensor_gpu_cpu() { if (n_eles && run_input.shock_cap) hf_check(hf_dev_download(ctx, ele_type, HF_SENSOR, sensor.get_ptr_cpu(), sensor.size())); }

@@ -262,6 +262,8 @@ public:
   void evaluate_invFlux_over_int();
   void shock_capture();
   void extrapolate_sgsFlux();
+  void calc_sgs_terms();
+  void compute_filter_upts();
   /*! distance vector of every solution point to the nearest no-slip wall flux point, brute force (reference src/eles.cpp:2698-2813) */
   void calc_wall_distance(std::vector<hf_array<double>> &loc_noslip_bdy);
   void cp_sensor_gpu_cpu();
@@ -342,7 +344,7 @@ public:
   hf_array<double> modal_vandermonde, modal_inv_vandermonde;
   hf_array<double> loc_over_int_cubpts, weight_over_int_cubpts, opp_over_int_cubpts, over_int_filter, JGinv_over_int_cubpts;
   hf_array<double> sensor_w_top, sensor_w_all, exp_filter, sensor;
-  hf_array<double> wall_distance, Jacobian_fpts;
+  hf_array<double> wall_distance, Jacobian_fpts, filter_upts;
 };
 
 class eles_hexas : public eles

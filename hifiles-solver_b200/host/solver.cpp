@@ -127,8 +127,9 @@ void InitSolution(struct solution *FlowSol)
 void CalcResidual(int in_file_num, int in_rk_stage, struct solution *FlowSol)
 {
   (void)in_file_num;
-  (void)in_rk_stage;
   int n = FlowSol->n_ele_types;
+  if (run_input.LES == 1 && in_rk_stage == 0 && (run_input.SGS_model == 2 || run_input.SGS_model == 3 || run_input.SGS_model == 4))
+    for (int i = 0; i < n; i++) FlowSol->mesh_eles(i)->calc_sgs_terms();
   for (int i = 0; i < n; i++) FlowSol->mesh_eles(i)->extrapolate_solution();
   if (FlowSol->nproc > 1)
     for (int i = 0; i < FlowSol->n_mpi_inter_types; i++) FlowSol->mesh_mpi_inters[i].send_solution();

@@ -55,7 +55,7 @@ typedef struct hf_params
   double s0;                  /* sensor threshold */
   /* large-eddy simulation (reference src/eles.cpp:2395-2646): sub-grid-scale flux added to the viscous flux */
   int LES;                    /* 1: on */
-  int SGS_model;              /* 0 Smagorinsky (with wall damping), 1 WALE */
+  int SGS_model;              /* 0 Smagorinsky (with wall damping), 1 WALE, 2 WALE-similarity, 3 SVV, 4 similarity */
   double C_s, Kappa, prandtl_t, filter_ratio;
 } hf_params;
 
@@ -95,6 +95,7 @@ typedef struct hf_eles_desc
   const double *wall_distance;         /* (upt,ele,dim) vector to the nearest no-slip wall point (1e20 without walls); Smagorinsky */
   const double *Jacobian_fpts;         /* (a,b,fpt,ele) dx_a/dxi_b at the flux points: takes the SGS flux back to physical space */
   double ele_vol_factor;               /* reference-element volume: element volume = detjac * factor (<type>::calc_ele_vol) */
+  const double *filter_upts;           /* [n_upts x n_upts] LES test filter (SGS models 2, 3, 4), <type>::compute_filter_upts */
 } hf_eles_desc;
 
 /* Interior interfaces of one face type (mirror of int_inters::set_interior, reference src/int_inters.cpp:67-121).
@@ -142,7 +143,8 @@ enum hf_array_id
   HF_DISU_UPTS0 = 0, HF_DISU_UPTS1 = 1, HF_DIV_TCONF_UPTS = 2, HF_DISU_FPTS = 3, HF_TDISF_UPTS = 4,
   HF_NORM_TDISF_FPTS = 5, HF_NORM_TCONF_FPTS = 6, HF_DELTA_DISU_FPTS = 7, HF_GRAD_DISU_UPTS = 8,
   HF_GRAD_DISU_FPTS = 9, HF_SRC_UPTS = 10, HF_DT_LOCAL = 11, HF_SENSOR = 12, /* (ele) Persson sensor of the last shock_capture */
-  HF_SGSF_UPTS = 13, HF_SGSF_FPTS = 14 /* (pt,ele,field,dim) sub-grid-scale flux, LES runs */
+  HF_SGSF_UPTS = 13, HF_SGSF_FPTS = 14, /* (pt,ele,field,dim) sub-grid-scale flux, LES runs */
+  HF_DISUF_UPTS = 15, HF_LU = 16, HF_LE = 17 /* filtered solution (upt,ele,field), Leonard tensors (upt,ele,3|6) and (upt,ele,dim) */
 };
 
 /* element operations = the eles methods CalcResidual calls (reference src/solver.cpp:65-216) */
@@ -158,7 +160,8 @@ enum hf_eles_op
   HF_CALCULATE_CORRECTED_DIVERGENCE = 7, /* eles::calculate_corrected_divergence reference src/eles.cpp:1738 */
   HF_EVALUATE_INVFLUX_OVER_INT = 8,  /* eles::evaluate_invFlux_over_int     reference src/eles.cpp:1480 */
   HF_SHOCK_CAPTURE = 9,              /* eles::shock_capture                 reference src/eles.cpp:2918 */
-  HF_EXTRAPOLATE_SGSFLUX = 10        /* eles::extrapolate_sgsFlux           reference src/eles.cpp:2817 */
+  HF_EXTRAPOLATE_SGSFLUX = 10,       /* eles::extrapolate_sgsFlux           reference src/eles.cpp:2817 */
+  HF_CALC_SGS_TERMS = 11             /* eles::calc_sgs_terms (first RK stage) reference src/eles.cpp:2058 */
 };
 enum hf_inters_op
 {

@@ -171,6 +171,7 @@ static void dump_setup(struct solution *S)
     }
     if (run_input.shock_cap) put(p + "exp_filter", e->exp_filter);
     if (run_input.LES && run_input.SGS_model == 0) put(p + "wall_distance", e->wall_distance);
+    if (run_input.LES && run_input.SGS_model >= 2) put(p + "filter_upts", e->filter_upts);
   }
   const char *iname[3] = {"seg", "tri", "quad"};
   for (int t = 0; t < S->n_int_inter_types; t++)
@@ -265,9 +266,18 @@ static void calc_residual_stagewise(struct solution *S, const string &tag)
       else if (arr == "norm_tdisf_fpts") put(p, e->norm_tdisf_fpts);
       else if (arr == "div_tconf_upts") put(p, e->div_tconf_upts(0));
       else if (arr == "sgsf_upts") put(p, e->sgsf_upts);
+      else if (arr == "disuf_upts") put(p, e->disuf_upts);
+      else if (arr == "Lu") put(p, e->Lu);
+      else if (arr == "Le") put(p, e->Le);
       else if (arr == "sgsf_fpts") put(p, e->sgsf_fpts);
     }
   };
+  if (run_input.LES == 1 && (run_input.SGS_model == 2 || run_input.SGS_model == 3 || run_input.SGS_model == 4))
+  {
+    for (int i = 0; i < n; i++) S->mesh_eles(i)->calc_sgs_terms();
+    dump1("s01_calc_sgs_terms", "disuf_upts");
+    if (run_input.SGS_model != 3) { dump1("s01_calc_sgs_terms", "Lu"); dump1("s01_calc_sgs_terms", "Le"); }
+  }
   for (int i = 0; i < n; i++) S->mesh_eles(i)->extrapolate_solution();
   dump1("s02_extrapolate_solution", "disu_fpts");
   if (run_input.viscous)
@@ -344,6 +354,21 @@ int main(int argc, char *argv[])
   }
   delete mesh_data;
   InitSolution(&FlowSol);
+  // Accommodation for a reference defect: eles::calc_sgs_terms filters the velocity-energy products with the column
+  // count of the velocity-velocity products (dim3*n_eles instead of n_dims*n_eles, src/eles.cpp:2164, 2170), writing
+  // past the end of Le (heap corruption, the stock binary aborts at exit).  The first n_dims slices it computes are
+  // correct; give ue / Le the larger extent so that the overrun lands in owned memory.
+  if (run_input.LES && (run_input.SGS_model == 2 || run_input.SGS_model == 4))
+    for (int t = 0; t < FlowSol.n_ele_types; t++)
+    {
+      eles *e = FlowSol.mesh_eles(t);
+      if (e->get_n_eles() == 0) continue;
+      int dim3 = e->n_dims == 2 ? 3 : 6;
+      e->ue.setup(e->n_upts_per_ele, e->n_eles, dim3);
+      e->Le.setup(e->n_upts_per_ele, e->n_eles, dim3);
+      e->ue.initialize_to_zero();
+      e->Le.initialize_to_zero();
+    }
   dump_setup(&FlowSol);
 
   int RKSteps = 1;

@@ -86,6 +86,14 @@ CASES = {
                                                      bc_In_type="char", bc_In_p_static=100747., bc_In_mach=0.3, bc_In_T_static=300., bc_In_nx=1., bc_In_ny=0.,
                                                      bc_Out_type="sub_out_simp", bc_Out_p_static=100000., bc_Wall_type="isotherm_wall", bc_Wall_T_static=310.,
                                                      bc_Top_type="adiabat_wall", bc_Top_u=20., LES=1, SGS_model=0, C_s=0.1, filter_ratio=2.0)),
+    # filter-based models: WALE-similarity (2), spectral vanishing viscosity (3), similarity (4); eles::calc_sgs_terms at the first stage
+    "hex_p3_les_wsm_vasilyev": ("hex", 3, dict(warp=0.1), dict(order=3, adv_type=2, riemann_solve_type=3, viscous=1, dt=1e-5, LES=1, SGS_model=2, C_s=0.325,
+                                                            filter_ratio=2.0, filter_type=0)),
+    "mixed_tri_quad_p3_les_similarity_gaussian": ("mixed", 4, dict(lengths=(6.2831853071795862,) * 2, origin=(0., 0.)),
+                                                  dict(order=3, adv_type=3, riemann_solve_type=0, viscous=1, dt=2e-5, dz_cyclic=None, LES=1, SGS_model=4, C_s=0.3,
+                                                       filter_ratio=2.0, filter_type=1)),
+    "tet_p2_les_svv_modal": ("tet", 2, {}, dict(order=2, adv_type=2, riemann_solve_type=2, viscous=1, dt=1e-5, LES=1, SGS_model=3, C_s=0.3, filter_ratio=2.0,
+                                                filter_type=2)),
     "hexpri_p2_les_smagorinsky_periodic": ("hexpri", (2, 2, 4), {}, dict(order=2, adv_type=2, riemann_solve_type=3, viscous=1, dt=2e-5, LES=1, SGS_model=0,
                                                                        C_s=0.1, filter_ratio=2.0)),
     # Persson sensor + exponential modal filter after every stage (eles::shock_capture, reference src/eles.cpp:2918-2959): BASELINE config 5;
@@ -155,6 +163,15 @@ def test_methods_one_by_one(tmp_path, hb, meshgen, name):
             for t in types:
                 check(key + "." + t + "." + arr, run.download(t, arr), ref[pre + key + "." + t + "." + arr], tol)
 
+        if CASES[name][3].get("LES") and CASES[name][3]["SGS_model"] >= 2:
+            each("calc_sgs_terms", "disuf_upts", "s01_calc_sgs_terms")
+            if CASES[name][3]["SGS_model"] != 3:
+                for t in types:
+                    nd = run.download(t, "Le").shape[2]
+                    key = pre + "s01_calc_sgs_terms." + t
+                    # the Leonard tensors are differences of nearly equal products: judged against the products' scale
+                    check("Lu " + t, run.download(t, "Lu"), ref[key + ".Lu"], 1e-13, scale_by=np.ones(1))
+                    check("Le " + t, run.download(t, "Le"), ref[key + ".Le"][:, :, :nd], 1e-13, scale_by=np.abs(ref[key + ".Le"][:, :, :nd]).max() + np.ones(1))
         each("extrapolate_solution", "disu_fpts", "s02_extrapolate_solution")
         if visc:
             each("calculate_gradient", "grad_disu_upts", "s04_calculate_gradient")
