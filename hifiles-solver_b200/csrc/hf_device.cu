@@ -677,7 +677,8 @@ __global__ void k_mpi_invflux(hf_views W, int n_pairs, int nf, const int *__rest
 
 template <int ND, int NF>
 __global__ void k_mpi_viscflux(hf_views W, int n_pairs, int nf, const int *__restrict__ idx_l, const int8_t *__restrict__ type_l,
-                               const int *__restrict__ lut, const double *__restrict__ in_disu, const double *__restrict__ in_grad, hf_phys P)
+                               const int *__restrict__ lut, const double *__restrict__ in_disu, const double *__restrict__ in_grad,
+                               const double *__restrict__ in_sgsf, hf_phys P)
 {
   int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= n_pairs) return;
@@ -695,6 +696,14 @@ __global__ void k_mpi_viscflux(hf_views W, int n_pairs, int nf, const int *__res
 #pragma unroll
     for (int k = 0; k < NF; k++) g[k + NF * d] = in_grad[lut[t] + (size_t)nf * (k + NF * (d + ND * (size_t)i))];
   vis_flux<ND, NF>(u_r, g, f_r, P);
+  if (in_sgsf) // LES: physical SGS flux of both sides (reference src/mpi_inters.cpp, calculate_common_viscFlux)
+  {
+    add_sgsf_fpt<ND, NF>(L, il, f_l);
+#pragma unroll
+    for (int d = 0; d < ND; d++)
+#pragma unroll
+      for (int k = 0; k < NF; k++) f_r[k + NF * d] += in_sgsf[lut[t] + (size_t)nf * (k + NF * (d + ND * (size_t)i))];
+  }
   load_norm<ND>(L, il, n);
   double beta = ldg_switched_beta<ND>(P.ldg_beta, n);
   ldg_flux<ND, NF>(0, u_l, u_r, f_l, f_r, n, fn, beta, P.ldg_tau);
@@ -723,6 +732,17 @@ __global__ void k_pack_grad(hf_views W, int n_pairs, int nf, int NF, int ND, con
   size_t sl = (size_t)L.n_fpts * L.n_eles;
   for (int d = 0; d < ND; d++)
     for (int k = 0; k < NF; k++) out[j + (size_t)nf * (k + NF * (d + ND * (size_t)i))] = L.grad_disu_fpts[idx_l[t] + (k + NF * d) * sl];
+}
+// the same message layout for the physical SGS flux (mpi_inters::send_sgsf_fpts)
+__global__ void k_pack_sgsf(hf_views W, int n_pairs, int nf, int NF, int ND, const int *__restrict__ idx_l, const int8_t *__restrict__ type_l, double *__restrict__ out)
+{
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_pairs) return;
+  int i = t / nf, j = t - i * nf;
+  const hf_ele_view &L = W.v[type_l[i]];
+  size_t sl = (size_t)L.n_fpts * L.n_eles;
+  for (int d = 0; d < ND; d++)
+    for (int k = 0; k < NF; k++) out[j + (size_t)nf * (k + NF * (d + ND * (size_t)i))] = L.sgsf_fpts[idx_l[t] + (k + NF * d) * sl];
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -955,6 +975,8 @@ int hf_dev_destroy(hf_ctx *c)
   hf_halo_destroy(c);
   hf_fused_destroy(c);
   for (void *p : c->allocs) cudaFree(p);
+  for (int t = 0; t < HF_N_ELE_TYPES; t++)
+    if (c->eles[t].d_stage) cudaFree(c->eles[t].d_stage);
   for (cudaEvent_t ev : c->kt_ev) cudaEventDestroy(ev);
   if (c->ev_a) cudaEventDestroy(c->ev_a);
   if (c->ev_b) cudaEventDestroy(c->ev_b);
@@ -987,7 +1009,7 @@ int hf_dev_set_params(hf_ctx *c, const hf_params *p)
   P.gamma_over_pr = p->gamma / p->prandtl;
   if (p->shock_cap && p->shock_cap != 1) HF_FAIL("Shock capturing method not implemented.");
   if (p->LES && (p->SGS_model < 0 || p->SGS_model > 4)) HF_FAIL("SGS model not implemented");
-  if (p->LES && c->nproc > 1) HF_FAIL("LES on several GPUs is not built yet (the SGS-flux halo exchange of mpi_inters::send_sgsf_fpts)");
+  if (p->LES && p->SGS_model == 0 && c->nproc > 1) HF_FAIL("the Smagorinsky model on several GPUs is not built yet (its wall distance needs the wall points of every rank)");
   if (p->equation == 0 && !(p->riemann_solve_type == 0 || p->riemann_solve_type == 2 || p->riemann_solve_type == 3))
     HF_FAIL("Riemann solver not implemented");
   if (p->viscous && p->vis_riemann_solve_type != 0) HF_FAIL("Viscous Riemann solver not implemented");
@@ -1007,6 +1029,37 @@ static std::vector<double> permute_eles(const double *src, size_t pre, int n_ele
       else memcpy(&out[host_off], src + dev_off, pre * sizeof(double));
     }
   return out;
+}
+
+// the same permutation on the device, for uploads / downloads of whole arrays (one thread per double)
+__global__ void k_permute_eles(const double *__restrict__ src, double *__restrict__ dst, long long pre, int n_eles, long long n, const int *__restrict__ pos,
+                               int to_device)
+{
+  long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (idx >= n) return;
+  const long long a = idx % pre, r = idx / pre;
+  const int e = (int)(r % n_eles);
+  const long long b = r / n_eles;
+  const long long other = a + pre * (pos[e] + (long long)n_eles * b); // idx is in host order, other in device order
+  if (to_device) dst[other] = src[idx];
+  else dst[idx] = src[other];
+}
+static int permute_on_device(hf_ctx *c, hf_eles_dev &e, const double *src, double *dst, size_t pre, size_t n, bool to_device)
+{
+  if (!e.d_pos && hf_alloc_copy(c, &e.d_pos, e.pos.data(), e.pos.size())) return 1;
+  k_permute_eles<<<hf_blocks((long long)n, 256), 256, 0, c->stream>>>(src, dst, (long long)pre, e.n_eles, (long long)n, e.d_pos, to_device ? 1 : 0);
+  HF_LAUNCH_CHECK(c);
+  return 0;
+}
+static int ensure_stage(hf_ctx *c, hf_eles_dev &e, size_t n)
+{
+  if (e.stage_n >= n) return 0;
+  if (e.d_stage) cudaFree(e.d_stage);
+  e.d_stage = nullptr;
+  cudaError_t err = cudaMalloc((void **)&e.d_stage, n * sizeof(double));
+  if (err != cudaSuccess) { hf_set_error(std::string("cudaMalloc (transfer staging): ") + cudaGetErrorString(err)); return 1; }
+  e.stage_n = n;
+  return 0;
 }
 
 int hf_dev_set_element_order(hf_ctx *c, int ele_type, int n_eles, const int *pos)
@@ -1314,6 +1367,7 @@ int hf_dev_upload_mpi_inters(hf_ctx *c, const hf_mpi_inters_desc *d)
   {
     if (hf_alloc_zero(c, &I.out_grad, nb * nd)) return 1;
     if (hf_alloc_zero(c, &I.in_grad, nb * nd)) return 1;
+    if (c->prm.LES && (hf_alloc_zero(c, &I.out_sgsf, nb * nd) || hf_alloc_zero(c, &I.in_sgsf, nb * nd))) return 1;
   }
   I.h_ele_type_l.assign(d->ele_type_l, d->ele_type_l + ni); I.h_ele_l.assign(d->ele_l, d->ele_l + ni);
   for (int i = 0; i < ni; i++) I.h_ele_l[i] = dev_ele(c->eles[I.h_ele_type_l[i]], I.h_ele_l[i]);
@@ -1536,7 +1590,7 @@ int hf_dev_mpi_inters_op(hf_ctx *c, int inter_type, int op)
     HF_LAUNCH_CHECK(c);
     return 0;
   case HF_COMMON_VISCFLUX:
-    HF_DISPATCH(nd, nfl, (k_mpi_viscflux<ND, NF><<<hf_blocks(n, 128), 128, 0, c->stream>>>(W, n, I.nf, I.idx_l, I.type_l, I.lut, I.in_disu, I.in_grad, c->phys)));
+    HF_DISPATCH(nd, nfl, (k_mpi_viscflux<ND, NF><<<hf_blocks(n, 128), 128, 0, c->stream>>>(W, n, I.nf, I.idx_l, I.type_l, I.lut, I.in_disu, I.in_grad, c->prm.LES ? I.in_sgsf : nullptr, c->phys)));
     HF_LAUNCH_CHECK(c);
     return 0;
   case 2: // send_solution: pack, then post the exchange on the comm stream
@@ -1550,6 +1604,13 @@ int hf_dev_mpi_inters_op(hf_ctx *c, int inter_type, int op)
     HF_LAUNCH_CHECK(c);
     return hf_halo_post(c, I, I.out_grad, I.in_grad, (size_t)I.nf * nfl * nd);
   case 5: // receive_corrected_gradient
+    return hf_halo_wait(c);
+  case 6: // send_sgsf_fpts (LES)
+    if (!c->prm.LES) HF_FAIL("send_sgsf_fpts called without LES");
+    k_pack_sgsf<<<hf_blocks(n, 128), 128, 0, c->stream>>>(W, n, I.nf, nfl, nd, I.idx_l, I.type_l, I.out_sgsf);
+    HF_LAUNCH_CHECK(c);
+    return hf_halo_post(c, I, I.out_sgsf, I.in_sgsf, (size_t)I.nf * nfl * nd);
+  case 7: // receive_sgsf_fpts
     return hf_halo_wait(c);
   default:
     HF_FAIL("unknown partition-interface operation");
@@ -1580,6 +1641,7 @@ static int staged_residual(hf_ctx *c, double time, int rk_stage)
     if (par) EACH_MPI(4);
     EACH_ELE(HF_EVALUATE_VISCFLUX);
     if (c->prm.LES) EACH_ELE(HF_EXTRAPOLATE_SGSFLUX);
+    if (c->prm.LES && par) EACH_MPI(6);
   }
   EACH_ELE(HF_EXTRAPOLATE_TOTALFLUX);
   EACH_ELE(HF_CALCULATE_DIVERGENCE);
@@ -1587,7 +1649,7 @@ static int staged_residual(hf_ctx *c, double time, int rk_stage)
   {
     EACH_INT(HF_COMMON_VISCFLUX);
     EACH_BDY(HF_COMMON_VISCFLUX);
-    if (par) { EACH_MPI(5); EACH_MPI(HF_COMMON_VISCFLUX); }
+    if (par) { EACH_MPI(5); if (c->prm.LES) EACH_MPI(7); EACH_MPI(HF_COMMON_VISCFLUX); }
   }
   EACH_ELE(HF_CALCULATE_CORRECTED_DIVERGENCE);
   return 0;
@@ -1771,14 +1833,14 @@ int hf_dev_download(hf_ctx *c, int ele_type, int which, double *host, size_t n_d
   // the fused path keeps face values in its own per-face layout: materialise the reference-layout array on request
   if (which == HF_DISU_FPTS && c->fused && hf_fused_available(c) &&
       op_apply(c, ell1(e.opp_0), e.disu_upts[0], 0, e.disu_fpts, (long long)e.n_eles * e.n_fields, false)) return 1;
-  HF_CUDA(cudaMemcpyAsync(host, p, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-  HF_CUDA(cudaStreamSynchronize(c->stream));
   if (!e.pos.empty())
   {
-    const size_t pre = pts_per_ele(e, which);
-    std::vector<double> t = permute_eles(host, pre, e.n_eles, n / (pre * e.n_eles), e.pos, false);
-    memcpy(host, t.data(), n * sizeof(double));
+    // device order -> host order in a staging buffer, then one flat copy
+    if (ensure_stage(c, e, n) || permute_on_device(c, e, p, e.d_stage, pts_per_ele(e, which), n, false)) return 1;
+    p = e.d_stage;
   }
+  HF_CUDA(cudaMemcpyAsync(host, p, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  HF_CUDA(cudaStreamSynchronize(c->stream));
   return 0;
 }
 
@@ -1795,14 +1857,15 @@ int hf_dev_upload(hf_ctx *c, int ele_type, int which, const double *host, size_t
     if (ensure_staged_buffers(c, e) || locate_array(c, e, which, &p, &n)) return 1;
     if (!p) HF_FAIL("upload: array is not materialised on the device");
   }
-  std::vector<double> t;
   if (!e.pos.empty())
   {
-    const size_t pre = pts_per_ele(e, which);
-    t = permute_eles(host, pre, e.n_eles, n / (pre * e.n_eles), e.pos, true);
-    host = t.data();
+    // flat copy into a staging buffer, then host order -> device order on the device
+    if (ensure_stage(c, e, n)) return 1;
+    HF_CUDA(cudaMemcpyAsync(e.d_stage, host, n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    if (permute_on_device(c, e, e.d_stage, p, pts_per_ele(e, which), n, true)) return 1;
   }
-  HF_CUDA(cudaMemcpyAsync(p, host, n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  else
+    HF_CUDA(cudaMemcpyAsync(p, host, n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
   HF_CUDA(cudaStreamSynchronize(c->stream));
   c->ufpts_valid = false;
   return 0;

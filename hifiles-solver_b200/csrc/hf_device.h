@@ -79,6 +79,9 @@ struct hf_eles_dev
   std::vector<double> h_face_geo;  // per (ele, face): tdA, unit normal[3] at the face's first flux point
   std::vector<int8_t> h_own_sign;  // (fpt,ele): sign of ldg_beta if this element is the left side of the face
   double affine_defect = 0.;       // max relative variation of the metrics inside an element
+  int *d_pos = nullptr;            // pos on the device
+  double *d_stage = nullptr;       // staging buffer of permuted uploads / downloads
+  size_t stage_n = 0;
   std::vector<int> pos;            // device element order: slot pos[e] holds host element e (empty = identity), hf_dev_set_element_order
 };
 
@@ -110,6 +113,7 @@ struct hf_mpi_inters_dev
   std::vector<int> nb_rank, nb_count;
   double *out_disu = nullptr, *in_disu = nullptr;   // [inter][field][fpt]
   double *out_grad = nullptr, *in_grad = nullptr;   // [inter][dim][field][fpt]
+  double *out_sgsf = nullptr, *in_sgsf = nullptr;   // [inter][dim][field][fpt], LES
   std::vector<int> h_ele_type_l, h_ele_l, h_loc_l, h_rot;
 };
 

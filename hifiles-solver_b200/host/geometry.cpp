@@ -497,7 +497,7 @@ void GeoPreprocess(struct solution *FlowSol, mesh &mesh_data)
   // isothermal / adiabatic wall face, per face type, in mesh-face order
   if (run_input.LES && run_input.SGS_model == 0)
   {
-    if (FlowSol->nproc > 1) FatalError("LES on several GPUs is not built yet");
+    if (FlowSol->nproc > 1) FatalError("the Smagorinsky model on several GPUs is not built yet (its wall distance needs the wall points of every rank)");
     vector<hf_array<double>> loc_noslip_bdy(3);
     for (int t = 0; t < 3; t++)
     {

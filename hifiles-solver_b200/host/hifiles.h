@@ -483,6 +483,8 @@ public:
   void receive_solution();
   void send_corrected_gradient();
   void receive_corrected_gradient();
+  void send_sgsf_fpts();
+  void receive_sgsf_fpts();
   void calculate_common_invFlux();
   void calculate_common_viscFlux();
   int nproc, rank;

@@ -205,5 +205,7 @@ void mpi_inters::send_solution() { if (n_inters) hf_check(hf_dev_mpi_inters_op(c
 void mpi_inters::receive_solution() { if (n_inters) hf_check(hf_dev_mpi_inters_op(ctx, inters_type, 3)); }
 void mpi_inters::send_corrected_gradient() { if (n_inters) hf_check(hf_dev_mpi_inters_op(ctx, inters_type, 4)); }
 void mpi_inters::receive_corrected_gradient() { if (n_inters) hf_check(hf_dev_mpi_inters_op(ctx, inters_type, 5)); }
+void mpi_inters::send_sgsf_fpts() { if (n_inters) hf_check(hf_dev_mpi_inters_op(ctx, inters_type, 6)); }
+void mpi_inters::receive_sgsf_fpts() { if (n_inters) hf_check(hf_dev_mpi_inters_op(ctx, inters_type, 7)); }
 void mpi_inters::calculate_common_invFlux() { if (n_inters) hf_check(hf_dev_mpi_inters_op(ctx, inters_type, HF_COMMON_INVFLUX)); }
 void mpi_inters::calculate_common_viscFlux() { if (n_inters) hf_check(hf_dev_mpi_inters_op(ctx, inters_type, HF_COMMON_VISCFLUX)); }

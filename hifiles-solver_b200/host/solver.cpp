@@ -151,7 +151,11 @@ void CalcResidual(int in_file_num, int in_rk_stage, struct solution *FlowSol)
       for (int i = 0; i < FlowSol->n_mpi_inter_types; i++) FlowSol->mesh_mpi_inters[i].send_corrected_gradient();
     for (int i = 0; i < n; i++) FlowSol->mesh_eles(i)->evaluate_viscFlux();
     if (run_input.LES)
+    {
       for (int i = 0; i < n; i++) FlowSol->mesh_eles(i)->extrapolate_sgsFlux();
+      if (FlowSol->nproc > 1)
+        for (int i = 0; i < FlowSol->n_mpi_inter_types; i++) FlowSol->mesh_mpi_inters[i].send_sgsf_fpts();
+    }
   }
   for (int i = 0; i < n; i++) FlowSol->mesh_eles(i)->extrapolate_totalFlux();
   for (int i = 0; i < n; i++) FlowSol->mesh_eles(i)->calculate_divergence();
@@ -162,6 +166,8 @@ void CalcResidual(int in_file_num, int in_rk_stage, struct solution *FlowSol)
     if (FlowSol->nproc > 1)
     {
       for (int i = 0; i < FlowSol->n_mpi_inter_types; i++) FlowSol->mesh_mpi_inters[i].receive_corrected_gradient();
+      if (run_input.LES)
+        for (int i = 0; i < FlowSol->n_mpi_inter_types; i++) FlowSol->mesh_mpi_inters[i].receive_sgsf_fpts();
       for (int i = 0; i < FlowSol->n_mpi_inter_types; i++) FlowSol->mesh_mpi_inters[i].calculate_common_viscFlux();
     }
   }

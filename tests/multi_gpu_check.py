@@ -95,7 +95,8 @@ def general(hb, mg, dist, rank, world, work, kind, n, order, steps):
             mg.write_input(inp, "m.neu", order=order, adv_type=2, dt=1e-5, riemann_solve_type=0, viscous=1, dz_cyclic=None)
         else:
             info = mg.mixed_box_3d(mesh, n, kind=kind)
-            mg.write_input(inp, "m.neu", order=order, adv_type=2, dt=1e-5, riemann_solve_type=2, viscous=1)
+            les = dict(LES=1, SGS_model=int(os.environ["HF_CHECK_LES"]), C_s=0.3, filter_ratio=2.0, filter_type=2) if os.environ.get("HF_CHECK_LES") else {}
+            mg.write_input(inp, "m.neu", order=order, adv_type=2, dt=1e-5, riemann_solve_type=2, viscous=1, **les)
         obj = [mg.slab_partition(info["centroids"], world, axis=1 if kind == "pritet" else 0)]
     dist.broadcast_object_list(obj, src=0)
     part = obj[0]

@@ -30,6 +30,18 @@ def test_two_ranks_match_single_domain(mode):
 
 
 @pytest.mark.gpu
+def test_two_ranks_match_single_domain_les():
+    """LES (WALE-similarity: eddy viscosity + Leonard tensors) on a partitioned tetrahedral mesh: the SGS-flux halo exchange"""
+    if n_gpus() < 2:
+        pytest.skip("needs 2 GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29535", os.path.join(ROOT, "tests", "multi_gpu_check.py"), "3", "2", "2", "staged", "tet"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=dict(os.environ, HF_CHECK_LES="2"))
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "OK" in r.stdout
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("kind,n", [("pritet", "4"), ("hexpri", "4"), ("mixed", "6")])
 def test_two_ranks_match_single_domain_simplex_and_mixed(kind, n):
     """partition faces of every face type (segments, triangles, quadrilaterals) between element types of every kind"""
