@@ -177,6 +177,39 @@ __device__ void set_boundary_conditions(int sol_spec, const hf_bc &B, const doub
     for (int i = 0; i < ND; i++) v_sq += (v_r[i] * v_r[i]);
     e_r = p_l / (gamma - 1.0) + 0.5 * rho_r * v_sq;
   }
+  else if ((bc_flag == HF_ISOTHERM_WALL || bc_flag == HF_ADIABAT_WALL) && B.use_wm)
+  {
+    // wall-modelled no-slip walls (reference src/bdy_inters.cpp:709-760, 800-833): the inviscid and LDG solutions slip,
+    // only the state handed to the wall model (sol_spec 2) sticks
+    T_r = B.T_static;
+    rho_r = rho_l;
+    if (sol_spec == 2)
+    {
+#pragma unroll
+      for (int i = 0; i < ND; i++) v_r[i] = B.velocity[i];
+    }
+    else
+    {
+      vn_l = 0.;
+#pragma unroll
+      for (int i = 0; i < ND; i++) vn_l += v_l[i] * norm[i];
+      if (sol_spec == 0)
+      {
+#pragma unroll
+        for (int i = 0; i < ND; i++) v_r[i] = v_l[i] - 2 * vn_l * norm[i];
+      }
+      else
+      {
+#pragma unroll
+        for (int i = 0; i < ND; i++) v_r[i] = v_l[i] - vn_l * norm[i];
+      }
+    }
+    v_sq = 0.;
+#pragma unroll
+    for (int i = 0; i < ND; i++) v_sq += (v_r[i] * v_r[i]);
+    if (bc_flag == HF_ISOTHERM_WALL && sol_spec == 2) e_r = rho_r * (R_ref / (gamma - 1.0) * T_r) + 0.5 * rho_r * v_sq;
+    else e_r = p_l / (gamma - 1.0) + 0.5 * rho_r * v_sq;
+  }
   else if (bc_flag == HF_ISOTHERM_WALL)
   {
     T_r = B.T_static;
@@ -332,4 +365,81 @@ __device__ void set_boundary_gradients(int bc_flag, const double *u_r, const dou
 #pragma unroll
     for (int i = 0; i < ND; i++) grad_ur[(ND + 1) + NF * i] -= dn * norm[i];
   }
+}
+
+// Wall shear stress and heat flux from the wall model (calc_wall_stress, reference src/wall_model_funcs.cpp:13-118):
+// u_wm = solution at the input point a distance `dist` off the wall, u_w = no-slip wall state; fn = normal viscous flux.
+struct hf_wm
+{
+  int wall_model;
+  double gamma, prandtl, prandtl_t, rt_inf, mu_inf, c_sth, fix_vis, Kappa;
+};
+template <int ND, int NF>
+__device__ void calc_wall_stress(const double *u_wm, const double *u_w, double dist, const double *norm, double *fn, const hf_wm &Q)
+{
+  const double rho_wm = u_wm[0], rho_w = u_w[0];
+  double v_wm_n = 0;
+#pragma unroll
+  for (int i = 0; i < ND; i++) v_wm_n += u_wm[i + 1] / rho_wm * norm[i];
+  double vw[ND], v_wm[ND], v_rel[ND], tw[ND], v_wm_mag = 0, v_rel_mag = 0;
+#pragma unroll
+  for (int i = 0; i < ND; i++)
+  {
+    v_wm[i] = u_wm[i + 1] / rho_wm - norm[i] * v_wm_n;
+    vw[i] = u_w[i + 1] / rho_w;
+    v_rel[i] = v_wm[i] - vw[i];
+    v_rel_mag += v_rel[i] * v_rel[i];
+    v_wm_mag += v_wm[i] * v_wm[i];
+  }
+  v_rel_mag = sqrt(v_rel_mag);
+  double ke_wm = 0., ke_w = 0.;
+#pragma unroll
+  for (int i = 0; i < ND; i++)
+  {
+    const double a = u_wm[i + 1] / rho_wm;
+    ke_wm += 0.5 * (a * a);
+    ke_w += 0.5 * (vw[i] * vw[i]);
+  }
+  const double inte_wm = u_wm[ND + 1] / rho_wm - ke_wm, inte_w = u_w[ND + 1] / rho_w - ke_w;
+  double tw_mag, qw;
+  if (Q.wall_model == 1) // Werner-Wengle
+  {
+    const double rt_ratio = (Q.gamma - 1.0) * inte_wm / (Q.rt_inf);
+    double mu_wm = (Q.mu_inf) * pow(rt_ratio, 1.5) * (1 + (Q.c_sth)) / (rt_ratio + (Q.c_sth));
+    mu_wm = mu_wm + Q.fix_vis * (Q.mu_inf - mu_wm);
+    const double Rey_c = 11.81 * 11.81;
+    const double Rey = rho_wm * v_rel_mag * dist / mu_wm;
+    const double uplus = Rey < Rey_c ? sqrt(Rey) : pow(8.3, 0.875) * pow(Rey, 0.125);
+    const double utau = v_rel_mag / uplus;
+    tw_mag = rho_wm * utau * utau;
+    if (Rey < Rey_c) qw = (inte_w - inte_wm) * Q.gamma * tw_mag / (Q.prandtl * v_rel_mag);
+    else qw = (inte_w - inte_wm) * Q.gamma * tw_mag / (Q.prandtl_t * (v_rel_mag + utau * 11.81 * (Q.prandtl / Q.prandtl_t - 1.0)));
+  }
+  else // compressible wall function with the Van Driest transformation, adiabatic wall (NASA-TM-112910)
+  {
+    const double Bc = sqrt(2 * Q.gamma * inte_w / Q.prandtl_t), C = 5.2;
+    const double ueq = Bc * asin(v_rel_mag / Bc);
+    double utau = 1., dutau;
+    const double rt_ratio = (Q.gamma - 1.0) * inte_w / (Q.rt_inf);
+    double mu_w = (Q.mu_inf) * pow(rt_ratio, 1.5) * (1 + (Q.c_sth)) / (rt_ratio + (Q.c_sth));
+    mu_w = mu_w + Q.fix_vis * (Q.mu_inf - mu_w);
+    int guard = 0;
+    do
+    {
+      dutau = -(utau * (log(rho_w * dist * utau / mu_w) / Q.Kappa + C) - ueq) / (1 / Q.Kappa * (log(rho_w * dist * utau / mu_w) + 1.) + C);
+      utau += dutau;
+    } while (fabs(dutau) > 1.e-6 && ++guard < 10000);
+    tw_mag = rho_w * utau * utau;
+    qw = 0.;
+  }
+#pragma unroll
+  for (int i = 0; i < ND; i++) tw[i] = tw_mag * v_rel[i] / v_rel_mag;
+  double vw_tw = 0.;
+#pragma unroll
+  for (int i = 0; i < ND; i++) vw_tw = vw_tw + vw[i] * tw[i];
+  fn[0] = 0;
+#pragma unroll
+  for (int i = 0; i < ND; i++) fn[i + 1] = tw[i];
+  fn[ND + 1] = -qw + vw_tw;
+  (void)v_wm_mag;
 }

@@ -619,7 +619,8 @@ __global__ void k_bdy_invflux(hf_views W, int n_pairs, int nf, const int *__rest
 
 template <int ND, int NF>
 __global__ void k_bdy_viscflux(hf_views W, int n_pairs, int nf, const int *__restrict__ idx_l, const int8_t *__restrict__ type_l,
-                               const int *__restrict__ bc_id, const hf_bc *__restrict__ bcs, hf_phys P, double R_ref)
+                               const int *__restrict__ bc_id, const hf_bc *__restrict__ bcs, hf_phys P, double R_ref, const int *__restrict__ wm_upt,
+                               const double *__restrict__ wm_dist, hf_wm Q)
 {
   int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= n_pairs) return;
@@ -631,6 +632,24 @@ __global__ void k_bdy_viscflux(hf_views W, int n_pairs, int nf, const int *__res
   double u_l[NF], u_r[NF], g_l[NF * ND], g_r[NF * ND], f_r[NF * ND], n[ND], fn[NF];
   load_fpt<ND, NF>(L, il, u_l);
   load_norm<ND>(L, il, n);
+  if (NF > 1 && B.use_wm && wm_upt && wm_upt[i] >= 0)
+  {
+    // wall-modelled interface (reference src/bdy_inters.cpp:1095-1131): no-slip wall state, stress from the wall model
+    // evaluated with the solution at the element's input point
+#pragma unroll
+    for (int k = 0; k < NF; k++) u_r[k] = 0.;
+    set_boundary_conditions<ND, NF>(2, B, u_l, u_r, n, P.gamma, R_ref);
+    double u_wm[NF];
+    const size_t su = (size_t)L.n_upts * L.n_eles;
+#pragma unroll
+    for (int k = 0; k < NF; k++) u_wm[k] = L.disu_upts[wm_upt[i] + k * su];
+    calc_wall_stress<ND, NF>(u_wm, u_r, wm_dist[i], n, fn, Q);
+    const double tdA = L.tdA_fpts[il];
+    const size_t sl = (size_t)L.n_fpts * L.n_eles;
+#pragma unroll
+    for (int k = 0; k < NF; k++) L.norm_tconf_fpts[il + k * sl] += fn[k] * tdA;
+    return;
+  }
   load_grad_fpt<ND, NF>(L, il, g_l);
 #pragma unroll
   for (int k = 0; k < NF; k++) u_r[k] = 0.;
@@ -893,6 +912,7 @@ hf_views hf_make_views(hf_ctx *c)
     v.delta_disu_fpts = e.delta_disu_fpts;
     v.grad_disu_fpts = e.grad_disu_fpts;
     v.sgsf_fpts = e.sgsf_fpts;
+    v.disu_upts = e.disu_upts[0];
     v.tdA_fpts = e.tdA_fpts;
     v.norm_fpts = e.norm_fpts;
   }
@@ -1331,6 +1351,20 @@ int hf_dev_upload_bdy_inters(hf_ctx *c, const hf_bdy_inters_desc *d)
   for (int i = 0; i < ni; i++) I.h_ele_l[i] = dev_ele(c->eles[I.h_ele_type_l[i]], I.h_ele_l[i]);
   I.h_loc_l.assign(d->local_inter_l, d->local_inter_l + ni);
   I.h_bc_id.assign(d->bc_id, d->bc_id + ni);
+  if (d->wm_upt && d->wm_dist)
+  {
+    // input points of the wall model, translated to the device element order
+    std::vector<int> w(ni, -1);
+    for (int i = 0; i < ni; i++)
+      if (d->wm_upt[i] >= 0)
+      {
+        const hf_eles_dev &L = c->eles[d->ele_type_l[i]];
+        const int ele = d->wm_upt[i] / L.n_upts, upt = d->wm_upt[i] - ele * L.n_upts;
+        w[i] = upt + L.n_upts * dev_ele(L, ele);
+      }
+    if (hf_alloc_copy(c, &I.wm_upt, w.data(), w.size())) return 1;
+    if (hf_alloc_copy(c, &I.wm_dist, d->wm_dist, (size_t)ni)) return 1;
+  }
   return 0;
 }
 
@@ -1567,7 +1601,12 @@ int hf_dev_bdy_inters_op(hf_ctx *c, int inter_type, int op, double time)
   if (op == HF_COMMON_INVFLUX)
     HF_DISPATCH(nd, nfl, (k_bdy_invflux<ND, NF><<<hf_blocks(n, 128), 128, 0, c->stream>>>(W, n, I.nf, I.idx_l, I.type_l, I.bc_id, c->bc_table, c->phys, c->prm.R_ref, c->prm.viscous)));
   else if (op == HF_COMMON_VISCFLUX)
-    HF_DISPATCH(nd, nfl, (k_bdy_viscflux<ND, NF><<<hf_blocks(n, 128), 128, 0, c->stream>>>(W, n, I.nf, I.idx_l, I.type_l, I.bc_id, c->bc_table, c->phys, c->prm.R_ref)));
+  {
+    hf_wm wmq;
+    wmq.wall_model = c->prm.wall_model; wmq.gamma = c->prm.gamma; wmq.prandtl = c->prm.prandtl; wmq.prandtl_t = c->prm.prandtl_t; wmq.rt_inf = c->prm.rt_inf;
+    wmq.mu_inf = c->prm.mu_inf; wmq.c_sth = c->prm.c_sth; wmq.fix_vis = (double)c->prm.fix_vis; wmq.Kappa = c->prm.Kappa;
+    HF_DISPATCH(nd, nfl, (k_bdy_viscflux<ND, NF><<<hf_blocks(n, 128), 128, 0, c->stream>>>(W, n, I.nf, I.idx_l, I.type_l, I.bc_id, c->bc_table, c->phys, c->prm.R_ref, I.wm_upt, I.wm_dist, wmq)));
+  }
   else
     HF_FAIL("unknown interface operation");
   HF_LAUNCH_CHECK(c);

@@ -33,6 +33,7 @@ struct hf_ele_view
   double *delta_disu_fpts;  // (fpt,ele,field)
   double *grad_disu_fpts;   // (fpt,ele,field,dim)
   double *sgsf_fpts;        // (fpt,ele,field,dim), LES only
+  const double *disu_upts;  // (upt,ele,field): wall-model input points
   const double *tdA_fpts;   // (fpt,ele)
   const double *norm_fpts;  // (fpt,ele,dim)
 };
@@ -101,6 +102,8 @@ struct hf_bdy_inters_dev
   int8_t *type_l = nullptr;
   int *bc_id = nullptr;
   double *pos_fpts = nullptr;
+  int *wm_upt = nullptr;     // wall model: flat input solution point per interface (-1: none)
+  double *wm_dist = nullptr;
   std::vector<int> h_ele_type_l, h_ele_l, h_loc_l, h_bc_id;
 };
 

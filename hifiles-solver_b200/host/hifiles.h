@@ -467,8 +467,9 @@ public:
   void mv_all_cpu_gpu();
   void evaluate_boundaryConditions_invFlux(struct solution *FlowSol, double time_bound);
   void evaluate_boundaryConditions_viscFlux(double time_bound);
-  hf_array<int> boundary_id;
-  hf_array<double> pos_fpts;
+  hf_array<int> boundary_id, wm_upt;
+  hf_array<double> pos_fpts, wm_dist;
+  bool any_wm = false;
 };
 
 class mpi_inters : public inters

@@ -540,7 +540,7 @@ void input::setup_params(int rank)
   if (RANS) FatalError("RANS (Spalart-Allmaras) is outside the hot-path scope of this build (SURVEY.md §2 #12)");
   if (LES && !viscous) FatalError("LES not supported with inviscid flow");
   if (LES && (SGS_model < 0 || SGS_model > 4)) FatalError("SGS model not implemented");
-  if (wall_model) FatalError("wall models are outside the hot-path scope of this build (SURVEY.md §8f rank 3)");
+  if (wall_model < 0 || wall_model > 2) FatalError("Wall model not implemented!");
   if (over_int && over_int_order < 0) FatalError("Invalid under sampling order");
   if (riemann_solve_type < 0 || riemann_solve_type > 3) FatalError("Riemann solver not implemented");
 

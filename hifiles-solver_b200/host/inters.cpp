@@ -132,8 +132,28 @@ void bdy_inters::set_boundary(int in_inter, int bc_id, int in_ele_type_l, int in
     int fpt = e->get_fpt_index(j, in_local_inter_l);
     for (int k = 0; k < n_dims; k++) pos_fpts(j, in_inter, k) = e->pos_fpts(fpt, in_ele_l, k);
   }
+  // wall model: the solution point of the element farthest from this face feeds it (reference src/bdy_inters.cpp:149-162,
+  // eles::calc_wm_upts_dist src/eles.cpp:4873-4903)
+  if (wm_upt.get_dim(0) != max(n_inters, 1)) { wm_upt.setup(max(n_inters, 1)); wm_upt.initialize_to_value(-1); wm_dist.setup(max(n_inters, 1)); }
   if (run_input.bc_list[bc_id].use_wm)
-    FatalError("wall models are outside the hot-path scope of this build (SURVEY.md §8f rank 3)");
+  {
+    double dist_min = 0., dist_max = 0.;
+    int best = 0;
+    for (int i = 0; i < e->n_upts_per_ele; i++)
+    {
+      for (int j = 0; j < n_fpts_per_inter; j++)
+      {
+        const int fpt = e->get_fpt_index(j, in_local_inter_l);
+        double d = 0.;
+        for (int k = 0; k < n_dims; k++) d += (e->pos_fpts(fpt, in_ele_l, k) - e->pos_upts(i, in_ele_l, k)) * e->norm_fpts(fpt, in_ele_l, k);
+        if (j == 0 || d < dist_min) dist_min = d;
+      }
+      if (dist_min > dist_max) { dist_max = dist_min; best = i; }
+    }
+    wm_upt(in_inter) = best + e->n_upts_per_ele * in_ele_l;
+    wm_dist(in_inter) = dist_max;
+    any_wm = true;
+  }
 }
 
 void bdy_inters::mv_all_cpu_gpu()
@@ -146,6 +166,8 @@ void bdy_inters::mv_all_cpu_gpu()
   d.ele_type_l = ele_type_l.get_ptr_cpu();
   d.ele_l = ele_l.get_ptr_cpu();
   d.local_inter_l = local_inter_l.get_ptr_cpu();
+  d.wm_upt = any_wm ? wm_upt.get_ptr_cpu() : nullptr;
+  d.wm_dist = any_wm ? wm_dist.get_ptr_cpu() : nullptr;
   d.bc_id = boundary_id.get_ptr_cpu();
   d.pos_fpts = pos_fpts.get_ptr_cpu();
   hf_check(hf_dev_upload_bdy_inters(ctx, &d));

@@ -52,6 +52,7 @@ static void upload_params(struct solution *FlowSol)
   p.Kappa = run_input.Kappa;
   p.prandtl_t = run_input.prandtl_t;
   p.filter_ratio = run_input.filter_ratio;
+  p.wall_model = run_input.wall_model;
   p.over_int = run_input.over_int;
   p.shock_cap = run_input.shock_cap;
   p.shock_det_field = run_input.shock_det_field;
@@ -73,6 +74,7 @@ static void upload_params(struct solution *FlowSol)
     t.T_total = b.T_total;
     t.mach = b.mach;
     t.nx = b.nx; t.ny = b.ny; t.nz = b.nz;
+    t.use_wm = b.use_wm;
   }
   hf_check(hf_dev_set_bc_table(FlowSol->ctx, (int)table.size(), table.empty() ? nullptr : table.data()));
 }

@@ -57,6 +57,7 @@ typedef struct hf_params
   int LES;                    /* 1: on */
   int SGS_model;              /* 0 Smagorinsky (with wall damping), 1 WALE, 2 WALE-similarity, 3 SVV, 4 similarity */
   double C_s, Kappa, prandtl_t, filter_ratio;
+  int wall_model;             /* 0 off, 1 Werner-Wengle, 2 compressible log law (reference src/wall_model_funcs.cpp:13-118) */
 } hf_params;
 
 /* One element type (mirror of class eles, reference include/eles.h; storage src/eles.cpp:100-213). */
@@ -115,6 +116,7 @@ typedef struct hf_bc
 {
   int bc_flag;
   double rho, velocity[3], p_static, T_static, p_total, T_total, mach, nx, ny, nz;
+  int use_wm; /* 1: this wall boundary takes its viscous flux from the wall model (bc::use_wm) */
 } hf_bc;
 
 /* Boundary interfaces of one face type (mirror of bdy_inters::set_boundary, reference src/bdy_inters.cpp:75-178). */
@@ -124,6 +126,10 @@ typedef struct hf_bdy_inters_desc
   const int *ele_type_l, *ele_l, *local_inter_l;
   const int *bc_id;         /* index into the hf_bc table, per interface */
   const double *pos_fpts;   /* (fpt,inter,dim) physical flux-point coordinates, or NULL */
+  /* wall model (reference src/bdy_inters.cpp:149-162): per interface the element's solution point farthest from the face
+   * (flat upt + n_upts*ele, -1 = no wall model on this interface) and its distance; NULL when no boundary uses it */
+  const int *wm_upt;
+  const double *wm_dist;
 } hf_bdy_inters_desc;
 
 /* Partition ("MPI") interfaces of one face type (mirror of mpi_inters::set_mpi + set_nout_proc, reference

@@ -94,6 +94,22 @@ CASES = {
                                                        filter_ratio=2.0, filter_type=1)),
     "tet_p2_les_svv_modal": ("tet", 2, {}, dict(order=2, adv_type=2, riemann_solve_type=2, viscous=1, dt=1e-5, LES=1, SGS_model=3, C_s=0.3, filter_ratio=2.0,
                                                 filter_type=2)),
+    # wall-modelled LES (calc_wall_stress, reference src/wall_model_funcs.cpp:13-118; bdy_inters.cpp:1095-1131): Werner-Wengle on an isothermal wall,
+    # the compressible log law on an adiabatic wall
+    "mixed_tri_quad_p3_les_wale_werner_wengle": ("mixed", (8, 6), dict(lengths=(4., 2.), origin=(0., 0.), bcs={"x-": "In", "x+": "Out", "y-": "Wall", "y+": "Top"}),
+                                                 dict(order=3, adv_type=3, riemann_solve_type=0, viscous=1, ic_form=1, dt=5e-5, fix_vis=0, Mach_c_ic=0.3, nx_c_ic=1.,
+                                                      ny_c_ic=0., nz_c_ic=0., T_c_ic=300., rho_c_ic=1.17, Mach_free_stream=0.3, rho_free_stream=1.17,
+                                                      T_free_stream=300., L_free_stream=1., dx_cyclic=None, dy_cyclic=None, dz_cyclic=None, bc_Cyclic_type=None,
+                                                      bc_In_type="char", bc_In_p_static=100747., bc_In_mach=0.3, bc_In_T_static=300., bc_In_nx=1., bc_In_ny=0.,
+                                                      bc_Out_type="sub_out_simp", bc_Out_p_static=100000., bc_Wall_type="isotherm_wall", bc_Wall_T_static=310.,
+                                                      bc_Wall_use_wm=1, bc_Top_type="adiabat_wall", bc_Top_u=20., LES=1, SGS_model=1, C_s=0.325,
+                                                      filter_ratio=2.0, wall_model=1)),
+    "hex_p2_les_wale_loglaw_wall": ("hex", (3, 3, 4), dict(lengths=(1., 1., 2.), bcs={"x-": "Cyclic", "x+": "Cyclic", "y-": "Cyclic", "y+": "Cyclic",
+                                                                                 "z-": "Wall", "z+": "Far"}),
+                                    dict(order=2, adv_type=1, riemann_solve_type=2, viscous=1, ic_form=1, dt=1e-4, Mach_c_ic=0.2, nx_c_ic=1., ny_c_ic=0.,
+                                         nz_c_ic=0., T_c_ic=300., rho_c_ic=1.17, Mach_free_stream=0.2, rho_free_stream=1.17, T_free_stream=300.,
+                                         L_free_stream=1., dx_cyclic=1., dy_cyclic=1., dz_cyclic=None, bc_Wall_type="adiabat_wall", bc_Wall_use_wm=1,
+                                         bc_Far_type="sub_out_char", bc_Far_p_static=100500., LES=1, SGS_model=1, C_s=0.325, filter_ratio=2.0, wall_model=2)),
     "hexpri_p2_les_smagorinsky_periodic": ("hexpri", (2, 2, 4), {}, dict(order=2, adv_type=2, riemann_solve_type=3, viscous=1, dt=2e-5, LES=1, SGS_model=0,
                                                                        C_s=0.1, filter_ratio=2.0)),
     # Persson sensor + exponential modal filter after every stage (eles::shock_capture, reference src/eles.cpp:2918-2959): BASELINE config 5;
