@@ -110,6 +110,17 @@ CASES = {
                                          nz_c_ic=0., T_c_ic=300., rho_c_ic=1.17, Mach_free_stream=0.2, rho_free_stream=1.17, T_free_stream=300.,
                                          L_free_stream=1., dx_cyclic=1., dy_cyclic=1., dz_cyclic=None, bc_Wall_type="adiabat_wall", bc_Wall_use_wm=1,
                                          bc_Far_type="sub_out_char", bc_Far_p_static=100500., LES=1, SGS_model=1, C_s=0.325, filter_ratio=2.0, wall_model=2)),
+    # BASELINE config 5 in one case: supersonic flow over a wall-modelled wall on a mixed hex / prism mesh, HLLC, LES (WALE), shock capturing,
+    # supersonic inlet / outlet, characteristic far field
+    "config5_hexpri_p2_les_wm_shockcap_hllc": ("hexpri", (3, 2, 4), dict(lengths=(1.5, 1., 2.), bcs={"x-": "In", "x+": "Out", "y-": "Cyclic", "y+": "Cyclic",
+                                                                                               "z-": "Wall", "z+": "Far"}),
+                                               dict(order=2, adv_type=2, riemann_solve_type=3, viscous=1, ic_form=1, dt=2e-6, fix_vis=0, Mach_c_ic=1.8, nx_c_ic=1., ny_c_ic=0.,
+                                                    nz_c_ic=0.02, T_c_ic=290., rho_c_ic=1.2, Mach_free_stream=1.8, rho_free_stream=1.2, T_free_stream=290., L_free_stream=1.,
+                                                    dx_cyclic=None, dy_cyclic=1., dz_cyclic=None, bc_In_type="sup_in", bc_In_p_static=101000., bc_In_mach=1.8,
+                                                    bc_In_T_static=290., bc_In_nx=1., bc_In_ny=0., bc_In_nz=0., bc_Out_type="sup_out",
+                                                    bc_Wall_type="adiabat_wall", bc_Wall_use_wm=1, bc_Far_type="char", bc_Far_p_static=101000., bc_Far_mach=1.8,
+                                                    bc_Far_T_static=290., bc_Far_nx=1., bc_Far_ny=0., bc_Far_nz=0., LES=1, SGS_model=1, C_s=0.325, filter_ratio=2.0,
+                                                    wall_model=1, shock_cap=1, s0=1e-9, expf_cutoff=1, calc_force=1, monitor_cp_freq=100000, area_ref=1.0)),
     "hexpri_p2_les_smagorinsky_periodic": ("hexpri", (2, 2, 4), {}, dict(order=2, adv_type=2, riemann_solve_type=3, viscous=1, dt=2e-5, LES=1, SGS_model=0,
                                                                        C_s=0.1, filter_ratio=2.0)),
     # Persson sensor + exponential modal filter after every stage (eles::shock_capture, reference src/eles.cpp:2918-2959): BASELINE config 5;
