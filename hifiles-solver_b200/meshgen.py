@@ -180,9 +180,11 @@ def slab_partition(centroids, nproc, axis=0):
     return part
 
 
-def mixed_box_2d(path, n, lengths=(20., 20.), bcs=None, origin=(-10., -10.), kind="tri", warp=0.0):
+def mixed_box_2d(path, n, lengths=(20., 20.), bcs=None, origin=(-10., -10.), kind="tri", warp=0.0, curve=0.0):
     """Nx x Ny cells on a rectangle.  kind: 'tri' (every cell split into two triangles along its (0,0)-(1,1) diagonal),
     'quad', or 'mixed' (quads in the left half, triangles in the right half: BASELINE config 2's element mix).
+    'tri6' = quadratic six-node triangles (`id 3 6 v0 m01 v1 m12 v2 m20`, mesh_reader.cpp:192-197); curve > 0 bows the
+    interior edges (mid-edge nodes displaced normal to their edge), like the shipped cylinder mesh's curved elements.
     Gambit records: triangles `id 3 3 n1 n2 n3` (counter-clockwise; edge k joins nodes k, k+1: mesh_reader.cpp:192-197,
     :333-334), quads as in quad_box."""
     if np.isscalar(n):
@@ -202,6 +204,19 @@ def mixed_box_2d(path, n, lengths=(20., 20.), bcs=None, origin=(-10., -10.), kin
     order = np.argsort(nid.ravel())
     nodes = np.column_stack([nid.ravel()[order], x.ravel()[order], y.ravel()[order]])
     cells, groups = [], {}
+    xy = {int(nid[a, b]): (x[a, b], y[a, b]) for a in range(px) for b in range(py)}
+    mids, extra = {}, []
+
+    def mid(a, b, interior):
+        key = (min(a, b), max(a, b))
+        if key not in mids:
+            (xa, ya), (xb, yb) = xy[key[0]], xy[key[1]]
+            xm, ym = 0.5 * (xa + xb), 0.5 * (ya + yb)
+            if curve and interior:
+                xm, ym = xm - curve * (yb - ya), ym + curve * (xb - xa)
+            mids[key] = px * py + 1 + len(extra)
+            extra.append((mids[key], xm, ym))
+        return mids[key]
 
     def bface(side, cid, ntype, k):
         if side in bcs:
@@ -211,6 +226,16 @@ def mixed_box_2d(path, n, lengths=(20., 20.), bcs=None, origin=(-10., -10.), kin
     for j in range(ny):
         for i in range(nx):
             v00, v10, v11, v01 = nid[i, j], nid[i + 1, j], nid[i + 1, j + 1], nid[i, j + 1]
+            if kind == "tri6":
+                for tri, sides in (((v00, v10, v11), (j == 0 and "y-", i == nx - 1 and "x+", False)),
+                                   ((v00, v11, v01), (False, j == ny - 1 and "y+", i == 0 and "x-"))):
+                    cid += 1
+                    on_bdy = [(j == 0, i == nx - 1, False), (False, j == ny - 1, i == 0)][0 if tri[1] == v10 else 1]
+                    ms = [mid(tri[q], tri[(q + 1) % 3], not on_bdy[q]) for q in range(3)]
+                    cells.append((cid, 3, [tri[0], ms[0], tri[1], ms[1], tri[2], ms[2]]))
+                    for q, side in enumerate(sides):
+                        if side: bface(side, cid, 3, q + 1)
+                continue
             as_quad = kind == "quad" or (kind == "mixed" and i < nx // 2)
             if as_quad:
                 cid += 1
@@ -228,6 +253,8 @@ def mixed_box_2d(path, n, lengths=(20., 20.), bcs=None, origin=(-10., -10.), kin
                 cells.append((cid, 3, [v00, v11, v01]))
                 if j == ny - 1: bface("y+", cid, 3, 2)
                 if i == 0: bface("x-", cid, 3, 3)
+    if extra:
+        nodes = np.vstack([nodes, np.array(extra)])
     return _write_neu(path, 2, nodes, cells, groups)
 
 

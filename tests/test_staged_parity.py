@@ -63,6 +63,17 @@ CASES = {
                                                 bc_In_type="char", bc_In_p_static=100747., bc_In_mach=0.3, bc_In_T_static=300., bc_In_nx=1., bc_In_ny=0.,
                                                 bc_Out_type="sub_out_simp", bc_Out_p_static=100000., bc_Wall_type="isotherm_wall", bc_Wall_T_static=310.,
                                                 bc_Top_type="adiabat_wall", bc_Top_u=20.)),
+    # curved six-node triangles with walls, supersonic inflow, Persson sensor + filter, global CFL time step: the shipped cylinder case's ingredients
+    # (reference testcases/navier-stokes/cylinder/input_cylinder_visc) on a generated mesh
+    "tri6_p3_ns_curved_supin_wall_cfl_shockcap": ("tri6", (6, 5), dict(lengths=(3., 2.), origin=(0., 0.), curve=0.08,
+                                                                      bcs={"x-": "In", "x+": "Out", "y-": "Wall", "y+": "Wall"}),
+                                                  dict(order=3, adv_type=2, riemann_solve_type=0, viscous=1, ic_form=1, dt_type=1, CFL=0.5, dt=None, fix_vis=0,
+                                                       ldg_tau=0.5, Mach_c_ic=1.1, nx_c_ic=1., ny_c_ic=0., nz_c_ic=0., T_c_ic=300., rho_c_ic=1.17723946,
+                                                       Mach_free_stream=1.0, rho_free_stream=1.17723946, T_free_stream=300., L_free_stream=1.,
+                                                       dx_cyclic=None, dy_cyclic=None, dz_cyclic=None, bc_Cyclic_type=None, bc_In_type="sup_in",
+                                                       bc_In_p_static=101325., bc_In_mach=1.1, bc_In_T_static=300., bc_In_nx=1., bc_In_ny=0.,
+                                                       bc_Out_type="sup_out", bc_Wall_type="isotherm_wall", bc_Wall_T_static=300., shock_cap=1, s0=1e-24,
+                                                       calc_force=1, monitor_cp_freq=100000, area_ref=1.0)),
     "tet_p3_ns_roem_rk34": ("tet", 2, {}, dict(order=3, adv_type=2, riemann_solve_type=2, viscous=1, dt=1e-5)),
     "tet_p2_ns_hllc_cfl_local_dt": ("tet", 2, dict(warp=0.15), dict(order=2, adv_type=3, riemann_solve_type=3, viscous=1, dt_type=2, CFL=0.3, dt=None)),
     "pri_p3_ns_roem_rk45": ("pri", 2, {}, dict(order=3, adv_type=3, riemann_solve_type=2, viscous=1, dt=1e-5)),
@@ -141,7 +152,7 @@ def make_mesh(meshgen, kind, mesh, n, mkw):
         meshgen.hex_box(mesh, n, **mkw)
     elif kind == "quad":
         meshgen.quad_box(mesh, n, **mkw)
-    elif kind in ("tri", "mixed"):
+    elif kind in ("tri", "mixed", "tri6"):
         meshgen.mixed_box_2d(mesh, n, kind=kind, **mkw)
     else:
         meshgen.mixed_box_3d(mesh, n, kind=kind, **mkw)
