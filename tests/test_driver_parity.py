@@ -1,6 +1,7 @@
 """GPU: the drop-in command line.  `HiFiLES <input_file>` of this repository (host mirror + device layer) and the
 reference's own binary (oracle/_ref/HiFiLES_ref) are run on the same input; the residual table printed on stdout and
-the log10-residual columns of history.plt (15 digits, reference src/output.cpp:2298-2378) must agree."""
+the log10-residual columns of history.plt (15 digits, reference src/output.cpp:2298-2378) must agree, and so must the
+ASCII restart file (Rest_<iter>_p0000.dat: the solution of every element, 15 digits, src/output.cpp:1753-1818)."""
 import os
 import re
 import subprocess
@@ -52,3 +53,41 @@ def test_command_line_matches_reference_binary(tmp_path, hb, meshgen):
     assert out["ref"][0].shape == out["ours"][0].shape and out["ref"][0].shape[0] == 4
     assert np.abs(out["ours"][0] - out["ref"][0]).max() <= 1e-8          # printed with 8 decimals
     assert np.abs(out["ours"][1] - out["ref"][1]).max() <= 1e-11         # log10 of the residual norms, 15 digits
+
+
+def restart_numbers(path):
+    """structure (all non-numeric lines, in order) and numbers of an ASCII restart file"""
+    text, nums = [], []
+    for line in open(path):
+        t = line.split()
+        try:
+            nums.extend(float(x) for x in t)
+        except ValueError:
+            text.append(line.strip())
+    return text, np.array(nums)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind", ["hex", "pritet"])
+def test_restart_file_matches_reference_binary(tmp_path, hb, meshgen, kind):
+    if not (os.path.exists(REF) and os.path.exists(OURS)):
+        pytest.skip("driver binaries not built")
+    out = {}
+    for who, exe in (("ref", REF), ("ours", OURS)):
+        d = tmp_path / who
+        d.mkdir()
+        if kind == "hex":
+            meshgen.hex_box(str(d / "m.neu"), 3)
+        else:
+            meshgen.mixed_box_3d(str(d / "m.neu"), (2, 4, 2), kind=kind)
+        # staged kernels (device_fused 0): they reproduce the reference's arithmetic, so the files agree to the last printed digit
+        meshgen.write_input(str(d / "input"), "m.neu", order=2, adv_type=2, dt=1e-5, riemann_solve_type=2, viscous=1, n_steps=2, monitor_res_freq=1,
+                            restart_dump_freq=2, device_fused=0)
+        env = dict(os.environ, HIFILES_HOME=util.REF_DIR if who == "ref" else os.path.join(util.ROOT, "hifiles-solver_b200"))
+        r = subprocess.run([exe, "input"], cwd=str(d), env=env, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+        out[who] = restart_numbers(str(d / "Rest_000000002_p0000.dat"))
+    assert out["ours"][0] == out["ref"][0]
+    assert out["ours"][1].shape == out["ref"][1].shape
+    scale = np.abs(out["ref"][1]).max()
+    assert np.abs(out["ours"][1] - out["ref"][1]).max() <= 1e-13 * scale
