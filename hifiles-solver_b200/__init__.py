@@ -82,6 +82,8 @@ def lib():
     L.hf_dev_timer_stop.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
     L.hf_dev_fused_status.argtypes = [C.c_void_p]
     L.hf_dev_fused_status.restype = C.c_char_p
+    L.hf_dev_fused_variant.argtypes = [C.c_void_p]
+    L.hf_dev_fused_variant.restype = C.c_char_p
     L.hf_dev_kernel_timer.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_longlong)]
     _lib = L
     return L
@@ -227,6 +229,9 @@ class Run:
 
     def fused_status(self):
         return lib().hf_dev_fused_status(self.ctx).decode()
+
+    def fused_variant(self):
+        return lib().hf_dev_fused_variant(self.ctx).decode()
 
     def rk_stage(self, stage, time=0.0, keep_residual=False):
         self._ckd(lib().hf_dev_rk_stage(self.ctx, stage, time, 1 if keep_residual else 0))

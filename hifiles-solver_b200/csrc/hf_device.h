@@ -159,6 +159,7 @@ int hf_fused_stage(hf_ctx *c, int rk_stage, double time, int keep_residual, int 
 int hf_fused_extrapolate(hf_ctx *c);
 int hf_fused_on_upload(hf_ctx *c, hf_eles_dev &e, const hf_eles_desc *d);
 void hf_fused_destroy(hf_ctx *c);
+int hf_fused_after_nccl(hf_ctx *c);
 // halo exchange over NCCL (hf_halo.cu): buffers are [inter][...] with `per_inter` doubles per interface, the message
 // to neighbour p is the contiguous slice of its nb_count interfaces (reference src/mpi_inters.cpp:244-255)
 int hf_halo_post(hf_ctx *c, hf_mpi_inters_dev &I, const double *out, double *in, size_t per_inter);

@@ -110,7 +110,8 @@ struct fused_args
   double *div;            // written when keep_residual
   const double *fu_cur;   // face u, read (neighbours)
   double *fu_next;        // face u of the updated solution, written (own faces)
-  double *fv;             // one-sided viscous normal flux at flux points: written by k_grad, read by k_resid
+  double *fv;             // one-sided viscous normal flux at flux points (4 per point): written by k_grad, read by k_resid;
+                          // generation 7: the complete common normal flux fc (5 per point) at the owned faces
   const double *em;       // [ele][EM]: JGinv[9], 1/detjac, 6 x (tdA, left normal[3])
   const int *nbr;         // [ele][6] neighbour face block
   const int *finfo;       // [ele][6] rot + 4*is_right + 8*partition face
@@ -126,6 +127,7 @@ struct fused_args
   rk_args rk;
   int viscous, keep_residual, do_update;
   int pf_dist;            // L2 software-prefetch distance in CTAs (0 = off)
+  unsigned long long own_xor; // generation 7: bmask ^ own_xor = the flux points this element owns (LDG weight 1)
 };
 
 __device__ __forceinline__ void cp_async8(void *smem, const void *gmem)
@@ -343,6 +345,11 @@ struct hf_fused_state
   bool elist_identity = false;
   double *out_u = nullptr, *out_g = nullptr;
   int E = 2, NT = 128;
+  bool os = false; // one-sided LDG kernels (generation 7) in use
+  int fv_blk = 0;  // doubles per face block of fv
+  unsigned long long own_xor = 0;
+  std::vector<unsigned long long> h_pmask; // own masks of the partition faces
+  std::string os_why;
 };
 
 void hf_fused_destroy(hf_ctx *c)
@@ -579,6 +586,14 @@ int hf_fused_prepare(hf_ctx *c)
   }
   for (size_t q = 0; q < nbr.size(); q++)
     if (nbr[q] < 0) return no("an element face has no neighbour");
+  // One-sided LDG (generation 7): |beta| = 0.5 makes the LDG weights exactly 1 and 0, so every flux-point pair has one
+  // owner (own weight 0.5 + beta when the bmask bit is clear, 0.5 - beta when set).  On several ranks the two sides of a
+  // partition face must agree on it: checked when the communicator arrives (hf_fused_after_nccl).
+  Z->os = visc && fabs(c->prm.ldg_beta) == 0.5 && !getenv("HF_FUSED_GEN6");
+  Z->own_xor = c->prm.ldg_beta > 0. ? (NN == 64 ? ~0ull : ((1ull << NN) - 1ull)) : 0ull;
+  Z->fv_blk = Z->os ? NF * NN : 4 * NN;
+  Z->h_pmask.resize(M.n_inters);
+  for (int i = 0; i < M.n_inters; i++) Z->h_pmask[i] = bmask[(size_t)M.h_ele_l[i] * 6 + M.h_loc_l[i]] ^ Z->own_xor;
   // per own flux point: where the neighbour's value of field 0 sits in fu (block * NF*NN + permuted flux point)
   std::vector<int> nidx((size_t)ne * NFP);
   if ((double)nblk_total(ne, M.n_inters) * NF * NN > 2.0e9) return no("face arrays exceed int32 indexing");
@@ -601,7 +616,7 @@ int hf_fused_prepare(hf_ctx *c)
   const size_t nblk = (size_t)ne * 6 + M.n_inters;
   if (hf_alloc_zero(c, &Z->fu[0], nblk * NF * NN)) return 1;
   if (hf_alloc_zero(c, &Z->fu[1], nblk * NF * NN)) return 1;
-  if (visc && hf_alloc_zero(c, &Z->fv, nblk * 4 * NN)) return 1;
+  if (visc && hf_alloc_zero(c, &Z->fv, nblk * NF * NN)) return 1;
   if (hf_alloc_copy(c, &Z->em, em.data(), em.size())) return 1;
   if (hf_alloc_copy(c, &Z->nbr, nbr.data(), nbr.size())) return 1;
   if (hf_alloc_copy(c, &Z->finfo, finfo.data(), finfo.size())) return 1;
@@ -613,7 +628,7 @@ int hf_fused_prepare(hf_ctx *c)
   if (M.n_inters)
   {
     if (hf_alloc_zero(c, &Z->out_u, (size_t)M.n_inters * NF * NN)) return 1;
-    if (visc && hf_alloc_zero(c, &Z->out_g, (size_t)M.n_inters * 4 * NN)) return 1;
+    if (visc && hf_alloc_zero(c, &Z->out_g, (size_t)M.n_inters * NF * NN)) return 1;
   }
   // host-side extracts are no longer needed
   std::vector<double>().swap(e.h_em);
@@ -631,7 +646,7 @@ int launch_all(hf_ctx *c, hf_fused_state *Z, fused_args &A, int what, int lo, in
   if (hi <= lo) return 0;
   A.lo = lo;
   A.hi = hi;
-  // what: 0 face values, 1 gradient kernel, 2 residual kernel
+  // what: 0 face values, 1 gradient kernel, 2 residual kernel; 3 / 4 = the one-sided (generation 7) pair
   const size_t smem_g = sizeof(smem6<N, E>), smem_r = smem_g;
   const int grid = (hi - lo + E - 1) / E;
   static bool attr_done = false;
@@ -645,12 +660,24 @@ int launch_all(hf_ctx *c, hf_fused_state *Z, fused_args &A, int what, int lo, in
     HF_CUDA(cudaFuncSetAttribute(k_grad6<N, E, NT, MINB>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     HF_CUDA(cudaFuncSetAttribute(k_resid6<N, E, NT, MINB, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     HF_CUDA(cudaFuncSetAttribute(k_resid6<N, E, NT, MINB, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    HF_CUDA(cudaFuncSetAttribute(k_grad7<N, E, NT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(smem7<N, E>)));
+    HF_CUDA(cudaFuncSetAttribute(k_resid7<N, E, NT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(smem7<N, E>)));
+    HF_CUDA(cudaFuncSetAttribute(k_grad7<N, E, NT, MINB>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    HF_CUDA(cudaFuncSetAttribute(k_resid7<N, E, NT, MINB>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     attr_done = true;
   }
   if (what == 0)
     k_face_values6<N, E, NT><<<grid, NT, smem_g, c->stream>>>(A);
   else if (what == 1)
     k_grad6<N, E, NT, MINB><<<grid, NT, smem_g, c->stream>>>(A);
+  else if (what == 3)
+    k_grad7<N, E, NT, MINB><<<grid, NT, sizeof(smem7<N, E>), c->stream>>>(A);
+  else if (what == 4)
+  {
+    hf_ktimer_begin(c);
+    k_resid7<N, E, NT, MINB><<<grid, NT, sizeof(smem7<N, E>), c->stream>>>(A);
+    hf_ktimer_end(c);
+  }
   else
   {
     hf_ktimer_begin(c);
@@ -660,7 +687,9 @@ int launch_all(hf_ctx *c, hf_fused_state *Z, fused_args &A, int what, int lo, in
   }
   c->launches++;
   cudaError_t err = cudaGetLastError();
-  if (err != cudaSuccess) { hf_set_error(std::string("fused kernel launch: ") + cudaGetErrorString(err)); return 1; }
+  static const bool debug_sync = getenv("HF_DEBUG_SYNC") != nullptr; // debugging aid: attribute an asynchronous fault to its kernel
+  if (err == cudaSuccess && debug_sync) err = cudaStreamSynchronize(c->stream);
+  if (err != cudaSuccess) { hf_set_error(std::string("fused kernel launch (kernel ") + std::to_string(what) + "): " + cudaGetErrorString(err)); return 1; }
   return 0;
 }
 
@@ -673,12 +702,19 @@ int launch(hf_ctx *c, hf_fused_state *Z, fused_args &A, int what, int lo, int hi
   case 3: return launch_all<4, 2, 128, 3>(c, Z, A, what, lo, hi);
   case 4:
   {
-    static int cfg = getenv("HF_FUSED_CFG") ? atoi(getenv("HF_FUSED_CFG")) : 0;
-    if (cfg == 1) return launch_all<5, 1, 64, 6>(c, Z, A, what, lo, hi);
-    if (cfg == 2) return launch_all<5, 2, 256, 2>(c, Z, A, what, lo, hi);
-    if (cfg == 3) return launch_all<5, 2, 192, 3>(c, Z, A, what, lo, hi);
-    if (cfg == 4) return launch_all<5, 3, 192, 2>(c, Z, A, what, lo, hi);
-    if (cfg == 5) return launch_all<5, 2, 128, 3>(c, Z, A, what, lo, hi);
+    // measurement aid: CTA shape per kernel family (HF_FUSED_CFG for all, HF_FUSED_CFG_G / _R for the gradient / residual kernel)
+    static const int cfg_all = getenv("HF_FUSED_CFG") ? atoi(getenv("HF_FUSED_CFG")) : 0;
+    static const int cfg_g = getenv("HF_FUSED_CFG_G") ? atoi(getenv("HF_FUSED_CFG_G")) : cfg_all;
+    static const int cfg_r = getenv("HF_FUSED_CFG_R") ? atoi(getenv("HF_FUSED_CFG_R")) : cfg_all;
+    int cfg = (what == 1 || what == 3) ? cfg_g : ((what == 2 || what == 4) ? cfg_r : cfg_all);
+    // measured on B200 (64^3): k_resid7 is fastest with one element per CTA and six CTAs per SM (80 registers), k_grad7 with
+    // two elements per CTA and three CTAs per SM
+    if (what == 4 && !getenv("HF_FUSED_CFG_R") && !getenv("HF_FUSED_CFG")) cfg = 3;
+    if (cfg == 1) return launch_all<5, 1, 125, 4>(c, Z, A, what, lo, hi);
+    if (cfg == 2) return launch_all<5, 1, 125, 5>(c, Z, A, what, lo, hi);
+    if (cfg == 3) return launch_all<5, 1, 125, 6>(c, Z, A, what, lo, hi);
+    if (cfg == 4) return launch_all<5, 1, 64, 8>(c, Z, A, what, lo, hi);
+    if (cfg == 5) return launch_all<5, 2, 250, 1>(c, Z, A, what, lo, hi);
     return launch_all<5, 2, 125, 3>(c, Z, A, what, lo, hi);
   }
   case 5: return launch_all<6, 1, 128, 3>(c, Z, A, what, lo, hi);
@@ -713,6 +749,7 @@ void base_args(hf_ctx *c, hf_fused_state *Z, fused_args &A)
   A.viscous = c->prm.viscous;
   static const int pf = getenv("HF_FUSED_PF") ? atoi(getenv("HF_FUSED_PF")) : 0; // measured: no effect on B200 (the other resident CTAs already cover the staging latency)
   A.pf_dist = pf;
+  A.own_xor = Z->own_xor;
 }
 
 // exchange the partition-face blocks of arr (blk_doubles each): pack -> ncclSend/Recv into the tail of arr, on the
@@ -788,17 +825,18 @@ int hf_fused_stage(hf_ctx *c, int rk_stage, double time, int keep_residual, int 
   const int ni = Z->n_interior, n = Z->n_eles;
   static const bool no_overlap = getenv("HF_NO_OVERLAP") != nullptr; // measurement aid: serialise exchange and compute
   if (no_overlap && exchange_wait(c)) return 1;
+  const int kg = Z->os ? 3 : 1, kr = Z->os ? 4 : 2;
   if (p.viscous)
   {
-    if (launch(c, Z, A, 1, 0, ni)) return 1;
+    if (launch(c, Z, A, kg, 0, ni)) return 1;
     if (exchange_wait(c)) return 1;
-    if (launch(c, Z, A, 1, ni, n)) return 1;
-    if (exchange_post(c, Z, Z->fv, Z->out_g, 4 * NN)) return 1;
+    if (launch(c, Z, A, kg, ni, n)) return 1;
+    if (exchange_post(c, Z, Z->fv, Z->out_g, Z->fv_blk)) return 1;
     if (no_overlap && exchange_wait(c)) return 1;
   }
-  if (launch(c, Z, A, 2, 0, ni)) return 1;
+  if (launch(c, Z, A, kr, 0, ni)) return 1;
   if (exchange_wait(c)) return 1;
-  if (launch(c, Z, A, 2, ni, n)) return 1;
+  if (launch(c, Z, A, kr, ni, n)) return 1;
   if (do_update)
   {
     Z->cur ^= 1;
@@ -806,6 +844,55 @@ int hf_fused_stage(hf_ctx *c, int rk_stage, double time, int keep_residual, int 
     c->ufpts_valid = true;
   }
   return 0;
+}
+
+// Called when the communicator of a multi-rank run arrives: the one-sided kernels need the two ranks of every partition
+// face to agree on the owner of each flux-point pair.  Each side applies the reference's sign switch to its OWN normal
+// (src/mpi_inters.cpp:400-483 with src/inters.cpp:566-581); on exact geometry the normals are opposite and the choices
+// complementary, but rounding-level normal components can make both sides claim (or disclaim) a pair.  The masks are
+// exchanged once; any disagreement anywhere sends every rank back to the two-sided generation-6 kernels.
+int hf_fused_after_nccl(hf_ctx *c)
+{
+  hf_fused_state *Z = c->fz;
+  if (!Z || !Z->available || !Z->os || c->nproc < 2) return 0;
+  hf_mpi_inters_dev &M = c->mpis[2];
+  const int N = Z->order + 1, NN = N * N, nm = Z->n_mpi;
+  double ok = 1.0;
+  if (nm)
+  {
+    static_assert(sizeof(unsigned long long) == sizeof(double), "masks travel as 8-byte words");
+    double *d_out = nullptr, *d_in = nullptr;
+    if (hf_alloc_copy(c, &d_out, (const double *)Z->h_pmask.data(), (size_t)nm)) return 1;
+    if (hf_alloc_zero(c, &d_in, (size_t)nm)) return 1;
+    if (hf_halo_post(c, M, d_out, d_in, 1) || hf_halo_wait(c)) return 1;
+    std::vector<unsigned long long> theirs(nm);
+    HF_CUDA(cudaMemcpyAsync(theirs.data(), d_in, (size_t)nm * 8, cudaMemcpyDeviceToHost, c->stream));
+    HF_CUDA(cudaStreamSynchronize(c->stream));
+    for (int i = 0; i < nm && ok == 1.0; i++)
+      for (int j = 0; j < NN; j++)
+      {
+        const int jn = Z->T.perm[(M.h_rot[i] & 3) * 36 + j];
+        if (((Z->h_pmask[i] >> j) & 1ull) == ((theirs[i] >> jn) & 1ull)) { ok = 0.0; break; }
+      }
+  }
+  if (hf_halo_allreduce_min(c, &ok)) return 1;
+  if (ok != 1.0)
+  {
+    Z->os = false;
+    Z->fv_blk = 4 * NN;
+    Z->os_why = "the ranks of a partition face disagree on the LDG owner of a flux-point pair (rounding-level normal components)";
+  }
+  return 0;
+}
+
+extern "C" const char *hf_dev_fused_variant(hf_ctx *c)
+{
+  if (!c->fz || !c->fz->available) return "none";
+  if (!c->prm.viscous) return "generation 6 (inviscid: k_resid6)";
+  if (c->fz->os) return "generation 7 (one-sided LDG: k_grad7 + k_resid7)";
+  static std::string s;
+  s = "generation 6 (two-sided LDG: k_grad6 + k_resid6)" + (c->fz->os_why.empty() ? std::string() : ": " + c->fz->os_why);
+  return s.c_str();
 }
 
 extern "C" const char *hf_dev_fused_status(hf_ctx *c)

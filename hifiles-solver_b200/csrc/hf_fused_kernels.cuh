@@ -559,3 +559,452 @@ __global__ void __launch_bounds__(NT) k_face_values6(const __grid_constant__ fus
   pass_FO<N, E, NT, 1>(S, A, ne);
   pass_FO<N, E, NT, 2>(S, A, ne);
 }
+
+// =====================================================================================================================
+// Generation 7: one-sided LDG (|ldg_beta| = 0.5, the reference's default and the TGV configuration).
+//
+// With beta = +-0.5 the LDG weights are exactly 1 and 0: at every flux-point pair ONE side (the "owner", picked by the
+// reference's sign switch on the face normal, src/inters.cpp:566-581, which also fires on rounding-level normal
+// components, so ownership is kept per flux point) supplies the viscous flux, and the common solution is the other
+// side's value.  Consequences used here:
+//   * the owner has everything the common flux needs (own u, neighbour u, own gradient): it evaluates Riemann + LDG
+//     once per pair in k_grad7 and stores the complete common normal flux fc (5 values per flux point, along the LEFT
+//     normal); the other side only reads it.  k_resid7 has no Riemann / viscous interface work left;
+//   * the LDG solution correction of an element only involves its owned flux points, so only those neighbour values
+//     are staged, only those face gradients are evaluated, and an element only publishes face values (fu) at the flux
+//     points it does not own.
+// Results are those of generation 6 (weights 1 and 0 are exact) with a third less traffic and fewer instructions.
+template <int N, int E>
+struct smem7
+{
+  static constexpr int NN = N * N, NU = N * NN, NFP = 6 * NN, PL = E * NU, FQ = E * NFP;
+  static constexpr int PLS = PL + ((N - PL % 16) + 16) % 16;
+  double su[NF][PLS];      // solution at solution points
+  double sx[NF][FQ];       // neighbour values at the OWNED flux points (the others are never loaded)
+  double sf[NF][FQ];       // k_grad7: own face values; k_resid7: common normal flux fc at every own flux point
+  double sg[ND * NF][PLS]; // reference-space gradient -> transformed flux -> divergence (planes 0..4)
+  double em[E][EM];
+  double scl[E][6];        // k_resid7: +-tdA that turns fc into the element's own norm_tconf
+  unsigned long long own[E][6]; // bit j: this element owns flux point j of the face
+  int finfo[E][6];
+  int ge[E];
+  int n_owned;
+  unsigned short olist[FQ]; // k_grad7: the owned flux points of the CTA, compacted
+};
+
+__device__ __forceinline__ bool own_bit(unsigned long long m, int j) { return (m >> j) & 1ull; }
+
+template <int N, int E, int NT, bool RESID, typename SM>
+__device__ __forceinline__ void stage7(SM &S, const fused_args &A, int l0, int ne)
+{
+  constexpr int NN = N * N, NU = N * NN, NFP = 6 * NN;
+  const int tid = threadIdx.x;
+  if (tid < ne) S.ge[tid] = elem_id(A, l0 + tid);
+  const size_t fs = (size_t)NU * A.n_eles;
+  if (!A.elist)
+  {
+    const double *src = A.u0 + (size_t)NU * l0;
+    for (int i = tid; i < ne * NU; i += NT)
+    {
+#pragma unroll
+      for (int k = 0; k < NF; k++) cp_async8(&S.su[k][i], src + i + k * fs);
+    }
+  }
+  else
+  {
+    for (int i = tid; i < ne * NU; i += NT)
+    {
+      const int e = i / NU, p = i - e * NU;
+      const double *src = A.u0 + p + (size_t)NU * A.elist[l0 + e];
+#pragma unroll
+      for (int k = 0; k < NF; k++) cp_async8(&S.su[k][i], src + k * fs);
+    }
+  }
+  for (int q = tid; q < ne * NFP; q += NT)
+  {
+    const int e = q / NFP, r = q - e * NFP, f = r / NN, j = r - f * NN;
+    const int ge = elem_id(A, l0 + e);
+    const bool own = own_bit(A.bmask[(size_t)ge * 6 + f] ^ A.own_xor, j);
+    int ni = 0;
+    if (own || RESID) ni = A.nidx[(size_t)ge * NFP + r];
+    if (own)
+    {
+      const double *nb = A.fu_cur + ni;
+#pragma unroll
+      for (int k = 0; k < NF; k++) cp_async8(&S.sx[k][q], nb + k * NN);
+    }
+    if constexpr (RESID)
+    {
+      const double *src = A.fv + (own ? (size_t)ge * (NF * NFP) + (size_t)f * (NF * NN) + j : (size_t)ni);
+#pragma unroll
+      for (int k = 0; k < NF; k++) cp_async8(&S.sf[k][q], src + k * NN);
+    }
+  }
+  for (int i = tid; i < ne * EM; i += NT)
+  {
+    const int e = i / EM;
+    cp_async8(&S.em[0][0] + i, A.em + (size_t)elem_id(A, l0 + e) * EM + (i - e * EM));
+  }
+  if (tid < ne * 6)
+  {
+    const int e = tid / 6, f = tid - e * 6;
+    const size_t gf = (size_t)elem_id(A, l0 + e) * 6 + f;
+    S.own[0][tid] = A.bmask[gf] ^ A.own_xor;
+    S.finfo[0][tid] = A.finfo[gf];
+  }
+  cp_async_commit();
+}
+
+// L pass, one-sided: own face values at both ends of the line, LDG correction with the neighbour's value where this
+// element owns the flux point (weight 1, else 0), corrected reference-space derivative along the line
+template <int N, int E, int NT, int DIR, bool STORE_FACE, typename SM>
+__device__ __forceinline__ void pass_L7(SM &S, const fused_args &A, int ne)
+{
+  constexpr int NN = N * N, NU = N * NN, NFP = 6 * NN, stride = line_dir<N, DIR>::stride, FM = line_dir<N, DIR>::fminus, FP = line_dir<N, DIR>::fplus;
+  for (int t = threadIdx.x; t < NF * NN; t += NT)
+  {
+    int k, base, jm, jp;
+    line_task<N, DIR>(t, k, base, jm, jp);
+#pragma unroll
+    for (int e = 0; e < E; e++)
+    {
+      if (e >= ne) break;
+      const double *x = S.su[k] + e * NU + base;
+      double v[N];
+#pragma unroll
+      for (int j = 0; j < N; j++) v[j] = x[j * stride];
+      double um = A.tL[0][0] * v[0], up = A.tL[1][0] * v[0];
+#pragma unroll
+      for (int j = 1; j < N; j++) { um += A.tL[0][j] * v[j]; up += A.tL[1][j] * v[j]; }
+      const int fmq = e * NFP + FM * NN + jm, fpq = e * NFP + FP * NN + jp;
+      if constexpr (STORE_FACE)
+      {
+        S.sf[k][fmq] = um;
+        S.sf[k][fpq] = up;
+      }
+      // unconditional loads (slots of flux points this element does not own hold stale data, discarded by the select)
+      const double xm = S.sx[k][fmq], xp = S.sx[k][fpq];
+      const double dm = own_bit(S.own[e][FM], jm) ? xm - um : 0.;
+      const double dp = own_bit(S.own[e][FP], jp) ? xp - up : 0.;
+      double *o = S.sg[DIR * NF + k] + e * NU + base;
+#pragma unroll
+      for (int i = 0; i < N; i++)
+      {
+        double acc = A.tD[i * N] * v[0];
+#pragma unroll
+        for (int j = 1; j < N; j++) acc += A.tD[i * N + j] * v[j];
+        acc += A.tc5[FP * N + i] * dp;
+        acc += A.tc5[FM * N + i] * dm;
+        o[i * stride] = acc;
+      }
+    }
+  }
+}
+
+// owned flux points: gradient extrapolated along the line behind the point, physical gradient, viscous flux of the own
+// side, Riemann flux, complete common normal flux -> fc
+template <int N, int E, int NT, typename SM>
+__device__ __forceinline__ void pass_GF7(SM &S, const fused_args &A, int ne)
+{
+  constexpr int NN = N * N, NU = N * NN, NFP = 6 * NN;
+  const int n_owned = S.n_owned;
+  for (int i = threadIdx.x; i < n_owned; i += NT)
+  {
+    const int q = S.olist[i];
+    const int e = q / NFP, r = q - e * NFP, f = r / NN, j = r - f * NN;
+    const int info = S.finfo[e][f];
+    const bool is_right = (info & 4) != 0;
+    const double *J = S.em[e];
+    const double idj = J[9];
+    int base, stride;
+    line_of_fpt<N>(f, j, base, stride);
+    const int side = face_sgn(f) > 0 ? 1 : 0;
+    double w[N];
+#pragma unroll
+    for (int m = 0; m < N; m++) w[m] = A.tL[side][m];
+    double uo[NF], un[NF], fn[NF], vn[NF];
+    {
+      double g[NF * ND], fv[NF * ND];
+#pragma unroll
+      for (int k = 0; k < NF; k++)
+      {
+        uo[k] = S.sf[k][q];
+        double gr[ND];
+#pragma unroll
+        for (int c = 0; c < ND; c++)
+        {
+          const double *x = S.sg[c * NF + k] + e * NU + base;
+          double a = 0.;
+#pragma unroll
+          for (int m = 0; m < N; m++) a += w[m] * x[m * stride];
+          gr[c] = a * idj;
+        }
+        g[k] = gr[0] * J[0] + gr[1] * J[1] + gr[2] * J[2];
+        g[k + 5] = gr[0] * J[3] + gr[1] * J[4] + gr[2] * J[5];
+        g[k + 10] = gr[0] * J[6] + gr[1] * J[7] + gr[2] * J[8];
+      }
+      vis_flux_fast(uo, g, fv, A.P);
+      const double *n = &S.em[e][10 + 4 * f + 1];
+      const double n0 = n[0], n1 = n[1], n2 = n[2];
+      vn[0] = 0.;
+#pragma unroll
+      for (int k = 1; k < NF; k++) vn[k] = fv[k] * n0 + fv[k + 5] * n1 + fv[k + 10] * n2;
+    }
+    {
+      const double *n = &S.em[e][10 + 4 * f + 1];
+      const double nl[3] = {n[0], n[1], n[2]};
+      double ul[NF], ur[NF];
+#pragma unroll
+      for (int k = 0; k < NF; k++)
+      {
+        un[k] = S.sx[k][q];
+        ul[k] = is_right ? un[k] : uo[k];
+        ur[k] = is_right ? uo[k] : un[k];
+      }
+      riemann_fast(ul, ur, nl, fn, A.P);
+    }
+    const double ts = is_right ? -A.P.ldg_tau : A.P.ldg_tau;
+    fn[0] -= ts * (un[0] - uo[0]);
+#pragma unroll
+    for (int k = 1; k < NF; k++) fn[k] += vn[k] - ts * (un[k] - uo[k]);
+    double *out = A.fv + ((size_t)S.ge[e] * 6 + f) * (NF * NN) + j;
+#pragma unroll
+    for (int k = 0; k < NF; k++) out[k * NN] = fn[k];
+  }
+}
+
+template <int N, int E, int NT, int MINB>
+__global__ void __launch_bounds__(NT, MINB) k_grad7(const __grid_constant__ fused_args A)
+{
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  typedef smem7<N, E> SM;
+  SM &S = *reinterpret_cast<SM *>(smem_raw);
+  constexpr int NN = N * N, NFP = 6 * NN;
+  const int l0 = A.lo + blockIdx.x * E;
+  const int ne = min(E, A.hi - l0);
+  if (threadIdx.x == 0) S.n_owned = 0;
+  stage7<N, E, NT, false>(S, A, l0, ne);
+  cp_async_wait_all();
+  __syncthreads();
+  for (int q = threadIdx.x; q < ne * NFP; q += NT)
+  {
+    const int e = q / NFP, r = q - e * NFP, f = r / NN;
+    if (own_bit(S.own[e][f], r - f * NN)) S.olist[atomicAdd(&S.n_owned, 1)] = (unsigned short)q;
+  }
+  pass_L7<N, E, NT, 0, true>(S, A, ne);
+  pass_L7<N, E, NT, 1, true>(S, A, ne);
+  pass_L7<N, E, NT, 2, true>(S, A, ne);
+  __syncthreads();
+  pass_GF7<N, E, NT>(S, A, ne);
+}
+
+// divergence pass, one-sided variant: the common flux comes from sf (scaled per face), the z pass finishes with the RK
+// update and publishes the z-face values at the flux points this element does not own
+template <int N, int E, int NT, int DIR, typename SM>
+__device__ __forceinline__ void pass_D7(SM &S, const fused_args &A, int ne)
+{
+  constexpr int NN = N * N, NU = N * NN, NFP = 6 * NN, stride = line_dir<N, DIR>::stride, FM = line_dir<N, DIR>::fminus, FP = line_dir<N, DIR>::fplus;
+  for (int t = threadIdx.x; t < NF * NN; t += NT)
+  {
+    int k, base, jm, jp;
+    line_task<N, DIR>(t, k, base, jm, jp);
+#pragma unroll
+    for (int e = 0; e < E; e++)
+    {
+      if (e >= ne) break;
+      const double *x = S.sg[DIR * NF + k] + e * NU + base;
+      double v[N];
+#pragma unroll
+      for (int j = 0; j < N; j++) v[j] = x[j * stride];
+      double nm = A.tL[0][0] * v[0], np = A.tL[1][0] * v[0];
+#pragma unroll
+      for (int j = 1; j < N; j++) { nm += A.tL[0][j] * v[j]; np += A.tL[1][j] * v[j]; }
+      const bool own_m = own_bit(S.own[e][FM], jm), own_p = own_bit(S.own[e][FP], jp);
+      // a partition neighbour evaluated fc along its own (opposite) normal
+      double sm = S.scl[e][FM], sp = S.scl[e][FP];
+      if ((S.finfo[e][FM] & 8) && !own_m) sm = -sm;
+      if ((S.finfo[e][FP] & 8) && !own_p) sp = -sp;
+      const double dm = S.sf[k][e * NFP + FM * NN + jm] * sm + nm;
+      const double dp = S.sf[k][e * NFP + FP * NN + jp] * sp - np;
+      double *o = S.sg[k] + e * NU + base;
+      double out[N];
+#pragma unroll
+      for (int i = 0; i < N; i++)
+      {
+        double acc = A.tD[i * N] * v[0];
+#pragma unroll
+        for (int j = 1; j < N; j++) acc += A.tD[i * N + j] * v[j];
+        acc += A.tc3[FP * N + i] * dp;
+        acc += A.tc3[FM * N + i] * dm;
+        out[i] = acc;
+      }
+      if (DIR == 0)
+      {
+#pragma unroll
+        for (int i = 0; i < N; i++) o[i * stride] = out[i];
+      }
+      else if (DIR == 1)
+      {
+#pragma unroll
+        for (int i = 0; i < N; i++) o[i * stride] += out[i];
+      }
+      else
+      {
+        const int ge = S.ge[e];
+        const double inv_detjac = S.em[e][9];
+        const double dtl = A.dt_local ? A.dt_local[ge] : A.rk.dt;
+        const double dt_fac = A.dt_local ? dtl / A.rk.fac : A.rk.dt_fac;
+        const size_t gi0 = (size_t)base + (size_t)NU * ge + (size_t)k * NU * A.n_eles;
+        double *us = S.su[k] + e * NU + base;
+        double unew[N];
+#pragma unroll
+        for (int i = 0; i < N; i++)
+        {
+          const double acc = o[i * stride] + out[i];
+          const size_t gi = gi0 + i * stride;
+          if (A.keep_residual) A.div[gi] = acc;
+          double u = us[i * stride];
+          if (A.do_update)
+          {
+            const double rr = acc * inv_detjac;
+            if (A.rk.copy_u1) A.u1[gi] = u;
+            if (A.rk.mode == 0)
+              u -= dt_fac * rr;
+            else if (A.rk.mode == 1)
+              u = A.rk.c1 * u + A.rk.c2 * A.u1[gi] + dt_fac * (-rr);
+            else
+            {
+              const double dlt = A.rk.c1 * A.u1[gi] + dtl * (-rr);
+              A.u1[gi] = dlt;
+              u += A.rk.c2 * dlt;
+            }
+            A.u0_out[gi] = u;
+            us[i * stride] = u;
+          }
+          unew[i] = u;
+        }
+        if (A.do_update)
+        {
+          // the owner of a flux-point pair is the only reader of the other side's value there
+          double *blk = A.fu_next + (size_t)ge * 6 * (NF * NN) + k * NN;
+          if (!own_m)
+          {
+            double um = A.tL[0][0] * unew[0];
+#pragma unroll
+            for (int j = 1; j < N; j++) um += A.tL[0][j] * unew[j];
+            blk[FM * (NF * NN) + jm] = um;
+          }
+          if (!own_p)
+          {
+            double up = A.tL[1][0] * unew[0];
+#pragma unroll
+            for (int j = 1; j < N; j++) up += A.tL[1][j] * unew[j];
+            blk[FP * (NF * NN) + jp] = up;
+          }
+        }
+      }
+    }
+  }
+}
+
+template <int N, int E, int NT, int DIR, typename SM>
+__device__ __forceinline__ void pass_FO7(SM &S, const fused_args &A, int ne)
+{
+  constexpr int NN = N * N, NU = N * NN, stride = line_dir<N, DIR>::stride, FM = line_dir<N, DIR>::fminus, FP = line_dir<N, DIR>::fplus;
+  for (int t = threadIdx.x; t < NF * NN; t += NT)
+  {
+    int k, base, jm, jp;
+    line_task<N, DIR>(t, k, base, jm, jp);
+#pragma unroll
+    for (int e = 0; e < E; e++)
+    {
+      if (e >= ne) break;
+      const bool pub_m = !own_bit(S.own[e][FM], jm), pub_p = !own_bit(S.own[e][FP], jp);
+      const double *x = S.su[k] + e * NU + base;
+      double v[N];
+#pragma unroll
+      for (int j = 0; j < N; j++) v[j] = x[j * stride];
+      double *blk = A.fu_next + (size_t)S.ge[e] * 6 * (NF * NN) + k * NN;
+      if (pub_m)
+      {
+        double um = 0.;
+#pragma unroll
+        for (int j = 0; j < N; j++) um += A.tL[0][j] * v[j];
+        blk[FM * (NF * NN) + jm] = um;
+      }
+      if (pub_p)
+      {
+        double up = 0.;
+#pragma unroll
+        for (int j = 0; j < N; j++) up += A.tL[1][j] * v[j];
+        blk[FP * (NF * NN) + jp] = up;
+      }
+    }
+  }
+}
+
+template <int N, int E, int NT, int MINB>
+__global__ void __launch_bounds__(NT, MINB) k_resid7(const __grid_constant__ fused_args A)
+{
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  typedef smem7<N, E> SM;
+  SM &S = *reinterpret_cast<SM *>(smem_raw);
+  constexpr int NN = N * N, NU = N * NN;
+  const int tid = threadIdx.x;
+  const int l0 = A.lo + blockIdx.x * E;
+  const int ne = min(E, A.hi - l0);
+  stage7<N, E, NT, true>(S, A, l0, ne);
+  cp_async_wait_all();
+  __syncthreads();
+  if (tid < ne * 6)
+  {
+    // norm_tconf of this element = fc * scl: minus on the right side of an interior face
+    const int e = tid / 6, f = tid - e * 6;
+    const double tdA = S.em[e][10 + 4 * f];
+    S.scl[e][f] = (S.finfo[e][f] & 4) ? -tdA : tdA;
+  }
+  pass_L7<N, E, NT, 0, false>(S, A, ne);
+  pass_L7<N, E, NT, 1, false>(S, A, ne);
+  pass_L7<N, E, NT, 2, false>(S, A, ne);
+  __syncthreads();
+  for (int q = tid; q < ne * NU; q += NT)
+  {
+    const int e = q / NU;
+    const double *J = S.em[e];
+    double u[NF], f[NF * ND];
+#pragma unroll
+    for (int k = 0; k < NF; k++) u[k] = S.su[k][q];
+    inv_flux_fast(u, f, A.P.gamma - 1.0);
+    {
+      double g[NF * ND], fv[NF * ND];
+      const double idj = J[9];
+#pragma unroll
+      for (int k = 0; k < NF; k++)
+      {
+        const double g0 = S.sg[k][q] * idj, g1 = S.sg[NF + k][q] * idj, g2 = S.sg[2 * NF + k][q] * idj;
+        g[k] = g0 * J[0] + g1 * J[1] + g2 * J[2];
+        g[k + 5] = g0 * J[3] + g1 * J[4] + g2 * J[5];
+        g[k + 10] = g0 * J[6] + g1 * J[7] + g2 * J[8];
+      }
+      vis_flux_fast(u, g, fv, A.P);
+#pragma unroll
+      for (int d = 0; d < ND; d++)
+#pragma unroll
+        for (int k = 1; k < NF; k++) f[k + NF * d] += fv[k + NF * d];
+    }
+#pragma unroll
+    for (int k = 0; k < NF; k++)
+#pragma unroll
+      for (int l = 0; l < ND; l++) S.sg[l * NF + k][q] = J[l] * f[k] + J[l + 3] * f[k + 5] + J[l + 6] * f[k + 10];
+  }
+  __syncthreads();
+  pass_D7<N, E, NT, 0>(S, A, ne);
+  __syncthreads();
+  pass_D7<N, E, NT, 1>(S, A, ne);
+  __syncthreads();
+  pass_D7<N, E, NT, 2>(S, A, ne);
+  if (!A.do_update) return;
+  __syncthreads();
+  pass_FO7<N, E, NT, 0>(S, A, ne);
+  pass_FO7<N, E, NT, 1>(S, A, ne);
+}

@@ -86,7 +86,7 @@ extern "C" int hf_dev_nccl_init(hf_ctx *c, const void *unique_id_128_bytes)
   nccl_comm_t comm = nullptr;
   HF_NCCL(g_nccl.comm_init(&comm, c->nproc, id, c->rank));
   c->nccl_comm = comm;
-  return 0;
+  return hf_fused_after_nccl(c);
 }
 
 int hf_halo_post(hf_ctx *c, hf_mpi_inters_dev &I, const double *out, double *in, size_t per_inter)

@@ -233,6 +233,9 @@ long long hf_dev_launch_count(hf_ctx *ctx);
 int hf_dev_set_mode(hf_ctx *ctx, int fused);
 /* "available", or the reason the fused kernels cannot be used for this mesh / input (the staged kernels then run) */
 const char *hf_dev_fused_status(hf_ctx *ctx);
+/* which fused kernel pair runs: "generation 7 (one-sided LDG ...)" when |ldg_beta| = 0.5 (each flux-point pair has one
+ * owner that evaluates the whole common flux), else "generation 6 ..." with the reason; "none" without fused kernels */
+const char *hf_dev_fused_variant(hf_ctx *ctx);
 /* CUDA-event timing on the compute stream: start/stop bracket, elapsed in milliseconds. */
 int hf_dev_timer_start(hf_ctx *ctx);
 int hf_dev_timer_stop(hf_ctx *ctx, float *ms);

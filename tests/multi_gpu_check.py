@@ -50,6 +50,7 @@ def main():
         run.set_mode(False)
     else:
         assert run.fused_status() == "available", run.fused_status()
+    variant = run.fused_variant() if mode != "staged" else "staged"
     run.run(steps, fused=True)
     u = run.download("hex", "disu_upts")
     gid = run.host_array("hex.ele2global_ele")
@@ -74,8 +75,8 @@ def main():
         sc[1:4] = sc[1:4].max()
         err = (np.abs(got - ref).reshape(-1, 5).max(0) / sc).max()
         ok = bool(err < 1e-12)
-        print("multi_gpu_check: world=%d n=%d order=%d steps=%d mode=%s partition faces on rank 0: %d  max rel err vs single domain %.3e  %s"
-              % (world, n, order, steps, mode, n_mpi, err, "OK" if ok else "FAIL"))
+        print("multi_gpu_check: world=%d n=%d order=%d steps=%d mode=%s [%s] partition faces on rank 0: %d  max rel err vs single domain %.3e  %s"
+              % (world, n, order, steps, mode, variant, n_mpi, err, "OK" if ok else "FAIL"))
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.broadcast(flag, src=0)
     dist.barrier()

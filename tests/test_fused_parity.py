@@ -9,9 +9,33 @@ import pytest
 import util
 from test_staged_parity import CASES, make_case, check
 
+import os
+
+# fused-only cases: other LDG parameters (beta = -0.5 flips the owner of every flux-point pair, tau != 0 adds the penalty
+# term; beta = 0.25 has no single owner and must run the two-sided generation-6 kernels; a sheared mesh is affine with
+# normals that are not axis aligned)
+CASES.update({
+    "hex_p2_ns_hllc_betaneg_tau": ("hex", 4, {}, dict(order=2, adv_type=2, riemann_solve_type=3, viscous=1, dt=2e-5, ldg_beta=-0.5, ldg_tau=0.1)),
+    # RoeM on the Taylor-Green field needs a shifted box: its f = |Ma|^h factor (reference src/inters.cpp:400-404) is
+    # ill-conditioned at Ma -> 0 (h ~ 1e-3: a normal Mach number of 1e-17 instead of 3e-17 changes f by 1e-3), and with
+    # faces ON the vortex's symmetry planes the face-normal velocity is pure rounding noise, so any evaluation order other
+    # than the reference's own (the fused kernels use FMA and reciprocals) moves the solution by ~1e-8 (measured 7e-9;
+    # the staged kernels, which keep the reference's order, stay bit-identical there).  Off the symmetry planes RoeM
+    # agrees to 1e-12 like the other solvers.
+    "hex_p3_ns_roem_beta025": ("hex", 3, dict(origin=(0.3, 0.2, 0.1)), dict(order=3, adv_type=3, riemann_solve_type=2, viscous=1, dt=1e-5, ldg_beta=0.25, ldg_tau=0.05)),
+    "hex_p3_ns_roem_rk34": ("hex", 3, dict(origin=(0.3, 0.2, 0.1)), dict(order=3, adv_type=2, riemann_solve_type=2, viscous=1, dt=1e-5)),
+})
 FUSED_CASES = ["hex_p2_ns_hllc_rk34", "hex_p3_ns_rusanov_rk45", "hex_p2_euler_roem_rk24", "hex_p1_ns_sutherland_euler", "hex_p4_ns_hllc_rk34",
-               "hex_p2_euler_hllc_shockcap"]  # the last one: fused stages + the shock-capturing kernel after each of them
+               "hex_p2_euler_hllc_shockcap",  # fused stages + the shock-capturing kernel after each of them
+               "hex_p2_ns_hllc_betaneg_tau", "hex_p3_ns_roem_beta025", "hex_p3_ns_roem_rk34"]
 TOL = 1e-12
+
+
+def expected_variant(name):
+    o = CASES[name][3]
+    if not o["viscous"]:
+        return "generation 6 (inviscid"
+    return "generation 7" if abs(o.get("ldg_beta", 0.5)) == 0.5 else "generation 6 (two-sided"
 
 
 @pytest.mark.gpu
@@ -24,6 +48,7 @@ def test_fused_steps_vs_reference(tmp_path, hb, meshgen, name):
     ref = util.run_reference(inp, n_steps, stagewise=False)
     with hb.Run(inp) as run:
         assert run.fused_status() == "available", run.fused_status()
+        assert run.fused_variant().startswith(expected_variant(name)), run.fused_variant()
         n0 = run.launch_count()
         run.run(n_steps, fused=True)
         assert run.launch_count() > n0
@@ -47,6 +72,27 @@ def test_fused_residual_only_vs_staged(tmp_path, hb, meshgen, name):
         run.calc_residual(0)
         fused = run.download("hex", "div_tconf_upts")
         check("div_tconf_upts fused vs staged", fused, staged, 5e-11)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["hex_p2_ns_hllc_rk34", "hex_p4_ns_hllc_rk34", "hex_p2_ns_hllc_betaneg_tau"])
+def test_two_sided_kernels_on_one_sided_cases(tmp_path, hb, meshgen, name, monkeypatch):
+    """The generation-6 (two-sided LDG) kernels stay the path for |beta| != 0.5: keep them checked on the cases that
+    normally run generation 7, and check that the two generations agree to rounding."""
+    inp = make_case(tmp_path, meshgen, name)
+    with hb.Run(inp) as run:
+        assert run.fused_variant().startswith("generation 7")
+        run.run(2, fused=True)
+        u7 = run.download("hex", "disu_upts")
+    monkeypatch.setenv("HF_FUSED_GEN6", "1")
+    with hb.Run(inp) as run:
+        assert run.fused_variant().startswith("generation 6 (two-sided")
+        run.run(2, fused=True)
+        u6 = run.download("hex", "disu_upts")
+    check("generation 7 vs 6", u7, u6, 1e-13)
+    if util.have_reference():
+        ref = util.run_reference(inp, 2, stagewise=False)
+        check("generation 6 vs reference", u6, ref["final.hex.disu_upts"], TOL)
 
 
 @pytest.mark.gpu
