@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 
 import util
-from test_staged_parity import CASES, make_case, check
+from test_staged_parity import CASES, EULER_IC, make_case, check
 
 import os
 
@@ -16,18 +16,21 @@ import os
 # normals that are not axis aligned)
 CASES.update({
     "hex_p2_ns_hllc_betaneg_tau": ("hex", 4, {}, dict(order=2, adv_type=2, riemann_solve_type=3, viscous=1, dt=2e-5, ldg_beta=-0.5, ldg_tau=0.1)),
-    # RoeM on the Taylor-Green field needs a shifted box: its f = |Ma|^h factor (reference src/inters.cpp:400-404) is
-    # ill-conditioned at Ma -> 0 (h ~ 1e-3: a normal Mach number of 1e-17 instead of 3e-17 changes f by 1e-3), and with
-    # faces ON the vortex's symmetry planes the face-normal velocity is pure rounding noise, so any evaluation order other
-    # than the reference's own (the fused kernels use FMA and reciprocals) moves the solution by ~1e-8 (measured 7e-9;
-    # the staged kernels, which keep the reference's order, stay bit-identical there).  Off the symmetry planes RoeM
-    # agrees to 1e-12 like the other solvers.
-    "hex_p3_ns_roem_beta025": ("hex", 3, dict(origin=(0.3, 0.2, 0.1)), dict(order=3, adv_type=3, riemann_solve_type=2, viscous=1, dt=1e-5, ldg_beta=0.25, ldg_tau=0.05)),
-    "hex_p3_ns_roem_rk34": ("hex", 3, dict(origin=(0.3, 0.2, 0.1)), dict(order=3, adv_type=2, riemann_solve_type=2, viscous=1, dt=1e-5)),
+    # two-sided generation-6 kernels (beta = 0.25 has no single owner) and RoeM with viscosity, on the vortex field of the
+    # Euler case (box with exactly representable geometry)
+    "hex_p2_ns_roem_vortex_beta025": ("hex", 4, dict(lengths=(20.,) * 3, origin=(-10.,) * 3),
+                                      dict(order=2, adv_type=3, riemann_solve_type=2, viscous=1, dt=1e-3, ic_form=0, test_case=1, dx_cyclic=20.,
+                                           dy_cyclic=20., dz_cyclic=20., ldg_beta=0.25, ldg_tau=0.05, **EULER_IC)),
+    "hex_p2_ns_roem_vortex": ("hex", 4, dict(lengths=(20.,) * 3, origin=(-10.,) * 3),
+                              dict(order=2, adv_type=2, riemann_solve_type=2, viscous=1, dt=1e-3, ic_form=0, test_case=1, dx_cyclic=20.,
+                                   dy_cyclic=20., dz_cyclic=20., **EULER_IC)),
+    "hex_p3_ns_rusanov_beta025": ("hex", 3, {}, dict(order=3, adv_type=3, riemann_solve_type=0, viscous=1, dt=1e-5, ldg_beta=0.25, ldg_tau=0.05)),
+    # RoeM on the Taylor-Green box: see test_roem_on_rounding_level_normal_mach
+    "hex_p3_ns_roem_tgv": ("hex", 3, dict(origin=(0.3, 0.2, 0.1)), dict(order=3, adv_type=2, riemann_solve_type=2, viscous=1, dt=1e-5)),
 })
 FUSED_CASES = ["hex_p2_ns_hllc_rk34", "hex_p3_ns_rusanov_rk45", "hex_p2_euler_roem_rk24", "hex_p1_ns_sutherland_euler", "hex_p4_ns_hllc_rk34",
                "hex_p2_euler_hllc_shockcap",  # fused stages + the shock-capturing kernel after each of them
-               "hex_p2_ns_hllc_betaneg_tau", "hex_p3_ns_roem_beta025", "hex_p3_ns_roem_rk34"]
+               "hex_p2_ns_hllc_betaneg_tau", "hex_p2_ns_roem_vortex_beta025", "hex_p2_ns_roem_vortex", "hex_p3_ns_rusanov_beta025"]
 TOL = 1e-12
 
 
@@ -93,6 +96,28 @@ def test_two_sided_kernels_on_one_sided_cases(tmp_path, hb, meshgen, name, monke
     if util.have_reference():
         ref = util.run_reference(inp, 2, stagewise=False)
         check("generation 6 vs reference", u6, ref["final.hex.disu_upts"], TOL)
+
+
+@pytest.mark.gpu
+def test_roem_on_rounding_level_normal_mach(tmp_path, hb, meshgen):
+    """RoeM's f = |Ma_n|^h factor (reference src/inters.cpp:400-404, with the `Ma_n != 0 ? pow : 1` switch) is discontinuous
+    at Ma_n = 0: h ~ 1e-5..1e-3, so f jumps from exactly 1 at Ma_n = 0 to 1 - 46 h at Ma_n = 1e-20.  On the Taylor-Green box
+    (w = 0 initially, face normals with 1e-16 noise from the 2 pi geometry) the face-normal Mach number of many flux points IS
+    rounding noise, so the flux depends on the rounding of every product: the staged kernels (the reference's operation
+    order, no FMA) reproduce the reference bit for bit, the fused kernels (FMA, sum-factorised operators) land 1e-8 .. 1e-6
+    away -- with the reciprocal-based RoeM and with the reference's own RoeM formulas alike (measured: the same 1.907e-06).
+    HLLC / Rusanov on the same case, and RoeM on a field without such points (hex_p2_ns_roem_vortex), agree to 1e-12."""
+    if not util.have_reference():
+        pytest.skip("oracle/_ref not built")
+    inp = make_case(tmp_path, meshgen, "hex_p3_ns_roem_tgv")
+    ref = util.run_reference(inp, 3, stagewise=False)
+    with hb.Run(inp) as run:
+        run.set_mode(False)
+        run.run(3, fused=False)
+        check("staged", run.download("hex", "disu_upts"), ref["final.hex.disu_upts"], 1e-14)
+    with hb.Run(inp) as run:
+        run.run(3, fused=True)
+        check("fused", run.download("hex", "disu_upts"), ref["final.hex.disu_upts"], 1e-4)
 
 
 @pytest.mark.gpu

@@ -86,3 +86,15 @@ def test_input_errors_match_reference_behaviour(tmp_path, hb, meshgen):
     inp = meshgen.write_input(str(tmp_path / "input2"), "does_not_exist.neu", order=1)
     with pytest.raises(hb.HiFiLESError, match="Unable to open mesh file"):
         hb.Run(inp, host_only=True)
+
+
+def test_fused_kernels_sass_sanity():
+    """ptxas 12.9 miscompiled one instantiation of the fused residual kernel (a shared-memory address built on the stack
+    pointer / an unrelated thread offset; found as 'misaligned address' on the GPU): tools/sass_sanity.py looks for that
+    pattern in every fused kernel of the built object."""
+    import subprocess, sys
+    obj = os.path.join(util.ROOT, "hifiles-solver_b200", "build", "hf_fused.cu.o")
+    if not os.path.exists(obj):
+        pytest.skip("object file not built")
+    r = subprocess.run([sys.executable, os.path.join(util.ROOT, "tools", "sass_sanity.py"), obj], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout[-2000:]
