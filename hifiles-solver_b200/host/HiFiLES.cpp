@@ -1,6 +1,7 @@
 // Driver with the reference's command line: HiFiLES <input_file>  (reference src/HiFiLES.cpp:41-343).
 // Output is reduced to what the hot path's parity comparators need: the residual table on stdout and history.plt
 // (reference src/output.cpp:2250-2408).  Plot / restart / probe writers are out of scope.
+#include <unistd.h>
 #include "hifiles.h"
 #include <cstdio>
 #include <ctime>
@@ -99,7 +100,8 @@ int main(int argc, char *argv[])
     InitSolution(&FlowSol);
     int RKSteps = get_n_rk_steps(run_input.adv_type);
     int n_fields = (run_input.equation == 0) ? FlowSol.n_dims + 2 : 1;
-    FILE *hist = fopen("history.plt", "w");
+    // a restarted run appends to an existing history file (reference src/output.cpp:2277-2288)
+    FILE *hist = fopen("history.plt", (run_input.restart_flag != 0 && access("history.plt", W_OK) != -1) ? "a" : "w");
     clock_t init_time = clock();
     int i_steps = 0;
     while (i_steps < run_input.n_steps)

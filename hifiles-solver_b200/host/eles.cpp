@@ -208,6 +208,13 @@ void eles::set_ics(double &time)
     }
   }
 
+  set_h_ref();
+}
+
+// element reference lengths for the CFL time step (computed after the initial data are set, from the analytic field or
+// from a restart file: reference src/eles.cpp:470-486, 732-749)
+void eles::set_h_ref()
+{
   if (run_input.dt_type > 0)
   {
     h_ref.setup(n_eles);

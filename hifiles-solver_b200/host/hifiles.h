@@ -243,6 +243,7 @@ public:
 
   void setup(int in_n_eles, int in_max_n_spts_per_ele);
   void set_ics(double &time);
+  void set_h_ref();
   void set_rank(int in_rank) { rank = in_rank; }
   void set_device(hf_ctx *in_ctx) { ctx = in_ctx; }
 
@@ -526,6 +527,8 @@ void ReadMesh(struct solution *FlowSol, mesh &mesh_data);
 void InitSolution(struct solution *FlowSol);
 void CalcResidual(int in_file_num, int in_rk_stage, struct solution *FlowSol);
 void calc_time_step(struct solution *FlowSol);
+/*! read ASCII restart files Rest_<iter>_p<file>.dat (reference src/solver.cpp:377-434) */
+void read_restart_ascii(int in_file_num, int in_n_files, struct solution *FlowSol);
 /*! output::CalcNormResidual (reference src/output.cpp:2166-2248): fills FlowSol->norm_residual */
 void CalcNormResidual(struct solution *FlowSol);
 int get_n_rk_steps(int adv_type);

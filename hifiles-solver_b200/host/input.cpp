@@ -168,8 +168,12 @@ void input::read_input_file(const string &fileName, int rank)
   opts.getScalarValue("test_case", test_case, 0);
   opts.getScalarValue("n_steps", n_steps);
   opts.getScalarValue("restart_flag", restart_flag, 0);
-  if (restart_flag)
-    FatalError("restart files are outside the hot-path scope of this build (SURVEY.md §8f)");
+  if (restart_flag) // 0: new case; 1: ascii restart file; 2: hdf5 restart file
+  {
+    opts.getScalarValue("restart_iter", restart_iter);
+    if (restart_flag == 1) opts.getScalarValue("n_restart_files", n_restart_files); // ascii files need to know number of files
+    else if (restart_flag == 2) FatalError("To read HDF5 resart file, HiFiLES have to be compiled with HDF5");
+  }
 
   /* ---- Monitoring ---- */
   opts.getScalarValue("plot_freq", plot_freq, INT32_MAX);

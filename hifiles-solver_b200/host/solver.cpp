@@ -118,11 +118,19 @@ static void upload_all(struct solution *FlowSol)
 
 void InitSolution(struct solution *FlowSol)
 {
-  if (run_input.restart_flag != 0)
-    FatalError("restart files are outside the hot-path scope of this build");
-  FlowSol->ini_iter = 0;
-  for (int i = 0; i < FlowSol->n_ele_types; i++)
-    if (FlowSol->mesh_eles(i)->get_n_eles() != 0) FlowSol->mesh_eles(i)->set_ics(FlowSol->time);
+  if (run_input.restart_flag == 0)
+  {
+    FlowSol->ini_iter = 0;
+    for (int i = 0; i < FlowSol->n_ele_types; i++)
+      if (FlowSol->mesh_eles(i)->get_n_eles() != 0) FlowSol->mesh_eles(i)->set_ics(FlowSol->time);
+  }
+  else if (run_input.restart_flag == 1) // read ascii restart files
+  {
+    FlowSol->ini_iter = run_input.restart_iter;
+    read_restart_ascii(run_input.restart_iter, run_input.n_restart_files, FlowSol);
+  }
+  else
+    FatalError("HiFiLES need to be compiled with HDF5 to read hdf5 format restart file");
   if (!FlowSol->no_device) upload_all(FlowSol);
 }
 
