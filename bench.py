@@ -163,6 +163,7 @@ def main():
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--cpu-n", type=int, default=10, help="elements per direction of the CPU baseline sample")
     ap.add_argument("--staged", action="store_true", help="time the staged (reference-order) kernels instead of the fused ones")
+    ap.add_argument("--partition", default="bricks", choices=["bricks", "metis"], help="N > 1: brick partition of the cube, or METIS k-way of the dual graph (the reference's ParMETIS call)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -200,7 +201,7 @@ def main():
             hb, mg, inp = make_case(work, args.n, args.order)
     part, nccl_id = None, None
     if world > 1:
-        part = mg.block_partition(args.n, mg.blocks_for(world))
+        part = mg.block_partition(args.n, mg.blocks_for(world)) if args.partition == "bricks" else None
         idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
         if rank == 0:
             idt = torch.tensor(list(hb.nccl_unique_id()), dtype=torch.uint8, device="cuda")
@@ -323,7 +324,7 @@ def main():
                                    "1 step = 1 time step = %d RK stages" % (args.n, args.order, n_rk),
                        "kernels": "fused" if fused else "staged", "elements_per_gpu": n_eles, "dof_total": dof_total,
                        "l2": "no flush needed: state per GPU %.2f GB >> 126 MB L2" % (dof_local * 8 / 1e9), "setup_s": round(t_setup, 1),
-                       "partition": "bricks %s" % (mg.blocks_for(world),) if world > 1 else "none"},
+                       "partition": ("bricks %s" % (mg.blocks_for(world),) if args.partition == "bricks" else "METIS k-way (dual graph)") if world > 1 else "none"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
             "residual_finite": finite,
         }

@@ -715,6 +715,9 @@ int launch(hf_ctx *c, hf_fused_state *Z, fused_args &A, int what, int lo, int hi
     if (cfg == 3) return launch_all<5, 1, 125, 6>(c, Z, A, what, lo, hi);
     if (cfg == 4) return launch_all<5, 1, 64, 8>(c, Z, A, what, lo, hi);
     if (cfg == 5) return launch_all<5, 2, 250, 1>(c, Z, A, what, lo, hi);
+    if (cfg == 6) return launch_all<5, 1, 96, 5>(c, Z, A, what, lo, hi);
+    if (cfg == 7) return launch_all<5, 2, 160, 2>(c, Z, A, what, lo, hi);
+    if (cfg == 8) return launch_all<5, 1, 96, 6>(c, Z, A, what, lo, hi);
     return launch_all<5, 2, 125, 3>(c, Z, A, what, lo, hi);
   }
   case 5: return launch_all<6, 1, 128, 3>(c, Z, A, what, lo, hi);

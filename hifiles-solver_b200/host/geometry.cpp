@@ -218,8 +218,10 @@ static void build_rank_mesh(struct solution *FlowSol, mesh &mesh_data, int rank)
   m_r.partial_read_connectivity(0, mesh_data.num_cells_global);
   if (FlowSol->nproc > 1)
   {
+    // no partition handed in: partition the dual graph as the reference's repartition_mesh does (METIS instead of ParMETIS)
+    if (FlowSol->part.empty()) partition_mesh_kway(mesh_data, mesh_data.n_dims, FlowSol->nproc, FlowSol->part);
     if ((int)FlowSol->part.size() != mesh_data.num_cells_global)
-      FatalError("partition vector missing or of the wrong size");
+      FatalError("partition vector of the wrong size");
     mesh_data.apply_partition(FlowSol->part, rank);
   }
   mesh_data.create_iv2ivg();

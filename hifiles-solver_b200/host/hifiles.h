@@ -196,6 +196,7 @@ public:
   static int compare_faces(const int *vlist1, const int *vlist2, int num_v_per_f, int &rtag);
   /*! keep the cells with part[global cell] == rank, in ascending global id (reference src/mesh.cpp:188-311) */
   void apply_partition(const std::vector<int> &part, int rank);
+  int get_corner_vlist(int in_ic, int *v) const;
 
   int n_dims, n_ele_dims, n_bdy;
   int num_verts_global, num_cells_global, num_verts, num_cells, num_inters, n_unmatched_inters;
@@ -527,6 +528,8 @@ void ReadMesh(struct solution *FlowSol, mesh &mesh_data);
 void InitSolution(struct solution *FlowSol);
 void CalcResidual(int in_file_num, int in_rk_stage, struct solution *FlowSol);
 void calc_time_step(struct solution *FlowSol);
+/*! k-way partition of the mesh's dual graph (METIS), the serial counterpart of the reference's ParMETIS call (src/mesh.cpp:72-183) */
+void partition_mesh_kway(const mesh &m, int n_dims, int nproc, std::vector<int> &part);
 /*! read ASCII restart files Rest_<iter>_p<file>.dat (reference src/solver.cpp:377-434) */
 void read_restart_ascii(int in_file_num, int in_n_files, struct solution *FlowSol);
 /*! output::CalcNormResidual (reference src/output.cpp:2166-2248): fills FlowSol->norm_residual */

@@ -37,6 +37,8 @@ def worker(rank, world, port, workdir, n, order, part_kind, q):
         dist.init_process_group("gloo", rank=rank, world_size=world)
         if part_kind == "bricks":
             part = mg.block_partition(n, mg.blocks_for(world))
+        elif part_kind == "metis":
+            part = None  # the host mirror partitions the dual graph itself (METIS), identically on every rank
         else:
             part = np.random.default_rng(11).integers(0, world, n ** 3).astype(np.int32)
         inp = os.path.join(workdir, "input")
@@ -65,7 +67,7 @@ def worker(rank, world, port, workdir, n, order, part_kind, q):
         q.put("rank %d: %s\n%s" % (rank, e, traceback.format_exc()))
 
 
-@pytest.mark.parametrize("world,part_kind", [(2, "bricks"), (2, "random"), (4, "bricks")])
+@pytest.mark.parametrize("world,part_kind", [(2, "bricks"), (2, "random"), (4, "bricks"), (2, "metis"), (4, "metis")])
 def test_halo_pairing_rules(tmp_path, hb, meshgen, world, part_kind):
     import torch.multiprocessing as mp
     n, order = 4, 2
@@ -73,7 +75,7 @@ def test_halo_pairing_rules(tmp_path, hb, meshgen, world, part_kind):
     meshgen.write_input(str(tmp_path / "input"), "m.neu", order=order)
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 29600 + world * 7 + (3 if part_kind == "random" else 0)
+    port = 29600 + world * 7 + {"bricks": 0, "random": 3, "metis": 5}[part_kind]
     procs = [ctx.Process(target=worker, args=(r, world, port, str(tmp_path), n, order, part_kind, q)) for r in range(world)]
     for p in procs:
         p.start()
@@ -86,6 +88,10 @@ def test_halo_pairing_rules(tmp_path, hb, meshgen, world, part_kind):
     assert sorted(allg.tolist()) == list(range(n ** 3))
     for r in res:
         assert np.all(np.diff(r["gid"]) > 0)
+    if part_kind == "metis":
+        # k-way partition with the reference's 5 % imbalance tolerance (src/mesh.cpp:152-155); METIS may exceed it slightly on tiny graphs
+        sizes = [len(r["gid"]) for r in res]
+        assert max(sizes) <= 1.15 * n ** 3 / world and min(sizes) > 0, sizes
     L = 2 * np.pi
     nn = order + 1
     total = 0

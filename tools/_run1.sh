@@ -1,8 +1,5 @@
 mkdir -p gpurun_out
-( time timeout 1500 python -m pytest tests -q -m gpu -x ) > gpurun_out/t_all.log 2>&1; echo "tests exit $?" >> gpurun_out/t_all.log
-tail -6 gpurun_out/t_all.log
-python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
-timeout 600 python bench.py > gpurun_out/bench_default.log 2>&1; tail -1 gpurun_out/bench_default.log
-timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_ref.log 2>&1; tail -1 gpurun_out/bench_ref.log
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_r01c.csv python bench.py --steps 2 --warmup 3 --no-cpu --no-e2e > gpurun_out/ncu_list.log 2>&1
-wc -l gpurun_out/launches_r01c.csv
+for g in 3 4 6 7 8; do
+  HF_FUSED_CFG_G=$g timeout 300 python bench.py --steps 4 --warmup 3 --no-cpu --no-e2e > gpurun_out/g_$g.log 2>&1
+  echo "cfg_g $g: $(tail -1 gpurun_out/g_$g.log | python -c 'import sys,json; d=json.loads(sys.stdin.read()); print(round(d["value"],2), round(d["ms_per_step"]/4,3), round(d["roofline"]["launch_ms"],3))' 2>&1 | tail -1)"
+done
