@@ -949,6 +949,106 @@ static int build_ell(hf_ctx *c, hf_ell &E, const double *dense, int rows, int co
   return 0;
 }
 
+// ---- integral diagnostics (eles::CalcIntegralQuantities, reference src/eles.cpp:5485-5628) ------------------------------------
+// One CTA per element: thread j interpolates the solution and its physical gradient to volume cubature point j with
+// opp_volume_cubpts (sum over solution points in ascending order, as the reference), evaluates the requested
+// quantities there and weighs them with weight * detjac; thread q then adds the element's terms in cubature-point order.
+// The host adds the per-element sums in element order, so the only difference to the reference's single running sum is
+// the grouping by element.
+struct hf_iq_kinds { int n; int kind[HF_MAX_INTEGRAL_QUANTITIES]; };
+template <int ND>
+__global__ void k_integral_quantities(int n_eles, int n_upts, int n_cub, const double *__restrict__ u, const double *__restrict__ grad,
+                                      const double *__restrict__ opp, const double *__restrict__ w, const double *__restrict__ detjac,
+                                      const int *__restrict__ pos, hf_iq_kinds K, double gamma, double *__restrict__ elem_out)
+{
+  constexpr int NF = ND + 2;
+  extern __shared__ double terms[]; // [q][n_cub]
+  const int i = blockIdx.x;
+  const size_t s = pos ? pos[i] : i;
+  const size_t fs = (size_t)n_upts * n_eles;
+  for (int j = threadIdx.x; j < n_cub; j += blockDim.x)
+  {
+    double uc[NF], gc[NF][ND];
+    for (int m = 0; m < NF; m++)
+    {
+      double a = 0.;
+      for (int k = 0; k < n_upts; k++) a += opp[j + (size_t)n_cub * k] * u[k + n_upts * s + fs * m];
+      uc[m] = a;
+    }
+    for (int m = 0; m < NF; m++)
+      for (int n = 0; n < ND; n++)
+      {
+        double a = 0.;
+        for (int k = 0; k < n_upts; k++) a += opp[j + (size_t)n_cub * k] * grad[k + n_upts * s + fs * (m + NF * n)];
+        gc[m][n] = a;
+      }
+    const double irho = 1. / uc[0];
+    double dv[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}}; // dv[a][b] = d v_a / d x_b
+    for (int a = 0; a < ND; a++)
+      for (int b = 0; b < ND; b++) dv[a][b] = irho * (gc[1 + a][b] - uc[1 + a] * irho * gc[0][b]);
+    const double wd = w[j] * detjac[j + (size_t)n_cub * i];
+    for (int q = 0; q < K.n; q++)
+    {
+      double diagnostic = 0.0;
+      const int kind = K.kind[q];
+      if (kind == 0) // kineticenergy
+      {
+        double tke = 0.0;
+        for (int n = 1; n < ND + 1; n++) tke += 0.5 * uc[n] * uc[n];
+        diagnostic = irho * tke;
+      }
+      else if (kind == 1) // enstropy
+      {
+        const double wz = dv[1][0] - dv[0][1];
+        diagnostic = wz * wz;
+        if (ND == 3)
+        {
+          const double wx = dv[2][1] - dv[1][2], wy = dv[0][2] - dv[2][0];
+          diagnostic += wx * wx + wy * wy;
+        }
+        diagnostic *= 0.5 / irho;
+      }
+      else if (kind == 2) // pressuredilatation
+      {
+        double tke = 0.0;
+        for (int n = 1; n < ND + 1; n++) tke += 0.5 * uc[n] * uc[n];
+        const double pressure = (gamma - 1.0) * (uc[ND + 1] - irho * tke);
+        diagnostic = (ND == 2) ? pressure * (dv[0][0] + dv[1][1]) : pressure * (dv[0][0] + dv[1][1] + dv[2][2]);
+      }
+      else // straincolonproduct (3), devstraincolonproduct (4)
+      {
+        double S[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+        S[0][0] = dv[0][0];
+        S[0][1] = (dv[0][1] + dv[1][0]) / 2.0;
+        S[1][0] = S[0][1];
+        S[1][1] = dv[1][1];
+        double diag = (S[0][0] + S[1][1]) / 3.0;
+        if (ND == 3)
+        {
+          S[0][2] = (dv[0][2] + dv[2][0]) / 2.0;
+          S[1][2] = (dv[1][2] + dv[2][1]) / 2.0;
+          S[2][0] = S[0][2];
+          S[2][1] = S[1][2];
+          S[2][2] = dv[2][2];
+          diag += S[2][2] / 3.0;
+        }
+        if (kind == 4)
+          for (int a = 0; a < ND; a++) S[a][a] -= diag;
+        for (int a = 0; a < ND; a++)
+          for (int b = 0; b < ND; b++) diagnostic += S[a][b] * S[a][b];
+      }
+      terms[q * n_cub + j] = diagnostic * wd;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < K.n)
+  {
+    double sum = 0.;
+    for (int j = 0; j < n_cub; j++) sum += terms[threadIdx.x * n_cub + j];
+    elem_out[(size_t)i * K.n + threadIdx.x] = sum;
+  }
+}
+
 extern "C" {
 
 const char *hf_dev_last_error(void) { return g_err.c_str(); }
@@ -1907,6 +2007,55 @@ int hf_dev_upload(hf_ctx *c, int ele_type, int which, const double *host, size_t
     HF_CUDA(cudaMemcpyAsync(p, host, n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
   HF_CUDA(cudaStreamSynchronize(c->stream));
   c->ufpts_valid = false;
+  return 0;
+}
+
+int hf_dev_set_volume_cubature(hf_ctx *c, int ele_type, int n_cubpts, const double *opp_volume_cubpts, const double *weights, const double *vol_detjac)
+{
+  HF_CUDA(cudaSetDevice(c->device));
+  if (ele_type < 0 || ele_type >= HF_N_ELE_TYPES || !c->eles[ele_type].present) HF_FAIL("element type not present on the device");
+  hf_eles_dev &e = c->eles[ele_type];
+  if (n_cubpts <= 0) HF_FAIL("volume cubature without points");
+  e.n_vol_cub = n_cubpts;
+  if (hf_alloc_copy(c, &e.opp_vol_cub, opp_volume_cubpts, (size_t)n_cubpts * e.n_upts)) return 1;
+  if (hf_alloc_copy(c, &e.w_vol_cub, weights, (size_t)n_cubpts)) return 1;
+  if (hf_alloc_copy(c, &e.detjac_vol_cub, vol_detjac, (size_t)n_cubpts * e.n_eles)) return 1;
+  if (hf_alloc_zero(c, &e.iq_elem, (size_t)e.n_eles * HF_MAX_INTEGRAL_QUANTITIES)) return 1;
+  c->want_gradient = true;
+  return 0;
+}
+
+int hf_dev_integral_quantities(hf_ctx *c, int ele_type, int n_quantities, const int *kinds, double *out)
+{
+  HF_CUDA(cudaSetDevice(c->device));
+  if (ele_type < 0 || ele_type >= HF_N_ELE_TYPES || !c->eles[ele_type].present) HF_FAIL("element type not present on the device");
+  hf_eles_dev &e = c->eles[ele_type];
+  if (!e.n_vol_cub) HF_FAIL("hf_dev_set_volume_cubature has not been called for this element type");
+  if (n_quantities < 1 || n_quantities > HF_MAX_INTEGRAL_QUANTITIES) HF_FAIL("number of integral quantities out of range");
+  if (c->prm.equation != 0) HF_FAIL("integral quantities are defined for the Euler / Navier-Stokes equations");
+  if (!e.grad_disu_upts)
+    HF_FAIL("integral quantities need grad_disu_upts of the last residual evaluation (viscous run, residual kept on the monitored stage)");
+  hf_iq_kinds K;
+  K.n = n_quantities;
+  for (int q = 0; q < n_quantities; q++)
+  {
+    if (kinds[q] < 0 || kinds[q] > 4) HF_FAIL("integral diagnostic quantity not recognized");
+    K.kind[q] = kinds[q];
+  }
+  const size_t smem = (size_t)n_quantities * e.n_vol_cub * sizeof(double);
+  const int *pos = e.pos.empty() ? nullptr : e.d_pos;
+  if (e.n_dims == 2)
+    k_integral_quantities<2><<<e.n_eles, 128, smem, c->stream>>>(e.n_eles, e.n_upts, e.n_vol_cub, e.disu_upts[0], e.grad_disu_upts, e.opp_vol_cub, e.w_vol_cub,
+                                                                 e.detjac_vol_cub, pos, K, c->phys.gamma, e.iq_elem);
+  else
+    k_integral_quantities<3><<<e.n_eles, 128, smem, c->stream>>>(e.n_eles, e.n_upts, e.n_vol_cub, e.disu_upts[0], e.grad_disu_upts, e.opp_vol_cub, e.w_vol_cub,
+                                                                 e.detjac_vol_cub, pos, K, c->phys.gamma, e.iq_elem);
+  HF_LAUNCH_CHECK(c);
+  std::vector<double> h((size_t)e.n_eles * n_quantities);
+  HF_CUDA(cudaMemcpyAsync(h.data(), e.iq_elem, h.size() * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  HF_CUDA(cudaStreamSynchronize(c->stream));
+  for (int i = 0; i < e.n_eles; i++)
+    for (int q = 0; q < n_quantities; q++) out[q] += h[(size_t)i * n_quantities + q];
   return 0;
 }
 

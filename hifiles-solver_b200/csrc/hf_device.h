@@ -58,6 +58,9 @@ struct hf_eles_dev
   double ele_vol_factor = 0.;
   hf_ell filter_upts;
   double *disuf_upts = nullptr, *uu = nullptr, *ue = nullptr, *Lu = nullptr, *Le = nullptr;
+  // volume cubature of the integral diagnostics (eles::CalcIntegralQuantities)
+  int n_vol_cub = 0;
+  double *opp_vol_cub = nullptr, *w_vol_cub = nullptr, *detjac_vol_cub = nullptr, *iq_elem = nullptr;
   // shock capturing (dense, row-major access by mode)
   double *inv_vandermonde = nullptr, *exp_filter = nullptr, *sensor_w_top = nullptr, *sensor_w_all = nullptr, *sensor = nullptr;
   double *detjac_upts = nullptr, *JGinv_upts = nullptr, *detjac_fpts = nullptr, *JGinv_fpts = nullptr;
@@ -131,6 +134,7 @@ struct hf_ctx
   bool have_params = false;
   int fused = 1;
   bool finalized = false;
+  bool want_gradient = false; // integral diagnostics requested: the fused kernels also store grad_disu_upts when they keep the residual
   bool ufpts_valid = false; // disu_fpts holds opp_0 * current disu_upts(0) (fused path bookkeeping)
   hf_eles_dev eles[HF_N_ELE_TYPES];
   hf_int_inters_dev ints[HF_N_INTER_TYPES];

@@ -108,6 +108,7 @@ struct fused_args
   double *u0_out;
   double *u1;
   double *div;            // written when keep_residual
+  double *grad_out;       // grad_disu_upts (upt,ele,field,dim): physical gradient at solution points, written when non-null (integral diagnostics)
   const double *fu_cur;   // face u, read (neighbours)
   double *fu_next;        // face u of the updated solution, written (own faces)
   double *fv;             // one-sided viscous normal flux at flux points (4 per point): written by k_grad, read by k_resid;
@@ -654,16 +655,20 @@ int launch_all(hf_ctx *c, hf_fused_state *Z, fused_args &A, int what, int lo, in
   {
     HF_CUDA(cudaFuncSetAttribute(k_face_values6<N, E, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_g));
     HF_CUDA(cudaFuncSetAttribute(k_grad6<N, E, NT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_g));
-    HF_CUDA(cudaFuncSetAttribute(k_resid6<N, E, NT, MINB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_r));
-    HF_CUDA(cudaFuncSetAttribute(k_resid6<N, E, NT, MINB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_r));
+    HF_CUDA(cudaFuncSetAttribute(k_resid6<N, E, NT, MINB, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_r));
+    HF_CUDA(cudaFuncSetAttribute(k_resid6<N, E, NT, MINB, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_r));
+    HF_CUDA(cudaFuncSetAttribute(k_resid6<N, E, NT, MINB, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_r));
     // ask for the largest shared-memory carve-out so that MINB blocks fit on an SM
     HF_CUDA(cudaFuncSetAttribute(k_grad6<N, E, NT, MINB>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-    HF_CUDA(cudaFuncSetAttribute(k_resid6<N, E, NT, MINB, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-    HF_CUDA(cudaFuncSetAttribute(k_resid6<N, E, NT, MINB, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    HF_CUDA(cudaFuncSetAttribute(k_resid6<N, E, NT, MINB, true, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    HF_CUDA(cudaFuncSetAttribute(k_resid6<N, E, NT, MINB, true, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    HF_CUDA(cudaFuncSetAttribute(k_resid6<N, E, NT, MINB, false, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     HF_CUDA(cudaFuncSetAttribute(k_grad7<N, E, NT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(smem7<N, E>)));
-    HF_CUDA(cudaFuncSetAttribute(k_resid7<N, E, NT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(smem7<N, E>)));
+    HF_CUDA(cudaFuncSetAttribute(k_resid7<N, E, NT, MINB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(smem7<N, E>)));
+    HF_CUDA(cudaFuncSetAttribute(k_resid7<N, E, NT, MINB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(smem7<N, E>)));
     HF_CUDA(cudaFuncSetAttribute(k_grad7<N, E, NT, MINB>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-    HF_CUDA(cudaFuncSetAttribute(k_resid7<N, E, NT, MINB>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    HF_CUDA(cudaFuncSetAttribute(k_resid7<N, E, NT, MINB, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    HF_CUDA(cudaFuncSetAttribute(k_resid7<N, E, NT, MINB, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     attr_done = true;
   }
   if (what == 0)
@@ -675,14 +680,16 @@ int launch_all(hf_ctx *c, hf_fused_state *Z, fused_args &A, int what, int lo, in
   else if (what == 4)
   {
     hf_ktimer_begin(c);
-    k_resid7<N, E, NT, MINB><<<grid, NT, sizeof(smem7<N, E>), c->stream>>>(A);
+    if (A.grad_out) k_resid7<N, E, NT, MINB, true><<<grid, NT, sizeof(smem7<N, E>), c->stream>>>(A);
+    else k_resid7<N, E, NT, MINB, false><<<grid, NT, sizeof(smem7<N, E>), c->stream>>>(A);
     hf_ktimer_end(c);
   }
   else
   {
     hf_ktimer_begin(c);
-    if (A.viscous) k_resid6<N, E, NT, MINB, true><<<grid, NT, smem_r, c->stream>>>(A);
-    else k_resid6<N, E, NT, MINB, false><<<grid, NT, smem_r, c->stream>>>(A);
+    if (A.viscous && A.grad_out) k_resid6<N, E, NT, MINB, true, true><<<grid, NT, smem_r, c->stream>>>(A);
+    else if (A.viscous) k_resid6<N, E, NT, MINB, true, false><<<grid, NT, smem_r, c->stream>>>(A);
+    else k_resid6<N, E, NT, MINB, false, false><<<grid, NT, smem_r, c->stream>>>(A);
     hf_ktimer_end(c);
   }
   c->launches++;
@@ -707,17 +714,14 @@ int launch(hf_ctx *c, hf_fused_state *Z, fused_args &A, int what, int lo, int hi
     static const int cfg_g = getenv("HF_FUSED_CFG_G") ? atoi(getenv("HF_FUSED_CFG_G")) : cfg_all;
     static const int cfg_r = getenv("HF_FUSED_CFG_R") ? atoi(getenv("HF_FUSED_CFG_R")) : cfg_all;
     int cfg = (what == 1 || what == 3) ? cfg_g : ((what == 2 || what == 4) ? cfg_r : cfg_all);
-    // measured on B200 (64^3): k_resid7 is fastest with one element per CTA and six CTAs per SM (80 registers), k_grad7 with
-    // two elements per CTA and three CTAs per SM
+    // measured on B200 (64^3): both generation-7 kernels are fastest with one element per CTA and six CTAs per SM (80
+    // registers; k_grad7 is within 2 % of that for every shape tried, profiles/ncu_r01_summary.md)
     if (what == 4 && !getenv("HF_FUSED_CFG_R") && !getenv("HF_FUSED_CFG")) cfg = 3;
+    if (what == 3 && !getenv("HF_FUSED_CFG_G") && !getenv("HF_FUSED_CFG")) cfg = 3;
     if (cfg == 1) return launch_all<5, 1, 125, 4>(c, Z, A, what, lo, hi);
     if (cfg == 2) return launch_all<5, 1, 125, 5>(c, Z, A, what, lo, hi);
     if (cfg == 3) return launch_all<5, 1, 125, 6>(c, Z, A, what, lo, hi);
-    if (cfg == 4) return launch_all<5, 1, 64, 8>(c, Z, A, what, lo, hi);
-    if (cfg == 5) return launch_all<5, 2, 250, 1>(c, Z, A, what, lo, hi);
-    if (cfg == 6) return launch_all<5, 1, 96, 5>(c, Z, A, what, lo, hi);
-    if (cfg == 7) return launch_all<5, 2, 160, 2>(c, Z, A, what, lo, hi);
-    if (cfg == 8) return launch_all<5, 1, 96, 6>(c, Z, A, what, lo, hi);
+    // shapes measured and dropped (profiles/ncu_r01_summary.md): <5,1,64,8>, <5,2,250,1>, <5,1,96,5>, <5,2,160,2>, <5,1,96,6>, <5,2,256,2>, <5,3,192,2>
     return launch_all<5, 2, 125, 3>(c, Z, A, what, lo, hi);
   }
   case 5: return launch_all<6, 1, 128, 3>(c, Z, A, what, lo, hi);
@@ -797,6 +801,13 @@ int hf_fused_stage(hf_ctx *c, int rk_stage, double time, int keep_residual, int 
   base_args(c, Z, A);
   A.keep_residual = keep_residual;
   A.do_update = do_update;
+  if (keep_residual && c->want_gradient && c->prm.viscous)
+  {
+    // integral diagnostics read grad_disu_upts as the last residual evaluation left it (reference src/eles.cpp:5515-5525)
+    hf_eles_dev &eh = c->eles[4];
+    if (!eh.grad_disu_upts && hf_alloc_zero(c, &eh.grad_disu_upts, (size_t)eh.n_upts * eh.n_eles * NF * ND)) return 1;
+    A.grad_out = eh.grad_disu_upts;
+  }
   const hf_params &p = c->prm;
   rk_args &R = A.rk;
   R.dt = p.dt; R.fac = 1.0; R.mode = 0; R.copy_u1 = 0; R.c1 = R.c2 = 0.;

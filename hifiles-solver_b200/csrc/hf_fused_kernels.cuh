@@ -437,7 +437,7 @@ __device__ __forceinline__ void pass_FO(SM &S, const fused_args &A, int ne)
   }
 }
 
-template <int N, int E, int NT, int MINB, bool VISC>
+template <int N, int E, int NT, int MINB, bool VISC, bool GOUT>
 __global__ void __launch_bounds__(NT, MINB) k_resid6(const __grid_constant__ fused_args A)
 {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -476,6 +476,14 @@ __global__ void __launch_bounds__(NT, MINB) k_resid6(const __grid_constant__ fus
         g[k + 10] = g0 * J[6] + g1 * J[7] + g2 * J[8];
       }
       vis_flux_fast(u, g, fv, A.P);
+      if constexpr (GOUT) // integral diagnostics: grad_disu_upts of this residual evaluation (a separate instantiation: the stores cost registers)
+      {
+        const size_t gi = (size_t)(q - e * NU) + (size_t)NU * S.ge[e], fs = (size_t)NU * A.n_eles;
+#pragma unroll
+        for (int d = 0; d < ND; d++)
+#pragma unroll
+          for (int k = 0; k < NF; k++) A.grad_out[gi + fs * (k + NF * d)] = g[k + NF * d];
+      }
 #pragma unroll
       for (int d = 0; d < ND; d++)
 #pragma unroll
@@ -943,7 +951,7 @@ __device__ __forceinline__ void pass_FO7(SM &S, const fused_args &A, int ne)
   }
 }
 
-template <int N, int E, int NT, int MINB>
+template <int N, int E, int NT, int MINB, bool GOUT>
 __global__ void __launch_bounds__(NT, MINB) k_resid7(const __grid_constant__ fused_args A)
 {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -987,6 +995,14 @@ __global__ void __launch_bounds__(NT, MINB) k_resid7(const __grid_constant__ fus
         g[k + 10] = g0 * J[6] + g1 * J[7] + g2 * J[8];
       }
       vis_flux_fast(u, g, fv, A.P);
+      if constexpr (GOUT) // integral diagnostics: grad_disu_upts of this residual evaluation (a separate instantiation: the stores cost registers)
+      {
+        const size_t gi = (size_t)(q - e * NU) + (size_t)NU * S.ge[e], fs = (size_t)NU * A.n_eles;
+#pragma unroll
+        for (int d = 0; d < ND; d++)
+#pragma unroll
+          for (int k = 0; k < NF; k++) A.grad_out[gi + fs * (k + NF * d)] = g[k + NF * d];
+      }
 #pragma unroll
       for (int d = 0; d < ND; d++)
 #pragma unroll

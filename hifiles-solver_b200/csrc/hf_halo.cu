@@ -128,6 +128,21 @@ int hf_halo_allreduce_min(hf_ctx *c, double *v)
   return 0;
 }
 
+/* sum of v[n] over the ranks, result on every rank (the reference reduces its diagnostics to rank 0 with MPI_Reduce(SUM),
+ * src/output.cpp:2030-2037) */
+extern "C" int hf_dev_allreduce_sum(hf_ctx *c, double *v, int n)
+{
+  if (c->nproc < 2) return 0;
+  if (!c->nccl_comm) { hf_set_error("multi-rank context but hf_dev_nccl_init was not called"); return 1; }
+  if ((size_t)n * sizeof(double) > c->scratch_bytes) { hf_set_error("hf_dev_allreduce_sum: too many values"); return 1; }
+  HF_CUDA(cudaSetDevice(c->device));
+  HF_CUDA(cudaMemcpyAsync(c->scratch, v, n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  HF_NCCL(g_nccl.allreduce(c->scratch, c->scratch, (size_t)n, k_nccl_float64, 0 /* ncclSum */, (nccl_comm_t)c->nccl_comm, c->stream));
+  HF_CUDA(cudaMemcpyAsync(v, c->scratch, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  HF_CUDA(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
 void hf_halo_destroy(hf_ctx *c)
 {
   if (c->nccl_comm && g_nccl.comm_destroy) g_nccl.comm_destroy((nccl_comm_t)c->nccl_comm);

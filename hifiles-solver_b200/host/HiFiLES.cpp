@@ -101,24 +101,39 @@ int main(int argc, char *argv[])
     int RKSteps = get_n_rk_steps(run_input.adv_type);
     int n_fields = (run_input.equation == 0) ? FlowSol.n_dims + 2 : 1;
     // a restarted run appends to an existing history file (reference src/output.cpp:2277-2288)
-    FILE *hist = fopen("history.plt", (run_input.restart_flag != 0 && access("history.plt", W_OK) != -1) ? "a" : "w");
+    const bool append = run_input.restart_flag != 0 && access("history.plt", W_OK) != -1;
+    FILE *hist = fopen("history.plt", append ? "a" : "w");
+    const int n_diags = run_input.n_integral_quantities;
+    if (hist && !append)
+    {
+      // header of output::HistoryOutput (reference src/output.cpp:2299-2343)
+      fprintf(hist, "TITLE = \"HiFiLES simulation\"\nVARIABLES = \"Iteration\"");
+      if (run_input.equation == 0)
+      {
+        if (FlowSol.n_dims == 2)
+          fprintf(hist, ",\"log<sub>10</sub>(Res[<greek>r</greek>])\",\"log<sub>10</sub>(Res[<greek>r</greek>v<sub>x</sub>])\",\"log<sub>10</sub>(Res[<greek>r</greek>v<sub>y</sub>])\",\"log<sub>10</sub>(Res[<greek>r</greek>E])\"");
+        else
+          fprintf(hist, ",\"log<sub>10</sub>(Res[<greek>r</greek>])\",\"log<sub>10</sub>(Res[<greek>r</greek>v<sub>x</sub>])\",\"log<sub>10</sub>(Res[<greek>r</greek>v<sub>y</sub>])\",\"log<sub>10</sub>(Res[<greek>r</greek>v<sub>z</sub>])\",\"log<sub>10</sub>(Res[<greek>r</greek>E])\"");
+      }
+      else
+        fprintf(hist, ",\"log<sub>10</sub>(Res[<greek>r</greek>])\"");
+      for (int i = 0; i < n_diags; i++) fprintf(hist, ",\"Diagnostics[%s]\"", run_input.integral_quantities(i).c_str());
+      fprintf(hist, ",\"Time<sub>Physical</sub>(sec)\",\"Time<sub>Comp</sub>(m)\"\nZONE T= \"Convergence history\"\n");
+    }
     clock_t init_time = clock();
     int i_steps = 0;
     while (i_steps < run_input.n_steps)
     {
       calc_time_step(&FlowSol);
-      for (int i = 0; i < RKSteps; i++)
-      {
-        CalcResidual(FlowSol.ini_iter + i_steps, i, &FlowSol);
-        for (int j = 0; j < FlowSol.n_ele_types; j++) FlowSol.mesh_eles(j)->AdvanceSolution(i, run_input.adv_type);
-        if (run_input.shock_cap)
-          for (int j = 0; j < FlowSol.n_ele_types; j++) FlowSol.mesh_eles(j)->shock_capture();
-      }
+      // the residual (and the gradient behind the integral diagnostics) of the last stage is read after monitored steps
+      const bool monitored = (i_steps + 1 == 1) || ((i_steps + 1) % run_input.monitor_res_freq == 0);
+      for (int i = 0; i < RKSteps; i++) AdvanceStage(FlowSol.ini_iter + i_steps, i, &FlowSol, monitored && i == RKSteps - 1);
       FlowSol.time += run_input.dt;
       run_input.time = FlowSol.time;
       i_steps++;
       if (i_steps == 1 || i_steps % run_input.monitor_res_freq == 0)
       {
+        if (n_diags) CalcIntegralQuantities(&FlowSol);
         CalcNormResidual(&FlowSol);
         if (i_steps == 1) printf("\n  Iter       Res[Rho]   Res[RhoVelx]   Res[RhoVely]%s      Res[RhoE]\n", FlowSol.n_dims == 3 ? "   Res[RhoVelz]" : "");
         printf("%6d", FlowSol.ini_iter + i_steps);
@@ -128,6 +143,8 @@ int main(int argc, char *argv[])
         {
           fprintf(hist, "%d", FlowSol.ini_iter + i_steps);
           for (int f = 0; f < n_fields; f++) fprintf(hist, ", %.15g", log10(FlowSol.norm_residual(f)));
+          for (int q = 0; q < n_diags; q++) fprintf(hist, ", %.15g", FlowSol.integral_quantities(q));
+          fprintf(hist, ", %.15g", (run_input.viscous && run_input.equation == 0) ? FlowSol.time * run_input.time_ref : FlowSol.time);
           fprintf(hist, ", %.15g\n", (double)(clock() - init_time) / CLOCKS_PER_SEC / 60.);
         }
       }

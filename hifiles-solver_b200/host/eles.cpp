@@ -361,6 +361,13 @@ void eles::set_transforms()
   set_transforms_upts();
   if (run_input.over_int) set_transforms_over_int_cubpts();
   set_transforms_fpts();
+  // metrics at the volume cubature points: only needed for the integral diagnostic quantities (reference src/eles.cpp:4026-4028)
+  if (run_input.n_integral_quantities != 0)
+  {
+    set_volume_cubpts(order, loc_volume_cubpts, weight_volume_cubpts);
+    set_opp_volume_cubpts();
+    set_transforms_vol_cubpts();
+  }
 }
 
 namespace
@@ -585,6 +592,9 @@ void eles::mv_all_cpu_gpu()
     d.exp_filter = exp_filter.get_ptr_cpu();
   }
   hf_check(hf_dev_upload_eles(ctx, &d));
+  if (run_input.n_integral_quantities != 0)
+    hf_check(hf_dev_set_volume_cubature(ctx, ele_type, loc_volume_cubpts.get_dim(1), opp_volume_cubpts.get_ptr_cpu(), weight_volume_cubpts.get_ptr_cpu(),
+                                        vol_detjac_vol_cubpts.get_ptr_cpu()));
 }
 
 void eles::cp_disu_upts_cpu_gpu()
@@ -650,4 +660,58 @@ double eles::compute_res_upts(int in_norm_type, int in_field)
       else if (in_norm_type == 2) sum += r * r;
     }
   return sum;
+}
+
+// ---- integral diagnostics ---------------------------------------------------------------------------------------------------
+// interpolation solution points -> volume cubature points (reference eles::set_opp_volume_cubpts, src/eles.cpp:3667-3687)
+void eles::set_opp_volume_cubpts()
+{
+  const int nc = loc_volume_cubpts.get_dim(1);
+  hf_array<double> loc(n_dims);
+  opp_volume_cubpts.setup(nc, n_upts_per_ele);
+  for (int i = 0; i < n_upts_per_ele; i++)
+    for (int j = 0; j < nc; j++)
+    {
+      for (int k = 0; k < n_dims; k++) loc(k) = loc_volume_cubpts(k, j);
+      opp_volume_cubpts(j, i) = eval_nodal_basis(i, loc);
+    }
+}
+
+// Jacobian determinant at the volume cubature points (reference eles::set_transforms_vol_cubpts, src/eles.cpp:4599-4632)
+void eles::set_transforms_vol_cubpts()
+{
+  const int nc = loc_volume_cubpts.get_dim(1);
+  hf_array<double> d_pos(n_dims, n_dims), loc(n_dims);
+  vol_detjac_vol_cubpts.setup(nc, n_eles);
+  for (int i = 0; i < n_eles; i++)
+    for (int j = 0; j < nc; j++)
+    {
+      for (int m = 0; m < n_dims; m++) loc(m) = loc_volume_cubpts(m, j);
+      calc_d_pos(loc, i, d_pos);
+      if (n_dims == 2)
+        vol_detjac_vol_cubpts(j, i) = d_pos(0, 0) * d_pos(1, 1) - d_pos(0, 1) * d_pos(1, 0);
+      else
+        vol_detjac_vol_cubpts(j, i) = d_pos(0, 0) * (d_pos(1, 1) * d_pos(2, 2) - d_pos(1, 2) * d_pos(2, 1)) -
+                                      d_pos(0, 1) * (d_pos(1, 0) * d_pos(2, 2) - d_pos(1, 2) * d_pos(2, 0)) +
+                                      d_pos(0, 2) * (d_pos(1, 0) * d_pos(2, 1) - d_pos(1, 1) * d_pos(2, 0));
+    }
+}
+
+// reference eles::CalcIntegralQuantities (src/eles.cpp:5485-5628): one device call, adds this type's share
+void eles::CalcIntegralQuantities(int n_integral_quantities, hf_array<double> &integral_quantities)
+{
+  if (n_eles == 0) return;
+  if (n_integral_quantities > HF_MAX_INTEGRAL_QUANTITIES) FatalError("too many integral quantities");
+  int kinds[HF_MAX_INTEGRAL_QUANTITIES];
+  for (int m = 0; m < n_integral_quantities; m++)
+  {
+    const string &q = run_input.integral_quantities(m);
+    if (q == "kineticenergy") kinds[m] = 0;
+    else if (q == "enstropy") kinds[m] = 1;
+    else if (q == "pressuredilatation") kinds[m] = 2;
+    else if (q == "straincolonproduct") kinds[m] = 3;
+    else if (q == "devstraincolonproduct") kinds[m] = 4;
+    else FatalError("integral diagnostic quantity not recognized");
+  }
+  hf_check(hf_dev_integral_quantities(ctx, ele_type, n_integral_quantities, kinds, integral_quantities.get_ptr_cpu()));
 }

@@ -245,6 +245,10 @@ public:
   void setup(int in_n_eles, int in_max_n_spts_per_ele);
   void set_ics(double &time);
   void set_h_ref();
+  /*! volume cubature of the integral diagnostics (reference src/eles.cpp:3667-3687, 4599-4632, 5485-5628) */
+  void set_opp_volume_cubpts();
+  void set_transforms_vol_cubpts();
+  void CalcIntegralQuantities(int n_integral_quantities, hf_array<double> &integral_quantities);
   void set_rank(int in_rank) { rank = in_rank; }
   void set_device(hf_ctx *in_ctx) { ctx = in_ctx; }
 
@@ -335,6 +339,7 @@ public:
   int rank, ele_type, n_eles, n_dims, n_fields, order, viscous, n_inters_per_ele;
   int n_upts_per_ele, n_fpts_per_ele, max_n_spts_per_ele, n_adv_levels, upts_type;
   hf_array<int> n_fpts_per_inter, n_spts_per_ele, ele2global_ele, bcid;
+  hf_array<double> loc_volume_cubpts, weight_volume_cubpts, opp_volume_cubpts, vol_detjac_vol_cubpts; // (dim,cubpt), (cubpt), (cubpt,upt), (cubpt,ele)
   hf_array<double> loc_upts, tloc_fpts, tnorm_fpts, loc_1d_upts;
   hf_array<double> shape, d_nodal_s_basis;
   hf_array<double> opp_0, opp_3, opp_6;
@@ -515,7 +520,7 @@ struct solution
   std::vector<int_inters> mesh_int_inters;
   std::vector<bdy_inters> mesh_bdy_inters;
   std::vector<mpi_inters> mesh_mpi_inters;
-  hf_array<double> norm_residual;
+  hf_array<double> norm_residual, integral_quantities;
   hf_ctx *ctx; // device context shared by all objects of this solution
   int no_device; // 1: host pre-processing only (CPU-side tests of setup logic); any hot-path call then fails loudly
   /*! optional partition vector (global cell -> rank); empty = block partition of the reference's initial read */
@@ -528,6 +533,12 @@ void ReadMesh(struct solution *FlowSol, mesh &mesh_data);
 void InitSolution(struct solution *FlowSol);
 void CalcResidual(int in_file_num, int in_rk_stage, struct solution *FlowSol);
 void calc_time_step(struct solution *FlowSol);
+/*! output::CalcIntegralQuantities (reference src/output.cpp:2017-2040): fills FlowSol->integral_quantities (summed over ranks) */
+void CalcIntegralQuantities(struct solution *FlowSol);
+/*! CalcResidual + AdvanceSolution (+ shock_capture) of one RK stage: one fused device call where the fused kernels are
+ *  available, the reference's sequence of methods otherwise.  monitored: the residual (and, for the integral diagnostics,
+ *  the gradient) of this stage will be read afterwards. */
+void AdvanceStage(int in_file_num, int in_rk_stage, struct solution *FlowSol, bool monitored);
 /*! k-way partition of the mesh's dual graph (METIS), the serial counterpart of the reference's ParMETIS call (src/mesh.cpp:72-183) */
 void partition_mesh_kway(const mesh &m, int n_dims, int nproc, std::vector<int> &part);
 /*! read ASCII restart files Rest_<iter>_p<file>.dat (reference src/solver.cpp:377-434) */

@@ -196,6 +196,9 @@ void input::read_input_file(const string &fileName, int rank)
   opts.getVectorValueOptional("diagnostic_fields", diagnostic_fields);
   opts.getVectorValueOptional("average_fields", average_fields);
   n_integral_quantities = integral_quantities.get_dim(0);
+  for (int i = 0; i < n_integral_quantities; i++) // lower case, as the reference (src/input.cpp:120-124)
+    std::transform(integral_quantities(i).begin(), integral_quantities(i).end(), integral_quantities(i).begin(), ::tolower);
+  if (n_integral_quantities && !viscous) FatalError("integral quantities read the solution gradient: viscous run needed");
   n_diagnostic_fields = diagnostic_fields.get_dim(0);
   n_average_fields = average_fields.get_dim(0);
 

@@ -184,6 +184,31 @@ void CalcResidual(int in_file_num, int in_rk_stage, struct solution *FlowSol)
   for (int i = 0; i < n; i++) FlowSol->mesh_eles(i)->calculate_corrected_divergence();
 }
 
+// One RK stage.  The reference's main loop calls CalcResidual, then AdvanceSolution for every element type, then
+// shock_capture (src/HiFiLES.cpp:205-217); on the device the three are one fused call where the fused kernels apply.
+void AdvanceStage(int in_file_num, int in_rk_stage, struct solution *FlowSol, bool monitored)
+{
+  if (run_input.device_fused && hf_dev_fused_status(FlowSol->ctx) == string("available"))
+  {
+    hf_check(hf_dev_rk_stage(FlowSol->ctx, in_rk_stage, FlowSol->time, monitored ? 1 : 0));
+    return;
+  }
+  CalcResidual(in_file_num, in_rk_stage, FlowSol);
+  for (int j = 0; j < FlowSol->n_ele_types; j++) FlowSol->mesh_eles(j)->AdvanceSolution(in_rk_stage, run_input.adv_type);
+  if (run_input.shock_cap)
+    for (int j = 0; j < FlowSol->n_ele_types; j++) FlowSol->mesh_eles(j)->shock_capture();
+}
+
+void CalcIntegralQuantities(struct solution *FlowSol)
+{
+  const int nintq = run_input.n_integral_quantities;
+  FlowSol->integral_quantities.setup(nintq > 0 ? nintq : 1);
+  for (int q = 0; q < nintq; q++) FlowSol->integral_quantities(q) = 0.;
+  for (int i = 0; i < FlowSol->n_ele_types; i++)
+    if (FlowSol->mesh_eles(i)->get_n_eles() != 0) FlowSol->mesh_eles(i)->CalcIntegralQuantities(nintq, FlowSol->integral_quantities);
+  if (FlowSol->nproc > 1 && nintq) hf_check(hf_dev_allreduce_sum(FlowSol->ctx, FlowSol->integral_quantities.get_ptr_cpu(), nintq));
+}
+
 void calc_time_step(struct solution *FlowSol)
 {
   if (run_input.dt_type == 0) return;

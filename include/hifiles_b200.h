@@ -225,6 +225,18 @@ int hf_dev_upload(hf_ctx *ctx, int ele_type, int which, const double *host, size
 /* eles::compute_res_upts summed over element types as output::CalcNormResidual does (reference
  * src/eles.cpp:5045-5074, src/output.cpp:2166-2248); out[n_fields]. Local to this rank (no collective). */
 int hf_dev_residual_norm(hf_ctx *ctx, int norm_type, double *out);
+/* Integral diagnostics = eles::CalcIntegralQuantities (reference src/eles.cpp:5485-5628; output::CalcIntegralQuantities
+ * src/output.cpp:2017-2040): interpolation of the solution and of grad_disu_upts (as left by the last residual evaluation,
+ * the reference's semantics) to the volume cubature points, quantity * weight * detjac summed over points and elements.
+ * hf_dev_set_volume_cubature hands over opp_volume_cubpts (cubpt, upt), weight_volume_cubpts and vol_detjac_vol_cubpts
+ * (cubpt, ele) of eles::set_opp_volume_cubpts / set_transforms_vol_cubpts and makes the fused kernels store the gradient
+ * whenever they keep the residual.  kinds: 0 kineticenergy, 1 enstropy, 2 pressuredilatation, 3 straincolonproduct,
+ * 4 devstraincolonproduct.  out[n_quantities] is ADDED to (one call per element type); local to this rank. */
+#define HF_MAX_INTEGRAL_QUANTITIES 8
+int hf_dev_set_volume_cubature(hf_ctx *ctx, int ele_type, int n_cubpts, const double *opp_volume_cubpts, const double *weights, const double *vol_detjac);
+int hf_dev_integral_quantities(hf_ctx *ctx, int ele_type, int n_quantities, const int *kinds, double *out);
+/* sum of v[n] over the ranks of the context's communicator, in place on every rank (no-op on one rank) */
+int hf_dev_allreduce_sum(hf_ctx *ctx, double *v, int n);
 int hf_dev_sync(hf_ctx *ctx);
 /* kernels launched by this context since creation (bench.py reports the delta as gpu_launches) */
 long long hf_dev_launch_count(hf_ctx *ctx);

@@ -55,6 +55,39 @@ def test_command_line_matches_reference_binary(tmp_path, hb, meshgen):
     assert np.abs(out["ours"][1] - out["ref"][1]).max() <= 1e-11         # log10 of the residual norms, 15 digits
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("kernels", ["staged", "fused"])
+def test_integral_quantities_match_reference_binary(tmp_path, hb, meshgen, kernels):
+    """history.plt with the Taylor-Green diagnostics of the shipped input (integral_quantities kineticenergy enstropy, plus
+    the strain products): eles::CalcIntegralQuantities on the device, against the reference binary.  The reference
+    evaluates them with the gradient the LAST residual evaluation left behind (the solution before the final RK stage's
+    update) -- kept: the staged kernels hold that array anyway, the fused kernels store it on monitored stages."""
+    if not (os.path.exists(REF) and os.path.exists(OURS)):
+        pytest.skip("driver binaries not built")
+    out = {}
+    for who, exe in (("ref", REF), ("ours", OURS)):
+        d = tmp_path / who
+        d.mkdir()
+        meshgen.hex_box(str(d / "tgv.neu"), 3)
+        meshgen.write_input(str(d / "input"), "tgv.neu", order=3, adv_type=2, dt=1e-5, riemann_solve_type=3, viscous=1, n_steps=3, monitor_res_freq=1,
+                            integral_quantities="4 kineticenergy enstropy pressuredilatation devstraincolonproduct",
+                            device_fused=1 if kernels == "fused" else 0)
+        env = dict(os.environ, HIFILES_HOME=util.REF_DIR if who == "ref" else os.path.join(util.ROOT, "hifiles-solver_b200"))
+        r = subprocess.run([exe, "input"], cwd=str(d), env=env, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+        out[who] = history_rows(str(d / "history.plt"), 10)
+        if who == "ours":
+            head = open(d / "history.plt").read().split("ZONE")[0]
+            assert 'Diagnostics[kineticenergy]' in head and 'Diagnostics[enstropy]' in head
+    ref, ours = out["ref"], out["ours"]
+    assert ref.shape == ours.shape == (3, 10)
+    # pressure dilatation and the strain products are sums of cancelling terms: rounding of the element-wise grouping shows at 2e-12
+    tol = 1e-11 if kernels == "staged" else 1e-10
+    for q in range(5, 9):  # the four diagnostics; column 9 is the physical time
+        assert np.abs(ours[:, q] - ref[:, q]).max() <= tol * np.abs(ref[:, q]).max(), "diagnostic %d: %s vs %s" % (q - 5, ours[:, q], ref[:, q])
+    assert np.abs(ours[:, 9] - ref[:, 9]).max() <= 1e-13 * np.abs(ref[:, 9]).max()
+
+
 def restart_numbers(path):
     """structure (all non-numeric lines, in order) and numbers of an ASCII restart file"""
     text, nums = [], []
