@@ -150,6 +150,8 @@ int main(int argc, char *argv[])
       }
       if (i_steps % run_input.restart_dump_freq == 0) write_restart_ascii(&FlowSol, FlowSol.ini_iter + i_steps);
     }
+    /*! Calculate Error (reference src/HiFiLES.cpp:324-325) */
+    if (run_input.test_case) compute_error(FlowSol.ini_iter + i_steps, &FlowSol);
     if (hist) fclose(hist);
     hf_check(hf_dev_sync(FlowSol.ctx));
     printf("Execution time= %f s\n", (double)(clock() - init_time) / CLOCKS_PER_SEC);

@@ -361,8 +361,8 @@ void eles::set_transforms()
   set_transforms_upts();
   if (run_input.over_int) set_transforms_over_int_cubpts();
   set_transforms_fpts();
-  // metrics at the volume cubature points: only needed for the integral diagnostic quantities (reference src/eles.cpp:4026-4028)
-  if (run_input.n_integral_quantities != 0)
+  // metrics at the volume cubature points: only needed for computing error and integral diagnostic quantities (reference src/eles.cpp:4026-4028)
+  if (run_input.test_case != 0 || run_input.n_integral_quantities != 0)
   {
     set_volume_cubpts(order, loc_volume_cubpts, weight_volume_cubpts);
     set_opp_volume_cubpts();
@@ -714,4 +714,52 @@ void eles::CalcIntegralQuantities(int n_integral_quantities, hf_array<double> &i
     else FatalError("integral diagnostic quantity not recognized");
   }
   hf_check(hf_dev_integral_quantities(ctx, ele_type, n_integral_quantities, kinds, integral_quantities.get_ptr_cpu()));
+}
+
+// reference eles::compute_error + get_pointwise_error (src/eles.cpp:5076-5290), on the host after a device -> host copy of
+// the solution: it runs once, at the end of a test-case run.  Built: test_case 1 (isentropic vortex); the advection /
+// diffusion and Couette test cases fail loudly.
+hf_array<double> eles::compute_error(int in_norm_type, double &time)
+{
+  if (run_input.test_case != 1) FatalError("Test case not recognized in compute error, exiting");
+  hf_array<double> disu_cubpt(n_fields), pos(n_dims), temp_loc(n_dims), error_sol(n_fields);
+  hf_array<double> error_sum(2, n_fields);
+  for (int m = 0; m < n_fields; m++) error_sum(0, m) = error_sum(1, m) = 0.;
+  const int n_cubpts_per_ele = loc_volume_cubpts.get_dim(1);
+  cp_disu_upts_gpu_cpu();
+  for (int i = 0; i < n_eles; i++)
+    for (int j = 0; j < n_cubpts_per_ele; j++)
+    {
+      const double detjac = vol_detjac_vol_cubpts(j, i);
+      for (int k = 0; k < n_dims; k++) temp_loc(k) = loc_volume_cubpts(k, j);
+      calc_pos(temp_loc, i, pos);
+      for (int m = 0; m < n_fields; m++)
+      {
+        disu_cubpt(m) = 0.;
+        for (int k = 0; k < n_upts_per_ele; k++) disu_cubpt(m) += opp_volume_cubpts(j, k) * disu_upts(0)(k, i, m);
+      }
+      double rho, vx, vy, vz, p;
+      eval_isentropic_vortex(pos, time, rho, vx, vy, vz, p, n_dims);
+      error_sol(0) = disu_cubpt(0) - rho;
+      error_sol(1) = disu_cubpt(1) - rho * vx;
+      error_sol(2) = disu_cubpt(2) - rho * vy;
+      if (n_dims == 2)
+        error_sol(3) = disu_cubpt(3) - (p / (run_input.gamma - 1) + 0.5 * rho * (vx * vx + vy * vy));
+      else
+      {
+        error_sol(3) = disu_cubpt(3) - rho * vz;
+        error_sol(4) = disu_cubpt(4) - (p / (run_input.gamma - 1) + 0.5 * rho * (vx * vx + vy * vy + vz * vz));
+      }
+      for (int m = 0; m < n_fields; m++)
+      {
+        double e0;
+        if (in_norm_type == 1) e0 = fabs(error_sol(m));
+        else if (in_norm_type == 2) e0 = error_sol(m) * error_sol(m);
+        else { FatalError("Error norm not supported!"); e0 = 0.; }
+        error_sum(0, m) += e0 * weight_volume_cubpts(j) * detjac;
+        // the gradient error of this test case is identically zero (src/eles.cpp:5137-5165)
+        error_sum(1, m) += 0. * weight_volume_cubpts(j) * detjac;
+      }
+    }
+  return error_sum;
 }

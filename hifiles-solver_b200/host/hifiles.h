@@ -249,6 +249,8 @@ public:
   void set_opp_volume_cubpts();
   void set_transforms_vol_cubpts();
   void CalcIntegralQuantities(int n_integral_quantities, hf_array<double> &integral_quantities);
+  /*! error against the analytic solution of the test case, integrated over the volume cubature (reference src/eles.cpp:5076-5290) */
+  hf_array<double> compute_error(int in_norm_type, double &time);
   void set_rank(int in_rank) { rank = in_rank; }
   void set_device(hf_ctx *in_ctx) { ctx = in_ctx; }
 
@@ -535,6 +537,8 @@ void CalcResidual(int in_file_num, int in_rk_stage, struct solution *FlowSol);
 void calc_time_step(struct solution *FlowSol);
 /*! output::CalcIntegralQuantities (reference src/output.cpp:2017-2040): fills FlowSol->integral_quantities (summed over ranks) */
 void CalcIntegralQuantities(struct solution *FlowSol);
+/*! output::compute_error (reference src/output.cpp:2052-2160): appends one line to error.dat */
+void compute_error(int in_file_num, struct solution *FlowSol);
 /*! CalcResidual + AdvanceSolution (+ shock_capture) of one RK stage: one fused device call where the fused kernels are
  *  available, the reference's sequence of methods otherwise.  monitored: the residual (and, for the integral diagnostics,
  *  the gradient) of this stage will be read afterwards. */

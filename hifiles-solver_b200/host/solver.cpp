@@ -209,6 +209,41 @@ void CalcIntegralQuantities(struct solution *FlowSol)
   if (FlowSol->nproc > 1 && nintq) hf_check(hf_dev_allreduce_sum(FlowSol->ctx, FlowSol->integral_quantities.get_ptr_cpu(), nintq));
 }
 
+void compute_error(int in_file_num, struct solution *FlowSol)
+{
+  const int n_fields = (run_input.equation == 0) ? FlowSol->n_dims + 2 : 1;
+  hf_array<double> error(2, n_fields);
+  for (int j = 0; j < n_fields; j++) error(0, j) = error(1, j) = 0.;
+  for (int i = 0; i < FlowSol->n_ele_types; i++)
+    if (FlowSol->mesh_eles(i)->get_n_eles() != 0)
+    {
+      hf_array<double> t = FlowSol->mesh_eles(i)->compute_error(run_input.error_norm_type, FlowSol->time);
+      for (int j = 0; j < n_fields; j++)
+      {
+        error(0, j) += t(0, j);
+        if (run_input.viscous) error(1, j) += t(1, j);
+      }
+    }
+  if (FlowSol->nproc > 1) hf_check(hf_dev_allreduce_sum(FlowSol->ctx, error.get_ptr_cpu(), 2 * n_fields));
+  if (FlowSol->rank != 0) return;
+  if (run_input.error_norm_type == 2)
+    for (int j = 0; j < n_fields; j++)
+    {
+      error(0, j) = sqrt(error(0, j));
+      if (run_input.viscous) error(1, j) = sqrt(error(1, j));
+    }
+  else if (run_input.error_norm_type != 1)
+    FatalError("Error norm not supported!");
+  FILE *f = fopen("error.dat", "a");
+  if (!f) FatalError("cannot open error.dat");
+  fprintf(f, "%d, %d, %s, %d, %d, %d, ", in_file_num, run_input.order, run_input.mesh_file.c_str(), run_input.adv_type, run_input.riemann_solve_type,
+          run_input.error_norm_type);
+  for (int j = 0; j < n_fields; j++) fprintf(f, (j == n_fields - 1 && run_input.viscous == 0) ? "%e\n" : "%e, ", error(0, j));
+  if (run_input.viscous)
+    for (int j = 0; j < n_fields; j++) fprintf(f, j == n_fields - 1 ? "%e\n" : "%e, ", error(1, j));
+  fclose(f);
+}
+
 void calc_time_step(struct solution *FlowSol)
 {
   if (run_input.dt_type == 0) return;

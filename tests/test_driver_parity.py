@@ -88,6 +88,39 @@ def test_integral_quantities_match_reference_binary(tmp_path, hb, meshgen, kerne
     assert np.abs(ours[:, 9] - ref[:, 9]).max() <= 1e-13 * np.abs(ref[:, 9]).max()
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind", ["quad", "hex"])
+def test_vortex_error_file_matches_reference_binary(tmp_path, hb, meshgen, kind):
+    """BASELINE config 1: isentropic vortex (test_case 1) on periodic quads, P=3 -- and its 3-D twin on hexahedra (fused
+    kernels).  At the end of a test-case run the reference integrates the error against the analytic vortex over the
+    volume cubature and appends it to error.dat (src/output.cpp:2052-2160, src/eles.cpp:5076-5290): the files must agree."""
+    if not (os.path.exists(REF) and os.path.exists(OURS)):
+        pytest.skip("driver binaries not built")
+    from test_staged_parity import EULER_IC
+    lines = {}
+    for who, exe in (("ref", REF), ("ours", OURS)):
+        d = tmp_path / who
+        d.mkdir()
+        if kind == "quad":
+            meshgen.quad_box(str(d / "m.neu"), 8)
+            extra = dict(dz_cyclic=None)
+        else:
+            meshgen.hex_box(str(d / "m.neu"), 4, lengths=(20.,) * 3, origin=(-10.,) * 3)
+            extra = dict(dz_cyclic=20.)
+        meshgen.write_input(str(d / "input"), "m.neu", order=3, adv_type=3, riemann_solve_type=0, viscous=0, ic_form=0, test_case=1, dt=1e-3,
+                            dx_cyclic=20., dy_cyclic=20., n_steps=5, monitor_res_freq=5, **extra, **EULER_IC)
+        env = dict(os.environ, HIFILES_HOME=util.REF_DIR if who == "ref" else os.path.join(util.ROOT, "hifiles-solver_b200"))
+        r = subprocess.run([exe, "input"], cwd=str(d), env=env, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+        lines[who] = open(d / "error.dat").read().strip().splitlines()
+    assert len(lines["ref"]) == len(lines["ours"]) == 1
+    a, b = [t.strip() for t in lines["ref"][0].split(",")], [t.strip() for t in lines["ours"][0].split(",")]
+    assert a[:6] == b[:6]                                    # step, order, mesh file, adv_type, riemann_solve_type, norm type
+    ea, eb = np.array([float(x) for x in a[6:]]), np.array([float(x) for x in b[6:]])
+    assert ea.shape == eb.shape == ((4,) if kind == "quad" else (5,))
+    assert np.all(ea[:3] > 0) and np.abs(eb - ea).max() <= 2e-6 * np.abs(ea).max()  # printed with 7 significant digits
+
+
 def restart_numbers(path):
     """structure (all non-numeric lines, in order) and numbers of an ASCII restart file"""
     text, nums = [], []
