@@ -61,6 +61,7 @@ def lib():
     L.hifiles_n_eles.argtypes = [C.c_void_p, C.c_int]
     L.hifiles_calc_time_step.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
     L.hifiles_nccl_init.argtypes = [C.c_void_p, C.c_char_p]
+    L.hifiles_write_vtu.argtypes = [C.c_void_p, C.c_int]
     L.hf_dev_nccl_unique_id.argtypes = [C.c_char_p]
     L.hf_dev_eles_op.argtypes = [C.c_void_p, C.c_int, C.c_int]
     L.hf_dev_int_inters_op.argtypes = [C.c_void_p, C.c_int, C.c_int]
@@ -229,6 +230,10 @@ class Run:
 
     def fused_status(self):
         return lib().hf_dev_fused_status(self.ctx).decode()
+
+    def write_vtu(self, it):
+        """output::write_vtu: Paraview file(s) of the current solution in the working directory"""
+        self._ck(lib().hifiles_write_vtu(self._h, int(it)))
 
     def fused_variant(self):
         return lib().hf_dev_fused_variant(self.ctx).decode()

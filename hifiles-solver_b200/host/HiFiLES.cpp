@@ -1,6 +1,6 @@
 // Driver with the reference's command line: HiFiLES <input_file>  (reference src/HiFiLES.cpp:41-343).
 // Output is reduced to what the hot path's parity comparators need: the residual table on stdout and history.plt
-// (reference src/output.cpp:2250-2408).  Plot / restart / probe writers are out of scope.
+// (reference src/output.cpp:2250-2408).  Paraview files (plot.cpp) and ASCII restart files are written as the reference does; Tecplot / CGNS / probe writers are not built.
 #include <unistd.h>
 #include "hifiles.h"
 #include <cstdio>
@@ -122,6 +122,9 @@ int main(int argc, char *argv[])
     }
     clock_t init_time = clock();
     int i_steps = 0;
+    /*! Dump initial Paraview file (reference src/HiFiLES.cpp:171-182; Tecplot / CGNS writers are not built) */
+    if (run_input.write_type == 0) write_vtu(FlowSol.ini_iter + i_steps, &FlowSol);
+    else FatalError("ERROR: Trying to write unrecognized file format ... ");
     while (i_steps < run_input.n_steps)
     {
       calc_time_step(&FlowSol);
@@ -148,6 +151,7 @@ int main(int argc, char *argv[])
           fprintf(hist, ", %.15g\n", (double)(clock() - init_time) / CLOCKS_PER_SEC / 60.);
         }
       }
+      if (i_steps % run_input.plot_freq == 0) write_vtu(FlowSol.ini_iter + i_steps, &FlowSol);
       if (i_steps % run_input.restart_dump_freq == 0) write_restart_ascii(&FlowSol, FlowSol.ini_iter + i_steps);
     }
     /*! Calculate Error (reference src/HiFiLES.cpp:324-325) */

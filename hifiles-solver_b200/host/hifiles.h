@@ -539,6 +539,8 @@ void calc_time_step(struct solution *FlowSol);
 void CalcIntegralQuantities(struct solution *FlowSol);
 /*! output::compute_error (reference src/output.cpp:2052-2160): appends one line to error.dat */
 void compute_error(int in_file_num, struct solution *FlowSol);
+/*! output::write_vtu (reference src/output.cpp:462-900): Paraview file(s) of the current solution */
+void write_vtu(int in_file_num, struct solution *FlowSol);
 /*! CalcResidual + AdvanceSolution (+ shock_capture) of one RK stage: one fused device call where the fused kernels are
  *  available, the reference's sequence of methods otherwise.  monitored: the residual (and, for the integral diagnostics,
  *  the gradient) of this stage will be read afterwards. */

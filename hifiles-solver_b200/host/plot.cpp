@@ -1,0 +1,266 @@
+// Paraview output (reference output::write_vtu, src/output.cpp:462-900): every element becomes one <Piece> of
+// p_res-resolution plot points and linear sub-cells; density, velocity and specific total energy are interpolated from the
+// solution points with opp_p.  Plot points, their numbering and the sub-cell connectivity follow the reference's
+// per-type rules (set_loc_ppts / set_connectivity_plot of src/eles_{hexas,quads,tris,tets,pris}.cpp) so that the files
+// agree with the reference's to the printed digits.  One .vtu per run in serial; with several ranks every rank writes
+// <name>_<iter>/<name>_<iter>_<rank>.vtu and rank 0 the .pvtu index.  Optional diagnostic / time-averaged fields are not
+// built (rejected at input time).  The solution is copied device -> host first (output::CopyGPUCPU).
+#include "hifiles.h"
+#include <cstdio>
+#include <fstream>
+#include <vector>
+#include <sys/stat.h>
+#include <dirent.h>
+#include <cstring>
+using namespace std;
+
+namespace
+{
+// plot-point numbering of the simplex types: rows of decreasing length
+inline int tri_idx(int i, int j, int p) { return i + j * (p + 1) - (j * (j + 1)) / 2; }
+inline int tet_layers(int n) { return n * (n + 1) * (n + 2) / 6; }
+inline int tet_idx(int i, int j, int k, int p) { return tet_layers(p) - tet_layers(p - k) + j * (p - k) - ((j - 1) * j) / 2 + i; }
+
+struct plot_topology
+{
+  int n_ppts = 0, n_peles = 0, n_verts = 0;
+  hf_array<double> loc_ppts; // (dim, ppt)
+  vector<int> con;           // [cell][vert]
+  hf_array<double> opp_p;    // (ppt, upt)
+};
+
+void add_cell(plot_topology &T, std::initializer_list<int> v)
+{
+  for (int x : v) T.con.push_back(x);
+  T.n_peles++;
+}
+
+void build_topology(eles *e, int p, plot_topology &T)
+{
+  const int type = e->get_ele_type(), nd = e->n_dims;
+  const double h = 1.0 * (p - 1);
+  auto put = [&](int q, int i, int j, int k) {
+    T.loc_ppts(0, q) = -1.0 + ((2.0 * i) / h);
+    T.loc_ppts(1, q) = -1.0 + ((2.0 * j) / h);
+    if (nd == 3) T.loc_ppts(2, q) = -1.0 + ((2.0 * k) / h);
+  };
+  if (type == HEX)
+  {
+    T.n_ppts = p * p * p; T.n_verts = 8;
+    T.loc_ppts.setup(3, T.n_ppts);
+    for (int k = 0; k < p; k++) for (int j = 0; j < p; j++) for (int i = 0; i < p; i++) put(i + p * j + p * p * k, i, j, k);
+    for (int k = 0; k < p - 1; k++) for (int l = 0; l < p - 1; l++) for (int m = 0; m < p - 1; m++)
+    {
+      const int a = m + p * l + p * p * k, b = a + p * p;
+      add_cell(T, {a, a + 1, a + p + 1, a + p, b, b + 1, b + p + 1, b + p});
+    }
+  }
+  else if (type == QUAD)
+  {
+    T.n_ppts = p * p; T.n_verts = 4;
+    T.loc_ppts.setup(2, T.n_ppts);
+    for (int j = 0; j < p; j++) for (int i = 0; i < p; i++) put(i + p * j, i, j, 0);
+    for (int k = 0; k < p - 1; k++) for (int l = 0; l < p - 1; l++)
+    {
+      const int a = l + p * k;
+      add_cell(T, {a, a + 1, a + p + 1, a + p});
+    }
+  }
+  else if (type == TRI)
+  {
+    T.n_ppts = (p + 1) * p / 2; T.n_verts = 3;
+    T.loc_ppts.setup(2, T.n_ppts);
+    for (int j = 0; j < p; j++) for (int i = 0; i < p - j; i++) put(tri_idx(i, j, p), i, j, 0);
+    for (int k = 0; k < p - 1; k++) for (int l = 0; l < p - k - 1; l++) // upright sub-triangles
+      add_cell(T, {tri_idx(l, k, p), tri_idx(l, k, p) + 1, tri_idx(l, k + 1, p)});
+    for (int k = 0; k < p - 2; k++) for (int l = 0; l < p - k - 2; l++) // inverted ones between them
+      add_cell(T, {tri_idx(l + 1, k, p), tri_idx(l + 1, k + 1, p), tri_idx(l, k + 1, p)});
+  }
+  else if (type == TET)
+  {
+    T.n_ppts = (p + 2) * (p + 1) * p / 6; T.n_verts = 4;
+    T.loc_ppts.setup(3, T.n_ppts);
+    for (int k = 0; k < p; k++) for (int j = 0; j < p - k; j++) for (int i = 0; i < p - k - j; i++) put(tet_idx(i, j, k, p), i, j, k);
+    // corner tetrahedra of every lattice cube
+    for (int k = 0; k < p - 1; k++) for (int j = 0; j < p - 1 - k; j++) for (int i = 0; i < p - 1 - k - j; i++)
+      add_cell(T, {tet_idx(i, j, k, p), tet_idx(i + 1, j, k, p), tet_idx(i, j + 1, k, p), tet_idx(i, j, k + 1, p)});
+    // the octahedron next to it, split into four
+    for (int k = 0; k < p - 2; k++) for (int j = 0; j < p - 2 - k; j++) for (int i = 0; i < p - 2 - k - j; i++)
+    {
+      const int v0 = tet_idx(i + 1, j, k, p), v1 = tet_idx(i + 1, j + 1, k, p), v2 = tet_idx(i + 1, j, k + 1, p);
+      const int v3 = tet_idx(i, j + 1, k + 1, p), v4 = tet_idx(i, j, k + 1, p), v5 = tet_idx(i, j + 1, k, p);
+      add_cell(T, {v0, v2, v1, v4});
+      add_cell(T, {v2, v3, v1, v4});
+      add_cell(T, {v5, v1, v3, v4});
+      add_cell(T, {v0, v4, v1, v5});
+    }
+    // the opposite corner
+    for (int k = 0; k < p - 3; k++) for (int j = 0; j < p - 3 - k; j++) for (int i = 0; i < p - 3 - k - j; i++)
+      add_cell(T, {tet_idx(i + 1, j + 1, k, p), tet_idx(i + 1, j, k + 1, p), tet_idx(i, j + 1, k + 1, p), tet_idx(i + 1, j + 1, k + 1, p)});
+  }
+  else
+  {
+    const int layer = p * (p + 1) / 2;
+    T.n_ppts = layer * p; T.n_verts = 6;
+    T.loc_ppts.setup(3, T.n_ppts);
+    for (int k = 0; k < p; k++) for (int j = 0; j < p; j++) for (int i = 0; i < p - j; i++) put(layer * k + tri_idx(i, j, p), i, j, k);
+    for (int l = 0; l < p - 1; l++) for (int j = 0; j < p - 1; j++) for (int k = 0; k < p - j - 1; k++)
+    {
+      const int a = tri_idx(k, j, p) + l * layer, b = a + 1, c = tri_idx(k, j + 1, p) + l * layer;
+      add_cell(T, {a, b, c, a + layer, b + layer, c + layer});
+    }
+    for (int l = 0; l < p - 1; l++) for (int j = 0; j < p - 2; j++) for (int k = 0; k < p - j - 2; k++)
+    {
+      const int a = tri_idx(k + 1, j, p) + l * layer, b = tri_idx(k + 1, j + 1, p) + l * layer, c = b - 1;
+      add_cell(T, {a, b, c, a + layer, b + layer, c + layer});
+    }
+  }
+  // solution points -> plot points (reference eles::set_opp_p, src/eles.cpp:3600-3621)
+  hf_array<double> loc(nd);
+  T.opp_p.setup(T.n_ppts, e->n_upts_per_ele);
+  for (int i = 0; i < e->n_upts_per_ele; i++)
+    for (int j = 0; j < T.n_ppts; j++)
+    {
+      for (int k = 0; k < nd; k++) loc(k) = T.loc_ppts(k, j);
+      T.opp_p(j, i) = e->eval_nodal_basis(i, loc);
+    }
+}
+
+// stream output with the reference's settings: precision 15, default float format
+struct num { double v; };
+ostream &operator<<(ostream &o, const num &n)
+{
+  char b[40];
+  snprintf(b, sizeof(b), "%.15g", n.v);
+  return o << b;
+}
+} // namespace
+
+void write_vtu(int in_file_num, struct solution *FlowSol)
+{
+  if (run_input.n_diagnostic_fields > 0 || run_input.n_average_fields > 0)
+    FatalError("diagnostic_fields / average_fields in the Paraview files are not built");
+  const int my_rank = FlowSol->rank, n_proc = FlowSol->nproc;
+  static const int vtktypes[5] = {5, 9, 10, 13, 12}; // tri, quad, tet, prism, hex (vtkCellType.h)
+  char dumpnum_s[256], vtu_s[600], pvtu_s[300];
+  const char *name = run_input.data_file_name.c_str();
+  snprintf(dumpnum_s, sizeof(dumpnum_s), "%s_%.09d", name, in_file_num);
+  if (n_proc > 1)
+  {
+    snprintf(vtu_s, sizeof(vtu_s), "%s/%s_%d.vtu", dumpnum_s, dumpnum_s, my_rank);
+    snprintf(pvtu_s, sizeof(pvtu_s), "%s.pvtu", dumpnum_s);
+    if (my_rank == 0)
+    {
+      struct stat st;
+      if (stat(dumpnum_s, &st) == -1) mkdir(dumpnum_s, 0755);
+      else if (DIR *dir = opendir(dumpnum_s))
+      {
+        // delete old .vtu files from the directory
+        while (struct dirent *fn = readdir(dir))
+          if (strcmp(fn->d_name, ".") != 0 && strcmp(fn->d_name, "..") != 0) remove((string(dumpnum_s) + '/' + fn->d_name).c_str());
+        closedir(dir);
+      }
+      cout << "Writing Paraview file " << dumpnum_s << " ...." << flush;
+      ofstream w(pvtu_s);
+      w << "<?xml version=\"1.0\" ?>" << endl;
+      w << "<VTKFile type=\"PUnstructuredGrid\" version=\"0.1\" byte_order=\"LittleEndian\" compressor=\"vtkZLibDataCompressor\">" << endl;
+      w << "	<PUnstructuredGrid GhostLevel=\"1\">" << endl;
+      w << "		<PPointData Scalars=\"Density\" Vectors=\"Velocity\">" << endl;
+      w << "			<PDataArray type=\"Float32\" Name=\"Density\" />" << endl;
+      w << "			<PDataArray type=\"Float32\" Name=\"Velocity\" NumberOfComponents=\"3\" />" << endl;
+      w << "			<PDataArray type=\"Float32\" Name=\"SpecificTotalEnergy\" />" << endl;
+      w << "		</PPointData>" << endl;
+      w << "		<PPoints>" << endl;
+      w << "			<PDataArray type=\"Float32\" Name=\"Points\" NumberOfComponents=\"3\" />" << endl;
+      w << "		</PPoints>" << endl;
+      for (int i = 0; i < n_proc; ++i) w << "		<Piece Source=\"" << dumpnum_s << "/" << dumpnum_s << "_" << i << ".vtu" << "\" />" << endl;
+      w << "	</PUnstructuredGrid>" << endl;
+      w << "</VTKFile>" << endl;
+    }
+    // the other ranks need the directory: every rank has passed device calls since rank 0 got here only if it exists, so
+    // make sure of it locally (same file system on one node)
+    struct stat st;
+    for (int spin = 0; stat(dumpnum_s, &st) == -1 && spin < 10000; spin++) hf_dev_sync(FlowSol->ctx);
+  }
+  else
+  {
+    snprintf(vtu_s, sizeof(vtu_s), "%s.vtu", dumpnum_s);
+    cout << "Writing Paraview file " << dumpnum_s << " ... " << flush;
+  }
+  ofstream w(vtu_s);
+  if (!w) FatalError(string("cannot open ") + vtu_s);
+  w << "<?xml version=\"1.0\" ?>" << endl;
+  w << "<VTKFile type=\"UnstructuredGrid\" version=\"0.1\" byte_order=\"LittleEndian\" compressor=\"vtkZLibDataCompressor\">" << endl;
+  w << "	<UnstructuredGrid>" << endl;
+  for (int t = 0; t < FlowSol->n_ele_types; t++)
+  {
+    eles *e = FlowSol->mesh_eles(t);
+    const int n_eles = e->get_n_eles();
+    if (n_eles == 0) continue;
+    if (!FlowSol->no_device) e->cp_disu_upts_gpu_cpu();
+    plot_topology T;
+    build_topology(e, run_input.p_res, T);
+    const int n_points = T.n_ppts, n_cells = T.n_peles, n_verts = T.n_verts, n_fields = e->n_fields, n_dims = e->n_dims, nu = e->n_upts_per_ele;
+    if (run_input.equation != 0) FatalError("Paraview output is built for the Euler / Navier-Stokes equations");
+    hf_array<double> u(n_points, n_fields), loc(n_dims), pos(n_dims);
+    for (int j = 0; j < n_eles; j++)
+    {
+      w << "		<Piece NumberOfPoints=\"" << n_points << "\" NumberOfCells=\"" << n_cells << "\">" << endl;
+      // prognostic fields at the plot points (reference eles::calc_disu_ppts: opp_p times the element's solution)
+      for (int m = 0; m < n_fields; m++)
+        for (int k = 0; k < n_points; k++)
+        {
+          double a = 0.;
+          for (int l = 0; l < nu; l++) a += e->disu_upts(0)(l, j, m) * T.opp_p(k, l);
+          u(k, m) = a;
+        }
+      w << "			<PointData>" << endl;
+      w << "				<DataArray type= \"Float32\" Name=\"Density\" format=\"ascii\">" << endl;
+      for (int k = 0; k < n_points; k++) w << num{u(k, 0)} << " ";
+      w << endl << "				</DataArray>" << endl;
+      w << "				<DataArray type= \"Float32\" NumberOfComponents=\"3\" Name=\"Velocity\" format=\"ascii\">" << endl;
+      for (int k = 0; k < n_points; k++)
+      {
+        w << num{u(k, 1) / u(k, 0)} << " " << num{u(k, 2) / u(k, 0)} << " ";
+        if (n_dims == 2) w << num{0.0} << " ";
+        else w << num{u(k, 3) / u(k, 0)} << " ";
+      }
+      w << endl << "				</DataArray>" << endl;
+      w << "				<DataArray type= \"Float32\" Name=\"SpecificTotalEnergy\" format=\"ascii\">" << endl;
+      for (int k = 0; k < n_points; k++) w << num{u(k, n_dims + 1) / u(k, 0)} << " ";
+      w << endl << "				</DataArray>" << endl;
+      w << "			</PointData>" << endl;
+      w << "			<Points>" << endl;
+      w << "				<DataArray type=\"Float32\" NumberOfComponents=\"3\" format=\"ascii\">" << endl;
+      for (int k = 0; k < n_points; k++)
+      {
+        for (int l = 0; l < n_dims; l++) loc(l) = T.loc_ppts(l, k);
+        e->calc_pos(loc, j, pos);
+        for (int l = 0; l < n_dims; l++) w << num{pos(l)} << " ";
+        if (n_dims == 2) w << "0 ";
+      }
+      w << endl << "				</DataArray>" << endl;
+      w << "			</Points>" << endl;
+      w << "			<Cells>" << endl;
+      w << "				<DataArray type=\"Int32\" Name=\"connectivity\" format=\"ascii\">" << endl;
+      for (int k = 0; k < n_cells; k++)
+      {
+        for (int l = 0; l < n_verts; l++) w << T.con[(size_t)k * n_verts + l] << " ";
+        w << endl;
+      }
+      w << "				</DataArray>" << endl;
+      w << "				<DataArray type=\"Int32\" Name=\"offsets\" format=\"ascii\">" << endl;
+      for (int k = 0; k < n_cells; k++) w << (k + 1) * n_verts << " ";
+      w << endl << "				</DataArray>" << endl;
+      w << "				<DataArray type=\"UInt8\" Name=\"types\" format=\"ascii\">" << endl;
+      for (int k = 0; k < n_cells; k++) w << vtktypes[t] << " ";
+      w << endl << "				</DataArray>" << endl;
+      w << "			</Cells>" << endl;
+      w << "		</Piece>" << endl;
+    }
+  }
+  w << "	</UnstructuredGrid>" << endl;
+  w << "</VTKFile>" << endl;
+  w.close();
+  if (my_rank == 0) cout << "done." << endl;
+}

@@ -1,0 +1,58 @@
+"""CPU: Paraview output.  The reference binary writes the initial solution as <name>_000000000.vtu before its first step
+(src/HiFiLES.cpp:171-182, src/output.cpp:462-900); the host mirror's write_vtu of the same initial solution must produce
+the same file: same XML, same plot-point numbering and sub-cell connectivity, numbers equal to the printed digits."""
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+import util
+
+REF = os.path.join(util.REF_DIR, "HiFiLES_ref")
+NUM = re.compile(r"^[-+0-9.eE]+$")
+
+
+def split_vtu(path):
+    """-> (structure tokens, numbers): every whitespace-separated token of the file, numeric ones replaced by '#'"""
+    text, nums = [], []
+    for tok in open(path).read().split():
+        if NUM.match(tok):
+            nums.append(float(tok))
+            text.append("#")
+        else:
+            text.append(tok)
+    return text, np.array(nums)
+
+
+@pytest.mark.parametrize("kind,order,p_res", [("hex", 2, 3), ("quadtri", 2, 4), ("pritet", 1, 4), ("pritet", 2, 2)])
+def test_initial_vtu_matches_reference_binary(tmp_path, hb, meshgen, kind, order, p_res, monkeypatch):
+    if not (util.have_reference() and os.path.exists(REF)):
+        pytest.skip("oracle/_ref not built")
+    extra = {}
+    if kind == "hex":
+        meshgen.hex_box(str(tmp_path / "m.neu"), 2)
+    elif kind == "quadtri":
+        meshgen.mixed_box_2d(str(tmp_path / "m.neu"), 4, kind="mixed", lengths=(6.2831853071795862,) * 2, origin=(0., 0.))
+        extra = dict(dz_cyclic=None)
+    else:
+        meshgen.mixed_box_3d(str(tmp_path / "m.neu"), (2, 2, 2), kind=kind)
+    inp = meshgen.write_input(str(tmp_path / "input"), "m.neu", order=order, adv_type=2, dt=1e-5, riemann_solve_type=0, viscous=1, n_steps=0,
+                              p_res=p_res, data_file_name="Plot", **extra)
+    ref_dir = tmp_path / "ref"
+    ref_dir.mkdir()
+    for f in ("m.neu", "input"):
+        os.symlink(tmp_path / f, ref_dir / f)
+    r = subprocess.run([REF, "input"], cwd=str(ref_dir), env=dict(os.environ, HIFILES_HOME=util.REF_DIR), capture_output=True, text=True, timeout=600)
+    assert os.path.exists(ref_dir / "Plot_000000000.vtu"), r.stdout[-2000:] + r.stderr[-2000:]
+    monkeypatch.chdir(tmp_path)
+    with hb.Run(inp, host_only=True) as run:
+        run.write_vtu(0)
+    ta, na = split_vtu(ref_dir / "Plot_000000000.vtu")
+    tb, nb = split_vtu(tmp_path / "Plot_000000000.vtu")
+    assert ta == tb, "XML structure / token layout differs"
+    assert na.shape == nb.shape and na.size > 100
+    scale = np.abs(na).max()
+    assert np.abs(na - nb).max() <= 1e-13 * scale
+    assert np.array_equal(na[np.abs(na - np.round(na)) == 0], nb[np.abs(na - np.round(na)) == 0])  # integers (connectivity, offsets, types) exactly
