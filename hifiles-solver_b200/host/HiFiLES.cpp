@@ -117,6 +117,9 @@ int main(int argc, char *argv[])
       }
       else
         fprintf(hist, ",\"log<sub>10</sub>(Res[<greek>r</greek>])\"");
+      if (run_input.equation == 0 && run_input.calc_force)
+        fprintf(hist, FlowSol.n_dims == 2 ? ",\"F<sub>x</sub>(Total)\",\"F<sub>y</sub>(Total)\",\"CL</sub>(Total)\",\"CD</sub>(Total)\""
+                                          : ",\"F<sub>x</sub>(Total)\",\"F<sub>y</sub>(Total)\",\"F<sub>z</sub>(Total)\",\"CL</sub>(Total)\",\"CD</sub>(Total)\"");
       for (int i = 0; i < n_diags; i++) fprintf(hist, ",\"Diagnostics[%s]\"", run_input.integral_quantities(i).c_str());
       fprintf(hist, ",\"Time<sub>Physical</sub>(sec)\",\"Time<sub>Comp</sub>(m)\"\nZONE T= \"Convergence history\"\n");
     }
@@ -136,16 +139,27 @@ int main(int argc, char *argv[])
       i_steps++;
       if (i_steps == 1 || i_steps % run_input.monitor_res_freq == 0)
       {
+        /*! Compute the value of the forces (reference src/HiFiLES.cpp:250-254) */
+        if (run_input.calc_force != 0) CalcForces(FlowSol.ini_iter + i_steps, (i_steps == 1 || i_steps % run_input.monitor_cp_freq == 0), &FlowSol);
         if (n_diags) CalcIntegralQuantities(&FlowSol);
         CalcNormResidual(&FlowSol);
-        if (i_steps == 1) printf("\n  Iter       Res[Rho]   Res[RhoVelx]   Res[RhoVely]%s      Res[RhoE]\n", FlowSol.n_dims == 3 ? "   Res[RhoVelz]" : "");
+        if (i_steps == 1)
+          printf("\n  Iter       Res[Rho]   Res[RhoVelx]   Res[RhoVely]%s      Res[RhoE]%s\n", FlowSol.n_dims == 3 ? "   Res[RhoVelz]" : "",
+                 !run_input.calc_force ? "" : (FlowSol.n_dims == 3 ? "       Fx_Total       Fy_Total       Fz_Total" : "       Fx_Total       Fy_Total"));
         printf("%6d", FlowSol.ini_iter + i_steps);
         for (int f = 0; f < n_fields; f++) printf(" %14.8f", FlowSol.norm_residual(f));
+        if (run_input.calc_force != 0)
+          for (int d = 0; d < FlowSol.n_dims; d++) printf(" %14.8f", FlowSol.inv_force(d) + FlowSol.vis_force(d));
         printf("\n");
         if (hist)
         {
           fprintf(hist, "%d", FlowSol.ini_iter + i_steps);
           for (int f = 0; f < n_fields; f++) fprintf(hist, ", %.15g", log10(FlowSol.norm_residual(f)));
+          if (run_input.calc_force != 0)
+          {
+            for (int d = 0; d < FlowSol.n_dims; d++) fprintf(hist, ", %.15g", FlowSol.inv_force(d) + FlowSol.vis_force(d));
+            fprintf(hist, ", %.15g, %.15g", FlowSol.coeff_lift, FlowSol.coeff_drag);
+          }
           for (int q = 0; q < n_diags; q++) fprintf(hist, ", %.15g", FlowSol.integral_quantities(q));
           fprintf(hist, ", %.15g", (run_input.viscous && run_input.equation == 0) ? FlowSol.time * run_input.time_ref : FlowSol.time);
           fprintf(hist, ", %.15g\n", (double)(clock() - init_time) / CLOCKS_PER_SEC / 60.);

@@ -362,7 +362,11 @@ void eles::set_transforms()
   if (run_input.over_int) set_transforms_over_int_cubpts();
   set_transforms_fpts();
   // metrics at the volume cubature points: only needed for computing error and integral diagnostic quantities (reference src/eles.cpp:4026-4028)
-  if (run_input.test_case != 0 || run_input.n_integral_quantities != 0)
+  // metrics at the interface cubature points: only when surface forces are asked for (reference src/eles.cpp:4022-4024)
+  if (run_input.calc_force != 0) set_inters_cubpts_and_transforms();
+  // (calc_force: the viscous traction needs grad_disu_upts of the monitored stage, which the fused kernels store once a volume
+  // cubature is registered with the device)
+  if (run_input.test_case != 0 || run_input.n_integral_quantities != 0 || run_input.calc_force != 0)
   {
     set_volume_cubpts(order, loc_volume_cubpts, weight_volume_cubpts);
     set_opp_volume_cubpts();
@@ -592,7 +596,7 @@ void eles::mv_all_cpu_gpu()
     d.exp_filter = exp_filter.get_ptr_cpu();
   }
   hf_check(hf_dev_upload_eles(ctx, &d));
-  if (run_input.n_integral_quantities != 0)
+  if (run_input.n_integral_quantities != 0 || run_input.calc_force != 0)
     hf_check(hf_dev_set_volume_cubature(ctx, ele_type, loc_volume_cubpts.get_dim(1), opp_volume_cubpts.get_ptr_cpu(), weight_volume_cubpts.get_ptr_cpu(),
                                         vol_detjac_vol_cubpts.get_ptr_cpu()));
 }

@@ -251,6 +251,9 @@ public:
   void CalcIntegralQuantities(int n_integral_quantities, hf_array<double> &integral_quantities);
   /*! error against the analytic solution of the test case, integrated over the volume cubature (reference src/eles.cpp:5076-5290) */
   hf_array<double> compute_error(int in_norm_type, double &time);
+  /*! surface forces on walls (reference src/eles.cpp:5704-5990 and the interface-cubature setup behind it) */
+  void set_inters_cubpts_and_transforms();
+  void compute_wall_forces(hf_array<double> &inv_force, hf_array<double> &vis_force, double &temp_cl, double &temp_cd, std::ofstream &coeff_file, bool write_forces);
   void set_rank(int in_rank) { rank = in_rank; }
   void set_device(hf_ctx *in_ctx) { ctx = in_ctx; }
 
@@ -341,6 +344,9 @@ public:
   int rank, ele_type, n_eles, n_dims, n_fields, order, viscous, n_inters_per_ele;
   int n_upts_per_ele, n_fpts_per_ele, max_n_spts_per_ele, n_adv_levels, upts_type;
   hf_array<int> n_fpts_per_inter, n_spts_per_ele, ele2global_ele, bcid;
+  hf_array<int> n_cubpts_per_inter;
+  std::vector<hf_array<double>> loc_inters_cubpts, weight_inters_cubpts, opp_inters_cubpts, inter_detjac_inters_cubpts, norm_inters_cubpts; // per local face
+  std::vector<int> bdy_ele2ele;
   hf_array<double> loc_volume_cubpts, weight_volume_cubpts, opp_volume_cubpts, vol_detjac_vol_cubpts; // (dim,cubpt), (cubpt), (cubpt,upt), (cubpt,ele)
   hf_array<double> loc_upts, tloc_fpts, tnorm_fpts, loc_1d_upts;
   hf_array<double> shape, d_nodal_s_basis;
@@ -522,7 +528,8 @@ struct solution
   std::vector<int_inters> mesh_int_inters;
   std::vector<bdy_inters> mesh_bdy_inters;
   std::vector<mpi_inters> mesh_mpi_inters;
-  hf_array<double> norm_residual, integral_quantities;
+  hf_array<double> norm_residual, integral_quantities, inv_force, vis_force;
+  double coeff_lift = 0., coeff_drag = 0.;
   hf_ctx *ctx; // device context shared by all objects of this solution
   int no_device; // 1: host pre-processing only (CPU-side tests of setup logic); any hot-path call then fails loudly
   /*! optional partition vector (global cell -> rank); empty = block partition of the reference's initial read */
@@ -541,6 +548,8 @@ void CalcIntegralQuantities(struct solution *FlowSol);
 void compute_error(int in_file_num, struct solution *FlowSol);
 /*! output::write_vtu (reference src/output.cpp:462-900): Paraview file(s) of the current solution */
 void write_vtu(int in_file_num, struct solution *FlowSol);
+/*! output::CalcForces (reference src/output.cpp:1915-2012): fills inv_force, vis_force, coeff_lift, coeff_drag; optionally the cp files */
+void CalcForces(int in_file_num, bool write_forces, struct solution *FlowSol);
 /*! CalcResidual + AdvanceSolution (+ shock_capture) of one RK stage: one fused device call where the fused kernels are
  *  available, the reference's sequence of methods otherwise.  monitored: the residual (and, for the integral diagnostics,
  *  the gradient) of this stage will be read afterwards. */

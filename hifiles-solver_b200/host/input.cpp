@@ -185,11 +185,6 @@ void input::read_input_file(const string &fileName, int rank)
   {
     opts.getScalarValue("monitor_cp_freq", monitor_cp_freq);
     opts.getScalarValue("area_ref", area_ref);
-    // The option is accepted because the reference needs it for every case with an inlet boundary (its inlet-area routine
-    // reads face metrics that are only built with calc_force); the surface-force integration itself
-    // (output::CalcForces, eles::compute_wall_forces, src/eles.cpp:5704-5990) is not built: say so, once.
-    if (rank == 0)
-      cout << "NOTE: calc_force is set, but surface forces / cp files are not computed by this build (history.plt has no force columns)" << endl;
   }
   opts.getScalarValue("res_norm_type", res_norm_type, 2);
   opts.getScalarValue("error_norm_type", error_norm_type, 2);

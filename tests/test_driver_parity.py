@@ -121,6 +121,51 @@ def test_vortex_error_file_matches_reference_binary(tmp_path, hb, meshgen, kind)
     assert np.all(ea[:3] > 0) and np.abs(eb - ea).max() <= 2e-6 * np.abs(ea).max()  # printed with 7 significant digits
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["quad_p2_ns_walls_char_out", "quad_p3_euler_slip_supin_supout", "hex_p2_ns_wall_char_periodic",
+                                  "config5_hexpri_p2_les_wm_shockcap_hllc", "mixed_tri_quad_p3_ns_rusanov_walls", "pritet_p2_ns_walls"])
+def test_surface_forces_match_reference_binary(tmp_path, hb, meshgen, name):
+    """calc_force: output::CalcForces / eles::compute_wall_forces (pressure and viscous traction integrated over the wall
+    faces' cubature points) -- force, CL, CD columns of history.plt and the cp / cf file against the reference binary."""
+    if not (os.path.exists(REF) and os.path.exists(OURS)):
+        pytest.skip("driver binaries not built")
+    from test_staged_parity import CASES, make_mesh
+    if name == "pritet_p2_ns_walls":  # tetrahedra and prisms with walls on every face kind (x: prism quads / tet triangles, z: triangles)
+        base = CASES["hex_p2_ns_wall_char_periodic"]
+        kind, n, mkw, opts = "pritet", (2, 4, 2), dict(lengths=(1., 2., 1.), bcs={"x-": "Wall", "x+": "Wall", "y-": "Cyclic", "y+": "Cyclic", "z-": "Wall", "z+": "Far"}), \
+            dict(base[3], dx_cyclic=None, dy_cyclic=2., dz_cyclic=None)
+    else:
+        kind, n, mkw, opts = CASES[name]
+    opts = dict(opts, calc_force=1, monitor_cp_freq=2, area_ref=1.5, n_steps=2, monitor_res_freq=1, device_fused=0)
+    nd = 2 if kind in ("quad", "tri", "mixed") else 3
+    nf = nd + 2
+    out = {}
+    for who, exe in (("ref", REF), ("ours", OURS)):
+        d = tmp_path / who
+        d.mkdir()
+        make_mesh(meshgen, kind, str(d / "m.neu"), n, mkw)
+        meshgen.write_input(str(d / "input"), "m.neu", **opts)
+        env = dict(os.environ, HIFILES_HOME=util.REF_DIR if who == "ref" else os.path.join(util.ROOT, "hifiles-solver_b200"))
+        r = subprocess.run([exe, "input"], cwd=str(d), env=env, capture_output=True, text=True, timeout=900)
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+        hist = history_rows(str(d / "history.plt"), nf + nd + 2)
+        cp = [l.split() for l in open(d / "force_files_000000002" / "cp_000000002_p0000.dat").read().splitlines()]
+        out[who] = (hist, cp)
+    (ha, ca), (hb_, cb) = out["ref"], out["ours"]
+    assert ha.shape == hb_.shape == (2, nf + nd + 2)
+    fa, fb = ha[:, nf:], hb_[:, nf:]
+    assert np.abs(fa).max() > 0
+    assert np.abs(fb - fa).max() <= 1e-10 * np.abs(fa).max(), "forces / coefficients: %s vs %s" % (fb, fa)
+    assert len(ca) == len(cb) and len(ca) > 3
+    for la, lb in zip(ca, cb):
+        assert len(la) == len(lb)
+        if len(la) == 1 or la[0] == "x":
+            assert la == lb
+        else:
+            va, vb = np.array([float(x) for x in la]), np.array([float(x) for x in lb])
+            assert np.abs(va - vb).max() <= 1e-9 * max(1.0, np.abs(va).max())
+
+
 def restart_numbers(path):
     """structure (all non-numeric lines, in order) and numbers of an ASCII restart file"""
     text, nums = [], []

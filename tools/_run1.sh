@@ -1,8 +1,3 @@
 mkdir -p gpurun_out
-( time timeout 1500 python -m pytest tests -q -m gpu -x ) > gpurun_out/t_all.log 2>&1; echo "tests exit $?" >> gpurun_out/t_all.log
-tail -6 gpurun_out/t_all.log
-python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
-timeout 600 python bench.py > gpurun_out/bench_default.log 2>&1; tail -1 gpurun_out/bench_default.log | cut -c1-200
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_r01d.csv python bench.py --steps 2 --warmup 3 --no-cpu --no-e2e > gpurun_out/ncu_list.log 2>&1
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:"k_resid7|k_grad7" -s 8 -c 2 -o gpurun_out/prof_r01d_64 python bench.py --steps 2 --warmup 3 --no-cpu --no-e2e > gpurun_out/ncu_full.log 2>&1
-ls -la gpurun_out/*.ncu-rep | tail -2
+timeout 900 python -m pytest tests/test_driver_parity.py -q -m gpu -k "surface_forces and (mixed_tri or pritet)" > gpurun_out/t_drv.log 2>&1; echo "tests exit $?" >> gpurun_out/t_drv.log
+grep "^E   \|^FAILED\|passed\|failed" gpurun_out/t_drv.log | head -30
