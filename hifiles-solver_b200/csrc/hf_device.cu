@@ -2025,6 +2025,12 @@ int hf_dev_set_volume_cubature(hf_ctx *c, int ele_type, int n_cubpts, const doub
   return 0;
 }
 
+int hf_dev_set_keep_gradient(hf_ctx *c, int on)
+{
+  c->want_gradient = on != 0;
+  return 0;
+}
+
 int hf_dev_integral_quantities(hf_ctx *c, int ele_type, int n_quantities, const int *kinds, double *out)
 {
   HF_CUDA(cudaSetDevice(c->device));

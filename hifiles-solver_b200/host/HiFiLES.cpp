@@ -132,7 +132,8 @@ int main(int argc, char *argv[])
     {
       calc_time_step(&FlowSol);
       // the residual (and the gradient behind the integral diagnostics) of the last stage is read after monitored steps
-      const bool monitored = (i_steps + 1 == 1) || ((i_steps + 1) % run_input.monitor_res_freq == 0);
+      const bool monitored = (i_steps + 1 == 1) || ((i_steps + 1) % run_input.monitor_res_freq == 0) ||
+                             (run_input.n_diagnostic_fields > 0 && (i_steps + 1) % run_input.plot_freq == 0);
       for (int i = 0; i < RKSteps; i++) AdvanceStage(FlowSol.ini_iter + i_steps, i, &FlowSol, monitored && i == RKSteps - 1);
       FlowSol.time += run_input.dt;
       run_input.time = FlowSol.time;

@@ -364,9 +364,7 @@ void eles::set_transforms()
   // metrics at the volume cubature points: only needed for computing error and integral diagnostic quantities (reference src/eles.cpp:4026-4028)
   // metrics at the interface cubature points: only when surface forces are asked for (reference src/eles.cpp:4022-4024)
   if (run_input.calc_force != 0) set_inters_cubpts_and_transforms();
-  // (calc_force: the viscous traction needs grad_disu_upts of the monitored stage, which the fused kernels store once a volume
-  // cubature is registered with the device)
-  if (run_input.test_case != 0 || run_input.n_integral_quantities != 0 || run_input.calc_force != 0)
+  if (run_input.test_case != 0 || run_input.n_integral_quantities != 0)
   {
     set_volume_cubpts(order, loc_volume_cubpts, weight_volume_cubpts);
     set_opp_volume_cubpts();
@@ -596,7 +594,9 @@ void eles::mv_all_cpu_gpu()
     d.exp_filter = exp_filter.get_ptr_cpu();
   }
   hf_check(hf_dev_upload_eles(ctx, &d));
-  if (run_input.n_integral_quantities != 0 || run_input.calc_force != 0)
+  // surface forces and the gradient-based plot fields read grad_disu_upts of the monitored stage
+  if (viscous && (run_input.calc_force != 0 || run_input.n_diagnostic_fields != 0)) hf_check(hf_dev_set_keep_gradient(ctx, 1));
+  if (run_input.n_integral_quantities != 0)
     hf_check(hf_dev_set_volume_cubature(ctx, ele_type, loc_volume_cubpts.get_dim(1), opp_volume_cubpts.get_ptr_cpu(), weight_volume_cubpts.get_ptr_cpu(),
                                         vol_detjac_vol_cubpts.get_ptr_cpu()));
 }

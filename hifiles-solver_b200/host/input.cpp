@@ -200,6 +200,8 @@ void input::read_input_file(const string &fileName, int rank)
     std::transform(integral_quantities(i).begin(), integral_quantities(i).end(), integral_quantities(i).begin(), ::tolower);
   if (n_integral_quantities && !viscous) FatalError("integral quantities read the solution gradient: viscous run needed");
   n_diagnostic_fields = diagnostic_fields.get_dim(0);
+  for (int i = 0; i < n_diagnostic_fields; i++)
+    std::transform(diagnostic_fields(i).begin(), diagnostic_fields(i).end(), diagnostic_fields(i).begin(), ::tolower);
   n_average_fields = average_fields.get_dim(0);
 
   /* ---- Basic Solver Parameters ---- */

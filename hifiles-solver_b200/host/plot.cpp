@@ -3,8 +3,10 @@
 // solution points with opp_p.  Plot points, their numbering and the sub-cell connectivity follow the reference's
 // per-type rules (set_loc_ppts / set_connectivity_plot of src/eles_{hexas,quads,tris,tets,pris}.cpp) so that the files
 // agree with the reference's to the printed digits.  One .vtu per run in serial; with several ranks every rank writes
-// <name>_<iter>/<name>_<iter>_<rank>.vtu and rank 0 the .pvtu index.  Optional diagnostic / time-averaged fields are not
-// built (rejected at input time).  The solution is copied device -> host first (output::CopyGPUCPU).
+// <name>_<iter>/<name>_<iter>_<rank>.vtu and rank 0 the .pvtu index.  Optional diagnostic fields (u, v, w, energy, mach,
+// pressure, vorticity, q_criterion, scaled_q_criterion, sensor: eles::calc_diagnostic_fields_ppts, src/eles.cpp:3858-4010) are
+// evaluated at the plot points from the interpolated solution and gradient; time-averaged fields are not built.  The
+// solution (and gradient) is copied device -> host first (output::CopyGPUCPU).
 #include "hifiles.h"
 #include <cstdio>
 #include <fstream>
@@ -138,8 +140,8 @@ ostream &operator<<(ostream &o, const num &n)
 
 void write_vtu(int in_file_num, struct solution *FlowSol)
 {
-  if (run_input.n_diagnostic_fields > 0 || run_input.n_average_fields > 0)
-    FatalError("diagnostic_fields / average_fields in the Paraview files are not built");
+  if (run_input.n_average_fields > 0) FatalError("average_fields in the Paraview files are not built");
+  const int n_diag_fields = run_input.n_diagnostic_fields;
   const int my_rank = FlowSol->rank, n_proc = FlowSol->nproc;
   static const int vtktypes[5] = {5, 9, 10, 13, 12}; // tri, quad, tet, prism, hex (vtkCellType.h)
   char dumpnum_s[256], vtu_s[600], pvtu_s[300];
@@ -169,6 +171,7 @@ void write_vtu(int in_file_num, struct solution *FlowSol)
       w << "			<PDataArray type=\"Float32\" Name=\"Density\" />" << endl;
       w << "			<PDataArray type=\"Float32\" Name=\"Velocity\" NumberOfComponents=\"3\" />" << endl;
       w << "			<PDataArray type=\"Float32\" Name=\"SpecificTotalEnergy\" />" << endl;
+      for (int m = 0; m < n_diag_fields; m++) w << "			<PDataArray type=\"Float32\" Name=\"" << run_input.diagnostic_fields(m) << "\" />" << endl;
       w << "		</PPointData>" << endl;
       w << "		<PPoints>" << endl;
       w << "			<PDataArray type=\"Float32\" Name=\"Points\" NumberOfComponents=\"3\" />" << endl;
@@ -198,11 +201,16 @@ void write_vtu(int in_file_num, struct solution *FlowSol)
     const int n_eles = e->get_n_eles();
     if (n_eles == 0) continue;
     if (!FlowSol->no_device) e->cp_disu_upts_gpu_cpu();
+    // gradient of the last monitored residual evaluation; before the first step the reference's array is still zero
+    const bool need_grad = n_diag_fields > 0 && run_input.viscous;
+    const bool have_grad = need_grad && !FlowSol->no_device && in_file_num != FlowSol->ini_iter;
+    if (have_grad) e->cp_grad_disu_upts_gpu_cpu();
+    if (n_diag_fields > 0 && run_input.shock_cap && !FlowSol->no_device) e->cp_sensor_gpu_cpu();
     plot_topology T;
     build_topology(e, run_input.p_res, T);
     const int n_points = T.n_ppts, n_cells = T.n_peles, n_verts = T.n_verts, n_fields = e->n_fields, n_dims = e->n_dims, nu = e->n_upts_per_ele;
     if (run_input.equation != 0) FatalError("Paraview output is built for the Euler / Navier-Stokes equations");
-    hf_array<double> u(n_points, n_fields), loc(n_dims), pos(n_dims);
+    hf_array<double> u(n_points, n_fields), loc(n_dims), pos(n_dims), g(n_points, n_fields, n_dims), diag(n_points, n_diag_fields > 0 ? n_diag_fields : 1);
     for (int j = 0; j < n_eles; j++)
     {
       w << "		<Piece NumberOfPoints=\"" << n_points << "\" NumberOfCells=\"" << n_cells << "\">" << endl;
@@ -214,6 +222,75 @@ void write_vtu(int in_file_num, struct solution *FlowSol)
           for (int l = 0; l < nu; l++) a += e->disu_upts(0)(l, j, m) * T.opp_p(k, l);
           u(k, m) = a;
         }
+      if (n_diag_fields > 0)
+      {
+        for (int d = 0; d < n_dims; d++)
+          for (int m = 0; m < n_fields; m++)
+            for (int k = 0; k < n_points; k++)
+            {
+              double a = 0.;
+              if (have_grad)
+                for (int l = 0; l < nu; l++) a += e->grad_disu_upts(l, j, m, d) * T.opp_p(k, l);
+              g(k, m, d) = a;
+            }
+        const double sensor = (run_input.shock_cap && e->sensor.size() > 0) ? e->sensor(j) : 0.;
+        for (int k = 0; k < n_points; k++)
+        {
+          double v_sq = 0.;
+          for (int m = 0; m < n_dims; m++) v_sq += (u(k, m + 1) * u(k, m + 1));
+          v_sq /= u(k, 0) * u(k, 0);
+          const double pressure = (run_input.gamma - 1.0) * (u(k, n_dims + 1) - 0.5 * u(k, 0) * v_sq);
+          const double irho = 1. / u(k, 0);
+          for (int q = 0; q < n_diag_fields; q++)
+          {
+            const string &name = run_input.diagnostic_fields(q);
+            double val = 0.;
+            if (name == "u") val = u(k, 1) * irho;
+            else if (name == "v") val = u(k, 2) * irho;
+            else if (name == "w") val = (n_dims == 2) ? 0. : u(k, 3) * irho;
+            else if (name == "energy") val = u(k, n_dims + 1);
+            else if (name == "mach") val = sqrt(v_sq / (run_input.gamma * pressure / u(k, 0)));
+            else if (name == "pressure") val = pressure;
+            else if (name == "vorticity" || name == "q_criterion" || name == "scaled_q_criterion")
+            {
+              if (!run_input.viscous) FatalError("Trying to calculate diagnostic field only supported by viscous simualtion");
+              double dvel[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}}; // d v_a / d x_b
+              for (int a = 0; a < n_dims; a++)
+              {
+                const double va = u(k, a + 1) * irho;
+                for (int b = 0; b < n_dims; b++) dvel[a][b] = irho * (g(k, a + 1, b) - va * g(k, 0, b));
+              }
+              if (n_dims == 2)
+              {
+                if (name != "vorticity") FatalError("Q criterion Not implemented in 2D");
+                val = fabs(dvel[1][0] - dvel[0][1]);
+              }
+              else
+              {
+                double wx = dvel[2][1] - dvel[1][2], wy = dvel[0][2] - dvel[2][0], wz = dvel[1][0] - dvel[0][1];
+                if (name == "vorticity") val = sqrt(wx * wx + wy * wy + wz * wz);
+                else
+                {
+                  wx *= 0.5; wy *= 0.5; wz *= 0.5;
+                  const double Sxy = 0.5 * (dvel[0][1] + dvel[1][0]), Sxz = 0.5 * (dvel[0][2] + dvel[2][0]), Syz = 0.5 * (dvel[1][2] + dvel[2][1]);
+                  const double SS = dvel[0][0] * dvel[0][0] + dvel[1][1] * dvel[1][1] + dvel[2][2] * dvel[2][2] + 2 * Sxy * Sxy + 2 * Sxz * Sxz + 2 * Syz * Syz;
+                  const double OO = 2 * wx * wx + 2 * wy * wy + 2 * wz * wz;
+                  val = (name == "q_criterion") ? 0.5 * (OO - SS) : 0.5 * (OO - SS) / (SS + 1.e-24);
+                }
+              }
+            }
+            else if (name == "sensor")
+            {
+              if (!run_input.shock_cap) FatalError("Sensor unavailable");
+              val = sensor;
+            }
+            else
+              FatalError("plot_quantity not recognized");
+            if (std::isnan(val)) FatalError("NaN in the calculation of plot quantity " + name);
+            diag(k, q) = val;
+          }
+        }
+      }
       w << "			<PointData>" << endl;
       w << "				<DataArray type= \"Float32\" Name=\"Density\" format=\"ascii\">" << endl;
       for (int k = 0; k < n_points; k++) w << num{u(k, 0)} << " ";
@@ -229,6 +306,12 @@ void write_vtu(int in_file_num, struct solution *FlowSol)
       w << "				<DataArray type= \"Float32\" Name=\"SpecificTotalEnergy\" format=\"ascii\">" << endl;
       for (int k = 0; k < n_points; k++) w << num{u(k, n_dims + 1) / u(k, 0)} << " ";
       w << endl << "				</DataArray>" << endl;
+      for (int m = 0; m < n_diag_fields; m++)
+      {
+        w << "				<DataArray type= \"Float32\" Name=\"" << run_input.diagnostic_fields(m) << "\" format=\"ascii\">" << endl;
+        for (int k = 0; k < n_points; k++) w << num{diag(k, m)} << " ";
+        w << endl << "				</DataArray>" << endl;
+      }
       w << "			</PointData>" << endl;
       w << "			<Points>" << endl;
       w << "				<DataArray type=\"Float32\" NumberOfComponents=\"3\" format=\"ascii\">" << endl;

@@ -233,6 +233,9 @@ int hf_dev_residual_norm(hf_ctx *ctx, int norm_type, double *out);
  * whenever they keep the residual.  kinds: 0 kineticenergy, 1 enstropy, 2 pressuredilatation, 3 straincolonproduct,
  * 4 devstraincolonproduct.  out[n_quantities] is ADDED to (one call per element type); local to this rank. */
 #define HF_MAX_INTEGRAL_QUANTITIES 8
+/* on != 0: stages that keep the residual also leave grad_disu_upts behind in fused mode (the staged kernels always do):
+ * surface forces and the vorticity-type plot fields read it like the integral diagnostics.  Set by hf_dev_set_volume_cubature too. */
+int hf_dev_set_keep_gradient(hf_ctx *ctx, int on);
 int hf_dev_set_volume_cubature(hf_ctx *ctx, int ele_type, int n_cubpts, const double *opp_volume_cubpts, const double *weights, const double *vol_detjac);
 int hf_dev_integral_quantities(hf_ctx *ctx, int ele_type, int n_quantities, const int *kinds, double *out);
 /* sum of v[n] over the ranks of the context's communicator, in place on every rank (no-op on one rank) */

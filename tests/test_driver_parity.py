@@ -166,6 +166,34 @@ def test_surface_forces_match_reference_binary(tmp_path, hb, meshgen, name):
             assert np.abs(va - vb).max() <= 1e-9 * max(1.0, np.abs(va).max())
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("kernels", ["staged", "fused"])
+def test_plot_file_with_diagnostic_fields_matches_reference_binary(tmp_path, hb, meshgen, kernels):
+    """Paraview file after two steps with gradient-based plot fields (vorticity, Q criterion): they use grad_disu_upts as the
+    last residual evaluation of the plotted step left it, which the fused kernels store on such steps."""
+    if not (os.path.exists(REF) and os.path.exists(OURS)):
+        pytest.skip("driver binaries not built")
+    from test_plot_cpu import split_vtu
+    out = {}
+    for who, exe in (("ref", REF), ("ours", OURS)):
+        d = tmp_path / who
+        d.mkdir()
+        meshgen.hex_box(str(d / "tgv.neu"), 3)
+        meshgen.write_input(str(d / "input"), "tgv.neu", order=2, adv_type=2, dt=1e-5, riemann_solve_type=3, viscous=1, n_steps=2, monitor_res_freq=100,
+                            plot_freq=2, p_res=3, data_file_name="Mesh", diagnostic_fields="5 pressure mach vorticity q_criterion scaled_q_criterion",
+                            device_fused=1 if kernels == "fused" else 0)
+        env = dict(os.environ, HIFILES_HOME=util.REF_DIR if who == "ref" else os.path.join(util.ROOT, "hifiles-solver_b200"))
+        r = subprocess.run([exe, "input"], cwd=str(d), env=env, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+        out[who] = split_vtu(d / "Mesh_000000002.vtu")
+    (ta, na), (tb, nb) = out["ref"], out["ours"]
+    assert ta == tb and na.shape == nb.shape
+    # values are printed with 15 digits; vorticity-type fields are differences of gradients: compare against the field's scale
+    tol = 1e-11 if kernels == "staged" else 1e-9
+    assert np.abs(na - nb).max() <= tol * np.abs(na).max()
+    assert np.abs(na).max() > 1.0
+
+
 def restart_numbers(path):
     """structure (all non-numeric lines, in order) and numbers of an ASCII restart file"""
     text, nums = [], []

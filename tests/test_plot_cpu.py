@@ -26,8 +26,9 @@ def split_vtu(path):
     return text, np.array(nums)
 
 
-@pytest.mark.parametrize("kind,order,p_res", [("hex", 2, 3), ("quadtri", 2, 4), ("pritet", 1, 4), ("pritet", 2, 2)])
-def test_initial_vtu_matches_reference_binary(tmp_path, hb, meshgen, kind, order, p_res, monkeypatch):
+@pytest.mark.parametrize("kind,order,p_res,diag", [("hex", 2, 3, None), ("quadtri", 2, 4, None), ("pritet", 1, 4, None), ("pritet", 2, 2, None),
+                                                   ("hex", 2, 2, "8 u V w energy Mach pressure vorticity q_criterion"), ("quadtri", 2, 3, "4 u w pressure vorticity")])
+def test_initial_vtu_matches_reference_binary(tmp_path, hb, meshgen, kind, order, p_res, diag, monkeypatch):
     if not (util.have_reference() and os.path.exists(REF)):
         pytest.skip("oracle/_ref not built")
     extra = {}
@@ -38,6 +39,8 @@ def test_initial_vtu_matches_reference_binary(tmp_path, hb, meshgen, kind, order
         extra = dict(dz_cyclic=None)
     else:
         meshgen.mixed_box_3d(str(tmp_path / "m.neu"), (2, 2, 2), kind=kind)
+    if diag:
+        extra["diagnostic_fields"] = diag  # optional plot fields; the gradient-based ones are zero before the first residual evaluation
     inp = meshgen.write_input(str(tmp_path / "input"), "m.neu", order=order, adv_type=2, dt=1e-5, riemann_solve_type=0, viscous=1, n_steps=0,
                               p_res=p_res, data_file_name="Plot", **extra)
     ref_dir = tmp_path / "ref"
