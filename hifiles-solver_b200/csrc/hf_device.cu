@@ -1503,6 +1503,7 @@ int hf_dev_upload_mpi_inters(hf_ctx *c, const hf_mpi_inters_desc *d)
     if (hf_alloc_zero(c, &I.in_grad, nb * nd)) return 1;
     if (c->prm.LES && (hf_alloc_zero(c, &I.out_sgsf, nb * nd) || hf_alloc_zero(c, &I.in_sgsf, nb * nd))) return 1;
   }
+  if (d->ele_global_l) I.h_gid.assign(d->ele_global_l, d->ele_global_l + ni); else I.h_gid.clear();
   I.h_ele_type_l.assign(d->ele_type_l, d->ele_type_l + ni); I.h_ele_l.assign(d->ele_l, d->ele_l + ni);
   for (int i = 0; i < ni; i++) I.h_ele_l[i] = dev_ele(c->eles[I.h_ele_type_l[i]], I.h_ele_l[i]);
   I.h_loc_l.assign(d->local_inter_l, d->local_inter_l + ni);

@@ -120,7 +120,7 @@ struct hf_mpi_inters_dev
   double *out_disu = nullptr, *in_disu = nullptr;   // [inter][field][fpt]
   double *out_grad = nullptr, *in_grad = nullptr;   // [inter][dim][field][fpt]
   double *out_sgsf = nullptr, *in_sgsf = nullptr;   // [inter][dim][field][fpt], LES
-  std::vector<int> h_ele_type_l, h_ele_l, h_loc_l, h_rot;
+  std::vector<int> h_ele_type_l, h_ele_l, h_loc_l, h_rot, h_gid;
 };
 
 struct hf_ctx

@@ -350,6 +350,7 @@ struct hf_fused_state
   int fv_blk = 0;  // doubles per face block of fv
   unsigned long long own_xor = 0;
   std::vector<unsigned long long> h_pmask; // own masks of the partition faces
+  std::vector<unsigned long long> h_bmask; // host copy of bmask (partition faces may be re-decided when the communicator arrives)
   std::string os_why;
 };
 
@@ -593,6 +594,7 @@ int hf_fused_prepare(hf_ctx *c)
   Z->os = visc && fabs(c->prm.ldg_beta) == 0.5 && !getenv("HF_FUSED_GEN6");
   Z->own_xor = c->prm.ldg_beta > 0. ? (NN == 64 ? ~0ull : ((1ull << NN) - 1ull)) : 0ull;
   Z->fv_blk = Z->os ? NF * NN : 4 * NN;
+  Z->h_bmask = bmask;
   Z->h_pmask.resize(M.n_inters);
   for (int i = 0; i < M.n_inters; i++) Z->h_pmask[i] = bmask[(size_t)M.h_ele_l[i] * 6 + M.h_loc_l[i]] ^ Z->own_xor;
   // per own flux point: where the neighbour's value of field 0 sits in fu (block * NF*NN + permuted flux point)
@@ -860,41 +862,70 @@ int hf_fused_stage(hf_ctx *c, int rk_stage, double time, int keep_residual, int 
   return 0;
 }
 
-// Called when the communicator of a multi-rank run arrives: the one-sided kernels need the two ranks of every partition
-// face to agree on the owner of each flux-point pair.  Each side applies the reference's sign switch to its OWN normal
-// (src/mpi_inters.cpp:400-483 with src/inters.cpp:566-581); on exact geometry the normals are opposite and the choices
-// complementary, but rounding-level normal components can make both sides claim (or disclaim) a pair.  The masks are
-// exchanged once; any disagreement anywhere sends every rank back to the two-sided generation-6 kernels.
+// Called when the communicator of a multi-rank run arrives.  On a partition face each rank would apply the reference's LDG
+// sign switch to its OWN normal (src/mpi_inters.cpp:400-483 with src/inters.cpp:566-581); on exact geometry the two normals
+// are opposite and the choices complementary, but rounding-level normal components (1e-16 on the 2 pi box) can make both
+// sides claim (or disclaim) a flux-point pair -- the reference's MPI build then differs from its own serial run by 1e-8
+// (measured with a METIS partition).  In a single-domain run the element with the lower id is the face's left side and
+// ITS normal decides, so the ranks exchange (own mask, global element id) once and the side with the lower id wins: the
+// partitioned run then makes exactly the serial run's choice.  Without global ids (ele_global_l == NULL) the masks are
+// only compared, and any disagreement anywhere sends every rank back to the two-sided generation-6 kernels.
 int hf_fused_after_nccl(hf_ctx *c)
 {
   hf_fused_state *Z = c->fz;
-  if (!Z || !Z->available || !Z->os || c->nproc < 2) return 0;
+  if (!Z || !Z->available || !c->prm.viscous || c->nproc < 2) return 0;
   hf_mpi_inters_dev &M = c->mpis[2];
   const int N = Z->order + 1, NN = N * N, nm = Z->n_mpi;
-  double ok = 1.0;
+  const unsigned long long full = NN == 64 ? ~0ull : ((1ull << NN) - 1ull);
+  const bool have_gid = (int)M.h_gid.size() == nm;
+  double ok = 1.0, gid_everywhere = have_gid ? 1.0 : 0.0;
+  if (hf_halo_allreduce_min(c, &gid_everywhere)) return 1;
   if (nm)
   {
     static_assert(sizeof(unsigned long long) == sizeof(double), "masks travel as 8-byte words");
+    std::vector<double> mine(2 * (size_t)nm), theirs(2 * (size_t)nm);
+    for (int i = 0; i < nm; i++)
+    {
+      memcpy(&mine[2 * (size_t)i], &Z->h_pmask[i], 8);
+      mine[2 * (size_t)i + 1] = have_gid ? (double)M.h_gid[i] : -1.0;
+    }
     double *d_out = nullptr, *d_in = nullptr;
-    if (hf_alloc_copy(c, &d_out, (const double *)Z->h_pmask.data(), (size_t)nm)) return 1;
-    if (hf_alloc_zero(c, &d_in, (size_t)nm)) return 1;
-    if (hf_halo_post(c, M, d_out, d_in, 1) || hf_halo_wait(c)) return 1;
-    std::vector<unsigned long long> theirs(nm);
-    HF_CUDA(cudaMemcpyAsync(theirs.data(), d_in, (size_t)nm * 8, cudaMemcpyDeviceToHost, c->stream));
+    if (hf_alloc_copy(c, &d_out, mine.data(), mine.size())) return 1;
+    if (hf_alloc_zero(c, &d_in, theirs.size())) return 1;
+    if (hf_halo_post(c, M, d_out, d_in, 2) || hf_halo_wait(c)) return 1;
+    HF_CUDA(cudaMemcpyAsync(theirs.data(), d_in, theirs.size() * 8, cudaMemcpyDeviceToHost, c->stream));
     HF_CUDA(cudaStreamSynchronize(c->stream));
-    for (int i = 0; i < nm && ok == 1.0; i++)
+    bool changed = false;
+    for (int i = 0; i < nm; i++)
+    {
+      unsigned long long their_mask;
+      memcpy(&their_mask, &theirs[2 * (size_t)i], 8);
+      // the complement of the neighbour's ownership, in this side's flux-point numbering
+      unsigned long long want = 0ull;
       for (int j = 0; j < NN; j++)
+        if (!((their_mask >> Z->T.perm[(M.h_rot[i] & 3) * 36 + j]) & 1ull)) want |= 1ull << j;
+      if (want == (Z->h_pmask[i] & full)) continue;
+      if (gid_everywhere == 1.0)
       {
-        const int jn = Z->T.perm[(M.h_rot[i] & 3) * 36 + j];
-        if (((Z->h_pmask[i] >> j) & 1ull) == ((theirs[i] >> jn) & 1ull)) { ok = 0.0; break; }
+        if ((double)M.h_gid[i] > theirs[2 * (size_t)i + 1])
+        {
+          // the neighbour is the serial run's left side: take its choice
+          Z->h_pmask[i] = want;
+          Z->h_bmask[(size_t)M.h_ele_l[i] * 6 + M.h_loc_l[i]] = want ^ Z->own_xor;
+          changed = true;
+        }
       }
+      else
+        ok = 0.0;
+    }
+    if (changed) HF_CUDA(cudaMemcpy(Z->bmask, Z->h_bmask.data(), Z->h_bmask.size() * sizeof(unsigned long long), cudaMemcpyHostToDevice));
   }
   if (hf_halo_allreduce_min(c, &ok)) return 1;
-  if (ok != 1.0)
+  if (ok != 1.0 && Z->os)
   {
     Z->os = false;
     Z->fv_blk = 4 * NN;
-    Z->os_why = "the ranks of a partition face disagree on the LDG owner of a flux-point pair (rounding-level normal components)";
+    Z->os_why = "the ranks of a partition face disagree on the LDG owner of a flux-point pair (rounding-level normal components) and no global element ids were given";
   }
   return 0;
 }

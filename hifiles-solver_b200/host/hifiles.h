@@ -494,6 +494,7 @@ public:
   void set_nproc(int in_nproc, int in_rank) { nproc = in_nproc; rank = in_rank; }
   void set_nout_proc(int in_nout, int in_p);
   void set_mpi(int in_inter, int in_ele_type_l, int in_ele_l, int in_local_inter_l, int rot_tag, struct solution *FlowSol);
+  std::vector<int> ele_global_l; // global id of the element behind every interface
   void mv_all_cpu_gpu();
   void send_solution();
   void receive_solution();

@@ -197,8 +197,10 @@ void mpi_inters::set_nout_proc(int in_nout, int in_p)
   neighbour_count.push_back(in_nout);
 }
 
-void mpi_inters::set_mpi(int in_inter, int in_ele_type_l, int in_ele_l, int in_local_inter_l, int rot_tag, struct solution *)
+void mpi_inters::set_mpi(int in_inter, int in_ele_type_l, int in_ele_l, int in_local_inter_l, int rot_tag, struct solution *FlowSol)
 {
+  if ((int)ele_global_l.size() < n_inters) ele_global_l.assign(n_inters, -1);
+  if (FlowSol) ele_global_l[in_inter] = FlowSol->mesh_eles(in_ele_type_l)->ele2global_ele(in_ele_l);
   ele_type_l(in_inter) = in_ele_type_l;
   ele_l(in_inter) = in_ele_l;
   local_inter_l(in_inter) = in_local_inter_l;
@@ -219,6 +221,7 @@ void mpi_inters::mv_all_cpu_gpu()
   d.n_neighbours = (int)neighbour_rank.size();
   d.neighbour_rank = neighbour_rank.data();
   d.neighbour_count = neighbour_count.data();
+  d.ele_global_l = ((int)ele_global_l.size() == n_inters) ? ele_global_l.data() : nullptr;
   hf_check(hf_dev_upload_mpi_inters(ctx, &d));
 }
 

@@ -141,6 +141,10 @@ typedef struct hf_mpi_inters_desc
   int n_neighbours;
   const int *neighbour_rank;  /* [n_neighbours] */
   const int *neighbour_count; /* [n_neighbours] interfaces exchanged with that rank, contiguous slices */
+  /* optional (may be NULL): global id of the element behind every interface.  In a single-domain run the element with the
+   * lower id is the interface's left side and its normal decides the LDG switch (src/inters.cpp:566-581); with the ids the fused
+   * kernels make the same choice on partition faces instead of letting either rank switch on its own normal */
+  const int *ele_global_l;
 } hf_mpi_inters_desc;
 
 /* which-array selectors for hf_dev_download / hf_dev_upload */

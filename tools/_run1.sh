@@ -1,3 +1,5 @@
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_driver_parity.py -q -m gpu -k "plot_file" > gpurun_out/t_drv.log 2>&1; echo "tests exit $?" >> gpurun_out/t_drv.log
-grep "^E   \|^FAILED\|passed\|failed" gpurun_out/t_drv.log | head -30
+( time timeout 1500 python -m pytest tests -q -m gpu -x ) > gpurun_out/t_all.log 2>&1; echo "tests exit $?" >> gpurun_out/t_all.log
+tail -6 gpurun_out/t_all.log
+python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
+timeout 600 python bench.py > gpurun_out/bench_default.log 2>&1; tail -1 gpurun_out/bench_default.log | cut -c1-200
