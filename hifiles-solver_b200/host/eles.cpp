@@ -767,3 +767,83 @@ hf_array<double> eles::compute_error(int in_norm_type, double &time)
     }
   return error_sum;
 }
+
+// ---- solution patch ------------------------------------------------------------------------------------------------------------
+// reference eles::set_patch (src/eles.cpp:535-652): patch_type 0 superposes an isentropic vortex ring (solid-body core of
+// radius ra, decaying to zero at rb, peak Mach number Mv) on the solution inside r <= rb around (xc, yc); patch_type 1 sets
+// the initial-condition state for x >= patch_x.  The expressions keep the reference's order of operations.
+void eles::set_patch()
+{
+  const double gamma = run_input.gamma;
+  const double temp_R = viscous ? run_input.R_ref : run_input.R_gas;
+  hf_array<double> pos(n_dims);
+  for (int i = 0; i < n_eles; i++)
+    for (int j = 0; j < n_upts_per_ele; j++)
+    {
+      for (int k = 0; k < n_dims; k++) pos(k) = pos_upts(j, i, k);
+      double rho, vx, vy, vz = 0., p;
+      if (run_input.patch_type == 0)
+      {
+        const double Mv = run_input.Mv, ra = run_input.ra, rb = run_input.rb, xc = run_input.xc, yc = run_input.yc;
+        const double r = sqrt(pow(pos(0) - xc, 2) + pow(pos(1) - yc, 2));
+        if (!(r <= rb)) continue;
+        rho = disu_upts(0)(j, i, 0);
+        vx = disu_upts(0)(j, i, 1) / disu_upts(0)(j, i, 0);
+        vy = disu_upts(0)(j, i, 2) / disu_upts(0)(j, i, 0);
+        if (n_dims == 2)
+          p = (disu_upts(0)(j, i, 3) - 0.5 * rho * (vx * vx + vy * vy)) * (gamma - 1.0);
+        else
+        {
+          vz = disu_upts(0)(j, i, 3) / disu_upts(0)(j, i, 0);
+          p = (disu_upts(0)(j, i, 4) - 0.5 * rho * (vx * vx + vy * vy + vz * vz)) * (gamma - 1.0);
+        }
+        const double vm = Mv * sqrt(gamma * p / rho); // peak swirl velocity
+        const double T0 = p / (rho * temp_R), cT = (gamma - 1) / (temp_R * gamma);
+        double temper;
+        if (r <= ra)
+        {
+          // solid-body core: (unit tangent) * vm * r / ra, associated left to right as the reference writes it
+          vx -= (pos(1) - yc) / r * vm * r / ra;
+          vy += (pos(0) - xc) / r * vm * r / ra;
+          const double core = pow(vm, 2) / pow(ra, 2) * 0.5 * (pow(ra, 2) - pow(r, 2));
+          const double ring = pow(vm, 2) * pow(ra, 2) / pow(pow(ra, 2) - pow(rb, 2), 2) *
+                              (0.5 * (pow(rb, 2) - pow(ra, 2)) - 0.5 * pow(rb, 4) * (1 / pow(rb, 2) - 1 / pow(ra, 2)) - 2 * pow(rb, 2) * (log(rb / ra)));
+          temper = T0 - cT * (core + ring);
+        }
+        else
+        {
+          vx -= (pos(1) - yc) / r * vm * ra / (pow(ra, 2) - pow(rb, 2)) * (r - pow(rb, 2) / r);
+          vy += (pos(0) - xc) / r * vm * ra / (pow(ra, 2) - pow(rb, 2)) * (r - pow(rb, 2) / r);
+          temper = T0 - cT * pow(vm, 2) * pow(ra, 2) / pow(pow(ra, 2) - pow(rb, 2), 2) *
+                            (0.5 * (pow(rb, 2) - pow(r, 2)) - 0.5 * pow(rb, 4) * (1 / (pow(rb, 2)) - 1 / (pow(r, 2))) - 2 * pow(rb, 2) * (log(rb / r)));
+        }
+        const double rho_temp = rho;
+        rho = rho * pow(temper / (p / (rho * temp_R)), 1 / (gamma - 1));
+        p = p * pow(temper / (p / (rho_temp * temp_R)), gamma / (gamma - 1));
+      }
+      else if (run_input.patch_type == 1)
+      {
+        if (!(pos(0) >= run_input.patch_x)) continue;
+        rho = run_input.rho_c_ic;
+        vx = run_input.u_c_ic;
+        vy = run_input.v_c_ic;
+        vz = run_input.w_c_ic;
+        p = run_input.p_c_ic;
+      }
+      else
+      {
+        FatalError("ERROR: Invalid form of patch ... ");
+        return;
+      }
+      disu_upts(0)(j, i, 0) = rho;
+      disu_upts(0)(j, i, 1) = rho * vx;
+      disu_upts(0)(j, i, 2) = rho * vy;
+      if (n_dims == 2)
+        disu_upts(0)(j, i, 3) = (p / (gamma - 1.0)) + (0.5 * rho * ((vx * vx) + (vy * vy)));
+      else
+      {
+        disu_upts(0)(j, i, 3) = rho * vz;
+        disu_upts(0)(j, i, 4) = (p / (gamma - 1.0)) + (0.5 * rho * ((vx * vx) + (vy * vy) + (vz * vz)));
+      }
+    }
+}

@@ -245,6 +245,8 @@ public:
   void setup(int in_n_eles, int in_max_n_spts_per_ele);
   void set_ics(double &time);
   void set_h_ref();
+  /*! overlay a vortex or a uniform state on the initial / restarted solution (reference eles::set_patch, src/eles.cpp:535-652) */
+  void set_patch();
   /*! volume cubature of the integral diagnostics (reference src/eles.cpp:3667-3687, 4599-4632, 5485-5628) */
   void set_opp_volume_cubpts();
   void set_transforms_vol_cubpts();

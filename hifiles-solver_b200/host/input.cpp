@@ -277,7 +277,19 @@ void input::read_input_file(const string &fileName, int rank)
 
   opts.getScalarValue("patch", patch, 0);
   if (patch)
-    FatalError("solution patching is outside the hot-path scope of this build");
+  {
+    opts.getScalarValue("patch_type", patch_type, 0); // 0: vortex, 1: uniform flow
+    if (patch_type == 0)
+    {
+      opts.getScalarValue("Mv", Mv, 0.5);
+      opts.getScalarValue("ra", ra, 0.075);
+      opts.getScalarValue("rb", rb, 0.175);
+      opts.getScalarValue("xc", xc, 0.25);
+      opts.getScalarValue("yc", yc, 0.5);
+    }
+    else if (patch_type == 1) // uniform patch for x > patch_x with the initial-condition state
+      opts.getScalarValue("patch_x", patch_x);
+  }
 
   if (ic_form == 9 || ic_form == 10)
     opts.getScalarValue("x_shock_ic", x_shock_ic);

@@ -131,6 +131,10 @@ void InitSolution(struct solution *FlowSol)
   }
   else
     FatalError("HiFiLES need to be compiled with HDF5 to read hdf5 format restart file");
+  // patch solution after flow field initialized (reference src/solver.cpp:352-354)
+  if (run_input.patch)
+    for (int i = 0; i < FlowSol->n_ele_types; i++)
+      if (FlowSol->mesh_eles(i)->get_n_eles() != 0) FlowSol->mesh_eles(i)->set_patch();
   if (!FlowSol->no_device) upload_all(FlowSol);
 }
 

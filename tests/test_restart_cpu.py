@@ -63,3 +63,28 @@ def test_hdf5_restart_is_rejected_as_in_the_reference_build_without_hdf5(tmp_pat
     inp = meshgen.write_input(str(tmp_path / "input"), "m.neu", order=1, restart_flag=2, restart_iter=2)
     with pytest.raises(hb.HiFiLESError, match="HDF5"):
         hb.Run(inp, host_only=True)
+
+
+@pytest.mark.parametrize("kind,patch", [("quad", dict(patch=1, patch_type=0, Mv=0.4, ra=1.5, rb=4.0, xc=0.5, yc=-0.25)),
+                                        ("hex", dict(patch=1, patch_type=0, Mv=0.3, ra=1.0, rb=2.5, xc=3.0, yc=3.1)),
+                                        ("hex", dict(patch=1, patch_type=1, patch_x=3.0, u_c_ic=30., v_c_ic=-5., w_c_ic=2., p_c_ic=90000.))])
+def test_solution_patch_matches_reference(tmp_path, hb, meshgen, kind, patch):
+    """eles::set_patch (reference src/eles.cpp:535-652): vortex ring / uniform state laid over the initial solution"""
+    if not util.have_reference():
+        pytest.skip("oracle/_ref not built")
+    if kind == "quad":
+        from test_staged_parity import EULER_IC
+        meshgen.quad_box(str(tmp_path / "m.neu"), 6)
+        opts = dict(order=3, adv_type=3, riemann_solve_type=0, viscous=0, ic_form=0, test_case=1, dt=1e-3, dx_cyclic=20., dy_cyclic=20., dz_cyclic=None, **EULER_IC)
+    else:
+        meshgen.hex_box(str(tmp_path / "m.neu"), 3)
+        opts = dict(order=2, adv_type=2, riemann_solve_type=0, viscous=1, dt=1e-5)
+    inp = meshgen.write_input(str(tmp_path / "input"), "m.neu", **dict(opts, **patch))
+    ref = util.run_reference(inp, 0, stagewise=False)
+    plain = util.run_reference(meshgen.write_input(str(tmp_path / "input_plain"), "m.neu", **opts), 0, stagewise=False)
+    with hb.Run(inp, host_only=True) as run:
+        for k, v in ref.items():
+            if k.endswith(".disu_upts_ic"):
+                a = run.host_array(k.replace("disu_upts_ic", "disu_upts"))
+                assert np.array_equal(a, v), "%s: patched solution differs from the reference (max abs %.3e)" % (k, np.abs(a - v).max())
+                assert not np.array_equal(v, plain[k]), "the patch did not touch the solution: the case checks nothing"
