@@ -1049,6 +1049,29 @@ __global__ void k_integral_quantities(int n_eles, int n_upts, int n_cub, const d
   }
 }
 
+// running time averages (eles::CalcTimeAverageQuantities, reference src/eles.cpp:5630-5702): one thread per solution point
+struct hf_avg_kinds { int n; int kind[HF_MAX_INTEGRAL_QUANTITIES]; };
+__global__ void k_time_average(long long n_pts, int n_upts, int n_dims, const double *__restrict__ u, double *__restrict__ avg, const double *__restrict__ dt_local,
+                               double dt_global, double time, double spinup_time, hf_avg_kinds K)
+{
+  long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (t >= n_pts) return;
+  const double rho = u[t];
+  const double dt = dt_local ? dt_local[t / n_upts] : dt_global;
+  double a, b;
+  if (time == spinup_time) { a = 0.0; b = 1.0; }
+  else { a = (time - spinup_time - dt) / (time - spinup_time); b = dt / (time - spinup_time); }
+  for (int i = 0; i < K.n; i++)
+  {
+    double current_value;
+    const int kind = K.kind[i];
+    if (kind == 0) current_value = rho;
+    else if (kind == 4) current_value = u[t + n_pts * (n_dims + 1)] / rho;
+    else current_value = u[t + n_pts * kind] / rho; // u, v, w: fields 1, 2, 3 (in 2-D the reference's w_average reads field 3 as well)
+    avg[t + n_pts * i] = a * avg[t + n_pts * i] + b * current_value;
+  }
+}
+
 extern "C" {
 
 const char *hf_dev_last_error(void) { return g_err.c_str(); }
@@ -1944,6 +1967,7 @@ static int locate_array(hf_ctx *c, hf_eles_dev &e, int which, double **p, size_t
   case HF_DISUF_UPTS: *p = e.disuf_upts; *n = NU * F; break;
   case HF_LU: *p = e.Lu; *n = NU * (D == 2 ? 3 : 6); break;
   case HF_LE: *p = e.Le; *n = NU * D; break;
+  case HF_DISU_AVERAGE_UPTS: *p = e.disu_average_upts; *n = NU * (size_t)e.n_average; break;
   default: HF_FAIL("unknown array id");
   }
   (void)c;
@@ -2023,6 +2047,33 @@ int hf_dev_set_volume_cubature(hf_ctx *c, int ele_type, int n_cubpts, const doub
   if (hf_alloc_copy(c, &e.detjac_vol_cub, vol_detjac, (size_t)n_cubpts * e.n_eles)) return 1;
   if (hf_alloc_zero(c, &e.iq_elem, (size_t)e.n_eles * HF_MAX_INTEGRAL_QUANTITIES)) return 1;
   c->want_gradient = true;
+  return 0;
+}
+
+int hf_dev_time_average(hf_ctx *c, int ele_type, int n_average_fields, const int *kinds, double time, double spinup_time)
+{
+  HF_CUDA(cudaSetDevice(c->device));
+  if (ele_type < 0 || ele_type >= HF_N_ELE_TYPES || !c->eles[ele_type].present) HF_FAIL("element type not present on the device");
+  hf_eles_dev &e = c->eles[ele_type];
+  if (c->prm.equation != 0) HF_FAIL("time averages are defined for the Euler / Navier-Stokes equations");
+  if (n_average_fields < 1 || n_average_fields > HF_MAX_INTEGRAL_QUANTITIES) HF_FAIL("number of average fields out of range");
+  const long long n_pts = (long long)e.n_upts * e.n_eles;
+  if (!e.disu_average_upts)
+  {
+    if (hf_alloc_zero(c, &e.disu_average_upts, (size_t)n_pts * n_average_fields)) return 1;
+    e.n_average = n_average_fields;
+  }
+  if (e.n_average != n_average_fields) HF_FAIL("the number of average fields changed");
+  hf_avg_kinds K;
+  K.n = n_average_fields;
+  for (int i = 0; i < n_average_fields; i++)
+  {
+    if (kinds[i] < 0 || kinds[i] > 4) HF_FAIL("average field not recognized");
+    K.kind[i] = kinds[i];
+  }
+  k_time_average<<<hf_blocks(n_pts, 256), 256, 0, c->stream>>>(n_pts, e.n_upts, e.n_dims, e.disu_upts[0], e.disu_average_upts,
+                                                             c->prm.dt_type == 2 ? e.dt_local : nullptr, c->prm.dt, time, spinup_time, K);
+  HF_LAUNCH_CHECK(c);
   return 0;
 }
 

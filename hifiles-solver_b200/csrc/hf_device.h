@@ -59,6 +59,8 @@ struct hf_eles_dev
   hf_ell filter_upts;
   double *disuf_upts = nullptr, *uu = nullptr, *ue = nullptr, *Lu = nullptr, *Le = nullptr;
   // volume cubature of the integral diagnostics (eles::CalcIntegralQuantities)
+  double *disu_average_upts = nullptr;
+  int n_average = 0;
   int n_vol_cub = 0;
   double *opp_vol_cub = nullptr, *w_vol_cub = nullptr, *detjac_vol_cub = nullptr, *iq_elem = nullptr;
   // shock capturing (dense, row-major access by mode)

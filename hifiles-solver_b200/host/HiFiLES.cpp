@@ -138,6 +138,9 @@ int main(int argc, char *argv[])
       FlowSol.time += run_input.dt;
       run_input.time = FlowSol.time;
       i_steps++;
+      /*! Compute time-averaged quantities (reference src/HiFiLES.cpp:241-245) */
+      if (i_steps == 1) run_input.spinup_time = FlowSol.time; // set start time for averaging
+      if (run_input.n_average_fields) CalcTimeAverageQuantities(&FlowSol);
       if (i_steps == 1 || i_steps % run_input.monitor_res_freq == 0)
       {
         /*! Compute the value of the forces (reference src/HiFiLES.cpp:250-254) */

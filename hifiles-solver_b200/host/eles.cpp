@@ -847,3 +847,30 @@ void eles::set_patch()
       }
     }
 }
+
+// ---- time averages ---------------------------------------------------------------------------------------------------------------
+void eles::CalcTimeAverageQuantities(double &time)
+{
+  if (n_eles == 0) return;
+  const int n = run_input.n_average_fields;
+  if (n > HF_MAX_INTEGRAL_QUANTITIES) FatalError("too many average fields");
+  int kinds[HF_MAX_INTEGRAL_QUANTITIES];
+  for (int i = 0; i < n; i++)
+  {
+    const string &f = run_input.average_fields(i);
+    if (f == "rho_average") kinds[i] = 0;
+    else if (f == "u_average") kinds[i] = 1;
+    else if (f == "v_average") kinds[i] = 2;
+    else if (f == "w_average") kinds[i] = 3;
+    else if (f == "e_average") kinds[i] = 4;
+    else FatalError("average field not recognized: " + f);
+  }
+  hf_check(hf_dev_time_average(ctx, ele_type, n, kinds, time, run_input.spinup_time));
+}
+
+void eles::cp_disu_average_upts_gpu_cpu()
+{
+  if (!n_eles || !run_input.n_average_fields) return;
+  if (disu_average_upts.size() == 0) disu_average_upts.setup(n_upts_per_ele, n_eles, run_input.n_average_fields);
+  hf_check(hf_dev_download(ctx, ele_type, HF_DISU_AVERAGE_UPTS, disu_average_upts.get_ptr_cpu(), disu_average_upts.size()));
+}

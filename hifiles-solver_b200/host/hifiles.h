@@ -104,6 +104,7 @@ public:
   double area_ref;
   hf_array<std::string> integral_quantities, diagnostic_fields, average_fields;
   int n_integral_quantities, n_diagnostic_fields, n_average_fields;
+  double spinup_time = 0.; // start time of the running averages (set at the first step, reference src/HiFiLES.cpp:242-243)
   // solver
   int riemann_solve_type, vis_riemann_solve_type, adv_type, dt_type;
   double dt, CFL, ldg_tau, ldg_beta, time;
@@ -245,6 +246,9 @@ public:
   void setup(int in_n_eles, int in_max_n_spts_per_ele);
   void set_ics(double &time);
   void set_h_ref();
+  /*! running time averages (reference src/eles.cpp:5630-5702): one device call per time step */
+  void CalcTimeAverageQuantities(double &time);
+  void cp_disu_average_upts_gpu_cpu();
   /*! overlay a vortex or a uniform state on the initial / restarted solution (reference eles::set_patch, src/eles.cpp:535-652) */
   void set_patch();
   /*! volume cubature of the integral diagnostics (reference src/eles.cpp:3667-3687, 4599-4632, 5485-5628) */
@@ -356,7 +360,7 @@ public:
   hf_array<hf_array<double>> opp_1, opp_2, opp_4, opp_5;
   hf_array<double> detjac_upts, JGinv_upts, detjac_fpts, JGinv_fpts, tdA_fpts, norm_fpts, pos_upts, pos_fpts, h_ref;
   hf_array<hf_array<double>> disu_upts, div_tconf_upts;
-  hf_array<double> src_upts, grad_disu_upts, dt_local;
+  hf_array<double> src_upts, grad_disu_upts, dt_local, disu_average_upts;
   std::vector<modal_mode> modes;
   hf_array<double> modal_vandermonde, modal_inv_vandermonde;
   hf_array<double> loc_over_int_cubpts, weight_over_int_cubpts, opp_over_int_cubpts, over_int_filter, JGinv_over_int_cubpts;
@@ -547,6 +551,8 @@ void CalcResidual(int in_file_num, int in_rk_stage, struct solution *FlowSol);
 void calc_time_step(struct solution *FlowSol);
 /*! output::CalcIntegralQuantities (reference src/output.cpp:2017-2040): fills FlowSol->integral_quantities (summed over ranks) */
 void CalcIntegralQuantities(struct solution *FlowSol);
+/*! output::CalcTimeAverageQuantities (reference src/output.cpp:2042-2053) */
+void CalcTimeAverageQuantities(struct solution *FlowSol);
 /*! output::compute_error (reference src/output.cpp:2052-2160): appends one line to error.dat */
 void compute_error(int in_file_num, struct solution *FlowSol);
 /*! output::write_vtu (reference src/output.cpp:462-900): Paraview file(s) of the current solution */

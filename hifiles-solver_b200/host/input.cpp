@@ -203,6 +203,8 @@ void input::read_input_file(const string &fileName, int rank)
   for (int i = 0; i < n_diagnostic_fields; i++)
     std::transform(diagnostic_fields(i).begin(), diagnostic_fields(i).end(), diagnostic_fields(i).begin(), ::tolower);
   n_average_fields = average_fields.get_dim(0);
+  for (int i = 0; i < n_average_fields; i++)
+    std::transform(average_fields(i).begin(), average_fields(i).end(), average_fields(i).begin(), ::tolower);
 
   /* ---- Basic Solver Parameters ---- */
   opts.getScalarValue("riemann_solve_type", riemann_solve_type);

@@ -5,7 +5,8 @@
 // agree with the reference's to the printed digits.  One .vtu per run in serial; with several ranks every rank writes
 // <name>_<iter>/<name>_<iter>_<rank>.vtu and rank 0 the .pvtu index.  Optional diagnostic fields (u, v, w, energy, mach,
 // pressure, vorticity, q_criterion, scaled_q_criterion, sensor: eles::calc_diagnostic_fields_ppts, src/eles.cpp:3858-4010) are
-// evaluated at the plot points from the interpolated solution and gradient; time-averaged fields are not built.  The
+// evaluated at the plot points from the interpolated solution and gradient; time-averaged fields (average_fields) are
+// interpolated from the running averages the device keeps (hf_dev_time_average).  The
 // solution (and gradient) is copied device -> host first (output::CopyGPUCPU).
 #include "hifiles.h"
 #include <cstdio>
@@ -140,7 +141,7 @@ ostream &operator<<(ostream &o, const num &n)
 
 void write_vtu(int in_file_num, struct solution *FlowSol)
 {
-  if (run_input.n_average_fields > 0) FatalError("average_fields in the Paraview files are not built");
+  const int n_average_fields = run_input.n_average_fields;
   const int n_diag_fields = run_input.n_diagnostic_fields;
   const int my_rank = FlowSol->rank, n_proc = FlowSol->nproc;
   static const int vtktypes[5] = {5, 9, 10, 13, 12}; // tri, quad, tet, prism, hex (vtkCellType.h)
@@ -171,6 +172,7 @@ void write_vtu(int in_file_num, struct solution *FlowSol)
       w << "			<PDataArray type=\"Float32\" Name=\"Density\" />" << endl;
       w << "			<PDataArray type=\"Float32\" Name=\"Velocity\" NumberOfComponents=\"3\" />" << endl;
       w << "			<PDataArray type=\"Float32\" Name=\"SpecificTotalEnergy\" />" << endl;
+      for (int m = 0; m < n_average_fields; m++) w << "			<PDataArray type=\"Float32\" Name=\"" << run_input.average_fields(m) << "\" />" << endl;
       for (int m = 0; m < n_diag_fields; m++) w << "			<PDataArray type=\"Float32\" Name=\"" << run_input.diagnostic_fields(m) << "\" />" << endl;
       w << "		</PPointData>" << endl;
       w << "		<PPoints>" << endl;
@@ -205,6 +207,9 @@ void write_vtu(int in_file_num, struct solution *FlowSol)
     const bool need_grad = n_diag_fields > 0 && run_input.viscous;
     const bool have_grad = need_grad && !FlowSol->no_device && in_file_num != FlowSol->ini_iter;
     if (have_grad) e->cp_grad_disu_upts_gpu_cpu();
+    // running averages: zero before the first step, as the reference's freshly allocated array
+    const bool have_avg = n_average_fields > 0 && !FlowSol->no_device && in_file_num != FlowSol->ini_iter;
+    if (have_avg) e->cp_disu_average_upts_gpu_cpu();
     if (n_diag_fields > 0 && run_input.shock_cap && !FlowSol->no_device) e->cp_sensor_gpu_cpu();
     plot_topology T;
     build_topology(e, run_input.p_res, T);
@@ -306,6 +311,18 @@ void write_vtu(int in_file_num, struct solution *FlowSol)
       w << "				<DataArray type= \"Float32\" Name=\"SpecificTotalEnergy\" format=\"ascii\">" << endl;
       for (int k = 0; k < n_points; k++) w << num{u(k, n_dims + 1) / u(k, 0)} << " ";
       w << endl << "				</DataArray>" << endl;
+      for (int m = 0; m < n_average_fields; m++)
+      {
+        w << "				<DataArray type= \"Float32\" Name=\"" << run_input.average_fields(m) << "\" format=\"ascii\">" << endl;
+        for (int k = 0; k < n_points; k++)
+        {
+          double a = 0.;
+          if (have_avg)
+            for (int l = 0; l < nu; l++) a += e->disu_average_upts(l, j, m) * T.opp_p(k, l);
+          w << num{a} << " ";
+        }
+        w << endl << "				</DataArray>" << endl;
+      }
       for (int m = 0; m < n_diag_fields; m++)
       {
         w << "				<DataArray type= \"Float32\" Name=\"" << run_input.diagnostic_fields(m) << "\" format=\"ascii\">" << endl;

@@ -203,6 +203,12 @@ void AdvanceStage(int in_file_num, int in_rk_stage, struct solution *FlowSol, bo
     for (int j = 0; j < FlowSol->n_ele_types; j++) FlowSol->mesh_eles(j)->shock_capture();
 }
 
+void CalcTimeAverageQuantities(struct solution *FlowSol)
+{
+  for (int i = 0; i < FlowSol->n_ele_types; i++)
+    if (FlowSol->mesh_eles(i)->get_n_eles() != 0) FlowSol->mesh_eles(i)->CalcTimeAverageQuantities(FlowSol->time);
+}
+
 void CalcIntegralQuantities(struct solution *FlowSol)
 {
   const int nintq = run_input.n_integral_quantities;

@@ -154,7 +154,8 @@ enum hf_array_id
   HF_NORM_TDISF_FPTS = 5, HF_NORM_TCONF_FPTS = 6, HF_DELTA_DISU_FPTS = 7, HF_GRAD_DISU_UPTS = 8,
   HF_GRAD_DISU_FPTS = 9, HF_SRC_UPTS = 10, HF_DT_LOCAL = 11, HF_SENSOR = 12, /* (ele) Persson sensor of the last shock_capture */
   HF_SGSF_UPTS = 13, HF_SGSF_FPTS = 14, /* (pt,ele,field,dim) sub-grid-scale flux, LES runs */
-  HF_DISUF_UPTS = 15, HF_LU = 16, HF_LE = 17 /* filtered solution (upt,ele,field), Leonard tensors (upt,ele,3|6) and (upt,ele,dim) */
+  HF_DISUF_UPTS = 15, HF_LU = 16, HF_LE = 17, /* filtered solution (upt,ele,field), Leonard tensors (upt,ele,3|6) and (upt,ele,dim) */
+  HF_DISU_AVERAGE_UPTS = 18 /* (upt,ele,average field): running time averages, hf_dev_time_average */
 };
 
 /* element operations = the eles methods CalcResidual calls (reference src/solver.cpp:65-216) */
@@ -240,6 +241,11 @@ int hf_dev_residual_norm(hf_ctx *ctx, int norm_type, double *out);
 /* on != 0: stages that keep the residual also leave grad_disu_upts behind in fused mode (the staged kernels always do):
  * surface forces and the vorticity-type plot fields read it like the integral diagnostics.  Set by hf_dev_set_volume_cubature too. */
 int hf_dev_set_keep_gradient(hf_ctx *ctx, int on);
+/* Running time averages at the solution points = eles::CalcTimeAverageQuantities (reference src/eles.cpp:5630-5702), called once
+ * per time step: average <- a * average + b * current with a = (time - spinup - dt) / (time - spinup), b = dt / (time - spinup)
+ * (a = 0, b = 1 while time == spinup).  kinds: 0 rho_average, 1 u_average, 2 v_average, 3 w_average, 4 e_average.
+ * The array (HF_DISU_AVERAGE_UPTS) is created zeroed by the first call. */
+int hf_dev_time_average(hf_ctx *ctx, int ele_type, int n_average_fields, const int *kinds, double time, double spinup_time);
 int hf_dev_set_volume_cubature(hf_ctx *ctx, int ele_type, int n_cubpts, const double *opp_volume_cubpts, const double *weights, const double *vol_detjac);
 int hf_dev_integral_quantities(hf_ctx *ctx, int ele_type, int n_quantities, const int *kinds, double *out);
 /* sum of v[n] over the ranks of the context's communicator, in place on every rank (no-op on one rank) */

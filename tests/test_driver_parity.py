@@ -194,6 +194,32 @@ def test_plot_file_with_diagnostic_fields_matches_reference_binary(tmp_path, hb,
     assert np.abs(na).max() > 1.0
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("kernels", ["staged", "fused"])
+def test_time_averaged_fields_match_reference_binary(tmp_path, hb, meshgen, kernels):
+    """average_fields: the running averages updated on the device after every step (eles::CalcTimeAverageQuantities),
+    compared through the Paraview file after three steps"""
+    if not (os.path.exists(REF) and os.path.exists(OURS)):
+        pytest.skip("driver binaries not built")
+    from test_plot_cpu import split_vtu
+    out = {}
+    for who, exe in (("ref", REF), ("ours", OURS)):
+        d = tmp_path / who
+        d.mkdir()
+        meshgen.hex_box(str(d / "tgv.neu"), 3)
+        meshgen.write_input(str(d / "input"), "tgv.neu", order=2, adv_type=2, dt=1e-5, riemann_solve_type=3, viscous=1, n_steps=3, monitor_res_freq=100,
+                            plot_freq=3, p_res=2, data_file_name="Mesh", average_fields="5 rho_average u_average v_average w_average e_average",
+                            device_fused=1 if kernels == "fused" else 0)
+        env = dict(os.environ, HIFILES_HOME=util.REF_DIR if who == "ref" else os.path.join(util.ROOT, "hifiles-solver_b200"))
+        r = subprocess.run([exe, "input"], cwd=str(d), env=env, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+        out[who] = split_vtu(d / "Mesh_000000003.vtu")
+    (ta, na), (tb, nb) = out["ref"], out["ours"]
+    assert ta == tb and na.shape == nb.shape
+    assert "Name=\"u_average\"" in ta
+    assert np.abs(na - nb).max() <= 1e-11 * np.abs(na).max()
+
+
 def restart_numbers(path):
     """structure (all non-numeric lines, in order) and numbers of an ASCII restart file"""
     text, nums = [], []

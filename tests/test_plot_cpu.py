@@ -27,7 +27,8 @@ def split_vtu(path):
 
 
 @pytest.mark.parametrize("kind,order,p_res,diag", [("hex", 2, 3, None), ("quadtri", 2, 4, None), ("pritet", 1, 4, None), ("pritet", 2, 2, None),
-                                                   ("hex", 2, 2, "8 u V w energy Mach pressure vorticity q_criterion"), ("quadtri", 2, 3, "4 u w pressure vorticity")])
+                                                   ("hex", 2, 2, "8 u V w energy Mach pressure vorticity q_criterion"), ("quadtri", 2, 3, "4 u w pressure vorticity"),
+                                                   ("hex", 1, 2, "avg")])
 def test_initial_vtu_matches_reference_binary(tmp_path, hb, meshgen, kind, order, p_res, diag, monkeypatch):
     if not (util.have_reference() and os.path.exists(REF)):
         pytest.skip("oracle/_ref not built")
@@ -39,7 +40,9 @@ def test_initial_vtu_matches_reference_binary(tmp_path, hb, meshgen, kind, order
         extra = dict(dz_cyclic=None)
     else:
         meshgen.mixed_box_3d(str(tmp_path / "m.neu"), (2, 2, 2), kind=kind)
-    if diag:
+    if diag == "avg":
+        extra["average_fields"] = "5 rho_average u_average v_average w_average e_average"  # zero before the first step
+    elif diag:
         extra["diagnostic_fields"] = diag  # optional plot fields; the gradient-based ones are zero before the first residual evaluation
     inp = meshgen.write_input(str(tmp_path / "input"), "m.neu", order=order, adv_type=2, dt=1e-5, riemann_solve_type=0, viscous=1, n_steps=0,
                               p_res=p_res, data_file_name="Plot", **extra)
