@@ -125,9 +125,8 @@ int main(int argc, char *argv[])
     }
     clock_t init_time = clock();
     int i_steps = 0;
-    /*! Dump initial Paraview file (reference src/HiFiLES.cpp:171-182; Tecplot / CGNS writers are not built) */
-    if (run_input.write_type == 0) write_vtu(FlowSol.ini_iter + i_steps, &FlowSol);
-    else FatalError("ERROR: Trying to write unrecognized file format ... ");
+    /*! Dump initial Paraview or Tecplot file (reference src/HiFiLES.cpp:171-182; the CGNS writer is not built) */
+    write_plot(FlowSol.ini_iter + i_steps, &FlowSol);
     while (i_steps < run_input.n_steps)
     {
       calc_time_step(&FlowSol);
@@ -169,7 +168,7 @@ int main(int argc, char *argv[])
           fprintf(hist, ", %.15g\n", (double)(clock() - init_time) / CLOCKS_PER_SEC / 60.);
         }
       }
-      if (i_steps % run_input.plot_freq == 0) write_vtu(FlowSol.ini_iter + i_steps, &FlowSol);
+      if (i_steps % run_input.plot_freq == 0) write_plot(FlowSol.ini_iter + i_steps, &FlowSol);
       if (i_steps % run_input.restart_dump_freq == 0) write_restart_ascii(&FlowSol, FlowSol.ini_iter + i_steps);
     }
     /*! Calculate Error (reference src/HiFiLES.cpp:324-325) */

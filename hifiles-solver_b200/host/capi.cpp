@@ -146,7 +146,7 @@ int hifiles_nccl_init(void *handle, const char *unique_id_128_bytes)
 /* output::write_vtu of the current solution into the working directory (file name from data_file_name and iter) */
 int hifiles_write_vtu(void *handle, int iter)
 {
-  return guard([&]() { write_vtu(iter, &((run_handle *)handle)->FlowSol); });
+  return guard([&]() { write_plot(iter, &((run_handle *)handle)->FlowSol); });
 }
 
 int hifiles_norm_residual(void *handle, double *out, int n)

@@ -557,6 +557,10 @@ void CalcTimeAverageQuantities(struct solution *FlowSol);
 void compute_error(int in_file_num, struct solution *FlowSol);
 /*! output::write_vtu (reference src/output.cpp:462-900): Paraview file(s) of the current solution */
 void write_vtu(int in_file_num, struct solution *FlowSol);
+/*! output::write_tec (reference src/output.cpp:165-451): Tecplot ASCII file of the current solution */
+void write_tec(int in_file_num, struct solution *FlowSol);
+/*! the plot file of the format write_type selects (0 Paraview, 1 Tecplot; CGNS is not built) */
+void write_plot(int in_file_num, struct solution *FlowSol);
 /*! output::CalcForces (reference src/output.cpp:1915-2012): fills inv_force, vis_force, coeff_lift, coeff_drag; optionally the cp files */
 void CalcForces(int in_file_num, bool write_forces, struct solution *FlowSol);
 /*! CalcResidual + AdvanceSolution (+ shock_capture) of one RK stage: one fused device call where the fused kernels are

@@ -139,10 +139,156 @@ ostream &operator<<(ostream &o, const num &n)
 }
 } // namespace
 
+// everything a plot file holds for one element type: topology, and per element the fields at the plot points
+struct plot_fields
+{
+  eles *e = nullptr;
+  plot_topology T;
+  int n_points = 0, n_cells = 0, n_verts = 0, n_fields = 0, n_dims = 0, nu = 0, n_diag_fields = 0, n_average_fields = 0;
+  bool have_grad = false, have_avg = false;
+  hf_array<double> u, g, diag, avg, pos;
+
+  // copies the arrays device -> host (output::CopyGPUCPU) and builds the plot topology
+  void setup(eles *in_e, struct solution *FlowSol, int in_file_num)
+  {
+    e = in_e;
+    n_diag_fields = run_input.n_diagnostic_fields;
+    n_average_fields = run_input.n_average_fields;
+    if (run_input.equation != 0) FatalError("plot files are built for the Euler / Navier-Stokes equations");
+    if (!FlowSol->no_device) e->cp_disu_upts_gpu_cpu();
+    // gradient of the last monitored residual evaluation; before the first step the reference's array is still zero
+    have_grad = n_diag_fields > 0 && run_input.viscous && !FlowSol->no_device && in_file_num != FlowSol->ini_iter;
+    if (have_grad) e->cp_grad_disu_upts_gpu_cpu();
+    // running averages: zero before the first step, as the reference's freshly allocated array
+    have_avg = n_average_fields > 0 && !FlowSol->no_device && in_file_num != FlowSol->ini_iter;
+    if (have_avg) e->cp_disu_average_upts_gpu_cpu();
+    if (n_diag_fields > 0 && run_input.shock_cap && !FlowSol->no_device) e->cp_sensor_gpu_cpu();
+    build_topology(e, run_input.p_res, T);
+    n_points = T.n_ppts; n_cells = T.n_peles; n_verts = T.n_verts; n_fields = e->n_fields; n_dims = e->n_dims; nu = e->n_upts_per_ele;
+    u.setup(n_points, n_fields);
+    g.setup(n_points, n_fields, n_dims);
+    diag.setup(n_points, n_diag_fields > 0 ? n_diag_fields : 1);
+    avg.setup(n_points, n_average_fields > 0 ? n_average_fields : 1);
+    pos.setup(n_points, n_dims);
+  }
+
+  // fields of element j at its plot points (reference eles::calc_disu_ppts, calc_time_average_ppts, calc_grad_disu_ppts,
+  // calc_sensor_ppts, calc_diagnostic_fields_ppts, calc_pos_ppts: src/eles.cpp:3714-4010)
+  void eval(int j)
+  {
+    for (int m = 0; m < n_fields; m++)
+      for (int k = 0; k < n_points; k++)
+      {
+        double a = 0.;
+        for (int l = 0; l < nu; l++) a += e->disu_upts(0)(l, j, m) * T.opp_p(k, l);
+        u(k, m) = a;
+      }
+    for (int m = 0; m < n_average_fields; m++)
+      for (int k = 0; k < n_points; k++)
+      {
+        double a = 0.;
+        if (have_avg)
+          for (int l = 0; l < nu; l++) a += e->disu_average_upts(l, j, m) * T.opp_p(k, l);
+        avg(k, m) = a;
+      }
+    hf_array<double> loc(n_dims), p(n_dims);
+    for (int k = 0; k < n_points; k++)
+    {
+      for (int l = 0; l < n_dims; l++) loc(l) = T.loc_ppts(l, k);
+      e->calc_pos(loc, j, p);
+      for (int l = 0; l < n_dims; l++) pos(k, l) = p(l);
+    }
+    if (n_diag_fields == 0) return;
+    for (int d = 0; d < n_dims; d++)
+      for (int m = 0; m < n_fields; m++)
+        for (int k = 0; k < n_points; k++)
+        {
+          double a = 0.;
+          if (have_grad)
+            for (int l = 0; l < nu; l++) a += e->grad_disu_upts(l, j, m, d) * T.opp_p(k, l);
+          g(k, m, d) = a;
+        }
+    const double sensor = (run_input.shock_cap && e->sensor.size() > 0) ? e->sensor(j) : 0.;
+    for (int k = 0; k < n_points; k++)
+    {
+      double v_sq = 0.;
+      for (int m = 0; m < n_dims; m++) v_sq += (u(k, m + 1) * u(k, m + 1));
+      v_sq /= u(k, 0) * u(k, 0);
+      const double pressure = (run_input.gamma - 1.0) * (u(k, n_dims + 1) - 0.5 * u(k, 0) * v_sq);
+      const double irho = 1. / u(k, 0);
+      for (int q = 0; q < n_diag_fields; q++)
+      {
+        const string &name = run_input.diagnostic_fields(q);
+        double val = 0.;
+        if (name == "u") val = u(k, 1) * irho;
+        else if (name == "v") val = u(k, 2) * irho;
+        else if (name == "w") val = (n_dims == 2) ? 0. : u(k, 3) * irho;
+        else if (name == "energy") val = u(k, n_dims + 1);
+        else if (name == "mach") val = sqrt(v_sq / (run_input.gamma * pressure / u(k, 0)));
+        else if (name == "pressure") val = pressure;
+        else if (name == "vorticity" || name == "q_criterion" || name == "scaled_q_criterion")
+        {
+          if (!run_input.viscous) FatalError("Trying to calculate diagnostic field only supported by viscous simualtion");
+          double dvel[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}}; // d v_a / d x_b
+          for (int a = 0; a < n_dims; a++)
+          {
+            const double va = u(k, a + 1) * irho;
+            for (int b = 0; b < n_dims; b++) dvel[a][b] = irho * (g(k, a + 1, b) - va * g(k, 0, b));
+          }
+          if (n_dims == 2)
+          {
+            if (name != "vorticity") FatalError("Q criterion Not implemented in 2D");
+            val = fabs(dvel[1][0] - dvel[0][1]);
+          }
+          else
+          {
+            double wx = dvel[2][1] - dvel[1][2], wy = dvel[0][2] - dvel[2][0], wz = dvel[1][0] - dvel[0][1];
+            if (name == "vorticity") val = sqrt(wx * wx + wy * wy + wz * wz);
+            else
+            {
+              wx *= 0.5; wy *= 0.5; wz *= 0.5;
+              const double Sxy = 0.5 * (dvel[0][1] + dvel[1][0]), Sxz = 0.5 * (dvel[0][2] + dvel[2][0]), Syz = 0.5 * (dvel[1][2] + dvel[2][1]);
+              const double SS = dvel[0][0] * dvel[0][0] + dvel[1][1] * dvel[1][1] + dvel[2][2] * dvel[2][2] + 2 * Sxy * Sxy + 2 * Sxz * Sxz + 2 * Syz * Syz;
+              const double OO = 2 * wx * wx + 2 * wy * wy + 2 * wz * wz;
+              val = (name == "q_criterion") ? 0.5 * (OO - SS) : 0.5 * (OO - SS) / (SS + 1.e-24);
+            }
+          }
+        }
+        else if (name == "sensor")
+        {
+          if (!run_input.shock_cap) FatalError("Sensor unavailable");
+          val = sensor;
+        }
+        else
+          FatalError("plot_quantity not recognized");
+        if (std::isnan(val)) FatalError("NaN in the calculation of plot quantity " + name);
+        diag(k, q) = val;
+      }
+    }
+  }
+};
+
+// empty an existing output directory or create it (rank 0), then wait until it is there (all ranks, same file system)
+static void prepare_directory(const char *dir_s, struct solution *FlowSol)
+{
+  if (FlowSol->rank == 0)
+  {
+    struct stat st;
+    if (stat(dir_s, &st) == -1) mkdir(dir_s, 0755);
+    else if (DIR *dir = opendir(dir_s))
+    {
+      while (struct dirent *fn = readdir(dir))
+        if (strcmp(fn->d_name, ".") != 0 && strcmp(fn->d_name, "..") != 0) remove((string(dir_s) + '/' + fn->d_name).c_str());
+      closedir(dir);
+    }
+  }
+  struct stat st;
+  for (int spin = 0; stat(dir_s, &st) == -1 && spin < 10000; spin++) hf_dev_sync(FlowSol->ctx);
+}
+
 void write_vtu(int in_file_num, struct solution *FlowSol)
 {
-  const int n_average_fields = run_input.n_average_fields;
-  const int n_diag_fields = run_input.n_diagnostic_fields;
+  const int n_diag_fields = run_input.n_diagnostic_fields, n_average_fields = run_input.n_average_fields;
   const int my_rank = FlowSol->rank, n_proc = FlowSol->nproc;
   static const int vtktypes[5] = {5, 9, 10, 13, 12}; // tri, quad, tet, prism, hex (vtkCellType.h)
   char dumpnum_s[256], vtu_s[600], pvtu_s[300];
@@ -152,17 +298,9 @@ void write_vtu(int in_file_num, struct solution *FlowSol)
   {
     snprintf(vtu_s, sizeof(vtu_s), "%s/%s_%d.vtu", dumpnum_s, dumpnum_s, my_rank);
     snprintf(pvtu_s, sizeof(pvtu_s), "%s.pvtu", dumpnum_s);
+    prepare_directory(dumpnum_s, FlowSol);
     if (my_rank == 0)
     {
-      struct stat st;
-      if (stat(dumpnum_s, &st) == -1) mkdir(dumpnum_s, 0755);
-      else if (DIR *dir = opendir(dumpnum_s))
-      {
-        // delete old .vtu files from the directory
-        while (struct dirent *fn = readdir(dir))
-          if (strcmp(fn->d_name, ".") != 0 && strcmp(fn->d_name, "..") != 0) remove((string(dumpnum_s) + '/' + fn->d_name).c_str());
-        closedir(dir);
-      }
       cout << "Writing Paraview file " << dumpnum_s << " ...." << flush;
       ofstream w(pvtu_s);
       w << "<?xml version=\"1.0\" ?>" << endl;
@@ -182,10 +320,6 @@ void write_vtu(int in_file_num, struct solution *FlowSol)
       w << "	</PUnstructuredGrid>" << endl;
       w << "</VTKFile>" << endl;
     }
-    // the other ranks need the directory: every rank has passed device calls since rank 0 got here only if it exists, so
-    // make sure of it locally (same file system on one node)
-    struct stat st;
-    for (int spin = 0; stat(dumpnum_s, &st) == -1 && spin < 10000; spin++) hf_dev_sync(FlowSol->ctx);
   }
   else
   {
@@ -202,100 +336,14 @@ void write_vtu(int in_file_num, struct solution *FlowSol)
     eles *e = FlowSol->mesh_eles(t);
     const int n_eles = e->get_n_eles();
     if (n_eles == 0) continue;
-    if (!FlowSol->no_device) e->cp_disu_upts_gpu_cpu();
-    // gradient of the last monitored residual evaluation; before the first step the reference's array is still zero
-    const bool need_grad = n_diag_fields > 0 && run_input.viscous;
-    const bool have_grad = need_grad && !FlowSol->no_device && in_file_num != FlowSol->ini_iter;
-    if (have_grad) e->cp_grad_disu_upts_gpu_cpu();
-    // running averages: zero before the first step, as the reference's freshly allocated array
-    const bool have_avg = n_average_fields > 0 && !FlowSol->no_device && in_file_num != FlowSol->ini_iter;
-    if (have_avg) e->cp_disu_average_upts_gpu_cpu();
-    if (n_diag_fields > 0 && run_input.shock_cap && !FlowSol->no_device) e->cp_sensor_gpu_cpu();
-    plot_topology T;
-    build_topology(e, run_input.p_res, T);
-    const int n_points = T.n_ppts, n_cells = T.n_peles, n_verts = T.n_verts, n_fields = e->n_fields, n_dims = e->n_dims, nu = e->n_upts_per_ele;
-    if (run_input.equation != 0) FatalError("Paraview output is built for the Euler / Navier-Stokes equations");
-    hf_array<double> u(n_points, n_fields), loc(n_dims), pos(n_dims), g(n_points, n_fields, n_dims), diag(n_points, n_diag_fields > 0 ? n_diag_fields : 1);
+    plot_fields P;
+    P.setup(e, FlowSol, in_file_num);
+    const int n_points = P.n_points, n_cells = P.n_cells, n_verts = P.n_verts, n_dims = P.n_dims;
     for (int j = 0; j < n_eles; j++)
     {
+      P.eval(j);
+      const hf_array<double> &u = P.u;
       w << "		<Piece NumberOfPoints=\"" << n_points << "\" NumberOfCells=\"" << n_cells << "\">" << endl;
-      // prognostic fields at the plot points (reference eles::calc_disu_ppts: opp_p times the element's solution)
-      for (int m = 0; m < n_fields; m++)
-        for (int k = 0; k < n_points; k++)
-        {
-          double a = 0.;
-          for (int l = 0; l < nu; l++) a += e->disu_upts(0)(l, j, m) * T.opp_p(k, l);
-          u(k, m) = a;
-        }
-      if (n_diag_fields > 0)
-      {
-        for (int d = 0; d < n_dims; d++)
-          for (int m = 0; m < n_fields; m++)
-            for (int k = 0; k < n_points; k++)
-            {
-              double a = 0.;
-              if (have_grad)
-                for (int l = 0; l < nu; l++) a += e->grad_disu_upts(l, j, m, d) * T.opp_p(k, l);
-              g(k, m, d) = a;
-            }
-        const double sensor = (run_input.shock_cap && e->sensor.size() > 0) ? e->sensor(j) : 0.;
-        for (int k = 0; k < n_points; k++)
-        {
-          double v_sq = 0.;
-          for (int m = 0; m < n_dims; m++) v_sq += (u(k, m + 1) * u(k, m + 1));
-          v_sq /= u(k, 0) * u(k, 0);
-          const double pressure = (run_input.gamma - 1.0) * (u(k, n_dims + 1) - 0.5 * u(k, 0) * v_sq);
-          const double irho = 1. / u(k, 0);
-          for (int q = 0; q < n_diag_fields; q++)
-          {
-            const string &name = run_input.diagnostic_fields(q);
-            double val = 0.;
-            if (name == "u") val = u(k, 1) * irho;
-            else if (name == "v") val = u(k, 2) * irho;
-            else if (name == "w") val = (n_dims == 2) ? 0. : u(k, 3) * irho;
-            else if (name == "energy") val = u(k, n_dims + 1);
-            else if (name == "mach") val = sqrt(v_sq / (run_input.gamma * pressure / u(k, 0)));
-            else if (name == "pressure") val = pressure;
-            else if (name == "vorticity" || name == "q_criterion" || name == "scaled_q_criterion")
-            {
-              if (!run_input.viscous) FatalError("Trying to calculate diagnostic field only supported by viscous simualtion");
-              double dvel[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}}; // d v_a / d x_b
-              for (int a = 0; a < n_dims; a++)
-              {
-                const double va = u(k, a + 1) * irho;
-                for (int b = 0; b < n_dims; b++) dvel[a][b] = irho * (g(k, a + 1, b) - va * g(k, 0, b));
-              }
-              if (n_dims == 2)
-              {
-                if (name != "vorticity") FatalError("Q criterion Not implemented in 2D");
-                val = fabs(dvel[1][0] - dvel[0][1]);
-              }
-              else
-              {
-                double wx = dvel[2][1] - dvel[1][2], wy = dvel[0][2] - dvel[2][0], wz = dvel[1][0] - dvel[0][1];
-                if (name == "vorticity") val = sqrt(wx * wx + wy * wy + wz * wz);
-                else
-                {
-                  wx *= 0.5; wy *= 0.5; wz *= 0.5;
-                  const double Sxy = 0.5 * (dvel[0][1] + dvel[1][0]), Sxz = 0.5 * (dvel[0][2] + dvel[2][0]), Syz = 0.5 * (dvel[1][2] + dvel[2][1]);
-                  const double SS = dvel[0][0] * dvel[0][0] + dvel[1][1] * dvel[1][1] + dvel[2][2] * dvel[2][2] + 2 * Sxy * Sxy + 2 * Sxz * Sxz + 2 * Syz * Syz;
-                  const double OO = 2 * wx * wx + 2 * wy * wy + 2 * wz * wz;
-                  val = (name == "q_criterion") ? 0.5 * (OO - SS) : 0.5 * (OO - SS) / (SS + 1.e-24);
-                }
-              }
-            }
-            else if (name == "sensor")
-            {
-              if (!run_input.shock_cap) FatalError("Sensor unavailable");
-              val = sensor;
-            }
-            else
-              FatalError("plot_quantity not recognized");
-            if (std::isnan(val)) FatalError("NaN in the calculation of plot quantity " + name);
-            diag(k, q) = val;
-          }
-        }
-      }
       w << "			<PointData>" << endl;
       w << "				<DataArray type= \"Float32\" Name=\"Density\" format=\"ascii\">" << endl;
       for (int k = 0; k < n_points; k++) w << num{u(k, 0)} << " ";
@@ -314,19 +362,13 @@ void write_vtu(int in_file_num, struct solution *FlowSol)
       for (int m = 0; m < n_average_fields; m++)
       {
         w << "				<DataArray type= \"Float32\" Name=\"" << run_input.average_fields(m) << "\" format=\"ascii\">" << endl;
-        for (int k = 0; k < n_points; k++)
-        {
-          double a = 0.;
-          if (have_avg)
-            for (int l = 0; l < nu; l++) a += e->disu_average_upts(l, j, m) * T.opp_p(k, l);
-          w << num{a} << " ";
-        }
+        for (int k = 0; k < n_points; k++) w << num{P.avg(k, m)} << " ";
         w << endl << "				</DataArray>" << endl;
       }
       for (int m = 0; m < n_diag_fields; m++)
       {
         w << "				<DataArray type= \"Float32\" Name=\"" << run_input.diagnostic_fields(m) << "\" format=\"ascii\">" << endl;
-        for (int k = 0; k < n_points; k++) w << num{diag(k, m)} << " ";
+        for (int k = 0; k < n_points; k++) w << num{P.diag(k, m)} << " ";
         w << endl << "				</DataArray>" << endl;
       }
       w << "			</PointData>" << endl;
@@ -334,9 +376,7 @@ void write_vtu(int in_file_num, struct solution *FlowSol)
       w << "				<DataArray type=\"Float32\" NumberOfComponents=\"3\" format=\"ascii\">" << endl;
       for (int k = 0; k < n_points; k++)
       {
-        for (int l = 0; l < n_dims; l++) loc(l) = T.loc_ppts(l, k);
-        e->calc_pos(loc, j, pos);
-        for (int l = 0; l < n_dims; l++) w << num{pos(l)} << " ";
+        for (int l = 0; l < n_dims; l++) w << num{P.pos(k, l)} << " ";
         if (n_dims == 2) w << "0 ";
       }
       w << endl << "				</DataArray>" << endl;
@@ -345,7 +385,7 @@ void write_vtu(int in_file_num, struct solution *FlowSol)
       w << "				<DataArray type=\"Int32\" Name=\"connectivity\" format=\"ascii\">" << endl;
       for (int k = 0; k < n_cells; k++)
       {
-        for (int l = 0; l < n_verts; l++) w << T.con[(size_t)k * n_verts + l] << " ";
+        for (int l = 0; l < n_verts; l++) w << P.T.con[(size_t)k * n_verts + l] << " ";
         w << endl;
       }
       w << "				</DataArray>" << endl;
@@ -363,4 +403,85 @@ void write_vtu(int in_file_num, struct solution *FlowSol)
   w << "</VTKFile>" << endl;
   w.close();
   if (my_rank == 0) cout << "done." << endl;
+}
+
+// Tecplot output (reference output::write_tec, src/output.cpp:165-451): one finite-element zone per element type, point
+// data = position, conservative variables, optional averages and diagnostic fields; connectivity one-based.
+void write_tec(int in_file_num, struct solution *FlowSol)
+{
+  const int n_diag_fields = run_input.n_diagnostic_fields, n_average_fields = run_input.n_average_fields, n_dims = FlowSol->n_dims;
+  char file_name_s[600], dumpnum_s[256];
+  const char *name = run_input.data_file_name.c_str();
+  if (FlowSol->nproc != 1)
+  {
+    snprintf(dumpnum_s, sizeof(dumpnum_s), "%s_%.09d", name, in_file_num);
+    snprintf(file_name_s, sizeof(file_name_s), "%s/%s_p%.04d.plt", dumpnum_s, dumpnum_s, FlowSol->rank);
+    prepare_directory(dumpnum_s, FlowSol);
+  }
+  else
+    snprintf(file_name_s, sizeof(file_name_s), "%s_%.09d_p%.04d.plt", name, in_file_num, FlowSol->rank);
+  if (FlowSol->rank == 0) cout << "Writing Tecplot file number " << in_file_num << " ...." << flush;
+  ofstream w(file_name_s);
+  if (!w) FatalError(string("cannot open ") + file_name_s);
+  w << "Title = \"HiFiLES Solution\"" << endl;
+  string fields = n_dims == 2 ? "Variables = \"x\", \"y\", \"rho\", \"mom_x\", \"mom_y\", \"rhoE\""
+                              : "Variables = \"x\", \"y\", \"z\", \"rho\", \"mom_x\", \"mom_y\", \"mom_z\", \"rhoE\"";
+  for (int m = 0; m < n_average_fields; m++) fields += ", \"" + run_input.average_fields(m) + "\"";
+  for (int m = 0; m < n_diag_fields; m++) fields += ", \"" + run_input.diagnostic_fields(m) + "\"";
+  w << fields << endl;
+  static const char *zonetype[5] = {"FETRIANGLE", "FEQUADRILATERAL", "FETETRAHEDRON", "FEBRICK", "FEBRICK"};
+  bool time_written = false;
+  for (int t = 0; t < FlowSol->n_ele_types; t++)
+  {
+    eles *e = FlowSol->mesh_eles(t);
+    const int n_eles = e->get_n_eles();
+    if (n_eles == 0) continue;
+    plot_fields P;
+    P.setup(e, FlowSol, in_file_num);
+    w << "ZONE N = " << n_eles * P.n_points << ", E = " << n_eles * P.n_cells << ", DATAPACKING = POINT, ZONETYPE = " << zonetype[e->get_ele_type()] << endl;
+    if (!time_written)
+    {
+      w << "SolutionTime=" << num{FlowSol->time} << endl;
+      time_written = true;
+    }
+    for (int j = 0; j < n_eles; j++)
+    {
+      P.eval(j);
+      for (int k = 0; k < P.n_points; k++)
+      {
+        for (int l = 0; l < n_dims; l++) w << num{P.pos(k, l)} << " ";
+        for (int l = 0; l < P.n_fields; l++)
+        {
+          if (std::isnan(P.u(k, l))) FatalError("Nan in tecplot file, exiting");
+          w << num{P.u(k, l)} << " ";
+        }
+        for (int l = 0; l < n_average_fields; l++)
+        {
+          if (std::isnan(P.avg(k, l))) FatalError("Nan in tecplot file, exiting");
+          w << num{P.avg(k, l)} << " ";
+        }
+        for (int l = 0; l < n_diag_fields; l++) w << num{P.diag(k, l)} << " ";
+        w << endl;
+      }
+    }
+    for (int j = 0; j < n_eles; j++)
+      for (int k = 0; k < P.n_cells; k++)
+      {
+        for (int l = 0; l < P.n_verts; l++)
+        {
+          w << P.T.con[(size_t)k * P.n_verts + l] + j * P.n_points + 1;
+          if (l != P.n_verts - 1) w << " ";
+        }
+        w << endl;
+      }
+  }
+  w.close();
+  if (FlowSol->rank == 0) cout << "done." << endl;
+}
+
+void write_plot(int in_file_num, struct solution *FlowSol)
+{
+  if (run_input.write_type == 0) write_vtu(in_file_num, FlowSol);
+  else if (run_input.write_type == 1) write_tec(in_file_num, FlowSol);
+  else FatalError("ERROR: Trying to write unrecognized file format ... ");
 }
