@@ -192,6 +192,7 @@ void input::read_input_file(const string &fileName, int rank)
   opts.getScalarValue("p_res", p_res, 2);
   opts.getScalarValue("write_type", write_type, 0);
   opts.getScalarValue("probe", probe, 0);
+  if (probe) FatalError("probes (probe_input.cpp) are not built in this host mirror");
   opts.getVectorValueOptional("integral_quantities", integral_quantities);
   opts.getVectorValueOptional("diagnostic_fields", diagnostic_fields);
   opts.getVectorValueOptional("average_fields", average_fields);
@@ -356,6 +357,7 @@ void input::read_input_file(const string &fileName, int rank)
   }
 
   opts.getScalarValue("body_forcing", forcing, 0);
+  if (forcing) FatalError("body forcing (eles::evaluate_body_force, periodic channel / hill) is not built in this host mirror");
   opts.getScalarValue("perturb_ic", perturb_ic, 0);
   if (ic_form == 6)
   {
