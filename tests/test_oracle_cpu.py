@@ -75,3 +75,15 @@ def test_ldg_switch_is_antisymmetric():
     keep = ~((n[:, 0] == 0) & (n[:, 0] + n[:, 1] == 0) & (n[:, 0] + n[:, 2] == 0))
     a, b = ho.ldg_switched_beta(0.5, n[keep]), ho.ldg_switched_beta(0.5, -n[keep])
     assert np.all(a == -b)
+
+
+@pytest.mark.parametrize("name", ["hex2_p3_ns_rusanov_rk45", "hex3_p2_ns_hllc_rk34", "hex3_p1_ns_roem_sutherland_rk24"])
+def test_face_gradient_formulation_prototype(name):
+    """tools/face_gradient_proto.py: the planned k_grad formulation (normal face gradient from the line in registers,
+    tangential ones as in-face derivatives of the face values + edge corrections) reproduces the reference's gradient at the
+    flux points (dense operators and golden dump) -- the math behind the next kernel generation, pinned on the CPU."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("face_gradient_proto", os.path.join(util.ROOT, "tools", "face_gradient_proto.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    assert mod.main(os.path.join(util.ROOT, "tests", "golden", name + ".npz")) == 0
