@@ -873,7 +873,21 @@ int hf_fused_stage(hf_ctx *c, int rk_stage, double time, int keep_residual, int 
 int hf_fused_after_nccl(hf_ctx *c)
 {
   hf_fused_state *Z = c->fz;
-  if (!Z || !Z->available || !c->prm.viscous || c->nproc < 2) return 0;
+  if (c->nproc < 2) return 0;
+  // the fused kernels exchange other halo data than the staged ones: either every rank uses them or none does (a rank
+  // whose part of the mesh has boundary faces, say, cannot)
+  double all_available = (Z && Z->available) ? 1.0 : 0.0;
+  if (hf_halo_allreduce_min(c, &all_available)) return 1;
+  if (all_available != 1.0)
+  {
+    if (Z && Z->available)
+    {
+      Z->available = false;
+      Z->why = "another rank cannot use the fused kernels on its part of the mesh";
+    }
+    return 0;
+  }
+  if (!c->prm.viscous) return 0;
   hf_mpi_inters_dev &M = c->mpis[2];
   const int N = Z->order + 1, NN = N * N, nm = Z->n_mpi;
   const unsigned long long full = NN == 64 ? ~0ull : ((1ull << NN) - 1ull);
