@@ -123,6 +123,8 @@ struct fused_args
   double tD[36];          // D[i*N+j] = d l_j / dxi at xi_i
   double tL[2][6];        // [0]: l_i(-1), [1]: l_i(+1)
   double tc3[36], tc5[36]; // opp_3 / opp_5 entry of face f at directional index m: [f*N+m]
+  double tLD[2][6];       // generation 8: (l(s) . D)[j], the face-normal derivative of a line's face value
+  double tLc[6][2];       // generation 8: l(s) . c5[f]
   const int *nidx;        // [ele][NFP] index into fu (field 0) of the neighbour's value facing each own flux point
   hf_phys P;
   rk_args rk;
@@ -679,6 +681,18 @@ int launch_all(hf_ctx *c, hf_fused_state *Z, fused_args &A, int what, int lo, in
     k_grad6<N, E, NT, MINB><<<grid, NT, smem_g, c->stream>>>(A);
   else if (what == 3)
     k_grad7<N, E, NT, MINB><<<grid, NT, sizeof(smem7<N, E>), c->stream>>>(A);
+  else if (what == 5)
+  {
+    // experimental generation-8 gradient kernel (HF_FUSED_GRAD8=1): not validated on a GPU yet
+    static bool attr8 = false;
+    if (!attr8)
+    {
+      HF_CUDA(cudaFuncSetAttribute(k_grad8<N, E, NT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(smem8<N, E>)));
+      HF_CUDA(cudaFuncSetAttribute(k_grad8<N, E, NT, MINB>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+      attr8 = true;
+    }
+    k_grad8<N, E, NT, MINB><<<grid, NT, sizeof(smem8<N, E>), c->stream>>>(A);
+  }
   else if (what == 4)
   {
     hf_ktimer_begin(c);
@@ -715,11 +729,11 @@ int launch(hf_ctx *c, hf_fused_state *Z, fused_args &A, int what, int lo, int hi
     static const int cfg_all = getenv("HF_FUSED_CFG") ? atoi(getenv("HF_FUSED_CFG")) : 0;
     static const int cfg_g = getenv("HF_FUSED_CFG_G") ? atoi(getenv("HF_FUSED_CFG_G")) : cfg_all;
     static const int cfg_r = getenv("HF_FUSED_CFG_R") ? atoi(getenv("HF_FUSED_CFG_R")) : cfg_all;
-    int cfg = (what == 1 || what == 3) ? cfg_g : ((what == 2 || what == 4) ? cfg_r : cfg_all);
+    int cfg = (what == 1 || what == 3 || what == 5) ? cfg_g : ((what == 2 || what == 4) ? cfg_r : cfg_all);
     // measured on B200 (64^3): both generation-7 kernels are fastest with one element per CTA and six CTAs per SM (80
     // registers; k_grad7 is within 2 % of that for every shape tried, profiles/ncu_r01_summary.md)
     if (what == 4 && !getenv("HF_FUSED_CFG_R") && !getenv("HF_FUSED_CFG")) cfg = 3;
-    if (what == 3 && !getenv("HF_FUSED_CFG_G") && !getenv("HF_FUSED_CFG")) cfg = 3;
+    if ((what == 3 || what == 5) && !getenv("HF_FUSED_CFG_G") && !getenv("HF_FUSED_CFG")) cfg = 3;
     if (cfg == 1) return launch_all<5, 1, 125, 4>(c, Z, A, what, lo, hi);
     if (cfg == 2) return launch_all<5, 1, 125, 5>(c, Z, A, what, lo, hi);
     if (cfg == 3) return launch_all<5, 1, 125, 6>(c, Z, A, what, lo, hi);
@@ -754,6 +768,24 @@ void base_args(hf_ctx *c, hf_fused_state *Z, fused_args &A)
   A.dt_local = (c->prm.dt_type == 2) ? e.dt_local : nullptr;
   for (int i = 0; i < 36; i++) { A.tD[i] = Z->T.D[i]; A.tc3[i] = Z->T.c3[i]; A.tc5[i] = Z->T.c5[i]; }
   for (int i = 0; i < 6; i++) { A.tL[0][i] = Z->T.Lm[i]; A.tL[1][i] = Z->T.Lp[i]; }
+  {
+    const int N = Z->order + 1;
+    for (int s2 = 0; s2 < 2; s2++)
+    {
+      for (int j = 0; j < N; j++)
+      {
+        double a = 0.;
+        for (int i = 0; i < N; i++) a += A.tL[s2][i] * A.tD[i * N + j];
+        A.tLD[s2][j] = a;
+      }
+      for (int f = 0; f < 6; f++)
+      {
+        double a = 0.;
+        for (int i = 0; i < N; i++) a += A.tL[s2][i] * A.tc5[f * N + i];
+        A.tLc[f][s2] = a;
+      }
+    }
+  }
   A.P = c->phys;
   A.viscous = c->prm.viscous;
   static const int pf = getenv("HF_FUSED_PF") ? atoi(getenv("HF_FUSED_PF")) : 0; // measured: no effect on B200 (the other resident CTAs already cover the staging latency)
@@ -841,7 +873,8 @@ int hf_fused_stage(hf_ctx *c, int rk_stage, double time, int keep_residual, int 
   const int ni = Z->n_interior, n = Z->n_eles;
   static const bool no_overlap = getenv("HF_NO_OVERLAP") != nullptr; // measurement aid: serialise exchange and compute
   if (no_overlap && exchange_wait(c)) return 1;
-  const int kg = Z->os ? 3 : 1, kr = Z->os ? 4 : 2;
+  static const bool grad8 = getenv("HF_FUSED_GRAD8") != nullptr; // experimental generation-8 gradient kernel, see hf_fused_kernels.cuh
+  const int kg = Z->os ? (grad8 ? 5 : 3) : 1, kr = Z->os ? 4 : 2;
   if (p.viscous)
   {
     if (launch(c, Z, A, kg, 0, ni)) return 1;

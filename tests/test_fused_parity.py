@@ -129,3 +129,13 @@ def test_warped_mesh_falls_back_to_staged(tmp_path, hb, meshgen):
         run.run(1, fused=True)  # must silently use the staged kernels, not fail and not use the fused ones
         if ref is not None:
             check("final disu_upts", run.download("hex", "disu_upts"), ref["final.hex.disu_upts"], 1e-14)
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not os.environ.get("HF_TEST_GRAD8"), reason="experimental generation-8 gradient kernel: opt-in (HF_TEST_GRAD8=1) until it is validated")
+def test_experimental_grad8_matches_generation7():
+    """k_grad8 (face gradients without volume gradient planes, hf_fused_kernels.cuh) against k_grad7 on small cases"""
+    import subprocess
+    import sys
+    r = subprocess.run([sys.executable, os.path.join(util.ROOT, "tools", "grad8_check.py")], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
