@@ -733,7 +733,8 @@ int launch(hf_ctx *c, hf_fused_state *Z, fused_args &A, int what, int lo, int hi
     // measured on B200 (64^3): both generation-7 kernels are fastest with one element per CTA and six CTAs per SM (80
     // registers; k_grad7 is within 2 % of that for every shape tried, profiles/ncu_r01_summary.md)
     if (what == 4 && !getenv("HF_FUSED_CFG_R") && !getenv("HF_FUSED_CFG")) cfg = 3;
-    if ((what == 3 || what == 5) && !getenv("HF_FUSED_CFG_G") && !getenv("HF_FUSED_CFG")) cfg = 3;
+    if (what == 3 && !getenv("HF_FUSED_CFG_G") && !getenv("HF_FUSED_CFG")) cfg = 3;
+    if (what == 5 && !getenv("HF_FUSED_CFG_G") && !getenv("HF_FUSED_CFG")) cfg = 2; // 41 kB per element: five CTAs per SM fit (untuned)
     if (cfg == 1) return launch_all<5, 1, 125, 4>(c, Z, A, what, lo, hi);
     if (cfg == 2) return launch_all<5, 1, 125, 5>(c, Z, A, what, lo, hi);
     if (cfg == 3) return launch_all<5, 1, 125, 6>(c, Z, A, what, lo, hi);
