@@ -1112,13 +1112,15 @@ __device__ __forceinline__ void pass_E8(SM &S, const fused_args &A, int ne)
   constexpr int NN = N * N, NFP = 6 * NN;
   for (int w = threadIdx.x; w < ne * 6 * 2 * 2 * N * NF; w += NT)
   {
+    // task order (edge point, side, slot, field) inside a face, faces outermost: the 20 N tasks of a face are consecutive, so
+    // the warps of a face without owned flux points skip it as a whole
     int r = w;
     const int m = r % N; r /= N;
     const int side = r % 2; r /= 2;
     const int slot = r % 2; r /= 2;
-    const int F = r % 6; r /= 6;
-    const int k = r % NF;
-    const int e = r / NF;
+    const int k = r % NF; r /= NF;
+    const int F = r % 6;
+    const int e = r / 6;
     if (S.own[e][F] == 0ull) continue;
     const int n = face_dir(F), t = tan_dir(n, slot), o = tan_dir(n, 1 - slot);
     const int ft = side ? dir_plus_face(t) : dir_minus_face(t);
@@ -1146,9 +1148,9 @@ __device__ __forceinline__ void pass_T8(SM &S, const fused_args &A, int ne)
     int r = w;
     const int m = r % N; r /= N;
     const int slot = r % 2; r /= 2;
-    const int F = r % 6; r /= 6;
-    const int k = r % NF;
-    const int e = r / NF;
+    const int k = r % NF; r /= NF;
+    const int F = r % 6;
+    const int e = r / 6;
     if (S.own[e][F] == 0ull) continue;
     const int n = face_dir(F), t = tan_dir(n, slot), o = tan_dir(n, 1 - slot);
     const int ftm = dir_minus_face(t), ftp = dir_plus_face(t);
