@@ -1028,7 +1028,8 @@ __global__ void __launch_bounds__(NT, MINB) k_resid7(const __grid_constant__ fus
 // =====================================================================================================================
 // Generation 8 of the gradient kernel (EXPERIMENTAL: written at the end of round 1 with the GPU budget all but spent; one GPU
 // run: it reproduces k_grad7 to 1e-17 after two steps on P = 1, 2, 4 cases (profiles/grad8_vs_grad7_r01.txt), but it has not been
-// timed or profiled yet and is only reachable with HF_FUSED_GRAD8=1).  Same contract as k_grad7 (one-sided
+// timed or profiled yet and is only reachable with HF_FUSED_GRAD8=1; the task order of pass_E8 / pass_T8 was permuted after
+// that run -- which thread does which task, not what is computed -- and has not run on a GPU since).  Same contract as k_grad7 (one-sided
 // LDG: the common normal flux fc at the owned flux points), without the 15 volume gradient planes: the reference-space
 // gradient at a flux point of a face normal to direction n is
 //   normal      G_n = (l.D).u(line) + (l.c5[n+]) delta_{n+} + (l.c5[n-]) delta_{n-}        -- from the line a thread of the
