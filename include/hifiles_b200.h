@@ -238,8 +238,10 @@ int hf_dev_residual_norm(hf_ctx *ctx, int norm_type, double *out);
  * whenever they keep the residual.  kinds: 0 kineticenergy, 1 enstropy, 2 pressuredilatation, 3 straincolonproduct,
  * 4 devstraincolonproduct.  out[n_quantities] is ADDED to (one call per element type); local to this rank. */
 #define HF_MAX_INTEGRAL_QUANTITIES 8
-/* on != 0: stages that keep the residual also leave grad_disu_upts behind in fused mode (the staged kernels always do):
- * surface forces and the vorticity-type plot fields read it like the integral diagnostics.  Set by hf_dev_set_volume_cubature too. */
+/* on != 0: stages that keep the residual also leave grad_disu_upts behind in fused mode (the staged kernels always do), as
+ * the reference's arrays hold it after the last CalcResidual of a step (output::CopyGPUCPU -> cp_grad_disu_upts_gpu_cpu,
+ * reference src/output.cpp:2535-2556): surface forces (src/eles.cpp:5772-5785) and the vorticity-type plot fields
+ * (src/eles.cpp:3781-3817) read it like the integral diagnostics.  Set by hf_dev_set_volume_cubature too. */
 int hf_dev_set_keep_gradient(hf_ctx *ctx, int on);
 /* Running time averages at the solution points = eles::CalcTimeAverageQuantities (reference src/eles.cpp:5630-5702), called once
  * per time step: average <- a * average + b * current with a = (time - spinup - dt) / (time - spinup), b = dt / (time - spinup)

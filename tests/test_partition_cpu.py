@@ -113,3 +113,28 @@ def test_halo_pairing_rules(tmp_path, hb, meshgen, world, part_kind):
                 assert d.max() < 1e-9, "flux points of a shared face do not coincide (ranks %d/%d, face %d)" % (a["rank"], b_rank, k)
                 total += 1
     assert total > 0
+
+
+@pytest.mark.parametrize("kind,n,world", [("pritet", (2, 4, 2), 2), ("hexpri", (2, 2, 4), 3), ("mixed2d", 6, 4)])
+def test_metis_partition_of_mixed_meshes(tmp_path, hb, meshgen, kind, n, world):
+    """The k-way partitioner on meshes of several element types (corner vertices of triangles, quadrilaterals, tetrahedra,
+    prisms, hexahedra in the dual graph): every rank computes the same vector, every cell lands on exactly one rank, the
+    parts are balanced.  Ranks are built one after the other in this process (host only)."""
+    mesh = str(tmp_path / "m.neu")
+    extra = {}
+    if kind == "mixed2d":
+        info = meshgen.mixed_box_2d(mesh, n, kind="mixed", lengths=(6.2831853071795862,) * 2, origin=(0., 0.))
+        extra = dict(dz_cyclic=None)
+    else:
+        info = meshgen.mixed_box_3d(mesh, n, kind=kind)
+    n_cells = len(info["centroids"])
+    inp = meshgen.write_input(str(tmp_path / "input"), "m.neu", order=1, adv_type=2, dt=1e-5, riemann_solve_type=0, viscous=1, **extra)
+    owned = []
+    for rank in range(world):
+        with hb.Run(inp, rank=rank, nproc=world, part=None, host_only=True) as run:
+            mine = np.concatenate([run.host_array(t + ".ele2global_ele") for t in run.ele_types()])
+            owned.append(mine)
+    allc = np.concatenate(owned)
+    assert sorted(allc.tolist()) == list(range(n_cells))
+    sizes = [len(o) for o in owned]
+    assert min(sizes) > 0 and max(sizes) <= 1.25 * n_cells / world, sizes
