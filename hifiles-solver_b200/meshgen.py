@@ -180,6 +180,63 @@ def slab_partition(centroids, nproc, axis=0):
     return part
 
 
+def quad8_box(path, n, lengths=(20., 20.), bcs=None, origin=(-10., -10.), curve=0.0):
+    """n = N or (Nx,Ny) eight-node (serendipity) quadrilaterals: `id 2 8 c0 m01 c1 m12 c2 m23 c3 m30`, corners and mid-edge
+    nodes alternating counter-clockwise as Gambit writes them (mesh_reader.cpp:199-206 maps them to corners 0-3, mid-edge
+    nodes 4-7).  curve > 0 bows the interior edges: mid-edge nodes displaced normal to their edge."""
+    if np.isscalar(n):
+        n = (n, n)
+    nx, ny = n
+    if bcs is None:
+        bcs = {s: "Cyclic" for s in ("x-", "x+", "y-", "y+")}
+    px, py = 2 * nx + 1, 2 * ny + 1
+    gi, gj = np.meshgrid(np.arange(px), np.arange(py), indexing="ij")
+    used = ~((gi % 2 == 1) & (gj % 2 == 1))
+    x = origin[0] + lengths[0] * gi / (2. * nx)
+    y = origin[1] + lengths[1] * gj / (2. * ny)
+    if curve:
+        interior = (gi > 0) & (gi < px - 1) & (gj > 0) & (gj < py - 1)
+        on_x_edge = (gi % 2 == 1) & (gj % 2 == 0) & interior   # mid node of an edge along x: move in y
+        on_y_edge = (gi % 2 == 0) & (gj % 2 == 1) & interior
+        y = y + np.where(on_x_edge, curve * lengths[1] / ny * np.sin(1.3 * gi + 0.4 * gj), 0.)
+        x = x + np.where(on_y_edge, curve * lengths[0] / nx * np.cos(0.7 * gi + 1.1 * gj), 0.)
+    nid = np.zeros((px, py), dtype=np.int64)
+    order = np.argsort((gi + px * gj)[used])
+    ids = np.empty(order.size, dtype=np.int64)
+    ids[order] = 1 + np.arange(order.size)
+    nid[used] = ids
+    sel = np.argsort(nid[used])
+    nodes = np.column_stack([nid[used][sel], x[used][sel], y[used][sel]])
+    cx, cy = np.meshgrid(np.arange(nx), np.arange(ny), indexing="ij")
+    cid = 1 + cx + nx * cy
+    at = lambda di, dj: nid[2 * cx + di, 2 * cy + dj]
+    conn = np.stack([cid, np.full_like(cid, 2), np.full_like(cid, 8), at(0, 0), at(1, 0), at(2, 0), at(2, 1), at(2, 2), at(1, 2), at(0, 2), at(0, 1)],
+                    axis=-1).reshape(-1, 11)
+    conn = conn[np.argsort(conn[:, 0])]
+    side_faces = {"y-": (cid[:, 0], 1), "x+": (cid[nx - 1, :], 2), "y+": (cid[:, ny - 1], 3), "x-": (cid[0, :], 4)}
+    groups = {}
+    for side, name in bcs.items():
+        cells, k = side_faces[side]
+        rows = np.column_stack([np.sort(cells.ravel()), np.full(cells.size, 2), np.full(cells.size, k)])
+        groups.setdefault(name, []).append(rows)
+    with open(path, "w") as f:
+        f.write(_header(os.path.basename(path), nodes.shape[0], conn.shape[0], len(groups), 2))
+        f.write("   NODAL COORDINATES 2.3.16\n")
+        _write_rows(f, nodes, "%10d %19.16e %19.16e")
+        f.write("ENDOFSECTION\n      ELEMENTS/CELLS 2.3.16\n")
+        buf = io.StringIO()
+        np.savetxt(buf, conn, fmt="%8d %2d %2d %8d%8d%8d%8d%8d%8d%8d\n               %8d")
+        f.write(buf.getvalue())
+        f.write("ENDOFSECTION\n")
+        _group(f, conn.shape[0])
+        for name, parts in groups.items():
+            rows = np.concatenate(parts)
+            f.write(" BOUNDARY CONDITIONS 2.3.16\n%32s%8d%8d%8d%8d\n" % (name, 1, rows.shape[0], 0, 6))
+            _write_rows(f, rows, "%10d%5d%5d")
+            f.write("ENDOFSECTION\n")
+    return dict(n_cells=conn.shape[0], n_nodes=nodes.shape[0])
+
+
 def mixed_box_2d(path, n, lengths=(20., 20.), bcs=None, origin=(-10., -10.), kind="tri", warp=0.0, curve=0.0):
     """Nx x Ny cells on a rectangle.  kind: 'tri' (every cell split into two triangles along its (0,0)-(1,1) diagonal),
     'quad', or 'mixed' (quads in the left half, triangles in the right half: BASELINE config 2's element mix).

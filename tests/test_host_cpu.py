@@ -147,3 +147,27 @@ def test_shipped_cases_set_up_bit_identically(tmp_path, hb, monkeypatch, name):
             assert np.array_equal(a, v), "%s differs from the reference (max abs %.3e)" % (k, np.abs(a.astype(float) - v).max())
             checked += 1
     assert checked >= 30
+
+
+def test_eight_node_quadrilaterals_set_up_bit_identically(tmp_path, hb, meshgen):
+    """Curved serendipity quadrilaterals (reference src/eles_quads.cpp eval_nodal_s_basis n_spts == 8, the Gambit node
+    order of src/mesh_reader.cpp:199-206): shape functions, curved metrics, operators and initial condition against the
+    unmodified reference, bit for bit."""
+    if not util.have_reference():
+        pytest.skip("oracle/_ref not built")
+    two_pi = 6.2831853071795862
+    meshgen.quad8_box(str(tmp_path / "m.neu"), 4, lengths=(two_pi, two_pi), origin=(0., 0.), curve=0.05)
+    inp = meshgen.write_input(str(tmp_path / "input"), "m.neu", order=2, adv_type=2, dt=1e-5, riemann_solve_type=0, viscous=1, dz_cyclic=None)
+    ref = util.run_reference(inp, 0, stagewise=False)
+    assert ref["quad.detjac_upts"].max() - ref["quad.detjac_upts"].min() > 0.05   # the elements are really curved
+    skip = ("step", "final", "history", "mesh", "meta", "params", "rk_", "case")
+    checked = 0
+    with hb.Run(inp, host_only=True) as run:
+        for k, v in ref.items():
+            if k.startswith(skip) or k.endswith(("tdA_idx_l", "tdA_idx_r", "norm_idx", "bc_flags")):
+                continue
+            a = run.host_array(k.replace("disu_upts_ic", "disu_upts"))
+            assert a.shape == v.shape, k
+            assert np.array_equal(a, v), "%s differs from the reference (max abs %.3e)" % (k, np.abs(a.astype(float) - v).max())
+            checked += 1
+    assert checked >= 30
