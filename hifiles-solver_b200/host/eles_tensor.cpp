@@ -114,10 +114,73 @@ double eles_hexas::eval_d_nodal_basis(int in_index, int in_cpnt, hf_array<double
   return eval_lagrange(in_loc(0), k, loc_1d_upts) * eval_lagrange(in_loc(1), j, loc_1d_upts) * eval_d_lagrange(in_loc(2), i, loc_1d_upts);
 }
 
+// 20-node serendipity hexahedron (reference src/eles_hexas.cpp:1215-1257, 1292-1356).  Node p sits at (px,py,pz): the eight
+// corners counter-clockwise bottom then top, then the mid-edge nodes of the bottom ring, the vertical edges and the top ring.
+//   corner:    N = px py pz / 8 (x+px)(y+py)(z+pz) (px x + py y + pz z - 2)
+//   mid-edge:  N = -pu pv / 4 (u+pu)(v+pv)(w^2-1),  w the edge direction, u < v the other two
+// Every product and sum below is associated as the reference writes it (overall signs are exact in floating point, so only
+// the order of the magnitudes matters): the metrics of curved hexes are bit-identical to the reference's.
+static const int hex20_pos[20][3] = {
+    {-1, -1, -1}, {1, -1, -1}, {1, 1, -1}, {-1, 1, -1}, {-1, -1, 1}, {1, -1, 1}, {1, 1, 1}, {-1, 1, 1},
+    {0, -1, -1}, {1, 0, -1}, {0, 1, -1}, {-1, 0, -1},
+    {-1, -1, 0}, {1, -1, 0}, {1, 1, 0}, {-1, 1, 0},
+    {0, -1, 1}, {1, 0, 1}, {0, 1, 1}, {-1, 0, 1}};
+
+static inline void hex20_edge_axes(const int *p, int &u, int &v, int &w)
+{
+  w = p[0] == 0 ? 0 : p[1] == 0 ? 1 : 2;
+  u = w == 0 ? 1 : 0;
+  v = w == 2 ? 1 : 2;
+}
+
+static double hex20_basis(int m, const double *x)
+{
+  const int *p = hex20_pos[m];
+  if (m < 8)
+  {
+    double f4 = ((p[0] * x[0] - 2.) + p[1] * x[1]) + p[2] * x[2];
+    return (p[0] * p[1] * p[2]) * (0.125 * (x[0] + p[0])) * (x[1] + p[1]) * (x[2] + p[2]) * f4;
+  }
+  int u, v, w;
+  hex20_edge_axes(p, u, v, w);
+  return (-p[u] * p[v]) * (0.25 * (x[u] + p[u])) * (x[v] + p[v]) * (x[w] * x[w] - 1.);
+}
+
+static void hex20_d_basis(int m, const double *x, double *d)
+{
+  const int *p = hex20_pos[m];
+  if (m < 8)
+  {
+    double sgn = p[0] * p[1] * p[2];
+    for (int c = 0; c < 3; c++)
+    {
+      int a = c == 0 ? 1 : 0, b = c == 2 ? 1 : 2; // the two other directions
+      double t = p[a] * x[a] + p[b] * x[b];
+      // the reference adds the constant before the doubled term in three entries (src/eles_hexas.cpp:1301, 1322, 1323)
+      bool const_first = (c == 0 && m == 7) || (c == 1 && (m == 6 || m == 7));
+      double sum = const_first ? (t - 1.) + 2. * p[c] * x[c] : (t + 2. * p[c] * x[c]) - 1.;
+      d[c] = sgn * (0.125 * (x[b] + p[b])) * (x[a] + p[a]) * sum;
+    }
+    return;
+  }
+  int u, v, w;
+  hex20_edge_axes(p, u, v, w);
+  double c4 = -p[u] * p[v];
+  int first = w == 2 ? 0 : 2, second = w == 0 ? 1 : w == 1 ? 0 : 1; // order of the two linear factors behind (1/2) w
+  d[w] = c4 * 0.5 * x[w] * (x[first] + p[first]) * (x[second] + p[second]);
+  d[u] = c4 * (0.25 * (x[v] + p[v])) * (x[w] * x[w] - 1.);
+  d[v] = c4 * (0.25 * (x[u] + p[u])) * (x[w] * x[w] - 1.);
+}
+
 double eles_hexas::eval_nodal_s_basis(int in_index, hf_array<double> &in_loc, int in_n_spts)
 {
+  if (in_n_spts == 20)
+  {
+    double x[3] = {in_loc(0), in_loc(1), in_loc(2)};
+    return hex20_basis(in_index, x);
+  }
   if (!is_perfect_cube(in_n_spts))
-    FatalError("Shape basis not implemented yet, exiting"); // 20-node serendipity hexes: not built yet
+    FatalError("Shape basis not implemented yet, exiting");
   int n = (int)round(pow(in_n_spts, 1. / 3.));
   hf_array<double> l(n);
   set_loc_1d_spts(l, n);
@@ -129,6 +192,16 @@ double eles_hexas::eval_nodal_s_basis(int in_index, hf_array<double> &in_loc, in
 
 void eles_hexas::eval_d_nodal_s_basis(hf_array<double> &d, hf_array<double> &in_loc, int in_n_spts)
 {
+  if (in_n_spts == 20)
+  {
+    double x[3] = {in_loc(0), in_loc(1), in_loc(2)}, g[3];
+    for (int m = 0; m < 20; m++)
+    {
+      hex20_d_basis(m, x, g);
+      for (int c = 0; c < 3; c++) d(m, c) = g[c];
+    }
+    return;
+  }
   if (!is_perfect_cube(in_n_spts))
     FatalError("Shape basis not implemented yet, exiting");
   int n = (int)round(pow(in_n_spts, 1. / 3.));

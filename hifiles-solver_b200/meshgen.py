@@ -237,6 +237,70 @@ def quad8_box(path, n, lengths=(20., 20.), bcs=None, origin=(-10., -10.), curve=
     return dict(n_cells=conn.shape[0], n_nodes=nodes.shape[0])
 
 
+def hex20_box(path, n, lengths=(2 * np.pi,) * 3, bcs=None, origin=(0., 0., 0.), warp=0.0):
+    """n = N or (Nx,Ny,Nz) twenty-node (serendipity) hexahedra: `id 4 20 ...` with the nodes in Gambit's order, the 3x3x3
+    lattice of the cell without face and body centres, x slowest, then z, y fastest (mesh_reader.cpp:242-243 sends them to
+    corners 0-7 and mid-edge nodes 8-19).  warp > 0 displaces all interior nodes smoothly, so edges become parabolas."""
+    if np.isscalar(n):
+        n = (n, n, n)
+    nx, ny, nz = n
+    if bcs is None:
+        bcs = {s: "Cyclic" for s in ("x-", "x+", "y-", "y+", "z-", "z+")}
+    px, py, pz = 2 * nx + 1, 2 * ny + 1, 2 * nz + 1
+    gx, gy, gz = np.meshgrid(np.arange(px), np.arange(py), np.arange(pz), indexing="ij")
+    used = ((gx % 2) + (gy % 2) + (gz % 2)) <= 1
+    x = origin[0] + lengths[0] * gx / (2. * nx)
+    y = origin[1] + lengths[1] * gy / (2. * ny)
+    z = origin[2] + lengths[2] * gz / (2. * nz)
+    if warp:
+        bump = warp * np.sin(np.pi * gx / (2. * nx)) * np.sin(np.pi * gy / (2. * ny)) * np.sin(np.pi * gz / (2. * nz))
+        x = x + bump * lengths[0] / nx * np.sin(np.pi * gy / ny + 0.3)
+        y = y + bump * lengths[1] / ny * np.sin(np.pi * gz / nz + 0.7)
+        z = z + bump * lengths[2] / nz * np.sin(np.pi * gx / nx + 1.1)
+    nid = np.zeros((px, py, pz), dtype=np.int64)
+    key = (gx + px * (gy + py * gz))[used]
+    ids = np.empty(key.size, dtype=np.int64)
+    ids[np.argsort(key)] = 1 + np.arange(key.size)
+    nid[used] = ids
+    sel = np.argsort(ids)
+    nodes = np.column_stack([ids[sel], x[used][sel], y[used][sel], z[used][sel]])
+    cx, cy, cz = np.meshgrid(np.arange(nx), np.arange(ny), np.arange(nz), indexing="ij")
+    cid = 1 + cx + nx * (cy + ny * cz)
+    cols = [cid, np.full_like(cid, 4), np.full_like(cid, 20)]
+    for di in range(3):
+        for dk in range(3):
+            for dj in range(3):
+                if (di % 2) + (dj % 2) + (dk % 2) <= 1:
+                    cols.append(nid[2 * cx + di, 2 * cy + dj, 2 * cz + dk])
+    conn = np.stack(cols, axis=-1).reshape(-1, 23)
+    conn = conn[np.argsort(conn[:, 0])]
+    side_faces = {
+        "z-": (cid[:, :, 0], 1), "y+": (cid[:, ny - 1, :], 2), "z+": (cid[:, :, nz - 1], 3),
+        "y-": (cid[:, 0, :], 4), "x-": (cid[0, :, :], 5), "x+": (cid[nx - 1, :, :], 6)}
+    groups = {}
+    for side, name in bcs.items():
+        cells, k = side_faces[side]
+        rows = np.column_stack([np.sort(cells.ravel()), np.full(cells.size, 4), np.full(cells.size, k)])
+        groups.setdefault(name, []).append(rows)
+    with open(path, "w") as f:
+        f.write(_header(os.path.basename(path), nodes.shape[0], conn.shape[0], len(groups), 3))
+        f.write("   NODAL COORDINATES 2.3.16\n")
+        _write_rows(f, nodes, "%10d %19.16e %19.16e %19.16e")
+        f.write("ENDOFSECTION\n      ELEMENTS/CELLS 2.3.16\n")
+        buf = io.StringIO()
+        pad = "\n               "
+        np.savetxt(buf, conn, fmt="%8d %2d %2d " + "%8d" * 7 + pad + "%8d" * 7 + pad + "%8d" * 6)
+        f.write(buf.getvalue())
+        f.write("ENDOFSECTION\n")
+        _group(f, conn.shape[0])
+        for name, parts in groups.items():
+            rows = np.concatenate(parts)
+            f.write(" BOUNDARY CONDITIONS 2.3.16\n%32s%8d%8d%8d%8d\n" % (name, 1, rows.shape[0], 0, 6))
+            _write_rows(f, rows, "%10d%5d%5d")
+            f.write("ENDOFSECTION\n")
+    return dict(n_cells=conn.shape[0], n_nodes=nodes.shape[0])
+
+
 def mixed_box_2d(path, n, lengths=(20., 20.), bcs=None, origin=(-10., -10.), kind="tri", warp=0.0, curve=0.0):
     """Nx x Ny cells on a rectangle.  kind: 'tri' (every cell split into two triangles along its (0,0)-(1,1) diagonal),
     'quad', or 'mixed' (quads in the left half, triangles in the right half: BASELINE config 2's element mix).

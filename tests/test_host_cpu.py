@@ -171,3 +171,26 @@ def test_eight_node_quadrilaterals_set_up_bit_identically(tmp_path, hb, meshgen)
             assert np.array_equal(a, v), "%s differs from the reference (max abs %.3e)" % (k, np.abs(a.astype(float) - v).max())
             checked += 1
     assert checked >= 30
+
+
+def test_twenty_node_hexahedra_set_up_bit_identically(tmp_path, hb, meshgen):
+    """Curved serendipity hexahedra (reference src/eles_hexas.cpp:1215-1257 shape functions, 1292-1356 their derivatives,
+    node order of src/mesh_reader.cpp:242-243, face corners of src/mesh.cpp:575-620): metrics, operators, connectivity and
+    initial condition against the unmodified reference, bit for bit."""
+    if not util.have_reference():
+        pytest.skip("oracle/_ref not built")
+    meshgen.hex20_box(str(tmp_path / "m.neu"), 3, warp=0.15)
+    inp = meshgen.write_input(str(tmp_path / "input"), "m.neu", order=2, adv_type=2, dt=1e-5, riemann_solve_type=0, viscous=1)
+    ref = util.run_reference(inp, 0, stagewise=False)
+    assert ref["hex.detjac_upts"].max() - ref["hex.detjac_upts"].min() > 0.2   # the elements are really curved
+    skip = ("step", "final", "history", "mesh", "meta", "params", "rk_", "case")
+    checked = 0
+    with hb.Run(inp, host_only=True) as run:
+        for k, v in ref.items():
+            if k.startswith(skip) or k.endswith(("tdA_idx_l", "tdA_idx_r", "norm_idx", "bc_flags")):
+                continue
+            a = run.host_array(k.replace("disu_upts_ic", "disu_upts"))
+            assert a.shape == v.shape, k
+            assert np.array_equal(a, v), "%s differs from the reference (max abs %.3e)" % (k, np.abs(a.astype(float) - v).max())
+            checked += 1
+    assert checked >= 30
