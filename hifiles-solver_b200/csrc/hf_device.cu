@@ -1445,6 +1445,14 @@ int hf_dev_upload_int_inters(hf_ctx *c, const hf_int_inters_desc *d)
 int hf_dev_set_bc_table(hf_ctx *c, int n_bc, const hf_bc *table)
 {
   HF_CUDA(cudaSetDevice(c->device));
+  if (n_bc > 0 && c->bc_table && n_bc == c->n_bc)
+  {
+    // a changed table of the same size (ramped inlet): in place, behind the kernels already queued on the stream
+    c->h_bc.assign(table, table + n_bc);
+    HF_CUDA(cudaMemcpyAsync(c->bc_table, c->h_bc.data(), (size_t)n_bc * sizeof(hf_bc), cudaMemcpyHostToDevice, c->stream));
+    HF_CUDA(cudaStreamSynchronize(c->stream));
+    return 0;
+  }
   c->n_bc = n_bc;
   if (n_bc > 0 && hf_alloc_copy(c, &c->bc_table, table, (size_t)n_bc)) return 1;
   c->h_bc.assign(table, table + n_bc);

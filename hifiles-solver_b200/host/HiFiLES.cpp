@@ -130,6 +130,7 @@ int main(int argc, char *argv[])
     while (i_steps < run_input.n_steps)
     {
       calc_time_step(&FlowSol);
+      if (run_input.pressure_ramp) upload_bc_table(&FlowSol);
       // the residual (and the gradient behind the integral diagnostics) of the last stage is read after monitored steps
       const bool monitored = (i_steps + 1 == 1) || ((i_steps + 1) % run_input.monitor_res_freq == 0) ||
                              (run_input.n_diagnostic_fields > 0 && (i_steps + 1) % run_input.plot_freq == 0);
@@ -137,6 +138,7 @@ int main(int argc, char *argv[])
       FlowSol.time += run_input.dt;
       run_input.time = FlowSol.time;
       i_steps++;
+      if (run_input.pressure_ramp) run_input.ramp_counter++;
       /*! Compute time-averaged quantities (reference src/HiFiLES.cpp:241-245) */
       if (i_steps == 1) run_input.spinup_time = FlowSol.time; // set start time for averaging
       if (run_input.n_average_fields) CalcTimeAverageQuantities(&FlowSol);

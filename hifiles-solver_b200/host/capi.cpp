@@ -112,6 +112,7 @@ int hifiles_run(void *handle, int n_steps, int fused)
     for (int it = 0; it < n_steps; it++)
     {
       calc_time_step(S);
+      if (run_input.pressure_ramp) upload_bc_table(S);
       for (int i = 0; i < RKSteps; i++)
       {
         CalcResidual(S->ini_iter + it, i, S);
@@ -121,6 +122,7 @@ int hifiles_run(void *handle, int n_steps, int fused)
       }
       S->time += run_input.dt;
       run_input.time = S->time;
+      if (run_input.pressure_ramp) run_input.ramp_counter++;
     }
   });
 }

@@ -576,4 +576,5 @@ void CalcNormResidual(struct solution *FlowSol);
 int get_n_rk_steps(int adv_type);
 /*! B200 extension: all RK stages of n_steps steps on the device without host round trips */
 void AdvanceSteps(struct solution *FlowSol, int n_steps);
+void upload_bc_table(struct solution *FlowSol); // again every time step when an inlet ramps (pressure_ramp)
 void hf_check(int status);

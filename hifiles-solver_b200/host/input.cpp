@@ -400,7 +400,17 @@ void input::read_boundary_param()
       bdy_r.getScalarValue(pre + "nz", b.nz, 0.);
       bdy_r.getScalarValue(pre + "inlet_type", b.type, 0);
       if (b.pressure_ramp)
-        FatalError("pressure_ramp inlet is outside the hot-path scope of this build");
+      {
+        // total pressure / temperature ramped from the *_old values, one increment per time step (reference src/input.cpp:374-382)
+        pressure_ramp = 1;
+        ramp_counter = 1;
+        bdy_r.getScalarValue(pre + "p_ramp_coeff", b.p_ramp_coeff, 0.);
+        bdy_r.getScalarValue(pre + "T_ramp_coeff", b.T_ramp_coeff, 0.);
+        bdy_r.getScalarValue(pre + "p_total_old", b.p_total_old);
+        bdy_r.getScalarValue(pre + "T_total_old", b.T_total_old, T_free_stream);
+        if (b.T_ramp_coeff < 0.)
+          FatalError("T_ramp_coeff < 0 (isentropic total temperature at the inlet) is not built");
+      }
     }
     else if (flag == SUB_OUT_SIMP || flag == SUB_OUT_CHAR)
     {
@@ -455,7 +465,12 @@ void input::read_boundary_param()
     }
     else if (flag == SUB_IN_CHAR)
     {
-      if (viscous) { b.T_total /= T_ref; b.p_total /= p_ref; }
+      if (viscous)
+      {
+        b.T_total /= T_ref;
+        b.p_total /= p_ref;
+        if (b.pressure_ramp) { b.p_total_old /= p_ref; b.T_total_old /= T_ref; }
+      }
     }
     else if (flag == SUB_OUT_SIMP || flag == SUB_OUT_CHAR)
     {

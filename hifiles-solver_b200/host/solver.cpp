@@ -15,6 +15,46 @@ int get_n_rk_steps(int adv_type)
   return 0;
 }
 
+/*! Boundary parameter table of the device.  A characteristic subsonic inlet with pressure_ramp takes its total pressure and
+ *  temperature from the ramp of this time step (reference src/bdy_inters.cpp:481-510: linear in run_input.ramp_counter from
+ *  the *_old value, clipped at the target; the counter advances once per time step, src/HiFiLES.cpp:224-225). */
+void upload_bc_table(struct solution *FlowSol)
+{
+  vector<hf_bc> table(run_input.bc_list.size());
+  for (size_t i = 0; i < table.size(); i++)
+  {
+    bc &b = run_input.bc_list[i];
+    hf_bc &t = table[i];
+    memset(&t, 0, sizeof(t));
+    t.bc_flag = b.get_bc_flag();
+    t.rho = b.rho;
+    for (int k = 0; k < 3; k++) t.velocity[k] = b.velocity.size() == 3 ? b.velocity(k) : 0.;
+    t.p_static = b.p_static;
+    t.T_static = b.T_static;
+    t.p_total = b.p_total;
+    t.T_total = b.T_total;
+    if (t.bc_flag == SUB_IN_CHAR && b.pressure_ramp)
+    {
+      if (b.p_ramp_coeff)
+      {
+        double p = b.p_total_old + (b.p_total - b.p_total_old) * b.p_ramp_coeff * run_input.ramp_counter;
+        if (p >= b.p_total) p = b.p_total;
+        t.p_total = p;
+      }
+      if (b.T_ramp_coeff > 0)
+      {
+        double T = b.T_total_old + (b.T_total - b.T_total_old) * b.T_ramp_coeff * run_input.ramp_counter;
+        if (T >= b.T_total) T = b.T_total;
+        t.T_total = T;
+      }
+    }
+    t.mach = b.mach;
+    t.nx = b.nx; t.ny = b.ny; t.nz = b.nz;
+    t.use_wm = b.use_wm;
+  }
+  hf_check(hf_dev_set_bc_table(FlowSol->ctx, (int)table.size(), table.empty() ? nullptr : table.data()));
+}
+
 static void upload_params(struct solution *FlowSol)
 {
   hf_params p;
@@ -59,24 +99,7 @@ static void upload_params(struct solution *FlowSol)
   p.s0 = run_input.s0;
   hf_check(hf_dev_set_params(FlowSol->ctx, &p));
 
-  vector<hf_bc> table(run_input.bc_list.size());
-  for (size_t i = 0; i < table.size(); i++)
-  {
-    bc &b = run_input.bc_list[i];
-    hf_bc &t = table[i];
-    memset(&t, 0, sizeof(t));
-    t.bc_flag = b.get_bc_flag();
-    t.rho = b.rho;
-    for (int k = 0; k < 3; k++) t.velocity[k] = b.velocity.size() == 3 ? b.velocity(k) : 0.;
-    t.p_static = b.p_static;
-    t.T_static = b.T_static;
-    t.p_total = b.p_total;
-    t.T_total = b.T_total;
-    t.mach = b.mach;
-    t.nx = b.nx; t.ny = b.ny; t.nz = b.nz;
-    t.use_wm = b.use_wm;
-  }
-  hf_check(hf_dev_set_bc_table(FlowSol->ctx, (int)table.size(), table.empty() ? nullptr : table.data()));
+  upload_bc_table(FlowSol);
 }
 
 /*! Move everything to the device (the reference did this piecemeal with mv_all_cpu_gpu calls inside
@@ -264,6 +287,19 @@ void calc_time_step(struct solution *FlowSol)
 
 void AdvanceSteps(struct solution *FlowSol, int n_steps)
 {
+  if (run_input.pressure_ramp)
+  {
+    // the inlet state changes every step: one step per device call
+    for (int it = 0; it < n_steps; it++)
+    {
+      upload_bc_table(FlowSol);
+      hf_check(hf_dev_run_steps(FlowSol->ctx, 1, FlowSol->time));
+      FlowSol->time += run_input.dt;
+      run_input.ramp_counter++;
+    }
+    run_input.time = FlowSol->time;
+    return;
+  }
   hf_check(hf_dev_run_steps(FlowSol->ctx, n_steps, FlowSol->time));
   FlowSol->time += n_steps * run_input.dt;
   run_input.time = FlowSol->time;

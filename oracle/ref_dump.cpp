@@ -398,6 +398,7 @@ int main(int argc, char *argv[])
     }
     FlowSol.time += run_input.dt;
     run_input.time = FlowSol.time;
+    if (run_input.pressure_ramp) run_input.ramp_counter++; // as the reference's main loop (src/HiFiLES.cpp:224-225)
     // residual norms as output::CalcNormResidual (src/output.cpp:2166-2248), serial
     int nf = 0, np = 0;
     for (int t = 0; t < FlowSol.n_ele_types; t++)
