@@ -1,7 +1,7 @@
 // Boundary ghost states and boundary gradients: restatement of bdy_inters::set_boundary_conditions and
 // bdy_inters::set_boundary_gradients (reference src/bdy_inters.cpp:340-1019, 1138-1189) as device functions.
-// Wall-model (use_wm), pressure-ramp and synthetic-eddy inlet branches are not part of this build; the host
-// rejects inputs that ask for them.
+// The ramped inlet reaches the device as the step's total pressure / temperature in the boundary table (host
+// upload_bc_table); the synthetic-eddy inlet branch is not part of this build, the host rejects inputs that ask for it.
 #pragma once
 #include "hf_physics.cuh"
 #include "../../include/hifiles_b200.h"
@@ -86,6 +86,8 @@ __device__ void set_boundary_conditions(int sol_spec, const hf_bc &B, const doub
   else if (bc_flag == HF_SUB_IN_CHAR)
   {
     double p_total_temp = B.p_total, T_total_temp = B.T_total;
+    // ramped inlet with T_ramp_coeff < 0: isentropic relation across the interface (reference src/bdy_inters.cpp:500-501)
+    if (B.T_isentropic) T_total_temp = (p_l / (rho_l * R_ref)) * pow(p_total_temp / p_l, (gamma - 1.0) / gamma);
     double n_free_stream[3] = {B.nx, B.ny, B.nz};
     vn_l = 0.;
 #pragma unroll

@@ -408,8 +408,6 @@ void input::read_boundary_param()
         bdy_r.getScalarValue(pre + "T_ramp_coeff", b.T_ramp_coeff, 0.);
         bdy_r.getScalarValue(pre + "p_total_old", b.p_total_old);
         bdy_r.getScalarValue(pre + "T_total_old", b.T_total_old, T_free_stream);
-        if (b.T_ramp_coeff < 0.)
-          FatalError("T_ramp_coeff < 0 (isentropic total temperature at the inlet) is not built");
       }
     }
     else if (flag == SUB_OUT_SIMP || flag == SUB_OUT_CHAR)

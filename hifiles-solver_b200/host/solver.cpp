@@ -47,6 +47,7 @@ void upload_bc_table(struct solution *FlowSol)
         if (T >= b.T_total) T = b.T_total;
         t.T_total = T;
       }
+      t.T_isentropic = b.T_ramp_coeff < 0 ? 1 : 0;
     }
     t.mach = b.mach;
     t.nx = b.nx; t.ny = b.ny; t.nz = b.nz;

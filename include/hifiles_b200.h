@@ -117,6 +117,7 @@ typedef struct hf_bc
   int bc_flag;
   double rho, velocity[3], p_static, T_static, p_total, T_total, mach, nx, ny, nz;
   int use_wm; /* 1: this wall boundary takes its viscous flux from the wall model (bc::use_wm) */
+  int T_isentropic; /* 1: ramped characteristic inlet with T_ramp_coeff < 0, T_total = T_l (p_total / p_l)^((gamma-1)/gamma) */
 } hf_bc;
 
 /* Boundary interfaces of one face type (mirror of bdy_inters::set_boundary, reference src/bdy_inters.cpp:75-178). */

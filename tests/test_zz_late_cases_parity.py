@@ -50,6 +50,9 @@ INLET_CASES = {
     "quad_p2_ns_sub_in_char": CHANNEL,
     "quad_p2_ns_sub_in_char_ramped": dict(CHANNEL, bc_In_pressure_ramp=1, bc_In_p_ramp_coeff=0.2, bc_In_T_ramp_coeff=0.25,
                                           bc_In_p_total_old=104000., bc_In_T_total_old=303.),
+    # T_ramp_coeff < 0: total temperature from the isentropic relation across the interface (src/bdy_inters.cpp:500-501)
+    "quad_p2_ns_sub_in_char_ramped_isentropic": dict(CHANNEL, bc_In_pressure_ramp=1, bc_In_p_ramp_coeff=0.2, bc_In_T_ramp_coeff=-1.,
+                                                     bc_In_p_total_old=104000.),
 }
 
 
