@@ -195,6 +195,24 @@ void eles::set_ics(double &time)
           ics(4) = (p / (gamma - 1.0)) + (0.5 * rho * ((vx * vx) + (vy * vy) + (vz * vz)));
         }
       }
+      else if (run_input.ic_form == 2 || run_input.ic_form == 3) // advection-diffusion: sine wave, single / product
+      {
+        hf_array<double> grad_rho(n_dims);
+        if (run_input.ic_form == 2)
+          eval_sine_wave_single(pos, run_input.wave_speed, run_input.diff_coeff, time, rho, grad_rho, n_dims);
+        else
+          eval_sine_wave_group(pos, run_input.wave_speed, run_input.diff_coeff, time, rho, grad_rho, n_dims);
+        ics(0) = rho;
+      }
+      else if (run_input.ic_form == 4) // advection-diffusion: Gaussian pulse
+      {
+        eval_sphere_wave(pos, run_input.wave_speed, time, rho, n_dims);
+        ics(0) = rho;
+      }
+      else if (run_input.ic_form == 5) // advection-diffusion: constant
+        ics(0) = run_input.rho_c_ic;
+      else if (run_input.ic_form == 6) // polynomial velocity profile: the reference's eval_poly_ic stops here too (src/funcs.cpp:1928)
+        FatalError("Function deprecated!");
       else
         FatalError("ERROR: Invalid form of initial condition ...");
 

@@ -154,6 +154,48 @@ bool is_perfect_cube(int in_a)
   return (in_a == number * number * number);
 }
 
+// Exact solutions of the scalar advection-diffusion test equation, used as initial data (ic_form 2, 3, 4) and by
+// compute_error: a plane sine wave along (1,1[,1]), a product of sines, a Gaussian pulse (reference src/funcs.cpp:1742-1808).
+// The decay factor is written as the reference has it, exp(-n_dims * diff_coeff * pi^2 * t), so time 0 gives the same bits.
+static inline double ad_decay(double diff_coeff, double time, int n_dims) { return exp(-((double)n_dims) * diff_coeff * pi * pi * time); }
+
+void eval_sine_wave_single(hf_array<double> &pos, hf_array<double> &wave_speed, double diff_coeff, double time, double &rho, hf_array<double> &grad_rho, int n_dims)
+{
+  double x = pos(0) - wave_speed(0) * time, y = pos(1) - wave_speed(1) * time;
+  double angle = x + y;
+  if (n_dims == 3) angle = x + y + (pos(2) - wave_speed(2) * time);
+  rho = ad_decay(diff_coeff, time, n_dims) * sin(pi * angle);
+  for (int d = 0; d < n_dims; d++) grad_rho(d) = pi * ad_decay(diff_coeff, time, n_dims) * cos(pi * angle);
+}
+
+void eval_sine_wave_group(hf_array<double> &pos, hf_array<double> &wave_speed, double diff_coeff, double time, double &rho, hf_array<double> &grad_rho, int n_dims)
+{
+  double r[3] = {0., 0., 0.};
+  for (int d = 0; d < n_dims; d++) r[d] = pos(d) - wave_speed(d) * time;
+  const double a = ad_decay(diff_coeff, time, n_dims);
+  if (n_dims == 2)
+  {
+    rho = a * sin(pi * r[0]) * sin(pi * r[1]);
+    grad_rho(0) = pi * a * cos(pi * r[0]) * sin(pi * r[1]);
+    grad_rho(1) = pi * a * sin(pi * r[0]) * cos(pi * r[1]);
+  }
+  else
+  {
+    rho = a * sin(pi * r[0]) * sin(pi * r[1]) * sin(pi * r[2]);
+    grad_rho(0) = pi * a * cos(pi * r[0]) * sin(pi * r[1]) * sin(pi * r[2]);
+    grad_rho(1) = pi * a * sin(pi * r[0]) * cos(pi * r[1]) * sin(pi * r[2]);
+    grad_rho(2) = pi * a * sin(pi * r[0]) * sin(pi * r[1]) * cos(pi * r[2]);
+  }
+}
+
+// the reference reads three coordinates whatever n_dims is (src/funcs.cpp:1797-1808): the pulse is a 3-D initial condition
+void eval_sphere_wave(hf_array<double> &pos, hf_array<double> &wave_speed, double time, double &rho, int n_dims)
+{
+  if (n_dims != 3) FatalError("ic_form 4 (spherical pulse) needs a three-dimensional mesh");
+  double x = pos(0) - wave_speed(0) * time, y = pos(1) - wave_speed(1) * time, z = pos(2) - wave_speed(2) * time;
+  rho = exp(-0.5 * (x * x + y * y + z * z));
+}
+
 void eval_isentropic_vortex(hf_array<double> &pos, double time, double &rho, double &vx, double &vy, double &vz, double &p, int n_dims)
 {
   (void)n_dims;

@@ -161,6 +161,9 @@ double compute_eta(int vcjh_scheme, int order);
 bool is_perfect_square(int in_a);
 bool is_perfect_cube(int in_a);
 void eval_isentropic_vortex(hf_array<double> &pos, double time, double &rho, double &vx, double &vy, double &vz, double &p, int n_dims);
+void eval_sine_wave_single(hf_array<double> &pos, hf_array<double> &wave_speed, double diff_coeff, double time, double &rho, hf_array<double> &grad_rho, int n_dims);
+void eval_sine_wave_group(hf_array<double> &pos, hf_array<double> &wave_speed, double diff_coeff, double time, double &rho, hf_array<double> &grad_rho, int n_dims);
+void eval_sphere_wave(hf_array<double> &pos, hf_array<double> &wave_speed, double time, double &rho, int n_dims);
 /*! 1-D Gauss (rule 0) / Gauss-Lobatto (rule 1) points and weights from the reference's binary tables
  *  (reference src/cubature_1d.cpp:50-85). */
 void cubature_1d(int in_rule, int in_order, hf_array<double> &locs, hf_array<double> &weights);

@@ -194,3 +194,48 @@ def test_twenty_node_hexahedra_set_up_bit_identically(tmp_path, hb, meshgen):
             assert np.array_equal(a, v), "%s differs from the reference (max abs %.3e)" % (k, np.abs(a.astype(float) - v).max())
             checked += 1
     assert checked >= 30
+
+
+# Scalar advection-diffusion test equation (equation 1): Lax-Friedrichs common flux, n_fields = 1, the analytic initial
+# fields of reference src/funcs.cpp:1742-1808 (ic_form 2 plane sine wave, 3 product of sines, 4 Gaussian pulse, 5 constant).
+ADVECTION_DIFFUSION = dict(equation=1, viscous=1, riemann_solve_type=1, vis_riemann_solve_type=0, order=3, adv_type=3, dt=1e-3,
+                           wave_speed_x=1.0, wave_speed_y=0.5, wave_speed_z=0.25, diff_coeff=0.01, rho_c_ic=0.75, **{"lambda": 1.0})
+ADVECTION_DIFFUSION_CASES = {
+    "quad_sine_single": ("quad_box", (4, 4), dict(lengths=(2., 2.), origin=(-1., -1.)), dict(ic_form=2, dx_cyclic=2., dy_cyclic=2., dz_cyclic=None)),
+    "quad_sine_group_warped": ("quad_box", (4, 3), dict(lengths=(2., 2.), origin=(-1., -1.), warp=0.05), dict(ic_form=3, dx_cyclic=2., dy_cyclic=2., dz_cyclic=None)),
+    "tri_constant": ("tri_box", (3, 3), dict(lengths=(2., 2.), origin=(-1., -1.)), dict(ic_form=5, dx_cyclic=2., dy_cyclic=2., dz_cyclic=None)),
+    "hex_sine_single": ("hex_box", 3, dict(lengths=(2., 2., 2.), origin=(-1., -1., -1.)), dict(ic_form=2, order=2, dx_cyclic=2., dy_cyclic=2., dz_cyclic=2.)),
+    "hex_gaussian_pulse": ("hex_box", 3, dict(lengths=(6., 6., 6.), origin=(-3., -3., -3.)), dict(ic_form=4, order=2, dx_cyclic=6., dy_cyclic=6., dz_cyclic=6.)),
+}
+
+
+@pytest.mark.parametrize("name", list(ADVECTION_DIFFUSION_CASES))
+def test_advection_diffusion_setup_is_bit_identical(tmp_path, hb, meshgen, name):
+    if not util.have_reference():
+        pytest.skip("oracle/_ref not built")
+    gen, n, mkw, opts = ADVECTION_DIFFUSION_CASES[name]
+    getattr(meshgen, gen)(str(tmp_path / "m.neu"), n, **mkw)
+    inp = meshgen.write_input(str(tmp_path / "input"), "m.neu", **dict(ADVECTION_DIFFUSION, **opts))
+    ref = util.run_reference(inp, 0, stagewise=False)
+    skip = ("step", "final", "history", "mesh", "meta", "params", "rk_", "case")
+    checked = 0
+    with hb.Run(inp, host_only=True) as run:
+        for k, v in ref.items():
+            if k.startswith(skip) or k.endswith(("tdA_idx_l", "tdA_idx_r", "norm_idx", "bc_flags")):
+                continue
+            a = run.host_array(k.replace("disu_upts_ic", "disu_upts"))
+            assert a.shape == v.shape, k
+            assert np.array_equal(a, v), "%s differs from the reference (max abs %.3e)" % (k, np.abs(a.astype(float) - v).max())
+            if k.endswith("disu_upts_ic"):
+                assert v.ndim == 2 and np.abs(v).max() <= 1.0   # one scalar field (points, elements), amplitude of the analytic field
+            checked += 1
+    assert checked >= 30
+
+
+def test_polynomial_initial_condition_stops_as_in_the_reference(tmp_path, hb, meshgen):
+    """ic_form 6: the reference's eval_poly_ic is a FatalError("Function deprecated!") (src/funcs.cpp:1928)."""
+    meshgen.quad_box(str(tmp_path / "m.neu"), (2, 2))
+    inp = meshgen.write_input(str(tmp_path / "input"), "m.neu", ic_form=6, order=1, dx_cyclic=20., dy_cyclic=20., dz_cyclic=None,
+                              x_coeffs="13 " + " ".join(["0"] * 13), y_coeffs="13 " + " ".join(["0"] * 13), z_coeffs="13 " + " ".join(["0"] * 13))
+    with pytest.raises(hb.HiFiLESError, match="Function deprecated"):
+        hb.Run(inp, host_only=True)
