@@ -72,3 +72,28 @@ def test_time_steps_with_total_pressure_inlet(tmp_path, hb, meshgen, name):
         check("residual norm", run.norm_residual(), ref["history.norm_residual"][:, -1], 1e-12)
         check("final disu_upts", run.download("quad", "disu_upts"), ref["final.quad.disu_upts"], 1e-12)
         check("final div_tconf_upts", run.download("quad", "div_tconf_upts"), ref["final.quad.div_tconf_upts"], 1e-12)
+
+
+# Scalar advection-diffusion test equation (equation 1, one field): Lax-Friedrichs common flux (reference
+# src/inters.cpp:535-557), LDG for the diffusive part, periodic meshes.  Host setup is bit-identical on the CPU
+# (tests/test_host_cpu.py); the device physics for one field (hf_physics.cuh, NF == 1) has its first B200 run here.
+from test_host_cpu import ADVECTION_DIFFUSION, ADVECTION_DIFFUSION_CASES
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["quad_sine_single", "quad_sine_group_warped", "hex_sine_single"])
+def test_time_steps_of_the_advection_diffusion_equation(tmp_path, hb, meshgen, name):
+    if not util.have_reference():
+        pytest.skip("oracle/_ref not built")
+    gen, n, mkw, opts = ADVECTION_DIFFUSION_CASES[name]
+    getattr(meshgen, gen)(str(tmp_path / "m.neu"), n, **mkw)
+    inp = meshgen.write_input(str(tmp_path / "input"), "m.neu", **dict(ADVECTION_DIFFUSION, **opts))
+    n_steps = 3
+    ref = util.run_reference(inp, n_steps, stagewise=False)
+    with hb.Run(inp) as run:
+        run.set_mode(False)
+        run.run(n_steps, fused=False)
+        check("residual norm", run.norm_residual(), ref["history.norm_residual"][:, -1], 1e-13)
+        for t in run.ele_types():
+            check("final disu_upts " + t, run.download(t, "disu_upts"), ref["final." + t + ".disu_upts"], 1e-13)
+            check("final div_tconf_upts " + t, run.download(t, "div_tconf_upts"), ref["final." + t + ".div_tconf_upts"], 1e-13)
