@@ -133,11 +133,72 @@ def cpu_reference_rate(order, n_ref, budget_note=""):
         shutil.rmtree(work, ignore_errors=True)
 
 
+def cpu_reference_rate_all_cores(order, n_ref, replicas):
+    """The reference arm's figure: `replicas` concurrent copies of the unmodified serial reference, one per host core, each
+    on its own TGV n_ref^3 domain.  The reference's only way to use several cores is its MPI + ParMETIS build (absent
+    here); concurrent serial domains are that run without the halo exchange, i.e. an upper bound for it on this host.
+    Rate = all replicas' DOF-stage updates / the slowest replica's (3-step - 1-step) time."""
+    import util
+    from concurrent.futures import ThreadPoolExecutor
+    if not util.have_reference():
+        return None
+    work = tempfile.mkdtemp(prefix="hf_cpu_all_")
+    try:
+        env = dict(os.environ, HIFILES_HOME=util.REF_DIR, OMP_NUM_THREADS="1")
+        dirs = []
+        for r in range(replicas):
+            d = os.path.join(work, "r%d" % r)
+            os.makedirs(d)
+            _, _, inp = make_case(d, n_ref, order)
+            dirs.append((d, inp))
+
+        def one(arg):
+            d, inp = arg
+            t = {}
+            for steps in (1, 3):
+                t0 = time.time()
+                r = subprocess.run([util.REF_DUMP, os.path.basename(inp), os.path.join(d, "o.hfd"), str(steps), "0"], cwd=d, env=env,
+                                   capture_output=True, text=True)
+                t[steps] = time.time() - t0
+                if r.returncode != 0:
+                    return None
+            return t[3] - t[1]
+
+        with ThreadPoolExecutor(max_workers=replicas) as ex:
+            secs = list(ex.map(one, dirs))
+        if any(x is None for x in secs):
+            return None
+        dof = n_ref ** 3 * (order + 1) ** 3 * 5
+        sec = max(max(secs), 1e-9)
+        return dict(value=replicas * dof * 4 * 2 / sec / 1e9, seconds=sec, dof=dof * replicas,
+                    sample="%d concurrent serial runs (one per host core) of the unmodified reference, each TGV %d^3 hex P=%d, 2 time steps "
+                           "(8 RK stages); no halo exchange, so an upper bound for the reference's MPI build on these cores" % (replicas, n_ref, order))
+    finally:
+        shutil.rmtree(work, ignore_errors=True)
+
+
+def host_cores():
+    try:
+        import psutil
+        n = psutil.cpu_count(logical=False) or os.cpu_count()
+    except Exception:
+        n = os.cpu_count()
+    try:
+        n = min(n, len(os.sched_getaffinity(0)))
+    except Exception:
+        pass
+    return max(1, min(int(n or 1), 64))
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    res = cpu_reference_rate(args.order, args.cpu_n)
+    serial = cpu_reference_rate(args.order, args.cpu_n)
+    cores = host_cores()
+    res = cpu_reference_rate_all_cores(args.order, args.cpu_n, cores) if (serial is not None and cores > 1) else serial
+    if res is None:
+        res, cores = serial, 1
     n = args.n
     cfg = {"workload": "3-D Taylor-Green vortex Re=1600, %d^3 hexahedra, P=%d, HLLC+LDG, SSP-RK34" % (n, args.order),
            "sample": None}
@@ -148,7 +209,8 @@ def run_reference_arm(args):
     line = {"impl": "reference", "metric": "GDOF-RK-stage updates/s (TGV hex P=%d)" % args.order, "value": res["value"], "unit": "GDOF-stage/s",
             "n_gpus": args.gpus, "steps": 2, "warmup": 0, "ms_per_step": res["seconds"] / 2 * 1e3, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg,
-            "cpu_baseline": {"value": res["value"], "unit": "GDOF-stage/s", "cores": 1, "kind": "reference", "sample": res["sample"]},
+            "cpu_baseline": {"value": res["value"], "unit": "GDOF-stage/s", "cores": cores, "kind": "reference", "sample": res["sample"],
+                             "serial_value": serial["value"]},
             "e2e": {"value": res["value"], "unit": "GDOF-stage/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     print(json.dumps(line))
 
