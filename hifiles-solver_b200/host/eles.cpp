@@ -738,17 +738,25 @@ void eles::CalcIntegralQuantities(int n_integral_quantities, hf_array<double> &i
   hf_check(hf_dev_integral_quantities(ctx, ele_type, n_integral_quantities, kinds, integral_quantities.get_ptr_cpu()));
 }
 
-// reference eles::compute_error + get_pointwise_error (src/eles.cpp:5076-5290), on the host after a device -> host copy of
-// the solution: it runs once, at the end of a test-case run.  Built: test_case 1 (isentropic vortex); the advection /
-// diffusion and Couette test cases fail loudly.
+// reference eles::compute_error + get_pointwise_error (src/eles.cpp:5076-5276), on the host after a device -> host copy of
+// the solution (and, for a viscous run, of the gradient of the last residual evaluation): it runs once, at the end of a
+// test-case run.  Built: test_case 1 (isentropic vortex), 2 / 3 / 4 (advection-diffusion: plane sine wave, product of sines,
+// Gaussian pulse); the Couette case fails loudly.
 hf_array<double> eles::compute_error(int in_norm_type, double &time)
 {
-  if (run_input.test_case != 1) FatalError("Test case not recognized in compute error, exiting");
-  hf_array<double> disu_cubpt(n_fields), pos(n_dims), temp_loc(n_dims), error_sol(n_fields);
+  const int tc = run_input.test_case;
+  if (tc < 1 || tc > 4) FatalError("Test case not recognized in compute error, exiting");
+  if (in_norm_type != 1 && in_norm_type != 2) FatalError("Error norm not supported!");
+  hf_array<double> disu_cubpt(n_fields), grad_disu_cubpt(n_fields, n_dims), pos(n_dims), temp_loc(n_dims);
+  hf_array<double> error_sol(n_fields), error_grad_sol(n_fields, n_dims), grad_rho(n_dims);
   hf_array<double> error_sum(2, n_fields);
   for (int m = 0; m < n_fields; m++) error_sum(0, m) = error_sum(1, m) = 0.;
   const int n_cubpts_per_ele = loc_volume_cubpts.get_dim(1);
+  // the sine-wave cases compare the gradient too; without diffusion the exact solution is the undamped wave
+  const double diff = viscous ? run_input.diff_coeff : 0.;
   cp_disu_upts_gpu_cpu();
+  const bool with_grad = viscous && (tc == 2 || tc == 3); // the only cases whose gradient error is not identically zero
+  if (with_grad) cp_grad_disu_upts_gpu_cpu();
   for (int i = 0; i < n_eles; i++)
     for (int j = 0; j < n_cubpts_per_ele; j++)
     {
@@ -759,28 +767,54 @@ hf_array<double> eles::compute_error(int in_norm_type, double &time)
       {
         disu_cubpt(m) = 0.;
         for (int k = 0; k < n_upts_per_ele; k++) disu_cubpt(m) += opp_volume_cubpts(j, k) * disu_upts(0)(k, i, m);
+        for (int n = 0; n < n_dims; n++)
+        {
+          grad_disu_cubpt(m, n) = 0.;
+          if (with_grad)
+            for (int k = 0; k < n_upts_per_ele; k++) grad_disu_cubpt(m, n) += opp_volume_cubpts(j, k) * grad_disu_upts(k, i, m, n);
+          error_grad_sol(m, n) = 0.; // stays zero for the vortex and the pulse (src/eles.cpp:5149-5165, 5209-5214)
+        }
       }
-      double rho, vx, vy, vz, p;
-      eval_isentropic_vortex(pos, time, rho, vx, vy, vz, p, n_dims);
-      error_sol(0) = disu_cubpt(0) - rho;
-      error_sol(1) = disu_cubpt(1) - rho * vx;
-      error_sol(2) = disu_cubpt(2) - rho * vy;
-      if (n_dims == 2)
-        error_sol(3) = disu_cubpt(3) - (p / (run_input.gamma - 1) + 0.5 * rho * (vx * vx + vy * vy));
+      if (tc == 1)
+      {
+        double rho, vx, vy, vz, p;
+        eval_isentropic_vortex(pos, time, rho, vx, vy, vz, p, n_dims);
+        error_sol(0) = disu_cubpt(0) - rho;
+        error_sol(1) = disu_cubpt(1) - rho * vx;
+        error_sol(2) = disu_cubpt(2) - rho * vy;
+        if (n_dims == 2)
+          error_sol(3) = disu_cubpt(3) - (p / (run_input.gamma - 1) + 0.5 * rho * (vx * vx + vy * vy));
+        else
+        {
+          error_sol(3) = disu_cubpt(3) - rho * vz;
+          error_sol(4) = disu_cubpt(4) - (p / (run_input.gamma - 1) + 0.5 * rho * (vx * vx + vy * vy + vz * vz));
+        }
+      }
       else
       {
-        error_sol(3) = disu_cubpt(3) - rho * vz;
-        error_sol(4) = disu_cubpt(4) - (p / (run_input.gamma - 1) + 0.5 * rho * (vx * vx + vy * vy + vz * vz));
+        double rho;
+        if (tc == 2) eval_sine_wave_single(pos, run_input.wave_speed, diff, time, rho, grad_rho, n_dims);
+        else if (tc == 3) eval_sine_wave_group(pos, run_input.wave_speed, diff, time, rho, grad_rho, n_dims);
+        else eval_sphere_wave(pos, run_input.wave_speed, time, rho, n_dims);
+        error_sol(0) = disu_cubpt(0) - rho;
+        if (tc != 4)
+          for (int n = 0; n < n_dims; n++) error_grad_sol(0, n) = grad_disu_cubpt(0, n) - grad_rho(n);
       }
       for (int m = 0; m < n_fields; m++)
       {
-        double e0;
-        if (in_norm_type == 1) e0 = fabs(error_sol(m));
-        else if (in_norm_type == 2) e0 = error_sol(m) * error_sol(m);
-        else { FatalError("Error norm not supported!"); e0 = 0.; }
+        double e0 = 0., e1 = 0.;
+        if (in_norm_type == 1)
+        {
+          e0 += fabs(error_sol(m));
+          for (int n = 0; n < n_dims; n++) e1 += fabs(error_grad_sol(m, n));
+        }
+        else
+        {
+          e0 += error_sol(m) * error_sol(m);
+          for (int n = 0; n < n_dims; n++) e1 += error_grad_sol(m, n) * error_grad_sol(m, n);
+        }
         error_sum(0, m) += e0 * weight_volume_cubpts(j) * detjac;
-        // the gradient error of this test case is identically zero (src/eles.cpp:5137-5165)
-        error_sum(1, m) += 0. * weight_volume_cubpts(j) * detjac;
+        error_sum(1, m) += e1 * weight_volume_cubpts(j) * detjac;
       }
     }
   return error_sum;

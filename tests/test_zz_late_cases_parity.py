@@ -97,3 +97,38 @@ def test_time_steps_of_the_advection_diffusion_equation(tmp_path, hb, meshgen, n
         for t in run.ele_types():
             check("final disu_upts " + t, run.download(t, "disu_upts"), ref["final." + t + ".disu_upts"], 1e-13)
             check("final div_tconf_upts " + t, run.download(t, "div_tconf_upts"), ref["final." + t + ".div_tconf_upts"], 1e-13)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("test_case", [2, 3])
+def test_advection_diffusion_error_file_matches_reference_binary(tmp_path, hb, meshgen, test_case):
+    """test_case 2 / 3: error of the solution and of its gradient against the decaying sine waves, integrated over the volume
+    cubature and appended to error.dat (reference src/eles.cpp:5076-5276, src/output.cpp:2052-2160) by the command-line driver."""
+    import os
+    import subprocess
+    import numpy as np
+    from test_driver_parity import REF, OURS
+    if not (os.path.exists(REF) and os.path.exists(OURS)):
+        pytest.skip("driver binaries not built")
+    lines = {}
+    for who, exe in (("ref", REF), ("ours", OURS)):
+        d = tmp_path / who
+        d.mkdir()
+        meshgen.quad_box(str(d / "m.neu"), (6, 6), lengths=(2., 2.), origin=(-1., -1.))
+        meshgen.write_input(str(d / "input"), "m.neu", **dict(ADVECTION_DIFFUSION, ic_form=test_case, test_case=test_case, dx_cyclic=2., dy_cyclic=2.,
+                                                              dz_cyclic=None, n_steps=5, monitor_res_freq=5))
+        env = dict(os.environ, HIFILES_HOME=util.REF_DIR if who == "ref" else os.path.join(util.ROOT, "hifiles-solver_b200"))
+        r = subprocess.run([exe, "input"], cwd=str(d), env=env, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+        lines[who] = open(d / "error.dat").read().strip().splitlines()
+    assert len(lines["ref"]) == len(lines["ours"])
+    for la, lb in zip(lines["ref"], lines["ours"]):
+        a, b = [t.strip() for t in la.split(",") if t.strip()], [t.strip() for t in lb.split(",") if t.strip()]
+        assert len(a) == len(b)
+        for x, y in zip(a, b):
+            try:
+                fx, fy = float(x), float(y)
+            except ValueError:
+                assert x == y
+                continue
+            assert abs(fx - fy) <= 2e-6 * max(abs(fx), 1e-300)   # printed with 7 significant digits
