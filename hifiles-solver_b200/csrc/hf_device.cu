@@ -17,6 +17,7 @@
 
 static thread_local std::string g_err;
 void hf_set_error(const std::string &msg) { g_err = msg; }
+const std::string &hf_get_error() { return g_err; }
 
 #define HF_FAIL(msg)            \
   do {                          \
@@ -1548,6 +1549,8 @@ int hf_dev_finalize_setup(hf_ctx *c)
   if (c->fused && hf_fused_prepare(c)) return 1;
   c->finalized = true;
   HF_CUDA(cudaDeviceSynchronize());
+  // the communicator may have arrived first (INTEGRATION.md allows either order): agree across the ranks now
+  if (c->nproc > 1 && c->nccl_comm && !c->nccl_reconciled && hf_fused_after_nccl(c)) return 1;
   return 0;
 }
 

@@ -14,6 +14,7 @@
   } while (0)
 
 void hf_set_error(const std::string &msg);
+const std::string &hf_get_error();
 
 // ELLPACK form of a small operator: exact zeros dropped, columns ascending, so a row sum visits the non-zero
 // terms in the same order as the reference's dense dgemm (reference src/funcs.cpp:49-124).
@@ -136,6 +137,7 @@ struct hf_ctx
   bool have_params = false;
   int fused = 1;
   bool finalized = false;
+  bool nccl_reconciled = false; // hf_fused_after_nccl has run (needs both the communicator and the finalized setup, in either order)
   bool want_gradient = false; // integral diagnostics requested: the fused kernels also store grad_disu_upts when they keep the residual
   bool ufpts_valid = false; // disu_fpts holds opp_0 * current disu_upts(0) (fused path bookkeeping)
   hf_eles_dev eles[HF_N_ELE_TYPES];
@@ -190,13 +192,20 @@ template <typename T>
 int hf_alloc_copy(hf_ctx *c, T **p, const T *src, size_t n)
 {
   if (hf_alloc(c, p, n)) return 1;
-  if (n) HF_CUDA(cudaMemcpy(*p, src, n * sizeof(T), cudaMemcpyHostToDevice));
+  // the context's streams are non-blocking (not ordered against the legacy default stream): copy on the compute stream and
+  // wait, so that whatever is launched next on it, or on the communication stream behind an event, sees the data
+  if (n)
+  {
+    HF_CUDA(cudaMemcpyAsync(*p, src, n * sizeof(T), cudaMemcpyHostToDevice, c->stream));
+    HF_CUDA(cudaStreamSynchronize(c->stream));
+  }
   return 0;
 }
 template <typename T>
 int hf_alloc_zero(hf_ctx *c, T **p, size_t n)
 {
   if (hf_alloc(c, p, n)) return 1;
-  HF_CUDA(cudaMemset(*p, 0, (n ? n : 1) * sizeof(T)));
+  HF_CUDA(cudaMemsetAsync(*p, 0, (n ? n : 1) * sizeof(T), c->stream));
+  HF_CUDA(cudaStreamSynchronize(c->stream));
   return 0;
 }

@@ -908,6 +908,7 @@ int hf_fused_after_nccl(hf_ctx *c)
 {
   hf_fused_state *Z = c->fz;
   if (c->nproc < 2) return 0;
+  c->nccl_reconciled = true;
   // the fused kernels exchange other halo data than the staged ones: either every rank uses them or none does (a rank
   // whose part of the mesh has boundary faces, say, cannot)
   double all_available = (Z && Z->available) ? 1.0 : 0.0;

@@ -6,6 +6,7 @@
 #include "hf_device.h"
 #include <dlfcn.h>
 #include <cstring>
+#include <mutex>
 
 namespace
 {
@@ -36,9 +37,8 @@ nccl_api g_nccl;
 const int k_nccl_float64 = 8; // ncclFloat64
 const int k_nccl_min = 3;     // ncclMin
 
-int load_nccl()
+int load_nccl_once()
 {
-  if (g_nccl.lib) return 0;
   const char *names[] = {"libnccl.so.2", "libnccl.so"};
   for (const char *n : names)
   {
@@ -60,6 +60,16 @@ int load_nccl()
   HF_SYM(errstr, fn_errstr, "ncclGetErrorString");
 #undef HF_SYM
   return 0;
+}
+int load_nccl()
+{
+  // contexts may be created from several threads: bind the library once
+  static std::once_flag once;
+  static int status = 1;
+  static std::string err;
+  std::call_once(once, [] { status = load_nccl_once(); if (status) err = hf_get_error(); });
+  if (status) hf_set_error(err);
+  return status;
 }
 #define HF_NCCL(call)                                                                                      \
   do {                                                                                                     \
@@ -86,7 +96,9 @@ extern "C" int hf_dev_nccl_init(hf_ctx *c, const void *unique_id_128_bytes)
   nccl_comm_t comm = nullptr;
   HF_NCCL(g_nccl.comm_init(&comm, c->nproc, id, c->rank));
   c->nccl_comm = comm;
-  return hf_fused_after_nccl(c);
+  // the cross-rank agreement of the fused path needs the finalized setup: when the communicator comes first it runs at the
+  // end of hf_dev_finalize_setup instead
+  return c->finalized ? hf_fused_after_nccl(c) : 0;
 }
 
 int hf_halo_post(hf_ctx *c, hf_mpi_inters_dev &I, const double *out, double *in, size_t per_inter)
@@ -97,14 +109,16 @@ int hf_halo_post(hf_ctx *c, hf_mpi_inters_dev &I, const double *out, double *in,
   HF_CUDA(cudaStreamWaitEvent(c->comm_stream, c->ev_a, 0));
   HF_NCCL(g_nccl.group_start());
   size_t off = 0;
-  for (size_t p = 0; p < I.nb_rank.size(); p++)
+  int first_err = 0; // a failing send / recv must not leave the communicator inside an open group
+  for (size_t p = 0; p < I.nb_rank.size() && !first_err; p++)
   {
     size_t cnt = (size_t)I.nb_count[p] * per_inter;
-    HF_NCCL(g_nccl.send(out + off, cnt, k_nccl_float64, I.nb_rank[p], (nccl_comm_t)c->nccl_comm, c->comm_stream));
-    HF_NCCL(g_nccl.recv(in + off, cnt, k_nccl_float64, I.nb_rank[p], (nccl_comm_t)c->nccl_comm, c->comm_stream));
+    first_err = g_nccl.send(out + off, cnt, k_nccl_float64, I.nb_rank[p], (nccl_comm_t)c->nccl_comm, c->comm_stream);
+    if (!first_err) first_err = g_nccl.recv(in + off, cnt, k_nccl_float64, I.nb_rank[p], (nccl_comm_t)c->nccl_comm, c->comm_stream);
     off += cnt;
   }
-  HF_NCCL(g_nccl.group_end());
+  const int end_err = g_nccl.group_end();
+  if (first_err || end_err) { hf_set_error(std::string("ncclSend/ncclRecv of the halo exchange: ") + g_nccl.errstr(first_err ? first_err : end_err)); return 1; }
   HF_CUDA(cudaEventRecord(c->ev_b, c->comm_stream));
   c->halo_pending = true;
   return 0;
@@ -130,14 +144,18 @@ int hf_halo_allreduce_min(hf_ctx *c, double *v)
 
 /* sum of v[n] over the ranks, result on every rank (the reference reduces its diagnostics to rank 0 with MPI_Reduce(SUM),
  * src/output.cpp:2030-2037) */
-extern "C" int hf_dev_allreduce_sum(hf_ctx *c, double *v, int n)
+static int allreduce_host(hf_ctx *c, double *v, int n, int op);
+extern "C" int hf_dev_allreduce_sum(hf_ctx *c, double *v, int n) { return allreduce_host(c, v, n, 0 /* ncclSum */); }
+/* max over the ranks (MPI_MAX of the infinity-norm residual, reference src/output.cpp:2216-2221) */
+extern "C" int hf_dev_allreduce_max(hf_ctx *c, double *v, int n) { return allreduce_host(c, v, n, 2 /* ncclMax */); }
+static int allreduce_host(hf_ctx *c, double *v, int n, int op)
 {
   if (c->nproc < 2) return 0;
   if (!c->nccl_comm) { hf_set_error("multi-rank context but hf_dev_nccl_init was not called"); return 1; }
-  if ((size_t)n * sizeof(double) > c->scratch_bytes) { hf_set_error("hf_dev_allreduce_sum: too many values"); return 1; }
+  if ((size_t)n * sizeof(double) > c->scratch_bytes) { hf_set_error("hf_dev_allreduce: too many values"); return 1; }
   HF_CUDA(cudaSetDevice(c->device));
   HF_CUDA(cudaMemcpyAsync(c->scratch, v, n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
-  HF_NCCL(g_nccl.allreduce(c->scratch, c->scratch, (size_t)n, k_nccl_float64, 0 /* ncclSum */, (nccl_comm_t)c->nccl_comm, c->stream));
+  HF_NCCL(g_nccl.allreduce(c->scratch, c->scratch, (size_t)n, k_nccl_float64, op, (nccl_comm_t)c->nccl_comm, c->stream));
   HF_CUDA(cudaMemcpyAsync(v, c->scratch, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
   HF_CUDA(cudaStreamSynchronize(c->stream));
   return 0;

@@ -481,6 +481,13 @@ void write_tec(int in_file_num, struct solution *FlowSol)
 
 void write_plot(int in_file_num, struct solution *FlowSol)
 {
+  if (run_input.equation != 0)
+  {
+    // the reference's writers index momentum / energy fields the scalar test equation does not have (out-of-bounds reads of
+    // disu_ppts_temp, src/output.cpp:730-765): there is no defined file to reproduce, so none is written
+    if (FlowSol->rank == 0) cout << "Plot files are not written for the advection-diffusion test equation." << endl;
+    return;
+  }
   if (run_input.write_type == 0) write_vtu(in_file_num, FlowSol);
   else if (run_input.write_type == 1) write_tec(in_file_num, FlowSol);
   else FatalError("ERROR: Trying to write unrecognized file format ... ");

@@ -316,6 +316,16 @@ void CalcNormResidual(struct solution *FlowSol)
   for (int i = 0; i < FlowSol->n_ele_types; i++)
     if (FlowSol->mesh_eles(i)->get_n_eles() != 0)
       n_upts_global += (long long)FlowSol->mesh_eles(i)->get_n_eles() * FlowSol->mesh_eles(i)->get_n_upts_per_ele();
+  if (FlowSol->nproc > 1)
+  {
+    // reference src/output.cpp:2216-2231: MPI_MAX (norm 0) / MPI_SUM of the per-rank sums and of the point count; every rank
+    // gets the result, so the NaN abort below fires on all of them together
+    double cnt = (double)n_upts_global;
+    if (run_input.res_norm_type == 0) hf_check(hf_dev_allreduce_max(FlowSol->ctx, sums, n_fields));
+    else hf_check(hf_dev_allreduce_sum(FlowSol->ctx, sums, n_fields));
+    hf_check(hf_dev_allreduce_sum(FlowSol->ctx, &cnt, 1));
+    n_upts_global = (long long)(cnt + 0.5);
+  }
   for (int f = 0; f < n_fields; f++)
   {
     double s = sums[f];

@@ -187,7 +187,10 @@ int hf_dev_destroy(hf_ctx *ctx);
 const char *hf_dev_last_error(void);
 /* Use an externally created CUDA stream (cudaStream_t passed as void*) as the compute stream. */
 int hf_dev_set_stream(hf_ctx *ctx, void *cuda_stream);
-/* Join an NCCL communicator: unique_id is the 128-byte ncclUniqueId produced on rank 0 by hf_dev_nccl_unique_id. */
+/* Join an NCCL communicator: unique_id is the 128-byte ncclUniqueId produced on rank 0 by hf_dev_nccl_unique_id.
+ * Collective over the ranks.  May be called before or after hf_dev_finalize_setup: whichever of the two comes second
+ * runs the cross-rank agreement of the fused path (every rank or none uses the fused kernels; LDG owner of every
+ * flux-point pair on partition faces), so both calls must be made by every rank in the same order. */
 int hf_dev_nccl_unique_id(void *unique_id_128_bytes);
 int hf_dev_nccl_init(hf_ctx *ctx, const void *unique_id_128_bytes);
 
@@ -253,6 +256,8 @@ int hf_dev_set_volume_cubature(hf_ctx *ctx, int ele_type, int n_cubpts, const do
 int hf_dev_integral_quantities(hf_ctx *ctx, int ele_type, int n_quantities, const int *kinds, double *out);
 /* sum of v[n] over the ranks of the context's communicator, in place on every rank (no-op on one rank) */
 int hf_dev_allreduce_sum(hf_ctx *ctx, double *v, int n);
+/* max of v[n] over the ranks (MPI_Reduce(MPI_MAX) of the infinity-norm residual, reference src/output.cpp:2216-2221) */
+int hf_dev_allreduce_max(hf_ctx *ctx, double *v, int n);
 int hf_dev_sync(hf_ctx *ctx);
 /* kernels launched by this context since creation (bench.py reports the delta as gpu_launches) */
 long long hf_dev_launch_count(hf_ctx *ctx);

@@ -47,6 +47,11 @@ def field_scales(b):
 def rel_err(a, b):
     """Relative error used for the 1e-12 parity bar (FP64, north_star): per field, max |a-b| / scale(field)."""
     a = np.asarray(a); b = np.asarray(b)
+    # oracle/ref_dump.cpp (adims) drops trailing singleton dimensions, e.g. n_fields = 1 of the scalar test equation
+    while a.ndim > b.ndim and a.shape[-1] == 1:
+        a = a[..., 0]
+    while b.ndim > a.ndim and b.shape[-1] == 1:
+        b = b[..., 0]
     assert a.shape == b.shape, (a.shape, b.shape)
     if np.abs(b).max() == 0:
         return np.abs(a).max()
