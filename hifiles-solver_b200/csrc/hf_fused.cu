@@ -32,6 +32,8 @@
 #include <cstdlib>
 #include <cmath>
 #include <algorithm>
+#include <map>
+#include <array>
 
 #define HF_FAIL(msg)   \
   do {                 \
@@ -123,8 +125,13 @@ struct fused_args
   double tD[36];          // D[i*N+j] = d l_j / dxi at xi_i
   double tL[2][6];        // [0]: l_i(-1), [1]: l_i(+1)
   double tc3[36], tc5[36]; // opp_3 / opp_5 entry of face f at directional index m: [f*N+m]
-  double tLD[2][6];       // generation 8: (l(s) . D)[j], the face-normal derivative of a line's face value
-  double tLc[6][2];       // generation 8: l(s) . c5[f]
+  double tLD[2][6];       // generation 9: (l(s) . D)[j], the face-normal derivative of a line's face value
+  double c5s[2][6];       // generation 9: opp_5 entries of a minus [0] / plus [1] face at directional index m (equal for the three directions, checked at setup)
+  double lc5s[2][2];      // generation 9: [face side][s] = l(s) . c5s[face side]
+  double *gn;             // generation 9: [ele][face][FB] face-normal derivative of the own polynomial at the owned flux points
+  const unsigned *cls9;   // generation 9: [ele] element class | face kinds << 20 (elements with equal owner masks and face info share a class)
+  const uint2 *tw9;       // generation 9: [class][direction][task] packed line task of every thread (order of tools/bank_layout.py)
+  const unsigned *cl9;    // generation 9: [class][CL9_WORDS] pass lists of k_face9
   const int *nidx;        // [ele][NFP] index into fu (field 0) of the neighbour's value facing each own flux point
   hf_phys P;
   rk_args rk;
@@ -316,6 +323,7 @@ __device__ __forceinline__ void riemann_fast(const double *__restrict__ u_l, con
 __device__ __forceinline__ int elem_id(const fused_args &A, int pos) { return A.elist ? A.elist[pos] : pos; }
 
 #include "hf_fused_kernels.cuh"
+#include "hf_fused9.cuh"
 
 // gather partition-face blocks into the send buffer: out[inter][block] = arr[block_of(inter)]
 __global__ void k_pack_blocks(const double *__restrict__ arr, const int *__restrict__ blk, double *__restrict__ out, int n_inters, int blk_doubles)
@@ -348,11 +356,19 @@ struct hf_fused_state
   bool elist_identity = false;
   double *out_u = nullptr, *out_g = nullptr;
   int E = 2, NT = 128;
-  bool os = false; // one-sided LDG kernels (generation 7) in use
+  bool os = false; // one-sided LDG kernels (generation 7 / 9) in use
+  bool gen9 = false; // generation 9 (k_face9 + k_resid9): face blocks of FB doubles
+  double *gn = nullptr;
+  unsigned *cls9 = nullptr, *cl9 = nullptr;
+  uint2 *tw9 = nullptr;
+  int n_classes9 = 0;
+  double c5s[2][6] = {{0}};
+  int fu_blk = 0;  // doubles per face block of fu
   int fv_blk = 0;  // doubles per face block of fv
   unsigned long long own_xor = 0;
   std::vector<unsigned long long> h_pmask; // own masks of the partition faces
   std::vector<unsigned long long> h_bmask; // host copy of bmask (partition faces may be re-decided when the communicator arrives)
+  std::vector<int> h_finfo;
   std::string os_why;
 };
 
@@ -514,6 +530,91 @@ static inline double nblk_total(int ne, int n_mpi) { return (double)ne * 6 + n_m
 
 int hf_fused_available(hf_ctx *c) { return c->fz && c->fz->available; }
 
+// line-task table of k_resid9 at P = 4: every half-warp of a line access hits 16 distinct shared-memory banks
+// generated by tools/bank_layout.py 300000; word = field | c1 << 3 | c2 << 6
+static const unsigned short lut9_p4[3][125] = {
+  // direction 0: wavefronts per 8 half-warps (volume, face minus, face plus, flipped minus, flipped plus) = [8, 8, 8, 8, 8]; natural order: [8, 15, 8, 8, 15]
+  {8, 80, 33, 73, 193, 201, 225, 195, 203, 227, 267, 283, 291, 204, 212, 220, 96, 128, 224, 25, 65, 81, 2, 18, 66, 98, 19, 131, 139, 259, 275, 260, 64, 72, 136, 9, 97, 273, 67, 75, 91, 99, 147, 155, 163, 219, 92, 132, 144, 256, 288, 17, 265, 281, 289, 10, 26, 138, 258, 266, 282, 290, 83, 140, 160, 257, 210, 218, 35, 12, 20, 28, 36, 68, 76, 148, 156, 164, 284, 292, 88, 34, 130, 146, 154, 162, 194, 202, 226, 3, 4, 100, 196, 228, 268, 276, 0, 16, 24, 32, 152, 192, 264, 272, 280, 1, 89, 209, 217, 274, 11, 27, 200, 208, 216, 129, 137, 145, 153, 161, 74, 82, 90, 211, 84},
+  // direction 1: wavefronts per 8 half-warps (volume, face minus, face plus, flipped minus, flipped plus) = [8, 10, 10, 10, 10]; natural order: [16, 8, 15, 15, 8]
+  {64, 96, 128, 256, 272, 288, 25, 257, 289, 3, 27, 35, 267, 283, 196, 228, 216, 65, 193, 201, 209, 217, 225, 281, 138, 154, 75, 91, 12, 28, 204, 220, 264, 153, 161, 10, 155, 4, 68, 76, 84, 92, 100, 132, 140, 148, 156, 164, 8, 73, 81, 2, 18, 34, 274, 131, 147, 163, 195, 203, 211, 219, 227, 291, 80, 1, 17, 33, 273, 74, 130, 146, 162, 194, 202, 210, 218, 226, 290, 139, 0, 16, 24, 32, 72, 88, 152, 160, 280, 9, 89, 26, 266, 282, 11, 284, 224, 66, 82, 98, 258, 19, 67, 83, 99, 259, 275, 20, 212, 260, 276, 292, 136, 144, 192, 200, 208, 97, 129, 137, 145, 265, 90, 36, 268},
+  // direction 2: wavefronts per 8 half-warps (volume, face minus, face plus, flipped minus, flipped plus) = [8, 11, 8, 8, 11]; natural order: [12, 15, 8, 8, 15]
+  {96, 264, 33, 273, 66, 74, 90, 210, 11, 27, 203, 267, 275, 283, 204, 220, 272, 89, 257, 10, 18, 26, 98, 130, 154, 162, 266, 274, 132, 164, 268, 276, 24, 80, 1, 17, 65, 81, 97, 137, 153, 193, 209, 225, 138, 194, 131, 259, 128, 144, 152, 160, 200, 216, 288, 73, 129, 145, 161, 217, 163, 4, 20, 156, 136, 224, 82, 67, 75, 83, 99, 139, 155, 195, 211, 219, 227, 12, 28, 140, 72, 192, 208, 9, 25, 265, 281, 2, 218, 36, 68, 84, 100, 196, 212, 228, 0, 8, 16, 32, 64, 88, 201, 146, 258, 3, 19, 35, 91, 147, 76, 292, 256, 280, 289, 34, 202, 226, 282, 290, 291, 92, 148, 260, 284},
+};
+
+// Generation 9: elements with the same owner masks and face info (rotation, side, partition flag) do the same thing at every line end.
+// One table of packed line tasks (k_resid9) and one set of pass lists (k_face9) per such class; an element only stores its class
+// (a structured block has a handful of classes; the tables stay in L2).
+template <int N>
+static void build_classes9_n(const std::vector<unsigned long long> &bmask, const std::vector<int> &finfo, unsigned long long own_xor, int ne,
+                             std::vector<unsigned> &cls, std::vector<uint2> &tw, std::vector<unsigned> &cl)
+{
+  constexpr int NN = N * N, NTASK = NF * NN;
+  const unsigned long long full = NN == 64 ? ~0ull : ((1ull << NN) - 1ull);
+  std::map<std::array<unsigned long long, 12>, int> ids;
+  cls.resize(ne);
+  for (int i = 0; i < ne; i++)
+  {
+    std::array<unsigned long long, 12> key;
+    unsigned long long own[6];
+    int info[6];
+    unsigned kinds = 0;
+    for (int f = 0; f < 6; f++)
+    {
+      own[f] = (bmask[(size_t)i * 6 + f] ^ own_xor) & full;
+      info[f] = finfo[(size_t)i * 6 + f];
+      key[f] = own[f];
+      key[6 + f] = (unsigned long long)info[f];
+      kinds |= (own[f] == 0ull ? 0u : (own[f] == full ? 1u : 2u)) << (2 * f);
+    }
+    auto it = ids.find(key);
+    int id;
+    if (it == ids.end())
+    {
+      id = (int)ids.size();
+      ids.emplace(key, id);
+      tw.resize((size_t)(id + 1) * 3 * NTASK);
+      cl.resize((size_t)(id + 1) * CL9_WORDS);
+      for (int d = 0; d < 3; d++)
+      {
+        const int fm = d == 0 ? 4 : (d == 1 ? 1 : 0), fp = d == 0 ? 2 : (d == 1 ? 3 : 5);
+        for (int t = 0; t < NTASK; t++)
+        {
+          // natural order: field-major, lines in ascending solution-point order; P = 4 takes the bank-conflict-free table
+          const int k = t / NN, l = t % NN;
+          const unsigned lut = N == 5 ? lut9_p4[d][t] : (unsigned)(k | ((l % N) << 3) | ((l / N) << 6));
+          const task9 w = make_task9<N>(d, lut, own[fm], own[fp], info[fm], info[fp]);
+          tw[((size_t)id * 3 + d) * NTASK + t] = make_uint2(w.w0, w.w1);
+        }
+      }
+      make_class_lists9<N>(own, &cl[(size_t)id * CL9_WORDS]);
+    }
+    else
+      id = it->second;
+    cls[i] = (unsigned)id | (kinds << 20);
+  }
+}
+
+static int build_classes9(hf_ctx *c, hf_fused_state *Z, const std::vector<unsigned long long> &bmask, const std::vector<int> &finfo)
+{
+  const int ne = (int)(bmask.size() / 6);
+  std::vector<unsigned> cls, cl;
+  std::vector<uint2> tw;
+  switch (c->eles[4].order + 1)
+  {
+  case 2: build_classes9_n<2>(bmask, finfo, Z->own_xor, ne, cls, tw, cl); break;
+  case 3: build_classes9_n<3>(bmask, finfo, Z->own_xor, ne, cls, tw, cl); break;
+  case 4: build_classes9_n<4>(bmask, finfo, Z->own_xor, ne, cls, tw, cl); break;
+  case 5: build_classes9_n<5>(bmask, finfo, Z->own_xor, ne, cls, tw, cl); break;
+  case 6: build_classes9_n<6>(bmask, finfo, Z->own_xor, ne, cls, tw, cl); break;
+  }
+  Z->n_classes9 = (int)(cl.size() / CL9_WORDS);
+  if (Z->n_classes9 >= (1 << 20)) { Z->gen9 = false; return 0; } // the class shares a word with the face kinds
+  if (hf_alloc_copy(c, &Z->cls9, cls.data(), cls.size())) return 1;
+  if (hf_alloc_copy(c, &Z->tw9, tw.data(), tw.size())) return 1;
+  if (hf_alloc_copy(c, &Z->cl9, cl.data(), cl.size())) return 1;
+  return 0;
+}
+
 int hf_fused_prepare(hf_ctx *c)
 {
   if (c->fz) return 0;
@@ -595,13 +696,31 @@ int hf_fused_prepare(hf_ctx *c)
   // partition face must agree on it: checked when the communicator arrives (hf_fused_after_nccl).
   Z->os = visc && fabs(c->prm.ldg_beta) == 0.5 && !getenv("HF_FUSED_GEN6");
   Z->own_xor = c->prm.ldg_beta > 0. ? (NN == 64 ? ~0ull : ((1ull << NN) - 1ull)) : 0ull;
-  Z->fv_blk = Z->os ? NF * NN : 4 * NN;
+  // generation 9 (hf_fused9.cuh): the default at P = 4 (the shape it is tuned for; HF_FUSED_GEN9=1 turns it on at any order,
+  // HF_FUSED_GEN7=1 keeps generation 7).  Its tangential pass takes the correction-function derivative per side of the line, not per
+  // face: the three directions of a hexahedron share one 1-D function, verified here on the reference's numbers.
+  {
+    bool side_uniform = visc;
+    for (int m = 0; m < N && visc; m++)
+    {
+      Z->c5s[0][m] = T.c5[4 * N + m]; // minus faces: 4 (x), 1 (y), 0 (z)
+      Z->c5s[1][m] = T.c5[2 * N + m]; // plus faces: 2 (x), 3 (y), 5 (z)
+      if (T.c5[1 * N + m] != Z->c5s[0][m] || T.c5[0 * N + m] != Z->c5s[0][m] || T.c5[3 * N + m] != Z->c5s[1][m] || T.c5[5 * N + m] != Z->c5s[1][m])
+        side_uniform = false;
+    }
+    const bool want9 = getenv("HF_FUSED_GEN9") ? atoi(getenv("HF_FUSED_GEN9")) != 0 : N == 5;
+    Z->gen9 = Z->os && side_uniform && want9 && !getenv("HF_FUSED_GEN7");
+  }
+  const int FB = (NF * NN + 1) & ~1; // generation 9: face blocks padded to an even count (16-byte aligned for the bulk copies)
+  Z->fu_blk = Z->gen9 ? FB : NF * NN;
+  Z->fv_blk = Z->gen9 ? FB : (Z->os ? NF * NN : 4 * NN);
   Z->h_bmask = bmask;
+  Z->h_finfo = finfo;
   Z->h_pmask.resize(M.n_inters);
   for (int i = 0; i < M.n_inters; i++) Z->h_pmask[i] = bmask[(size_t)M.h_ele_l[i] * 6 + M.h_loc_l[i]] ^ Z->own_xor;
   // per own flux point: where the neighbour's value of field 0 sits in fu (block * NF*NN + permuted flux point)
   std::vector<int> nidx((size_t)ne * NFP);
-  if ((double)nblk_total(ne, M.n_inters) * NF * NN > 2.0e9) return no("face arrays exceed int32 indexing");
+  if ((double)nblk_total(ne, M.n_inters) * (NF * NN + 1) > 2.0e9) return no("face arrays exceed int32 indexing");
   for (int i = 0; i < ne; i++)
     for (int f = 0; f < 6; f++)
       for (int j = 0; j < NN; j++)
@@ -619,9 +738,14 @@ int hf_fused_prepare(hf_ctx *c)
   Z->order = e.order;
   Z->n_eles = ne;
   const size_t nblk = (size_t)ne * 6 + M.n_inters;
-  if (hf_alloc_zero(c, &Z->fu[0], nblk * NF * NN)) return 1;
-  if (hf_alloc_zero(c, &Z->fu[1], nblk * NF * NN)) return 1;
-  if (visc && hf_alloc_zero(c, &Z->fv, nblk * NF * NN)) return 1;
+  if (hf_alloc_zero(c, &Z->fu[0], nblk * FB)) return 1;
+  if (hf_alloc_zero(c, &Z->fu[1], nblk * FB)) return 1;
+  if (visc && hf_alloc_zero(c, &Z->fv, nblk * FB)) return 1;
+  if (Z->gen9)
+  {
+    if (hf_alloc_zero(c, &Z->gn, (size_t)ne * 6 * FB)) return 1;
+    if (build_classes9(c, Z, bmask, finfo)) return 1;
+  }
   if (hf_alloc_copy(c, &Z->em, em.data(), em.size())) return 1;
   if (hf_alloc_copy(c, &Z->nbr, nbr.data(), nbr.size())) return 1;
   if (hf_alloc_copy(c, &Z->finfo, finfo.data(), finfo.size())) return 1;
@@ -632,8 +756,8 @@ int hf_fused_prepare(hf_ctx *c)
   if (hf_alloc_copy(c, &Z->nidx, nidx.data(), nidx.size())) return 1;
   if (M.n_inters)
   {
-    if (hf_alloc_zero(c, &Z->out_u, (size_t)M.n_inters * NF * NN)) return 1;
-    if (visc && hf_alloc_zero(c, &Z->out_g, (size_t)M.n_inters * NF * NN)) return 1;
+    if (hf_alloc_zero(c, &Z->out_u, (size_t)M.n_inters * FB)) return 1;
+    if (visc && hf_alloc_zero(c, &Z->out_g, (size_t)M.n_inters * FB)) return 1;
   }
   // host-side extracts are no longer needed
   std::vector<double>().swap(e.h_em);
@@ -681,18 +805,6 @@ int launch_all(hf_ctx *c, hf_fused_state *Z, fused_args &A, int what, int lo, in
     k_grad6<N, E, NT, MINB><<<grid, NT, smem_g, c->stream>>>(A);
   else if (what == 3)
     k_grad7<N, E, NT, MINB><<<grid, NT, sizeof(smem7<N, E>), c->stream>>>(A);
-  else if (what == 5)
-  {
-    // experimental generation-8 gradient kernel (HF_FUSED_GRAD8=1): equals k_grad7 to 1e-17 on small cases, not timed yet
-    static bool attr8 = false;
-    if (!attr8)
-    {
-      HF_CUDA(cudaFuncSetAttribute(k_grad8<N, E, NT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(smem8<N, E>)));
-      HF_CUDA(cudaFuncSetAttribute(k_grad8<N, E, NT, MINB>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-      attr8 = true;
-    }
-    k_grad8<N, E, NT, MINB><<<grid, NT, sizeof(smem8<N, E>), c->stream>>>(A);
-  }
   else if (what == 4)
   {
     hf_ktimer_begin(c);
@@ -716,8 +828,69 @@ int launch_all(hf_ctx *c, hf_fused_state *Z, fused_args &A, int what, int lo, in
   return 0;
 }
 
+// generation 9: what 5 = k_face9, 6 = k_resid9, 7 = face data of the current solution (k_resid9 in mode 2); one element per CTA
+template <int N, int NT_R, int MINB_R, int NT_F, int MINB_F>
+int launch9(hf_ctx *c, fused_args &A, int what, int lo, int hi)
+{
+  if (hi <= lo) return 0;
+  A.lo = lo;
+  A.hi = hi;
+  const int grid = hi - lo;
+  const int smem_r = (int)sizeof(smem9r<N>), smem_f = (int)sizeof(smem9f<N>);
+  static bool attr_done = false;
+  if (!attr_done)
+  {
+    HF_CUDA(cudaFuncSetAttribute(k_resid9<N, NT_R, MINB_R, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_r));
+    HF_CUDA(cudaFuncSetAttribute(k_resid9<N, NT_R, MINB_R, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_r));
+    HF_CUDA(cudaFuncSetAttribute(k_resid9<N, NT_R, MINB_R, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_r));
+    HF_CUDA(cudaFuncSetAttribute(k_face9<N, NT_F, MINB_F>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_f));
+    HF_CUDA(cudaFuncSetAttribute(k_resid9<N, NT_R, MINB_R, 0>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    HF_CUDA(cudaFuncSetAttribute(k_resid9<N, NT_R, MINB_R, 1>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    HF_CUDA(cudaFuncSetAttribute(k_face9<N, NT_F, MINB_F>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    attr_done = true;
+  }
+  if (what == 5)
+    k_face9<N, NT_F, MINB_F><<<grid, NT_F, smem_f, c->stream>>>(A);
+  else if (what == 7)
+    k_resid9<N, NT_R, MINB_R, 2><<<grid, NT_R, smem_r, c->stream>>>(A);
+  else
+  {
+    hf_ktimer_begin(c);
+    if (A.grad_out) k_resid9<N, NT_R, MINB_R, 1><<<grid, NT_R, smem_r, c->stream>>>(A);
+    else k_resid9<N, NT_R, MINB_R, 0><<<grid, NT_R, smem_r, c->stream>>>(A);
+    hf_ktimer_end(c);
+  }
+  c->launches++;
+  cudaError_t err = cudaGetLastError();
+  static const bool debug_sync = getenv("HF_DEBUG_SYNC") != nullptr;
+  if (err == cudaSuccess && debug_sync) err = cudaStreamSynchronize(c->stream);
+  if (err != cudaSuccess) { hf_set_error(std::string("fused kernel launch (generation 9, kernel ") + std::to_string(what) + "): " + cudaGetErrorString(err)); return 1; }
+  return 0;
+}
+
 int launch(hf_ctx *c, hf_fused_state *Z, fused_args &A, int what, int lo, int hi)
 {
+  if (what >= 5)
+  {
+    switch (Z->order)
+    {
+    case 1: return launch9<2, 32, 8, 32, 8>(c, A, what, lo, hi);
+    case 2: return launch9<3, 64, 8, 64, 8>(c, A, what, lo, hi);
+    case 3: return launch9<4, 96, 6, 96, 6>(c, A, what, lo, hi);
+    case 4:
+    {
+      // measurement aid: HF_FUSED_CFG9 bit 0 = five residual CTAs per SM (96 registers), bit 1 = 96-thread face kernel
+      static const int cfg9 = getenv("HF_FUSED_CFG9") ? atoi(getenv("HF_FUSED_CFG9")) : 0;
+      if (cfg9 == 1) return launch9<5, 128, 5, 128, 6>(c, A, what, lo, hi);
+      if (cfg9 == 2) return launch9<5, 128, 6, 96, 6>(c, A, what, lo, hi);
+      if (cfg9 == 3) return launch9<5, 128, 5, 96, 6>(c, A, what, lo, hi);
+      return launch9<5, 128, 6, 128, 6>(c, A, what, lo, hi);
+    }
+    case 5: return launch9<6, 192, 2, 192, 2>(c, A, what, lo, hi);
+    }
+    hf_set_error("fused path: unsupported order");
+    return 1;
+  }
   switch (Z->order)
   {
   case 1: return launch_all<2, 8, 128, 3>(c, Z, A, what, lo, hi);
@@ -729,12 +902,11 @@ int launch(hf_ctx *c, hf_fused_state *Z, fused_args &A, int what, int lo, int hi
     static const int cfg_all = getenv("HF_FUSED_CFG") ? atoi(getenv("HF_FUSED_CFG")) : 0;
     static const int cfg_g = getenv("HF_FUSED_CFG_G") ? atoi(getenv("HF_FUSED_CFG_G")) : cfg_all;
     static const int cfg_r = getenv("HF_FUSED_CFG_R") ? atoi(getenv("HF_FUSED_CFG_R")) : cfg_all;
-    int cfg = (what == 1 || what == 3 || what == 5) ? cfg_g : ((what == 2 || what == 4) ? cfg_r : cfg_all);
+    int cfg = (what == 1 || what == 3) ? cfg_g : ((what == 2 || what == 4) ? cfg_r : cfg_all);
     // measured on B200 (64^3): both generation-7 kernels are fastest with one element per CTA and six CTAs per SM (80
     // registers; k_grad7 is within 2 % of that for every shape tried, profiles/ncu_r01_summary.md)
     if (what == 4 && !getenv("HF_FUSED_CFG_R") && !getenv("HF_FUSED_CFG")) cfg = 3;
     if (what == 3 && !getenv("HF_FUSED_CFG_G") && !getenv("HF_FUSED_CFG")) cfg = 3;
-    if (what == 5 && !getenv("HF_FUSED_CFG_G") && !getenv("HF_FUSED_CFG")) cfg = 2; // 41 kB per element: five CTAs per SM fit (untuned)
     if (cfg == 1) return launch_all<5, 1, 125, 4>(c, Z, A, what, lo, hi);
     if (cfg == 2) return launch_all<5, 1, 125, 5>(c, Z, A, what, lo, hi);
     if (cfg == 3) return launch_all<5, 1, 125, 6>(c, Z, A, what, lo, hi);
@@ -779,14 +951,20 @@ void base_args(hf_ctx *c, hf_fused_state *Z, fused_args &A)
         for (int i = 0; i < N; i++) a += A.tL[s2][i] * A.tD[i * N + j];
         A.tLD[s2][j] = a;
       }
-      for (int f = 0; f < 6; f++)
+      for (int side = 0; side < 2; side++)
       {
         double a = 0.;
-        for (int i = 0; i < N; i++) a += A.tL[s2][i] * A.tc5[f * N + i];
-        A.tLc[f][s2] = a;
+        for (int i = 0; i < N; i++) a += A.tL[s2][i] * Z->c5s[side][i];
+        A.lc5s[side][s2] = a;
       }
     }
+    for (int side = 0; side < 2; side++)
+      for (int i = 0; i < N; i++) A.c5s[side][i] = Z->c5s[side][i];
   }
+  A.gn = Z->gn;
+  A.cls9 = Z->cls9;
+  A.tw9 = Z->tw9;
+  A.cl9 = Z->cl9;
   A.P = c->phys;
   A.viscous = c->prm.viscous;
   static const int pf = getenv("HF_FUSED_PF") ? atoi(getenv("HF_FUSED_PF")) : 0; // measured: no effect on B200 (the other resident CTAs already cover the staging latency)
@@ -817,9 +995,8 @@ int hf_fused_extrapolate(hf_ctx *c)
   base_args(c, Z, A);
   A.fu_next = Z->fu[Z->cur]; // fill the current buffer
   if (exchange_wait(c)) return 1; // an exchange into this buffer may still be in flight
-  if (launch(c, Z, A, 0, 0, Z->n_eles)) return 1;
-  const int NN = (Z->order + 1) * (Z->order + 1);
-  if (exchange_post(c, Z, Z->fu[Z->cur], Z->out_u, NF * NN)) return 1;
+  if (launch(c, Z, A, Z->gen9 ? 7 : 0, 0, Z->n_eles)) return 1;
+  if (exchange_post(c, Z, Z->fu[Z->cur], Z->out_u, Z->fu_blk)) return 1;
   c->ufpts_valid = true;
   return 0;
 }
@@ -831,7 +1008,6 @@ int hf_fused_stage(hf_ctx *c, int rk_stage, double time, int keep_residual, int 
   if (!Z || !Z->available) HF_FAIL("fused path not available");
   HF_CUDA(cudaSetDevice(c->device));
   if (!c->ufpts_valid && hf_fused_extrapolate(c)) return 1;
-  const int NN = (Z->order + 1) * (Z->order + 1);
   fused_args A;
   base_args(c, Z, A);
   A.keep_residual = keep_residual;
@@ -874,8 +1050,7 @@ int hf_fused_stage(hf_ctx *c, int rk_stage, double time, int keep_residual, int 
   const int ni = Z->n_interior, n = Z->n_eles;
   static const bool no_overlap = getenv("HF_NO_OVERLAP") != nullptr; // measurement aid: serialise exchange and compute
   if (no_overlap && exchange_wait(c)) return 1;
-  static const bool grad8 = getenv("HF_FUSED_GRAD8") != nullptr; // experimental generation-8 gradient kernel, see hf_fused_kernels.cuh
-  const int kg = Z->os ? (grad8 ? 5 : 3) : 1, kr = Z->os ? 4 : 2;
+  const int kg = Z->gen9 ? 5 : (Z->os ? 3 : 1), kr = Z->gen9 ? 6 : (Z->os ? 4 : 2);
   if (p.viscous)
   {
     if (launch(c, Z, A, kg, 0, ni)) return 1;
@@ -890,7 +1065,7 @@ int hf_fused_stage(hf_ctx *c, int rk_stage, double time, int keep_residual, int 
   if (do_update)
   {
     Z->cur ^= 1;
-    if (exchange_post(c, Z, Z->fu[Z->cur], Z->out_u, NF * NN)) return 1; // waited for by the next stage
+    if (exchange_post(c, Z, Z->fu[Z->cur], Z->out_u, Z->fu_blk)) return 1; // waited for by the next stage
     c->ufpts_valid = true;
   }
   return 0;
@@ -967,12 +1142,18 @@ int hf_fused_after_nccl(hf_ctx *c)
       else
         ok = 0.0;
     }
-    if (changed) HF_CUDA(cudaMemcpy(Z->bmask, Z->h_bmask.data(), Z->h_bmask.size() * sizeof(unsigned long long), cudaMemcpyHostToDevice));
+    if (changed)
+    {
+      HF_CUDA(cudaMemcpy(Z->bmask, Z->h_bmask.data(), Z->h_bmask.size() * sizeof(unsigned long long), cudaMemcpyHostToDevice));
+      if (Z->gen9 && build_classes9(c, Z, Z->h_bmask, Z->h_finfo)) return 1; // the element classes follow the owner masks
+    }
   }
   if (hf_halo_allreduce_min(c, &ok)) return 1;
   if (ok != 1.0 && Z->os)
   {
     Z->os = false;
+    Z->gen9 = false;
+    Z->fu_blk = NF * NN;
     Z->fv_blk = 4 * NN;
     Z->os_why = "the ranks of a partition face disagree on the LDG owner of a flux-point pair (rounding-level normal components) and no global element ids were given";
   }
@@ -983,6 +1164,7 @@ extern "C" const char *hf_dev_fused_variant(hf_ctx *c)
 {
   if (!c->fz || !c->fz->available) return "none";
   if (!c->prm.viscous) return "generation 6 (inviscid: k_resid6)";
+  if (c->fz->gen9) return "generation 9 (one-sided LDG: k_face9 + k_resid9)";
   if (c->fz->os) return "generation 7 (one-sided LDG: k_grad7 + k_resid7)";
   static std::string s;
   s = "generation 6 (two-sided LDG: k_grad6 + k_resid6)" + (c->fz->os_why.empty() ? std::string() : ": " + c->fz->os_why);

@@ -1025,246 +1025,3 @@ __global__ void __launch_bounds__(NT, MINB) k_resid7(const __grid_constant__ fus
   pass_FO7<N, E, NT, 1>(S, A, ne);
 }
 
-// =====================================================================================================================
-// Generation 8 of the gradient kernel (EXPERIMENTAL: written at the end of round 1 with the GPU budget all but spent; one GPU
-// run: it reproduces k_grad7 to 1e-17 after two steps on P = 1, 2, 4 cases (profiles/grad8_vs_grad7_r01.txt), but it has not been
-// timed or profiled yet and is only reachable with HF_FUSED_GRAD8=1; the task order of pass_E8 / pass_T8 was permuted after
-// that run -- which thread does which task, not what is computed -- and has not run on a GPU since).  Same contract as k_grad7 (one-sided
-// LDG: the common normal flux fc at the owned flux points), without the 15 volume gradient planes: the reference-space
-// gradient at a flux point of a face normal to direction n is
-//   normal      G_n = (l.D).u(line) + (l.c5[n+]) delta_{n+} + (l.c5[n-]) delta_{n-}        -- from the line a thread of the
-//               L pass already holds in registers, no extra loads
-//   tangential  G_t = D(q_t, :).uF(along t inside the face) + c5[t+](q_t) Delta_{t+} + c5[t-](q_t) Delta_{t-},
-//               Delta = the side face's LDG correction extrapolated along n to the shared edge  -- 5-wide line operators
-//               inside the face: N loads feed N outputs
-// (tools/face_gradient_proto.py pins the formulation against the reference's golden dumps at 1e-13.)  Why: the gather of
-// k_grad7's owned-flux-point pass reads 75 values per point at one FMA per load and is 57 % of that kernel's shared-memory
-// wavefronts, and a 64-bit LDS costs two pipe cycles however few distinct words it reads
-// (profiles/microbench/lds_multicast_b200.txt), so the lever is FP64 work per loaded double.
-template <int N, int E>
-struct smem8
-{
-  static constexpr int NN = N * N, NU = N * NN, NFP = 6 * NN, PL = E * NU, FQ = E * NFP;
-  static constexpr int PLS = PL + ((N - PL % 16) + 16) % 16;
-  double su[NF][PLS];      // solution at solution points
-  double sx[NF][FQ];       // neighbour values at the owned flux points -> LDG correction delta (0 where not owned), in place
-  double sf[NF][FQ];       // own face values
-  double gn[NF][FQ];       // reference-space gradient at the flux points, normal component
-  double gt[2][NF][FQ];    // the two tangential components (directions in ascending order)
-  double ed[NF][E][6][2][2][N]; // per face, tangential slot, side: the side face's delta extrapolated to the shared edge
-  double em[E][EM];
-  unsigned long long own[E][6];
-  int finfo[E][6];
-  int ge[E];
-  int n_owned;
-  unsigned short olist[FQ];
-};
-
-__device__ __forceinline__ int dir_minus_face(int d) { return d == 0 ? 4 : (d == 1 ? 1 : 0); }
-__device__ __forceinline__ int dir_plus_face(int d) { return d == 0 ? 2 : (d == 1 ? 3 : 5); }
-// the two directions tangential to direction n, ascending
-__device__ __forceinline__ int tan_dir(int n, int slot) { return n == 0 ? (slot ? 2 : 1) : (n == 1 ? (slot ? 2 : 0) : (slot ? 1 : 0)); }
-
-// line pass: own face values, LDG correction (kept in place of the neighbour values), normal gradient component at both ends
-template <int N, int E, int NT, int DIR, typename SM>
-__device__ __forceinline__ void pass_L8(SM &S, const fused_args &A, int ne)
-{
-  constexpr int NN = N * N, NU = N * NN, NFP = 6 * NN, stride = line_dir<N, DIR>::stride, FM = line_dir<N, DIR>::fminus, FP = line_dir<N, DIR>::fplus;
-  for (int t = threadIdx.x; t < NF * NN; t += NT)
-  {
-    int k, base, jm, jp;
-    line_task<N, DIR>(t, k, base, jm, jp);
-#pragma unroll
-    for (int e = 0; e < E; e++)
-    {
-      if (e >= ne) break;
-      const double *x = S.su[k] + e * NU + base;
-      double v[N];
-#pragma unroll
-      for (int j = 0; j < N; j++) v[j] = x[j * stride];
-      double um = A.tL[0][0] * v[0], up = A.tL[1][0] * v[0], gm = A.tLD[0][0] * v[0], gp = A.tLD[1][0] * v[0];
-#pragma unroll
-      for (int j = 1; j < N; j++)
-      {
-        um += A.tL[0][j] * v[j];
-        up += A.tL[1][j] * v[j];
-        gm += A.tLD[0][j] * v[j];
-        gp += A.tLD[1][j] * v[j];
-      }
-      const int fmq = e * NFP + FM * NN + jm, fpq = e * NFP + FP * NN + jp;
-      const double xm = S.sx[k][fmq], xp = S.sx[k][fpq];
-      const double dm = own_bit(S.own[e][FM], jm) ? xm - um : 0.;
-      const double dp = own_bit(S.own[e][FP], jp) ? xp - up : 0.;
-      S.sf[k][fmq] = um;
-      S.sf[k][fpq] = up;
-      S.sx[k][fmq] = dm;
-      S.sx[k][fpq] = dp;
-      S.gn[k][fmq] = gm + A.tLc[FP][0] * dp + A.tLc[FM][0] * dm;
-      S.gn[k][fpq] = gp + A.tLc[FP][1] * dp + A.tLc[FM][1] * dm;
-    }
-  }
-}
-
-// edge pass: for every face with owned flux points, the deltas of its four side faces extrapolated along the face's normal
-// direction to the shared edges
-template <int N, int E, int NT, typename SM>
-__device__ __forceinline__ void pass_E8(SM &S, const fused_args &A, int ne)
-{
-  constexpr int NN = N * N, NFP = 6 * NN;
-  for (int w = threadIdx.x; w < ne * 6 * 2 * 2 * N * NF; w += NT)
-  {
-    // task order (edge point, side, slot, field) inside a face, faces outermost: the 20 N tasks of a face are consecutive, so
-    // the warps of a face without owned flux points skip it as a whole
-    int r = w;
-    const int m = r % N; r /= N;
-    const int side = r % 2; r /= 2;
-    const int slot = r % 2; r /= 2;
-    const int k = r % NF; r /= NF;
-    const int F = r % 6;
-    const int e = r / 6;
-    if (S.own[e][F] == 0ull) continue;
-    const int n = face_dir(F), t = tan_dir(n, slot), o = tan_dir(n, 1 - slot);
-    const int ft = side ? dir_plus_face(t) : dir_minus_face(t);
-    const int sF = face_sgn(F) > 0 ? 1 : 0;
-    double acc = 0.;
-#pragma unroll
-    for (int i = 0; i < N; i++)
-    {
-      // solution-point coordinates of the line: i along n, 0 along t, m along the other tangential direction (no indexed
-      // local array: that would live in local memory)
-      const int ca = n == 0 ? i : (o == 0 ? m : 0), cb = n == 1 ? i : (o == 1 ? m : 0), cc = n == 2 ? i : (o == 2 ? m : 0);
-      acc += A.tL[sF][i] * S.sx[k][e * NFP + ft * NN + fpt_of_upt<N>(ft, ca, cb, cc)];
-    }
-    S.ed[k][e][F][slot][side][m] = acc;
-  }
-}
-
-// tangential pass: in-face line derivative of the face values + the two edge corrections
-template <int N, int E, int NT, typename SM>
-__device__ __forceinline__ void pass_T8(SM &S, const fused_args &A, int ne)
-{
-  constexpr int NN = N * N, NFP = 6 * NN;
-  for (int w = threadIdx.x; w < ne * 6 * 2 * N * NF; w += NT)
-  {
-    int r = w;
-    const int m = r % N; r /= N;
-    const int slot = r % 2; r /= 2;
-    const int k = r % NF; r /= NF;
-    const int F = r % 6;
-    const int e = r / 6;
-    if (S.own[e][F] == 0ull) continue;
-    const int n = face_dir(F), t = tan_dir(n, slot), o = tan_dir(n, 1 - slot);
-    const int ftm = dir_minus_face(t), ftp = dir_plus_face(t);
-    int q[N];
-    double uf[N];
-#pragma unroll
-    for (int j = 0; j < N; j++)
-    {
-      const int ca = t == 0 ? j : (o == 0 ? m : 0), cb = t == 1 ? j : (o == 1 ? m : 0), cc = t == 2 ? j : (o == 2 ? m : 0);
-      q[j] = e * NFP + F * NN + fpt_of_upt<N>(F, ca, cb, cc);
-      uf[j] = S.sf[k][q[j]];
-    }
-    const double edm = S.ed[k][e][F][slot][0][m], edp = S.ed[k][e][F][slot][1][m];
-#pragma unroll
-    for (int i = 0; i < N; i++)
-    {
-      double acc = A.tD[i * N] * uf[0];
-#pragma unroll
-      for (int j = 1; j < N; j++) acc += A.tD[i * N + j] * uf[j];
-      acc += A.tc5[ftp * N + i] * edp;
-      acc += A.tc5[ftm * N + i] * edm;
-      S.gt[slot][k][q[i]] = acc;
-    }
-  }
-}
-
-// owned flux points: gradient components from gn / gt, then as pass_GF7
-template <int N, int E, int NT, typename SM>
-__device__ __forceinline__ void pass_GF8(SM &S, const fused_args &A, int ne)
-{
-  constexpr int NN = N * N, NFP = 6 * NN;
-  (void)ne;
-  const int n_owned = S.n_owned;
-  for (int i = threadIdx.x; i < n_owned; i += NT)
-  {
-    const int q = S.olist[i];
-    const int e = q / NFP, r = q - e * NFP, f = r / NN, j = r - f * NN;
-    const int info = S.finfo[e][f];
-    const bool is_right = (info & 4) != 0;
-    const double *J = S.em[e];
-    const double idj = J[9];
-    const int n = face_dir(f);
-    double uo[NF], un[NF], fn[NF], vn[NF];
-    {
-      double g[NF * ND], fv[NF * ND];
-#pragma unroll
-      for (int k = 0; k < NF; k++)
-      {
-        uo[k] = S.sf[k][q];
-        const double an = S.gn[k][q] * idj, a0 = S.gt[0][k][q] * idj, a1 = S.gt[1][k][q] * idj;
-        const double gr0 = n == 0 ? an : a0;                    // t0 = 0 unless n = 0
-        const double gr1 = n == 1 ? an : (n == 0 ? a0 : a1);    // direction 1 is t0 for n = 0, t1 for n = 2
-        const double gr2 = n == 2 ? an : a1;                    // t1 = 2 unless n = 2
-        g[k] = gr0 * J[0] + gr1 * J[1] + gr2 * J[2];
-        g[k + 5] = gr0 * J[3] + gr1 * J[4] + gr2 * J[5];
-        g[k + 10] = gr0 * J[6] + gr1 * J[7] + gr2 * J[8];
-      }
-      vis_flux_fast(uo, g, fv, A.P);
-      const double *nrm = &S.em[e][10 + 4 * f + 1];
-      const double n0 = nrm[0], n1 = nrm[1], n2 = nrm[2];
-      vn[0] = 0.;
-#pragma unroll
-      for (int k = 1; k < NF; k++) vn[k] = fv[k] * n0 + fv[k + 5] * n1 + fv[k + 10] * n2;
-    }
-    {
-      const double *nrm = &S.em[e][10 + 4 * f + 1];
-      const double nl[3] = {nrm[0], nrm[1], nrm[2]};
-      double ul[NF], ur[NF];
-#pragma unroll
-      for (int k = 0; k < NF; k++)
-      {
-        un[k] = uo[k] + S.sx[k][q]; // the neighbour's value back from the correction (an owned point: delta = u_nbr - u_own)
-        ul[k] = is_right ? un[k] : uo[k];
-        ur[k] = is_right ? uo[k] : un[k];
-      }
-      riemann_fast(ul, ur, nl, fn, A.P);
-    }
-    const double ts = is_right ? -A.P.ldg_tau : A.P.ldg_tau;
-    fn[0] -= ts * (un[0] - uo[0]);
-#pragma unroll
-    for (int k = 1; k < NF; k++) fn[k] += vn[k] - ts * (un[k] - uo[k]);
-    double *out = A.fv + ((size_t)S.ge[e] * 6 + f) * (NF * NN) + j;
-#pragma unroll
-    for (int k = 0; k < NF; k++) out[k * NN] = fn[k];
-  }
-}
-
-template <int N, int E, int NT, int MINB>
-__global__ void __launch_bounds__(NT, MINB) k_grad8(const __grid_constant__ fused_args A)
-{
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  typedef smem8<N, E> SM;
-  SM &S = *reinterpret_cast<SM *>(smem_raw);
-  constexpr int NN = N * N, NFP = 6 * NN;
-  const int l0 = A.lo + blockIdx.x * E;
-  const int ne = min(E, A.hi - l0);
-  if (threadIdx.x == 0) S.n_owned = 0;
-  stage7<N, E, NT, false>(S, A, l0, ne);
-  // slots of flux points this element does not own are never loaded: clear them, the in-place deltas are summed over whole lines
-  cp_async_wait_all();
-  __syncthreads();
-  for (int q = threadIdx.x; q < ne * NFP; q += NT)
-  {
-    const int e = q / NFP, r = q - e * NFP, f = r / NN;
-    if (own_bit(S.own[e][f], r - f * NN)) S.olist[atomicAdd(&S.n_owned, 1)] = (unsigned short)q;
-  }
-  pass_L8<N, E, NT, 0>(S, A, ne);
-  pass_L8<N, E, NT, 1>(S, A, ne);
-  pass_L8<N, E, NT, 2>(S, A, ne);
-  __syncthreads();
-  pass_E8<N, E, NT>(S, A, ne);
-  __syncthreads();
-  pass_T8<N, E, NT>(S, A, ne);
-  __syncthreads();
-  pass_GF8<N, E, NT>(S, A, ne);
-}

@@ -38,7 +38,9 @@ def expected_variant(name):
     o = CASES[name][3]
     if not o["viscous"]:
         return "generation 6 (inviscid"
-    return "generation 7" if abs(o.get("ldg_beta", 0.5)) == 0.5 else "generation 6 (two-sided"
+    if abs(o.get("ldg_beta", 0.5)) != 0.5:
+        return "generation 6 (two-sided"
+    return "generation 9" if o["order"] == 4 else "generation 7"  # generation 9 is the default at P = 4 (hf_fused.cu)
 
 
 @pytest.mark.gpu
@@ -84,7 +86,7 @@ def test_two_sided_kernels_on_one_sided_cases(tmp_path, hb, meshgen, name, monke
     normally run generation 7, and check that the two generations agree to rounding."""
     inp = make_case(tmp_path, meshgen, name)
     with hb.Run(inp) as run:
-        assert run.fused_variant().startswith("generation 7")
+        assert run.fused_variant().startswith(("generation 7", "generation 9"))
         run.run(2, fused=True)
         u7 = run.download("hex", "disu_upts")
     monkeypatch.setenv("HF_FUSED_GEN6", "1")
@@ -132,10 +134,26 @@ def test_warped_mesh_falls_back_to_staged(tmp_path, hb, meshgen):
 
 
 @pytest.mark.gpu
-@pytest.mark.skipif(not os.environ.get("HF_TEST_GRAD8"), reason="experimental generation-8 gradient kernel: opt-in (HF_TEST_GRAD8=1) until it is validated")
-def test_experimental_grad8_matches_generation7():
-    """k_grad8 (face gradients without volume gradient planes, hf_fused_kernels.cuh) against k_grad7 on small cases"""
-    import subprocess
-    import sys
-    r = subprocess.run([sys.executable, os.path.join(util.ROOT, "tools", "grad8_check.py")], capture_output=True, text=True, timeout=600)
-    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+@pytest.mark.parametrize("name", ["hex_p1_ns_sutherland_euler", "hex_p2_ns_hllc_rk34", "hex_p2_ns_hllc_betaneg_tau", "hex_p3_ns_rusanov_rk45", "hex_p4_ns_hllc_rk34"])
+def test_generation9_at_every_order_vs_reference_and_generation7(tmp_path, hb, meshgen, name, monkeypatch):
+    """k_face9 + k_resid9 (hf_fused9.cuh) are the default at P = 4 only; HF_FUSED_GEN9=1 turns them on at any order.  Three time
+    steps against the unmodified reference, and against generation 7 (HF_FUSED_GEN7=1) which they must reproduce to rounding."""
+    inp = make_case(tmp_path, meshgen, name)
+    n_steps = 3
+    monkeypatch.setenv("HF_FUSED_GEN9", "1")
+    with hb.Run(inp) as run:
+        assert run.fused_variant().startswith("generation 9"), run.fused_variant()
+        run.run(n_steps, fused=True)
+        u9, r9, d9 = run.download("hex", "disu_upts"), run.norm_residual(), run.download("hex", "div_tconf_upts")
+    monkeypatch.delenv("HF_FUSED_GEN9")
+    monkeypatch.setenv("HF_FUSED_GEN7", "1")
+    with hb.Run(inp) as run:
+        assert run.fused_variant().startswith("generation 7"), run.fused_variant()
+        run.run(n_steps, fused=True)
+        u7 = run.download("hex", "disu_upts")
+    check("generation 9 vs 7", u9, u7, 1e-13)
+    if util.have_reference():
+        ref = util.run_reference(inp, n_steps, stagewise=False)
+        check("residual norm", r9, ref["history.norm_residual"][:, -1], TOL)
+        check("final disu_upts", u9, ref["final.hex.disu_upts"], TOL)
+        check("final div_tconf_upts", d9, ref["final.hex.div_tconf_upts"], 5e-11)
