@@ -106,73 +106,56 @@ def make_case(workdir, n, order, blocks=(1, 1, 1), **over):
     return hb, mg, inp
 
 
-def cpu_reference_rate(order, n_ref, budget_note=""):
-    """Times the UNMODIFIED reference CPU solver (oracle/_ref, serial: the reference has no threading and its MPI build
-    needs MPI + ParMETIS, absent here) on a bounded sample: TGV n_ref^3 hexes, same order and options; rate from the
-    difference between a 3-step and a 1-step run so that setup is excluded."""
-    import util
-    if not util.have_reference():
+REF_BIN = os.path.join(ROOT, "oracle", "_ref", "HiFiLES_ref")
+
+
+def _ref_time_comp(workdir, inp, env):
+    """One run of the unmodified reference binary; returns the seconds between its first and its last monitored time step, read
+    from the last column of history.plt (Time_Comp: the reference's own clock() since start, in minutes; reference
+    src/output.cpp:2403-2406, src/HiFiLES.cpp:334-335).  The difference of two rows excludes the set-up."""
+    r = subprocess.run([REF_BIN, os.path.basename(inp)], cwd=workdir, env=env, capture_output=True, text=True)
+    hist = os.path.join(workdir, "history.plt")
+    if r.returncode != 0 or not os.path.exists(hist):
         return None
-    work = tempfile.mkdtemp(prefix="hf_cpu_")
-    try:
-        _, _, inp = make_case(work, n_ref, order)
-        env = dict(os.environ, HIFILES_HOME=util.REF_DIR)
-        times = {}
-        for steps in (1, 3):
-            t0 = time.time()
-            r = subprocess.run([util.REF_DUMP, os.path.basename(inp), os.path.join(work, "o.hfd"), str(steps), "0"], cwd=work, env=env,
-                               capture_output=True, text=True)
-            times[steps] = time.time() - t0
-            if r.returncode != 0:
-                return None
-        dof = n_ref ** 3 * (order + 1) ** 3 * 5
-        sec = max(times[3] - times[1], 1e-9)
-        return dict(value=dof * 4 * 2 / sec / 1e9, seconds=sec, sample="TGV %d^3 hex P=%d, 2 time steps (8 RK stages) of the unmodified reference, serial%s"
-                    % (n_ref, order, budget_note), dof=dof)
-    finally:
-        shutil.rmtree(work, ignore_errors=True)
+    rows = [l for l in open(hist).read().splitlines() if l and l[0].isdigit()]
+    if len(rows) < 2:
+        return None
+    t = [float(l.split(",")[-1]) * 60.0 for l in rows]
+    return (t[-1] - t[0]) / (len(rows) - 1)
 
 
-def cpu_reference_rate_all_cores(order, n_ref, replicas):
-    """The reference arm's figure: `replicas` concurrent copies of the unmodified serial reference, one per host core, each
-    on its own TGV n_ref^3 domain.  The reference's only way to use several cores is its MPI + ParMETIS build (absent
-    here); concurrent serial domains are that run without the halo exchange, i.e. an upper bound for it on this host.
-    Rate = all replicas' DOF-stage updates / the slowest replica's (3-step - 1-step) time."""
+def cpu_reference_rate(order, n_ref, replicas=1):
+    """Times the UNMODIFIED reference CPU solver (oracle/_ref/HiFiLES_ref, built from /root/reference by oracle/build_ref.sh) on the
+    bounded sample SURVEY.md section 8(d) names: the Taylor-Green case on n_ref^3 hexahedra (15^3 = the size of the mesh the reference
+    ships), same order and options as the GPU workload, two time steps; seconds per step = difference of the reference's own
+    Time_Comp between the two monitored steps.  replicas > 1: that many concurrent serial runs, one per host core, each on its own
+    domain -- the reference has no threading and its MPI build needs MPI + ParMETIS (absent), so concurrent serial domains are its
+    multi-core run without the halo exchange, an upper bound for it on these cores; rate = all replicas' updates / slowest replica."""
     import util
     from concurrent.futures import ThreadPoolExecutor
-    if not util.have_reference():
+    if not (os.path.exists(REF_BIN) and util.have_reference()):
         return None
-    work = tempfile.mkdtemp(prefix="hf_cpu_all_")
+    work = tempfile.mkdtemp(prefix="hf_cpu_")
     try:
         env = dict(os.environ, HIFILES_HOME=util.REF_DIR, OMP_NUM_THREADS="1")
         dirs = []
         for r in range(replicas):
             d = os.path.join(work, "r%d" % r)
             os.makedirs(d)
-            _, _, inp = make_case(d, n_ref, order)
+            _, _, inp = make_case(d, n_ref, order, n_steps=2, monitor_res_freq=1, plot_freq=1000000, restart_dump_freq=1000000)
             dirs.append((d, inp))
-
-        def one(arg):
-            d, inp = arg
-            t = {}
-            for steps in (1, 3):
-                t0 = time.time()
-                r = subprocess.run([util.REF_DUMP, os.path.basename(inp), os.path.join(d, "o.hfd"), str(steps), "0"], cwd=d, env=env,
-                                   capture_output=True, text=True)
-                t[steps] = time.time() - t0
-                if r.returncode != 0:
-                    return None
-            return t[3] - t[1]
-
         with ThreadPoolExecutor(max_workers=replicas) as ex:
-            secs = list(ex.map(one, dirs))
+            secs = list(ex.map(lambda a: _ref_time_comp(a[0], a[1], env), dirs))
         if any(x is None for x in secs):
             return None
         dof = n_ref ** 3 * (order + 1) ** 3 * 5
         sec = max(max(secs), 1e-9)
-        return dict(value=replicas * dof * 4 * 2 / sec / 1e9, seconds=sec, dof=dof * replicas,
-                    sample="%d concurrent serial runs (one per host core) of the unmodified reference, each TGV %d^3 hex P=%d, 2 time steps "
-                           "(8 RK stages); no halo exchange, so an upper bound for the reference's MPI build on these cores" % (replicas, n_ref, order))
+        n_rk = 4
+        what = "TGV %d^3 hex P=%d, HLLC + LDG, SSP-RK34: one time step (4 RK stages) between two rows of the reference's own Time_Comp" % (n_ref, order)
+        sample = ("unmodified reference, serial: " + what) if replicas == 1 else (
+            "%d concurrent serial runs (one per host core) of the unmodified reference, each " % replicas + what +
+            "; no halo exchange, so an upper bound for the reference's MPI build on these cores")
+        return dict(value=replicas * dof * n_rk / sec / 1e9, seconds=sec, dof=dof * replicas, sample=sample)
     finally:
         shutil.rmtree(work, ignore_errors=True)
 
@@ -196,7 +179,7 @@ def run_reference_arm(args):
         return
     serial = cpu_reference_rate(args.order, args.cpu_n)
     cores = host_cores()
-    res = cpu_reference_rate_all_cores(args.order, args.cpu_n, cores) if (serial is not None and cores > 1) else serial
+    res = cpu_reference_rate(args.order, args.cpu_n, cores) if (serial is not None and cores > 1) else serial
     if res is None:
         res, cores = serial, 1
     n = args.n
@@ -207,12 +190,94 @@ def run_reference_arm(args):
         return
     cfg["sample"] = res["sample"]
     line = {"impl": "reference", "metric": "GDOF-RK-stage updates/s (TGV hex P=%d)" % args.order, "value": res["value"], "unit": "GDOF-stage/s",
-            "n_gpus": args.gpus, "steps": 2, "warmup": 0, "ms_per_step": res["seconds"] / 2 * 1e3, "higher_is_better": True, "scaling": "strong",
+            "n_gpus": args.gpus, "steps": 1, "warmup": 1, "ms_per_step": res["seconds"] * 1e3, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg,
             "cpu_baseline": {"value": res["value"], "unit": "GDOF-stage/s", "cores": cores, "kind": "reference", "sample": res["sample"],
                              "serial_value": serial["value"]},
             "e2e": {"value": res["value"], "unit": "GDOF-stage/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     print(json.dumps(line))
+
+
+def parity_gate(hb, mg, dist, rank, world, work, order):
+    """Before anything is timed: a small Taylor-Green case (8^3 elements on several GPUs, 6^3 on one; same order, fluxes and RK scheme as
+    the workload; 3 time steps) runs through the SAME kernels and halo exchange as the timed run -- on N > 1 GPUs once per partition
+    kind (bricks, METIS k-way) -- and is compared on rank 0 with the single-domain run of the fused kernels and with the unmodified
+    reference CPU solver (oracle/_ref/ref_dump).  Returns the dict that goes into the JSON line as "parity"."""
+    import numpy as np
+    import torch
+    import util
+    n, steps = (8 if world > 1 else 6), 3
+    d = os.path.join(work, "parity")
+    if rank == 0:
+        os.makedirs(d, exist_ok=True)
+    if dist is not None:
+        dist.barrier()
+    inp = None
+    if rank == 0:
+        _, _, inp = make_case(d, n, order)
+    if dist is not None:
+        dist.barrier()
+        if rank != 0:
+            _, _, inp = make_case(d, n, order)
+    nu = (order + 1) ** 3
+
+    def scaled_err(got, ref):
+        sc = np.abs(ref).reshape(-1, 5).max(0)
+        sc[1:4] = sc[1:4].max()
+        return float((np.abs(got - ref).reshape(-1, 5).max(0) / sc).max())
+
+    def gathered(part_kind):
+        part, nccl_id = None, None
+        if world > 1:
+            part = mg.block_partition(n, mg.blocks_for(world)) if part_kind == "bricks" else None
+            idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
+            if rank == 0:
+                idt = torch.tensor(list(hb.nccl_unique_id()), dtype=torch.uint8, device="cuda")
+            dist.broadcast(idt, src=0)
+            nccl_id = bytes(idt.cpu().tolist())
+        with hb.Run(inp, rank=rank, nproc=world, part=part, nccl_id=nccl_id) as run:
+            variant = run.fused_variant() if run.fused_status() == "available" else "staged: " + run.fused_status()
+            run.run(steps, fused=True)
+            u = run.download("hex", "disu_upts")
+            gid = run.host_array("hex.ele2global_ele")
+            res = run.norm_residual()
+        full = torch.zeros((n ** 3, nu, 5), dtype=torch.float64, device="cuda")
+        full[torch.from_numpy(gid.astype(np.int64)).cuda()] = torch.from_numpy(np.ascontiguousarray(u.transpose(1, 0, 2))).cuda()
+        if dist is not None:
+            dist.all_reduce(full)
+        return full.cpu().numpy(), variant, res
+
+    out = {"case": "TGV %d^3 hex P=%d, HLLC + LDG, SSP-RK34, %d time steps" % (n, order, steps), "measure": "max over fields of max|a-b| / max|b| (momentum components share a scale)"}
+    runs = {}
+    for kind in (("bricks", "metis") if world > 1 else ("none",)):
+        runs[kind] = gathered(kind)
+    if rank == 0:
+        single, ref_u, ref_res = None, None, None
+        if world > 1:
+            with hb.Run(inp) as one:
+                one.run(steps, fused=True)
+                us, gs = one.download("hex", "disu_upts"), one.host_array("hex.ele2global_ele")
+            single = np.zeros((n ** 3, nu, 5))
+            single[gs] = us.transpose(1, 0, 2)
+        if util.have_reference():
+            r = util.run_reference(inp, steps, stagewise=False)
+            ref_u = np.ascontiguousarray(r["final.hex.disu_upts"].transpose(1, 0, 2))  # the serial reference numbers its elements globally
+            ref_res = r["history.norm_residual"][:, -1]
+        for kind, (got, variant, res) in runs.items():
+            e = {"kernels": variant}
+            if single is not None:
+                e["vs_single_domain"] = scaled_err(got, single)
+            if ref_u is not None:
+                e["vs_reference"] = scaled_err(got, ref_u)
+                e["residual_norm_vs_reference"] = float(np.abs(np.asarray(res) - ref_res).max() / np.abs(ref_res).max())
+            out["partition " + kind if world > 1 else "single domain"] = e
+        worst = max([v.get("vs_reference", 0.) for v in out.values() if isinstance(v, dict)] + [v.get("vs_single_domain", 0.) for v in out.values() if isinstance(v, dict)])
+        out["max"] = worst
+        out["ok"] = bool(worst <= 1e-12)
+        out["reference"] = "oracle/_ref/ref_dump (unmodified reference CPU solver)" if ref_u is not None else "absent"
+    if dist is not None:
+        dist.barrier()
+    return out
 
 
 def main():
@@ -223,7 +288,8 @@ def main():
     ap.add_argument("--size", dest="n", type=int, default=64, help="elements per direction of the global mesh")
     ap.add_argument("--order", type=int, default=4)
     ap.add_argument("--impl", default="ours")
-    ap.add_argument("--cpu-n", type=int, default=10, help="elements per direction of the CPU baseline sample")
+    ap.add_argument("--cpu-n", type=int, default=15, help="elements per direction of the CPU baseline sample (15 = the reference's shipped TGV mesh)")
+    ap.add_argument("--no-parity", action="store_true", help="skip the parity gate (small partitioned case against single domain and reference)")
     ap.add_argument("--staged", action="store_true", help="time the staged (reference-order) kernels instead of the fused ones")
     ap.add_argument("--partition", default="bricks", choices=["bricks", "metis"], help="N > 1: brick partition of the cube, or METIS k-way of the dual graph (the reference's ParMETIS call)")
     ap.add_argument("--no-cpu", action="store_true")
@@ -269,6 +335,10 @@ def main():
             idt = torch.tensor(list(hb.nccl_unique_id()), dtype=torch.uint8, device="cuda")
         dist.broadcast(idt, src=0)
         nccl_id = bytes(idt.cpu().tolist())
+
+    parity = None
+    if not args.no_parity:
+        parity = parity_gate(hb, mg, dist, rank, world, work, args.order)
 
     t_setup = time.time()
     run = hb.Run(inp, rank=rank, nproc=world, part=part, nccl_id=nccl_id)
@@ -334,10 +404,11 @@ def main():
                     "whole_stage": {"algorithmic_bytes_per_dof_stage": stage_b,
                                     "achieved": (dof_total / world) * n_rk * args.steps / (ms * 1e-3) * stage_b / 1e9,
                                     "frac": (dof_total / world) * n_rk * args.steps / (ms * 1e-3) * stage_b / 1e9 / peak}}
-        tr = os.path.join(ROOT, "profiles", "traffic_r01.json")
+        # DRAM bytes of one k_resid launch from the ncu capture of the same command (profiles/), per element x this rank's elements
+        tr = os.path.join(ROOT, "profiles", "traffic_r02.json")
         if os.path.exists(tr):
             try:
-                roofline["traffic"] = json.load(open(tr)).get("k_resid_dram_bytes_per_launch")
+                roofline["traffic"] = json.load(open(tr))["k_resid_dram_bytes_per_element"] * n_eles
             except Exception:
                 pass
 
@@ -388,7 +459,7 @@ def main():
                        "l2": "no flush needed: state per GPU %.2f GB >> 126 MB L2" % (dof_local * 8 / 1e9), "setup_s": round(t_setup, 1),
                        "partition": ("bricks %s" % (mg.blocks_for(world),) if args.partition == "bricks" else "METIS k-way (dual graph)") if world > 1 else "none"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
-            "residual_finite": finite,
+            "residual_finite": finite, "parity": parity,
         }
         print(json.dumps(line))
     if dist is not None:

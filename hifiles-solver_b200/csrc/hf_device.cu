@@ -773,7 +773,7 @@ __global__ void k_pack_sgsf(hf_views W, int n_pairs, int nf, int NF, int ND, con
 // mode 2: r = a*r + dt*(-div/detjac); u += b*r        (RK45 / RK414), c1 = a, c2 = b
 __global__ void k_rk_update(long long n, long long n_pts, int n_upts, double *__restrict__ u0, double *__restrict__ u1, const double *__restrict__ div,
                             const double *__restrict__ detjac, const double *__restrict__ dt_local, double dt, double fac, double c1, double c2,
-                            int mode, int copy_u1)
+                            int mode, int copy_u1, int *__restrict__ nan_flag)
 {
   long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (idx >= n) return;
@@ -782,6 +782,7 @@ __global__ void k_rk_update(long long n, long long n_pts, int n_upts, double *__
   double u = u0[idx];
   if (copy_u1) u1[idx] = u;
   double r = div[idx] / detjac[p];
+  if (r != r) *nan_flag = 1 + (int)(p / n_upts);
   if (mode == 0)
     u -= dtl / fac * (r - 0.0);
   else if (mode == 1)
@@ -1106,6 +1107,9 @@ int hf_dev_create(hf_ctx **out, int device, int rank, int nproc)
   HF_CUDA(cudaEventCreate(&c->ev_t1));
   c->scratch_bytes = 1 << 20;
   if (hf_alloc_zero(c, &c->scratch, c->scratch_bytes / sizeof(double))) return 1;
+  if (hf_alloc_zero(c, &c->d_nan, 1)) return 1;
+  HF_CUDA(cudaMallocHost((void **)&c->h_nan, sizeof(int)));
+  *c->h_nan = 0;
   memset(&c->prm, 0, sizeof(c->prm));
   *out = c;
   return 0;
@@ -1128,6 +1132,7 @@ int hf_dev_destroy(hf_ctx *c)
   if (c->ev_t1) cudaEventDestroy(c->ev_t1);
   if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
   if (c->comm_stream) cudaStreamDestroy(c->comm_stream);
+  if (c->h_nan) cudaFreeHost(c->h_nan);
   delete c;
   return 0;
 }
@@ -1864,7 +1869,7 @@ static int advance_one(hf_ctx *c, hf_eles_dev &e, int stage)
     HF_FAIL("ERROR: Time integration type not recognised ... ");
   const double *dtl = (p.dt_type == 2) ? e.dt_local : nullptr;
   k_rk_update<<<hf_blocks(n, 256), 256, 0, c->stream>>>(n, n_pts, e.n_upts, e.disu_upts[0], e.disu_upts[1], e.div_tconf_upts, e.detjac_upts, dtl,
-                                                        p.dt, fac, c1, c2, mode, copy);
+                                                        p.dt, fac, c1, c2, mode, copy, c->d_nan);
   HF_LAUNCH_CHECK(c);
   c->ufpts_valid = false;
   return 0;
@@ -1904,15 +1909,36 @@ int hf_dev_rk_stage(hf_ctx *c, int rk_stage, double time, int keep_residual)
   return 0;
 }
 
+// reads the NaN flag back (all ranks agree) and fails, as the reference does, when it is set
+static int hf_check_nan(hf_ctx *c)
+{
+  HF_CUDA(cudaMemcpyAsync(c->h_nan, c->d_nan, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  HF_CUDA(cudaStreamSynchronize(c->stream));
+  double ok = *c->h_nan ? 0.0 : 1.0;
+  if (c->nproc > 1 && hf_halo_allreduce_min(c, &ok)) return 1; // every rank leaves together (a lone abort would leave the others in the next exchange)
+  if (ok == 1.0) return 0;
+  char msg[256];
+  if (*c->h_nan)
+    snprintf(msg, sizeof(msg), "Residual is NaN (element %d of rank %d, device order). Aborting...", *c->h_nan - 1, c->rank);
+  else
+    snprintf(msg, sizeof(msg), "Residual is NaN on another rank. Aborting...");
+  HF_CUDA(cudaMemsetAsync(c->d_nan, 0, sizeof(int), c->stream));
+  HF_FAIL(msg);
+}
+
 int hf_dev_run_steps(hf_ctx *c, int n_steps, double time0)
 {
   if (c->prm.dt_type != 0) HF_FAIL("hf_dev_run_steps needs a fixed time step (dt_type 0)");
   double t = time0;
+  static const bool no_guard = getenv("HF_NO_NAN_GUARD") != nullptr; // measurement aid
   for (int s = 0; s < n_steps; s++)
   {
     for (int i = 0; i < c->prm.n_rk; i++)
       if (hf_dev_rk_stage(c, i, t, (s == n_steps - 1 && i == c->prm.n_rk - 1) ? 1 : 0)) return 1;
     t += c->prm.dt;
+    // the reference scans the residual for NaN after every stage (src/eles.cpp:1781-1795); here the update kernels raise a flag and the
+    // host looks at it once per time step
+    if (!no_guard && hf_check_nan(c)) return 1;
   }
   return 0;
 }

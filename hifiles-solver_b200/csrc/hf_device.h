@@ -137,6 +137,10 @@ struct hf_ctx
   bool have_params = false;
   int fused = 1;
   bool finalized = false;
+  // NaN guard of the residual (reference src/eles.cpp:1781-1795 scans div_tconf_upts after every stage): the update kernels raise
+  // a device flag (1 + element in device order), read back once per time step
+  int *d_nan = nullptr;
+  int *h_nan = nullptr; // pinned
   bool nccl_reconciled = false; // hf_fused_after_nccl has run (needs both the communicator and the finalized setup, in either order)
   bool want_gradient = false; // integral diagnostics requested: the fused kernels also store grad_disu_upts when they keep the residual
   bool ufpts_valid = false; // disu_fpts holds opp_0 * current disu_upts(0) (fused path bookkeeping)

@@ -120,6 +120,7 @@ struct fused_args
   const int *finfo;       // [ele][6] rot + 4*is_right + 8*partition face
   const unsigned long long *bmask; // [ele][6] per face: bit j clear = own LDG weight 0.5 + beta, set = 0.5 - beta (see hf_fused_prepare)
   const double *dt_local;
+  int *nan_flag;          // raised (1 + element) when the residual of a point is NaN (reference src/eles.cpp:1781-1795)
   // 1-D operator tables of the run's order; kernel parameters live in the constant bank, so the unrolled line passes use
   // them as immediate constant operands (no registers, no shared memory)
   double tD[36];          // D[i*N+j] = d l_j / dxi at xi_i
@@ -939,6 +940,7 @@ void base_args(hf_ctx *c, hf_fused_state *Z, fused_args &A)
   A.bmask = Z->bmask;
   A.nidx = Z->nidx;
   A.dt_local = (c->prm.dt_type == 2) ? e.dt_local : nullptr;
+  A.nan_flag = c->d_nan;
   for (int i = 0; i < 36; i++) { A.tD[i] = Z->T.D[i]; A.tc3[i] = Z->T.c3[i]; A.tc5[i] = Z->T.c5[i]; }
   for (int i = 0; i < 6; i++) { A.tL[0][i] = Z->T.Lm[i]; A.tL[1][i] = Z->T.Lp[i]; }
   {

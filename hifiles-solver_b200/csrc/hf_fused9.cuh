@@ -81,11 +81,6 @@ __device__ __forceinline__ void bulk_commit_wait_read()
   asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
   asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");
 }
-// L2 prefetch of a 16-byte aligned range
-__device__ __forceinline__ void bulk_prefetch_l2(const void *src, unsigned bytes)
-{
-  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;\n" ::"l"(src), "r"(bytes) : "memory");
-}
 // generic-proxy writes to shared memory made visible to the bulk-copy (async) proxy
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
 // keeps a packed word packed: the compiler cannot look through it, so the fields are extracted where they are used instead of
@@ -147,20 +142,20 @@ struct smem9r
   double su[NUP];            // solution [field][NU]; unpadded planes (the task table takes care of the banks)
   double sg[(ND * NF * G::NU + 3) & ~1]; // [plane][NU]: reference-space gradient -> transformed flux -> divergence (planes 0..4); the y and z sets end as
                                   // staging of the published face data (16-byte aligned sub-blocks, see stage_ptr9)
-  static constexpr bool STAGE_IN_SG = 4 * G::FB <= NF * G::NU - 1; // P >= 4; lower orders get their own staging blocks
+  static constexpr bool STAGE_IN_SG = 4 * G::FB <= NF * G::NU; // P >= 4; lower orders get their own staging blocks
   double so[STAGE_IN_SG ? 2 : 8 * G::FB];
 };
 
-// where the published face data of face f is staged before its bulk store: fu of the z faces and gn of the z faces in the y set of sg
-// (dead once the y pass is through; the z pass produces them), fu of the x / y faces in sc, gn of the x / y faces in the z set (both
-// dead once the z pass is through)
+// where the published face data of face f is staged before its bulk store: the z faces (produced inside the z pass) in the common-flux
+// blocks of the x / y faces, which the x / y passes have used up; the x / y faces (produced after the z pass) in the x set (fu) and the
+// z set (gn) of sg
 template <int N, typename SM>
 __device__ __forceinline__ double *stage_ptr9(SM &S, int f, bool gn)
 {
   typedef geo9<N> G;
-  double *yset = SM::STAGE_IN_SG ? S.sg + ((NF * G::NU + 1) & ~1) : S.so, *zset = SM::STAGE_IN_SG ? S.sg + ((2 * NF * G::NU + 1) & ~1) : S.so + 4 * G::FB;
-  if (f == 0 || f == 5) return yset + ((f == 5 ? 1 : 0) + (gn ? 2 : 0)) * G::FB;
-  return gn ? zset + (f - 1) * G::FB : S.sc[f];
+  if (f == 0 || f == 5) return &S.sc[1][0] + ((f == 5 ? 1 : 0) + (gn ? 2 : 0)) * G::FB;
+  double *xset = SM::STAGE_IN_SG ? S.sg : S.so, *zset = SM::STAGE_IN_SG ? S.sg + ((2 * NF * G::NU + 1) & ~1) : S.so + 4 * G::FB;
+  return (gn ? zset : xset) + (f - 1) * G::FB;
 }
 
 // the line task of one thread: lut word = field | c1 << 3 | c2 << 6 with (c1, c2) the two coordinates of the line other than dir,
@@ -190,8 +185,9 @@ __host__ inline task9 make_task9(int dir, unsigned lut, unsigned long long own_f
 }
 
 // L pass: own face values at both ends of the line, LDG correction with the neighbour's value where this element owns the flux
-// point (weight 1, else 0), corrected reference-space derivative along the line
-template <int N, int DIR, typename SM>
+// point (weight 1, else 0), corrected reference-space derivative along the line.  WAIT: the neighbour blocks are still in flight; the
+// part that does not need them comes first
+template <int N, int DIR, bool WAIT, typename SM>
 __device__ __forceinline__ void pass_L9(SM &S, const fused_args &A, const task9 &tp)
 {
   constexpr int NU = N * N * N, stride = line_dir<N, DIR>::stride, FM = line_dir<N, DIR>::fminus, FP = line_dir<N, DIR>::fplus;
@@ -203,6 +199,15 @@ __device__ __forceinline__ void pass_L9(SM &S, const fused_args &A, const task9 
   double um = A.tL[0][0] * v[0], up = A.tL[1][0] * v[0];
 #pragma unroll
   for (int j = 1; j < N; j++) { um += A.tL[0][j] * v[j]; up += A.tL[1][j] * v[j]; }
+  double acc[N];
+#pragma unroll
+  for (int i = 0; i < N; i++)
+  {
+    acc[i] = A.tD[i * N] * v[0];
+#pragma unroll
+    for (int j = 1; j < N; j++) acc[i] += A.tD[i * N + j] * v[j];
+  }
+  if (WAIT) mbar_wait(&S.bar, 0);
   // unconditional loads (blocks of faces without owned points are never copied in: stale data, discarded by the select)
   const double xm = S.sx[FM][t.xm], xp = S.sx[FP][t.xp];
   const double dm = t.own_m ? xm - um : 0.;
@@ -211,12 +216,9 @@ __device__ __forceinline__ void pass_L9(SM &S, const fused_args &A, const task9 
 #pragma unroll
   for (int i = 0; i < N; i++)
   {
-    double acc = A.tD[i * N] * v[0];
-#pragma unroll
-    for (int j = 1; j < N; j++) acc += A.tD[i * N + j] * v[j];
-    acc += A.tc5[FP * N + i] * dp;
-    acc += A.tc5[FM * N + i] * dm;
-    o[i * stride] = acc;
+    acc[i] += A.tc5[FP * N + i] * dp;
+    acc[i] += A.tc5[FM * N + i] * dm;
+    o[i * stride] = acc[i];
   }
 }
 
@@ -265,7 +267,7 @@ __device__ __forceinline__ void pass_D9(SM &S, const fused_args &A, const task9 
   const double sm = t.neg_m ? -tm : tm, sp = t.neg_p ? -tq : tq;
   const double dm = S.sc[FM][t.cm] * sm + nm;
   const double dp = S.sc[FP][t.cp] * sp - np;
-  double *o = S.sg + t.v;
+  double *o = S.sg + (DIR == 1 ? NF * NU : 0) + t.v; // x and y passes write their own plane sets (no ordering between them), the z pass sums
   double out[N];
 #pragma unroll
   for (int i = 0; i < N; i++)
@@ -285,10 +287,11 @@ __device__ __forceinline__ void pass_D9(SM &S, const fused_args &A, const task9 
   else if (DIR == 1)
   {
 #pragma unroll
-    for (int i = 0; i < N; i++) o[i * stride] += out[i];
+    for (int i = 0; i < N; i++) o[i * stride] = out[i];
   }
   else
   {
+    const double *oy = S.sg + NF * NU + t.v;
     const double inv_detjac = S.em[9];
     const double dtl = A.dt_local ? A.dt_local[ge] : A.rk.dt;
     const double dt_fac = A.dt_local ? dtl / A.rk.fac : A.rk.dt_fac; // (dt / fac) * r, the reference's evaluation order (src/eles.cpp:1141, 1191)
@@ -298,8 +301,9 @@ __device__ __forceinline__ void pass_D9(SM &S, const fused_args &A, const task9 
 #pragma unroll
     for (int i = 0; i < N; i++)
     {
-      const double acc = o[i * stride] + out[i];
+      const double acc = (o[i * stride] + oy[i * stride]) + out[i];
       if (A.keep_residual) A.div[(size_t)(t.v % NU) + i * stride + (size_t)NU * ge + (size_t)(t.v / NU) * NU * A.n_eles] = acc;
+      if (acc != acc) *A.nan_flag = 1 + ge;
       double u = us[i * stride];
       if (A.do_update)
       {
@@ -467,7 +471,14 @@ __global__ void __launch_bounds__(NT, MINB) k_resid9(const __grid_constant__ fus
     __syncthreads(); // the solution is in; the mbarrier is initialised
     // SSP schemes: the first stage keeps the old solution in the second register (reference src/eles.cpp:1107-1117)
     if (A.do_update && A.rk.copy_u1) stage_out9<N, NT>(A.u1, S.su, A.n_eles, ge);
-    mbar_wait(&S.bar, 0);
+    if (has_task)
+    {
+      pass_L9<N, 0, true>(S, A, t0);
+      pass_L9<N, 1, false>(S, A, t1);
+      pass_L9<N, 2, false>(S, A, t2);
+    }
+    else
+      mbar_wait(&S.bar, 0);
     // mixed faces: the neighbour's common flux at the points it owns, patched into the own block (from the raw copy in sc2; a
     // third and further mixed face of one element goes through global memory)
     if (kinds & 0xaaau)
@@ -494,41 +505,7 @@ __global__ void __launch_bounds__(NT, MINB) k_resid9(const __grid_constant__ fus
         }
       }
     }
-    if (has_task)
-    {
-      pass_L9<N, 0>(S, A, t0);
-      pass_L9<N, 1>(S, A, t1);
-      pass_L9<N, 2>(S, A, t2);
-    }
     __syncthreads();
-    // L2 prefetch for the element that will run pf_dist CTAs further on (its predecessor in this SM slot): solution planes, and the
-    // face blocks it will copy in
-    if (A.pf_dist > 0 && tid >= NT - 32)
-    {
-      const int lane = tid & 31, pos = A.lo + (int)blockIdx.x + A.pf_dist;
-      if (pos < A.hi && lane < NF + 6)
-      {
-        const int pe = elem_id(A, pos);
-        if (lane < NF)
-        {
-          const char *p = (const char *)(A.u0 + (size_t)NU * (pe + (size_t)A.n_eles * lane));
-          p = (const char *)(((size_t)p + 15) & ~(size_t)15);
-          bulk_prefetch_l2(p, ((NU * 8 - 8) / 16) * 16);
-        }
-        else
-        {
-          const int f = lane - NF;
-          const unsigned pk = (__ldg(A.cls9 + pe) >> (20 + 2 * f)) & 3u;
-          const int nb = __ldg(A.nbr + (size_t)pe * 6 + f);
-          if (pk != 0u)
-          {
-            bulk_prefetch_l2(A.fu_cur + (size_t)nb * FB, FB * 8);
-            bulk_prefetch_l2(A.fv + ((size_t)pe * 6 + f) * FB, FB * 8);
-          }
-          if (pk != 1u) bulk_prefetch_l2(A.fv + (size_t)nb * FB, FB * 8);
-        }
-      }
-    }
     // the neighbour values are used up: their place takes the second RK register where the scheme reads it
     const bool need_u1 = A.do_update && ((A.rk.mode == 1 && !A.rk.copy_u1) || A.rk.mode == 2);
     if (need_u1) stage_in9<N, NT>(&S.sx[0][0], A.u1, A.n_eles, ge);
@@ -570,9 +547,11 @@ __global__ void __launch_bounds__(NT, MINB) k_resid9(const __grid_constant__ fus
         for (int l = 0; l < ND; l++) S.sg[(l * NF + k) * NU + q] = J[l] * f[k] + J[l + 3] * f[k + 5] + J[l + 6] * f[k + 10];
     }
     __syncthreads();
-    if (has_task) pass_D9<N, 0>(S, A, t0, ge);
-    __syncthreads();
-    if (has_task) pass_D9<N, 1>(S, A, t1, ge);
+    if (has_task)
+    {
+      pass_D9<N, 0>(S, A, t0, ge);
+      pass_D9<N, 1>(S, A, t1, ge);
+    }
     if (need_u1) cp_async_wait_all();
     __syncthreads();
     if (has_task) pass_D9<N, 2>(S, A, t2, ge);
@@ -733,22 +712,6 @@ __global__ void __launch_bounds__(NT, MINB) k_face9(const __grid_constant__ fuse
 #pragma unroll
           for (int k = 0; k < NF; k++) S.dl[f][k * NN + j] = d[it][k];
         }
-      }
-    }
-  }
-  if (A.pf_dist > 0 && warp == NW - 1 && lane < 6)
-  {
-    // L2 prefetch for the element that will run pf_dist CTAs further on
-    const int pos = A.lo + (int)blockIdx.x + A.pf_dist;
-    if (pos < A.hi)
-    {
-      const int pe = elem_id(A, pos);
-      if ((__ldg(A.cls9 + pe) >> (20 + 2 * lane)) & 3u)
-      {
-        const size_t ob = ((size_t)pe * 6 + lane) * FB;
-        bulk_prefetch_l2(A.fu_cur + ob, FB * 8);
-        bulk_prefetch_l2(A.gn + ob, FB * 8);
-        bulk_prefetch_l2(A.fu_cur + (size_t)__ldg(A.nbr + (size_t)pe * 6 + lane) * FB, FB * 8);
       }
     }
   }

@@ -374,6 +374,7 @@ __device__ __forceinline__ void pass_D(SM &S, const fused_args &A, int ne)
           const double acc = o[i * stride] + out[i];
           const size_t gi = gi0 + i * stride;
           if (A.keep_residual) A.div[gi] = acc;
+          if (acc != acc) *A.nan_flag = 1 + ge;
           double u = us[i * stride];
           if (A.do_update)
           {
@@ -871,6 +872,7 @@ __device__ __forceinline__ void pass_D7(SM &S, const fused_args &A, int ne)
           const double acc = o[i * stride] + out[i];
           const size_t gi = gi0 + i * stride;
           if (A.keep_residual) A.div[gi] = acc;
+          if (acc != acc) *A.nan_flag = 1 + ge;
           double u = us[i * stride];
           if (A.do_update)
           {

@@ -55,6 +55,7 @@ def main():
     u = run.download("hex", "disu_upts")
     gid = run.host_array("hex.ele2global_ele")
     n_mpi = run.n_inters("mpi", 2)
+    res_part = run.norm_residual()  # reduced over the ranks (reference src/output.cpp:2216-2231): every rank holds the global value
     run.close()
     # gather on rank 0
     nu = u.shape[0]
@@ -68,15 +69,31 @@ def main():
             single.run(steps, fused=True)
             us = single.download("hex", "disu_upts")
             gs = single.host_array("hex.ele2global_ele")
+            res_single = single.norm_residual()
         ref = np.zeros((n ** 3, nu, 5))
         ref[gs] = us.transpose(1, 0, 2)
         got = full.cpu().numpy()
-        sc = np.abs(ref).reshape(-1, 5).max(0)
-        sc[1:4] = sc[1:4].max()
-        err = (np.abs(got - ref).reshape(-1, 5).max(0) / sc).max()
-        ok = bool(err < 1e-12)
-        print("multi_gpu_check: world=%d n=%d order=%d steps=%d mode=%s [%s] partition faces on rank 0: %d  max rel err vs single domain %.3e  %s"
-              % (world, n, order, steps, mode, variant, n_mpi, err, "OK" if ok else "FAIL"))
+
+        def scaled(a, b):
+            sc = np.abs(b).reshape(-1, 5).max(0)
+            sc[1:4] = sc[1:4].max()
+            return (np.abs(a - b).reshape(-1, 5).max(0) / sc).max()
+
+        err = scaled(got, ref)
+        err_res = np.abs(np.asarray(res_part) - np.asarray(res_single)).max() / np.abs(res_single).max()
+        ok = bool(err < 1e-12 and err_res < 1e-12)
+        msg = ""
+        # and against the unmodified reference CPU solver (serial: it numbers its elements globally)
+        sys.path.insert(0, str(pathlib.Path(__file__).parent))
+        import util
+        if util.have_reference():
+            r = util.run_reference(inp, steps, stagewise=False)
+            err_ref = scaled(got, np.ascontiguousarray(r["final.hex.disu_upts"].transpose(1, 0, 2)))
+            err_ref_res = np.abs(np.asarray(res_part) - r["history.norm_residual"][:, -1]).max() / np.abs(r["history.norm_residual"][:, -1]).max()
+            ok = ok and bool(err_ref < 1e-12 and err_ref_res < 1e-12)
+            msg = "  vs reference CPU solver %.3e (residual norm %.3e)" % (err_ref, err_ref_res)
+        print("multi_gpu_check: world=%d n=%d order=%d steps=%d mode=%s [%s] partition faces on rank 0: %d  max rel err vs single domain %.3e (residual norm %.3e)%s  %s"
+              % (world, n, order, steps, mode, variant, n_mpi, err, err_res, msg, "OK" if ok else "FAIL"))
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.broadcast(flag, src=0)
     dist.barrier()

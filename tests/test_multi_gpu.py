@@ -30,6 +30,19 @@ def test_two_ranks_match_single_domain(mode):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("part", ["bricks", "metis"])
+def test_two_ranks_generation9_match_single_domain_and_reference(part):
+    """P = 4: the generation-9 kernels (k_face9 + k_resid9) with the halo exchange of their padded face blocks, brick and METIS partitions"""
+    if n_gpus() < 2:
+        pytest.skip("needs 2 GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29539", os.path.join(ROOT, "tests", "multi_gpu_check.py"), "4", "4", "2", "fused"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=dict(os.environ, HF_CHECK_PART=part))
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "OK" in r.stdout and "generation 9" in r.stdout
+
+
+@pytest.mark.gpu
 def test_two_ranks_match_single_domain_metis_partition():
     """fused kernels on a METIS k-way partition (ragged partition boundary instead of a plane)"""
     if n_gpus() < 2:

@@ -45,6 +45,21 @@ CASES = {
                                              dz_cyclic=None, bc_Cyclic_type=None, u_c_ic=600., v_c_ic=20., w_c_ic=0., p_c_ic=100000., rho_c_ic=1.2,
                                              bc_In_type="sup_in", bc_In_p_static=101000., bc_In_mach=1.8, bc_In_T_static=290., bc_In_nx=1., bc_In_ny=0.,
                                              bc_Out_type="sup_out", bc_Wall_type="slip_wall", calc_force=1, monitor_cp_freq=100000, area_ref=1.0)),
+    # the three remaining boundary kinds: density / velocity inlet with free pressure (sub_in_simp), dual-consistent slip wall
+    # (slip_wall_dual: mirrored normal velocity) -- reference src/bdy_inters.cpp:374-394, 976-995 -- inviscid and viscous
+    "quad_p3_euler_subinsimp_slipdual": ("quad", (6, 5), dict(lengths=(3., 2.), origin=(0., 0.), bcs={"x-": "In", "x+": "Out", "y-": "Wall", "y+": "Wall"}),
+                                         dict(order=3, adv_type=2, riemann_solve_type=3, viscous=0, ic_form=1, dt=1e-5, dx_cyclic=None, dy_cyclic=None,
+                                              dz_cyclic=None, bc_Cyclic_type=None, u_c_ic=100., v_c_ic=4., w_c_ic=0., p_c_ic=100000., rho_c_ic=1.2,
+                                              bc_In_type="sub_in_simp", bc_In_rho=1.21, bc_In_u=102., bc_In_v=3., bc_In_w=0.,
+                                              bc_Out_type="sub_out_simp", bc_Out_p_static=99500., bc_Wall_type="slip_wall_dual", calc_force=1, monitor_cp_freq=100000,
+                                              area_ref=1.0)),
+    "hex_p2_ns_subinsimp_slipdual": ("hex", (3, 2, 3), dict(lengths=(1.5, 1., 1.5), bcs={"x-": "In", "x+": "Out", "y-": "Cyclic", "y+": "Cyclic",
+                                                                                       "z-": "Wall", "z+": "Wall"}),
+                                     dict(order=2, adv_type=3, riemann_solve_type=0, viscous=1, ic_form=1, dt=1e-5, fix_vis=0, Mach_c_ic=0.3, nx_c_ic=1.,
+                                          ny_c_ic=0., nz_c_ic=0.05, T_c_ic=300., rho_c_ic=1.17, Mach_free_stream=0.3, rho_free_stream=1.17, T_free_stream=300.,
+                                          L_free_stream=1., dx_cyclic=None, dy_cyclic=1., dz_cyclic=None, bc_In_type="sub_in_simp", bc_In_rho=1.18,
+                                          bc_In_u=105., bc_In_v=0., bc_In_w=4., bc_Out_type="sub_out_simp", bc_Out_p_static=100000.,
+                                          bc_Wall_type="slip_wall_dual", calc_force=1, monitor_cp_freq=100000, area_ref=1.0)),
     "hex_p2_ns_wall_char_periodic": ("hex", (3, 3, 4), dict(lengths=(1., 1., 2.), bcs={"x-": "Cyclic", "x+": "Cyclic", "y-": "Cyclic", "y+": "Cyclic",
                                                                                    "z-": "Wall", "z+": "Far"}),
                                      dict(order=2, adv_type=1, riemann_solve_type=2, viscous=1, ic_form=1, dt=1e-4, Mach_c_ic=0.2, nx_c_ic=1., ny_c_ic=0.,

@@ -100,6 +100,29 @@ def test_time_steps_of_the_advection_diffusion_equation(tmp_path, hb, meshgen, n
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("gen,n,mkw", [("quad_box", (5, 4), dict(lengths=(2., 2.), origin=(-1., -1.), bcs={"x-": "Wall", "x+": "Wall", "y-": "Wall", "y+": "Wall"})),
+                                       ("hex_box", (3, 2, 3), dict(lengths=(2., 2., 2.), origin=(-1., -1., -1.),
+                                                                  bcs={"x-": "Wall", "x+": "Wall", "y-": "Cyclic", "y+": "Cyclic", "z-": "Wall", "z+": "Wall"}))])
+def test_advection_diffusion_with_dirichlet_walls(tmp_path, hb, meshgen, gen, n, mkw):
+    """ad_wall: the trivial Dirichlet boundary of the scalar test equation (u_r = 0, reference src/bdy_inters.cpp:1010-1019) on all / some sides"""
+    if not util.have_reference():
+        pytest.skip("oracle/_ref not built")
+    getattr(meshgen, gen)(str(tmp_path / "m.neu"), n, **mkw)
+    three_d = gen == "hex_box"
+    inp = meshgen.write_input(str(tmp_path / "input"), "m.neu", **dict(ADVECTION_DIFFUSION, ic_form=2, order=2, dx_cyclic=None, dy_cyclic=2. if three_d else None,
+                                                                    dz_cyclic=None, bc_Cyclic_type="cyclic" if three_d else None, bc_Wall_type="ad_wall"))
+    n_steps = 3
+    ref = util.run_reference(inp, n_steps, stagewise=False)
+    with hb.Run(inp) as run:
+        run.set_mode(False)
+        run.run(n_steps, fused=False)
+        check("residual norm", run.norm_residual(), ref["history.norm_residual"][:, -1], 1e-13)
+        for t in run.ele_types():
+            check("final disu_upts " + t, run.download(t, "disu_upts"), ref["final." + t + ".disu_upts"], 1e-13)
+            check("final div_tconf_upts " + t, run.download(t, "div_tconf_upts"), ref["final." + t + ".div_tconf_upts"], 1e-13)
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("test_case", [2, 3])
 def test_advection_diffusion_error_file_matches_reference_binary(tmp_path, hb, meshgen, test_case):
     """test_case 2 / 3: error of the solution and of its gradient against the decaying sine waves, integrated over the volume
