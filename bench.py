@@ -198,6 +198,134 @@ def run_reference_arm(args):
     print(json.dumps(line))
 
 
+# ---- the other BASELINE.json configurations (element types without fused kernels: the staged kernels run) ------------------------------
+EULER_VORTEX = dict(ic_form=0, test_case=1, dx_cyclic=20., dy_cyclic=20., dz_cyclic=None, u_c_ic=1., v_c_ic=1., w_c_ic=0., p_c_ic=1., rho_c_ic=1.)
+TWO_PI = 6.2831853071795862
+OTHER_CONFIGS = {
+    # number: (description, mesh generator, default size, CPU sample size, mesh kwargs, input options)
+    1: ("2-D Euler isentropic vortex, %s^2 quadrilaterals, P=3, Rusanov, RK45, periodic (BASELINE config 1)", "quad_box", 512, 192, {},
+        dict(order=3, adv_type=3, riemann_solve_type=0, viscous=0, dt=1e-4, **EULER_VORTEX)),
+    2: ("2-D Navier-Stokes on a mixed triangle / quadrilateral mesh (%s^2 cells, half of them split), P=3, Rusanov + LDG, SSP-RK34, periodic "
+        "(BASELINE config 2's discretisation on a synthetic periodic mesh)", "mixed_box_2d", 384, 128, dict(kind="mixed", lengths=(TWO_PI, TWO_PI), origin=(0., 0.)),
+        dict(order=3, adv_type=2, riemann_solve_type=0, viscous=1, dt=1e-6, dz_cyclic=None)),
+    4: ("3-D Navier-Stokes on a mixed prism / tetrahedron mesh (%s^3 cells), P=3, RoeM + LDG with over-integration (polynomial de-aliasing), SSP-RK34, periodic "
+        "(BASELINE config 4's discretisation on a synthetic periodic mesh)", "mixed_box_3d", 24, 10, dict(kind="pritet"),
+        dict(order=3, adv_type=2, riemann_solve_type=2, viscous=1, dt=1e-6, over_int=1, over_int_order=5)),
+}
+
+
+def make_other_case(workdir, config, n, **over):
+    hb = load_package()
+    import importlib
+    mg = importlib.import_module("hifiles_solver_b200.meshgen")
+    desc, gen, _, _, mkw, opts = OTHER_CONFIGS[config]
+    mesh = os.path.join(workdir, "cfg%d_%d.neu" % (config, n))
+    if not os.path.exists(mesh):
+        getattr(mg, gen)(mesh, n, **mkw)
+    o = dict(opts)
+    o.update(over)
+    inp = mg.write_input(os.path.join(workdir, "input_cfg%d_%d" % (config, n)), os.path.basename(mesh), **o)
+    return hb, mg, inp, desc % n
+
+
+def run_other_config(args):
+    """Configurations 1, 2, 4 on one GPU: same metric, same JSON line; the workload runs through the staged kernels (the reference's
+    method sequence, bit-exact), timed with the state resident in HBM, then end to end with host buffers; CPU baseline = the
+    unmodified reference on a bounded sample of the same configuration."""
+    import numpy as np
+    import torch
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the hot path has no CPU fallback")
+    if int(os.environ.get("WORLD_SIZE", "1")) != 1:
+        raise SystemExit("--config 1/2/4 run on one GPU")
+    cfg = args.config
+    n = args.n if args.n_given else OTHER_CONFIGS[cfg][2]
+    work = tempfile.mkdtemp(prefix="hf_bench_cfg_")
+    hb, mg, inp, desc = make_other_case(work, cfg, n)
+    t_setup = time.time()
+    run = hb.Run(inp)
+    t_setup = time.time() - t_setup
+    n_rk = int(run.scalar("n_rk"))
+    adv_type = int(run.scalar("adv_type"))
+    n_dims = int(run.scalar("n_dims"))
+    visc = int(run.scalar("viscous")) != 0
+    types = run.ele_types()
+    shapes = {t: run.download(t, "disu_upts").shape for t in types}
+    dof = float(sum(np.prod(shapes[t]) for t in types))
+    fpts = {"tri": lambda p: 3 * (p + 1), "quad": lambda p: 4 * (p + 1), "tet": lambda p: 2 * (p + 1) * (p + 2), "pri": lambda p: (p + 1) * (p + 2) + 3 * (p + 1) ** 2,
+            "hex": lambda p: 6 * (p + 1) ** 2}
+    # algorithmic bytes per DOF-stage of SURVEY.md 8(d), face term weighted over the element types by their DOF
+    bpd = sum(np.prod(shapes[t]) * BYTES_PER_DOF_STAGE["stage"](A_RK[adv_type], fpts[t](args.order_cfg) / shapes[t][0], n_dims, visc) for t in types) / dof
+
+    def sync():
+        run.sync()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        run.run(1, fused=True)
+    sync()
+    sampler = ClockSampler(0)
+    sampler.start()
+    l0 = run.launch_count()
+    run.timer_start()
+    run.run(args.steps, fused=True)
+    ms = run.timer_stop()
+    sync()
+    launches = run.launch_count() - l0
+    clocks = sampler.stop()
+    value = dof * n_rk * args.steps / (ms * 1e-3) / 1e9
+    peak, peak_src = measured_peak()
+    ach = value * bpd
+    roofline = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                "kernel": "all staged kernels of one RK stage (one kernel per reference method: operator products, point fluxes, interface fluxes, update)",
+                "algorithmic_bytes_per_dof_stage": bpd, "peak_source": peak_src,
+                "note": "the staged kernels materialise every intermediate array as the reference does; against the fused formulation's algorithmic bytes"}
+    e2e = None
+    if not args.no_e2e:
+        lib = hb.lib()
+        ids = {"tri": 0, "quad": 1, "tet": 2, "pri": 3, "hex": 4}
+        host = {t: torch.empty(int(np.prod(shapes[t])), dtype=torch.float64, pin_memory=True) for t in types}
+        ck = lambda st: (_ for _ in ()).throw(RuntimeError(lib.hf_dev_last_error().decode())) if st != 0 else None
+        for t in types:
+            ck(lib.hf_dev_download(run.ctx, ids[t], 0, ctypes.c_void_p(host[t].data_ptr()), host[t].numel()))
+        e2e_steps = max(2, min(args.steps, 5))
+        sync()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            for t in types:
+                ck(lib.hf_dev_upload(run.ctx, ids[t], 0, ctypes.c_void_p(host[t].data_ptr()), host[t].numel()))
+            run.run(1, fused=True)
+            for t in types:
+                ck(lib.hf_dev_download(run.ctx, ids[t], 0, ctypes.c_void_p(host[t].data_ptr()), host[t].numel()))
+        sync()
+        sec = time.perf_counter() - t0
+        nbytes = int(dof) * 8
+        e2e = {"value": dof * n_rk * e2e_steps / sec / 1e9, "unit": "GDOF-stage/s", "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes, "steps": e2e_steps}
+    finite = bool(np.all(np.isfinite(run.norm_residual())))
+    variant = run.fused_variant() if run.fused_status() == "available" else "staged (%s)" % run.fused_status()
+    run.close()
+    cpu = None
+    if not args.no_cpu:
+        import util
+        n_cpu = OTHER_CONFIGS[cfg][3]
+        d = os.path.join(work, "cpu")
+        os.makedirs(d)
+        _, _, cinp, cdesc = make_other_case(d, cfg, n_cpu, n_steps=2, monitor_res_freq=1)
+        sec = _ref_time_comp(d, cinp, dict(os.environ, HIFILES_HOME=util.REF_DIR)) if os.path.exists(REF_BIN) else None
+        if sec:
+            with hb.Run(cinp, host_only=True) as h:
+                cdof = float(sum(np.prod(h.host_array(t + ".disu_upts").shape) for t in h.ele_types()))
+            cpu = {"value": cdof * n_rk / sec / 1e9, "unit": "GDOF-stage/s", "cores": 1, "kind": "reference",
+                   "sample": "unmodified reference, serial: " + cdesc + "; one time step between two rows of its own Time_Comp"}
+    line = {"metric": "GDOF-RK-stage updates/s (BASELINE config %d)" % cfg, "value": value, "unit": "GDOF-stage/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": desc + "; 1 step = 1 time step = %d RK stages" % n_rk, "kernels": variant, "elements": {t: int(shapes[t][1]) for t in types}, "dof_total": dof,
+                       "l2": "no flush needed: solution %.2f GB plus the staged intermediates >> 126 MB L2" % (dof * 8 / 1e9), "setup_s": round(t_setup, 1)},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "residual_finite": finite}
+    print(json.dumps(line))
+    shutil.rmtree(work, ignore_errors=True)
+
+
 def parity_gate(hb, mg, dist, rank, world, work, order):
     """Before anything is timed: a small Taylor-Green case (8^3 elements on several GPUs, 6^3 on one; same order, fluxes and RK scheme as
     the workload; 3 time steps) runs through the SAME kernels and halo exchange as the timed run -- on N > 1 GPUs once per partition
@@ -285,7 +413,9 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--size", dest="n", type=int, default=64, help="elements per direction of the global mesh")
+    ap.add_argument("--size", dest="n", type=int, default=None, help="elements per direction of the global mesh (default 64 for config 3)")
+    ap.add_argument("--config", type=int, default=3, choices=[1, 2, 3, 4], help="BASELINE.json configuration: 3 (default) = TGV hex P=4, the headline; 1, 2, 4 = the "
+                    "quad / mixed 2-D / mixed 3-D configurations through the staged kernels, one GPU")
     ap.add_argument("--order", type=int, default=4)
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--cpu-n", type=int, default=15, help="elements per direction of the CPU baseline sample (15 = the reference's shipped TGV mesh)")
@@ -295,6 +425,14 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
+    args.n_given = args.n is not None
+    if args.n is None:
+        args.n = 64
+    if args.config != 3:
+        if args.impl == "reference":
+            raise SystemExit("--impl reference times configuration 3")
+        args.order_cfg = 3
+        return run_other_config(args)
     if args.impl == "reference":
         return run_reference_arm(args)
 

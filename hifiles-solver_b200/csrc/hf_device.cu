@@ -52,6 +52,7 @@ struct hf_ell3
   int nnz[3];
   const double *val[3];
   const int *col[3];
+  const double *dval[3]; // dense copies (null for sparse operators)
 };
 
 // out(row, c) = [out(row, c)] + sum_d sum_k E_d(row, k) * in_d(col_d(row,k), c): one running sum in ascending column
@@ -72,6 +73,84 @@ __global__ void k_op_apply(hf_ell3 E, const double *__restrict__ in, size_t in_d
     for (int k = 0; k < E.nnz[d]; k++) acc += val[(size_t)k * E.rows] * src[col[(size_t)k * E.rows]];
   }
   out[idx] = acc;
+}
+
+
+// Dense operators (triangles, tetrahedra, prisms: Dubiner-basis matrices without exact zeros) as FP64 tensor-core tiles.  The
+// product out(rows, c) = sum_d Op_d(rows, cols) in_d(cols, c) over n_cols = n_fields * n_eles columns is a batched GEMM with a tiny
+// left factor: 2 rows cols flops per 8 (rows + cols) bytes, 3 - 7 flop / byte at P = 3 -- near the FP64 : HBM balance of the B200,
+// so the kernel must neither re-read the operator per column nor spend one shared-memory load per FMA as the thread-per-output
+// kernel does.  One CTA takes 64 columns: the input tile is staged once in shared memory (coalesced), every warp owns 8-row blocks
+// of the operator and walks the k dimension in steps of 4: one operator fragment (a global load that hits L1) feeds eight
+// mma.sync.m8n8k4.f64 against eight column blocks -- 9 loads per 2 048 FMA.  The accumulation order inside a tile is the tensor
+// core's, not the reference's ascending column order, and products are fused: results differ from k_op_apply in the last bits
+// (1e-16 relative), which is why this path belongs to the fast mode (hf_dev_set_mode(ctx, 1)) and the bit-exact yardstick
+// (mode 0) keeps k_op_apply.
+constexpr int OPD_TC = 64;
+__device__ __forceinline__ void dmma884(double &d0, double &d1, double a, double b)
+{
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+template <bool ACC>
+__global__ void __launch_bounds__(128) k_op_dense_mma(hf_ell3 E, const double *__restrict__ in, size_t in_dim_stride, double *__restrict__ out, long long n_cols,
+                                                      int cols_pad)
+{
+  extern __shared__ double sm_in[]; // [E.n][OPD_TC][cols_pad], zero padded
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const long long c0 = (long long)blockIdx.x * OPD_TC;
+  const int nc = (int)min((long long)OPD_TC, n_cols - c0);
+  for (int d = 0; d < E.n; d++)
+  {
+    const double *src = in + d * in_dim_stride + c0 * E.cols;
+    double *dst = sm_in + (size_t)d * OPD_TC * cols_pad;
+    for (int i = tid; i < OPD_TC * cols_pad; i += 128)
+    {
+      const int n = i / cols_pad, k = i - n * cols_pad;
+      dst[i] = (n < nc && k < E.cols) ? src[(size_t)n * E.cols + k] : 0.0;
+    }
+  }
+  __syncthreads();
+  const int kb = (E.cols + 3) / 4, rb = (E.rows + 7) / 8;
+  const int ar = lane >> 2, ak = lane & 3; // fragment coordinates: A(row ar, k ak), B(k ak, column ar), C(row ar, columns 2 ak, 2 ak + 1)
+  for (int r = warp; r < rb; r += 4)
+  {
+    const int row = r * 8 + ar;
+    const bool row_ok = row < E.rows;
+    double acc[OPD_TC / 8][2];
+#pragma unroll
+    for (int nb = 0; nb < OPD_TC / 8; nb++)
+    {
+#pragma unroll
+      for (int h = 0; h < 2; h++)
+      {
+        const int col = nb * 8 + 2 * ak + h;
+        acc[nb][h] = (ACC && row_ok && col < nc) ? out[row + (size_t)E.rows * (c0 + col)] : 0.0;
+      }
+    }
+    for (int d = 0; d < E.n; d++)
+    {
+      const double *val = E.dval[d];
+      const double *b0 = sm_in + (size_t)d * OPD_TC * cols_pad + (size_t)ar * cols_pad + ak;
+      for (int kk = 0; kk < kb; kk++)
+      {
+        const int k = kk * 4 + ak;
+        const double a = (row_ok && k < E.cols) ? val[(size_t)k * E.rows + row] : 0.0;
+#pragma unroll
+        for (int nb = 0; nb < OPD_TC / 8; nb++) dmma884(acc[nb][0], acc[nb][1], a, b0[(size_t)nb * 8 * cols_pad + kk * 4]);
+      }
+    }
+    if (row_ok)
+    {
+#pragma unroll
+      for (int nb = 0; nb < OPD_TC / 8; nb++)
+#pragma unroll
+        for (int h = 0; h < 2; h++)
+        {
+          const int col = nb * 8 + 2 * ak + h;
+          if (col < nc) out[row + (size_t)E.rows * (c0 + col)] = acc[nb][h];
+        }
+    }
+  }
 }
 
 // Persson's modal sensor and the exponential filter, one CTA per element (reference src/eles.cpp:2918-2959 and
@@ -948,6 +1027,9 @@ static int build_ell(hf_ctx *c, hf_ell &E, const double *dense, int rows, int co
   E.rows = rows; E.cols = cols; E.nnz = nnz;
   if (hf_alloc_copy(c, &E.val, val.data(), val.size())) return 1;
   if (hf_alloc_copy(c, &E.col, col.data(), col.size())) return 1;
+  size_t filled = 0;
+  for (size_t i = 0; i < (size_t)rows * cols; i++) filled += dense[i] != 0.0;
+  if (2 * filled >= (size_t)rows * cols && hf_alloc_copy(c, &E.dval, dense, (size_t)rows * cols)) return 1;
   return 0;
 }
 
@@ -1570,7 +1652,7 @@ static hf_ell3 ell1(const hf_ell &E)
 {
   hf_ell3 r;
   memset(&r, 0, sizeof(r));
-  r.n = 1; r.rows = E.rows; r.cols = E.cols; r.nnz[0] = E.nnz; r.val[0] = E.val; r.col[0] = E.col;
+  r.n = 1; r.rows = E.rows; r.cols = E.cols; r.nnz[0] = E.nnz; r.val[0] = E.val; r.col[0] = E.col; r.dval[0] = E.dval;
   return r;
 }
 static hf_ell3 elln(const hf_ell *E, int n)
@@ -1578,13 +1660,37 @@ static hf_ell3 elln(const hf_ell *E, int n)
   hf_ell3 r;
   memset(&r, 0, sizeof(r));
   r.n = n; r.rows = E[0].rows; r.cols = E[0].cols;
-  for (int d = 0; d < n; d++) { r.nnz[d] = E[d].nnz; r.val[d] = E[d].val; r.col[d] = E[d].col; }
+  for (int d = 0; d < n; d++) { r.nnz[d] = E[d].nnz; r.val[d] = E[d].val; r.col[d] = E[d].col; r.dval[d] = E[d].dval; }
   return r;
 }
 
 static int op_apply(hf_ctx *c, const hf_ell3 &E, const double *in, size_t in_dim_stride, double *out, long long n_cols, bool acc)
 {
   long long n = (long long)E.rows * n_cols;
+  // fast mode: dense operators (no exact zero dropped from any row: simplex / prism bases) go to the tensor-core kernel
+  bool dense = c->fused != 0 && E.rows >= 8 && E.cols >= 4 && !getenv("HF_NO_DMMA");
+  for (int d = 0; d < E.n && dense; d++) dense = E.dval[d] != nullptr;
+  if (dense)
+  {
+    int cols_pad = E.cols;
+    while (cols_pad % 8 != 4) cols_pad++; // column stride = 4 (mod 8) doubles: the B fragments of a half-warp hit 16 distinct banks
+    const size_t smem = (size_t)E.n * OPD_TC * cols_pad * sizeof(double);
+    if (smem <= 160 * 1024)
+    {
+      static bool attr_done = false;
+      if (!attr_done)
+      {
+        HF_CUDA(cudaFuncSetAttribute(k_op_dense_mma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+        HF_CUDA(cudaFuncSetAttribute(k_op_dense_mma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+        attr_done = true;
+      }
+      const unsigned grid = (unsigned)((n_cols + OPD_TC - 1) / OPD_TC);
+      if (acc) k_op_dense_mma<true><<<grid, 128, smem, c->stream>>>(E, in, in_dim_stride, out, n_cols, cols_pad);
+      else k_op_dense_mma<false><<<grid, 128, smem, c->stream>>>(E, in, in_dim_stride, out, n_cols, cols_pad);
+      HF_LAUNCH_CHECK(c);
+      return 0;
+    }
+  }
   if (acc) k_op_apply<true><<<hf_blocks(n, 256), 256, 0, c->stream>>>(E, in, in_dim_stride, out, n_cols);
   else k_op_apply<false><<<hf_blocks(n, 256), 256, 0, c->stream>>>(E, in, in_dim_stride, out, n_cols);
   HF_LAUNCH_CHECK(c);

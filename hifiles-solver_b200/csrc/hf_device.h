@@ -23,6 +23,7 @@ struct hf_ell
   int rows = 0, cols = 0, nnz = 0;
   double *val = nullptr; // [nnz][rows]
   int *col = nullptr;    // [nnz][rows]; padding entries have val 0 and repeat the row's last column
+  double *dval = nullptr; // [cols][rows] with the zeros in place, kept for operators that are at least half full (tensor-core kernel of the fast mode)
 };
 
 // Per element-type view handed to kernels by value.

@@ -129,6 +129,7 @@ struct fused_args
   double tLD[2][6];       // generation 9: (l(s) . D)[j], the face-normal derivative of a line's face value
   double c5s[2][6];       // generation 9: opp_5 entries of a minus [0] / plus [1] face at directional index m (equal for the three directions, checked at setup)
   double lc5s[2][2];      // generation 9: [face side][s] = l(s) . c5s[face side]
+  double *send_u, *send_g; // generation 9: send buffers of the partition faces ([interface][FB]); the kernels fill them directly (no pack kernel)
   double *gn;             // generation 9: [ele][face][FB] face-normal derivative of the own polynomial at the owned flux points
   const unsigned *cls9;   // generation 9: [ele] element class | face kinds << 20 (elements with equal owner masks and face info share a class)
   const uint2 *tw9;       // generation 9: [class][direction][task] packed line task of every thread (order of tools/bank_layout.py)
@@ -964,6 +965,8 @@ void base_args(hf_ctx *c, hf_fused_state *Z, fused_args &A)
       for (int i = 0; i < N; i++) A.c5s[side][i] = Z->c5s[side][i];
   }
   A.gn = Z->gn;
+  A.send_u = Z->out_u;
+  A.send_g = Z->out_g;
   A.cls9 = Z->cls9;
   A.tw9 = Z->tw9;
   A.cl9 = Z->cl9;
@@ -980,9 +983,12 @@ int exchange_post(hf_ctx *c, hf_fused_state *Z, double *arr, double *out, int bl
 {
   if (Z->n_mpi == 0) return 0;
   hf_mpi_inters_dev &M = c->mpis[2];
-  long long n = (long long)Z->n_mpi * blk_doubles;
-  k_pack_blocks<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(arr, Z->mpi_blk, out, Z->n_mpi, blk_doubles);
-  c->launches++;
+  if (!Z->gen9) // generation 9 publishes partition faces straight into the send buffer
+  {
+    long long n = (long long)Z->n_mpi * blk_doubles;
+    k_pack_blocks<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(arr, Z->mpi_blk, out, Z->n_mpi, blk_doubles);
+    c->launches++;
+  }
   return hf_halo_post(c, M, out, arr + (size_t)Z->n_eles * 6 * blk_doubles, (size_t)blk_doubles);
 }
 int exchange_wait(hf_ctx *c) { return hf_halo_wait(c); }

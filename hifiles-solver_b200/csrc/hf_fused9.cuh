@@ -372,6 +372,9 @@ __device__ __forceinline__ void publish_faces9(SM &S, const fused_args &A, int g
 {
   typedef geo9<N> G;
   bulk_s2g(A.fu_next + ((size_t)ge * 6 + f) * G::FB, stage_ptr9<N>(S, f, false), G::FB * 8);
+  // a partition face (its neighbour block is a receive block behind the last element): the message goes straight into the send buffer
+  const int nb = __ldg(A.nbr + (size_t)ge * 6 + f) - 6 * A.n_eles;
+  if (nb >= 0) bulk_s2g(A.send_u + (size_t)nb * G::FB, stage_ptr9<N>(S, f, false), G::FB * 8);
   if (any_owned) bulk_s2g(A.gn + ((size_t)ge * 6 + f) * G::FB, stage_ptr9<N>(S, f, true), G::FB * 8);
   bulk_commit_wait_read();
 }
@@ -587,6 +590,7 @@ struct smem9f
   double ed[6][2][2][NF][N]; // per face, tangential slot, side: the side face's delta extrapolated along the face normal to the shared edge
   unsigned long long own[6];
   int info[6];
+  int send[6];            // partition faces: interface number (block in the send buffer), else -1
   int n_owned;
   unsigned cl[CL9_WORDS];  // the element class's pass lists
   unsigned short olist[6 * N * N];
@@ -648,6 +652,7 @@ __global__ void __launch_bounds__(NT, MINB) k_face9(const __grid_constant__ fuse
       nb = __ldg(A.nbr + (size_t)ge * 6 + lane);
       S.own[lane] = o;
       S.info[lane] = __ldg(A.finfo + (size_t)ge * 6 + lane);
+      S.send[lane] = nb - 6 * A.n_eles;
     }
     if (lane == 0)
     {
@@ -838,5 +843,11 @@ __global__ void __launch_bounds__(NT, MINB) k_face9(const __grid_constant__ fuse
     double *out = A.fv + ((size_t)ge * 6 + f) * FB + j;
 #pragma unroll
     for (int k = 0; k < NF; k++) out[k * NN] = fn[k];
+    if (S.send[f] >= 0) // partition face: the same values into the message to the neighbour rank
+    {
+      double *msg = A.send_g + (size_t)S.send[f] * FB + j;
+#pragma unroll
+      for (int k = 0; k < NF; k++) msg[k * NN] = fn[k];
+    }
   }
 }
