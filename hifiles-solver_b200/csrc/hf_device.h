@@ -142,6 +142,15 @@ struct hf_ctx
   // a device flag (1 + element in device order), read back once per time step
   int *d_nan = nullptr;
   int *h_nan = nullptr; // pinned
+  // stage timeline (measurement aid, HF_STAGE_TIMELINE=1; nsys is not available on the GPU boxes): events on the compute and the
+  // communication stream around every launch / exchange of the last recorded RK stages, read back by hf_timeline_report
+  bool tl_on = false;
+  std::vector<cudaEvent_t> tl_ev; // [slot][12]
+  int tl_stage = 0, tl_xmark = 7; // tl_xmark: which pair of marks the next exchange records (7/8 common flux, 9/10 face values)
+  // completion counters of the halo exchanges, bumped on the communication stream behind every exchange ([0] face values, [1] common
+  // flux): the generation-9 kernels wait on them inside the kernel (one launch per kernel instead of interior + halo range)
+  unsigned *d_xflag = nullptr;
+  unsigned x_posted[2] = {0, 0};
   bool nccl_reconciled = false; // hf_fused_after_nccl has run (needs both the communicator and the finalized setup, in either order)
   bool want_gradient = false; // integral diagnostics requested: the fused kernels also store grad_disu_upts when they keep the residual
   bool ufpts_valid = false; // disu_fpts holds opp_0 * current disu_upts(0) (fused path bookkeeping)
@@ -175,13 +184,14 @@ void hf_fused_destroy(hf_ctx *c);
 int hf_fused_after_nccl(hf_ctx *c);
 // halo exchange over NCCL (hf_halo.cu): buffers are [inter][...] with `per_inter` doubles per interface, the message
 // to neighbour p is the contiguous slice of its nb_count interfaces (reference src/mpi_inters.cpp:244-255)
-int hf_halo_post(hf_ctx *c, hf_mpi_inters_dev &I, const double *out, double *in, size_t per_inter);
+int hf_halo_post(hf_ctx *c, hf_mpi_inters_dev &I, const double *out, double *in, size_t per_inter, int which = -1);
 int hf_halo_wait(hf_ctx *c);
 int hf_halo_allreduce_min(hf_ctx *c, double *v);
 void hf_halo_destroy(hf_ctx *c);
 // bracket the dominant kernel: call before / after its launch (no-ops unless the kernel timer is on)
 void hf_ktimer_begin(hf_ctx *c);
 void hf_ktimer_end(hf_ctx *c);
+void hf_tl_mark(hf_ctx *c, int what, bool comm); // what 0..11, see hf_timeline_report
 
 template <typename T>
 int hf_alloc(hf_ctx *c, T **p, size_t n)

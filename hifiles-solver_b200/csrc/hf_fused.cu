@@ -120,6 +120,9 @@ struct fused_args
   const int *finfo;       // [ele][6] rot + 4*is_right + 8*partition face
   const unsigned long long *bmask; // [ele][6] per face: bit j clear = own LDG weight 0.5 + beta, set = 0.5 - beta (see hf_fused_prepare)
   const double *dt_local;
+  const unsigned *wait_flag; // generation 9, one launch per kernel: CTAs from position wait_from on (the partition-adjacent elements) wait until
+  unsigned wait_value;       // *wait_flag >= wait_value, i.e. until the exchange they read from has landed
+  int wait_from;
   int *nan_flag;          // raised (1 + element) when the residual of a point is NaN (reference src/eles.cpp:1781-1795)
   // 1-D operator tables of the run's order; kernel parameters live in the constant bank, so the unrolled line passes use
   // them as immediate constant operands (no registers, no shared memory)
@@ -979,7 +982,7 @@ void base_args(hf_ctx *c, hf_fused_state *Z, fused_args &A)
 
 // exchange the partition-face blocks of arr (blk_doubles each): pack -> ncclSend/Recv into the tail of arr, on the
 // communication stream; the compute stream carries on and calls exchange_wait before it touches the received blocks
-int exchange_post(hf_ctx *c, hf_fused_state *Z, double *arr, double *out, int blk_doubles)
+int exchange_post(hf_ctx *c, hf_fused_state *Z, double *arr, double *out, int blk_doubles, int which = -1)
 {
   if (Z->n_mpi == 0) return 0;
   hf_mpi_inters_dev &M = c->mpis[2];
@@ -989,7 +992,7 @@ int exchange_post(hf_ctx *c, hf_fused_state *Z, double *arr, double *out, int bl
     k_pack_blocks<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(arr, Z->mpi_blk, out, Z->n_mpi, blk_doubles);
     c->launches++;
   }
-  return hf_halo_post(c, M, out, arr + (size_t)Z->n_eles * 6 * blk_doubles, (size_t)blk_doubles);
+  return hf_halo_post(c, M, out, arr + (size_t)Z->n_eles * 6 * blk_doubles, (size_t)blk_doubles, which);
 }
 int exchange_wait(hf_ctx *c) { return hf_halo_wait(c); }
 } // namespace
@@ -1004,7 +1007,7 @@ int hf_fused_extrapolate(hf_ctx *c)
   A.fu_next = Z->fu[Z->cur]; // fill the current buffer
   if (exchange_wait(c)) return 1; // an exchange into this buffer may still be in flight
   if (launch(c, Z, A, Z->gen9 ? 7 : 0, 0, Z->n_eles)) return 1;
-  if (exchange_post(c, Z, Z->fu[Z->cur], Z->out_u, Z->fu_blk)) return 1;
+  if (exchange_post(c, Z, Z->fu[Z->cur], Z->out_u, Z->fu_blk, 0)) return 1;
   c->ufpts_valid = true;
   return 0;
 }
@@ -1059,23 +1062,57 @@ int hf_fused_stage(hf_ctx *c, int rk_stage, double time, int keep_residual, int 
   static const bool no_overlap = getenv("HF_NO_OVERLAP") != nullptr; // measurement aid: serialise exchange and compute
   if (no_overlap && exchange_wait(c)) return 1;
   const int kg = Z->gen9 ? 5 : (Z->os ? 3 : 1), kr = Z->gen9 ? 6 : (Z->os ? 4 : 2);
+  hf_tl_mark(c, 0, false);
+  // Generation 9 with enough interior work: ONE launch per kernel.  The partition-adjacent elements sit at the end of the launch order and
+  // wait, inside the kernel, for the completion counter of the exchange they read from (bumped on the communication stream); by the time
+  // the grid reaches them the exchange posted a kernel earlier has long landed.  Saves the drain / ramp of two extra launches per stage.
+  // Small interiors keep the two-range launches: a grid that starts with waiting CTAs could keep the NCCL kernel off the SMs.
+  static const bool no_single = getenv("HF_SPLIT_LAUNCH") != nullptr;
+  const bool single = Z->gen9 && Z->n_mpi > 0 && !no_overlap && !no_single && ni >= 4096 && c->d_xflag != nullptr;
+  if (single)
+  {
+    A.wait_flag = c->d_xflag;
+    A.wait_from = ni;
+    A.wait_value = c->x_posted[0];
+    if (launch(c, Z, A, kg, 0, n)) return 1;
+    hf_tl_mark(c, 3, false);
+    c->tl_xmark = 7;
+    if (exchange_post(c, Z, Z->fv, Z->out_g, Z->fv_blk, 1)) return 1;
+    A.wait_flag = c->d_xflag + 1;
+    A.wait_value = c->x_posted[1];
+    if (launch(c, Z, A, kr, 0, n)) return 1;
+    hf_tl_mark(c, 6, false);
+    c->tl_xmark = 9;
+  }
+  else
+  {
   if (p.viscous)
   {
     if (launch(c, Z, A, kg, 0, ni)) return 1;
+    hf_tl_mark(c, 1, false);
     if (exchange_wait(c)) return 1;
+    hf_tl_mark(c, 2, false);
     if (launch(c, Z, A, kg, ni, n)) return 1;
-    if (exchange_post(c, Z, Z->fv, Z->out_g, Z->fv_blk)) return 1;
+    hf_tl_mark(c, 3, false);
+    c->tl_xmark = 7;
+    if (exchange_post(c, Z, Z->fv, Z->out_g, Z->fv_blk, 1)) return 1;
     if (no_overlap && exchange_wait(c)) return 1;
   }
   if (launch(c, Z, A, kr, 0, ni)) return 1;
+  hf_tl_mark(c, 4, false);
   if (exchange_wait(c)) return 1;
+  hf_tl_mark(c, 5, false);
   if (launch(c, Z, A, kr, ni, n)) return 1;
+  hf_tl_mark(c, 6, false);
+  c->tl_xmark = 9;
+  }
   if (do_update)
   {
     Z->cur ^= 1;
-    if (exchange_post(c, Z, Z->fu[Z->cur], Z->out_u, Z->fu_blk)) return 1; // waited for by the next stage
+    if (exchange_post(c, Z, Z->fu[Z->cur], Z->out_u, Z->fu_blk, 0)) return 1; // waited for by the next stage
     c->ufpts_valid = true;
   }
+  c->tl_stage++;
   return 0;
 }
 

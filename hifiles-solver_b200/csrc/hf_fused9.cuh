@@ -83,6 +83,24 @@ __device__ __forceinline__ void bulk_commit_wait_read()
 }
 // generic-proxy writes to shared memory made visible to the bulk-copy (async) proxy
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
+// partition-adjacent elements of a single-launch stage: wait until the halo exchange they read from has been counted complete
+__device__ __forceinline__ void wait_exchange9(const fused_args &A)
+{
+  if (A.wait_flag != nullptr && A.lo + (int)blockIdx.x >= A.wait_from)
+  {
+    if (threadIdx.x == 0)
+    {
+      unsigned v;
+      for (;;)
+      {
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];\n" : "=r"(v) : "l"(A.wait_flag) : "memory");
+        if ((int)(v - A.wait_value) >= 0) break;
+        __nanosleep(256);
+      }
+    }
+    __syncthreads();
+  }
+}
 // keeps a packed word packed: the compiler cannot look through it, so the fields are extracted where they are used instead of
 // being hoisted into (and spilled from) two dozen registers at kernel start
 __device__ __forceinline__ unsigned opaque(unsigned x)
@@ -391,6 +409,7 @@ __global__ void __launch_bounds__(NT, MINB) k_resid9(const __grid_constant__ fus
   constexpr int NN = G::NN, NU = G::NU, FB = G::FB;
   const int tid = threadIdx.x;
   const int ge = elem_id(A, A.lo + blockIdx.x);
+  if (MODE != 2) wait_exchange9(A);
   stage_in9<N, NT>(S.su, A.u0, A.n_eles, ge);
   // element class | face kinds << 20 (2 bits per face: 0 no owned flux point, 1 all owned, 2 mixed); the thread's three line tasks
   // (one per direction) come from the class's table
@@ -640,6 +659,7 @@ __global__ void __launch_bounds__(NT, MINB) k_face9(const __grid_constant__ fuse
   static_assert(NF * N <= 32, "one lane per (field, edge point)");
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int ge = elem_id(A, A.lo + blockIdx.x);
+  wait_exchange9(A);
   // the first warp posts the bulk copies: one thread per face with owned flux points fetches the own face values, the own normal
   // derivative and the neighbour's face values
   if (warp == 0)

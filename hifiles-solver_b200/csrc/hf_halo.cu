@@ -101,12 +101,19 @@ extern "C" int hf_dev_nccl_init(hf_ctx *c, const void *unique_id_128_bytes)
   return c->finalized ? hf_fused_after_nccl(c) : 0;
 }
 
-int hf_halo_post(hf_ctx *c, hf_mpi_inters_dev &I, const double *out, double *in, size_t per_inter)
+__global__ void k_bump_flag(unsigned *flag, unsigned value)
+{
+  __threadfence_system();
+  *(volatile unsigned *)flag = value;
+}
+
+int hf_halo_post(hf_ctx *c, hf_mpi_inters_dev &I, const double *out, double *in, size_t per_inter, int which)
 {
   if (!c->nccl_comm) { hf_set_error("partition interfaces present but hf_dev_nccl_init was not called"); return 1; }
   // the pack kernel ran on the compute stream: order the exchange after it, without blocking the compute stream
   HF_CUDA(cudaEventRecord(c->ev_a, c->stream));
   HF_CUDA(cudaStreamWaitEvent(c->comm_stream, c->ev_a, 0));
+  hf_tl_mark(c, c->tl_xmark, true);
   HF_NCCL(g_nccl.group_start());
   size_t off = 0;
   int first_err = 0; // a failing send / recv must not leave the communicator inside an open group
@@ -119,6 +126,14 @@ int hf_halo_post(hf_ctx *c, hf_mpi_inters_dev &I, const double *out, double *in,
   }
   const int end_err = g_nccl.group_end();
   if (first_err || end_err) { hf_set_error(std::string("ncclSend/ncclRecv of the halo exchange: ") + g_nccl.errstr(first_err ? first_err : end_err)); return 1; }
+  hf_tl_mark(c, c->tl_xmark + 1, true);
+  if (which >= 0)
+  {
+    // the received blocks are complete once this tiny kernel runs (stream order behind the NCCL kernels): kernels already running on
+    // the compute stream see the counter move
+    if (!c->d_xflag && hf_alloc_zero(c, &c->d_xflag, 2)) return 1;
+    k_bump_flag<<<1, 1, 0, c->comm_stream>>>(c->d_xflag + which, ++c->x_posted[which]);
+  }
   HF_CUDA(cudaEventRecord(c->ev_b, c->comm_stream));
   c->halo_pending = true;
   return 0;

@@ -157,3 +157,23 @@ def test_generation9_at_every_order_vs_reference_and_generation7(tmp_path, hb, m
         check("residual norm", r9, ref["history.norm_residual"][:, -1], TOL)
         check("final disu_upts", u9, ref["final.hex.disu_upts"], TOL)
         check("final div_tconf_upts", d9, ref["final.hex.div_tconf_upts"], 5e-11)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", ["generation 9", "generation 7", "staged"])
+def test_nan_residual_stops_the_run(tmp_path, hb, meshgen, mode, monkeypatch):
+    """The reference scans div_tconf_upts for NaN after every stage and aborts ("Residual is NaN ...", src/eles.cpp:1781-1795); the
+    device kernels raise a flag that hf_dev_run_steps turns into the same failure."""
+    inp = make_case(tmp_path, meshgen, "hex_p4_ns_hllc_rk34")
+    if mode == "generation 7":
+        monkeypatch.setenv("HF_FUSED_GEN7", "1")
+    with hb.Run(inp) as run:
+        if mode == "staged":
+            run.set_mode(False)
+        else:
+            assert run.fused_variant().startswith(mode)
+        u = run.download("hex", "disu_upts")
+        u[3, 5, 0] = np.nan
+        run.upload("hex", "disu_upts", u)
+        with pytest.raises(hb.HiFiLESError, match="Residual is NaN"):
+            run.run(1, fused=mode != "staged")

@@ -43,6 +43,19 @@ def test_two_ranks_generation9_match_single_domain_and_reference(part):
 
 
 @pytest.mark.gpu
+def test_two_ranks_single_launch_stage_with_in_kernel_wait():
+    """enough interior elements (>= 4096 per rank) for the one-launch-per-kernel stage: partition-adjacent elements wait inside the
+    kernel for the exchange counter (hf_fused.cu, hf_fused9.cuh wait_exchange9)"""
+    if n_gpus() < 2:
+        pytest.skip("needs 2 GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29541", os.path.join(ROOT, "tests", "multi_gpu_check.py"), "22", "4", "1", "fused"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "OK" in r.stdout and "generation 9" in r.stdout
+
+
+@pytest.mark.gpu
 def test_two_ranks_match_single_domain_metis_partition():
     """fused kernels on a METIS k-way partition (ragged partition boundary instead of a plane)"""
     if n_gpus() < 2:
