@@ -73,6 +73,8 @@ def lib():
     L.hf_dev_run_steps.argtypes = [C.c_void_p, C.c_int, C.c_double]
     L.hf_dev_download.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_size_t]
     L.hf_dev_upload.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_size_t]
+    L.hf_dev_upload_begin.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_size_t]
+    L.hf_dev_upload_commit.argtypes = [C.c_void_p, C.c_int]
     L.hf_dev_residual_norm.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double)]
     L.hf_dev_sync.argtypes = [C.c_void_p]
     L.hf_dev_launch_count.argtypes = [C.c_void_p]
@@ -83,6 +85,8 @@ def lib():
     L.hf_dev_timer_stop.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
     L.hf_dev_fused_status.argtypes = [C.c_void_p]
     L.hf_dev_fused_status.restype = C.c_char_p
+    L.hf_dev_elem_status.argtypes = [C.c_void_p]
+    L.hf_dev_elem_status.restype = C.c_char_p
     L.hf_dev_fused_variant.argtypes = [C.c_void_p]
     L.hf_dev_fused_variant.restype = C.c_char_p
     L.hf_dev_kernel_timer.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_longlong)]
@@ -216,6 +220,18 @@ class Run:
         a = np.asfortranarray(arr, dtype=np.float64).ravel(order="F")
         self._ckd(lib().hf_dev_upload(self.ctx, ELE_TYPES[ele_type], HF_ARRAY_IDS[which], a.ctypes.data, a.size))
 
+    def upload_begin(self, ele_type, which, arr):
+        """hf_dev_upload_begin: returns the (page-locked) staging array that must stay alive until the commit has been consumed."""
+        import torch
+        a = np.asfortranarray(arr, dtype=np.float64).ravel(order="F")
+        pinned = torch.empty(a.size, dtype=torch.float64, pin_memory=True)
+        pinned.numpy()[:] = a
+        self._ckd(lib().hf_dev_upload_begin(self.ctx, ELE_TYPES[ele_type], HF_ARRAY_IDS[which], C.c_void_p(pinned.data_ptr()), a.size))
+        return pinned
+
+    def upload_commit(self, ele_type):
+        self._ckd(lib().hf_dev_upload_commit(self.ctx, ELE_TYPES[ele_type]))
+
     def eles_op(self, ele_type, op):
         self._ckd(lib().hf_dev_eles_op(self.ctx, ELE_TYPES[ele_type], ELES_OPS[op]))
 
@@ -234,6 +250,9 @@ class Run:
     def write_vtu(self, it):
         """output::write_vtu: Paraview file(s) of the current solution in the working directory"""
         self._ck(lib().hifiles_write_vtu(self._h, int(it)))
+
+    def elem_status(self):
+        return lib().hf_dev_elem_status(self.ctx).decode()
 
     def fused_variant(self):
         return lib().hf_dev_fused_variant(self.ctx).decode()

@@ -1215,9 +1215,13 @@ int hf_dev_destroy(hf_ctx *c)
   cudaDeviceSynchronize();
   hf_halo_destroy(c);
   hf_fused_destroy(c);
+  hf_elem_destroy(c);
   for (void *p : c->allocs) cudaFree(p);
   for (int t = 0; t < HF_N_ELE_TYPES; t++)
+  {
     if (c->eles[t].d_stage) cudaFree(c->eles[t].d_stage);
+    if (c->eles[t].d_xfer) cudaFree(c->eles[t].d_xfer);
+  }
   for (cudaEvent_t ev : c->kt_ev) cudaEventDestroy(ev);
   if (c->ev_a) cudaEventDestroy(c->ev_a);
   if (c->ev_b) cudaEventDestroy(c->ev_b);
@@ -1225,6 +1229,9 @@ int hf_dev_destroy(hf_ctx *c)
   if (c->ev_t1) cudaEventDestroy(c->ev_t1);
   if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
   if (c->comm_stream) cudaStreamDestroy(c->comm_stream);
+  if (c->xfer_stream) cudaStreamDestroy(c->xfer_stream);
+  if (c->ev_xfer) cudaEventDestroy(c->ev_xfer);
+  if (c->ev_xfer_free) cudaEventDestroy(c->ev_xfer_free);
   if (c->h_nan) cudaFreeHost(c->h_nan);
   delete c;
   return 0;
@@ -1454,9 +1461,12 @@ static int upload_eles_impl(hf_ctx *c, const hf_eles_desc *d)
   }
   // tdisf_upts, norm_tdisf_fpts, grad_disu_upts are only needed by the staged path: allocated lazily
   if (c->fused && hf_fused_on_upload(c, e, d)) return 1;
+  if (c->fused && hf_elem_on_upload(c, e, d)) return 1;
   return 0;
 }
 
+static int ensure_staged_buffers(hf_ctx *c, hf_eles_dev &e);
+extern "C++" int hf_ensure_staged_buffers(hf_ctx *c, hf_eles_dev &e) { return ensure_staged_buffers(c, e); }
 static int ensure_staged_buffers(hf_ctx *c, hf_eles_dev &e)
 {
   const size_t NU = (size_t)e.n_upts * e.n_eles, NFP = (size_t)e.n_fpts * e.n_eles, F = e.n_fields;
@@ -1958,10 +1968,10 @@ int hf_dev_calc_residual(hf_ctx *c, int rk_stage, double time)
   return staged_residual(c, time, rk_stage);
 }
 
-static int advance_one(hf_ctx *c, hf_eles_dev &e, int stage)
+// what one stage of the time scheme does to (u0, u1), as the parameters of k_rk_update (reference src/eles.cpp:1080-1265)
+extern "C++" int hf_rk_coeffs(hf_ctx *c, int stage, int *mode_out, int *copy_out, double *fac_out, double *c1_out, double *c2_out)
 {
   const hf_params &p = c->prm;
-  long long n_pts = (long long)e.n_upts * e.n_eles, n = n_pts * e.n_fields;
   int mode = 0, copy = 0;
   double fac = 1.0, c1 = 0., c2 = 0.;
   if (p.adv_type == 0) { mode = 0; fac = 1.0; }
@@ -1984,6 +1994,17 @@ static int advance_one(hf_ctx *c, hf_eles_dev &e, int stage)
   }
   else
     HF_FAIL("ERROR: Time integration type not recognised ... ");
+  *mode_out = mode; *copy_out = copy; *fac_out = fac; *c1_out = c1; *c2_out = c2;
+  return 0;
+}
+
+static int advance_one(hf_ctx *c, hf_eles_dev &e, int stage)
+{
+  const hf_params &p = c->prm;
+  long long n_pts = (long long)e.n_upts * e.n_eles, n = n_pts * e.n_fields;
+  int mode = 0, copy = 0;
+  double fac = 1.0, c1 = 0., c2 = 0.;
+  if (hf_rk_coeffs(c, stage, &mode, &copy, &fac, &c1, &c2)) return 1;
   const double *dtl = (p.dt_type == 2) ? e.dt_local : nullptr;
   k_rk_update<<<hf_blocks(n, 256), 256, 0, c->stream>>>(n, n_pts, e.n_upts, e.disu_upts[0], e.disu_upts[1], e.div_tconf_upts, e.detjac_upts, dtl,
                                                         p.dt, fac, c1, c2, mode, copy, c->d_nan);
@@ -2013,6 +2034,11 @@ int hf_dev_rk_stage(hf_ctx *c, int rk_stage, double time, int keep_residual)
   if (c->fused && hf_fused_available(c))
   {
     if (hf_fused_stage(c, rk_stage, time, keep_residual, 1)) return 1;
+  }
+  else if (c->fused && hf_elem_available(c))
+  {
+    // every other element type / mesh in fast mode: blocked element kernels (hf_elem.cu) around the staged interface kernels
+    if (hf_elem_stage(c, rk_stage, time, keep_residual)) return 1;
   }
   else
   {
@@ -2218,6 +2244,64 @@ int hf_dev_upload(hf_ctx *c, int ele_type, int which, const double *host, size_t
   else
     HF_CUDA(cudaMemcpyAsync(p, host, n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
   HF_CUDA(cudaStreamSynchronize(c->stream));
+  c->ufpts_valid = false;
+  return 0;
+}
+
+// Two-phase upload: the host -> device copy runs on a transfer stream while the compute stream is still busy with the previous
+// time step; hf_dev_upload_commit then orders the compute stream behind the copy and moves the data into the array (device ->
+// device, or the element permutation).  The reference's eles::cp_disu_upts_cpu_gpu (src/eles.cpp cp_* family) is synchronous; a
+// host that feeds a new state every step (the end-to-end measurement of bench.py) hides the PCIe time behind the stages this way.
+int hf_dev_upload_begin(hf_ctx *c, int ele_type, int which, const double *host, size_t n_doubles)
+{
+  HF_CUDA(cudaSetDevice(c->device));
+  if (ele_type < 0 || ele_type >= HF_N_ELE_TYPES || !c->eles[ele_type].present) HF_FAIL("element type not present on the device");
+  hf_eles_dev &e = c->eles[ele_type];
+  double *p; size_t n;
+  if (locate_array(c, e, which, &p, &n)) return 1;
+  if (n_doubles != n) HF_FAIL("upload: size mismatch");
+  if (!p) HF_FAIL("upload: array is not materialised on the device");
+  if (e.xfer_pending) HF_FAIL("hf_dev_upload_begin: the previous two-phase upload of this element type was not committed");
+  if (!c->xfer_stream)
+  {
+    HF_CUDA(cudaStreamCreateWithFlags(&c->xfer_stream, cudaStreamNonBlocking));
+    HF_CUDA(cudaEventCreateWithFlags(&c->ev_xfer, cudaEventDisableTiming));
+    HF_CUDA(cudaEventCreateWithFlags(&c->ev_xfer_free, cudaEventDisableTiming));
+  }
+  if (e.xfer_n < n)
+  {
+    if (e.d_xfer) cudaFree(e.d_xfer);
+    e.d_xfer = nullptr;
+    cudaError_t err = cudaMalloc((void **)&e.d_xfer, n * sizeof(double));
+    if (err != cudaSuccess) { hf_set_error(std::string("cudaMalloc (two-phase upload buffer): ") + cudaGetErrorString(err)); return 1; }
+    e.xfer_n = n;
+  }
+  else
+    HF_CUDA(cudaStreamWaitEvent(c->xfer_stream, c->ev_xfer_free, 0)); // the last commit has finished reading the buffer
+  HF_CUDA(cudaMemcpyAsync(e.d_xfer, host, n * sizeof(double), cudaMemcpyHostToDevice, c->xfer_stream));
+  HF_CUDA(cudaEventRecord(c->ev_xfer, c->xfer_stream));
+  e.xfer_pending = true;
+  e.xfer_which = which;
+  return 0;
+}
+
+int hf_dev_upload_commit(hf_ctx *c, int ele_type)
+{
+  HF_CUDA(cudaSetDevice(c->device));
+  if (ele_type < 0 || ele_type >= HF_N_ELE_TYPES || !c->eles[ele_type].present) HF_FAIL("element type not present on the device");
+  hf_eles_dev &e = c->eles[ele_type];
+  if (!e.xfer_pending) HF_FAIL("hf_dev_upload_commit without hf_dev_upload_begin");
+  double *p; size_t n;
+  if (locate_array(c, e, e.xfer_which, &p, &n)) return 1;
+  HF_CUDA(cudaStreamWaitEvent(c->stream, c->ev_xfer, 0));
+  if (!e.pos.empty())
+  {
+    if (permute_on_device(c, e, e.d_xfer, p, pts_per_ele(e, e.xfer_which), n, true)) return 1;
+  }
+  else
+    HF_CUDA(cudaMemcpyAsync(p, e.d_xfer, n * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+  HF_CUDA(cudaEventRecord(c->ev_xfer_free, c->stream));
+  e.xfer_pending = false;
   c->ufpts_valid = false;
   return 0;
 }

@@ -90,6 +90,10 @@ struct hf_eles_dev
   int *d_pos = nullptr;            // pos on the device
   double *d_stage = nullptr;       // staging buffer of permuted uploads / downloads
   size_t stage_n = 0;
+  double *d_xfer = nullptr;        // landing buffer of two-phase uploads (hf_dev_upload_begin / _commit)
+  size_t xfer_n = 0;
+  bool xfer_pending = false;
+  int xfer_which = 0;
   std::vector<int> pos;            // device element order: slot pos[e] holds host element e (empty = identity), hf_dev_set_element_order
 };
 
@@ -130,7 +134,8 @@ struct hf_mpi_inters_dev
 struct hf_ctx
 {
   int device = 0, rank = 0, nproc = 1;
-  cudaStream_t stream = nullptr, comm_stream = nullptr;
+  cudaStream_t stream = nullptr, comm_stream = nullptr, xfer_stream = nullptr;
+  cudaEvent_t ev_xfer = nullptr, ev_xfer_free = nullptr;
   bool own_stream = false;
   cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_t0 = nullptr, ev_t1 = nullptr;
   hf_params prm;
@@ -167,6 +172,7 @@ struct hf_ctx
   void *nccl_comm = nullptr;
   bool halo_pending = false;
   struct hf_fused_state *fz = nullptr; // fused-path state (hf_fused.cu)
+  struct hf_elem_state *ez = nullptr;  // blocked element kernels (hf_elem.cu)
   // per-launch timing of the dominant kernel (bench roofline): event pairs recorded around its launches
   bool ktimer_on = false;
   std::vector<cudaEvent_t> kt_ev; // pool, pairs
@@ -182,6 +188,15 @@ int hf_fused_extrapolate(hf_ctx *c);
 int hf_fused_on_upload(hf_ctx *c, hf_eles_dev &e, const hf_eles_desc *d);
 void hf_fused_destroy(hf_ctx *c);
 int hf_fused_after_nccl(hf_ctx *c);
+// blocked element kernels (hf_elem.cu): the fast mode of every mesh the sum-factorised hexahedron kernels do not take
+int hf_elem_on_upload(hf_ctx *c, hf_eles_dev &e, const hf_eles_desc *d);
+int hf_elem_available(hf_ctx *c);
+const char *hf_elem_status(hf_ctx *c);
+int hf_elem_stage(hf_ctx *c, int rk_stage, double time, int keep_residual);
+int hf_elem_extrapolate(hf_ctx *c);
+void hf_elem_destroy(hf_ctx *c);
+int hf_ensure_staged_buffers(hf_ctx *c, hf_eles_dev &e);
+int hf_rk_coeffs(hf_ctx *c, int stage, int *mode, int *copy, double *fac, double *c1, double *c2);
 // halo exchange over NCCL (hf_halo.cu): buffers are [inter][...] with `per_inter` doubles per interface, the message
 // to neighbour p is the contiguous slice of its nb_count interfaces (reference src/mpi_inters.cpp:244-255)
 int hf_halo_post(hf_ctx *c, hf_mpi_inters_dev &I, const double *out, double *in, size_t per_inter, int which = -1);

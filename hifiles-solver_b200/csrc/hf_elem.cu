@@ -1,0 +1,650 @@
+// Blocked element kernels: the element-local operator chain of one RK stage for EVERY element type (quadrilaterals, triangles,
+// tetrahedra, prisms, and hexahedra that the sum-factorised kernels of hf_fused.cu do not take: curved ones, meshes with boundary
+// faces), as two kernels per element type and stage instead of one kernel per reference method.
+//
+//   k_elem_grad  (viscous)   u, delta_disu_fpts -> reference-space gradient  opp_4(d) u + opp_5(d) delta   (eles::calculate_gradient +
+//                            the correction of eles::correct_gradient, reference src/eles.cpp:1823-1886, 1890-1950) -> opp_6 to the
+//                            flux points -> physical gradient with the flux-point metrics (:1990-2011) -> grad_disu_fpts
+//   k_elem_resid             u [, delta] -> gradient again (cheaper than storing it) -> physical gradient at the solution points
+//                            (:1955-1986) -> inviscid + viscous flux, transformed (evaluate_invFlux :1415-1478, evaluate_viscFlux
+//                            :2285-2392) -> divergence opp_2(d) (:1651-1725) and normal flux at the flux points opp_1(d) (:1549-1620)
+//                            -> opp_3 (common - own normal flux) (calculate_corrected_divergence :1738-1817) -> RK update
+//                            (AdvanceSolution :1080-1265) -> opp_0 of the UPDATED solution = the next stage's extrapolate_solution
+//                            (:1360-1411) -> disu_upts(0), disu_fpts
+//
+// The interface kernels in between (k_int_* / k_bdy_* / k_mpi_* of hf_device.cu: Riemann solvers, LDG, the twelve boundary kinds,
+// wall model, halo exchange) are the staged ones, unchanged: they read disu_fpts / grad_disu_fpts and write norm_tconf_fpts /
+// delta_disu_fpts.  What disappears is every element-local intermediate array of the reference (tdisf_upts, grad_disu_upts,
+// norm_tdisf_fpts, div_tconf_upts: SURVEY §8a rows a4-a6, a9-a12, a15, a16 in two launches).
+//
+// One CTA takes a tile of E elements: NC = E * n_fields columns of every array live in shared memory as [column][point] with a
+// column stride = 4 (mod 8) doubles.  Every small-operator product is a batched contraction on the FP64 tensor cores
+// (mma.sync.m8n8k4.f64): the DATA tile is the A operand (8 columns x 4 points, read from shared memory without bank conflicts), the
+// OPERATOR is the B operand, stored on the host in fragment order (one coalesced 256-byte read per k-step, L1-resident, zero padding
+// baked in), and a lane's two results are neighbouring points of one column (one 16-byte shared-memory store).  A warp task is one
+// block of 8 operator rows against CG column blocks, the tasks of all products of a phase are pooled over the CTA's warps.
+// Accumulation order is the tensor core's and products are fused, so results differ from the reference's ascending dgemm sums in
+// the last bits (1e-15 relative): this is the fast mode (hf_dev_set_mode(ctx, 1)); mode 0 keeps the bit-exact staged kernels.
+#include "hf_device.h"
+#include <cstdlib>
+#include <cstring>
+
+namespace
+{
+constexpr int EL_THREADS = 256;
+constexpr int EL_CG = 2; // column blocks per warp task (they share the operator fragment)
+
+struct el_term
+{
+  const double *op; // operator in fragment order: [row block][k step][lane]
+  int kb;           // k steps (4 points each)
+  int src, ss;      // shared-memory offset and column stride of the data (doubles)
+};
+struct el_prod
+{
+  el_term t[4];
+  int n_terms, rb; // row blocks of 8
+  int dst, ds;     // shared-memory offset and column stride of the result
+  int mode;        // 0 dst = acc, 1 dst += acc, 2 dst -= acc
+};
+struct el_phase
+{
+  el_prod p[3];
+  int n;
+};
+
+struct el_args
+{
+  int n_eles, nu, nf, E, mb; // mb: column blocks of 8 (E * n_fields rounded up)
+  int SU, SF;                // column strides: solution-point arrays, flux-point arrays
+  int o_u, o_g, o_dl, o_fc, o_gf, o_dj;
+  int visc, inv_from_global, store_div, store_grad;
+  const double *u_in;
+  double *u0, *u1;
+  const double *delu, *ntconf;
+  double *disu_fpts, *grad_fpts, *div_out, *grad_out;
+  const double *tdisf_in;
+  const double *detjac_u, *JG_u, *detjac_f, *JG_f, *dt_local;
+  double dt, fac, c1, c2;
+  int rk_mode, rk_copy;
+  int *nan_flag;
+  el_phase ph_grad, ph_gf, ph_div, ph_corr, ph_face;
+  size_t smem_doubles;
+  hf_phys P;
+};
+
+__device__ __forceinline__ void dmma884(double &d0, double &d1, double a, double b)
+{
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+
+// all products of one phase, tasks pooled over the warps of the CTA
+__device__ __forceinline__ void run_phase(const el_phase &PH, int mb, double *sm)
+{
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const int ar = lane >> 2, ak = lane & 3;
+  const int ng = (mb + EL_CG - 1) / EL_CG;
+  int total = 0;
+  for (int p = 0; p < PH.n; p++) total += PH.p[p].rb * ng;
+  for (int task = warp; task < total; task += nw)
+  {
+    int p = 0, loc = task;
+    while (loc >= PH.p[p].rb * ng) { loc -= PH.p[p].rb * ng; p++; }
+    const el_prod &Q = PH.p[p];
+    const int rb = loc / ng, cb0 = (loc - rb * ng) * EL_CG;
+    double acc[EL_CG][2];
+#pragma unroll
+    for (int j = 0; j < EL_CG; j++) acc[j][0] = acc[j][1] = 0.0;
+    for (int t = 0; t < Q.n_terms; t++)
+    {
+      const el_term &T = Q.t[t];
+      const double *opf = T.op + (size_t)rb * T.kb * 32 + lane;
+      const double *src = sm + T.src + (cb0 * 8 + ar) * T.ss + ak;
+#pragma unroll 4
+      for (int kk = 0; kk < T.kb; kk++)
+      {
+        const double b = __ldg(opf + kk * 32);
+#pragma unroll
+        for (int j = 0; j < EL_CG; j++)
+          if (cb0 + j < mb) dmma884(acc[j][0], acc[j][1], src[j * 8 * T.ss + kk * 4], b);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < EL_CG; j++)
+      if (cb0 + j < mb)
+      {
+        double2 *dst = reinterpret_cast<double2 *>(sm + Q.dst + ((cb0 + j) * 8 + ar) * Q.ds + rb * 8 + 2 * ak);
+        if (Q.mode == 0)
+          *dst = make_double2(acc[j][0], acc[j][1]);
+        else
+        {
+          double2 v = *dst;
+          if (Q.mode == 1) { v.x += acc[j][0]; v.y += acc[j][1]; }
+          else { v.x -= acc[j][0]; v.y -= acc[j][1]; }
+          *dst = v;
+        }
+      }
+  }
+}
+
+// 8-byte asynchronous copies global -> shared (LDGSTS): a tile's loads are all in flight at once -- with one ordinary load per thread
+// and loop iteration the kernels ran at a seventh of the HBM rate (too few bytes in flight per SM)
+__device__ __forceinline__ void cp_async8(double *dst, const double *src)
+{
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all()
+{
+  asm volatile("cp.async.commit_group;\n" ::: "memory");
+  asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+}
+// [field][element of the tile][point] of a global array -> shared columns (field-major inside the tile: column = field * E + element)
+template <int NF>
+__device__ __forceinline__ void load_cols(const el_args &A, double *dst, int stride, const double *__restrict__ g, int npt, int e0, int ne)
+{
+  const int per_field = ne * npt;
+  const size_t fstride = (size_t)npt * A.n_eles;
+  for (int r = threadIdx.x; r < per_field; r += blockDim.x)
+  {
+    const int el = r / npt, pt = r - el * npt;
+    double *d = dst + el * stride + pt;
+    const double *s = g + (size_t)npt * e0 + r;
+#pragma unroll
+    for (int k = 0; k < NF; k++) cp_async8(d + k * A.E * stride, s + fstride * k);
+  }
+}
+// one value per (element, point): detjac
+__device__ __forceinline__ void load_pts(double *dst, const double *__restrict__ g, int n)
+{
+  for (int r = threadIdx.x; r < n; r += blockDim.x) cp_async8(dst + r, g + r);
+}
+template <int NF>
+__device__ __forceinline__ void store_cols(const el_args &A, const double *src, int stride, double *__restrict__ g, int npt, int e0, int ne)
+{
+  const int per_field = ne * npt;
+  const size_t fstride = (size_t)npt * A.n_eles;
+  for (int r = threadIdx.x; r < per_field; r += blockDim.x)
+  {
+    const int el = r / npt, pt = r - el * npt;
+    const double *sp = src + el * stride + pt;
+    double *d = g + (size_t)npt * e0 + r;
+#pragma unroll
+    for (int k = 0; k < NF; k++) d[fstride * k] = sp[k * A.E * stride];
+  }
+}
+
+__device__ __forceinline__ void zero_smem(double *sm, size_t n)
+{
+  double2 *p = reinterpret_cast<double2 *>(sm);
+  for (size_t i = threadIdx.x; i < n / 2; i += blockDim.x) p[i] = make_double2(0.0, 0.0);
+}
+
+// physical gradient from the reference-space one: (1 / detjac) * JGinv^T (reference src/eles.cpp:1955-2011)
+template <int ND, int NF>
+__device__ __forceinline__ void to_physical(const double *gr, const double *J, double inv_detjac, double *g)
+{
+#pragma unroll
+  for (int k = 0; k < NF; k++)
+#pragma unroll
+    for (int d = 0; d < ND; d++)
+    {
+      double acc = 0.0;
+#pragma unroll
+      for (int l = 0; l < ND; l++) acc += (inv_detjac * gr[k + NF * l]) * J[l + ND * d];
+      g[k + NF * d] = acc;
+    }
+}
+
+template <int ND, int NF>
+__global__ void __launch_bounds__(EL_THREADS, 2) k_elem_grad(const __grid_constant__ el_args A)
+{
+  extern __shared__ __align__(16) double sm[];
+  const int e0 = blockIdx.x * A.E;
+  const int ne = min(A.E, A.n_eles - e0);
+  const int ncp = A.mb * 8;
+  zero_smem(sm, A.smem_doubles);
+  __syncthreads();
+  load_cols<NF>(A, sm + A.o_u, A.SU, A.u_in, A.nu, e0, ne);
+  load_cols<NF>(A, sm + A.o_dl, A.SF, A.delu, A.nf, e0, ne);
+  cp_async_wait_all();
+  __syncthreads();
+  run_phase(A.ph_grad, A.mb, sm);
+  __syncthreads();
+  run_phase(A.ph_gf, A.mb, sm);
+  __syncthreads();
+  const size_t NFP = (size_t)A.nf * A.n_eles;
+  for (int i = threadIdx.x; i < ne * A.nf; i += blockDim.x)
+  {
+    const int el = i / A.nf, fp = i - el * A.nf;
+    const size_t p = (size_t)A.nf * (e0 + el) + fp;
+    double J[ND * ND], gr[NF * ND], g[NF * ND];
+#pragma unroll
+    for (int q = 0; q < ND * ND; q++) J[q] = A.JG_f[p * (ND * ND) + q];
+    const double inv_detjac = 1.0 / A.detjac_f[p];
+#pragma unroll
+    for (int l = 0; l < ND; l++)
+#pragma unroll
+      for (int k = 0; k < NF; k++) gr[k + NF * l] = sm[A.o_gf + (l * ncp + k * A.E + el) * A.SF + fp];
+    to_physical<ND, NF>(gr, J, inv_detjac, g);
+#pragma unroll
+    for (int q = 0; q < NF * ND; q++) A.grad_fpts[p + q * NFP] = g[q];
+  }
+}
+
+template <int ND, int NF>
+__global__ void __launch_bounds__(EL_THREADS, 2) k_elem_resid(const __grid_constant__ el_args A)
+{
+  extern __shared__ __align__(16) double sm[];
+  const int e0 = blockIdx.x * A.E;
+  const int ne = min(A.E, A.n_eles - e0);
+  const int ncp = A.mb * 8;
+  const size_t NUP = (size_t)A.nu * A.n_eles;
+  zero_smem(sm, A.smem_doubles);
+  __syncthreads();
+  load_cols<NF>(A, sm + A.o_u, A.SU, A.u_in, A.nu, e0, ne);
+  if (A.visc) load_cols<NF>(A, sm + A.o_dl, A.SF, A.delu, A.nf, e0, ne);
+  load_cols<NF>(A, sm + A.o_fc, A.SF, A.ntconf, A.nf, e0, ne);
+  load_pts(sm + A.o_dj, A.detjac_u + (size_t)A.nu * e0, ne * A.nu);
+  cp_async_wait_all();
+  __syncthreads();
+  if (A.visc)
+  {
+    run_phase(A.ph_grad, A.mb, sm);
+    __syncthreads();
+  }
+  // fluxes at the solution points, transformed, in place over the gradient
+  for (int i = threadIdx.x; i < ne * A.nu; i += blockDim.x)
+  {
+    const int el = i / A.nu, pt = i - el * A.nu;
+    const size_t p = (size_t)A.nu * (e0 + el) + pt;
+    double uu[NF], J[ND * ND], f[NF * ND], t[NF * ND];
+#pragma unroll
+    for (int k = 0; k < NF; k++) uu[k] = sm[A.o_u + (k * A.E + el) * A.SU + pt];
+#pragma unroll
+    for (int q = 0; q < ND * ND; q++) J[q] = A.JG_u[p * (ND * ND) + q];
+    if (A.inv_from_global)
+    {
+#pragma unroll
+      for (int q = 0; q < NF * ND; q++) t[q] = A.tdisf_in[p + q * NUP];
+    }
+    else
+    {
+      inv_flux<ND, NF>(uu, f, A.P);
+#pragma unroll
+      for (int k = 0; k < NF; k++)
+#pragma unroll
+        for (int l = 0; l < ND; l++)
+        {
+          double acc = 0.0;
+#pragma unroll
+          for (int m = 0; m < ND; m++) acc += J[l + ND * m] * f[k + NF * m];
+          t[k + NF * l] = acc;
+        }
+    }
+    if (A.visc)
+    {
+      double gr[NF * ND], g[NF * ND];
+#pragma unroll
+      for (int l = 0; l < ND; l++)
+#pragma unroll
+        for (int k = 0; k < NF; k++) gr[k + NF * l] = sm[A.o_g + (l * ncp + k * A.E + el) * A.SU + pt];
+      to_physical<ND, NF>(gr, J, 1.0 / sm[A.o_dj + i], g);
+      if (A.store_grad)
+      {
+#pragma unroll
+        for (int q = 0; q < NF * ND; q++) A.grad_out[p + q * NUP] = g[q];
+      }
+      vis_flux<ND, NF>(uu, g, f, A.P);
+#pragma unroll
+      for (int k = 0; k < NF; k++)
+#pragma unroll
+        for (int l = 0; l < ND; l++)
+        {
+          double acc = t[k + NF * l];
+#pragma unroll
+          for (int m = 0; m < ND; m++) acc += J[l + ND * m] * f[k + NF * m];
+          t[k + NF * l] = acc;
+        }
+    }
+#pragma unroll
+    for (int l = 0; l < ND; l++)
+#pragma unroll
+      for (int k = 0; k < NF; k++) sm[A.o_g + (l * ncp + k * A.E + el) * A.SU + pt] = t[k + NF * l];
+  }
+  __syncthreads();
+  run_phase(A.ph_div, A.mb, sm); // divergence -> o_dl; common minus own normal flux -> o_fc
+  __syncthreads();
+  // the flux planes are dead: the second RK register travels into the first of them while the correction product runs
+  const bool need_u1 = A.rk_mode == 2 || (A.rk_mode == 1 && !A.rk_copy);
+  if (need_u1) load_cols<NF>(A, sm + A.o_g, A.SU, A.u1, A.nu, e0, ne);
+  run_phase(A.ph_corr, A.mb, sm); // + opp_3 (common - own)
+  cp_async_wait_all();
+  __syncthreads();
+  // RK update (the arithmetic of k_rk_update, reference src/eles.cpp:1080-1265)
+  {
+    const int per_field = ne * A.nu;
+    for (int r = threadIdx.x; r < per_field; r += blockDim.x)
+    {
+      const int el = r / A.nu, pt = r - el * A.nu;
+      const size_t p = (size_t)A.nu * e0 + r;
+      const double inv_dj = 1.0 / sm[A.o_dj + r];
+      const double dtl = A.dt_local ? A.dt_local[e0 + el] : A.dt;
+#pragma unroll
+      for (int k = 0; k < NF; k++)
+      {
+        const size_t idx = p + NUP * k;
+        const int so = (k * A.E + el);
+        const double div = sm[A.o_dl + so * A.SF + pt];
+        if (A.store_div) A.div_out[idx] = div;
+        double u = sm[A.o_u + so * A.SU + pt];
+        if (A.rk_copy) A.u1[idx] = u;
+        const double res = div * inv_dj;
+        if (res != res) *A.nan_flag = 1 + e0 + el;
+        if (A.rk_mode == 0)
+          u -= dtl / A.fac * res;
+        else if (A.rk_mode == 1)
+        {
+          const double uo = A.rk_copy ? u : sm[A.o_g + so * A.SU + pt];
+          u = A.c1 * u + A.c2 * uo + dtl / A.fac * (-res);
+        }
+        else
+        {
+          const double d = A.c1 * sm[A.o_g + so * A.SU + pt] + dtl * (-res);
+          A.u1[idx] = d;
+          u += A.c2 * d;
+        }
+        A.u0[idx] = u;
+        sm[A.o_u + so * A.SU + pt] = u;
+      }
+    }
+  }
+  __syncthreads();
+  run_phase(A.ph_face, A.mb, sm); // opp_0 of the updated solution -> o_fc
+  __syncthreads();
+  store_cols<NF>(A, sm + A.o_fc, A.SF, A.disu_fpts, A.nf, e0, ne);
+}
+
+// only the last phase: disu_fpts = opp_0 disu_upts(0) (first stage after an upload, shock capturing)
+template <int ND, int NF>
+__global__ void __launch_bounds__(EL_THREADS, 2) k_elem_face(const __grid_constant__ el_args A)
+{
+  extern __shared__ __align__(16) double sm[];
+  const int e0 = blockIdx.x * A.E;
+  const int ne = min(A.E, A.n_eles - e0);
+  zero_smem(sm, A.smem_doubles);
+  __syncthreads();
+  load_cols<NF>(A, sm + A.o_u, A.SU, A.u_in, A.nu, e0, ne);
+  cp_async_wait_all();
+  __syncthreads();
+  run_phase(A.ph_face, A.mb, sm);
+  __syncthreads();
+  store_cols<NF>(A, sm + A.o_fc, A.SF, A.disu_fpts, A.nf, e0, ne);
+}
+
+inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
+
+// operator (rows x cols, column-major) in B-fragment order of mma.m8n8k4: [row block][k step][lane], lane = 4 * (row in block) + (k in step)
+std::vector<double> fragment_order(const double *op, int rows, int cols)
+{
+  const int RB = (rows + 7) / 8, KB = (cols + 3) / 4;
+  std::vector<double> out((size_t)RB * KB * 32, 0.0);
+  for (int rb = 0; rb < RB; rb++)
+    for (int kk = 0; kk < KB; kk++)
+      for (int lane = 0; lane < 32; lane++)
+      {
+        const int row = rb * 8 + (lane >> 2), k = kk * 4 + (lane & 3);
+        if (row < rows && k < cols) out[((size_t)rb * KB + kk) * 32 + lane] = op[(size_t)k * rows + row];
+      }
+  return out;
+}
+} // namespace
+
+struct hf_elem_type
+{
+  bool ready = false;
+  double *op0 = nullptr, *op1[3] = {nullptr, nullptr, nullptr}, *op2[3] = {nullptr, nullptr, nullptr}, *op3 = nullptr;
+  double *op4[3] = {nullptr, nullptr, nullptr}, *op5[3] = {nullptr, nullptr, nullptr}, *op6 = nullptr;
+  int E = 0, mb = 0, SU = 0, SF = 0;
+  size_t smem_resid = 0, smem_grad = 0;
+};
+struct hf_elem_state
+{
+  hf_elem_type t[HF_N_ELE_TYPES];
+  bool attr_done = false;
+};
+
+int hf_elem_on_upload(hf_ctx *c, hf_eles_dev &e, const hf_eles_desc *d)
+{
+  if (!c->ez) c->ez = new hf_elem_state();
+  hf_elem_type &T = c->ez->t[d->ele_type];
+  const int nu = e.n_upts, nf = e.n_fpts, nd = e.n_dims, NF = e.n_fields;
+  const bool visc = c->prm.viscous != 0;
+  auto up = [&](double **dst, const double *op, int rows, int cols) -> int {
+    std::vector<double> f = fragment_order(op, rows, cols);
+    return hf_alloc_copy(c, dst, f.data(), f.size());
+  };
+  if (up(&T.op0, d->opp_0, nf, nu) || up(&T.op3, d->opp_3, nu, nf)) return 1;
+  for (int i = 0; i < nd; i++)
+  {
+    if (up(&T.op1[i], d->opp_1[i], nf, nu) || up(&T.op2[i], d->opp_2[i], nu, nu)) return 1;
+    if (visc && (up(&T.op4[i], d->opp_4[i], nu, nu) || up(&T.op5[i], d->opp_5[i], nu, nf))) return 1;
+  }
+  if (visc && up(&T.op6, d->opp_6, nf, nu)) return 1;
+  const int nup = round_up(nu, 8), nfp = round_up(nf, 8);
+  T.SU = nup + 4;
+  T.SF = (nfp > nup ? nfp : nup) + 4; // the divergence (solution points) is accumulated in a flux-point buffer
+  // elements per CTA: whole 8-column blocks with little padding, shared memory for three CTAs per SM if the element allows it
+  auto bytes_resid = [&](int mb) { return sizeof(double) * ((size_t)mb * 8 * ((size_t)T.SU * (1 + nd) + 2 * (size_t)T.SF) + (size_t)((mb * 8 / NF * nu + 1) & ~1)); };
+  auto bytes_grad = [&](int mb) { return sizeof(double) * (size_t)mb * 8 * ((size_t)T.SU * (1 + nd) + (size_t)T.SF * (1 + nd)); };
+  int best = 0;
+  double best_score = -1.0;
+  const char *force = getenv("HF_ELEM_E");
+  const size_t budget = (getenv("HF_ELEM_KB") ? (size_t)atoi(getenv("HF_ELEM_KB")) : 72) * 1024; // measurement aid: shared memory per CTA to aim for
+  for (int E = 1; E <= 64; E++)
+  {
+    const int mb = round_up(E * NF, 8) / 8;
+    const size_t b = (visc && bytes_grad(mb) > bytes_resid(mb)) ? bytes_grad(mb) : bytes_resid(mb);
+    if (b > 200 * 1024) break;
+    const double eff = (double)(E * NF) / (mb * 8);
+    // prefer: fits three per SM (72 kB), then padding efficiency, then more columns (operator fragments amortised, more warp tasks)
+    double score = eff + (b <= budget ? 1.0 : (b <= 110 * 1024 ? 0.5 : 0.0)) + 0.002 * (mb > 12 ? 12 : mb);
+    if (force && atoi(force) == E) score = 100.0;
+    if (score > best_score) { best_score = score; best = E; }
+  }
+  if (best == 0) return 0; // element too large for a shared-memory tile: the staged kernels run
+  T.E = best;
+  T.mb = round_up(best * NF, 8) / 8;
+  T.smem_resid = bytes_resid(T.mb);
+  T.smem_grad = bytes_grad(T.mb);
+  T.ready = true;
+  return 0;
+}
+
+void hf_elem_destroy(hf_ctx *c)
+{
+  delete c->ez;
+  c->ez = nullptr;
+}
+
+const char *hf_elem_status(hf_ctx *c)
+{
+  if (!c->ez) return "blocked element kernels: not prepared (staged-only context)";
+  if (c->prm.LES) return "blocked element kernels: LES runs through the staged kernels";
+  for (int t = 0; t < HF_N_ELE_TYPES; t++)
+    if (c->eles[t].present && !c->ez->t[t].ready) return "blocked element kernels: an element type does not fit a shared-memory tile";
+  if (!((c->prm.n_dims == 2 && c->prm.n_fields == 4) || (c->prm.n_dims == 3 && c->prm.n_fields == 5) || c->prm.n_fields == 1))
+    return "blocked element kernels: unsupported (n_dims, n_fields)";
+  return "available";
+}
+int hf_elem_available(hf_ctx *c)
+{
+  const bool off = getenv("HF_NO_ELEM") != nullptr; // read per call: tests switch it inside one process
+  return !off && strcmp(hf_elem_status(c), "available") == 0;
+}
+
+static void fill_args(hf_ctx *c, hf_eles_dev &e, const hf_elem_type &T, el_args &A)
+{
+  memset(&A, 0, sizeof(A));
+  const int nd = e.n_dims;
+  const bool visc = c->prm.viscous != 0;
+  A.n_eles = e.n_eles; A.nu = e.n_upts; A.nf = e.n_fpts; A.E = T.E; A.mb = T.mb; A.SU = T.SU; A.SF = T.SF;
+  const int ncp = T.mb * 8;
+  A.o_u = 0;
+  A.o_g = ncp * T.SU;
+  A.o_dl = A.o_g + nd * ncp * T.SU;
+  A.o_fc = A.o_dl + ncp * T.SF; // k_elem_resid
+  A.o_gf = A.o_dl + ncp * T.SF; // k_elem_grad
+  A.o_dj = A.o_fc + ncp * T.SF; // k_elem_resid: detjac at the tile's solution points
+  A.visc = visc;
+  A.u_in = e.disu_upts[0]; A.u0 = e.disu_upts[0]; A.u1 = e.disu_upts[1];
+  A.delu = e.delta_disu_fpts; A.ntconf = e.norm_tconf_fpts; A.disu_fpts = e.disu_fpts; A.grad_fpts = e.grad_disu_fpts;
+  A.div_out = e.div_tconf_upts; A.grad_out = e.grad_disu_upts; A.tdisf_in = e.tdisf_upts;
+  A.detjac_u = e.detjac_upts; A.JG_u = e.JGinv_upts; A.detjac_f = e.detjac_fpts; A.JG_f = e.JGinv_fpts;
+  A.nan_flag = c->d_nan;
+  A.P = c->phys;
+  const int kbu = (e.n_upts + 3) / 4, kbf = (e.n_fpts + 3) / 4, rbu = (e.n_upts + 7) / 8, rbf = (e.n_fpts + 7) / 8;
+  // reference-space gradient, corrected: opp_4(d) u + opp_5(d) delta
+  A.ph_grad.n = visc ? nd : 0;
+  for (int d = 0; d < nd && visc; d++)
+  {
+    el_prod &Q = A.ph_grad.p[d];
+    Q.n_terms = 2; Q.rb = rbu; Q.dst = A.o_g + d * ncp * T.SU; Q.ds = T.SU; Q.mode = 0;
+    Q.t[0] = {T.op4[d], kbu, A.o_u, T.SU};
+    Q.t[1] = {T.op5[d], kbf, A.o_dl, T.SF};
+  }
+  // gradient at the flux points: opp_6 g(d)
+  A.ph_gf.n = visc ? nd : 0;
+  for (int d = 0; d < nd && visc; d++)
+  {
+    el_prod &Q = A.ph_gf.p[d];
+    Q.n_terms = 1; Q.rb = rbf; Q.dst = A.o_gf + d * ncp * T.SF; Q.ds = T.SF; Q.mode = 0;
+    Q.t[0] = {T.op6, kbu, A.o_g + d * ncp * T.SU, T.SU};
+  }
+  // divergence sum_d opp_2(d) f(d) -> o_dl;  o_fc -= sum_d opp_1(d) f(d)
+  A.ph_div.n = 2;
+  {
+    el_prod &Q = A.ph_div.p[0];
+    Q.n_terms = nd; Q.rb = rbu; Q.dst = A.o_dl; Q.ds = T.SF; Q.mode = 0;
+    for (int d = 0; d < nd; d++) Q.t[d] = {T.op2[d], kbu, A.o_g + d * ncp * T.SU, T.SU};
+    el_prod &R = A.ph_div.p[1];
+    R.n_terms = nd; R.rb = rbf; R.dst = A.o_fc; R.ds = T.SF; R.mode = 2;
+    for (int d = 0; d < nd; d++) R.t[d] = {T.op1[d], kbu, A.o_g + d * ncp * T.SU, T.SU};
+  }
+  A.ph_corr.n = 1;
+  {
+    el_prod &Q = A.ph_corr.p[0];
+    Q.n_terms = 1; Q.rb = rbu; Q.dst = A.o_dl; Q.ds = T.SF; Q.mode = 1;
+    Q.t[0] = {T.op3, kbf, A.o_fc, T.SF};
+  }
+  A.ph_face.n = 1;
+  {
+    el_prod &Q = A.ph_face.p[0];
+    Q.n_terms = 1; Q.rb = rbf; Q.dst = A.o_fc; Q.ds = T.SF; Q.mode = 0;
+    Q.t[0] = {T.op0, kbu, A.o_u, T.SU};
+  }
+}
+
+#define EL_LAUNCH(KERNEL, smem)                                                                                          \
+  do {                                                                                                                   \
+    const unsigned grid = (unsigned)((e.n_eles + T.E - 1) / T.E);                                                        \
+    if (nd == 3 && nfl == 5) KERNEL<3, 5><<<grid, EL_THREADS, smem, c->stream>>>(A);                                     \
+    else if (nd == 2 && nfl == 4) KERNEL<2, 4><<<grid, EL_THREADS, smem, c->stream>>>(A);                                \
+    else if (nd == 2 && nfl == 1) KERNEL<2, 1><<<grid, EL_THREADS, smem, c->stream>>>(A);                                \
+    else KERNEL<3, 1><<<grid, EL_THREADS, smem, c->stream>>>(A);                                                         \
+    c->launches++;                                                                                                       \
+    cudaError_t e_ = cudaGetLastError();                                                                                 \
+    if (e_ != cudaSuccess) { hf_set_error(std::string("kernel launch (blocked element kernel): ") + cudaGetErrorString(e_)); return 1; } \
+  } while (0)
+
+static int set_attrs(hf_ctx *c)
+{
+  if (c->ez->attr_done) return 0;
+  const int lim = 200 * 1024;
+#define EL_ATTR(K) HF_CUDA(cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, lim))
+  EL_ATTR((k_elem_grad<3, 5>)); EL_ATTR((k_elem_grad<2, 4>)); EL_ATTR((k_elem_grad<2, 1>)); EL_ATTR((k_elem_grad<3, 1>));
+  EL_ATTR((k_elem_resid<3, 5>)); EL_ATTR((k_elem_resid<2, 4>)); EL_ATTR((k_elem_resid<2, 1>)); EL_ATTR((k_elem_resid<3, 1>));
+  EL_ATTR((k_elem_face<3, 5>)); EL_ATTR((k_elem_face<2, 4>)); EL_ATTR((k_elem_face<2, 1>)); EL_ATTR((k_elem_face<3, 1>));
+#undef EL_ATTR
+  c->ez->attr_done = true;
+  return 0;
+}
+
+// disu_fpts = opp_0 disu_upts(0) for every element type
+int hf_elem_extrapolate(hf_ctx *c)
+{
+  if (set_attrs(c)) return 1;
+  for (int t = 0; t < HF_N_ELE_TYPES; t++)
+  {
+    hf_eles_dev &e = c->eles[t];
+    if (!e.present) continue;
+    const hf_elem_type &T = c->ez->t[t];
+    const int nd = e.n_dims, nfl = e.n_fields;
+    el_args A;
+    fill_args(c, e, T, A);
+    A.smem_doubles = T.smem_resid / sizeof(double);
+    EL_LAUNCH(k_elem_face, T.smem_resid);
+  }
+  c->ufpts_valid = true;
+  return 0;
+}
+
+// One RK stage: CalcResidual (reference src/solver.cpp:50-223) + AdvanceSolution for every element type.
+int hf_elem_stage(hf_ctx *c, int rk_stage, double time, int keep_residual)
+{
+  HF_CUDA(cudaSetDevice(c->device));
+  if (set_attrs(c)) return 1;
+  const bool visc = c->prm.viscous != 0, par = c->nproc > 1;
+  const int stage = rk_stage & 0xff;
+#define EACH_INT(OP) for (int t = 0; t < HF_N_INTER_TYPES; t++) if (hf_dev_int_inters_op(c, t, OP)) return 1
+#define EACH_BDY(OP) for (int t = 0; t < HF_N_INTER_TYPES; t++) if (hf_dev_bdy_inters_op(c, t, OP, time)) return 1
+#define EACH_MPI(OP) for (int t = 0; t < HF_N_INTER_TYPES; t++) if (hf_dev_mpi_inters_op(c, t, OP)) return 1
+  if (!c->ufpts_valid && hf_elem_extrapolate(c)) return 1;
+  if (par) EACH_MPI(2);
+  if (c->prm.over_int)
+    for (int t = 0; t < HF_N_ELE_TYPES; t++)
+      if (c->eles[t].present && hf_dev_eles_op(c, t, HF_EVALUATE_INVFLUX_OVER_INT)) return 1;
+  EACH_INT(HF_COMMON_INVFLUX);
+  EACH_BDY(HF_COMMON_INVFLUX);
+  if (par) { EACH_MPI(3); EACH_MPI(HF_COMMON_INVFLUX); }
+  if (visc)
+  {
+    for (int t = 0; t < HF_N_ELE_TYPES; t++)
+    {
+      hf_eles_dev &e = c->eles[t];
+      if (!e.present) continue;
+      const hf_elem_type &T = c->ez->t[t];
+      const int nd = e.n_dims, nfl = e.n_fields;
+      el_args A;
+      fill_args(c, e, T, A);
+      A.smem_doubles = T.smem_grad / sizeof(double);
+      EL_LAUNCH(k_elem_grad, T.smem_grad);
+    }
+    if (par) EACH_MPI(4);
+    EACH_INT(HF_COMMON_VISCFLUX);
+    EACH_BDY(HF_COMMON_VISCFLUX);
+    if (par) { EACH_MPI(5); EACH_MPI(HF_COMMON_VISCFLUX); }
+  }
+  for (int t = 0; t < HF_N_ELE_TYPES; t++)
+  {
+    hf_eles_dev &e = c->eles[t];
+    if (!e.present) continue;
+    const hf_elem_type &T = c->ez->t[t];
+    const int nd = e.n_dims, nfl = e.n_fields;
+    el_args A;
+    fill_args(c, e, T, A);
+    A.smem_doubles = T.smem_resid / sizeof(double);
+    A.inv_from_global = c->prm.over_int ? 1 : 0;
+    A.store_div = keep_residual ? 1 : 0;
+    if (keep_residual && visc && c->want_gradient && hf_ensure_staged_buffers(c, e)) return 1; // grad_disu_upts for the integral diagnostics
+    A.grad_out = e.grad_disu_upts;
+    A.store_grad = (keep_residual && visc && c->want_gradient) ? 1 : 0;
+    A.dt = c->prm.dt;
+    A.dt_local = (c->prm.dt_type == 2) ? e.dt_local : nullptr;
+    if (hf_rk_coeffs(c, stage, &A.rk_mode, &A.rk_copy, &A.fac, &A.c1, &A.c2)) return 1;
+    EL_LAUNCH(k_elem_resid, T.smem_resid);
+  }
+  c->ufpts_valid = true;
+  return 0;
+}
+
+extern "C" const char *hf_dev_elem_status(hf_ctx *c) { return hf_elem_status(c); }

@@ -2,6 +2,7 @@
 // through these with ctypes).  One handle = one `struct solution` + its run_input, i.e. what the reference's
 // main() owns (src/HiFiLES.cpp:41-130).  run_input is a process-wide singleton in the reference
 // (src/global.cpp:29); it is here too, so only one handle may be live at a time.
+#include <string>
 #include "hifiles.h"
 #include <cstring>
 #include <memory>
@@ -109,12 +110,20 @@ int hifiles_run(void *handle, int n_steps, int fused)
       return;
     }
     int RKSteps = get_n_rk_steps(run_input.adv_type);
+    // CFL time steps (dt_type 1, 2): calc_time_step on the device before every step, then the stages -- through the blocked element
+    // kernels when the fast mode was asked for and they apply, else method by method as the reference's main loop
+    const bool stage_calls = fused && std::string(hf_dev_fused_status(S->ctx)) != "available" && std::string(hf_dev_elem_status(S->ctx)) == "available";
     for (int it = 0; it < n_steps; it++)
     {
       calc_time_step(S);
       if (run_input.pressure_ramp) upload_bc_table(S);
       for (int i = 0; i < RKSteps; i++)
       {
+        if (stage_calls)
+        {
+          hf_check(hf_dev_rk_stage(S->ctx, i, S->time, (it == n_steps - 1 && i == RKSteps - 1) ? 1 : 0));
+          continue;
+        }
         CalcResidual(S->ini_iter + it, i, S);
         for (int j = 0; j < S->n_ele_types; j++) S->mesh_eles(j)->AdvanceSolution(i, run_input.adv_type);
         if (run_input.shock_cap)

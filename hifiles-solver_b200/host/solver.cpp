@@ -216,7 +216,7 @@ void CalcResidual(int in_file_num, int in_rk_stage, struct solution *FlowSol)
 // shock_capture (src/HiFiLES.cpp:205-217); on the device the three are one fused call where the fused kernels apply.
 void AdvanceStage(int in_file_num, int in_rk_stage, struct solution *FlowSol, bool monitored)
 {
-  if (run_input.device_fused && hf_dev_fused_status(FlowSol->ctx) == string("available"))
+  if (run_input.device_fused && (hf_dev_fused_status(FlowSol->ctx) == string("available") || hf_dev_elem_status(FlowSol->ctx) == string("available")))
   {
     hf_check(hf_dev_rk_stage(FlowSol->ctx, in_rk_stage, FlowSol->time, monitored ? 1 : 0));
     return;

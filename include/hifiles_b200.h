@@ -231,6 +231,13 @@ int hf_dev_set_dt(hf_ctx *ctx, double dt);
 /* ---- data movement (replaces hf_array::cp_gpu_cpu / cp_cpu_gpu and eles::cp_*_gpu_cpu) ------------------- */
 int hf_dev_download(hf_ctx *ctx, int ele_type, int which, double *host, size_t n_doubles);
 int hf_dev_upload(hf_ctx *ctx, int ele_type, int which, const double *host, size_t n_doubles);
+/* Two-phase form of hf_dev_upload for hosts that hand over a new array while the device is still computing (the reference's
+ * eles::cp_disu_upts_cpu_gpu, include/eles.h:410-445, is synchronous): _begin starts the host -> device copy on a transfer stream
+ * and returns at once (host must be page-locked and stay untouched until _commit has been called and the next synchronising call
+ * returned); _commit orders the compute stream behind the copy and moves the data into the array.  One pending upload per
+ * element type. */
+int hf_dev_upload_begin(hf_ctx *ctx, int ele_type, int which, const double *host, size_t n_doubles);
+int hf_dev_upload_commit(hf_ctx *ctx, int ele_type);
 /* eles::compute_res_upts summed over element types as output::CalcNormResidual does (reference
  * src/eles.cpp:5045-5074, src/output.cpp:2166-2248); out[n_fields]. Local to this rank (no collective). */
 int hf_dev_residual_norm(hf_ctx *ctx, int norm_type, double *out);
@@ -269,6 +276,10 @@ const char *hf_dev_fused_status(hf_ctx *ctx);
 /* which fused kernel pair runs: "generation 7 (one-sided LDG ...)" when |ldg_beta| = 0.5 (each flux-point pair has one
  * owner that evaluates the whole common flux), else "generation 6 ..." with the reason; "none" without fused kernels */
 const char *hf_dev_fused_variant(hf_ctx *ctx);
+/* "available" when the blocked element kernels (hf_elem.cu: two kernels per element type and stage around the interface kernels, any
+ * element type, boundary faces, curved elements) serve hf_dev_rk_stage / hf_dev_run_steps in fast mode wherever the sum-factorised
+ * hexahedron kernels do not; otherwise the reason why the staged kernels run. */
+const char *hf_dev_elem_status(hf_ctx *ctx);
 /* CUDA-event timing on the compute stream: start/stop bracket, elapsed in milliseconds. */
 int hf_dev_timer_start(hf_ctx *ctx);
 int hf_dev_timer_stop(hf_ctx *ctx, float *ms);

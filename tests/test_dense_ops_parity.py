@@ -20,7 +20,8 @@ def test_fast_mode_steps_vs_reference(tmp_path, hb, meshgen, name, monkeypatch):
     inp = make_case(tmp_path, meshgen, name)
     n_steps = 3
     ref = util.run_reference(inp, n_steps, stagewise=False)
-    with hb.Run(inp) as run:  # default mode = fast: fused kernels where they exist, tensor-core operator products for dense operators
+    monkeypatch.setenv("HF_NO_ELEM", "1")  # without the blocked element kernels (test_elem_parity.py) the fast mode is: staged kernels + tensor-core operator products
+    with hb.Run(inp) as run:
         run.run(n_steps, fused=True)
         fast = {t: run.download(t, "disu_upts") for t in run.ele_types()}
         check("residual norm", run.norm_residual(), ref["history.norm_residual"][:, -1], 1e-12)

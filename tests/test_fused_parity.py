@@ -177,3 +177,29 @@ def test_nan_residual_stops_the_run(tmp_path, hb, meshgen, mode, monkeypatch):
         run.upload("hex", "disu_upts", u)
         with pytest.raises(hb.HiFiLESError, match="Residual is NaN"):
             run.run(1, fused=mode != "staged")
+
+
+@pytest.mark.gpu
+def test_two_phase_upload_equals_synchronous_upload(tmp_path, hb, meshgen):
+    """hf_dev_upload_begin / hf_dev_upload_commit (the copy overlaps the previous step's kernels) leave the same state behind as
+    hf_dev_upload = eles::cp_disu_upts_cpu_gpu: two steps from the same uploaded field, bit for bit; a second begin without a commit
+    is refused."""
+    inp = make_case(tmp_path, meshgen, "hex_p4_ns_hllc_rk34")
+    with hb.Run(inp) as run:
+        u0 = run.download("hex", "disu_upts")
+        run.run(1, fused=True)
+        run.upload("hex", "disu_upts", u0)
+        run.run(2, fused=True)
+        a = run.download("hex", "disu_upts")
+        keep = run.upload_begin("hex", "disu_upts", u0)  # travels while the device is idle or busy: ordered by the commit
+        with pytest.raises(hb.HiFiLESError, match="not committed"):
+            run.upload_begin("hex", "disu_upts", u0)
+        run.upload_commit("hex")
+        keep2 = run.upload_begin("hex", "disu_upts", a)  # the next upload may start while the steps below run
+        run.run(2, fused=True)
+        b = run.download("hex", "disu_upts")
+        run.upload_commit("hex")
+        c = run.download("hex", "disu_upts")
+        del keep, keep2
+    assert np.array_equal(a, b)
+    assert np.array_equal(a, c)
