@@ -32,7 +32,6 @@
 namespace
 {
 constexpr int EL_THREADS = 256;
-constexpr int EL_CG = 2; // column blocks per warp task (they share the operator fragment)
 
 struct el_term
 {
@@ -57,6 +56,7 @@ struct el_args
 {
   int n_eles, nu, nf, E, mb; // mb: column blocks of 8 (E * n_fields rounded up)
   int SU, SF;                // column strides: solution-point arrays, flux-point arrays
+  unsigned mg_u, mg_f;       // ceil(2^32 / nu), ceil(2^32 / nf): r / n = umulhi(r, magic) for the small r of a tile
   int o_u, o_g, o_dl, o_fc, o_gf, o_dj;
   int visc, inv_from_global, store_div, store_grad;
   const double *u_in;
@@ -78,12 +78,15 @@ __device__ __forceinline__ void dmma884(double &d0, double &d1, double a, double
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
 }
 
-// all products of one phase, tasks pooled over the warps of the CTA
+// all products of one phase, tasks pooled over the warps of the CTA.  The k steps of every operator are padded to pairs on the host
+// (zero fragments) and a task always works on two column blocks (the second one a copy of the first when the tile has an odd
+// block left over, its result dropped), so the inner loop carries no predicate: 2 fragment loads, 4 data loads, 4 DMMA per
+// iteration, the next iteration's fragments requested before this one's tensor-core instructions.
 __device__ __forceinline__ void run_phase(const el_phase &PH, int mb, double *sm)
 {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
   const int ar = lane >> 2, ak = lane & 3;
-  const int ng = (mb + EL_CG - 1) / EL_CG;
+  const int ng = (mb + 1) >> 1;
   int total = 0;
   for (int p = 0; p < PH.n; p++) total += PH.p[p].rb * ng;
   for (int task = warp; task < total; task += nw)
@@ -91,39 +94,52 @@ __device__ __forceinline__ void run_phase(const el_phase &PH, int mb, double *sm
     int p = 0, loc = task;
     while (loc >= PH.p[p].rb * ng) { loc -= PH.p[p].rb * ng; p++; }
     const el_prod &Q = PH.p[p];
-    const int rb = loc / ng, cb0 = (loc - rb * ng) * EL_CG;
-    double acc[EL_CG][2];
-#pragma unroll
-    for (int j = 0; j < EL_CG; j++) acc[j][0] = acc[j][1] = 0.0;
-    for (int t = 0; t < Q.n_terms; t++)
+    const int rb = loc / ng, cb0 = (loc - rb * ng) * 2;
+    const bool two = cb0 + 1 < mb;
+    double a00 = 0.0, a01 = 0.0, a10 = 0.0, a11 = 0.0;
+    const int nt = Q.n_terms;
+    for (int t = 0; t < nt; t++)
     {
       const el_term &T = Q.t[t];
+      const int kb2 = T.kb >> 1, ss = T.ss;
       const double *opf = T.op + (size_t)rb * T.kb * 32 + lane;
-      const double *src = sm + T.src + (cb0 * 8 + ar) * T.ss + ak;
-#pragma unroll 4
-      for (int kk = 0; kk < T.kb; kk++)
+      const double *s0 = sm + T.src + (cb0 * 8 + ar) * ss + ak;
+      const double *s1 = two ? s0 + 8 * ss : s0;
+      double b0 = __ldg(opf), b1 = __ldg(opf + 32);
+      for (int q = 0; q < kb2; q++)
       {
-        const double b = __ldg(opf + kk * 32);
-#pragma unroll
-        for (int j = 0; j < EL_CG; j++)
-          if (cb0 + j < mb) dmma884(acc[j][0], acc[j][1], src[j * 8 * T.ss + kk * 4], b);
+        opf += 64;
+        double n0 = 0.0, n1 = 0.0;
+        if (q + 1 < kb2) { n0 = __ldg(opf); n1 = __ldg(opf + 32); }
+        dmma884(a00, a01, s0[0], b0);
+        dmma884(a10, a11, s1[0], b0);
+        dmma884(a00, a01, s0[4], b1);
+        dmma884(a10, a11, s1[4], b1);
+        s0 += 8; s1 += 8;
+        b0 = n0; b1 = n1;
       }
     }
-#pragma unroll
-    for (int j = 0; j < EL_CG; j++)
-      if (cb0 + j < mb)
+    const int mode = Q.mode;
+    double2 *d0 = reinterpret_cast<double2 *>(sm + Q.dst + (cb0 * 8 + ar) * Q.ds + rb * 8 + 2 * ak);
+    double2 *d1 = d0 + 4 * Q.ds; // 8 columns further, in double2 units
+    if (mode == 0)
+    {
+      *d0 = make_double2(a00, a01);
+      if (two) *d1 = make_double2(a10, a11);
+    }
+    else
+    {
+      const double sg = mode == 1 ? 1.0 : -1.0;
+      double2 v = *d0;
+      v.x += sg * a00; v.y += sg * a01;
+      *d0 = v;
+      if (two)
       {
-        double2 *dst = reinterpret_cast<double2 *>(sm + Q.dst + ((cb0 + j) * 8 + ar) * Q.ds + rb * 8 + 2 * ak);
-        if (Q.mode == 0)
-          *dst = make_double2(acc[j][0], acc[j][1]);
-        else
-        {
-          double2 v = *dst;
-          if (Q.mode == 1) { v.x += acc[j][0]; v.y += acc[j][1]; }
-          else { v.x -= acc[j][0]; v.y -= acc[j][1]; }
-          *dst = v;
-        }
+        double2 w = *d1;
+        w.x += sg * a10; w.y += sg * a11;
+        *d1 = w;
       }
+    }
   }
 }
 
@@ -139,14 +155,32 @@ __device__ __forceinline__ void cp_async_wait_all()
   asm volatile("cp.async.wait_group 0;\n" ::: "memory");
 }
 // [field][element of the tile][point] of a global array -> shared columns (field-major inside the tile: column = field * E + element)
+__device__ __forceinline__ void cp_async16(double *dst, const double *src)
+{
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
 template <int NF>
-__device__ __forceinline__ void load_cols(const el_args &A, double *dst, int stride, const double *__restrict__ g, int npt, int e0, int ne)
+__device__ __forceinline__ void load_cols(const el_args &A, double *dst, int stride, const double *__restrict__ g, int npt, unsigned mg, int e0, int ne)
 {
   const int per_field = ne * npt;
   const size_t fstride = (size_t)npt * A.n_eles;
+  if ((npt & 1) == 0 && (fstride & 1) == 0)
+  {
+    // even point count: pairs of points are 16-byte aligned on both sides; .cg keeps the streamed tile out of L1, which then holds
+    // the operator fragments
+    for (int r = 2 * threadIdx.x; r < per_field; r += 2 * blockDim.x)
+    {
+      const int el = (int)__umulhi((unsigned)r, mg), pt = r - el * npt;
+      double *d = dst + el * stride + pt;
+      const double *s = g + (size_t)npt * e0 + r;
+#pragma unroll
+      for (int k = 0; k < NF; k++) cp_async16(d + k * A.E * stride, s + fstride * k);
+    }
+    return;
+  }
   for (int r = threadIdx.x; r < per_field; r += blockDim.x)
   {
-    const int el = r / npt, pt = r - el * npt;
+    const int el = (int)__umulhi((unsigned)r, mg), pt = r - el * npt;
     double *d = dst + el * stride + pt;
     const double *s = g + (size_t)npt * e0 + r;
 #pragma unroll
@@ -159,13 +193,13 @@ __device__ __forceinline__ void load_pts(double *dst, const double *__restrict__
   for (int r = threadIdx.x; r < n; r += blockDim.x) cp_async8(dst + r, g + r);
 }
 template <int NF>
-__device__ __forceinline__ void store_cols(const el_args &A, const double *src, int stride, double *__restrict__ g, int npt, int e0, int ne)
+__device__ __forceinline__ void store_cols(const el_args &A, const double *src, int stride, double *__restrict__ g, int npt, unsigned mg, int e0, int ne)
 {
   const int per_field = ne * npt;
   const size_t fstride = (size_t)npt * A.n_eles;
   for (int r = threadIdx.x; r < per_field; r += blockDim.x)
   {
-    const int el = r / npt, pt = r - el * npt;
+    const int el = (int)__umulhi((unsigned)r, mg), pt = r - el * npt;
     const double *sp = src + el * stride + pt;
     double *d = g + (size_t)npt * e0 + r;
 #pragma unroll
@@ -204,8 +238,8 @@ __global__ void __launch_bounds__(EL_THREADS, 2) k_elem_grad(const __grid_consta
   const int ncp = A.mb * 8;
   zero_smem(sm, A.smem_doubles);
   __syncthreads();
-  load_cols<NF>(A, sm + A.o_u, A.SU, A.u_in, A.nu, e0, ne);
-  load_cols<NF>(A, sm + A.o_dl, A.SF, A.delu, A.nf, e0, ne);
+  load_cols<NF>(A, sm + A.o_u, A.SU, A.u_in, A.nu, A.mg_u, e0, ne);
+  load_cols<NF>(A, sm + A.o_dl, A.SF, A.delu, A.nf, A.mg_f, e0, ne);
   cp_async_wait_all();
   __syncthreads();
   run_phase(A.ph_grad, A.mb, sm);
@@ -215,7 +249,7 @@ __global__ void __launch_bounds__(EL_THREADS, 2) k_elem_grad(const __grid_consta
   const size_t NFP = (size_t)A.nf * A.n_eles;
   for (int i = threadIdx.x; i < ne * A.nf; i += blockDim.x)
   {
-    const int el = i / A.nf, fp = i - el * A.nf;
+    const int el = (int)__umulhi((unsigned)i, A.mg_f), fp = i - el * A.nf;
     const size_t p = (size_t)A.nf * (e0 + el) + fp;
     double J[ND * ND], gr[NF * ND], g[NF * ND];
 #pragma unroll
@@ -241,9 +275,9 @@ __global__ void __launch_bounds__(EL_THREADS, 2) k_elem_resid(const __grid_const
   const size_t NUP = (size_t)A.nu * A.n_eles;
   zero_smem(sm, A.smem_doubles);
   __syncthreads();
-  load_cols<NF>(A, sm + A.o_u, A.SU, A.u_in, A.nu, e0, ne);
-  if (A.visc) load_cols<NF>(A, sm + A.o_dl, A.SF, A.delu, A.nf, e0, ne);
-  load_cols<NF>(A, sm + A.o_fc, A.SF, A.ntconf, A.nf, e0, ne);
+  load_cols<NF>(A, sm + A.o_u, A.SU, A.u_in, A.nu, A.mg_u, e0, ne);
+  if (A.visc) load_cols<NF>(A, sm + A.o_dl, A.SF, A.delu, A.nf, A.mg_f, e0, ne);
+  load_cols<NF>(A, sm + A.o_fc, A.SF, A.ntconf, A.nf, A.mg_f, e0, ne);
   load_pts(sm + A.o_dj, A.detjac_u + (size_t)A.nu * e0, ne * A.nu);
   cp_async_wait_all();
   __syncthreads();
@@ -255,7 +289,7 @@ __global__ void __launch_bounds__(EL_THREADS, 2) k_elem_resid(const __grid_const
   // fluxes at the solution points, transformed, in place over the gradient
   for (int i = threadIdx.x; i < ne * A.nu; i += blockDim.x)
   {
-    const int el = i / A.nu, pt = i - el * A.nu;
+    const int el = (int)__umulhi((unsigned)i, A.mg_u), pt = i - el * A.nu;
     const size_t p = (size_t)A.nu * (e0 + el) + pt;
     double uu[NF], J[ND * ND], f[NF * ND], t[NF * ND];
 #pragma unroll
@@ -316,7 +350,7 @@ __global__ void __launch_bounds__(EL_THREADS, 2) k_elem_resid(const __grid_const
   __syncthreads();
   // the flux planes are dead: the second RK register travels into the first of them while the correction product runs
   const bool need_u1 = A.rk_mode == 2 || (A.rk_mode == 1 && !A.rk_copy);
-  if (need_u1) load_cols<NF>(A, sm + A.o_g, A.SU, A.u1, A.nu, e0, ne);
+  if (need_u1) load_cols<NF>(A, sm + A.o_g, A.SU, A.u1, A.nu, A.mg_u, e0, ne);
   run_phase(A.ph_corr, A.mb, sm); // + opp_3 (common - own)
   cp_async_wait_all();
   __syncthreads();
@@ -325,7 +359,7 @@ __global__ void __launch_bounds__(EL_THREADS, 2) k_elem_resid(const __grid_const
     const int per_field = ne * A.nu;
     for (int r = threadIdx.x; r < per_field; r += blockDim.x)
     {
-      const int el = r / A.nu, pt = r - el * A.nu;
+      const int el = (int)__umulhi((unsigned)r, A.mg_u), pt = r - el * A.nu;
       const size_t p = (size_t)A.nu * e0 + r;
       const double inv_dj = 1.0 / sm[A.o_dj + r];
       const double dtl = A.dt_local ? A.dt_local[e0 + el] : A.dt;
@@ -361,7 +395,7 @@ __global__ void __launch_bounds__(EL_THREADS, 2) k_elem_resid(const __grid_const
   __syncthreads();
   run_phase(A.ph_face, A.mb, sm); // opp_0 of the updated solution -> o_fc
   __syncthreads();
-  store_cols<NF>(A, sm + A.o_fc, A.SF, A.disu_fpts, A.nf, e0, ne);
+  store_cols<NF>(A, sm + A.o_fc, A.SF, A.disu_fpts, A.nf, A.mg_f, e0, ne);
 }
 
 // only the last phase: disu_fpts = opp_0 disu_upts(0) (first stage after an upload, shock capturing)
@@ -373,12 +407,12 @@ __global__ void __launch_bounds__(EL_THREADS, 2) k_elem_face(const __grid_consta
   const int ne = min(A.E, A.n_eles - e0);
   zero_smem(sm, A.smem_doubles);
   __syncthreads();
-  load_cols<NF>(A, sm + A.o_u, A.SU, A.u_in, A.nu, e0, ne);
+  load_cols<NF>(A, sm + A.o_u, A.SU, A.u_in, A.nu, A.mg_u, e0, ne);
   cp_async_wait_all();
   __syncthreads();
   run_phase(A.ph_face, A.mb, sm);
   __syncthreads();
-  store_cols<NF>(A, sm + A.o_fc, A.SF, A.disu_fpts, A.nf, e0, ne);
+  store_cols<NF>(A, sm + A.o_fc, A.SF, A.disu_fpts, A.nf, A.mg_f, e0, ne);
 }
 
 inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
@@ -386,7 +420,7 @@ inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
 // operator (rows x cols, column-major) in B-fragment order of mma.m8n8k4: [row block][k step][lane], lane = 4 * (row in block) + (k in step)
 std::vector<double> fragment_order(const double *op, int rows, int cols)
 {
-  const int RB = (rows + 7) / 8, KB = (cols + 3) / 4;
+  const int RB = (rows + 7) / 8, KB = ((cols + 3) / 4 + 1) & ~1; // k steps padded to pairs (run_phase)
   std::vector<double> out((size_t)RB * KB * 32, 0.0);
   for (int rb = 0; rb < RB; rb++)
     for (int kk = 0; kk < KB; kk++)
@@ -404,7 +438,7 @@ struct hf_elem_type
   bool ready = false;
   double *op0 = nullptr, *op1[3] = {nullptr, nullptr, nullptr}, *op2[3] = {nullptr, nullptr, nullptr}, *op3 = nullptr;
   double *op4[3] = {nullptr, nullptr, nullptr}, *op5[3] = {nullptr, nullptr, nullptr}, *op6 = nullptr;
-  int E = 0, mb = 0, SU = 0, SF = 0;
+  int E = 0, mb = 0, Eg = 0, mbg = 0, SU = 0, SF = 0; // tile of k_elem_resid / k_elem_face (E, mb) and of k_elem_grad (Eg, mbg)
   size_t smem_resid = 0, smem_grad = 0;
 };
 struct hf_elem_state
@@ -430,32 +464,37 @@ int hf_elem_on_upload(hf_ctx *c, hf_eles_dev &e, const hf_eles_desc *d)
     if (visc && (up(&T.op4[i], d->opp_4[i], nu, nu) || up(&T.op5[i], d->opp_5[i], nu, nf))) return 1;
   }
   if (visc && up(&T.op6, d->opp_6, nf, nu)) return 1;
-  const int nup = round_up(nu, 8), nfp = round_up(nf, 8);
+  const int nup = round_up(nu, 8), nfp = round_up(nf, 8); // multiples of 8 also cover the k steps padded to pairs (8 points)
   T.SU = nup + 4;
   T.SF = (nfp > nup ? nfp : nup) + 4; // the divergence (solution points) is accumulated in a flux-point buffer
   // elements per CTA: whole 8-column blocks with little padding, shared memory for three CTAs per SM if the element allows it
   auto bytes_resid = [&](int mb) { return sizeof(double) * ((size_t)mb * 8 * ((size_t)T.SU * (1 + nd) + 2 * (size_t)T.SF) + (size_t)((mb * 8 / NF * nu + 1) & ~1)); };
   auto bytes_grad = [&](int mb) { return sizeof(double) * (size_t)mb * 8 * ((size_t)T.SU * (1 + nd) + (size_t)T.SF * (1 + nd)); };
-  int best = 0;
-  double best_score = -1.0;
-  const char *force = getenv("HF_ELEM_E");
   const size_t budget = (getenv("HF_ELEM_KB") ? (size_t)atoi(getenv("HF_ELEM_KB")) : 72) * 1024; // measurement aid: shared memory per CTA to aim for
-  for (int E = 1; E <= 64; E++)
-  {
-    const int mb = round_up(E * NF, 8) / 8;
-    const size_t b = (visc && bytes_grad(mb) > bytes_resid(mb)) ? bytes_grad(mb) : bytes_resid(mb);
-    if (b > 200 * 1024) break;
-    const double eff = (double)(E * NF) / (mb * 8);
-    // prefer: fits three per SM (72 kB), then padding efficiency, then more columns (operator fragments amortised, more warp tasks)
-    double score = eff + (b <= budget ? 1.0 : (b <= 110 * 1024 ? 0.5 : 0.0)) + 0.002 * (mb > 12 ? 12 : mb);
-    if (force && atoi(force) == E) score = 100.0;
-    if (score > best_score) { best_score = score; best = E; }
-  }
-  if (best == 0) return 0; // element too large for a shared-memory tile: the staged kernels run
-  T.E = best;
-  T.mb = round_up(best * NF, 8) / 8;
+  auto pick = [&](auto bytes, const char *force_env) {
+    int best = 0;
+    double best_score = -1.0;
+    const char *force = getenv(force_env);
+    for (int E = 1; E <= 64; E++)
+    {
+      const int mb = round_up(E * NF, 8) / 8;
+      const size_t b = bytes(mb);
+      if (b > 200 * 1024) break;
+      const double eff = (double)(E * NF) / (mb * 8);
+      // prefer: fits three per SM, then padding efficiency, then more columns (operator fragments amortised, more warp tasks)
+      double score = eff + (b <= budget ? 1.0 : (b <= 110 * 1024 ? 0.5 : 0.0)) + 0.002 * (mb > 12 ? 12 : mb);
+      if (force && atoi(force) == E) score = 100.0;
+      if (score > best_score) { best_score = score; best = E; }
+    }
+    return best;
+  };
+  T.E = pick(bytes_resid, "HF_ELEM_E");
+  T.Eg = visc ? pick(bytes_grad, "HF_ELEM_EG") : T.E;
+  if (T.E == 0 || T.Eg == 0) return 0; // element too large for a shared-memory tile: the staged kernels run
+  T.mb = round_up(T.E * NF, 8) / 8;
+  T.mbg = round_up(T.Eg * NF, 8) / 8;
   T.smem_resid = bytes_resid(T.mb);
-  T.smem_grad = bytes_grad(T.mb);
+  T.smem_grad = bytes_grad(T.mbg);
   T.ready = true;
   return 0;
 }
@@ -482,13 +521,14 @@ int hf_elem_available(hf_ctx *c)
   return !off && strcmp(hf_elem_status(c), "available") == 0;
 }
 
-static void fill_args(hf_ctx *c, hf_eles_dev &e, const hf_elem_type &T, el_args &A)
+static void fill_args(hf_ctx *c, hf_eles_dev &e, const hf_elem_type &T, el_args &A, bool grad_kernel = false)
 {
   memset(&A, 0, sizeof(A));
+  const int E = grad_kernel ? T.Eg : T.E, mb = grad_kernel ? T.mbg : T.mb;
   const int nd = e.n_dims;
   const bool visc = c->prm.viscous != 0;
-  A.n_eles = e.n_eles; A.nu = e.n_upts; A.nf = e.n_fpts; A.E = T.E; A.mb = T.mb; A.SU = T.SU; A.SF = T.SF;
-  const int ncp = T.mb * 8;
+  A.n_eles = e.n_eles; A.nu = e.n_upts; A.nf = e.n_fpts; A.E = E; A.mb = mb; A.mg_u = (unsigned)((0x100000000ull + e.n_upts - 1) / e.n_upts); A.mg_f = (unsigned)((0x100000000ull + e.n_fpts - 1) / e.n_fpts); A.SU = T.SU; A.SF = T.SF;
+  const int ncp = mb * 8;
   A.o_u = 0;
   A.o_g = ncp * T.SU;
   A.o_dl = A.o_g + nd * ncp * T.SU;
@@ -502,7 +542,7 @@ static void fill_args(hf_ctx *c, hf_eles_dev &e, const hf_elem_type &T, el_args 
   A.detjac_u = e.detjac_upts; A.JG_u = e.JGinv_upts; A.detjac_f = e.detjac_fpts; A.JG_f = e.JGinv_fpts;
   A.nan_flag = c->d_nan;
   A.P = c->phys;
-  const int kbu = (e.n_upts + 3) / 4, kbf = (e.n_fpts + 3) / 4, rbu = (e.n_upts + 7) / 8, rbf = (e.n_fpts + 7) / 8;
+  const int kbu = ((e.n_upts + 3) / 4 + 1) & ~1, kbf = ((e.n_fpts + 3) / 4 + 1) & ~1, rbu = (e.n_upts + 7) / 8, rbf = (e.n_fpts + 7) / 8;
   // reference-space gradient, corrected: opp_4(d) u + opp_5(d) delta
   A.ph_grad.n = visc ? nd : 0;
   for (int d = 0; d < nd && visc; d++)
@@ -546,7 +586,7 @@ static void fill_args(hf_ctx *c, hf_eles_dev &e, const hf_elem_type &T, el_args 
 
 #define EL_LAUNCH(KERNEL, smem)                                                                                          \
   do {                                                                                                                   \
-    const unsigned grid = (unsigned)((e.n_eles + T.E - 1) / T.E);                                                        \
+    const unsigned grid = (unsigned)((e.n_eles + A.E - 1) / A.E);                                                        \
     if (nd == 3 && nfl == 5) KERNEL<3, 5><<<grid, EL_THREADS, smem, c->stream>>>(A);                                     \
     else if (nd == 2 && nfl == 4) KERNEL<2, 4><<<grid, EL_THREADS, smem, c->stream>>>(A);                                \
     else if (nd == 2 && nfl == 1) KERNEL<2, 1><<<grid, EL_THREADS, smem, c->stream>>>(A);                                \
@@ -615,7 +655,7 @@ int hf_elem_stage(hf_ctx *c, int rk_stage, double time, int keep_residual)
       const hf_elem_type &T = c->ez->t[t];
       const int nd = e.n_dims, nfl = e.n_fields;
       el_args A;
-      fill_args(c, e, T, A);
+      fill_args(c, e, T, A, true);
       A.smem_doubles = T.smem_grad / sizeof(double);
       EL_LAUNCH(k_elem_grad, T.smem_grad);
     }
