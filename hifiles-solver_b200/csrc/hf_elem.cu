@@ -33,10 +33,11 @@ namespace
 {
 constexpr int EL_THREADS = 256;
 
+// host-side description of one product: dst (mode) sum_t op_t * src_t
 struct el_term
 {
   const double *op; // operator in fragment order: [row block][k step][lane]
-  int kb;           // k steps (4 points each)
+  int kb;           // k steps (4 points each), even
   int src, ss;      // shared-memory offset and column stride of the data (doubles)
 };
 struct el_prod
@@ -46,9 +47,20 @@ struct el_prod
   int dst, ds;     // shared-memory offset and column stride of the result
   int mode;        // 0 dst = acc, 1 dst += acc, 2 dst -= acc
 };
+// what a warp executes: one block of 8 operator rows against two column blocks, every offset resolved on the host (decoding
+// (product, row block, column group) per task in the kernel cost four times the instructions of the tensor-core loop itself)
+struct el_task
+{
+  int n_terms, mode, dst, ds, two, pad;
+  struct
+  {
+    const double *op; // already at the task's row block
+    int kb2, src, ss, pad;
+  } t[4];
+};
 struct el_phase
 {
-  el_prod p[3];
+  const el_task *tasks;
   int n;
 };
 
@@ -82,28 +94,21 @@ __device__ __forceinline__ void dmma884(double &d0, double &d1, double a, double
 // (zero fragments) and a task always works on two column blocks (the second one a copy of the first when the tile has an odd
 // block left over, its result dropped), so the inner loop carries no predicate: 2 fragment loads, 4 data loads, 4 DMMA per
 // iteration, the next iteration's fragments requested before this one's tensor-core instructions.
-__device__ __forceinline__ void run_phase(const el_phase &PH, int mb, double *sm)
+__device__ __forceinline__ void run_phase(const el_phase &PH, double *sm)
 {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
   const int ar = lane >> 2, ak = lane & 3;
-  const int ng = (mb + 1) >> 1;
-  int total = 0;
-  for (int p = 0; p < PH.n; p++) total += PH.p[p].rb * ng;
-  for (int task = warp; task < total; task += nw)
+  for (int task = warp; task < PH.n; task += nw)
   {
-    int p = 0, loc = task;
-    while (loc >= PH.p[p].rb * ng) { loc -= PH.p[p].rb * ng; p++; }
-    const el_prod &Q = PH.p[p];
-    const int rb = loc / ng, cb0 = (loc - rb * ng) * 2;
-    const bool two = cb0 + 1 < mb;
+    const el_task *K = PH.tasks + task;
+    const int nt = __ldg(&K->n_terms), mode = __ldg(&K->mode), ds = __ldg(&K->ds);
+    const bool two = __ldg(&K->two) != 0;
     double a00 = 0.0, a01 = 0.0, a10 = 0.0, a11 = 0.0;
-    const int nt = Q.n_terms;
     for (int t = 0; t < nt; t++)
     {
-      const el_term &T = Q.t[t];
-      const int kb2 = T.kb >> 1, ss = T.ss;
-      const double *opf = T.op + (size_t)rb * T.kb * 32 + lane;
-      const double *s0 = sm + T.src + (cb0 * 8 + ar) * ss + ak;
+      const int kb2 = __ldg(&K->t[t].kb2), ss = __ldg(&K->t[t].ss);
+      const double *opf = reinterpret_cast<const double *>(__ldg(reinterpret_cast<const unsigned long long *>(&K->t[t].op))) + lane;
+      const double *s0 = sm + __ldg(&K->t[t].src) + ar * ss + ak;
       const double *s1 = two ? s0 + 8 * ss : s0;
       double b0 = __ldg(opf), b1 = __ldg(opf + 32);
       for (int q = 0; q < kb2; q++)
@@ -119,9 +124,8 @@ __device__ __forceinline__ void run_phase(const el_phase &PH, int mb, double *sm
         b0 = n0; b1 = n1;
       }
     }
-    const int mode = Q.mode;
-    double2 *d0 = reinterpret_cast<double2 *>(sm + Q.dst + (cb0 * 8 + ar) * Q.ds + rb * 8 + 2 * ak);
-    double2 *d1 = d0 + 4 * Q.ds; // 8 columns further, in double2 units
+    double2 *d0 = reinterpret_cast<double2 *>(sm + __ldg(&K->dst) + ar * ds + 2 * ak);
+    double2 *d1 = d0 + 4 * ds; // 8 columns further, in double2 units
     if (mode == 0)
     {
       *d0 = make_double2(a00, a01);
@@ -242,9 +246,9 @@ __global__ void __launch_bounds__(EL_THREADS, 2) k_elem_grad(const __grid_consta
   load_cols<NF>(A, sm + A.o_dl, A.SF, A.delu, A.nf, A.mg_f, e0, ne);
   cp_async_wait_all();
   __syncthreads();
-  run_phase(A.ph_grad, A.mb, sm);
+  run_phase(A.ph_grad, sm);
   __syncthreads();
-  run_phase(A.ph_gf, A.mb, sm);
+  run_phase(A.ph_gf, sm);
   __syncthreads();
   const size_t NFP = (size_t)A.nf * A.n_eles;
   for (int i = threadIdx.x; i < ne * A.nf; i += blockDim.x)
@@ -265,8 +269,8 @@ __global__ void __launch_bounds__(EL_THREADS, 2) k_elem_grad(const __grid_consta
   }
 }
 
-template <int ND, int NF>
-__global__ void __launch_bounds__(EL_THREADS, 2) k_elem_resid(const __grid_constant__ el_args A)
+template <int ND, int NF, int MINB>
+__global__ void __launch_bounds__(EL_THREADS, MINB) k_elem_resid(const __grid_constant__ el_args A)
 {
   extern __shared__ __align__(16) double sm[];
   const int e0 = blockIdx.x * A.E;
@@ -283,7 +287,7 @@ __global__ void __launch_bounds__(EL_THREADS, 2) k_elem_resid(const __grid_const
   __syncthreads();
   if (A.visc)
   {
-    run_phase(A.ph_grad, A.mb, sm);
+    run_phase(A.ph_grad, sm);
     __syncthreads();
   }
   // fluxes at the solution points, transformed, in place over the gradient
@@ -346,12 +350,12 @@ __global__ void __launch_bounds__(EL_THREADS, 2) k_elem_resid(const __grid_const
       for (int k = 0; k < NF; k++) sm[A.o_g + (l * ncp + k * A.E + el) * A.SU + pt] = t[k + NF * l];
   }
   __syncthreads();
-  run_phase(A.ph_div, A.mb, sm); // divergence -> o_dl; common minus own normal flux -> o_fc
+  run_phase(A.ph_div, sm); // divergence -> o_dl; common minus own normal flux -> o_fc
   __syncthreads();
   // the flux planes are dead: the second RK register travels into the first of them while the correction product runs
   const bool need_u1 = A.rk_mode == 2 || (A.rk_mode == 1 && !A.rk_copy);
   if (need_u1) load_cols<NF>(A, sm + A.o_g, A.SU, A.u1, A.nu, A.mg_u, e0, ne);
-  run_phase(A.ph_corr, A.mb, sm); // + opp_3 (common - own)
+  run_phase(A.ph_corr, sm); // + opp_3 (common - own)
   cp_async_wait_all();
   __syncthreads();
   // RK update (the arithmetic of k_rk_update, reference src/eles.cpp:1080-1265)
@@ -393,7 +397,7 @@ __global__ void __launch_bounds__(EL_THREADS, 2) k_elem_resid(const __grid_const
     }
   }
   __syncthreads();
-  run_phase(A.ph_face, A.mb, sm); // opp_0 of the updated solution -> o_fc
+  run_phase(A.ph_face, sm); // opp_0 of the updated solution -> o_fc
   __syncthreads();
   store_cols<NF>(A, sm + A.o_fc, A.SF, A.disu_fpts, A.nf, A.mg_f, e0, ne);
 }
@@ -410,7 +414,7 @@ __global__ void __launch_bounds__(EL_THREADS, 2) k_elem_face(const __grid_consta
   load_cols<NF>(A, sm + A.o_u, A.SU, A.u_in, A.nu, A.mg_u, e0, ne);
   cp_async_wait_all();
   __syncthreads();
-  run_phase(A.ph_face, A.mb, sm);
+  run_phase(A.ph_face, sm);
   __syncthreads();
   store_cols<NF>(A, sm + A.o_fc, A.SF, A.disu_fpts, A.nf, A.mg_f, e0, ne);
 }
@@ -440,12 +444,16 @@ struct hf_elem_type
   double *op4[3] = {nullptr, nullptr, nullptr}, *op5[3] = {nullptr, nullptr, nullptr}, *op6 = nullptr;
   int E = 0, mb = 0, Eg = 0, mbg = 0, SU = 0, SF = 0; // tile of k_elem_resid / k_elem_face (E, mb) and of k_elem_grad (Eg, mbg)
   size_t smem_resid = 0, smem_grad = 0;
+  // task tables on the device: [0] k_elem_resid / k_elem_face, [1] k_elem_grad; phases grad, gf, div, corr, face
+  el_phase ph[2][5];
 };
 struct hf_elem_state
 {
   hf_elem_type t[HF_N_ELE_TYPES];
   bool attr_done = false;
 };
+
+static int build_phases(hf_ctx *c, const hf_eles_dev &e, struct hf_elem_type &T);
 
 int hf_elem_on_upload(hf_ctx *c, hf_eles_dev &e, const hf_eles_desc *d)
 {
@@ -495,6 +503,7 @@ int hf_elem_on_upload(hf_ctx *c, hf_eles_dev &e, const hf_eles_desc *d)
   T.mbg = round_up(T.Eg * NF, 8) / 8;
   T.smem_resid = bytes_resid(T.mb);
   T.smem_grad = bytes_grad(T.mbg);
+  if (build_phases(c, e, T)) return 1;
   T.ready = true;
   return 0;
 }
@@ -521,20 +530,130 @@ int hf_elem_available(hf_ctx *c)
   return !off && strcmp(hf_elem_status(c), "available") == 0;
 }
 
+struct el_layout
+{
+  int o_u, o_g, o_dl, o_fc, o_gf, o_dj;
+};
+static el_layout layout_of(const hf_elem_type &T, int nd, int mb)
+{
+  el_layout L;
+  const int ncp = mb * 8;
+  L.o_u = 0;
+  L.o_g = ncp * T.SU;
+  L.o_dl = L.o_g + nd * ncp * T.SU;
+  L.o_fc = L.o_dl + ncp * T.SF; // k_elem_resid
+  L.o_gf = L.o_dl + ncp * T.SF; // k_elem_grad
+  L.o_dj = L.o_fc + ncp * T.SF; // k_elem_resid: detjac at the tile's solution points
+  return L;
+}
+
+// products of a phase -> warp tasks (row block x pair of column blocks), uploaded once per element type
+static int compile_phase(hf_ctx *c, const std::vector<el_prod> &prods, int mb, el_phase *out)
+{
+  std::vector<el_task> tasks;
+  const int ng = (mb + 1) / 2;
+  for (const el_prod &Q : prods)
+    for (int rb = 0; rb < Q.rb; rb++)
+      for (int g = 0; g < ng; g++)
+      {
+        el_task K;
+        memset(&K, 0, sizeof(K));
+        K.n_terms = Q.n_terms; K.mode = Q.mode; K.ds = Q.ds;
+        K.two = (2 * g + 1 < mb) ? 1 : 0;
+        K.dst = Q.dst + 2 * g * 8 * Q.ds + rb * 8;
+        for (int t = 0; t < Q.n_terms; t++)
+        {
+          K.t[t].op = Q.t[t].op + (size_t)rb * Q.t[t].kb * 32;
+          K.t[t].kb2 = Q.t[t].kb / 2;
+          K.t[t].src = Q.t[t].src + 2 * g * 8 * Q.t[t].ss;
+          K.t[t].ss = Q.t[t].ss;
+        }
+        tasks.push_back(K);
+      }
+  out->n = (int)tasks.size();
+  out->tasks = nullptr;
+  if (tasks.empty()) return 0;
+  el_task *d = nullptr;
+  if (hf_alloc_copy(c, &d, tasks.data(), tasks.size())) return 1;
+  out->tasks = d;
+  return 0;
+}
+
+static int build_phases(hf_ctx *c, const hf_eles_dev &e, hf_elem_type &T)
+{
+  const int nd = e.n_dims;
+  const bool visc = c->prm.viscous != 0;
+  const int kbu = ((e.n_upts + 3) / 4 + 1) & ~1, kbf = ((e.n_fpts + 3) / 4 + 1) & ~1, rbu = (e.n_upts + 7) / 8, rbf = (e.n_fpts + 7) / 8;
+  for (int which = 0; which < 2; which++)
+  {
+    const int mb = which ? T.mbg : T.mb, ncp = mb * 8;
+    const el_layout L = layout_of(T, nd, mb);
+    std::vector<el_prod> grad, gf, div, corr, face;
+    // reference-space gradient, corrected: opp_4(d) u + opp_5(d) delta
+    for (int d = 0; d < nd && visc; d++)
+    {
+      el_prod Q;
+      memset(&Q, 0, sizeof(Q));
+      Q.n_terms = 2; Q.rb = rbu; Q.dst = L.o_g + d * ncp * T.SU; Q.ds = T.SU; Q.mode = 0;
+      Q.t[0] = {T.op4[d], kbu, L.o_u, T.SU};
+      Q.t[1] = {T.op5[d], kbf, L.o_dl, T.SF};
+      grad.push_back(Q);
+    }
+    if (which == 1)
+    {
+      // gradient at the flux points: opp_6 g(d)
+      for (int d = 0; d < nd && visc; d++)
+      {
+        el_prod Q;
+        memset(&Q, 0, sizeof(Q));
+        Q.n_terms = 1; Q.rb = rbf; Q.dst = L.o_gf + d * ncp * T.SF; Q.ds = T.SF; Q.mode = 0;
+        Q.t[0] = {T.op6, kbu, L.o_g + d * ncp * T.SU, T.SU};
+        gf.push_back(Q);
+      }
+    }
+    else
+    {
+      // divergence sum_d opp_2(d) f(d) -> o_dl;  o_fc -= sum_d opp_1(d) f(d)
+      el_prod Q, R;
+      memset(&Q, 0, sizeof(Q));
+      memset(&R, 0, sizeof(R));
+      Q.n_terms = nd; Q.rb = rbu; Q.dst = L.o_dl; Q.ds = T.SF; Q.mode = 0;
+      R.n_terms = nd; R.rb = rbf; R.dst = L.o_fc; R.ds = T.SF; R.mode = 2;
+      for (int d = 0; d < nd; d++)
+      {
+        Q.t[d] = {T.op2[d], kbu, L.o_g + d * ncp * T.SU, T.SU};
+        R.t[d] = {T.op1[d], kbu, L.o_g + d * ncp * T.SU, T.SU};
+      }
+      div.push_back(R); // the longer tasks first
+      div.push_back(Q);
+      el_prod C;
+      memset(&C, 0, sizeof(C));
+      C.n_terms = 1; C.rb = rbu; C.dst = L.o_dl; C.ds = T.SF; C.mode = 1;
+      C.t[0] = {T.op3, kbf, L.o_fc, T.SF};
+      corr.push_back(C);
+      el_prod F;
+      memset(&F, 0, sizeof(F));
+      F.n_terms = 1; F.rb = rbf; F.dst = L.o_fc; F.ds = T.SF; F.mode = 0;
+      F.t[0] = {T.op0, kbu, L.o_u, T.SU};
+      face.push_back(F);
+    }
+    if (compile_phase(c, grad, mb, &T.ph[which][0]) || compile_phase(c, gf, mb, &T.ph[which][1]) || compile_phase(c, div, mb, &T.ph[which][2]) ||
+        compile_phase(c, corr, mb, &T.ph[which][3]) || compile_phase(c, face, mb, &T.ph[which][4])) return 1;
+  }
+  return 0;
+}
+
 static void fill_args(hf_ctx *c, hf_eles_dev &e, const hf_elem_type &T, el_args &A, bool grad_kernel = false)
 {
   memset(&A, 0, sizeof(A));
   const int E = grad_kernel ? T.Eg : T.E, mb = grad_kernel ? T.mbg : T.mb;
-  const int nd = e.n_dims;
   const bool visc = c->prm.viscous != 0;
-  A.n_eles = e.n_eles; A.nu = e.n_upts; A.nf = e.n_fpts; A.E = E; A.mb = mb; A.mg_u = (unsigned)((0x100000000ull + e.n_upts - 1) / e.n_upts); A.mg_f = (unsigned)((0x100000000ull + e.n_fpts - 1) / e.n_fpts); A.SU = T.SU; A.SF = T.SF;
-  const int ncp = mb * 8;
-  A.o_u = 0;
-  A.o_g = ncp * T.SU;
-  A.o_dl = A.o_g + nd * ncp * T.SU;
-  A.o_fc = A.o_dl + ncp * T.SF; // k_elem_resid
-  A.o_gf = A.o_dl + ncp * T.SF; // k_elem_grad
-  A.o_dj = A.o_fc + ncp * T.SF; // k_elem_resid: detjac at the tile's solution points
+  A.n_eles = e.n_eles; A.nu = e.n_upts; A.nf = e.n_fpts; A.E = E; A.mb = mb;
+  A.mg_u = (unsigned)((0x100000000ull + e.n_upts - 1) / e.n_upts);
+  A.mg_f = (unsigned)((0x100000000ull + e.n_fpts - 1) / e.n_fpts);
+  A.SU = T.SU; A.SF = T.SF;
+  const el_layout L = layout_of(T, e.n_dims, mb);
+  A.o_u = L.o_u; A.o_g = L.o_g; A.o_dl = L.o_dl; A.o_fc = L.o_fc; A.o_gf = L.o_gf; A.o_dj = L.o_dj;
   A.visc = visc;
   A.u_in = e.disu_upts[0]; A.u0 = e.disu_upts[0]; A.u1 = e.disu_upts[1];
   A.delu = e.delta_disu_fpts; A.ntconf = e.norm_tconf_fpts; A.disu_fpts = e.disu_fpts; A.grad_fpts = e.grad_disu_fpts;
@@ -542,46 +661,8 @@ static void fill_args(hf_ctx *c, hf_eles_dev &e, const hf_elem_type &T, el_args 
   A.detjac_u = e.detjac_upts; A.JG_u = e.JGinv_upts; A.detjac_f = e.detjac_fpts; A.JG_f = e.JGinv_fpts;
   A.nan_flag = c->d_nan;
   A.P = c->phys;
-  const int kbu = ((e.n_upts + 3) / 4 + 1) & ~1, kbf = ((e.n_fpts + 3) / 4 + 1) & ~1, rbu = (e.n_upts + 7) / 8, rbf = (e.n_fpts + 7) / 8;
-  // reference-space gradient, corrected: opp_4(d) u + opp_5(d) delta
-  A.ph_grad.n = visc ? nd : 0;
-  for (int d = 0; d < nd && visc; d++)
-  {
-    el_prod &Q = A.ph_grad.p[d];
-    Q.n_terms = 2; Q.rb = rbu; Q.dst = A.o_g + d * ncp * T.SU; Q.ds = T.SU; Q.mode = 0;
-    Q.t[0] = {T.op4[d], kbu, A.o_u, T.SU};
-    Q.t[1] = {T.op5[d], kbf, A.o_dl, T.SF};
-  }
-  // gradient at the flux points: opp_6 g(d)
-  A.ph_gf.n = visc ? nd : 0;
-  for (int d = 0; d < nd && visc; d++)
-  {
-    el_prod &Q = A.ph_gf.p[d];
-    Q.n_terms = 1; Q.rb = rbf; Q.dst = A.o_gf + d * ncp * T.SF; Q.ds = T.SF; Q.mode = 0;
-    Q.t[0] = {T.op6, kbu, A.o_g + d * ncp * T.SU, T.SU};
-  }
-  // divergence sum_d opp_2(d) f(d) -> o_dl;  o_fc -= sum_d opp_1(d) f(d)
-  A.ph_div.n = 2;
-  {
-    el_prod &Q = A.ph_div.p[0];
-    Q.n_terms = nd; Q.rb = rbu; Q.dst = A.o_dl; Q.ds = T.SF; Q.mode = 0;
-    for (int d = 0; d < nd; d++) Q.t[d] = {T.op2[d], kbu, A.o_g + d * ncp * T.SU, T.SU};
-    el_prod &R = A.ph_div.p[1];
-    R.n_terms = nd; R.rb = rbf; R.dst = A.o_fc; R.ds = T.SF; R.mode = 2;
-    for (int d = 0; d < nd; d++) R.t[d] = {T.op1[d], kbu, A.o_g + d * ncp * T.SU, T.SU};
-  }
-  A.ph_corr.n = 1;
-  {
-    el_prod &Q = A.ph_corr.p[0];
-    Q.n_terms = 1; Q.rb = rbu; Q.dst = A.o_dl; Q.ds = T.SF; Q.mode = 1;
-    Q.t[0] = {T.op3, kbf, A.o_fc, T.SF};
-  }
-  A.ph_face.n = 1;
-  {
-    el_prod &Q = A.ph_face.p[0];
-    Q.n_terms = 1; Q.rb = rbf; Q.dst = A.o_fc; Q.ds = T.SF; Q.mode = 0;
-    Q.t[0] = {T.op0, kbu, A.o_u, T.SU};
-  }
+  const int w = grad_kernel ? 1 : 0;
+  A.ph_grad = T.ph[w][0]; A.ph_gf = T.ph[w][1]; A.ph_div = T.ph[w][2]; A.ph_corr = T.ph[w][3]; A.ph_face = T.ph[w][4];
 }
 
 #define EL_LAUNCH(KERNEL, smem)                                                                                          \
@@ -602,7 +683,8 @@ static int set_attrs(hf_ctx *c)
   const int lim = 200 * 1024;
 #define EL_ATTR(K) HF_CUDA(cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, lim))
   EL_ATTR((k_elem_grad<3, 5>)); EL_ATTR((k_elem_grad<2, 4>)); EL_ATTR((k_elem_grad<2, 1>)); EL_ATTR((k_elem_grad<3, 1>));
-  EL_ATTR((k_elem_resid<3, 5>)); EL_ATTR((k_elem_resid<2, 4>)); EL_ATTR((k_elem_resid<2, 1>)); EL_ATTR((k_elem_resid<3, 1>));
+  EL_ATTR((k_elem_resid<3, 5, 2>)); EL_ATTR((k_elem_resid<2, 4, 2>)); EL_ATTR((k_elem_resid<2, 1, 2>)); EL_ATTR((k_elem_resid<3, 1, 2>));
+  EL_ATTR((k_elem_resid<3, 5, 3>)); EL_ATTR((k_elem_resid<2, 4, 3>)); EL_ATTR((k_elem_resid<2, 1, 3>)); EL_ATTR((k_elem_resid<3, 1, 3>));
   EL_ATTR((k_elem_face<3, 5>)); EL_ATTR((k_elem_face<2, 4>)); EL_ATTR((k_elem_face<2, 1>)); EL_ATTR((k_elem_face<3, 1>));
 #undef EL_ATTR
   c->ez->attr_done = true;
@@ -681,7 +763,25 @@ int hf_elem_stage(hf_ctx *c, int rk_stage, double time, int keep_residual)
     A.dt = c->prm.dt;
     A.dt_local = (c->prm.dt_type == 2) ? e.dt_local : nullptr;
     if (hf_rk_coeffs(c, stage, &A.rk_mode, &A.rk_copy, &A.fac, &A.c1, &A.c2)) return 1;
-    EL_LAUNCH(k_elem_resid, T.smem_resid);
+    {
+      // three CTAs per SM at 80 registers (a few spills in the flux phase) against two at 112 - 128: chosen by measurement
+      static const int minb = getenv("HF_ELEM_MINB") ? atoi(getenv("HF_ELEM_MINB")) : 3;
+      const unsigned grid = (unsigned)((e.n_eles + A.E - 1) / A.E);
+      const size_t smem = T.smem_resid;
+#define EL_RESID(ND_, NF_)                                                                                 \
+      do {                                                                                                 \
+        if (minb >= 3) k_elem_resid<ND_, NF_, 3><<<grid, EL_THREADS, smem, c->stream>>>(A);                \
+        else k_elem_resid<ND_, NF_, 2><<<grid, EL_THREADS, smem, c->stream>>>(A);                          \
+      } while (0)
+      if (nd == 3 && nfl == 5) EL_RESID(3, 5);
+      else if (nd == 2 && nfl == 4) EL_RESID(2, 4);
+      else if (nd == 2 && nfl == 1) EL_RESID(2, 1);
+      else EL_RESID(3, 1);
+#undef EL_RESID
+      c->launches++;
+      cudaError_t e_ = cudaGetLastError();
+      if (e_ != cudaSuccess) { hf_set_error(std::string("kernel launch (k_elem_resid): ") + cudaGetErrorString(e_)); return 1; }
+    }
   }
   c->ufpts_valid = true;
   return 0;
