@@ -279,6 +279,22 @@ def run_other_config(args):
     roofline = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
                 "kernel": None, "algorithmic_bytes_per_dof_stage": bpd, "peak_source": peak_src,
                 "note": "whole stage (element kernels + interface kernels) against the algorithmic bytes of SURVEY 8(d), face term weighted over the element types"}
+    # dense-operator element types (triangles, tetrahedra, prisms): SURVEY 8(d) names the FP64 pipe as the relevant bound.  Algorithmic
+    # flops of the dense operator chain per element and stage: 2 F [Nf Nu (opp_0) + D Nf Nu (opp_1) + D Nu^2 (opp_2) + Nu Nf (opp_3)
+    # + viscous: D Nu^2 (opp_4) + D Nu Nf (opp_5) + D Nf Nu (opp_6)]; peak = the DMMA rate measured on this pool's B200
+    # (profiles/microbench/dmma_b200.txt: 62.9 FMA/clk/SM = 36.6 TFLOP/s, which is also the DFMA rate)
+    flops = 0.0
+    for t in types:
+        nu_t, ne_t, nf_t = shapes[t]
+        nfp_t = fpts[t](args.order_cfg)
+        per_ele = 2.0 * nf_t * (nfp_t * nu_t * (1 + n_dims) + n_dims * nu_t ** 2 + nu_t * nfp_t + (n_dims * nu_t ** 2 + 2 * n_dims * nu_t * nfp_t if visc else 0))
+        flops += per_ele * ne_t
+    tf = flops * n_rk * args.steps / (ms * 1e-3) / 1e12
+    roofline["fp64"] = {"achieved": tf, "peak": 36.6, "unit": "TFLOP/s", "frac": tf / 36.6, "algorithmic_flop_per_dof_stage": flops / dof,
+                        "peak_source": "profiles/microbench/dmma_b200.txt (measured DMMA m8n8k4 rate, B200)"}
+    if tf / 36.6 > ach / peak:
+        roofline["bound"] = "tensor"
+        roofline["note"] += "; dense operators: the FP64 tensor-core view (roofline.fp64) is the tighter bound"
     e2e = None
     if not args.no_e2e:
         lib = hb.lib()

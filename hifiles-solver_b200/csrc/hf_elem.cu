@@ -478,7 +478,9 @@ int hf_elem_on_upload(hf_ctx *c, hf_eles_dev &e, const hf_eles_desc *d)
   // elements per CTA: whole 8-column blocks with little padding, shared memory for three CTAs per SM if the element allows it
   auto bytes_resid = [&](int mb) { return sizeof(double) * ((size_t)mb * 8 * ((size_t)T.SU * (1 + nd) + 2 * (size_t)T.SF) + (size_t)((mb * 8 / NF * nu + 1) & ~1)); };
   auto bytes_grad = [&](int mb) { return sizeof(double) * (size_t)mb * 8 * ((size_t)T.SU * (1 + nd) + (size_t)T.SF * (1 + nd)); };
-  const size_t budget = (getenv("HF_ELEM_KB") ? (size_t)atoi(getenv("HF_ELEM_KB")) : 72) * 1024; // measurement aid: shared memory per CTA to aim for
+  // shared memory per CTA to aim for (measured, GDOF-stage/s at 48 / 72 / 100 kB: quadrilaterals P=3 32.1 / 30.4 / 30.1, triangles +
+  // quadrilaterals 10.0 / 9.4 / -, tetrahedra + prisms 2.84 / 3.29 / 3.13); HF_ELEM_KB overrides
+  const size_t budget = (getenv("HF_ELEM_KB") ? (size_t)atoi(getenv("HF_ELEM_KB")) : (nd == 2 ? 48 : 72)) * 1024;
   auto pick = [&](auto bytes, const char *force_env) {
     int best = 0;
     double best_score = -1.0;
