@@ -23,10 +23,10 @@ for f in $SRCS HiFiLES; do
   pids+=($!)
 done
 for p in "${pids[@]}"; do wait $p; done
-g++ $(ls "$OUT"/obj/*.o | grep -v '/ref_dump.o$') -o "$OUT/HiFiLES_ref"
+g++ $(ls "$OUT"/obj/*.o | grep -v '/ref_dump.o$' | grep -v '/ref_gpu.o$') -o "$OUT/HiFiLES_ref"
 # instrumented dumper (our own TU, oracle/ref_dump.cpp) linked against the reference objects minus its main()
 if [ -f "$HERE/ref_dump.cpp" ]; then
-  objs=$(ls "$OUT"/obj/*.o | grep -v '/HiFiLES.o$' | grep -v '/ref_dump.o$')
+  objs=$(ls "$OUT"/obj/*.o | grep -v '/HiFiLES.o$' | grep -v '/ref_dump.o$' | grep -v '/ref_gpu.o$')
   g++ $CXXFLAGS -c "$HERE/ref_dump.cpp" -o "$OUT/obj/ref_dump.o"
   g++ "$OUT/obj/ref_dump.o" $objs -o "$OUT/ref_dump"
 fi
