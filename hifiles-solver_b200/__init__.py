@@ -71,6 +71,7 @@ def lib():
     L.hf_dev_advance_solution.argtypes = [C.c_void_p, C.c_int]
     L.hf_dev_rk_stage.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_int]
     L.hf_dev_run_steps.argtypes = [C.c_void_p, C.c_int, C.c_double]
+    L.hf_dev_check_residual.argtypes = [C.c_void_p]
     L.hf_dev_download.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_size_t]
     L.hf_dev_upload.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_size_t]
     L.hf_dev_upload_begin.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_size_t]

@@ -2014,7 +2014,7 @@ static int advance_one(hf_ctx *c, hf_eles_dev &e, int stage)
 }
 
 // rk_stage: bits 0-7 the stage; bits 8.. = 1 + element type to advance one type only (0 = all types)
-int hf_dev_advance_solution(hf_ctx *c, int rk_stage)
+static int advance_all(hf_ctx *c, int rk_stage)
 {
   if (!c->finalized) HF_FAIL("hf_dev_finalize_setup has not been called");
   HF_CUDA(cudaSetDevice(c->device));
@@ -2026,6 +2026,18 @@ int hf_dev_advance_solution(hf_ctx *c, int rk_stage)
     if (advance_one(c, c->eles[t], stage)) return 1;
   }
   return 0;
+}
+static int hf_check_nan(hf_ctx *c, bool collective = true);
+// The method-by-method call sequence of the reference's main loop (CalcResidual, then AdvanceSolution per element type): the reference
+// scans the residual for NaN in every calculate_corrected_divergence (src/eles.cpp:1781-1795); here the update kernel raises the
+// device flag and this call reads it back -- one synchronisation per stage, which is what this path (the yardstick, not the fast
+// path) can afford.  hf_dev_rk_stage / hf_dev_run_steps read the flag once per call instead.
+int hf_dev_advance_solution(hf_ctx *c, int rk_stage)
+{
+  if (advance_all(c, rk_stage)) return 1;
+  // no cross-rank agreement here: ranks without elements of a type do not make this call (eles::AdvanceSolution per element type), so a
+  // collective would not match; a rank that finds NaN fails alone, as the reference's FatalError -> MPI_Abort does
+  return hf_check_nan(c, false);
 }
 
 int hf_dev_rk_stage(hf_ctx *c, int rk_stage, double time, int keep_residual)
@@ -2043,7 +2055,7 @@ int hf_dev_rk_stage(hf_ctx *c, int rk_stage, double time, int keep_residual)
   else
   {
     if (staged_residual(c, time, rk_stage)) return 1;
-    if (hf_dev_advance_solution(c, rk_stage)) return 1;
+    if (advance_all(c, rk_stage)) return 1;
   }
   // shock capturing follows the update of every stage (reference src/HiFiLES.cpp:213-217)
   if (c->prm.shock_cap)
@@ -2053,12 +2065,12 @@ int hf_dev_rk_stage(hf_ctx *c, int rk_stage, double time, int keep_residual)
 }
 
 // reads the NaN flag back (all ranks agree) and fails, as the reference does, when it is set
-static int hf_check_nan(hf_ctx *c)
+static int hf_check_nan(hf_ctx *c, bool collective)
 {
   HF_CUDA(cudaMemcpyAsync(c->h_nan, c->d_nan, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
   HF_CUDA(cudaStreamSynchronize(c->stream));
   double ok = *c->h_nan ? 0.0 : 1.0;
-  if (c->nproc > 1 && hf_halo_allreduce_min(c, &ok)) return 1; // every rank leaves together (a lone abort would leave the others in the next exchange)
+  if (collective && c->nproc > 1 && hf_halo_allreduce_min(c, &ok)) return 1; // every rank leaves together (a lone abort would leave the others in the next exchange)
   if (ok == 1.0) return 0;
   char msg[256];
   if (*c->h_nan)
@@ -2118,6 +2130,9 @@ int hf_dev_run_steps(hf_ctx *c, int n_steps, double time0)
   hf_timeline_report(c);
   return 0;
 }
+
+// the NaN guard of hosts that issue hf_dev_rk_stage themselves (hf_dev_run_steps does this at its end)
+int hf_dev_check_residual(hf_ctx *c) { return hf_check_nan(c); }
 
 int hf_dev_set_dt(hf_ctx *c, double dt)
 {

@@ -133,6 +133,7 @@ int hifiles_run(void *handle, int n_steps, int fused)
       run_input.time = S->time;
       if (run_input.pressure_ramp) run_input.ramp_counter++;
     }
+    if (stage_calls) hf_check(hf_dev_check_residual(S->ctx));
   });
 }
 

@@ -613,7 +613,8 @@ void eles::mv_all_cpu_gpu()
   }
   hf_check(hf_dev_upload_eles(ctx, &d));
   // surface forces and the gradient-based plot fields read grad_disu_upts of the monitored stage
-  if (viscous && (run_input.calc_force != 0 || run_input.n_diagnostic_fields != 0)) hf_check(hf_dev_set_keep_gradient(ctx, 1));
+  // (and so does the gradient error of the advection-diffusion test cases, eles::compute_error)
+  if (viscous && (run_input.calc_force != 0 || run_input.n_diagnostic_fields != 0 || run_input.test_case == 2 || run_input.test_case == 3)) hf_check(hf_dev_set_keep_gradient(ctx, 1));
   if (run_input.n_integral_quantities != 0)
     hf_check(hf_dev_set_volume_cubature(ctx, ele_type, loc_volume_cubpts.get_dim(1), opp_volume_cubpts.get_ptr_cpu(), weight_volume_cubpts.get_ptr_cpu(),
                                         vol_detjac_vol_cubpts.get_ptr_cpu()));

@@ -219,6 +219,7 @@ void AdvanceStage(int in_file_num, int in_rk_stage, struct solution *FlowSol, bo
   if (run_input.device_fused && (hf_dev_fused_status(FlowSol->ctx) == string("available") || hf_dev_elem_status(FlowSol->ctx) == string("available")))
   {
     hf_check(hf_dev_rk_stage(FlowSol->ctx, in_rk_stage, FlowSol->time, monitored ? 1 : 0));
+    if (monitored) hf_check(hf_dev_check_residual(FlowSol->ctx)); // the host synchronises on monitored stages anyway (residual norm)
     return;
   }
   CalcResidual(in_file_num, in_rk_stage, FlowSol);

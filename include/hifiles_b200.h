@@ -219,6 +219,10 @@ int hf_dev_advance_solution(hf_ctx *ctx, int rk_stage);
 int hf_dev_rk_stage(hf_ctx *ctx, int rk_stage, double time, int keep_residual);
 /* n_steps full time steps (all RK stages each), fused path, no host synchronisation inside. */
 int hf_dev_run_steps(hf_ctx *ctx, int n_steps, double time0);
+/* The per-stage NaN scan of the reference (src/eles.cpp:1781-1795: "Residual is NaN" -> abort) for hosts that call hf_dev_rk_stage
+ * themselves: the update kernels raise a device flag, this reads it (one synchronisation; all ranks agree) and fails with the reference's
+ * message.  hf_dev_run_steps does it once per call, hf_dev_advance_solution after every stage. */
+int hf_dev_check_residual(hf_ctx *ctx);
 /* Individual methods, for per-operator parity tests and for hosts that keep the reference's call sequence. */
 int hf_dev_eles_op(hf_ctx *ctx, int ele_type, int op);
 int hf_dev_int_inters_op(hf_ctx *ctx, int inter_type, int op);
