@@ -35,7 +35,7 @@ def main():
     mesh = os.path.join(work, "tgv.neu")
     inp = os.path.join(work, "input")
     if kind != "hex":
-        return general(hb, mg, dist, rank, world, work, kind, n, order, steps)
+        return general(hb, mg, dist, rank, world, work, kind, n, order, steps, mode)
     if rank == 0:
         mg.hex_box(mesh, n)
         mg.write_input(inp, "tgv.neu", order=order, adv_type=2, dt=1e-5, riemann_solve_type=3, viscous=1)
@@ -101,8 +101,11 @@ def main():
     sys.exit(0 if int(flag.item()) == 1 else 1)
 
 
-def general(hb, mg, dist, rank, world, work, kind, n, order, steps):
-    """staged kernels on a partitioned simplex / prism / mixed mesh (triangular, quadrilateral and segment partition faces)"""
+def general(hb, mg, dist, rank, world, work, kind, n, order, steps, mode="staged"):
+    """staged kernels (mode "staged") or the blocked element kernels of the fast mode (mode "fused": hf_elem.cu around the halo
+    exchange of the staged interface kernels) on a partitioned simplex / prism / mixed mesh (triangular, quadrilateral and segment
+    partition faces); the yardstick is the single-domain run of the staged kernels"""
+    fast = mode != "staged"
     mesh = os.path.join(work, "m.neu")
     inp = os.path.join(work, "input")
     two_d = kind in ("tri", "mixed", "quad")
@@ -123,8 +126,12 @@ def general(hb, mg, dist, rank, world, work, kind, n, order, steps):
         idt = torch.tensor(list(hb.nccl_unique_id()), dtype=torch.uint8, device="cuda")
     dist.broadcast(idt, src=0)
     run = hb.Run(inp, rank=rank, nproc=world, part=part, nccl_id=bytes(idt.cpu().tolist()))
-    run.set_mode(False)
-    run.run(steps, fused=False)
+    if fast:
+        assert run.elem_status() == "available", run.elem_status()
+        run.run(steps, fused=True)
+    else:
+        run.set_mode(False)
+        run.run(steps, fused=False)
     mine = {t: (run.download(t, "disu_upts"), run.host_array(t + ".ele2global_ele")) for t in run.ele_types()}
     n_mpi = sum(run.n_inters("mpi", i) for i in range(3))
     run.close()
@@ -157,8 +164,8 @@ def general(hb, mg, dist, rank, world, work, kind, n, order, steps):
             worst = max(worst, err)
             ok = ok and bool(err < 1e-12)
     if rank == 0:
-        print("multi_gpu_check: world=%d kind=%s n=%s order=%d steps=%d mode=staged partition faces on rank 0: %d  max rel err vs single domain %.3e  %s"
-              % (world, kind, n, order, steps, n_mpi, worst, "OK" if ok else "FAIL"))
+        print("multi_gpu_check: world=%d kind=%s n=%s order=%d steps=%d mode=%s partition faces on rank 0: %d  max rel err vs single domain %.3e  %s"
+              % (world, kind, n, order, steps, "blocked element kernels" if fast else "staged", n_mpi, worst, "OK" if ok else "FAIL"))
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.broadcast(flag, src=0)
     dist.barrier()

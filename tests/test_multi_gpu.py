@@ -80,13 +80,15 @@ def test_two_ranks_match_single_domain_les():
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("mode", ["staged", "fused"])
 @pytest.mark.parametrize("kind,n", [("pritet", "4"), ("hexpri", "4"), ("mixed", "6")])
-def test_two_ranks_match_single_domain_simplex_and_mixed(kind, n):
-    """partition faces of every face type (segments, triangles, quadrilaterals) between element types of every kind"""
+def test_two_ranks_match_single_domain_simplex_and_mixed(kind, n, mode):
+    """partition faces of every face type (segments, triangles, quadrilaterals) between element types of every kind; mode "fused" = the
+    blocked element kernels of the fast mode (hf_elem.cu) around the same halo exchange"""
     if n_gpus() < 2:
         pytest.skip("needs 2 GPUs")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
-           "--master-port", "29534", os.path.join(ROOT, "tests", "multi_gpu_check.py"), n, "2", "2", "staged", kind]
+           "--master-port", "29534", os.path.join(ROOT, "tests", "multi_gpu_check.py"), n, "2", "2", mode, kind]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "OK" in r.stdout
