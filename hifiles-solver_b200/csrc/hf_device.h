@@ -86,6 +86,7 @@ struct hf_eles_dev
   std::vector<double> h_em;        // per element: JGinv(l,m) at point 0 (ND*ND), detjac
   std::vector<double> h_face_geo;  // per (ele, face): tdA, unit normal[3] at the face's first flux point
   std::vector<int8_t> h_own_sign;  // (fpt,ele): sign of ldg_beta if this element is the left side of the face
+  std::vector<double> h_norm_fpts; // (fpt,ele,dim) kept for RoeM runs: the fused kernels give that solver the exact normal of every flux point
   double affine_defect = 0.;       // max relative variation of the metrics inside an element
   int *d_pos = nullptr;            // pos on the device
   double *d_stage = nullptr;       // staging buffer of permuted uploads / downloads

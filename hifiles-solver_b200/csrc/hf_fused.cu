@@ -138,6 +138,7 @@ struct fused_args
   const uint2 *tw9;       // generation 9: [class][direction][task] packed line task of every thread (order of tools/bank_layout.py)
   const unsigned *cl9;    // generation 9: [class][CL9_WORDS] pass lists of k_face9
   const int *nidx;        // [ele][NFP] index into fu (field 0) of the neighbour's value facing each own flux point
+  const double *nlf;      // RoeM only (else null): [ele][face][flux point][3] the LEFT side's normal at exactly this flux point, see hf_fused_prepare
   hf_phys P;
   rk_args rk;
   int viscous, keep_residual, do_update;
@@ -356,6 +357,7 @@ struct hf_fused_state
   fused_tables T;
   int *mpi_blk = nullptr; // [n_mpi] own face block of every partition interface
   int *nidx = nullptr;    // [ele][NFP] neighbour value index into fu
+  double *nlf = nullptr;  // RoeM: left normal per flux point
   int *elist = nullptr;   // interior elements (ascending), then elements with a partition face (ascending)
   int n_interior = 0;
   bool elist_identity = false;
@@ -386,12 +388,12 @@ void hf_fused_destroy(hf_ctx *c)
 // called from hf_dev_upload_eles while the host metric arrays are at hand
 int hf_fused_on_upload(hf_ctx *c, hf_eles_dev &e, const hf_eles_desc *d)
 {
-  (void)c;
   if (e.ele_type != 4 || e.n_dims != 3) return 0;
   const int nu = e.n_upts, nf = e.n_fpts, ne = e.n_eles, nfi = nf / 6;
   e.h_em.assign((size_t)ne * 10, 0.);
   e.h_face_geo.assign((size_t)ne * 24, 0.);
   e.h_own_sign.assign((size_t)ne * nf, 1);
+  if (c->prm.riemann_solve_type == 2) e.h_norm_fpts.assign(d->norm_fpts, d->norm_fpts + (size_t)3 * nf * ne);
   double defect = 0.;
   for (int i = 0; i < ne; i++)
   {
@@ -759,6 +761,34 @@ int hf_fused_prepare(hf_ctx *c)
   if (hf_alloc_copy(c, &Z->mpi_blk, mpi_blk.data(), mpi_blk.size())) return 1;
   if (hf_alloc_copy(c, &Z->elist, elist.data(), elist.size())) return 1;
   if (hf_alloc_copy(c, &Z->nidx, nidx.data(), nidx.size())) return 1;
+  if (c->prm.riemann_solve_type == 2)
+  {
+    // RoeM's f = |Ma_n|^h with its `Ma_n != 0 ? pow : 1` switch (reference src/inters.cpp:400-404) is discontinuous at Ma_n = 0, and the
+    // reference's normals differ inside a face in the last bit: of the flux points of one face some carry an exact 0 in a component,
+    // others 1e-16 (measured on the reference's dumps: a quarter of the faces).  With ONE normal per face (em) the normal Mach number
+    // of a flow along the face is exactly 0 at other points than in the reference, f jumps by 40 h there, and the result leaves the
+    // reference by 1e-7 .. 1e-6 (tools/roem_probe.py).  So this solver -- and only it -- gets the reference's normal of every
+    // flux point: the left side's, i.e. the own one on left elements and partition faces, the neighbour's at the facing point on
+    // right elements.
+    if (e.h_norm_fpts.size() != (size_t)3 * NFP * ne) return no("RoeM: the flux-point normals were not kept at upload");
+    std::vector<double> nlf((size_t)ne * NFP * 3);
+    const size_t S = (size_t)NFP * ne;
+    for (int i = 0; i < ne; i++)
+      for (int f = 0; f < 6; f++)
+        for (int j = 0; j < NN; j++)
+        {
+          const int info = finfo[(size_t)i * 6 + f];
+          size_t src = (size_t)(f * NN + j) + (size_t)NFP * i;
+          if ((info & 4) && !(info & 8))
+          {
+            const int blk = nbr[(size_t)i * 6 + f];
+            const int jn = nidx[(size_t)i * NFP + f * NN + j] - blk * (NF * NN);
+            src = (size_t)((blk % 6) * NN + jn) + (size_t)NFP * (blk / 6);
+          }
+          for (int k = 0; k < 3; k++) nlf[((size_t)(i * 6 + f) * NN + j) * 3 + k] = e.h_norm_fpts[src + k * S];
+        }
+    if (hf_alloc_copy(c, &Z->nlf, nlf.data(), nlf.size())) return 1;
+  }
   if (M.n_inters)
   {
     if (hf_alloc_zero(c, &Z->out_u, (size_t)M.n_inters * FB)) return 1;
@@ -943,6 +973,7 @@ void base_args(hf_ctx *c, hf_fused_state *Z, fused_args &A)
   A.finfo = Z->finfo;
   A.bmask = Z->bmask;
   A.nidx = Z->nidx;
+  A.nlf = Z->nlf;
   A.dt_local = (c->prm.dt_type == 2) ? e.dt_local : nullptr;
   A.nan_flag = c->d_nan;
   for (int i = 0; i < 36; i++) { A.tD[i] = Z->T.D[i]; A.tc3[i] = Z->T.c3[i]; A.tc5[i] = Z->T.c5[i]; }

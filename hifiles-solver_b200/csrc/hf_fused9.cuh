@@ -846,7 +846,12 @@ __global__ void __launch_bounds__(NT, MINB) k_face9(const __grid_constant__ fuse
     }
     {
       const double *nrm = &S.em[10 + 4 * f + 1];
-      const double nl[3] = {nrm[0], nrm[1], nrm[2]};
+      double nl[3] = {nrm[0], nrm[1], nrm[2]};
+      if (A.nlf) // RoeM: the reference's normal of exactly this flux point (hf_fused_prepare)
+      {
+        const double *q3 = A.nlf + ((size_t)(ge * 6 + f) * NN + j) * 3;
+        nl[0] = q3[0]; nl[1] = q3[1]; nl[2] = q3[2];
+      }
       double ul[NF], ur[NF];
 #pragma unroll
       for (int k = 0; k < NF; k++)

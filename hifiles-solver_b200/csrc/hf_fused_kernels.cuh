@@ -524,7 +524,13 @@ __global__ void __launch_bounds__(NT, MINB) k_resid6(const __grid_constant__ fus
       double ul[NF], ur[NF];
 #pragma unroll
       for (int k = 0; k < NF; k++) { ul[k] = is_right ? un[k] : uo[k]; ur[k] = is_right ? uo[k] : un[k]; }
-      riemann_fast(ul, ur, n, fn, A.P);
+      double nr[3] = {n[0], n[1], n[2]};
+      if (A.nlf) // RoeM: the reference's normal of exactly this flux point (hf_fused_prepare)
+      {
+        const double *q3 = A.nlf + ((size_t)(S.ge[e] * 6 + f) * NN + j) * 3;
+        nr[0] = q3[0]; nr[1] = q3[1]; nr[2] = q3[2];
+      }
+      riemann_fast(ul, ur, nr, fn, A.P);
     }
     if constexpr (VISC)
     {
@@ -761,7 +767,12 @@ __device__ __forceinline__ void pass_GF7(SM &S, const fused_args &A, int ne)
     }
     {
       const double *n = &S.em[e][10 + 4 * f + 1];
-      const double nl[3] = {n[0], n[1], n[2]};
+      double nl[3] = {n[0], n[1], n[2]};
+      if (A.nlf) // RoeM: the reference's normal of exactly this flux point (hf_fused_prepare)
+      {
+        const double *q3 = A.nlf + ((size_t)(S.ge[e] * 6 + f) * NN + j) * 3;
+        nl[0] = q3[0]; nl[1] = q3[1]; nl[2] = q3[2];
+      }
       double ul[NF], ur[NF];
 #pragma unroll
       for (int k = 0; k < NF; k++)

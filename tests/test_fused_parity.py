@@ -102,13 +102,14 @@ def test_two_sided_kernels_on_one_sided_cases(tmp_path, hb, meshgen, name, monke
 
 @pytest.mark.gpu
 def test_roem_on_rounding_level_normal_mach(tmp_path, hb, meshgen):
-    """RoeM's f = |Ma_n|^h factor (reference src/inters.cpp:400-404, with the `Ma_n != 0 ? pow : 1` switch) is discontinuous
-    at Ma_n = 0: h ~ 1e-5..1e-3, so f jumps from exactly 1 at Ma_n = 0 to 1 - 46 h at Ma_n = 1e-20.  On the Taylor-Green box
-    (w = 0 initially, face normals with 1e-16 noise from the 2 pi geometry) the face-normal Mach number of many flux points IS
-    rounding noise, so the flux depends on the rounding of every product: the staged kernels (the reference's operation
-    order, no FMA) reproduce the reference bit for bit, the fused kernels (FMA, sum-factorised operators) land 1e-8 .. 1e-6
-    away -- with the reciprocal-based RoeM and with the reference's own RoeM formulas alike (measured: the same 1.907e-06).
-    HLLC / Rusanov on the same case, and RoeM on a field without such points (hex_p2_ns_roem_vortex), agree to 1e-12."""
+    """RoeM's f = |Ma_n|^h factor (reference src/inters.cpp:400-404, with the `Ma_n != 0 ? pow : 1` switch) is discontinuous at
+    Ma_n = 0: f jumps from exactly 1 at Ma_n = 0 to 1 - 40 h at Ma_n = 1e-17.  The reference's normals differ inside a face in the
+    last bit (of the flux points of one face some carry an exact 0 in a component, others 1e-16), so on the Taylor-Green box (w = 0,
+    flow along the z faces) WHERE the normal Mach number is exactly zero depends on the normal of the individual flux point.  Round 1's
+    fused kernels used one normal per face and landed 2e-7 .. 2e-6 from the reference (HLLC / Rusanov on the same case: 7e-16);
+    they now hand RoeM the reference's normal of every flux point (hf_fused_prepare, `nlf`) and agree to 1e-12 like every other
+    path.  The last block shows that it was this switch and not ill-conditioning: a last-bit change of a tenth of the initial
+    field moves the reference's own arithmetic (the staged kernels, bit-identical) by 1e-15 only."""
     if not util.have_reference():
         pytest.skip("oracle/_ref not built")
     inp = make_case(tmp_path, meshgen, "hex_p3_ns_roem_tgv")
@@ -117,9 +118,26 @@ def test_roem_on_rounding_level_normal_mach(tmp_path, hb, meshgen):
         run.set_mode(False)
         run.run(3, fused=False)
         check("staged", run.download("hex", "disu_upts"), ref["final.hex.disu_upts"], 1e-14)
+    for env in ({}, {"HF_FUSED_GEN6": "1"}):
+        for k in ("HF_FUSED_GEN6",):
+            os.environ.pop(k, None)
+        os.environ.update(env)
+        try:
+            with hb.Run(inp) as run:
+                assert run.fused_status() == "available"
+                run.run(3, fused=True)
+                check("fused " + run.fused_variant(), run.download("hex", "disu_upts"), ref["final.hex.disu_upts"], TOL)
+        finally:
+            for k in env:
+                os.environ.pop(k, None)
     with hb.Run(inp) as run:
-        run.run(3, fused=True)
-        check("fused", run.download("hex", "disu_upts"), ref["final.hex.disu_upts"], 1e-4)
+        run.set_mode(False)
+        u0 = run.download("hex", "disu_upts")
+        rng = np.random.default_rng(7)
+        up = np.where(rng.random(u0.shape) < 0.1, np.nextafter(u0, np.inf), u0)
+        run.upload("hex", "disu_upts", up)
+        run.run(3, fused=False)
+        check("reference arithmetic, last-bit perturbed input", run.download("hex", "disu_upts"), ref["final.hex.disu_upts"], TOL)
 
 
 @pytest.mark.gpu
