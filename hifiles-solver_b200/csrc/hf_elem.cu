@@ -49,13 +49,15 @@ struct el_prod
 };
 // what a warp executes: one block of 8 operator rows against two column blocks, every offset resolved on the host (decoding
 // (product, row block, column group) per task in the kernel cost four times the instructions of the tensor-core loop itself)
-struct el_task
+struct __align__(16) el_task
 {
-  int n_terms, mode, dst, ds, two, pad;
-  struct
+  int n_terms, mode, dst, ds; // read as one int4
+  int two, pad0, pad1, pad2;
+  struct __align__(16)
   {
-    const double *op; // already at the task's row block
-    int kb2, src, ss, pad;
+    int kb2, src, ss, pad; // read as one int4
+    const double *op;      // already at the task's row block
+    long long pad2;
   } t[4];
 };
 struct el_phase
@@ -94,6 +96,21 @@ __device__ __forceinline__ void dmma884(double &d0, double &d1, double a, double
 // (zero fragments) and a task always works on two column blocks (the second one a copy of the first when the tile has an odd
 // block left over, its result dropped), so the inner loop carries no predicate: 2 fragment loads, 4 data loads, 4 DMMA per
 // iteration, the next iteration's fragments requested before this one's tensor-core instructions.
+// one term of a task with a compile-time number of k-step pairs: fully unrolled, all operator fragments requested up front
+template <int KB2>
+__device__ __forceinline__ void term_unrolled(const double *__restrict__ opf, const double *s0, const double *s1, double &a00, double &a01, double &a10,
+                                              double &a11)
+{
+  double b[2 * KB2];
+#pragma unroll
+  for (int q = 0; q < 2 * KB2; q++) b[q] = __ldg(opf + q * 32);
+#pragma unroll
+  for (int q = 0; q < 2 * KB2; q++)
+  {
+    dmma884(a00, a01, s0[q * 4], b[q]);
+    dmma884(a10, a11, s1[q * 4], b[q]);
+  }
+}
 __device__ __forceinline__ void run_phase(const el_phase &PH, double *sm)
 {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
@@ -101,30 +118,40 @@ __device__ __forceinline__ void run_phase(const el_phase &PH, double *sm)
   for (int task = warp; task < PH.n; task += nw)
   {
     const el_task *K = PH.tasks + task;
-    const int nt = __ldg(&K->n_terms), mode = __ldg(&K->mode), ds = __ldg(&K->ds);
+    const int4 hd = __ldg(reinterpret_cast<const int4 *>(K)); // n_terms, mode, dst, ds
+    const int nt = hd.x, mode = hd.y, ds = hd.w;
     const bool two = __ldg(&K->two) != 0;
     double a00 = 0.0, a01 = 0.0, a10 = 0.0, a11 = 0.0;
     for (int t = 0; t < nt; t++)
     {
-      const int kb2 = __ldg(&K->t[t].kb2), ss = __ldg(&K->t[t].ss);
+      const int4 td = __ldg(reinterpret_cast<const int4 *>(&K->t[t].kb2)); // kb2, src, ss, pad
+      const int kb2 = td.x, ss = td.z;
       const double *opf = reinterpret_cast<const double *>(__ldg(reinterpret_cast<const unsigned long long *>(&K->t[t].op))) + lane;
-      const double *s0 = sm + __ldg(&K->t[t].src) + ar * ss + ak;
+      const double *s0 = sm + td.y + ar * ss + ak;
       const double *s1 = two ? s0 + 8 * ss : s0;
-      double b0 = __ldg(opf), b1 = __ldg(opf + 32);
-      for (int q = 0; q < kb2; q++)
+      // the operator sizes of P = 3 (and below) as straight-line code: quadrilaterals / triangles 2, tetrahedra 3 and 5, prisms 5 and 9
+      if (kb2 == 2) term_unrolled<2>(opf, s0, s1, a00, a01, a10, a11);
+      else if (kb2 == 3) term_unrolled<3>(opf, s0, s1, a00, a01, a10, a11);
+      else if (kb2 == 5) term_unrolled<5>(opf, s0, s1, a00, a01, a10, a11);
+      else if (kb2 == 1) term_unrolled<1>(opf, s0, s1, a00, a01, a10, a11);
+      else
       {
-        opf += 64;
-        double n0 = 0.0, n1 = 0.0;
-        if (q + 1 < kb2) { n0 = __ldg(opf); n1 = __ldg(opf + 32); }
-        dmma884(a00, a01, s0[0], b0);
-        dmma884(a10, a11, s1[0], b0);
-        dmma884(a00, a01, s0[4], b1);
-        dmma884(a10, a11, s1[4], b1);
-        s0 += 8; s1 += 8;
-        b0 = n0; b1 = n1;
+        double b0 = __ldg(opf), b1 = __ldg(opf + 32);
+        for (int q = 0; q < kb2; q++)
+        {
+          opf += 64;
+          double n0 = 0.0, n1 = 0.0;
+          if (q + 1 < kb2) { n0 = __ldg(opf); n1 = __ldg(opf + 32); }
+          dmma884(a00, a01, s0[0], b0);
+          dmma884(a10, a11, s1[0], b0);
+          dmma884(a00, a01, s0[4], b1);
+          dmma884(a10, a11, s1[4], b1);
+          s0 += 8; s1 += 8;
+          b0 = n0; b1 = n1;
+        }
       }
     }
-    double2 *d0 = reinterpret_cast<double2 *>(sm + __ldg(&K->dst) + ar * ds + 2 * ak);
+    double2 *d0 = reinterpret_cast<double2 *>(sm + hd.z + ar * ds + 2 * ak);
     double2 *d1 = d0 + 4 * ds; // 8 columns further, in double2 units
     if (mode == 0)
     {
