@@ -73,6 +73,7 @@ struct el_args
   unsigned mg_u, mg_f;       // ceil(2^32 / nu), ceil(2^32 / nf): r / n = umulhi(r, magic) for the small r of a tile
   int o_u, o_g, o_dl, o_fc, o_gf, o_dj;
   int visc, inv_from_global, store_div, store_grad;
+  int grad_from_global; // k_elem_grad has stored the physical gradient at the solution points: k_elem_resid reads it instead of forming it again
   const double *u_in;
   double *u0, *u1;
   const double *delu, *ntconf;
@@ -277,6 +278,28 @@ __global__ void __launch_bounds__(EL_THREADS, 2) k_elem_grad(const __grid_consta
   __syncthreads();
   run_phase(A.ph_gf, sm);
   __syncthreads();
+  if (A.grad_from_global)
+  {
+    // physical gradient at the solution points (reference src/eles.cpp:1955-1986) for k_elem_resid: written once here instead of the whole
+    // opp_4 / opp_5 product being repeated there
+    const size_t NUP = (size_t)A.nu * A.n_eles;
+    for (int i = threadIdx.x; i < ne * A.nu; i += blockDim.x)
+    {
+      const int el = (int)__umulhi((unsigned)i, A.mg_u), pt = i - el * A.nu;
+      const size_t p = (size_t)A.nu * (e0 + el) + pt;
+      double J[ND * ND], gr[NF * ND], g[NF * ND];
+#pragma unroll
+      for (int q = 0; q < ND * ND; q++) J[q] = A.JG_u[p * (ND * ND) + q];
+      const double inv_detjac = 1.0 / A.detjac_u[p];
+#pragma unroll
+      for (int l = 0; l < ND; l++)
+#pragma unroll
+        for (int k = 0; k < NF; k++) gr[k + NF * l] = sm[A.o_g + (l * ncp + k * A.E + el) * A.SU + pt];
+      to_physical<ND, NF>(gr, J, inv_detjac, g);
+#pragma unroll
+      for (int q = 0; q < NF * ND; q++) A.grad_out[p + q * NUP] = g[q];
+    }
+  }
   const size_t NFP = (size_t)A.nf * A.n_eles;
   for (int i = threadIdx.x; i < ne * A.nf; i += blockDim.x)
   {
@@ -307,12 +330,21 @@ __global__ void __launch_bounds__(EL_THREADS, MINB) k_elem_resid(const __grid_co
   zero_smem(sm, A.smem_doubles);
   __syncthreads();
   load_cols<NF>(A, sm + A.o_u, A.SU, A.u_in, A.nu, A.mg_u, e0, ne);
-  if (A.visc) load_cols<NF>(A, sm + A.o_dl, A.SF, A.delu, A.nf, A.mg_f, e0, ne);
+  if (A.visc)
+  {
+    if (A.grad_from_global)
+    {
+#pragma unroll
+      for (int d = 0; d < ND; d++) load_cols<NF>(A, sm + A.o_g + d * ncp * A.SU, A.SU, A.grad_out + (size_t)d * NF * NUP, A.nu, A.mg_u, e0, ne);
+    }
+    else
+      load_cols<NF>(A, sm + A.o_dl, A.SF, A.delu, A.nf, A.mg_f, e0, ne);
+  }
   load_cols<NF>(A, sm + A.o_fc, A.SF, A.ntconf, A.nf, A.mg_f, e0, ne);
   load_pts(sm + A.o_dj, A.detjac_u + (size_t)A.nu * e0, ne * A.nu);
   cp_async_wait_all();
   __syncthreads();
-  if (A.visc)
+  if (A.visc && !A.grad_from_global)
   {
     run_phase(A.ph_grad, sm);
     __syncthreads();
@@ -353,8 +385,14 @@ __global__ void __launch_bounds__(EL_THREADS, MINB) k_elem_resid(const __grid_co
       for (int l = 0; l < ND; l++)
 #pragma unroll
         for (int k = 0; k < NF; k++) gr[k + NF * l] = sm[A.o_g + (l * ncp + k * A.E + el) * A.SU + pt];
-      to_physical<ND, NF>(gr, J, 1.0 / sm[A.o_dj + i], g);
-      if (A.store_grad)
+      if (A.grad_from_global)
+      {
+#pragma unroll
+        for (int q = 0; q < NF * ND; q++) g[q] = gr[q];
+      }
+      else
+        to_physical<ND, NF>(gr, J, 1.0 / sm[A.o_dj + i], g);
+      if (A.store_grad && !A.grad_from_global)
       {
 #pragma unroll
         for (int q = 0; q < NF * ND; q++) A.grad_out[p + q * NUP] = g[q];
@@ -746,6 +784,9 @@ int hf_elem_stage(hf_ctx *c, int rk_stage, double time, int keep_residual)
   if (set_attrs(c)) return 1;
   const bool visc = c->prm.viscous != 0, par = c->nproc > 1;
   const int stage = rk_stage & 0xff;
+  // the physical gradient at the solution points travels from k_elem_grad to k_elem_resid through grad_disu_upts (D doubles per DOF
+  // written and read) instead of the opp_4 / opp_5 product being repeated; HF_ELEM_REGRAD=1 keeps the recomputation (measurement aid)
+  static const bool keep_grad = getenv("HF_ELEM_REGRAD") == nullptr;
 #define EACH_INT(OP) for (int t = 0; t < HF_N_INTER_TYPES; t++) if (hf_dev_int_inters_op(c, t, OP)) return 1
 #define EACH_BDY(OP) for (int t = 0; t < HF_N_INTER_TYPES; t++) if (hf_dev_bdy_inters_op(c, t, OP, time)) return 1
 #define EACH_MPI(OP) for (int t = 0; t < HF_N_INTER_TYPES; t++) if (hf_dev_mpi_inters_op(c, t, OP)) return 1
@@ -768,6 +809,12 @@ int hf_elem_stage(hf_ctx *c, int rk_stage, double time, int keep_residual)
       el_args A;
       fill_args(c, e, T, A, true);
       A.smem_doubles = T.smem_grad / sizeof(double);
+      if (keep_grad)
+      {
+        if (!e.grad_disu_upts && hf_alloc_zero(c, &e.grad_disu_upts, (size_t)e.n_upts * e.n_eles * e.n_fields * e.n_dims)) return 1;
+        A.grad_out = e.grad_disu_upts;
+        A.grad_from_global = 1;
+      }
       EL_LAUNCH(k_elem_grad, T.smem_grad);
     }
     if (par) EACH_MPI(4);
@@ -789,6 +836,7 @@ int hf_elem_stage(hf_ctx *c, int rk_stage, double time, int keep_residual)
     if (keep_residual && visc && c->want_gradient && hf_ensure_staged_buffers(c, e)) return 1; // grad_disu_upts for the integral diagnostics
     A.grad_out = e.grad_disu_upts;
     A.store_grad = (keep_residual && visc && c->want_gradient) ? 1 : 0;
+    A.grad_from_global = (visc && keep_grad) ? 1 : 0;
     A.dt = c->prm.dt;
     A.dt_local = (c->prm.dt_type == 2) ? e.dt_local : nullptr;
     if (hf_rk_coeffs(c, stage, &A.rk_mode, &A.rk_copy, &A.fac, &A.c1, &A.c2)) return 1;
