@@ -26,6 +26,7 @@
 // Accumulation order is the tensor core's and products are fused, so results differ from the reference's ascending dgemm sums in
 // the last bits (1e-15 relative): this is the fast mode (hf_dev_set_mode(ctx, 1)); mode 0 keeps the bit-exact staged kernels.
 #include "hf_device.h"
+#include <algorithm>
 #include <cstdlib>
 #include <cstring>
 
@@ -34,10 +35,20 @@ namespace
 constexpr int EL_THREADS = 256;
 
 // host-side description of one product: dst (mode) sum_t op_t * src_t
+// an operator on the device in fragment order.  Dense: [row block][k step][lane], k steps padded to pairs.  Sparse (tensor-product
+// operators of quadrilaterals / hexahedra: most 8 x 4 fragments are entirely zero): per row block only the non-zero fragments, with the
+// list of their k steps.
+struct el_op
+{
+  double *frag = nullptr;
+  int *kidx = nullptr;
+  bool sparse = false;
+  int kb = 0;                 // dense: k steps
+  std::vector<int> off, cnt;  // sparse: first fragment / number of fragments of every row block
+};
 struct el_term
 {
-  const double *op; // operator in fragment order: [row block][k step][lane]
-  int kb;           // k steps (4 points each), even
+  const el_op *op;
   int src, ss;      // shared-memory offset and column stride of the data (doubles)
 };
 struct el_prod
@@ -55,9 +66,9 @@ struct __align__(16) el_task
   int two, pad0, pad1, pad2;
   struct __align__(16)
   {
-    int kb2, src, ss, pad; // read as one int4
+    int kb2, src, ss, pad; // read as one int4; kb2 < 0: -kb2 fragments of a sparse operator, their k steps listed in kidx
     const double *op;      // already at the task's row block
-    long long pad2;
+    const int *kidx;       // sparse operators: k step of every stored fragment of this row block
   } t[4];
 };
 struct el_phase
@@ -135,6 +146,23 @@ __device__ __forceinline__ void run_phase(const el_phase &PH, double *sm)
       else if (kb2 == 3) term_unrolled<3>(opf, s0, s1, a00, a01, a10, a11);
       else if (kb2 == 5) term_unrolled<5>(opf, s0, s1, a00, a01, a10, a11);
       else if (kb2 == 1) term_unrolled<1>(opf, s0, s1, a00, a01, a10, a11);
+      else if (kb2 < 0)
+      {
+        // sparse operator: only the non-zero fragments of this row block, each with its k step
+        const int *kx = reinterpret_cast<const int *>(__ldg(reinterpret_cast<const unsigned long long *>(&K->t[t].kidx)));
+        const int cnt = -kb2;
+        double b0 = __ldg(opf);
+        int k0 = __ldg(kx);
+        for (int q = 0; q < cnt; q++)
+        {
+          double n0 = 0.0;
+          int k1 = 0;
+          if (q + 1 < cnt) { n0 = __ldg(opf + (q + 1) * 32); k1 = __ldg(kx + q + 1); }
+          dmma884(a00, a01, s0[k0 * 4], b0);
+          dmma884(a10, a11, s1[k0 * 4], b0);
+          b0 = n0; k0 = k1;
+        }
+      }
       else
       {
         double b0 = __ldg(opf), b1 = __ldg(opf + 32);
@@ -486,27 +514,65 @@ __global__ void __launch_bounds__(EL_THREADS, 2) k_elem_face(const __grid_consta
 
 inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
 
-// operator (rows x cols, column-major) in B-fragment order of mma.m8n8k4: [row block][k step][lane], lane = 4 * (row in block) + (k in step)
-std::vector<double> fragment_order(const double *op, int rows, int cols)
+// operator (rows x cols, column-major) in B-fragment order of mma.m8n8k4: lane = 4 * (row in block) + (k in step)
+int upload_op(hf_ctx *c, el_op &O, const double *op, int rows, int cols)
 {
-  const int RB = (rows + 7) / 8, KB = ((cols + 3) / 4 + 1) & ~1; // k steps padded to pairs (run_phase)
-  std::vector<double> out((size_t)RB * KB * 32, 0.0);
+  const int RB = (rows + 7) / 8, KBr = (cols + 3) / 4, KB = (KBr + 1) & ~1; // dense: k steps padded to pairs (run_phase)
+  auto fragment = [&](int rb, int kk, double *out) {
+    bool any = false;
+    for (int lane = 0; lane < 32; lane++)
+    {
+      const int row = rb * 8 + (lane >> 2), k = kk * 4 + (lane & 3);
+      out[lane] = (row < rows && k < cols) ? op[(size_t)k * rows + row] : 0.0;
+      any = any || out[lane] != 0.0;
+    }
+    return any;
+  };
+  double f[32];
+  long long nnz = 0;
   for (int rb = 0; rb < RB; rb++)
-    for (int kk = 0; kk < KB; kk++)
-      for (int lane = 0; lane < 32; lane++)
+    for (int kk = 0; kk < KBr; kk++) nnz += fragment(rb, kk, f) ? 1 : 0;
+  O.sparse = nnz * 5 <= (long long)RB * KBr * 2 && !getenv("HF_ELEM_DENSE"); // at most 40 % of the fragments carry anything (hexahedra; the 16 x 16 operators of P = 3 quadrilaterals stay dense: straight-line code)
+  O.kb = KB;
+  std::vector<double> frag;
+  std::vector<int> kidx;
+  if (O.sparse)
+  {
+    O.off.assign(RB, 0);
+    O.cnt.assign(RB, 0);
+    for (int rb = 0; rb < RB; rb++)
+    {
+      O.off[rb] = (int)kidx.size();
+      for (int kk = 0; kk < KBr; kk++)
+        if (fragment(rb, kk, f))
+        {
+          frag.insert(frag.end(), f, f + 32);
+          kidx.push_back(kk);
+        }
+      if ((int)kidx.size() == O.off[rb]) // an all-zero row block still needs one fragment (zeros)
       {
-        const int row = rb * 8 + (lane >> 2), k = kk * 4 + (lane & 3);
-        if (row < rows && k < cols) out[((size_t)rb * KB + kk) * 32 + lane] = op[(size_t)k * rows + row];
+        for (int q = 0; q < 32; q++) f[q] = 0.0;
+        frag.insert(frag.end(), f, f + 32);
+        kidx.push_back(0);
       }
-  return out;
+      O.cnt[rb] = (int)kidx.size() - O.off[rb];
+    }
+    if (hf_alloc_copy(c, &O.kidx, kidx.data(), kidx.size())) return 1;
+  }
+  else
+  {
+    frag.assign((size_t)RB * KB * 32, 0.0);
+    for (int rb = 0; rb < RB; rb++)
+      for (int kk = 0; kk < KBr; kk++) fragment(rb, kk, &frag[((size_t)rb * KB + kk) * 32]);
+  }
+  return hf_alloc_copy(c, &O.frag, frag.data(), frag.size());
 }
 } // namespace
 
 struct hf_elem_type
 {
   bool ready = false;
-  double *op0 = nullptr, *op1[3] = {nullptr, nullptr, nullptr}, *op2[3] = {nullptr, nullptr, nullptr}, *op3 = nullptr;
-  double *op4[3] = {nullptr, nullptr, nullptr}, *op5[3] = {nullptr, nullptr, nullptr}, *op6 = nullptr;
+  el_op op0, op1[3], op2[3], op3, op4[3], op5[3], op6;
   int E = 0, mb = 0, Eg = 0, mbg = 0, SU = 0, SF = 0; // tile of k_elem_resid / k_elem_face (E, mb) and of k_elem_grad (Eg, mbg)
   size_t smem_resid = 0, smem_grad = 0;
   // task tables on the device: [0] k_elem_resid / k_elem_face, [1] k_elem_grad; phases grad, gf, div, corr, face
@@ -526,10 +592,7 @@ int hf_elem_on_upload(hf_ctx *c, hf_eles_dev &e, const hf_eles_desc *d)
   hf_elem_type &T = c->ez->t[d->ele_type];
   const int nu = e.n_upts, nf = e.n_fpts, nd = e.n_dims, NF = e.n_fields;
   const bool visc = c->prm.viscous != 0;
-  auto up = [&](double **dst, const double *op, int rows, int cols) -> int {
-    std::vector<double> f = fragment_order(op, rows, cols);
-    return hf_alloc_copy(c, dst, f.data(), f.size());
-  };
+  auto up = [&](el_op *dst, const double *op, int rows, int cols) -> int { return upload_op(c, *dst, op, rows, cols); };
   if (up(&T.op0, d->opp_0, nf, nu) || up(&T.op3, d->opp_3, nu, nf)) return 1;
   for (int i = 0; i < nd; i++)
   {
@@ -546,22 +609,30 @@ int hf_elem_on_upload(hf_ctx *c, hf_eles_dev &e, const hf_eles_desc *d)
   // shared memory per CTA to aim for (measured, GDOF-stage/s at 48 / 72 / 100 kB: quadrilaterals P=3 32.1 / 30.4 / 30.1, triangles +
   // quadrilaterals 10.0 / 9.4 / -, tetrahedra + prisms 2.84 / 3.29 / 3.13); HF_ELEM_KB overrides
   const size_t budget = (getenv("HF_ELEM_KB") ? (size_t)atoi(getenv("HF_ELEM_KB")) : (nd == 2 ? 48 : 72)) * 1024;
+  // tile = E elements.  Padding of the E * n_fields columns to whole 8-column blocks is paid in every tensor-core instruction, so it comes
+  // first (measured on P = 4 hexahedra: one element per CTA, 5 of 8 columns used, 2.76 GDOF-stage/s; three elements, 15 of 16, 3.77 although
+  // only one CTA fits an SM); among the well-filled tiles the largest one inside the shared-memory budget, else the smallest one.
   auto pick = [&](auto bytes, const char *force_env) {
-    int best = 0;
-    double best_score = -1.0;
     const char *force = getenv(force_env);
+    if (force && atoi(force) > 0) return atoi(force);
+    double best_eff = 0.0;
+    for (int E = 1; E <= 64; E++)
+    {
+      const int mb = round_up(E * NF, 8) / 8;
+      if (bytes(mb) > 200 * 1024) break;
+      best_eff = std::max(best_eff, (double)(E * NF) / (mb * 8));
+    }
+    int in_budget = 0, smallest = 0;
     for (int E = 1; E <= 64; E++)
     {
       const int mb = round_up(E * NF, 8) / 8;
       const size_t b = bytes(mb);
       if (b > 200 * 1024) break;
-      const double eff = (double)(E * NF) / (mb * 8);
-      // prefer: fits three per SM, then padding efficiency, then more columns (operator fragments amortised, more warp tasks)
-      double score = eff + (b <= budget ? 1.0 : (b <= 110 * 1024 ? 0.5 : 0.0)) + 0.002 * (mb > 12 ? 12 : mb);
-      if (force && atoi(force) == E) score = 100.0;
-      if (score > best_score) { best_score = score; best = E; }
+      if ((double)(E * NF) / (mb * 8) < std::min(0.9, best_eff)) continue;
+      if (!smallest) smallest = E;
+      if (b <= budget) in_budget = E;
     }
-    return best;
+    return in_budget ? in_budget : smallest;
   };
   T.E = pick(bytes_resid, "HF_ELEM_E");
   T.Eg = visc ? pick(bytes_grad, "HF_ELEM_EG") : T.E;
@@ -630,8 +701,18 @@ static int compile_phase(hf_ctx *c, const std::vector<el_prod> &prods, int mb, e
         K.dst = Q.dst + 2 * g * 8 * Q.ds + rb * 8;
         for (int t = 0; t < Q.n_terms; t++)
         {
-          K.t[t].op = Q.t[t].op + (size_t)rb * Q.t[t].kb * 32;
-          K.t[t].kb2 = Q.t[t].kb / 2;
+          const el_op &O = *Q.t[t].op;
+          if (O.sparse)
+          {
+            K.t[t].op = O.frag + (size_t)O.off[rb] * 32;
+            K.t[t].kidx = O.kidx + O.off[rb];
+            K.t[t].kb2 = -O.cnt[rb];
+          }
+          else
+          {
+            K.t[t].op = O.frag + (size_t)rb * O.kb * 32;
+            K.t[t].kb2 = O.kb / 2;
+          }
           K.t[t].src = Q.t[t].src + 2 * g * 8 * Q.t[t].ss;
           K.t[t].ss = Q.t[t].ss;
         }
@@ -650,7 +731,7 @@ static int build_phases(hf_ctx *c, const hf_eles_dev &e, hf_elem_type &T)
 {
   const int nd = e.n_dims;
   const bool visc = c->prm.viscous != 0;
-  const int kbu = ((e.n_upts + 3) / 4 + 1) & ~1, kbf = ((e.n_fpts + 3) / 4 + 1) & ~1, rbu = (e.n_upts + 7) / 8, rbf = (e.n_fpts + 7) / 8;
+  const int rbu = (e.n_upts + 7) / 8, rbf = (e.n_fpts + 7) / 8;
   for (int which = 0; which < 2; which++)
   {
     const int mb = which ? T.mbg : T.mb, ncp = mb * 8;
@@ -662,8 +743,8 @@ static int build_phases(hf_ctx *c, const hf_eles_dev &e, hf_elem_type &T)
       el_prod Q;
       memset(&Q, 0, sizeof(Q));
       Q.n_terms = 2; Q.rb = rbu; Q.dst = L.o_g + d * ncp * T.SU; Q.ds = T.SU; Q.mode = 0;
-      Q.t[0] = {T.op4[d], kbu, L.o_u, T.SU};
-      Q.t[1] = {T.op5[d], kbf, L.o_dl, T.SF};
+      Q.t[0] = {&T.op4[d], L.o_u, T.SU};
+      Q.t[1] = {&T.op5[d], L.o_dl, T.SF};
       grad.push_back(Q);
     }
     if (which == 1)
@@ -674,7 +755,7 @@ static int build_phases(hf_ctx *c, const hf_eles_dev &e, hf_elem_type &T)
         el_prod Q;
         memset(&Q, 0, sizeof(Q));
         Q.n_terms = 1; Q.rb = rbf; Q.dst = L.o_gf + d * ncp * T.SF; Q.ds = T.SF; Q.mode = 0;
-        Q.t[0] = {T.op6, kbu, L.o_g + d * ncp * T.SU, T.SU};
+        Q.t[0] = {&T.op6, L.o_g + d * ncp * T.SU, T.SU};
         gf.push_back(Q);
       }
     }
@@ -688,20 +769,20 @@ static int build_phases(hf_ctx *c, const hf_eles_dev &e, hf_elem_type &T)
       R.n_terms = nd; R.rb = rbf; R.dst = L.o_fc; R.ds = T.SF; R.mode = 2;
       for (int d = 0; d < nd; d++)
       {
-        Q.t[d] = {T.op2[d], kbu, L.o_g + d * ncp * T.SU, T.SU};
-        R.t[d] = {T.op1[d], kbu, L.o_g + d * ncp * T.SU, T.SU};
+        Q.t[d] = {&T.op2[d], L.o_g + d * ncp * T.SU, T.SU};
+        R.t[d] = {&T.op1[d], L.o_g + d * ncp * T.SU, T.SU};
       }
       div.push_back(R); // the longer tasks first
       div.push_back(Q);
       el_prod C;
       memset(&C, 0, sizeof(C));
       C.n_terms = 1; C.rb = rbu; C.dst = L.o_dl; C.ds = T.SF; C.mode = 1;
-      C.t[0] = {T.op3, kbf, L.o_fc, T.SF};
+      C.t[0] = {&T.op3, L.o_fc, T.SF};
       corr.push_back(C);
       el_prod F;
       memset(&F, 0, sizeof(F));
       F.n_terms = 1; F.rb = rbf; F.dst = L.o_fc; F.ds = T.SF; F.mode = 0;
-      F.t[0] = {T.op0, kbu, L.o_u, T.SU};
+      F.t[0] = {&T.op0, L.o_u, T.SU};
       face.push_back(F);
     }
     if (compile_phase(c, grad, mb, &T.ph[which][0]) || compile_phase(c, gf, mb, &T.ph[which][1]) || compile_phase(c, div, mb, &T.ph[which][2]) ||
