@@ -84,6 +84,10 @@ struct el_args
   unsigned mg_u, mg_f;       // ceil(2^32 / nu), ceil(2^32 / nf): r / n = umulhi(r, magic) for the small r of a tile
   int o_u, o_g, o_dl, o_fc, o_gf, o_dj;
   int visc, inv_from_global, store_div, store_grad;
+  int over_int;         // 1: de-aliased inviscid flux inside k_elem_resid (phases ph_oi, ph_filt; at o_cub, stride SC: the solution at the cubature points, then D flux planes)
+  int n_cub, SC, o_cub;
+  unsigned mg_c;        // ceil(2^32 / n_cub)
+  const double *JG_cub; // JGinv_over_int_cubpts (l,m,cubpt,ele)
   int grad_from_global; // k_elem_grad has stored the physical gradient at the solution points: k_elem_resid reads it instead of forming it again
   const double *u_in;
   double *u0, *u1;
@@ -94,7 +98,7 @@ struct el_args
   double dt, fac, c1, c2;
   int rk_mode, rk_copy;
   int *nan_flag;
-  el_phase ph_grad, ph_gf, ph_div, ph_corr, ph_face;
+  el_phase ph_grad, ph_gf, ph_div, ph_corr, ph_face, ph_oi, ph_filt;
   size_t smem_doubles;
   hf_phys P;
 };
@@ -358,7 +362,7 @@ __global__ void __launch_bounds__(EL_THREADS, MINB) k_elem_resid(const __grid_co
   zero_smem(sm, A.smem_doubles);
   __syncthreads();
   load_cols<NF>(A, sm + A.o_u, A.SU, A.u_in, A.nu, A.mg_u, e0, ne);
-  if (A.visc)
+  if (A.visc && !A.over_int)
   {
     if (A.grad_from_global)
     {
@@ -377,6 +381,38 @@ __global__ void __launch_bounds__(EL_THREADS, MINB) k_elem_resid(const __grid_co
     run_phase(A.ph_grad, sm);
     __syncthreads();
   }
+  if (A.over_int)
+  {
+    // polynomial de-aliasing (eles::evaluate_invFlux_over_int, reference src/eles.cpp:1480-1545): solution to the cubature points, inviscid
+    // flux there with the cubature-point metrics, L2 projection back onto the solution basis -> the flux planes o_g.  (The gradient of a
+    // viscous run is then read from global memory in the point loop below: the planes are taken.)
+    run_phase(A.ph_oi, sm); // plane 0 of o_cub = opp_over_int_cubpts u
+    __syncthreads();
+    for (int i = threadIdx.x; i < ne * A.n_cub; i += blockDim.x)
+    {
+      const int el = (int)__umulhi((unsigned)i, A.mg_c), cp = i - el * A.n_cub;
+      const size_t p = (size_t)A.n_cub * (e0 + el) + cp;
+      double uu[NF], J[ND * ND], f[NF * ND];
+#pragma unroll
+      for (int k = 0; k < NF; k++) uu[k] = sm[A.o_cub + (k * A.E + el) * A.SC + cp];
+#pragma unroll
+      for (int q = 0; q < ND * ND; q++) J[q] = A.JG_cub[p * (ND * ND) + q];
+      inv_flux<ND, NF>(uu, f, A.P);
+#pragma unroll
+      for (int k = 0; k < NF; k++)
+#pragma unroll
+        for (int l = 0; l < ND; l++)
+        {
+          double acc = 0.0;
+#pragma unroll
+          for (int m = 0; m < ND; m++) acc += J[l + ND * m] * f[k + NF * m];
+          sm[A.o_cub + ((1 + l) * ncp + k * A.E + el) * A.SC + cp] = acc;
+        }
+    }
+    __syncthreads();
+    run_phase(A.ph_filt, sm); // o_g(d) = over_int_filter flux(d)
+    __syncthreads();
+  }
   // fluxes at the solution points, transformed, in place over the gradient
   for (int i = threadIdx.x; i < ne * A.nu; i += blockDim.x)
   {
@@ -391,6 +427,13 @@ __global__ void __launch_bounds__(EL_THREADS, MINB) k_elem_resid(const __grid_co
     {
 #pragma unroll
       for (int q = 0; q < NF * ND; q++) t[q] = A.tdisf_in[p + q * NUP];
+    }
+    else if (A.over_int)
+    {
+#pragma unroll
+      for (int l = 0; l < ND; l++)
+#pragma unroll
+        for (int k = 0; k < NF; k++) t[k + NF * l] = sm[A.o_g + (l * ncp + k * A.E + el) * A.SU + pt];
     }
     else
     {
@@ -409,10 +452,18 @@ __global__ void __launch_bounds__(EL_THREADS, MINB) k_elem_resid(const __grid_co
     if (A.visc)
     {
       double gr[NF * ND], g[NF * ND];
+      if (A.over_int)
+      {
 #pragma unroll
-      for (int l = 0; l < ND; l++)
+        for (int q = 0; q < NF * ND; q++) gr[q] = A.grad_out[p + q * NUP]; // physical gradient of k_elem_grad
+      }
+      else
+      {
 #pragma unroll
-        for (int k = 0; k < NF; k++) gr[k + NF * l] = sm[A.o_g + (l * ncp + k * A.E + el) * A.SU + pt];
+        for (int l = 0; l < ND; l++)
+#pragma unroll
+          for (int k = 0; k < NF; k++) gr[k + NF * l] = sm[A.o_g + (l * ncp + k * A.E + el) * A.SU + pt];
+      }
       if (A.grad_from_global)
       {
 #pragma unroll
@@ -572,11 +623,13 @@ int upload_op(hf_ctx *c, el_op &O, const double *op, int rows, int cols)
 struct hf_elem_type
 {
   bool ready = false;
-  el_op op0, op1[3], op2[3], op3, op4[3], op5[3], op6;
+  el_op op0, op1[3], op2[3], op3, op4[3], op5[3], op6, op_oi, op_filt;
+  bool fused_oi = false; // over-integration inside k_elem_resid (else the staged evaluate_invFlux_over_int feeds it)
+  int n_cub = 0, SC = 0;
   int E = 0, mb = 0, Eg = 0, mbg = 0, SU = 0, SF = 0; // tile of k_elem_resid / k_elem_face (E, mb) and of k_elem_grad (Eg, mbg)
   size_t smem_resid = 0, smem_grad = 0;
   // task tables on the device: [0] k_elem_resid / k_elem_face, [1] k_elem_grad; phases grad, gf, div, corr, face
-  el_phase ph[2][5];
+  el_phase ph[2][7]; // + over-integration: interpolation to the cubature points, projection back
 };
 struct hf_elem_state
 {
@@ -603,8 +656,15 @@ int hf_elem_on_upload(hf_ctx *c, hf_eles_dev &e, const hf_eles_desc *d)
   const int nup = round_up(nu, 8), nfp = round_up(nf, 8); // multiples of 8 also cover the k steps padded to pairs (8 points)
   T.SU = nup + 4;
   T.SF = (nfp > nup ? nfp : nup) + 4; // the divergence (solution points) is accumulated in a flux-point buffer
+  if (c->prm.over_int && d->n_over_int_cubpts > 0 && !getenv("HF_ELEM_NO_OI"))
+  {
+    T.n_cub = d->n_over_int_cubpts;
+    T.SC = round_up(T.n_cub, 8) + 4;
+    T.fused_oi = true;
+    if (T.fused_oi && (up(&T.op_oi, d->opp_over_int_cubpts, T.n_cub, nu) || up(&T.op_filt, d->over_int_filter, nu, T.n_cub))) return 1;
+  }
   // elements per CTA: whole 8-column blocks with little padding, shared memory for three CTAs per SM if the element allows it
-  auto bytes_resid = [&](int mb) { return sizeof(double) * ((size_t)mb * 8 * ((size_t)T.SU * (1 + nd) + 2 * (size_t)T.SF) + (size_t)((mb * 8 / NF * nu + 1) & ~1)); };
+  auto bytes_resid = [&](int mb) { return sizeof(double) * ((size_t)mb * 8 * ((size_t)T.SU * (1 + nd) + 2 * (size_t)T.SF + (T.fused_oi ? (size_t)(1 + nd) * T.SC : 0)) + (size_t)((mb * 8 / NF * nu + 1) & ~1)); };
   auto bytes_grad = [&](int mb) { return sizeof(double) * (size_t)mb * 8 * ((size_t)T.SU * (1 + nd) + (size_t)T.SF * (1 + nd)); };
   // shared memory per CTA to aim for (measured, GDOF-stage/s at 48 / 72 / 100 kB: quadrilaterals P=3 32.1 / 30.4 / 30.1, triangles +
   // quadrilaterals 10.0 / 9.4 / -, tetrahedra + prisms 2.84 / 3.29 / 3.13); HF_ELEM_KB overrides
@@ -670,9 +730,9 @@ int hf_elem_available(hf_ctx *c)
 
 struct el_layout
 {
-  int o_u, o_g, o_dl, o_fc, o_gf, o_dj;
+  int o_u, o_g, o_dl, o_fc, o_gf, o_dj, o_cub;
 };
-static el_layout layout_of(const hf_elem_type &T, int nd, int mb)
+static el_layout layout_of(const hf_elem_type &T, int nd, int mb, int nu = 0, int NF = 1)
 {
   el_layout L;
   const int ncp = mb * 8;
@@ -682,6 +742,7 @@ static el_layout layout_of(const hf_elem_type &T, int nd, int mb)
   L.o_fc = L.o_dl + ncp * T.SF; // k_elem_resid
   L.o_gf = L.o_dl + ncp * T.SF; // k_elem_grad
   L.o_dj = L.o_fc + ncp * T.SF; // k_elem_resid: detjac at the tile's solution points
+  L.o_cub = L.o_dj + ((mb * 8 / NF * nu + 1) & ~1); // k_elem_resid with over-integration: flux planes at the cubature points
   return L;
 }
 
@@ -735,8 +796,8 @@ static int build_phases(hf_ctx *c, const hf_eles_dev &e, hf_elem_type &T)
   for (int which = 0; which < 2; which++)
   {
     const int mb = which ? T.mbg : T.mb, ncp = mb * 8;
-    const el_layout L = layout_of(T, nd, mb);
-    std::vector<el_prod> grad, gf, div, corr, face;
+    const el_layout L = layout_of(T, nd, mb, e.n_upts, e.n_fields);
+    std::vector<el_prod> grad, gf, div, corr, face, oi, filt;
     // reference-space gradient, corrected: opp_4(d) u + opp_5(d) delta
     for (int d = 0; d < nd && visc; d++)
     {
@@ -784,9 +845,26 @@ static int build_phases(hf_ctx *c, const hf_eles_dev &e, hf_elem_type &T)
       F.n_terms = 1; F.rb = rbf; F.dst = L.o_fc; F.ds = T.SF; F.mode = 0;
       F.t[0] = {&T.op0, L.o_u, T.SU};
       face.push_back(F);
+      if (T.fused_oi)
+      {
+        el_prod O;
+        memset(&O, 0, sizeof(O));
+        O.n_terms = 1; O.rb = (T.n_cub + 7) / 8; O.dst = L.o_cub; O.ds = T.SC; O.mode = 0;
+        O.t[0] = {&T.op_oi, L.o_u, T.SU};
+        oi.push_back(O);
+        for (int d = 0; d < nd; d++)
+        {
+          el_prod P;
+          memset(&P, 0, sizeof(P));
+          P.n_terms = 1; P.rb = rbu; P.dst = L.o_g + d * ncp * T.SU; P.ds = T.SU; P.mode = 0;
+          P.t[0] = {&T.op_filt, L.o_cub + (1 + d) * ncp * T.SC, T.SC};
+          filt.push_back(P);
+        }
+      }
     }
     if (compile_phase(c, grad, mb, &T.ph[which][0]) || compile_phase(c, gf, mb, &T.ph[which][1]) || compile_phase(c, div, mb, &T.ph[which][2]) ||
-        compile_phase(c, corr, mb, &T.ph[which][3]) || compile_phase(c, face, mb, &T.ph[which][4])) return 1;
+        compile_phase(c, corr, mb, &T.ph[which][3]) || compile_phase(c, face, mb, &T.ph[which][4]) || compile_phase(c, oi, mb, &T.ph[which][5]) ||
+        compile_phase(c, filt, mb, &T.ph[which][6])) return 1;
   }
   return 0;
 }
@@ -800,7 +878,8 @@ static void fill_args(hf_ctx *c, hf_eles_dev &e, const hf_elem_type &T, el_args 
   A.mg_u = (unsigned)((0x100000000ull + e.n_upts - 1) / e.n_upts);
   A.mg_f = (unsigned)((0x100000000ull + e.n_fpts - 1) / e.n_fpts);
   A.SU = T.SU; A.SF = T.SF;
-  const el_layout L = layout_of(T, e.n_dims, mb);
+  const el_layout L = layout_of(T, e.n_dims, mb, e.n_upts, e.n_fields);
+  A.o_cub = L.o_cub;
   A.o_u = L.o_u; A.o_g = L.o_g; A.o_dl = L.o_dl; A.o_fc = L.o_fc; A.o_gf = L.o_gf; A.o_dj = L.o_dj;
   A.visc = visc;
   A.u_in = e.disu_upts[0]; A.u0 = e.disu_upts[0]; A.u1 = e.disu_upts[1];
@@ -811,6 +890,9 @@ static void fill_args(hf_ctx *c, hf_eles_dev &e, const hf_elem_type &T, el_args 
   A.P = c->phys;
   const int w = grad_kernel ? 1 : 0;
   A.ph_grad = T.ph[w][0]; A.ph_gf = T.ph[w][1]; A.ph_div = T.ph[w][2]; A.ph_corr = T.ph[w][3]; A.ph_face = T.ph[w][4];
+  A.ph_oi = T.ph[w][5]; A.ph_filt = T.ph[w][6];
+  A.n_cub = T.n_cub; A.SC = T.SC; A.JG_cub = e.JGinv_over_int;
+  A.mg_c = T.n_cub ? (unsigned)((0x100000000ull + T.n_cub - 1) / T.n_cub) : 0;
 }
 
 #define EL_LAUNCH(KERNEL, smem)                                                                                          \
@@ -873,9 +955,12 @@ int hf_elem_stage(hf_ctx *c, int rk_stage, double time, int keep_residual)
 #define EACH_MPI(OP) for (int t = 0; t < HF_N_INTER_TYPES; t++) if (hf_dev_mpi_inters_op(c, t, OP)) return 1
   if (!c->ufpts_valid && hf_elem_extrapolate(c)) return 1;
   if (par) EACH_MPI(2);
+  // over-integration: inside k_elem_resid where the element's tile has room for the cubature-point planes (and the gradient comes from
+  // k_elem_grad), else the staged evaluate_invFlux_over_int writes the de-aliased inviscid flux for it
+  auto oi_fused = [&](int t) { return c->prm.over_int && c->ez->t[t].fused_oi && (!visc || keep_grad); };
   if (c->prm.over_int)
     for (int t = 0; t < HF_N_ELE_TYPES; t++)
-      if (c->eles[t].present && hf_dev_eles_op(c, t, HF_EVALUATE_INVFLUX_OVER_INT)) return 1;
+      if (c->eles[t].present && !oi_fused(t) && hf_dev_eles_op(c, t, HF_EVALUATE_INVFLUX_OVER_INT)) return 1;
   EACH_INT(HF_COMMON_INVFLUX);
   EACH_BDY(HF_COMMON_INVFLUX);
   if (par) { EACH_MPI(3); EACH_MPI(HF_COMMON_INVFLUX); }
@@ -912,7 +997,8 @@ int hf_elem_stage(hf_ctx *c, int rk_stage, double time, int keep_residual)
     el_args A;
     fill_args(c, e, T, A);
     A.smem_doubles = T.smem_resid / sizeof(double);
-    A.inv_from_global = c->prm.over_int ? 1 : 0;
+    A.over_int = oi_fused(t) ? 1 : 0;
+    A.inv_from_global = (c->prm.over_int && !A.over_int) ? 1 : 0;
     A.store_div = keep_residual ? 1 : 0;
     if (keep_residual && visc && c->want_gradient && hf_ensure_staged_buffers(c, e)) return 1; // grad_disu_upts for the integral diagnostics
     A.grad_out = e.grad_disu_upts;
