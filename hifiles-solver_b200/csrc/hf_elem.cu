@@ -715,7 +715,6 @@ void hf_elem_destroy(hf_ctx *c)
 const char *hf_elem_status(hf_ctx *c)
 {
   if (!c->ez) return "blocked element kernels: not prepared (staged-only context)";
-  if (c->prm.LES) return "blocked element kernels: LES runs through the staged kernels";
   for (int t = 0; t < HF_N_ELE_TYPES; t++)
     if (c->eles[t].present && !c->ez->t[t].ready) return "blocked element kernels: an element type does not fit a shared-memory tile";
   if (!((c->prm.n_dims == 2 && c->prm.n_fields == 4) || (c->prm.n_dims == 3 && c->prm.n_fields == 5) || c->prm.n_fields == 1))
@@ -953,11 +952,17 @@ int hf_elem_stage(hf_ctx *c, int rk_stage, double time, int keep_residual)
 #define EACH_INT(OP) for (int t = 0; t < HF_N_INTER_TYPES; t++) if (hf_dev_int_inters_op(c, t, OP)) return 1
 #define EACH_BDY(OP) for (int t = 0; t < HF_N_INTER_TYPES; t++) if (hf_dev_bdy_inters_op(c, t, OP, time)) return 1
 #define EACH_MPI(OP) for (int t = 0; t < HF_N_INTER_TYPES; t++) if (hf_dev_mpi_inters_op(c, t, OP)) return 1
+  const bool les = c->prm.LES != 0;
+  // LES: filtered solution and Leonard tensors at the first stage of a step (reference src/solver.cpp:54-62); the SVV model replaces the
+  // solution by the filtered one, so this precedes the face values
+  if (les && c->prm.SGS_model >= 2 && stage == 0)
+    for (int t = 0; t < HF_N_ELE_TYPES; t++)
+      if (c->eles[t].present && hf_dev_eles_op(c, t, HF_CALC_SGS_TERMS)) return 1;
   if (!c->ufpts_valid && hf_elem_extrapolate(c)) return 1;
   if (par) EACH_MPI(2);
   // over-integration: inside k_elem_resid where the element's tile has room for the cubature-point planes (and the gradient comes from
   // k_elem_grad), else the staged evaluate_invFlux_over_int writes the de-aliased inviscid flux for it
-  auto oi_fused = [&](int t) { return c->prm.over_int && c->ez->t[t].fused_oi && (!visc || keep_grad); };
+  auto oi_fused = [&](int t) { return c->prm.over_int && !les && c->ez->t[t].fused_oi && (!visc || keep_grad); };
   if (c->prm.over_int)
     for (int t = 0; t < HF_N_ELE_TYPES; t++)
       if (c->eles[t].present && !oi_fused(t) && hf_dev_eles_op(c, t, HF_EVALUATE_INVFLUX_OVER_INT)) return 1;
@@ -975,7 +980,7 @@ int hf_elem_stage(hf_ctx *c, int rk_stage, double time, int keep_residual)
       el_args A;
       fill_args(c, e, T, A, true);
       A.smem_doubles = T.smem_grad / sizeof(double);
-      if (keep_grad)
+      if (keep_grad || les)
       {
         if (!e.grad_disu_upts && hf_alloc_zero(c, &e.grad_disu_upts, (size_t)e.n_upts * e.n_eles * e.n_fields * e.n_dims)) return 1;
         A.grad_out = e.grad_disu_upts;
@@ -984,9 +989,22 @@ int hf_elem_stage(hf_ctx *c, int rk_stage, double time, int keep_residual)
       EL_LAUNCH(k_elem_grad, T.smem_grad);
     }
     if (par) EACH_MPI(4);
+    if (les)
+    {
+      // LES is a hybrid: the point fluxes with the sub-grid-scale models (eles::evaluate_viscFlux with calc_sgsf_upts) and the SGS flux
+      // at the flux points (extrapolate_sgsFlux) stay the staged kernels -- they read the physical gradient k_elem_grad has just left in
+      // grad_disu_upts and write the TOTAL transformed flux to tdisf_upts, which k_elem_resid then takes as it is
+      for (int t = 0; t < HF_N_ELE_TYPES; t++)
+      {
+        if (!c->eles[t].present) continue;
+        if (!c->prm.over_int && hf_dev_eles_op(c, t, HF_EVALUATE_INVFLUX)) return 1;
+        if (hf_dev_eles_op(c, t, HF_EVALUATE_VISCFLUX) || hf_dev_eles_op(c, t, HF_EXTRAPOLATE_SGSFLUX)) return 1;
+      }
+      if (par) EACH_MPI(6);
+    }
     EACH_INT(HF_COMMON_VISCFLUX);
     EACH_BDY(HF_COMMON_VISCFLUX);
-    if (par) { EACH_MPI(5); EACH_MPI(HF_COMMON_VISCFLUX); }
+    if (par) { EACH_MPI(5); if (les) EACH_MPI(7); EACH_MPI(HF_COMMON_VISCFLUX); }
   }
   for (int t = 0; t < HF_N_ELE_TYPES; t++)
   {
@@ -999,6 +1017,12 @@ int hf_elem_stage(hf_ctx *c, int rk_stage, double time, int keep_residual)
     A.smem_doubles = T.smem_resid / sizeof(double);
     A.over_int = oi_fused(t) ? 1 : 0;
     A.inv_from_global = (c->prm.over_int && !A.over_int) ? 1 : 0;
+    if (les)
+    {
+      A.visc = 0;            // tdisf_upts already holds inviscid + viscous + sub-grid-scale flux
+      A.inv_from_global = 1;
+      A.tdisf_in = e.tdisf_upts;
+    }
     A.store_div = keep_residual ? 1 : 0;
     if (keep_residual && visc && c->want_gradient && hf_ensure_staged_buffers(c, e)) return 1; // grad_disu_upts for the integral diagnostics
     A.grad_out = e.grad_disu_upts;

@@ -24,6 +24,11 @@ ELEM_CASES = [
     "mixed_tri_quad_p3_euler_shockcap", "pritet_p2_ns_hllc_shockcap",
     # CFL time steps (calc_time_step on the device before every step): global on curved triangles with the sensor, local on tetrahedra
     "tri6_p3_ns_curved_supin_wall_cfl_shockcap", "tet_p2_ns_hllc_cfl_local_dt", "quad_p2_ns_cfl_global_dt",
+    # LES (BASELINE config 5): the blocked kernels around the staged sub-grid-scale point fluxes -- eddy-viscosity models, filter-based
+    # models (calc_sgs_terms at the first stage; SVV replaces the solution), wall models, and config 5's combination with the sensor
+    "hex_p3_les_wale_rk34", "pritet_p2_les_wale_rk34", "mixed_tri_quad_p3_les_smagorinsky_walls", "hex_p3_les_wsm_vasilyev",
+    "mixed_tri_quad_p3_les_similarity_gaussian", "tet_p2_les_svv_modal", "mixed_tri_quad_p3_les_wale_werner_wengle", "hex_p2_les_wale_loglaw_wall",
+    "config5_hexpri_p2_les_wm_shockcap_hllc", "hexpri_p2_les_smagorinsky_periodic",
 ]
 
 
@@ -50,7 +55,9 @@ def test_blocked_element_kernels_vs_reference(tmp_path, hb, meshgen, name):
         staged_launches = run.launch_count() - n0
     # the blocked kernels really ran: far fewer launches than one kernel per reference method
     assert launches < 0.6 * staged_launches, (launches, staged_launches)
-    check("residual norm", res, ref["history.norm_residual"][:, -1], 1e-12)
+    # the residual is a derivative of fluxes; behind the sub-grid-scale models' pow(x, 1.25 | 1.5 | 2.5) (device and host libm differ by an
+    # ulp there) its norm is held to 1e-11, the solution itself to 1e-12 as everywhere
+    check("residual norm", res, ref["history.norm_residual"][:, -1], 1e-11 if CASES[name][3].get("LES") else 1e-12)
     for t in fast:
         check("final disu_upts " + t, fast[t], ref["final." + t + ".disu_upts"], 1e-12)
 
