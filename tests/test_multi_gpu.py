@@ -68,12 +68,14 @@ def test_two_ranks_match_single_domain_metis_partition():
 
 
 @pytest.mark.gpu
-def test_two_ranks_match_single_domain_les():
-    """LES (WALE-similarity: eddy viscosity + Leonard tensors) on a partitioned tetrahedral mesh: the SGS-flux halo exchange"""
+@pytest.mark.parametrize("mode", ["staged", "fused"])
+def test_two_ranks_match_single_domain_les(mode):
+    """LES (WALE-similarity: eddy viscosity + Leonard tensors) on a partitioned tetrahedral mesh: the SGS-flux halo exchange; mode "fused" =
+    the blocked element kernels around the staged sub-grid-scale point fluxes"""
     if n_gpus() < 2:
         pytest.skip("needs 2 GPUs")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
-           "--master-port", "29535", os.path.join(ROOT, "tests", "multi_gpu_check.py"), "3", "2", "2", "staged", "tet"]
+           "--master-port", "29535", os.path.join(ROOT, "tests", "multi_gpu_check.py"), "3", "2", "2", mode, "tet"]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=dict(os.environ, HF_CHECK_LES="2"))
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "OK" in r.stdout
