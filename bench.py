@@ -211,6 +211,15 @@ OTHER_CONFIGS = {
     4: ("3-D Navier-Stokes on a mixed prism / tetrahedron mesh (%s^3 cells), P=3, RoeM + LDG with over-integration (polynomial de-aliasing), SSP-RK34, periodic "
         "(BASELINE config 4's discretisation on a synthetic periodic mesh)", "mixed_box_3d", 24, 10, dict(kind="pritet"),
         dict(order=3, adv_type=2, riemann_solve_type=2, viscous=1, dt=1e-6, over_int=1, over_int_order=5)),
+    5: ("supersonic wall-bounded LES on a mixed hexahedron / prism mesh (%s^3 cells): Mach 1.8 inflow (sup_in), sup_out outflow, characteristic far field, adiabatic "
+        "wall with the Werner-Wengle wall model, WALE sub-grid model, Persson sensor + exponential filter after every stage, P=3, HLLC + LDG, SSP-RK34 "
+        "(BASELINE config 5's discretisation on a synthetic mesh)", "mixed_box_3d", 24, 8,
+        dict(kind="hexpri", lengths=(1.5, 1., 2.), bcs={"x-": "In", "x+": "Out", "y-": "Cyclic", "y+": "Cyclic", "z-": "Wall", "z+": "Far"}),
+        dict(order=3, adv_type=2, riemann_solve_type=3, viscous=1, ic_form=1, dt=1e-8, fix_vis=0, Mach_c_ic=1.8, nx_c_ic=1., ny_c_ic=0., nz_c_ic=0.02, T_c_ic=290., rho_c_ic=1.2,
+             Mach_free_stream=1.8, rho_free_stream=1.2, T_free_stream=290., L_free_stream=1., dx_cyclic=None, dy_cyclic=1., dz_cyclic=None, bc_In_type="sup_in",
+             bc_In_p_static=101000., bc_In_mach=1.8, bc_In_T_static=290., bc_In_nx=1., bc_In_ny=0., bc_In_nz=0., bc_Out_type="sup_out", bc_Wall_type="adiabat_wall",
+             bc_Wall_use_wm=1, bc_Far_type="char", bc_Far_p_static=101000., bc_Far_mach=1.8, bc_Far_T_static=290., bc_Far_nx=1., bc_Far_ny=0., bc_Far_nz=0., LES=1,
+             SGS_model=1, C_s=0.325, filter_ratio=2.0, wall_model=1, shock_cap=1, s0=1e-9, expf_cutoff=1, calc_force=1, monitor_cp_freq=100000, area_ref=1.0)),
 }
 
 
@@ -229,9 +238,9 @@ def make_other_case(workdir, config, n, **over):
 
 
 def run_other_config(args):
-    """Configurations 1, 2, 4 on one GPU: same metric, same JSON line; the workload runs through the staged kernels (the reference's
-    method sequence, bit-exact), timed with the state resident in HBM, then end to end with host buffers; CPU baseline = the
-    unmodified reference on a bounded sample of the same configuration."""
+    """Configurations 1, 2, 4, 5 on one GPU: same metric, same JSON line; the workload runs in fast mode (blocked element kernels around
+    the interface kernels), timed with the state resident in HBM, then end to end with host buffers; CPU baseline = the unmodified
+    reference on a bounded sample of the same configuration."""
     import numpy as np
     import torch
     if not torch.cuda.is_available():
@@ -456,8 +465,8 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--size", dest="n", type=int, default=None, help="elements per direction of the global mesh (default 64 for config 3)")
-    ap.add_argument("--config", type=int, default=3, choices=[1, 2, 3, 4], help="BASELINE.json configuration: 3 (default) = TGV hex P=4, the headline; 1, 2, 4 = the "
-                    "quad / mixed 2-D / mixed 3-D configurations through the staged kernels, one GPU")
+    ap.add_argument("--config", type=int, default=3, choices=[1, 2, 3, 4, 5], help="BASELINE.json configuration: 3 (default) = TGV hex P=4, the headline; 1, 2, 4, 5 = the "
+                    "quad / mixed 2-D / mixed 3-D / wall-bounded LES configurations through the blocked element kernels, one GPU")
     ap.add_argument("--order", type=int, default=4)
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--cpu-n", type=int, default=15, help="elements per direction of the CPU baseline sample (15 = the reference's shipped TGV mesh)")
