@@ -109,22 +109,22 @@ def make_case(workdir, n, order, blocks=(1, 1, 1), **over):
 REF_BIN = os.path.join(ROOT, "oracle", "_ref", "HiFiLES_ref")
 
 
-def _ref_time_comp(workdir, inp, env):
-    """One run of the unmodified reference binary; returns the seconds between its first and its last monitored time step, read
-    from the last column of history.plt (Time_Comp: the reference's own clock() since start, in minutes; reference
-    src/output.cpp:2403-2406, src/HiFiLES.cpp:334-335).  The difference of two rows excludes the set-up."""
+def _ref_time_comp(workdir, inp, env, warmup=0):
+    """One run of the unmodified reference binary; returns the seconds per time step between its monitored steps, read from the
+    last column of history.plt (Time_Comp: the reference's own clock() since start, in minutes; reference src/output.cpp:2403-2406,
+    src/HiFiLES.cpp:334-335).  Differences of rows exclude the set-up; the first `warmup` steps after the first row are left out."""
     r = subprocess.run([REF_BIN, os.path.basename(inp)], cwd=workdir, env=env, capture_output=True, text=True)
     hist = os.path.join(workdir, "history.plt")
     if r.returncode != 0 or not os.path.exists(hist):
         return None
     rows = [l for l in open(hist).read().splitlines() if l and l[0].isdigit()]
-    if len(rows) < 2:
+    if len(rows) < 2 + warmup:
         return None
     t = [float(l.split(",")[-1]) * 60.0 for l in rows]
-    return (t[-1] - t[0]) / (len(rows) - 1)
+    return (t[-1] - t[warmup]) / (len(rows) - 1 - warmup)
 
 
-def cpu_reference_rate(order, n_ref, replicas=1):
+def cpu_reference_rate(order, n_ref, replicas=1, steps=1, warmup=0):
     """Times the UNMODIFIED reference CPU solver (oracle/_ref/HiFiLES_ref, built from /root/reference by oracle/build_ref.sh) on the
     bounded sample SURVEY.md section 8(d) names: the Taylor-Green case on n_ref^3 hexahedra (15^3 = the size of the mesh the reference
     ships), same order and options as the GPU workload, two time steps; seconds per step = difference of the reference's own
@@ -142,16 +142,17 @@ def cpu_reference_rate(order, n_ref, replicas=1):
         for r in range(replicas):
             d = os.path.join(work, "r%d" % r)
             os.makedirs(d)
-            _, _, inp = make_case(d, n_ref, order, n_steps=2, monitor_res_freq=1, plot_freq=1000000, restart_dump_freq=1000000)
+            _, _, inp = make_case(d, n_ref, order, n_steps=1 + warmup + steps, monitor_res_freq=1, plot_freq=1000000, restart_dump_freq=1000000)
             dirs.append((d, inp))
         with ThreadPoolExecutor(max_workers=replicas) as ex:
-            secs = list(ex.map(lambda a: _ref_time_comp(a[0], a[1], env), dirs))
+            secs = list(ex.map(lambda a: _ref_time_comp(a[0], a[1], env, warmup), dirs))
         if any(x is None for x in secs):
             return None
         dof = n_ref ** 3 * (order + 1) ** 3 * 5
         sec = max(max(secs), 1e-9)
         n_rk = 4
-        what = "TGV %d^3 hex P=%d, HLLC + LDG, SSP-RK34: one time step (4 RK stages) between two rows of the reference's own Time_Comp" % (n_ref, order)
+        what = ("TGV %d^3 hex P=%d, HLLC + LDG, SSP-RK34: seconds per time step (4 RK stages) over %d step(s) after %d warm-up step(s), from the rows of the "
+                "reference's own Time_Comp" % (n_ref, order, steps, warmup))
         sample = ("unmodified reference, serial: " + what) if replicas == 1 else (
             "%d concurrent serial runs (one per host core) of the unmodified reference, each " % replicas + what +
             "; no halo exchange, so an upper bound for the reference's MPI build on these cores")
@@ -173,24 +174,37 @@ def host_cores():
     return max(1, min(int(n or 1), 64))
 
 
+def workload_text(n, order, n_rk=4):
+    return ("3-D Taylor-Green vortex Re=1600, %d^3 hexahedra (global), P=%d, HLLC + LDG(beta=0.5), SSP-RK34, periodic; "
+            "1 step = 1 time step = %d RK stages" % (n, order, n_rk))
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    # --steps K --warmup W as for the GPU arm, each step one time step of the bounded sample (the shipped mesh size, 15^3).  A serial
+    # calibration run (1 step) sizes them: W + K steps must fit about four minutes on this host, else both shrink in proportion (the
+    # line prints the numbers actually used)
     serial = cpu_reference_rate(args.order, args.cpu_n)
     cores = host_cores()
-    res = cpu_reference_rate(args.order, args.cpu_n, cores) if (serial is not None and cores > 1) else serial
+    steps, warmup = max(1, args.steps), max(0, args.warmup)
+    if serial is not None:
+        fit = max(1, int(240.0 / max(serial["seconds"] * 1.3, 1e-3)))  # concurrent replicas run a little slower than one
+        if steps + warmup > fit:
+            warmup = max(0, min(warmup, fit // 5))
+            steps = max(1, fit - warmup)
+    res = cpu_reference_rate(args.order, args.cpu_n, cores, steps, warmup) if serial is not None else None
     if res is None:
-        res, cores = serial, 1
+        res, cores, steps, warmup = serial, 1, 1, 0
     n = args.n
-    cfg = {"workload": "3-D Taylor-Green vortex Re=1600, %d^3 hexahedra, P=%d, HLLC+LDG, SSP-RK34" % (n, args.order),
-           "sample": None}
+    cfg = {"workload": workload_text(n, args.order), "sample": None}
     if res is None:
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref (compiled reference) is not present"}))
         return
     cfg["sample"] = res["sample"]
     line = {"impl": "reference", "metric": "GDOF-RK-stage updates/s (TGV hex P=%d)" % args.order, "value": res["value"], "unit": "GDOF-stage/s",
-            "n_gpus": args.gpus, "steps": 1, "warmup": 1, "ms_per_step": res["seconds"] * 1e3, "higher_is_better": True, "scaling": "strong",
+            "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": res["seconds"] * 1e3, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg,
             "cpu_baseline": {"value": res["value"], "unit": "GDOF-stage/s", "cores": cores, "kind": "reference", "sample": res["sample"],
                              "serial_value": serial["value"]},
@@ -669,8 +683,7 @@ def main():
             "metric": "GDOF-RK-stage updates/s (TGV hex P=%d)" % args.order, "value": value, "unit": "GDOF-stage/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "3-D Taylor-Green vortex Re=1600, %d^3 hexahedra (global), P=%d, HLLC + LDG(beta=0.5), SSP-RK34, periodic; "
-                                   "1 step = 1 time step = %d RK stages" % (args.n, args.order, n_rk),
+            "config": {"workload": workload_text(args.n, args.order, n_rk),
                        "kernels": "fused" if fused else "staged", "elements_per_gpu": n_eles, "dof_total": dof_total,
                        "l2": "no flush needed: state per GPU %.2f GB >> 126 MB L2" % (dof_local * 8 / 1e9), "setup_s": round(t_setup, 1),
                        "partition": ("bricks %s" % (mg.blocks_for(world),) if args.partition == "bricks" else "METIS k-way (dual graph)") if world > 1 else "none"},
