@@ -184,13 +184,13 @@ def run_reference_arm(args):
     if rank != 0:
         return
     # --steps K --warmup W as for the GPU arm, each step one time step of the bounded sample (the shipped mesh size, 15^3).  A serial
-    # calibration run (1 step) sizes them: W + K steps must fit about four minutes on this host, else both shrink in proportion (the
+    # calibration run (1 step) sizes them: W + K steps must fit about two and a half minutes on this host, else both shrink in proportion (the
     # line prints the numbers actually used)
     serial = cpu_reference_rate(args.order, args.cpu_n)
     cores = host_cores()
     steps, warmup = max(1, args.steps), max(0, args.warmup)
     if serial is not None:
-        fit = max(1, int(240.0 / max(serial["seconds"] * 1.3, 1e-3)))  # concurrent replicas run a little slower than one
+        fit = max(1, int(150.0 / max(serial["seconds"] * 1.3, 1e-3)))  # concurrent replicas run a little slower than one
         if steps + warmup > fit:
             warmup = max(0, min(warmup, fit // 5))
             steps = max(1, fit - warmup)
