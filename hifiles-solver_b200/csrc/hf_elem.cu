@@ -293,8 +293,8 @@ __device__ __forceinline__ void to_physical(const double *gr, const double *J, d
     }
 }
 
-template <int ND, int NF>
-__global__ void __launch_bounds__(EL_THREADS, 2) k_elem_grad(const __grid_constant__ el_args A)
+template <int ND, int NF, int MINB>
+__global__ void __launch_bounds__(EL_THREADS, MINB) k_elem_grad(const __grid_constant__ el_args A)
 {
   extern __shared__ __align__(16) double sm[];
   const int e0 = blockIdx.x * A.E;
@@ -911,9 +911,10 @@ static int set_attrs(hf_ctx *c)
   if (c->ez->attr_done) return 0;
   const int lim = 200 * 1024;
 #define EL_ATTR(K) HF_CUDA(cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, lim))
-  EL_ATTR((k_elem_grad<3, 5>)); EL_ATTR((k_elem_grad<2, 4>)); EL_ATTR((k_elem_grad<2, 1>)); EL_ATTR((k_elem_grad<3, 1>));
+  EL_ATTR((k_elem_grad<3, 5, 2>)); EL_ATTR((k_elem_grad<2, 4, 4>)); EL_ATTR((k_elem_grad<2, 1, 4>)); EL_ATTR((k_elem_grad<3, 1, 2>));
   EL_ATTR((k_elem_resid<3, 5, 2>)); EL_ATTR((k_elem_resid<2, 4, 2>)); EL_ATTR((k_elem_resid<2, 1, 2>)); EL_ATTR((k_elem_resid<3, 1, 2>));
   EL_ATTR((k_elem_resid<3, 5, 3>)); EL_ATTR((k_elem_resid<2, 4, 3>)); EL_ATTR((k_elem_resid<2, 1, 3>)); EL_ATTR((k_elem_resid<3, 1, 3>));
+  EL_ATTR((k_elem_resid<3, 5, 4>)); EL_ATTR((k_elem_resid<2, 4, 4>)); EL_ATTR((k_elem_resid<2, 1, 4>)); EL_ATTR((k_elem_resid<3, 1, 4>));
   EL_ATTR((k_elem_face<3, 5>)); EL_ATTR((k_elem_face<2, 4>)); EL_ATTR((k_elem_face<2, 1>)); EL_ATTR((k_elem_face<3, 1>));
 #undef EL_ATTR
   c->ez->attr_done = true;
@@ -986,7 +987,16 @@ int hf_elem_stage(hf_ctx *c, int rk_stage, double time, int keep_residual)
         A.grad_out = e.grad_disu_upts;
         A.grad_from_global = 1;
       }
-      EL_LAUNCH(k_elem_grad, T.smem_grad);
+      {
+        const unsigned grid = (unsigned)((e.n_eles + A.E - 1) / A.E);
+        if (nd == 3 && nfl == 5) k_elem_grad<3, 5, 2><<<grid, EL_THREADS, T.smem_grad, c->stream>>>(A);
+        else if (nd == 2 && nfl == 4) k_elem_grad<2, 4, 4><<<grid, EL_THREADS, T.smem_grad, c->stream>>>(A);
+        else if (nd == 2 && nfl == 1) k_elem_grad<2, 1, 4><<<grid, EL_THREADS, T.smem_grad, c->stream>>>(A);
+        else k_elem_grad<3, 1, 2><<<grid, EL_THREADS, T.smem_grad, c->stream>>>(A);
+        c->launches++;
+        cudaError_t e_ = cudaGetLastError();
+        if (e_ != cudaSuccess) { hf_set_error(std::string("kernel launch (k_elem_grad): ") + cudaGetErrorString(e_)); return 1; }
+      }
     }
     if (par) EACH_MPI(4);
     if (les)
@@ -1033,12 +1043,15 @@ int hf_elem_stage(hf_ctx *c, int rk_stage, double time, int keep_residual)
     if (hf_rk_coeffs(c, stage, &A.rk_mode, &A.rk_copy, &A.fac, &A.c1, &A.c2)) return 1;
     {
       // three CTAs per SM at 80 registers (a few spills in the flux phase) against two at 112 - 128: chosen by measurement
-      static const int minb = getenv("HF_ELEM_MINB") ? atoi(getenv("HF_ELEM_MINB")) : 3;
+      // (measured: 2-D meshes gain from four CTAs per SM at 64 registers -- quadrilaterals 33.0 -> 36.8, mixed 2-D 10.4 -> 10.9 GDOF-stage/s --
+      // 3-D ones are bounded by their shared-memory tiles and stay at three)
+      const int minb = getenv("HF_ELEM_MINB") ? atoi(getenv("HF_ELEM_MINB")) : (nd == 2 ? 4 : 3);
       const unsigned grid = (unsigned)((e.n_eles + A.E - 1) / A.E);
       const size_t smem = T.smem_resid;
 #define EL_RESID(ND_, NF_)                                                                                 \
       do {                                                                                                 \
-        if (minb >= 3) k_elem_resid<ND_, NF_, 3><<<grid, EL_THREADS, smem, c->stream>>>(A);                \
+        if (minb >= 4) k_elem_resid<ND_, NF_, 4><<<grid, EL_THREADS, smem, c->stream>>>(A);                \
+        else if (minb >= 3) k_elem_resid<ND_, NF_, 3><<<grid, EL_THREADS, smem, c->stream>>>(A);           \
         else k_elem_resid<ND_, NF_, 2><<<grid, EL_THREADS, smem, c->stream>>>(A);                          \
       } while (0)
       if (nd == 3 && nfl == 5) EL_RESID(3, 5);
