@@ -878,14 +878,19 @@ int launch9(hf_ctx *c, fused_args &A, int what, int lo, int hi)
     HF_CUDA(cudaFuncSetAttribute(k_resid9<N, NT_R, MINB_R, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_r));
     HF_CUDA(cudaFuncSetAttribute(k_resid9<N, NT_R, MINB_R, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_r));
     HF_CUDA(cudaFuncSetAttribute(k_resid9<N, NT_R, MINB_R, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_r));
-    HF_CUDA(cudaFuncSetAttribute(k_face9<N, NT_F, MINB_F>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_f));
+    HF_CUDA(cudaFuncSetAttribute(k_face9<N, NT_F, MINB_F, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_f));
+    HF_CUDA(cudaFuncSetAttribute(k_face9<N, NT_F, MINB_F, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_f));
     HF_CUDA(cudaFuncSetAttribute(k_resid9<N, NT_R, MINB_R, 0>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     HF_CUDA(cudaFuncSetAttribute(k_resid9<N, NT_R, MINB_R, 1>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-    HF_CUDA(cudaFuncSetAttribute(k_face9<N, NT_F, MINB_F>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    HF_CUDA(cudaFuncSetAttribute(k_face9<N, NT_F, MINB_F, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    HF_CUDA(cudaFuncSetAttribute(k_face9<N, NT_F, MINB_F, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     attr_done = true;
   }
   if (what == 5)
-    k_face9<N, NT_F, MINB_F><<<grid, NT_F, smem_f, c->stream>>>(A);
+  {
+    if (A.nlf) k_face9<N, NT_F, MINB_F, true><<<grid, NT_F, smem_f, c->stream>>>(A);
+    else k_face9<N, NT_F, MINB_F, false><<<grid, NT_F, smem_f, c->stream>>>(A);
+  }
   else if (what == 7)
     k_resid9<N, NT_R, MINB_R, 2><<<grid, NT_R, smem_r, c->stream>>>(A);
   else

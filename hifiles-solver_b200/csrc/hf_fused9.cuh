@@ -648,7 +648,7 @@ __host__ inline void make_class_lists9(const unsigned long long *own, unsigned *
   out[0] = (unsigned)n_e | ((unsigned)n_t << 8);
 }
 
-template <int N, int NT, int MINB>
+template <int N, int NT, int MINB, bool ROEM>
 __global__ void __launch_bounds__(NT, MINB) k_face9(const __grid_constant__ fused_args A)
 {
   typedef geo9<N> G;
@@ -847,8 +847,8 @@ __global__ void __launch_bounds__(NT, MINB) k_face9(const __grid_constant__ fuse
     {
       const double *nrm = &S.em[10 + 4 * f + 1];
       double nl[3] = {nrm[0], nrm[1], nrm[2]};
-      if (A.nlf) // RoeM: the reference's normal of exactly this flux point (hf_fused_prepare)
-      {
+      if constexpr (ROEM) // RoeM: the reference's normal of exactly this flux point (hf_fused_prepare); a kernel variant of its own, so that the
+      {                   // other solvers do not carry the pointer (the run-time test cost k_face9 2 % in registers / spills)
         const double *q3 = A.nlf + ((size_t)(ge * 6 + f) * NN + j) * 3;
         nl[0] = q3[0]; nl[1] = q3[1]; nl[2] = q3[2];
       }

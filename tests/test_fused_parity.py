@@ -118,8 +118,8 @@ def test_roem_on_rounding_level_normal_mach(tmp_path, hb, meshgen):
         run.set_mode(False)
         run.run(3, fused=False)
         check("staged", run.download("hex", "disu_upts"), ref["final.hex.disu_upts"], 1e-14)
-    for env in ({}, {"HF_FUSED_GEN6": "1"}):
-        for k in ("HF_FUSED_GEN6",):
+    for env in ({}, {"HF_FUSED_GEN6": "1"}, {"HF_FUSED_GEN9": "1"}):
+        for k in ("HF_FUSED_GEN6", "HF_FUSED_GEN9"):
             os.environ.pop(k, None)
         os.environ.update(env)
         try:
