@@ -27,6 +27,7 @@
 // out_buffer_disu[inter][field][fpt], src/mpi_inters.cpp:226-229).
 // Algorithmic traffic per element-stage, P = 4, RK34: see DESIGN.md (about 9 k doubles vs 56 k for the staged path).
 #include "hf_device.h"
+#include "hf_bc.cuh"
 #include <cstring>
 #include <type_traits>
 #include <cstdlib>
@@ -117,7 +118,7 @@ struct fused_args
                           // generation 7: the complete common normal flux fc (5 per point) at the owned faces
   const double *em;       // [ele][EM]: JGinv[9], 1/detjac, 6 x (tdA, left normal[3])
   const int *nbr;         // [ele][6] neighbour face block
-  const int *finfo;       // [ele][6] rot + 4*is_right + 8*partition face
+  const int *finfo;       // [ele][6] rot + 4*is_right + 8*partition face + 16*boundary face (then bits 8.. = index into the boundary table)
   const unsigned long long *bmask; // [ele][6] per face: bit j clear = own LDG weight 0.5 + beta, set = 0.5 - beta (see hf_fused_prepare)
   const double *dt_local;
   const unsigned *wait_flag; // generation 9, one launch per kernel: CTAs from position wait_from on (the partition-adjacent elements) wait until
@@ -144,6 +145,8 @@ struct fused_args
   int viscous, keep_residual, do_update;
   int pf_dist;            // L2 software-prefetch distance in CTAs (0 = off)
   unsigned long long own_xor; // generation 7: bmask ^ own_xor = the flux points this element owns (LDG weight 1)
+  const hf_bc *bct;       // generation 9 with boundary faces: the boundary table (finfo >> 8 of a boundary face indexes it)
+  double R_ref;
 };
 
 __device__ __forceinline__ void cp_async8(void *smem, const void *gmem)
@@ -347,6 +350,7 @@ struct hf_fused_state
   bool available = false;
   std::string why; // reason the fused path is not available
   int order = 0, n_eles = 0, n_mpi = 0;
+  int n_bdy = 0; // boundary faces (generation 9 only): virtual neighbour blocks behind the receive blocks of fu
   double *fu[2] = {nullptr, nullptr};
   int cur = 0;
   double *fv = nullptr;
@@ -633,8 +637,16 @@ int hf_fused_prepare(hf_ctx *c)
     if (c->eles[t].present) return no("fused kernels exist for hexahedra only");
   if (!e.present) return no("no hexahedra");
   if (c->prm.equation != 0 || e.n_fields != NF) return no("fused kernels exist for the Euler / Navier-Stokes equations only");
-  for (int t = 0; t < HF_N_INTER_TYPES; t++)
-    if (c->bdys[t].n_inters) return no("boundary interfaces present (fused path handles interior and partition faces)");
+  // boundary faces: generation 9 only (decided below); its face kernel evaluates the ghost state itself
+  hf_bdy_inters_dev &Bd = c->bdys[2];
+  if (c->bdys[0].n_inters || c->bdys[1].n_inters) return no("boundary faces of a non-quad type");
+  const int n_bdy = Bd.n_inters;
+  if (n_bdy)
+  {
+    if (getenv("HF_FUSED_BDY") && atoi(getenv("HF_FUSED_BDY")) == 0) return no("boundary interfaces present (HF_FUSED_BDY=0: blocked element kernels)");
+    if (Bd.wm_upt) return no("boundary interfaces with a wall model run through the blocked element kernels");
+    if ((int)Bd.h_ele_l.size() != n_bdy || (int)Bd.h_loc_l.size() != n_bdy || (int)Bd.h_bc_id.size() != n_bdy) return no("boundary interfaces: host lists not kept");
+  }
   if (!e.affine) return no("elements are not affine (metric variation inside an element)");
   if (c->prm.over_int) return no("over-integration runs through the staged kernels");
   if (c->prm.LES) return no("LES runs through the staged kernels");
@@ -696,6 +708,19 @@ int hf_fused_prepare(hf_ctx *c)
     for (int j = 0; j < NN; j++)
       if (e.h_own_sign[(size_t)el * NFP + fl * NN + j] < 0) bmask[(size_t)el * 6 + fl] |= 1ull << j;
   }
+  // boundary faces: every flux point owned (whatever the sign of beta), no rotation, the "neighbour" is the virtual block that k_face9 fills
+  // with the boundary's common solution
+  const unsigned long long full_mask = NN == 64 ? ~0ull : ((1ull << NN) - 1ull);
+  const unsigned long long own_xor0 = c->prm.ldg_beta > 0. ? full_mask : 0ull;
+  for (int i = 0; i < n_bdy; i++)
+  {
+    const int el = Bd.h_ele_l[i], fl = Bd.h_loc_l[i];
+    if (Bd.h_ele_type_l[i] != 4) return no("boundary interface of a non-hexahedron");
+    nbr[(size_t)el * 6 + fl] = ne * 6 + M.n_inters + i;
+    finfo[(size_t)el * 6 + fl] = 16 | (Bd.h_bc_id[i] << 8);
+    bmask[(size_t)el * 6 + fl] = full_mask ^ own_xor0;
+  }
+  Z->n_bdy = n_bdy;
   for (size_t q = 0; q < nbr.size(); q++)
     if (nbr[q] < 0) return no("an element face has no neighbour");
   // One-sided LDG (generation 7): |beta| = 0.5 makes the LDG weights exactly 1 and 0, so every flux-point pair has one
@@ -715,9 +740,11 @@ int hf_fused_prepare(hf_ctx *c)
       if (T.c5[1 * N + m] != Z->c5s[0][m] || T.c5[0 * N + m] != Z->c5s[0][m] || T.c5[3 * N + m] != Z->c5s[1][m] || T.c5[5 * N + m] != Z->c5s[1][m])
         side_uniform = false;
     }
-    const bool want9 = getenv("HF_FUSED_GEN9") ? atoi(getenv("HF_FUSED_GEN9")) != 0 : N == 5;
+    const bool want9 = getenv("HF_FUSED_GEN9") ? atoi(getenv("HF_FUSED_GEN9")) != 0 : (N == 5 || n_bdy > 0);
     Z->gen9 = Z->os && side_uniform && want9 && !getenv("HF_FUSED_GEN7");
   }
+  if (n_bdy && !Z->gen9)
+    return no("boundary interfaces present (the fused kernels take them in generation 9 only: viscous, |ldg_beta| = 0.5; otherwise the blocked element kernels)");
   const int FB = (NF * NN + 1) & ~1; // generation 9: face blocks padded to an even count (16-byte aligned for the bulk copies)
   Z->fu_blk = Z->gen9 ? FB : NF * NN;
   Z->fv_blk = Z->gen9 ? FB : (Z->os ? NF * NN : 4 * NN);
@@ -727,7 +754,7 @@ int hf_fused_prepare(hf_ctx *c)
   for (int i = 0; i < M.n_inters; i++) Z->h_pmask[i] = bmask[(size_t)M.h_ele_l[i] * 6 + M.h_loc_l[i]] ^ Z->own_xor;
   // per own flux point: where the neighbour's value of field 0 sits in fu (block * NF*NN + permuted flux point)
   std::vector<int> nidx((size_t)ne * NFP);
-  if ((double)nblk_total(ne, M.n_inters) * (NF * NN + 1) > 2.0e9) return no("face arrays exceed int32 indexing");
+  if (((double)nblk_total(ne, M.n_inters) + n_bdy) * (NF * NN + 1) > 2.0e9) return no("face arrays exceed int32 indexing");
   for (int i = 0; i < ne; i++)
     for (int f = 0; f < 6; f++)
       for (int j = 0; j < NN; j++)
@@ -745,8 +772,8 @@ int hf_fused_prepare(hf_ctx *c)
   Z->order = e.order;
   Z->n_eles = ne;
   const size_t nblk = (size_t)ne * 6 + M.n_inters;
-  if (hf_alloc_zero(c, &Z->fu[0], nblk * FB)) return 1;
-  if (hf_alloc_zero(c, &Z->fu[1], nblk * FB)) return 1;
+  if (hf_alloc_zero(c, &Z->fu[0], (nblk + n_bdy) * FB)) return 1;
+  if (hf_alloc_zero(c, &Z->fu[1], (nblk + n_bdy) * FB)) return 1;
   if (visc && hf_alloc_zero(c, &Z->fv, nblk * FB)) return 1;
   if (Z->gen9)
   {
@@ -789,10 +816,12 @@ int hf_fused_prepare(hf_ctx *c)
         }
     if (hf_alloc_copy(c, &Z->nlf, nlf.data(), nlf.size())) return 1;
   }
-  if (M.n_inters)
+  if (M.n_inters + n_bdy)
   {
-    if (hf_alloc_zero(c, &Z->out_u, (size_t)M.n_inters * FB)) return 1;
-    if (visc && hf_alloc_zero(c, &Z->out_g, (size_t)M.n_inters * FB)) return 1;
+    // k_resid9 publishes every face whose neighbour block lies behind the last element into the send buffer: the boundary faces' blocks
+    // ride along behind the partition faces' (never sent)
+    if (hf_alloc_zero(c, &Z->out_u, (size_t)(M.n_inters + n_bdy) * FB)) return 1;
+    if (visc && M.n_inters && hf_alloc_zero(c, &Z->out_g, (size_t)M.n_inters * FB)) return 1;
   }
   // host-side extracts are no longer needed
   std::vector<double>().swap(e.h_em);
@@ -878,18 +907,27 @@ int launch9(hf_ctx *c, fused_args &A, int what, int lo, int hi)
     HF_CUDA(cudaFuncSetAttribute(k_resid9<N, NT_R, MINB_R, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_r));
     HF_CUDA(cudaFuncSetAttribute(k_resid9<N, NT_R, MINB_R, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_r));
     HF_CUDA(cudaFuncSetAttribute(k_resid9<N, NT_R, MINB_R, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_r));
-    HF_CUDA(cudaFuncSetAttribute(k_face9<N, NT_F, MINB_F, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_f));
-    HF_CUDA(cudaFuncSetAttribute(k_face9<N, NT_F, MINB_F, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_f));
+    HF_CUDA(cudaFuncSetAttribute(k_face9<N, NT_F, MINB_F, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_f));
+    HF_CUDA(cudaFuncSetAttribute(k_face9<N, NT_F, MINB_F, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_f));
+    HF_CUDA(cudaFuncSetAttribute(k_face9<N, NT_F, MINB_F, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_f));
+    HF_CUDA(cudaFuncSetAttribute(k_face9<N, NT_F, MINB_F, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_f));
     HF_CUDA(cudaFuncSetAttribute(k_resid9<N, NT_R, MINB_R, 0>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     HF_CUDA(cudaFuncSetAttribute(k_resid9<N, NT_R, MINB_R, 1>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-    HF_CUDA(cudaFuncSetAttribute(k_face9<N, NT_F, MINB_F, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-    HF_CUDA(cudaFuncSetAttribute(k_face9<N, NT_F, MINB_F, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    HF_CUDA(cudaFuncSetAttribute(k_face9<N, NT_F, MINB_F, false, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    HF_CUDA(cudaFuncSetAttribute(k_face9<N, NT_F, MINB_F, true, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    HF_CUDA(cudaFuncSetAttribute(k_face9<N, NT_F, MINB_F, false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    HF_CUDA(cudaFuncSetAttribute(k_face9<N, NT_F, MINB_F, true, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     attr_done = true;
   }
   if (what == 5)
   {
-    if (A.nlf) k_face9<N, NT_F, MINB_F, true><<<grid, NT_F, smem_f, c->stream>>>(A);
-    else k_face9<N, NT_F, MINB_F, false><<<grid, NT_F, smem_f, c->stream>>>(A);
+    if (A.bct) // the mesh has boundary faces
+    {
+      if (A.nlf) k_face9<N, NT_F, MINB_F, true, true><<<grid, NT_F, smem_f, c->stream>>>(A);
+      else k_face9<N, NT_F, MINB_F, false, true><<<grid, NT_F, smem_f, c->stream>>>(A);
+    }
+    else if (A.nlf) k_face9<N, NT_F, MINB_F, true, false><<<grid, NT_F, smem_f, c->stream>>>(A);
+    else k_face9<N, NT_F, MINB_F, false, false><<<grid, NT_F, smem_f, c->stream>>>(A);
   }
   else if (what == 7)
     k_resid9<N, NT_R, MINB_R, 2><<<grid, NT_R, smem_r, c->stream>>>(A);
@@ -1014,6 +1052,8 @@ void base_args(hf_ctx *c, hf_fused_state *Z, fused_args &A)
   static const int pf = getenv("HF_FUSED_PF") ? atoi(getenv("HF_FUSED_PF")) : 0; // measured: no effect on B200 (the other resident CTAs already cover the staging latency)
   A.pf_dist = pf;
   A.own_xor = Z->own_xor;
+  A.bct = Z->n_bdy ? c->bc_table : nullptr;
+  A.R_ref = c->prm.R_ref;
 }
 
 // exchange the partition-face blocks of arr (blk_doubles each): pack -> ncclSend/Recv into the tail of arr, on the

@@ -192,7 +192,8 @@ __host__ inline task9 make_task9(int dir, unsigned lut, unsigned long long own_f
   // the right side of a face negates as well (norm_tconf of this element = +-tdA fc)
   const bool ngm = (((info_m & 8) != 0) && !om) != ((info_m & 4) != 0);
   const bool ngp = (((info_p & 8) != 0) && !op) != ((info_p & 4) != 0);
-  const int xm = perm9<N>(info_m, jm), xp = perm9<N>(info_p, jp);
+  // a boundary face's virtual neighbour block is in the own numbering
+  const int xm = (info_m & 16) ? jm : perm9<N>(info_m, jm), xp = (info_p & 16) ? jp : perm9<N>(info_p, jp);
   // common flux: a face without owned points holds the neighbour's raw block, any other the own block
   const int cm = own_fm == 0ull ? xm : jm, cp = own_fp == 0ull ? xp : jp;
   task9 t;
@@ -613,6 +614,7 @@ struct smem9f
   int n_owned;
   unsigned cl[CL9_WORDS];  // the element class's pass lists
   unsigned short olist[6 * N * N];
+  int vblk[6];            // boundary faces (BDY variant): the face's virtual neighbour block in fu (the boundary's common solution, for k_resid9), else -1
 };
 
 __host__ __device__ __forceinline__ int dir_minus_face9(int d) { return d == 0 ? 4 : (d == 1 ? 1 : 0); }
@@ -648,8 +650,16 @@ __host__ inline void make_class_lists9(const unsigned long long *own, unsigned *
   out[0] = (unsigned)n_e | ((unsigned)n_t << 8);
 }
 
-template <int N, int NT, int MINB, bool ROEM>
-__global__ void __launch_bounds__(NT, MINB) k_face9(const __grid_constant__ fused_args A)
+// BDY: the mesh has boundary faces.  A boundary face is a face whose flux points the element all owns; its "neighbour" is the ghost state
+// of bdy_inters::set_boundary_conditions (reference src/bdy_inters.cpp:213-338, 1024-1136; device restatement hf_bc.cuh) evaluated here
+// from the own face values:
+//   LDG common solution  u_c = u_r (ldg_solution, flux_spec 1; the viscous wall state on walls)  -> delta = u_c - u_l, and u_c goes into the
+//                        face's virtual neighbour block of fu, where k_resid9 finds it like any neighbour's face values
+//   inviscid             Riemann(u_l, u_r of the inviscid boundary state); slip_wall_dual: F(u_l).n
+//   viscous              F_v(u_r, boundary gradient of the own corrected gradient).n - tau (u_r - u_l)  (ldg_flux, flux_spec 1); none on a slip wall
+// A kernel variant of its own (the ghost-state code costs registers): meshes without boundary faces keep the other one.
+template <int N, int NT, int MINB, bool ROEM, bool BDY>
+__global__ void __launch_bounds__(NT, BDY ? (MINB > 1 ? MINB - 1 : 1) : MINB) k_face9(const __grid_constant__ fused_args A)
 {
   typedef geo9<N> G;
   typedef smem9f<N> SM;
@@ -666,13 +676,17 @@ __global__ void __launch_bounds__(NT, MINB) k_face9(const __grid_constant__ fuse
   {
     unsigned long long o = 0ull;
     int nb = 0;
+    bool bdy = false;
     if (lane < 6)
     {
       o = __ldg(A.bmask + (size_t)ge * 6 + lane) ^ A.own_xor;
       nb = __ldg(A.nbr + (size_t)ge * 6 + lane);
+      const int info = __ldg(A.finfo + (size_t)ge * 6 + lane);
+      bdy = BDY && (info & 16) != 0;
       S.own[lane] = o;
-      S.info[lane] = __ldg(A.finfo + (size_t)ge * 6 + lane);
-      S.send[lane] = nb - 6 * A.n_eles;
+      S.info[lane] = info;
+      S.send[lane] = bdy ? -1 : nb - 6 * A.n_eles;
+      if (BDY) S.vblk[lane] = bdy ? nb : -1;
     }
     if (lane == 0)
     {
@@ -684,13 +698,13 @@ __global__ void __launch_bounds__(NT, MINB) k_face9(const __grid_constant__ fuse
     {
       const int f = lane;
       const bool act = o != 0ull;
-      mbar_expect_tx(&S.bar, (act ? 3u * (unsigned)(FB * 8) : 0u) + (f == 0 ? (unsigned)(EM * 8) : 0u));
+      mbar_expect_tx(&S.bar, (act ? (bdy ? 2u : 3u) * (unsigned)(FB * 8) : 0u) + (f == 0 ? (unsigned)(EM * 8) : 0u));
       if (act)
       {
         const size_t ob = ((size_t)ge * 6 + f) * FB;
         bulk_g2s(S.uf[f], A.fu_cur + ob, FB * 8, &S.bar);
         bulk_g2s(S.gn[f], A.gn + ob, FB * 8, &S.bar);
-        bulk_g2s(S.dl[f], A.fu_cur + (size_t)nb * FB, FB * 8, &S.bar);
+        if (!bdy) bulk_g2s(S.dl[f], A.fu_cur + (size_t)nb * FB, FB * 8, &S.bar); // a boundary face has no neighbour block: its delta comes from the ghost state
       }
       if (f == 0) bulk_g2s(S.em, A.em + (size_t)ge * EM, EM * 8, &S.bar);
     }
@@ -717,9 +731,30 @@ __global__ void __launch_bounds__(NT, MINB) k_face9(const __grid_constant__ fuse
         if (o != 0ull)
         {
           const bool mine = (o >> j) & 1ull;
-          const int pj = perm9<N>(S.info[f], j);
+          if (BDY && (S.info[f] & 16))
+          {
+            // the LDG common solution of a boundary flux point is the ghost state (the viscous wall state on walls)
+            double ul[NF], ur[NF];
 #pragma unroll
-          for (int k = 0; k < NF; k++) d[it][k] = mine ? S.dl[f][k * NN + pj] - S.uf[f][k * NN + j] : 0.;
+            for (int k = 0; k < NF; k++) { ul[k] = S.uf[f][k * NN + j]; ur[k] = 0.; }
+            const hf_bc &B = A.bct[S.info[f] >> 8];
+            const double *nrm = &S.em[10 + 4 * f + 1];
+            set_boundary_conditions<ND, NF>(0, B, ul, ur, nrm, A.P.gamma, A.R_ref);
+            if (hf_is_wall(B.bc_flag)) set_boundary_conditions<ND, NF>(1, B, ul, ur, nrm, A.P.gamma, A.R_ref);
+            double *vb = const_cast<double *>(A.fu_cur) + (size_t)S.vblk[f] * FB + j;
+#pragma unroll
+            for (int k = 0; k < NF; k++)
+            {
+              d[it][k] = ur[k] - ul[k];
+              vb[k * NN] = ur[k];
+            }
+          }
+          else
+          {
+            const int pj = perm9<N>(S.info[f], j);
+#pragma unroll
+            for (int k = 0; k < NF; k++) d[it][k] = mine ? S.dl[f][k * NN + pj] - S.uf[f][k * NN + j] : 0.;
+          }
           if (mine) S.olist[atomicAdd(&S.n_owned, 1)] = (unsigned short)q;
         }
       }
@@ -819,8 +854,65 @@ __global__ void __launch_bounds__(NT, MINB) k_face9(const __grid_constant__ fuse
     // l(s) . c5 of the own face and of the opposite one
     const double lc_self = plus ? A.lc5s[1][1] : A.lc5s[0][0], lc_opp = plus ? A.lc5s[0][1] : A.lc5s[1][0];
     double uo[NF], un[NF], fn[NF], vn[NF];
+    if constexpr (!BDY) // meshes without boundary faces: the code the headline configuration was tuned with, untouched
     {
-      double g[NF * ND], fv[NF * ND];
+      {
+        double g[NF * ND], fv[NF * ND];
+#pragma unroll
+        for (int k = 0; k < NF; k++)
+        {
+          uo[k] = S.uf[f][k * NN + j];
+          const double ds = S.dl[f][k * NN + j];
+          const double dop = S.dl[fo][k * NN + jo];
+          un[k] = uo[k] + ds; // the neighbour's value back from the correction (an owned point: delta = u_nbr - u_own)
+          const double an = (S.gn[f][k * NN + j] + lc_self * ds + (opp ? lc_opp * dop : 0.)) * idj;
+          const double a0 = S.gt[0][f][k * NN + j] * idj, a1 = S.gt[1][f][k * NN + j] * idj;
+          const double gr0 = n == 0 ? an : a0;                 // t0 = 0 unless n = 0
+          const double gr1 = n == 1 ? an : (n == 0 ? a0 : a1); // direction 1 is t0 for n = 0, t1 for n = 2
+          const double gr2 = n == 2 ? an : a1;                 // t1 = 2 unless n = 2
+          g[k] = gr0 * J[0] + gr1 * J[1] + gr2 * J[2];
+          g[k + 5] = gr0 * J[3] + gr1 * J[4] + gr2 * J[5];
+          g[k + 10] = gr0 * J[6] + gr1 * J[7] + gr2 * J[8];
+        }
+        vis_flux_fast(uo, g, fv, A.P);
+        const double *nrm = &S.em[10 + 4 * f + 1];
+        const double n0 = nrm[0], n1 = nrm[1], n2 = nrm[2];
+        vn[0] = 0.;
+#pragma unroll
+        for (int k = 1; k < NF; k++) vn[k] = fv[k] * n0 + fv[k + 5] * n1 + fv[k + 10] * n2;
+      }
+      {
+        const double *nrm = &S.em[10 + 4 * f + 1];
+        double nl[3] = {nrm[0], nrm[1], nrm[2]};
+        if constexpr (ROEM) // RoeM: the reference's normal of exactly this flux point (hf_fused_prepare); a kernel variant of its own, so that the
+        {                   // other solvers do not carry the pointer (the run-time test cost k_face9 2 % in registers / spills)
+          const double *q3 = A.nlf + ((size_t)(ge * 6 + f) * NN + j) * 3;
+          nl[0] = q3[0]; nl[1] = q3[1]; nl[2] = q3[2];
+        }
+        double ul[NF], ur[NF];
+#pragma unroll
+        for (int k = 0; k < NF; k++)
+        {
+          ul[k] = is_right ? un[k] : uo[k];
+          ur[k] = is_right ? uo[k] : un[k];
+        }
+        riemann_fast(ul, ur, nl, fn, A.P);
+      }
+      const double ts = is_right ? -A.P.ldg_tau : A.P.ldg_tau;
+      fn[0] -= ts * (un[0] - uo[0]);
+#pragma unroll
+      for (int k = 1; k < NF; k++) fn[k] += vn[k] - ts * (un[k] - uo[k]);
+    }
+    else
+    {
+      const double *nrm = &S.em[10 + 4 * f + 1];
+      double nl[3] = {nrm[0], nrm[1], nrm[2]};
+      if constexpr (ROEM) // RoeM: the reference's normal of exactly this flux point (hf_fused_prepare); a kernel variant of its own, so that the
+      {                   // other solvers do not carry the pointer (the run-time test cost k_face9 2 % in registers / spills)
+        const double *q3 = A.nlf + ((size_t)(ge * 6 + f) * NN + j) * 3;
+        nl[0] = q3[0]; nl[1] = q3[1]; nl[2] = q3[2];
+      }
+      double g[NF * ND];
 #pragma unroll
       for (int k = 0; k < NF; k++)
       {
@@ -837,34 +929,59 @@ __global__ void __launch_bounds__(NT, MINB) k_face9(const __grid_constant__ fuse
         g[k + 5] = gr0 * J[3] + gr1 * J[4] + gr2 * J[5];
         g[k + 10] = gr0 * J[6] + gr1 * J[7] + gr2 * J[8];
       }
-      vis_flux_fast(uo, g, fv, A.P);
-      const double *nrm = &S.em[10 + 4 * f + 1];
-      const double n0 = nrm[0], n1 = nrm[1], n2 = nrm[2];
-      vn[0] = 0.;
-#pragma unroll
-      for (int k = 1; k < NF; k++) vn[k] = fv[k] * n0 + fv[k + 5] * n1 + fv[k + 10] * n2;
-    }
-    {
-      const double *nrm = &S.em[10 + 4 * f + 1];
-      double nl[3] = {nrm[0], nrm[1], nrm[2]};
-      if constexpr (ROEM) // RoeM: the reference's normal of exactly this flux point (hf_fused_prepare); a kernel variant of its own, so that the
-      {                   // other solvers do not carry the pointer (the run-time test cost k_face9 2 % in registers / spills)
-        const double *q3 = A.nlf + ((size_t)(ge * 6 + f) * NN + j) * 3;
-        nl[0] = q3[0]; nl[1] = q3[1]; nl[2] = q3[2];
-      }
-      double ul[NF], ur[NF];
-#pragma unroll
-      for (int k = 0; k < NF; k++)
+      if (BDY && (info & 16))
       {
-        ul[k] = is_right ? un[k] : uo[k];
-        ur[k] = is_right ? uo[k] : un[k];
-      }
-      riemann_fast(ul, ur, nl, fn, A.P);
-    }
-    const double ts = is_right ? -A.P.ldg_tau : A.P.ldg_tau;
-    fn[0] -= ts * (un[0] - uo[0]);
+        // boundary flux point (reference src/bdy_inters.cpp:213-338 inviscid, :1024-1090 viscous)
+        const hf_bc &B = A.bct[info >> 8];
+        double ur[NF];
 #pragma unroll
-    for (int k = 1; k < NF; k++) fn[k] += vn[k] - ts * (un[k] - uo[k]);
+        for (int k = 0; k < NF; k++) ur[k] = 0.;
+        set_boundary_conditions<ND, NF>(0, B, uo, ur, nrm, A.P.gamma, A.R_ref);
+        if (B.bc_flag == HF_SLIP_WALL_DUAL) // dual-consistent wall: the common flux is the left normal flux
+        {
+          side_state L;
+          make_side(uo, nl, A.P.gamma - 1.0, L);
+#pragma unroll
+          for (int k = 0; k < NF; k++) fn[k] = L.fn[k];
+        }
+        else
+          riemann_fast(uo, ur, nl, fn, A.P);
+        if (B.bc_flag != HF_SLIP_WALL) // a slip wall carries no viscous flux
+        {
+          double gr[NF * ND], fv[NF * ND];
+          set_boundary_conditions<ND, NF>(1, B, uo, ur, nrm, A.P.gamma, A.R_ref);
+          set_boundary_gradients<ND, NF>(B.bc_flag, ur, g, gr, nrm);
+          vis_flux_fast(ur, gr, fv, A.P);
+          fn[0] -= A.P.ldg_tau * (ur[0] - uo[0]);
+#pragma unroll
+          for (int k = 1; k < NF; k++) fn[k] += (fv[k] * nrm[0] + fv[k + 5] * nrm[1] + fv[k + 10] * nrm[2]) - A.P.ldg_tau * (ur[k] - uo[k]);
+        }
+      }
+      else
+      {
+        {
+          double fv[NF * ND];
+          vis_flux_fast(uo, g, fv, A.P);
+          vn[0] = 0.;
+#pragma unroll
+          for (int k = 1; k < NF; k++) vn[k] = fv[k] * nrm[0] + fv[k + 5] * nrm[1] + fv[k + 10] * nrm[2];
+        }
+        {
+          double ul[NF], ur[NF];
+#pragma unroll
+          for (int k = 0; k < NF; k++)
+          {
+            ul[k] = is_right ? un[k] : uo[k];
+            ur[k] = is_right ? uo[k] : un[k];
+          }
+          riemann_fast(ul, ur, nl, fn, A.P);
+        }
+        const double ts = is_right ? -A.P.ldg_tau : A.P.ldg_tau;
+        fn[0] -= ts * (un[0] - uo[0]);
+#pragma unroll
+        for (int k = 1; k < NF; k++) fn[k] += vn[k] - ts * (un[k] - uo[k]);
+      }
+    }
     double *out = A.fv + ((size_t)ge * 6 + f) * FB + j;
 #pragma unroll
     for (int k = 0; k < NF; k++) out[k * NN] = fn[k];

@@ -34,9 +34,11 @@ ELEM_CASES = [
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("name", ELEM_CASES)
-def test_blocked_element_kernels_vs_reference(tmp_path, hb, meshgen, name):
+def test_blocked_element_kernels_vs_reference(tmp_path, hb, meshgen, name, monkeypatch):
     if not util.have_reference():
         pytest.skip("oracle/_ref not built")
+    # affine hexahedra with boundary faces take the sum-factorised kernels by default (tests/test_fused_parity.py); here the blocked ones are meant
+    monkeypatch.setenv("HF_FUSED_BDY", "0")
     inp = make_case(tmp_path, meshgen, name)
     n_steps = 3
     ref = util.run_reference(inp, n_steps, stagewise=False)

@@ -221,3 +221,92 @@ def test_two_phase_upload_equals_synchronous_upload(tmp_path, hb, meshgen):
         del keep, keep2
     assert np.array_equal(a, b)
     assert np.array_equal(a, c)
+
+
+# ---- boundary faces inside the sum-factorised kernels (generation 9; hf_fused9.cuh, k_face9<..., BDY>) ---------------------------------------
+# Affine hexahedra with walls / inlets / outlets / far fields: the face kernel evaluates the ghost state (bdy_inters::set_boundary_conditions,
+# reference src/bdy_inters.cpp:340-1019), the boundary's LDG common solution (u_c = u_r), Riemann flux and viscous boundary flux
+# (:213-338, :1024-1090, set_boundary_gradients :1138-1189) for the element that owns the face.  Every boundary kind of the Navier-Stokes
+# equations, each order P = 1..4, all three Riemann solvers, both signs of beta.
+_FREE = dict(ic_form=1, Mach_c_ic=0.3, nx_c_ic=1., ny_c_ic=0., nz_c_ic=0.05, T_c_ic=300., rho_c_ic=1.17, Mach_free_stream=0.3, rho_free_stream=1.17,
+             T_free_stream=300., L_free_stream=1.)
+_CHANNEL_BCS = {"x-": "In", "x+": "Out", "y-": "Cyclic", "y+": "Cyclic", "z-": "Wall", "z+": "Top"}
+BDY_CASES = {
+    # adiabatic wall + characteristic outflow, RoeM, RK33 (the blocked-kernel case of tests/test_elem_parity.py, now on the fused path)
+    "hex_p2_ns_wall_char_periodic": None,
+    # density / velocity inlet, pressure outlet, dual-consistent slip walls, Rusanov, RK45, Sutherland viscosity
+    "hex_p2_ns_subinsimp_slipdual": None,
+    # BASELINE config 3's order: Riemann-invariant far field (char) inlet, pressure outlet, isothermal wall below, moving adiabatic wall above, HLLC, RK34
+    "hex_p4_ns_char_isotherm_adiabat_hllc": ("hex", (3, 2, 3), dict(lengths=(1.5, 1., 1.5), bcs=_CHANNEL_BCS),
+                                             dict(_FREE, order=4, adv_type=2, riemann_solve_type=3, viscous=1, dt=2e-6, fix_vis=0, dx_cyclic=None, dy_cyclic=1.,
+                                                  dz_cyclic=None, bc_In_type="char", bc_In_p_static=100747., bc_In_mach=0.3, bc_In_T_static=300., bc_In_nx=1.,
+                                                  bc_In_ny=0., bc_In_nz=0., bc_Out_type="sub_out_simp", bc_Out_p_static=100000., bc_Wall_type="isotherm_wall",
+                                                  bc_Wall_T_static=310., bc_Top_type="adiabat_wall", bc_Top_u=20., calc_force=1, monitor_cp_freq=100000,
+                                                  area_ref=1.0)),
+    # supersonic inlet / outlet, slip wall (no viscous boundary flux) and isothermal wall, RoeM, negative beta with a penalty
+    "hex_p3_ns_supin_supout_slip_roem_betaneg": ("hex", (3, 2, 3), dict(lengths=(1.5, 1., 1.5), bcs=_CHANNEL_BCS),
+                                                 dict(order=3, adv_type=2, riemann_solve_type=2, viscous=1, ic_form=1, dt=2e-6, dx_cyclic=None, dy_cyclic=1.,
+                                                      dz_cyclic=None, Mach_c_ic=1.8, nx_c_ic=1., ny_c_ic=0., nz_c_ic=0.02, T_c_ic=290., rho_c_ic=1.2,
+                                                      Mach_free_stream=1.8, rho_free_stream=1.2, T_free_stream=290., L_free_stream=1., ldg_beta=-0.5, ldg_tau=0.1,
+                                                      bc_In_type="sup_in", bc_In_p_static=101000., bc_In_mach=1.8, bc_In_T_static=290., bc_In_nx=1., bc_In_ny=0.,
+                                                      bc_In_nz=0., bc_Out_type="sup_out", bc_Wall_type="slip_wall", bc_Top_type="isotherm_wall", bc_Top_T_static=300.,
+                                                      calc_force=1, monitor_cp_freq=100000, area_ref=1.0)),
+    # total-pressure inlet (sub_in_char), characteristic outlet, walls on four sides (no periodic direction: corner elements with three
+    # boundary faces), P = 1, forward Euler
+    "hex_p1_ns_subinchar_suboutchar_walls": ("hex", (3, 3, 2), dict(lengths=(1.5, 1., 1.), bcs={"x-": "In", "x+": "Out", "y-": "Wall", "y+": "Wall", "z-": "Wall",
+                                                                                                 "z+": "Top"}),
+                                             dict(_FREE, order=1, adv_type=0, riemann_solve_type=3, viscous=1, dt=1e-5, dx_cyclic=None, dy_cyclic=None, dz_cyclic=None,
+                                                  bc_Cyclic_type=None, bc_In_type="sub_in_char", bc_In_p_total=107200., bc_In_T_total=305.4, bc_In_nx=1., bc_In_ny=0.,
+                                                  bc_In_nz=0., bc_Out_type="sub_out_char", bc_Out_p_static=100500., bc_Wall_type="adiabat_wall",
+                                                  bc_Top_type="slip_wall_dual", calc_force=1, monitor_cp_freq=100000, area_ref=1.0)),
+}
+for _k, _v in BDY_CASES.items():
+    if _v is not None:
+        CASES[_k] = _v
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", list(BDY_CASES))
+def test_fused_kernels_with_boundary_faces_vs_reference(tmp_path, hb, meshgen, name):
+    if not util.have_reference():
+        pytest.skip("oracle/_ref not built")
+    inp = make_case(tmp_path, meshgen, name)
+    n_steps = 3
+    ref = util.run_reference(inp, n_steps, stagewise=False)
+    with hb.Run(inp) as run:
+        assert run.fused_status() == "available", run.fused_status()
+        assert run.fused_variant().startswith("generation 9"), run.fused_variant()
+        n0 = run.launch_count()
+        run.run(n_steps, fused=True)
+        launches = run.launch_count() - n0
+        res = run.norm_residual()
+        u = run.download("hex", "disu_upts")
+        div = run.download("hex", "div_tconf_upts")
+    # two kernels per RK stage (+ the face values of the initial field + the residual norm), no interface kernels
+    n_rk = {0: 1, 1: 3, 2: 4, 3: 5, 4: 14}[CASES[name][3]["adv_type"]]
+    assert launches <= 3 * n_rk * n_steps + 10, launches
+    check("residual norm", res, ref["history.norm_residual"][:, -1], TOL)
+    check("final disu_upts", u, ref["final.hex.disu_upts"], TOL)
+    check("final div_tconf_upts", div, ref["final.hex.div_tconf_upts"], 5e-11)
+
+
+@pytest.mark.gpu
+def test_fused_boundary_faces_residual_vs_staged(tmp_path, hb, meshgen):
+    """CalcResidual alone on a mesh with boundary faces through both kernel families on the same state; and HF_FUSED_BDY=0 keeps such a
+    mesh on the blocked element kernels."""
+    inp = make_case(tmp_path, meshgen, "hex_p4_ns_char_isotherm_adiabat_hllc")
+    with hb.Run(inp) as run:
+        assert run.fused_status() == "available", run.fused_status()
+        run.set_mode(False)
+        run.calc_residual(0)
+        staged = run.download("hex", "div_tconf_upts")
+        run.set_mode(True)
+        run.calc_residual(0)
+        fused = run.download("hex", "div_tconf_upts")
+    check("div_tconf_upts fused vs staged", fused, staged, 5e-11)
+    os.environ["HF_FUSED_BDY"] = "0"
+    try:
+        with hb.Run(inp) as run:
+            assert run.fused_status() != "available" and run.elem_status() == "available", (run.fused_status(), run.elem_status())
+    finally:
+        del os.environ["HF_FUSED_BDY"]
