@@ -147,6 +147,8 @@ struct fused_args
   unsigned long long own_xor; // generation 7: bmask ^ own_xor = the flux points this element owns (LDG weight 1)
   const hf_bc *bct;       // generation 9 with boundary faces: the boundary table (finfo >> 8 of a boundary face indexes it)
   double R_ref;
+  const unsigned char *bskip; // [ele] 1 = the element has a boundary face (k_face9's plain launch leaves it to the boundary launch)
+  int bdy_mode;           // k_face9 variant: 0 no boundary faces, 1 the elements with a boundary face (elist), 2 all others
 };
 
 __device__ __forceinline__ void cp_async8(void *smem, const void *gmem)
@@ -351,6 +353,9 @@ struct hf_fused_state
   std::string why; // reason the fused path is not available
   int order = 0, n_eles = 0, n_mpi = 0;
   int n_bdy = 0; // boundary faces (generation 9 only): virtual neighbour blocks behind the receive blocks of fu
+  int n_bele = 0; // elements with a boundary face
+  int *belist = nullptr;          // [n_bele] those elements (device order, ascending)
+  unsigned char *bskip = nullptr; // [ele] 1 = has a boundary face
   double *fu[2] = {nullptr, nullptr};
   int cur = 0;
   double *fv = nullptr;
@@ -721,6 +726,11 @@ int hf_fused_prepare(hf_ctx *c)
     bmask[(size_t)el * 6 + fl] = full_mask ^ own_xor0;
   }
   Z->n_bdy = n_bdy;
+  std::vector<unsigned char> bskip(ne, 0);
+  std::vector<int> belist;
+  for (int i = 0; i < n_bdy; i++) bskip[Bd.h_ele_l[i]] = 1;
+  for (int i = 0; i < ne; i++) if (bskip[i]) belist.push_back(i);
+  Z->n_bele = (int)belist.size();
   for (size_t q = 0; q < nbr.size(); q++)
     if (nbr[q] < 0) return no("an element face has no neighbour");
   // One-sided LDG (generation 7): |beta| = 0.5 makes the LDG weights exactly 1 and 0, so every flux-point pair has one
@@ -779,6 +789,11 @@ int hf_fused_prepare(hf_ctx *c)
   {
     if (hf_alloc_zero(c, &Z->gn, (size_t)ne * 6 * FB)) return 1;
     if (build_classes9(c, Z, bmask, finfo)) return 1;
+  }
+  if (n_bdy)
+  {
+    if (hf_alloc_copy(c, &Z->belist, belist.data(), belist.size())) return 1;
+    if (hf_alloc_copy(c, &Z->bskip, bskip.data(), bskip.size())) return 1;
   }
   if (hf_alloc_copy(c, &Z->em, em.data(), em.size())) return 1;
   if (hf_alloc_copy(c, &Z->nbr, nbr.data(), nbr.size())) return 1;
@@ -907,27 +922,36 @@ int launch9(hf_ctx *c, fused_args &A, int what, int lo, int hi)
     HF_CUDA(cudaFuncSetAttribute(k_resid9<N, NT_R, MINB_R, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_r));
     HF_CUDA(cudaFuncSetAttribute(k_resid9<N, NT_R, MINB_R, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_r));
     HF_CUDA(cudaFuncSetAttribute(k_resid9<N, NT_R, MINB_R, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_r));
-    HF_CUDA(cudaFuncSetAttribute(k_face9<N, NT_F, MINB_F, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_f));
-    HF_CUDA(cudaFuncSetAttribute(k_face9<N, NT_F, MINB_F, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_f));
-    HF_CUDA(cudaFuncSetAttribute(k_face9<N, NT_F, MINB_F, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_f));
-    HF_CUDA(cudaFuncSetAttribute(k_face9<N, NT_F, MINB_F, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_f));
+    HF_CUDA(cudaFuncSetAttribute(k_face9<N, NT_F, MINB_F, false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_f));
+    HF_CUDA(cudaFuncSetAttribute(k_face9<N, NT_F, MINB_F, true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_f));
+    HF_CUDA(cudaFuncSetAttribute(k_face9<N, NT_F, MINB_F, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_f));
+    HF_CUDA(cudaFuncSetAttribute(k_face9<N, NT_F, MINB_F, true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_f));
+    HF_CUDA(cudaFuncSetAttribute(k_face9<N, NT_F, MINB_F, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_f));
+    HF_CUDA(cudaFuncSetAttribute(k_face9<N, NT_F, MINB_F, true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_f));
     HF_CUDA(cudaFuncSetAttribute(k_resid9<N, NT_R, MINB_R, 0>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     HF_CUDA(cudaFuncSetAttribute(k_resid9<N, NT_R, MINB_R, 1>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-    HF_CUDA(cudaFuncSetAttribute(k_face9<N, NT_F, MINB_F, false, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-    HF_CUDA(cudaFuncSetAttribute(k_face9<N, NT_F, MINB_F, true, false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-    HF_CUDA(cudaFuncSetAttribute(k_face9<N, NT_F, MINB_F, false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-    HF_CUDA(cudaFuncSetAttribute(k_face9<N, NT_F, MINB_F, true, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    HF_CUDA(cudaFuncSetAttribute(k_face9<N, NT_F, MINB_F, false, 0>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    HF_CUDA(cudaFuncSetAttribute(k_face9<N, NT_F, MINB_F, true, 0>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    HF_CUDA(cudaFuncSetAttribute(k_face9<N, NT_F, MINB_F, false, 1>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    HF_CUDA(cudaFuncSetAttribute(k_face9<N, NT_F, MINB_F, true, 1>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    HF_CUDA(cudaFuncSetAttribute(k_face9<N, NT_F, MINB_F, false, 2>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    HF_CUDA(cudaFuncSetAttribute(k_face9<N, NT_F, MINB_F, true, 2>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     attr_done = true;
   }
   if (what == 5)
   {
-    if (A.bct) // the mesh has boundary faces
+    if (A.bdy_mode == 1) // the elements with a boundary face
     {
-      if (A.nlf) k_face9<N, NT_F, MINB_F, true, true><<<grid, NT_F, smem_f, c->stream>>>(A);
-      else k_face9<N, NT_F, MINB_F, false, true><<<grid, NT_F, smem_f, c->stream>>>(A);
+      if (A.nlf) k_face9<N, NT_F, MINB_F, true, 1><<<grid, NT_F, smem_f, c->stream>>>(A);
+      else k_face9<N, NT_F, MINB_F, false, 1><<<grid, NT_F, smem_f, c->stream>>>(A);
     }
-    else if (A.nlf) k_face9<N, NT_F, MINB_F, true, false><<<grid, NT_F, smem_f, c->stream>>>(A);
-    else k_face9<N, NT_F, MINB_F, false, false><<<grid, NT_F, smem_f, c->stream>>>(A);
+    else if (A.bdy_mode == 2) // all others of a mesh with boundary faces
+    {
+      if (A.nlf) k_face9<N, NT_F, MINB_F, true, 2><<<grid, NT_F, smem_f, c->stream>>>(A);
+      else k_face9<N, NT_F, MINB_F, false, 2><<<grid, NT_F, smem_f, c->stream>>>(A);
+    }
+    else if (A.nlf) k_face9<N, NT_F, MINB_F, true, 0><<<grid, NT_F, smem_f, c->stream>>>(A);
+    else k_face9<N, NT_F, MINB_F, false, 0><<<grid, NT_F, smem_f, c->stream>>>(A);
   }
   else if (what == 7)
     k_resid9<N, NT_R, MINB_R, 2><<<grid, NT_R, smem_r, c->stream>>>(A);
@@ -1054,6 +1078,8 @@ void base_args(hf_ctx *c, hf_fused_state *Z, fused_args &A)
   A.own_xor = Z->own_xor;
   A.bct = Z->n_bdy ? c->bc_table : nullptr;
   A.R_ref = c->prm.R_ref;
+  A.bskip = Z->bskip;
+  A.bdy_mode = Z->n_bdy ? 2 : 0;
 }
 
 // exchange the partition-face blocks of arr (blk_doubles each): pack -> ncclSend/Recv into the tail of arr, on the
@@ -1143,6 +1169,16 @@ int hf_fused_stage(hf_ctx *c, int rk_stage, double time, int keep_residual, int 
   // wait, inside the kernel, for the completion counter of the exchange they read from (bumped on the communication stream); by the time
   // the grid reaches them the exchange posted a kernel earlier has long landed.  Saves the drain / ramp of two extra launches per stage.
   // Small interiors keep the two-range launches: a grid that starts with waiting CTAs could keep the NCCL kernel off the SMs.
+  // meshes with boundary faces: the few elements that have one run the face kernel's ghost-state variant in a launch of their own (behind the
+  // main launch, which skips them); partition-adjacent ones among them check the exchange counter like everybody else
+  auto face_boundary_elements = [&]() -> int {
+    if (!Z->gen9 || Z->n_bele == 0) return 0;
+    fused_args B = A;
+    B.elist = Z->belist;
+    B.bdy_mode = 1;
+    if (B.wait_flag) B.wait_from = 0;
+    return launch(c, Z, B, 5, 0, Z->n_bele);
+  };
   static const bool no_single = getenv("HF_SPLIT_LAUNCH") != nullptr;
   const bool single = Z->gen9 && Z->n_mpi > 0 && !no_overlap && !no_single && ni >= 4096 && c->d_xflag != nullptr;
   if (single)
@@ -1151,6 +1187,7 @@ int hf_fused_stage(hf_ctx *c, int rk_stage, double time, int keep_residual, int 
     A.wait_from = ni;
     A.wait_value = c->x_posted[0];
     if (launch(c, Z, A, kg, 0, n)) return 1;
+    if (face_boundary_elements()) return 1;
     hf_tl_mark(c, 3, false);
     c->tl_xmark = 7;
     if (exchange_post(c, Z, Z->fv, Z->out_g, Z->fv_blk, 1)) return 1;
@@ -1169,6 +1206,7 @@ int hf_fused_stage(hf_ctx *c, int rk_stage, double time, int keep_residual, int 
     if (exchange_wait(c)) return 1;
     hf_tl_mark(c, 2, false);
     if (launch(c, Z, A, kg, ni, n)) return 1;
+    if (face_boundary_elements()) return 1;
     hf_tl_mark(c, 3, false);
     c->tl_xmark = 7;
     if (exchange_post(c, Z, Z->fv, Z->out_g, Z->fv_blk, 1)) return 1;

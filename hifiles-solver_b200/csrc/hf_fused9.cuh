@@ -658,8 +658,10 @@ __host__ inline void make_class_lists9(const unsigned long long *own, unsigned *
 //   inviscid             Riemann(u_l, u_r of the inviscid boundary state); slip_wall_dual: F(u_l).n
 //   viscous              F_v(u_r, boundary gradient of the own corrected gradient).n - tau (u_r - u_l)  (ldg_flux, flux_spec 1); none on a slip wall
 // A kernel variant of its own (the ghost-state code costs registers): meshes without boundary faces keep the other one.
-template <int N, int NT, int MINB, bool ROEM, bool BDY>
-__global__ void __launch_bounds__(NT, BDY ? (MINB > 1 ? MINB - 1 : 1) : MINB) k_face9(const __grid_constant__ fused_args A)
+// Two launches on such a mesh: BDYM = 2, the plain code over all elements, those with a boundary face leaving at once; BDYM = 1, the variant
+// with the ghost-state code over the list of elements with a boundary face (a few per cent of a mesh).  BDYM = 0: no boundary faces.
+template <int N, int NT, int MINB, bool ROEM, int BDYM>
+__global__ void __launch_bounds__(NT, BDYM == 1 ? (MINB > 1 ? MINB - 1 : 1) : MINB) k_face9(const __grid_constant__ fused_args A)
 {
   typedef geo9<N> G;
   typedef smem9f<N> SM;
@@ -667,8 +669,13 @@ __global__ void __launch_bounds__(NT, BDY ? (MINB > 1 ? MINB - 1 : 1) : MINB) k_
   SM &S = *reinterpret_cast<SM *>(smem_raw);
   constexpr int P = G::P, NN = G::NN, FB = G::FB, NW = NT / 32;
   static_assert(NF * N <= 32, "one lane per (field, edge point)");
+  constexpr bool BDY = BDYM == 1;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int ge = elem_id(A, A.lo + blockIdx.x);
+  if constexpr (BDYM == 2)
+  {
+    if (A.bskip[ge]) return; // an element with a boundary face: the other launch's
+  }
   wait_exchange9(A);
   // the first warp posts the bulk copies: one thread per face with owned flux points fetches the own face values, the own normal
   // derivative and the neighbour's face values

@@ -37,8 +37,16 @@ def main():
     if kind != "hex":
         return general(hb, mg, dist, rank, world, work, kind, n, order, steps, mode)
     if rank == 0:
-        mg.hex_box(mesh, n)
-        mg.write_input(inp, "tgv.neu", order=order, adv_type=2, dt=1e-5, riemann_solve_type=3, viscous=1)
+        if os.environ.get("HF_CHECK_WALLS"):
+            # channel-like mesh: periodic in x, y; isothermal wall and characteristic far field in z (boundary faces inside the fused kernels)
+            mg.hex_box(mesh, n, lengths=(1., 1., 2.), bcs={"x-": "Cyclic", "x+": "Cyclic", "y-": "Cyclic", "y+": "Cyclic", "z-": "Wall", "z+": "Far"})
+            mg.write_input(inp, "tgv.neu", order=order, adv_type=2, dt=1e-5, riemann_solve_type=3, viscous=1, ic_form=1, Mach_c_ic=0.2, nx_c_ic=1., ny_c_ic=0.,
+                           nz_c_ic=0.05, T_c_ic=300., rho_c_ic=1.17, Mach_free_stream=0.2, rho_free_stream=1.17, T_free_stream=300., L_free_stream=1.,
+                           dx_cyclic=1., dy_cyclic=1., dz_cyclic=None, bc_Wall_type="isotherm_wall", bc_Wall_T_static=310., bc_Far_type="sub_out_char",
+                           bc_Far_p_static=100500.)
+        else:
+            mg.hex_box(mesh, n)
+            mg.write_input(inp, "tgv.neu", order=order, adv_type=2, dt=1e-5, riemann_solve_type=3, viscous=1)
     dist.barrier()
     part = None if os.environ.get("HF_CHECK_PART") == "metis" else mg.block_partition(n, mg.blocks_for(world))  # None: METIS k-way in the host mirror
     idt = torch.zeros(128, dtype=torch.uint8, device="cuda")

@@ -127,6 +127,18 @@ def test_vortex_error_file_matches_reference_binary(tmp_path, hb, meshgen, kind)
 def test_surface_forces_match_reference_binary(tmp_path, hb, meshgen, name):
     """calc_force: output::CalcForces / eles::compute_wall_forces (pressure and viscous traction integrated over the wall
     faces' cubature points) -- force, CL, CD columns of history.plt and the cp / cf file against the reference binary."""
+    surface_forces_case(tmp_path, meshgen, name, 0, 1e-10, 1e-9)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["hex_p2_ns_wall_char_periodic", "quad_p2_ns_walls_char_out"])
+def test_surface_forces_on_the_fast_paths(tmp_path, hb, meshgen, name):
+    """The same through the fast kernels: the sum-factorised hexahedron kernels with boundary faces (generation 9) and the blocked element
+    kernels keep grad_disu_upts of the monitored steps' last residual evaluation for the wall traction."""
+    surface_forces_case(tmp_path, meshgen, name, 1, 1e-9, 1e-8)
+
+
+def surface_forces_case(tmp_path, meshgen, name, device_fused, tol_force, tol_cp):
     if not (os.path.exists(REF) and os.path.exists(OURS)):
         pytest.skip("driver binaries not built")
     from test_staged_parity import CASES, make_mesh
@@ -136,7 +148,7 @@ def test_surface_forces_match_reference_binary(tmp_path, hb, meshgen, name):
             dict(base[3], dx_cyclic=None, dy_cyclic=2., dz_cyclic=None)
     else:
         kind, n, mkw, opts = CASES[name]
-    opts = dict(opts, calc_force=1, monitor_cp_freq=2, area_ref=1.5, n_steps=2, monitor_res_freq=1, device_fused=0)
+    opts = dict(opts, calc_force=1, monitor_cp_freq=2, area_ref=1.5, n_steps=2, monitor_res_freq=1, device_fused=device_fused)
     nd = 2 if kind in ("quad", "tri", "mixed") else 3
     nf = nd + 2
     out = {}
@@ -155,7 +167,7 @@ def test_surface_forces_match_reference_binary(tmp_path, hb, meshgen, name):
     assert ha.shape == hb_.shape == (2, nf + nd + 2)
     fa, fb = ha[:, nf:], hb_[:, nf:]
     assert np.abs(fa).max() > 0
-    assert np.abs(fb - fa).max() <= 1e-10 * np.abs(fa).max(), "forces / coefficients: %s vs %s" % (fb, fa)
+    assert np.abs(fb - fa).max() <= tol_force * np.abs(fa).max(), "forces / coefficients: %s vs %s" % (fb, fa)
     assert len(ca) == len(cb) and len(ca) > 3
     for la, lb in zip(ca, cb):
         assert len(la) == len(lb)
@@ -163,7 +175,7 @@ def test_surface_forces_match_reference_binary(tmp_path, hb, meshgen, name):
             assert la == lb
         else:
             va, vb = np.array([float(x) for x in la]), np.array([float(x) for x in lb])
-            assert np.abs(va - vb).max() <= 1e-9 * max(1.0, np.abs(va).max())
+            assert np.abs(va - vb).max() <= tol_cp * max(1.0, np.abs(va).max())
 
 
 @pytest.mark.gpu

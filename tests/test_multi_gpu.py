@@ -43,6 +43,20 @@ def test_two_ranks_generation9_match_single_domain_and_reference(part):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("part", ["bricks", "metis"])
+def test_two_ranks_fused_kernels_with_boundary_faces(part):
+    """partition faces AND boundary faces (isothermal wall, characteristic far field) in the generation-9 kernels: the boundary faces' virtual
+    neighbour blocks sit behind the halo receive blocks"""
+    if n_gpus() < 2:
+        pytest.skip("needs 2 GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29543", os.path.join(ROOT, "tests", "multi_gpu_check.py"), "4", "3", "2", "fused"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=dict(os.environ, HF_CHECK_PART=part, HF_CHECK_WALLS="1"))
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "OK" in r.stdout and "generation 9" in r.stdout
+
+
+@pytest.mark.gpu
 def test_two_ranks_single_launch_stage_with_in_kernel_wait():
     """enough interior elements (>= 4096 per rank) for the one-launch-per-kernel stage: partition-adjacent elements wait inside the
     kernel for the exchange counter (hf_fused.cu, hf_fused9.cuh wait_exchange9)"""
