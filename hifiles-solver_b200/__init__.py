@@ -62,6 +62,7 @@ def lib():
     L.hifiles_calc_time_step.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
     L.hifiles_nccl_init.argtypes = [C.c_void_p, C.c_char_p]
     L.hifiles_write_vtu.argtypes = [C.c_void_p, C.c_int]
+    L.hifiles_write_restart.argtypes = [C.c_void_p, C.c_int]
     L.hf_dev_nccl_unique_id.argtypes = [C.c_char_p]
     L.hf_dev_eles_op.argtypes = [C.c_void_p, C.c_int, C.c_int]
     L.hf_dev_int_inters_op.argtypes = [C.c_void_p, C.c_int, C.c_int]
@@ -251,6 +252,10 @@ class Run:
     def write_vtu(self, it):
         """output::write_vtu: Paraview file(s) of the current solution in the working directory"""
         self._ck(lib().hifiles_write_vtu(self._h, int(it)))
+
+    def write_restart(self, it):
+        """output::write_restart_ascii into the working directory (one file per rank in Rest_<iter>/ when partitioned)"""
+        self._ck(lib().hifiles_write_restart(self._h, int(it)))
 
     def elem_status(self):
         return lib().hf_dev_elem_status(self.ctx).decode()

@@ -986,6 +986,7 @@ int launch(hf_ctx *c, hf_fused_state *Z, fused_args &A, int what, int lo, int hi
       if (cfg9 == 1) return launch9<5, 128, 5, 128, 6>(c, A, what, lo, hi);
       if (cfg9 == 2) return launch9<5, 128, 6, 96, 6>(c, A, what, lo, hi);
       if (cfg9 == 3) return launch9<5, 128, 5, 96, 6>(c, A, what, lo, hi);
+      if (cfg9 == 4) return launch9<5, 128, 6, 128, 5>(c, A, what, lo, hi); // face kernel at 96 registers, five CTAs per SM
       return launch9<5, 128, 6, 128, 6>(c, A, what, lo, hi);
     }
     case 5: return launch9<6, 192, 2, 192, 2>(c, A, what, lo, hi);

@@ -9,75 +9,6 @@
 
 using namespace std;
 
-// ASCII restart file Rest_<iter>_p0000.dat: time, then per element type a header with the solution-point set and the
-// solution of every element under its global id, 15 significant digits (reference src/output.cpp:1753-1818,
-// src/eles.cpp:845-869, <type>::write_restart_info_ascii).  It is one of the reference's parity comparators.
-static void write_restart_ascii(struct solution *FlowSol, int in_file_num)
-{
-  char name[256];
-  if (FlowSol->nproc > 1) FatalError("restart files of partitioned runs are outside the scope of this build");
-  snprintf(name, sizeof(name), "Rest_%.09d_p%.04d.dat", in_file_num, 0);
-  cout << "Writing Restart file for step " << in_file_num << " ...." << flush;
-  ofstream f(name);
-  f.precision(15);
-  f << FlowSol->time << endl;
-  for (int t = 0; t < FlowSol->n_ele_types; t++)
-  {
-    eles *e = FlowSol->mesh_eles(t);
-    if (e->get_n_eles() == 0) continue;
-    e->cp_disu_upts_gpu_cpu();
-    const int type = e->get_ele_type();
-    static const char *title[5] = {"TRIS", "QUADS", "TETS", "PRIS", "HEXAS"};
-    static const char *count[5] = {"Number of solution points per triangular element", "Number of solution points per quadrilateral element",
-                                   "Number of solution points per element", "Number of solution points per prismatic element",
-                                   "Number of solution points per hexahedral element"};
-    f << title[type] << endl << "Order" << endl << e->order << endl << count[type] << endl << e->n_upts_per_ele << endl;
-    if (type == QUAD || type == HEX)
-    {
-      f << "Location of solution points in 1D" << endl;
-      for (int i = 0; i < e->order + 1; ++i) f << e->loc_1d_upts(i) << " ";
-      f << endl;
-    }
-    else if (type == PRISM)
-    {
-      eles_pris *p = static_cast<eles_pris *>(e);
-      f << "Number of solution points in triangle" << endl << p->n_upts_tri << endl;
-      f << "Location of solution points in 1D" << endl;
-      for (int i = 0; i < e->order + 1; ++i) f << p->loc_upts_pri_1d(i) << " ";
-      f << endl;
-      f << "Location of solution points in triangle" << endl;
-      for (int i = 0; i < p->n_upts_tri; i++)
-      {
-        for (int j = 0; j < 2; j++) f << p->loc_upts_pri_tri(j, i) << " ";
-        f << endl;
-      }
-    }
-    else
-    {
-      f << (type == TRI ? "Location of solution points in triangular elements" : "Location of solution points in tetrahedral elements") << endl;
-      for (int i = 0; i < e->n_upts_per_ele; i++)
-      {
-        for (int j = 0; j < e->n_dims; j++) f << e->loc_upts(j, i) << " ";
-        f << endl;
-      }
-    }
-    f << "n_eles" << endl << e->n_eles << endl << "ele2global_ele hf_array" << endl;
-    for (int i = 0; i < e->n_eles; i++) f << e->ele2global_ele(i) << " ";
-    f << endl << "data" << endl;
-    for (int i = 0; i < e->n_eles; i++)
-    {
-      f << e->ele2global_ele(i) << endl;
-      for (int j = 0; j < e->n_upts_per_ele; j++)
-      {
-        for (int k = 0; k < e->n_fields; k++) f << e->disu_upts(0)(j, i, k) << " ";
-        f << endl;
-      }
-    }
-    f << endl;
-  }
-  cout << "done" << endl;
-}
-
 int main(int argc, char *argv[])
 {
   if (argc < 2)

@@ -161,6 +161,13 @@ int hifiles_write_vtu(void *handle, int iter)
   return guard([&]() { write_plot(iter, &((run_handle *)handle)->FlowSol); });
 }
 
+/* output::write_restart_ascii of the current solution into the working directory: Rest_<iter>_p0000.dat, or one file per rank in the
+ * folder Rest_<iter>/ when the run is partitioned (reference src/output.cpp:1753-1818) */
+int hifiles_write_restart(void *handle, int iter)
+{
+  return guard([&]() { write_restart_ascii(&((run_handle *)handle)->FlowSol, iter); });
+}
+
 int hifiles_norm_residual(void *handle, double *out, int n)
 {
   return guard([&]() {

@@ -574,6 +574,8 @@ void AdvanceStage(int in_file_num, int in_rk_stage, struct solution *FlowSol, bo
 void partition_mesh_kway(const mesh &m, int n_dims, int nproc, std::vector<int> &part);
 /*! read ASCII restart files Rest_<iter>_p<file>.dat (reference src/solver.cpp:377-434) */
 void read_restart_ascii(int in_file_num, int in_n_files, struct solution *FlowSol);
+/*! write ASCII restart file(s): Rest_<iter>_p0000.dat, or Rest_<iter>/Rest_<iter>_p<rank>.dat of a partitioned run (reference src/output.cpp:1753-1818) */
+void write_restart_ascii(struct solution *FlowSol, int in_file_num);
 /*! output::CalcNormResidual (reference src/output.cpp:2166-2248): fills FlowSol->norm_residual */
 void CalcNormResidual(struct solution *FlowSol);
 int get_n_rk_steps(int adv_type);

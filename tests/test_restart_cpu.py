@@ -88,3 +88,39 @@ def test_solution_patch_matches_reference(tmp_path, hb, meshgen, kind, patch):
                 a = run.host_array(k.replace("disu_upts_ic", "disu_upts"))
                 assert np.array_equal(a, v), "%s: patched solution differs from the reference (max abs %.3e)" % (k, np.abs(a - v).max())
                 assert not np.array_equal(v, plain[k]), "the patch did not touch the solution: the case checks nothing"
+
+
+@pytest.mark.parametrize("kind,order", [("hex", 2), ("pritet", 1)])
+def test_partitioned_restart_files_are_read_by_the_reference(tmp_path, hb, meshgen, kind, order, monkeypatch):
+    """Writing side of a partitioned run (reference output::write_restart_ascii, src/output.cpp:1753-1818: one file per rank in
+    Rest_<iter>/): two ranks of the host mirror write their part of the initial solution, the UNMODIFIED reference reads the two
+    files back (restart_flag 1, n_restart_files 2) into its serial numbering; every value must come back as printed (15 digits)."""
+    if not util.have_reference():
+        pytest.skip("oracle/_ref not built")
+    extra = build_mesh(meshgen, kind, str(tmp_path / "m.neu"))
+    common = dict(adv_type=2, dt=1e-5, riemann_solve_type=0, viscous=1, monitor_res_freq=1, order=order, **extra)
+    inp0 = meshgen.write_input(str(tmp_path / "input_write"), "m.neu", n_steps=1, **common)
+    monkeypatch.chdir(tmp_path)
+    with hb.Run(inp0, host_only=True) as single:
+        n_cells = sum(single.host_array(t + ".ele2global_ele").size for t in single.ele_types())
+        ic = {t: (single.host_array(t + ".disu_upts").copy(), single.host_array(t + ".ele2global_ele").copy()) for t in single.ele_types()}
+    part = (np.arange(n_cells) % 2).astype(np.int32) if kind == "hex" else (np.arange(n_cells) // ((n_cells + 1) // 2)).astype(np.int32)
+    for rank in range(2):
+        with hb.Run(inp0, rank=rank, nproc=2, part=part, host_only=True) as run:
+            run.write_restart(7)
+    assert os.path.exists(tmp_path / "Rest_000000007" / "Rest_000000007_p0000.dat") and os.path.exists(tmp_path / "Rest_000000007" / "Rest_000000007_p0001.dat")
+    inp = meshgen.write_input(str(tmp_path / "input_read"), "m.neu", n_steps=1, restart_flag=1, restart_iter=7, n_restart_files=2, **common)
+    ref = util.run_reference(inp, 0, stagewise=False)
+    checked = 0
+    for t, (u, gid) in ic.items():
+        v = ref[t + ".disu_upts_ic"]
+        assert v.shape == u.shape
+        scale = np.abs(u).max()
+        assert scale > 0 and np.abs(v - u).max() <= 2e-15 * scale * 10, "%s: %.3e" % (t, np.abs(v - u).max() / scale)
+        checked += 1
+    assert checked >= 1
+    # and the host mirror reads its own partitioned files like the reference
+    with hb.Run(inp, host_only=True) as run:
+        for t, (u, gid) in ic.items():
+            a = run.host_array(t + ".disu_upts")
+            assert np.abs(a - u).max() <= 2e-14 * np.abs(u).max()
