@@ -750,7 +750,7 @@ int hf_fused_prepare(hf_ctx *c)
       if (T.c5[1 * N + m] != Z->c5s[0][m] || T.c5[0 * N + m] != Z->c5s[0][m] || T.c5[3 * N + m] != Z->c5s[1][m] || T.c5[5 * N + m] != Z->c5s[1][m])
         side_uniform = false;
     }
-    const bool want9 = getenv("HF_FUSED_GEN9") ? atoi(getenv("HF_FUSED_GEN9")) != 0 : (N == 5 || n_bdy > 0);
+    const bool want9 = getenv("HF_FUSED_GEN9") ? atoi(getenv("HF_FUSED_GEN9")) != 0 : (N == 5 || (n_bdy > 0 && N <= 5)); // with boundary faces: every order generation 9 is tested at (P = 1..4)
     Z->gen9 = Z->os && side_uniform && want9 && !getenv("HF_FUSED_GEN7");
   }
   if (n_bdy && !Z->gen9)
