@@ -1258,7 +1258,6 @@ int hf_dev_set_params(hf_ctx *c, const hf_params *p)
   P.gamma_over_pr = p->gamma / p->prandtl;
   if (p->shock_cap && p->shock_cap != 1) HF_FAIL("Shock capturing method not implemented.");
   if (p->LES && (p->SGS_model < 0 || p->SGS_model > 4)) HF_FAIL("SGS model not implemented");
-  if (p->LES && p->SGS_model == 0 && c->nproc > 1) HF_FAIL("the Smagorinsky model on several GPUs is not built yet (its wall distance needs the wall points of every rank)");
   if (p->equation == 0 && !(p->riemann_solve_type == 0 || p->riemann_solve_type == 2 || p->riemann_solve_type == 3))
     HF_FAIL("Riemann solver not implemented");
   if (p->viscous && p->vis_riemann_solve_type != 0) HF_FAIL("Viscous Riemann solver not implemented");
@@ -2360,6 +2359,27 @@ int hf_dev_time_average(hf_ctx *c, int ele_type, int n_average_fields, const int
   k_time_average<<<hf_blocks(n_pts, 256), 256, 0, c->stream>>>(n_pts, e.n_upts, e.n_dims, e.disu_upts[0], e.disu_average_upts,
                                                              c->prm.dt_type == 2 ? e.dt_local : nullptr, c->prm.dt, time, spinup_time, K);
   HF_LAUNCH_CHECK(c);
+  return 0;
+}
+
+int hf_dev_set_wall_distance(hf_ctx *c, int ele_type, const double *wall_distance, size_t n_doubles)
+{
+  if (ele_type < 0 || ele_type >= HF_N_ELE_TYPES) HF_FAIL("bad element type");
+  HF_CUDA(cudaSetDevice(c->device));
+  hf_eles_dev &e = c->eles[ele_type];
+  if (!e.present) HF_FAIL("element type not present on the device");
+  const size_t n = (size_t)e.n_upts * e.n_eles * e.n_dims;
+  if (n_doubles != n) HF_FAIL("hf_dev_set_wall_distance: size mismatch");
+  if (!e.wall_distance) HF_FAIL("hf_dev_set_wall_distance: the element type was uploaded without wall distances");
+  std::vector<double> tmp;
+  const double *src = wall_distance;
+  if (!e.pos.empty())
+  {
+    tmp = permute_eles(wall_distance, (size_t)e.n_upts, e.n_eles, (size_t)e.n_dims, e.pos, true);
+    src = tmp.data();
+  }
+  HF_CUDA(cudaMemcpyAsync(e.wall_distance, src, n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  HF_CUDA(cudaStreamSynchronize(c->stream));
   return 0;
 }
 

@@ -152,6 +152,7 @@ int hifiles_nccl_init(void *handle, const char *unique_id_128_bytes)
   return guard([&]() {
     solution *S = &((run_handle *)handle)->FlowSol;
     hf_check(hf_dev_nccl_init(S->ctx, unique_id_128_bytes));
+    FinishWallDistance(S); // Smagorinsky: the other ranks' wall points (reference src/geometry.cpp:768-892)
   });
 }
 

@@ -499,7 +499,6 @@ void GeoPreprocess(struct solution *FlowSol, mesh &mesh_data)
   // isothermal / adiabatic wall face, per face type, in mesh-face order
   if (run_input.LES && run_input.SGS_model == 0)
   {
-    if (FlowSol->nproc > 1) FatalError("the Smagorinsky model on several GPUs is not built yet (its wall distance needs the wall points of every rank)");
     vector<hf_array<double>> loc_noslip_bdy(3);
     for (int t = 0; t < 3; t++)
     {
@@ -517,6 +516,54 @@ void GeoPreprocess(struct solution *FlowSol, mesh &mesh_data)
         for (int j = 0; j < nfp; j++)
           for (int k = 0; k < FlowSol->n_dims; k++) loc_noslip_bdy[t](k, j, (int)w) = B.pos_fpts(j, walls[w], k);
     }
+    // several ranks: the distance to this rank's walls for now; the other ranks' wall points arrive with the communicator (FinishWallDistance)
+    if (FlowSol->nproc > 1)
+    {
+      FlowSol->loc_noslip_bdy_local = loc_noslip_bdy;
+      FlowSol->wall_distance_pending = true;
+    }
     for (int i = 0; i < FlowSol->n_ele_types; i++) FlowSol->mesh_eles(i)->calc_wall_distance(loc_noslip_bdy);
   }
+}
+
+// The wall points of every rank, rank by rank (reference src/geometry.cpp:768-880: MPI_Allgather of the counts, one MPI_Bcast per rank into a
+// global array): every rank places its block into a zeroed global array and the arrays are summed over the communicator (x + 0 + ... + 0 is
+// exact), in pieces of the reduction's staging buffer.  Then eles::calc_wall_distance again (src/geometry.cpp:884-892) and the device copy.
+void FinishWallDistance(struct solution *FlowSol)
+{
+  if (!FlowSol->wall_distance_pending) return;
+  if (!FlowSol->ctx) FatalError("the Smagorinsky wall distance of a partitioned run needs the device context's communicator");
+  vector<hf_array<double>> glob(3);
+  for (int t = 0; t < 3; t++)
+  {
+    hf_array<double> &mine = FlowSol->loc_noslip_bdy_local[t];
+    const int nfp = t == 0 ? run_input.order + 1 : (t == 1 ? (run_input.order + 2) * (run_input.order + 1) / 2 : (run_input.order + 1) * (run_input.order + 1));
+    const size_t per = (size_t)FlowSol->n_dims * nfp;
+    const size_t n_mine = mine.size() / per;
+    vector<double> cnt(FlowSol->nproc, 0.);
+    cnt[FlowSol->rank] = (double)n_mine;
+    hf_check(hf_dev_allreduce_sum(FlowSol->ctx, cnt.data(), FlowSol->nproc));
+    size_t kstart = 0, total = 0;
+    for (int p = 0; p < FlowSol->nproc; p++)
+    {
+      if (p == FlowSol->rank) kstart = total;
+      total += (size_t)llround(cnt[p]);
+    }
+    glob[t].setup(FlowSol->n_dims, nfp, (int)total);
+    if (total == 0) continue;
+    double *g = glob[t].get_ptr_cpu();
+    for (size_t q = 0; q < per * total; q++) g[q] = 0.;
+    if (n_mine) memcpy(g + per * kstart, mine.get_ptr_cpu(), per * n_mine * sizeof(double));
+    const size_t piece = 65536;
+    for (size_t off = 0; off < per * total; off += piece) hf_check(hf_dev_allreduce_sum(FlowSol->ctx, g + off, (int)min(piece, per * total - off)));
+  }
+  for (int i = 0; i < FlowSol->n_ele_types; i++)
+  {
+    eles *e = FlowSol->mesh_eles(i);
+    if (e->get_n_eles() == 0) continue;
+    e->calc_wall_distance(glob);
+    hf_check(hf_dev_set_wall_distance(FlowSol->ctx, e->get_ele_type(), e->wall_distance.get_ptr_cpu(), e->wall_distance.size()));
+  }
+  FlowSol->loc_noslip_bdy_local.clear();
+  FlowSol->wall_distance_pending = false;
 }

@@ -544,10 +544,16 @@ struct solution
   int no_device; // 1: host pre-processing only (CPU-side tests of setup logic); any hot-path call then fails loudly
   /*! optional partition vector (global cell -> rank); empty = block partition of the reference's initial read */
   std::vector<int> part;
+  /*! Smagorinsky on several ranks: this rank's no-slip wall flux points per face type, kept until the communicator arrives
+      (FinishWallDistance gathers the other ranks' and recomputes the wall distance; reference src/geometry.cpp:768-892) */
+  std::vector<hf_array<double>> loc_noslip_bdy_local;
+  bool wall_distance_pending = false;
 };
 
 void SetInput(struct solution *FlowSol);
 void GeoPreprocess(struct solution *FlowSol, mesh &mesh_data);
+/*! partitioned Smagorinsky run: wall points of every rank over the communicator, wall distance again, device arrays replaced */
+void FinishWallDistance(struct solution *FlowSol);
 void ReadMesh(struct solution *FlowSol, mesh &mesh_data);
 void InitSolution(struct solution *FlowSol);
 void CalcResidual(int in_file_num, int in_rk_stage, struct solution *FlowSol);

@@ -264,6 +264,10 @@ int hf_dev_set_keep_gradient(hf_ctx *ctx, int on);
  * The array (HF_DISU_AVERAGE_UPTS) is created zeroed by the first call. */
 int hf_dev_time_average(hf_ctx *ctx, int ele_type, int n_average_fields, const int *kinds, double time, double spinup_time);
 int hf_dev_set_volume_cubature(hf_ctx *ctx, int ele_type, int n_cubpts, const double *opp_volume_cubpts, const double *weights, const double *vol_detjac);
+/* Replaces the wall-distance vectors of an element type (hf_eles_desc.wall_distance: (upt,ele,dim), host element order) after the upload:
+ * a partitioned run knows the no-slip wall points of the other ranks only once the communicator exists (the reference gathers them with
+ * MPI_Allgather / MPI_Bcast during its geometry setup, src/geometry.cpp:768-880). */
+int hf_dev_set_wall_distance(hf_ctx *ctx, int ele_type, const double *wall_distance, size_t n_doubles);
 int hf_dev_integral_quantities(hf_ctx *ctx, int ele_type, int n_quantities, const int *kinds, double *out);
 /* sum of v[n] over the ranks of the context's communicator, in place on every rank (no-op on one rank) */
 int hf_dev_allreduce_sum(hf_ctx *ctx, double *v, int n);

@@ -119,14 +119,23 @@ def general(hb, mg, dist, rank, world, work, kind, n, order, steps, mode="staged
     two_d = kind in ("tri", "mixed", "quad")
     obj = [None]
     if rank == 0:
-        if two_d:
+        if two_d and os.environ.get("HF_CHECK_WALLS"):
+            # channel with ONE no-slip wall (below), cut into a lower and an upper slab: the upper rank has no wall point of its own, the
+            # Smagorinsky damping there needs the lower rank's (FinishWallDistance, reference src/geometry.cpp:768-892)
+            info = mg.mixed_box_2d(mesh, (n, n), kind=kind, lengths=(4., 2.), origin=(0., 0.), bcs={"x-": "In", "x+": "Out", "y-": "Wall", "y+": "Top"})
+            mg.write_input(inp, "m.neu", order=order, adv_type=3, riemann_solve_type=0, viscous=1, ic_form=1, dt=5e-5, fix_vis=0, Mach_c_ic=0.3, nx_c_ic=1., ny_c_ic=0.,
+                           nz_c_ic=0., T_c_ic=300., rho_c_ic=1.17, Mach_free_stream=0.3, rho_free_stream=1.17, T_free_stream=300., L_free_stream=1., dx_cyclic=None,
+                           dy_cyclic=None, dz_cyclic=None, bc_Cyclic_type=None, bc_In_type="char", bc_In_p_static=100747., bc_In_mach=0.3, bc_In_T_static=300.,
+                           bc_In_nx=1., bc_In_ny=0., bc_Out_type="sub_out_simp", bc_Out_p_static=100000., bc_Wall_type="isotherm_wall", bc_Wall_T_static=310.,
+                           bc_Top_type="slip_wall", LES=1, SGS_model=0, C_s=0.1, filter_ratio=2.0, calc_force=1, monitor_cp_freq=100000, area_ref=1.0)
+        elif two_d:
             info = mg.mixed_box_2d(mesh, n, kind=kind, lengths=(6.2831853071795862,) * 2, origin=(0., 0.))
             mg.write_input(inp, "m.neu", order=order, adv_type=2, dt=1e-5, riemann_solve_type=0, viscous=1, dz_cyclic=None)
         else:
             info = mg.mixed_box_3d(mesh, n, kind=kind)
             les = dict(LES=1, SGS_model=int(os.environ["HF_CHECK_LES"]), C_s=0.3, filter_ratio=2.0, filter_type=2) if os.environ.get("HF_CHECK_LES") else {}
             mg.write_input(inp, "m.neu", order=order, adv_type=2, dt=1e-5, riemann_solve_type=2, viscous=1, **les)
-        obj = [mg.slab_partition(info["centroids"], world, axis=1 if kind == "pritet" else 0)]
+        obj = [mg.slab_partition(info["centroids"], world, axis=1 if (kind == "pritet" or os.environ.get("HF_CHECK_WALLS")) else 0)]
     dist.broadcast_object_list(obj, src=0)
     part = obj[0]
     idt = torch.zeros(128, dtype=torch.uint8, device="cuda")

@@ -108,3 +108,17 @@ def test_two_ranks_match_single_domain_simplex_and_mixed(kind, n, mode):
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "OK" in r.stdout
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", ["staged", "fused"])
+def test_two_ranks_smagorinsky_wall_distance_across_ranks(mode):
+    """Smagorinsky near-wall damping on a partitioned mesh whose only no-slip wall lies on the other rank: the wall points of every rank
+    travel over the communicator once it exists (reference src/geometry.cpp:768-892 gathers them with MPI during the geometry setup)"""
+    if n_gpus() < 2:
+        pytest.skip("needs 2 GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29545", os.path.join(ROOT, "tests", "multi_gpu_check.py"), "6", "2", "2", mode, "mixed"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=dict(os.environ, HF_CHECK_WALLS="1"))
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "OK" in r.stdout
