@@ -738,8 +738,8 @@ int hf_fused_prepare(hf_ctx *c)
   // partition face must agree on it: checked when the communicator arrives (hf_fused_after_nccl).
   Z->os = visc && fabs(c->prm.ldg_beta) == 0.5 && !getenv("HF_FUSED_GEN6");
   Z->own_xor = c->prm.ldg_beta > 0. ? (NN == 64 ? ~0ull : ((1ull << NN) - 1ull)) : 0ull;
-  // generation 9 (hf_fused9.cuh): the default at P = 4 (the shape it is tuned for; HF_FUSED_GEN9=1 turns it on at any order,
-  // HF_FUSED_GEN7=1 keeps generation 7).  Its tangential pass takes the correction-function derivative per side of the line, not per
+  // generation 9 (hf_fused9.cuh): the default at P = 2, 3, 4 (measured faster than generation 7 there; HF_FUSED_GEN9=1 turns it on at any
+  // order, HF_FUSED_GEN7=1 keeps generation 7).  Its tangential pass takes the correction-function derivative per side of the line, not per
   // face: the three directions of a hexahedron share one 1-D function, verified here on the reference's numbers.
   {
     bool side_uniform = visc;
@@ -750,7 +750,7 @@ int hf_fused_prepare(hf_ctx *c)
       if (T.c5[1 * N + m] != Z->c5s[0][m] || T.c5[0 * N + m] != Z->c5s[0][m] || T.c5[3 * N + m] != Z->c5s[1][m] || T.c5[5 * N + m] != Z->c5s[1][m])
         side_uniform = false;
     }
-    const bool want9 = getenv("HF_FUSED_GEN9") ? atoi(getenv("HF_FUSED_GEN9")) != 0 : (N == 5 || (n_bdy > 0 && N <= 5)); // with boundary faces: every order generation 9 is tested at (P = 1..4)
+    const bool want9 = getenv("HF_FUSED_GEN9") ? atoi(getenv("HF_FUSED_GEN9")) != 0 : (N == 5 || N == 4 || N == 3 || (n_bdy > 0 && N <= 5)); // with boundary faces: every order generation 9 is tested at (P = 1..4)
     Z->gen9 = Z->os && side_uniform && want9 && !getenv("HF_FUSED_GEN7");
   }
   if (n_bdy && !Z->gen9)
@@ -977,8 +977,22 @@ int launch(hf_ctx *c, hf_fused_state *Z, fused_args &A, int what, int lo, int hi
     switch (Z->order)
     {
     case 1: return launch9<2, 32, 8, 32, 8>(c, A, what, lo, hi);
-    case 2: return launch9<3, 64, 8, 64, 8>(c, A, what, lo, hi);
-    case 3: return launch9<4, 96, 6, 96, 6>(c, A, what, lo, hi);
+    case 2:
+    {
+      // measured on B200 (48^3, periodic; GDOF-stage/s): eight CTAs per SM 13.6, twelve (80 registers) 16.5 -- generation 7: 15.3
+      static const int cfg9 = getenv("HF_FUSED_CFG9") ? atoi(getenv("HF_FUSED_CFG9")) : 0; // measurement aid
+      if (cfg9 == 1) return launch9<3, 64, 8, 64, 8>(c, A, what, lo, hi);
+      if (cfg9 == 2) return launch9<3, 64, 16, 64, 16>(c, A, what, lo, hi);
+      return launch9<3, 64, 12, 64, 12>(c, A, what, lo, hi);
+    }
+    case 3:
+    {
+      // six CTAs per SM 22.5, eight (80 registers) 26.0 -- generation 7: 23.6
+      static const int cfg9 = getenv("HF_FUSED_CFG9") ? atoi(getenv("HF_FUSED_CFG9")) : 0;
+      if (cfg9 == 1) return launch9<4, 96, 6, 96, 6>(c, A, what, lo, hi);
+      if (cfg9 == 2) return launch9<4, 96, 10, 96, 10>(c, A, what, lo, hi);
+      return launch9<4, 96, 8, 96, 8>(c, A, what, lo, hi);
+    }
     case 4:
     {
       // measurement aid: HF_FUSED_CFG9 bit 0 = five residual CTAs per SM (96 registers), bit 1 = 96-thread face kernel

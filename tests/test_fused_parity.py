@@ -40,7 +40,7 @@ def expected_variant(name):
         return "generation 6 (inviscid"
     if abs(o.get("ldg_beta", 0.5)) != 0.5:
         return "generation 6 (two-sided"
-    return "generation 9" if o["order"] == 4 else "generation 7"  # generation 9 is the default at P = 4 (hf_fused.cu)
+    return "generation 9" if o["order"] in (2, 3, 4) else "generation 7"  # generation 9 is the default at P = 2, 3, 4 (hf_fused.cu)
 
 
 @pytest.mark.gpu
@@ -118,8 +118,8 @@ def test_roem_on_rounding_level_normal_mach(tmp_path, hb, meshgen):
         run.set_mode(False)
         run.run(3, fused=False)
         check("staged", run.download("hex", "disu_upts"), ref["final.hex.disu_upts"], 1e-14)
-    for env in ({}, {"HF_FUSED_GEN6": "1"}, {"HF_FUSED_GEN9": "1"}):
-        for k in ("HF_FUSED_GEN6", "HF_FUSED_GEN9"):
+    for env in ({}, {"HF_FUSED_GEN6": "1"}, {"HF_FUSED_GEN7": "1"}, {"HF_FUSED_GEN9": "1"}):
+        for k in ("HF_FUSED_GEN6", "HF_FUSED_GEN7", "HF_FUSED_GEN9"):
             os.environ.pop(k, None)
         os.environ.update(env)
         try:
@@ -154,7 +154,7 @@ def test_warped_mesh_falls_back_to_staged(tmp_path, hb, meshgen):
 @pytest.mark.gpu
 @pytest.mark.parametrize("name", ["hex_p1_ns_sutherland_euler", "hex_p2_ns_hllc_rk34", "hex_p2_ns_hllc_betaneg_tau", "hex_p3_ns_rusanov_rk45", "hex_p4_ns_hllc_rk34"])
 def test_generation9_at_every_order_vs_reference_and_generation7(tmp_path, hb, meshgen, name, monkeypatch):
-    """k_face9 + k_resid9 (hf_fused9.cuh) are the default at P = 4 only; HF_FUSED_GEN9=1 turns them on at any order.  Three time
+    """k_face9 + k_resid9 (hf_fused9.cuh) are the default at P = 2, 3, 4; HF_FUSED_GEN9=1 turns them on at any order.  Three time
     steps against the unmodified reference, and against generation 7 (HF_FUSED_GEN7=1) which they must reproduce to rounding."""
     inp = make_case(tmp_path, meshgen, name)
     n_steps = 3
