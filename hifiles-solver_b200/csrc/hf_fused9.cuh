@@ -661,7 +661,8 @@ __host__ inline void make_class_lists9(const unsigned long long *own, unsigned *
 // Two launches on such a mesh: BDYM = 2, the plain code over all elements, those with a boundary face leaving at once; BDYM = 1, the variant
 // with the ghost-state code over the list of elements with a boundary face (a few per cent of a mesh).  BDYM = 0: no boundary faces.
 template <int N, int NT, int MINB, bool ROEM, int BDYM>
-__global__ void __launch_bounds__(NT, BDYM == 1 ? (MINB > 1 ? MINB - 1 : 1) : MINB) k_face9(const __grid_constant__ fused_args A)
+// (the boundary launch is a few per cent of the mesh: its variant gets registers rather than occupancy, at most five CTAs per SM)
+__global__ void __launch_bounds__(NT, BDYM == 1 ? (MINB > 6 ? 5 : (MINB > 1 ? MINB - 1 : 1)) : MINB) k_face9(const __grid_constant__ fused_args A)
 {
   typedef geo9<N> G;
   typedef smem9f<N> SM;
