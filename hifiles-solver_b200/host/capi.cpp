@@ -343,6 +343,31 @@ int hifiles_get_array(void *handle, const char *name, const void **ptr, int *dty
         if (arr == "ele_l") return set_i(I.ele_l);
         if (arr == "local_inter_l") return set_i(I.local_inter_l);
         if (arr == "boundary_id") return set_i(I.boundary_id);
+        if (arr == "bc_params")
+        {
+          // the boundary table as set_boundary_conditions reads it (run_input.bc_list after read_boundary_param's non-dimensionalisation), one
+          // column per boundary: rho, velocity[3], p_static, T_static, p_total, T_total, mach, nx, ny, nz, use_wm (oracle/ref_dump.cpp)
+          vector<double> &v = h->dbl_cache[full];
+          v.clear();
+          const int nb = (int)run_input.bc_list.size();
+          for (int i = 0; i < nb; i++)
+          {
+            bc &b = run_input.bc_list[i];
+            v.push_back(b.rho);
+            for (int k = 0; k < 3; k++) v.push_back(b.velocity.get_dim(0) > k ? b.velocity(k) : 0.);
+            v.push_back(b.p_static); v.push_back(b.T_static); v.push_back(b.p_total); v.push_back(b.T_total); v.push_back(b.mach);
+            v.push_back(b.nx); v.push_back(b.ny); v.push_back(b.nz); v.push_back((double)b.use_wm);
+          }
+          *ptr = v.data(); *dtype = 0; *ndim = 2; dims[0] = 13; dims[1] = nb;
+          return;
+        }
+        if (arr == "R_ref")
+        {
+          vector<double> &v = h->dbl_cache[full];
+          v.assign(1, run_input.viscous ? run_input.R_ref : run_input.R_gas);
+          *ptr = v.data(); *dtype = 0; *ndim = 1; dims[0] = 1;
+          return;
+        }
         if (arr == "idx_l")
         {
           vector<int> &v = h->int_cache[full];

@@ -10,7 +10,7 @@ Every function cites the reference routine it restates.  Arrays keep the referen
 (first index fastest): disu_upts(upt,ele,field), disu_fpts(fpt,ele,field), grad(pt,ele,field,dim),
 tdisf_upts(upt,ele,field,dim), JGinv(l,m,pt,ele), detjac(pt,ele), tdA(fpt,ele), norm_fpts(fpt,ele,dim), opp(row,col).
 Scope: Euler / Navier-Stokes on one element type with interior (incl. periodic) interfaces -- what BASELINE configs
-1 and 3 exercise.  Operator products use numpy's BLAS, so sums are not in the reference's order: agreement is to
+1 and 3 exercise -- and boundary interfaces (the eleven Navier-Stokes boundary kinds without ramp and wall model: SURVEY 8a rows a8, a14).  Operator products use numpy's BLAS, so sums are not in the reference's order: agreement is to
 rounding (1e-13), not bit-exact."""
 import numpy as np
 
@@ -163,6 +163,138 @@ def ldg_switched_beta(beta, n):
     return np.where(flip, -b, b)
 
 
+
+# ---- boundary interfaces (reference src/bdy_inters.cpp) -----------------------------------------------------------------------
+SUB_IN_SIMP, SUB_OUT_SIMP, SUB_IN_CHAR, SUB_OUT_CHAR, SUP_IN, SUP_OUT, SLIP_WALL, CYCLIC, ISOTHERM_WALL, ADIABAT_WALL, CHAR, SLIP_WALL_DUAL, AD_WALL = range(13)
+WALL_KINDS = (SLIP_WALL, ISOTHERM_WALL, ADIABAT_WALL, AD_WALL, SLIP_WALL_DUAL)
+
+
+class BC:
+    """one row of run_input.bc_list as set_boundary_conditions reads it (reference include/bc.h:50-58)"""
+    def __init__(self, flag, row):
+        self.flag = int(flag)
+        self.rho, self.velocity, self.p_static, self.T_static, self.p_total, self.T_total, self.mach = row[0], row[1:4], row[4], row[5], row[6], row[7], row[8]
+        self.n_free = row[9:12]
+        self.use_wm = int(row[12])
+
+
+def set_boundary_conditions(sol_spec, B, u_l, n, gamma, R_ref):
+    """bdy_inters::set_boundary_conditions, Navier-Stokes branch (reference src/bdy_inters.cpp:340-1008), for the points of ONE boundary:
+    u_l[q, field], n[q, dim] -> u_r[q, field].  sol_spec 0: inviscid ghost state, 1: viscous boundary solution.  No pressure ramp, no wall
+    model, no turbulent inlet (the inputs this restatement is pinned on use none)."""
+    nd = u_l.shape[-1] - 2
+    gm1 = gamma - 1.0
+    rho_l, e_l = u_l[:, 0], u_l[:, nd + 1]
+    v_l = u_l[:, 1:nd + 1] / rho_l[:, None]
+    p_l = gm1 * (e_l - 0.5 * rho_l * (v_l * v_l).sum(1))
+    vn_l = (v_l * n).sum(1)
+    vb = np.asarray(B.velocity[:nd], dtype=float)
+    f = B.flag
+    if f == SUB_IN_SIMP:                                  # :374-394 fixed density and velocity, pressure from inside
+        rho_r = np.full_like(rho_l, B.rho)
+        v_r = np.broadcast_to(vb, v_l.shape).copy()
+        e_r = p_l / gm1 + 0.5 * rho_r * (v_r * v_r).sum(1)
+    elif f == SUB_OUT_SIMP:                               # :399-466 fixed pressure; back flow and supersonic outflow branches
+        machn = np.abs(vn_l) / np.sqrt(gamma * p_l / rho_l)
+        back, sup = vn_l < 0, (vn_l >= 0) & (machn >= 1)
+        v_b = vn_l[:, None] * n
+        vsq_b = (v_b * v_b).sum(1)
+        T_b = B.T_total - 0.5 * vsq_b * gm1 / (R_ref * gamma)
+        p_b = B.p_static * (1.0 + 0.5 * gm1 * (vsq_b / (gamma * R_ref * T_b))) ** (-gamma / gm1)
+        rho_b = p_b / (R_ref * T_b)
+        e_b = p_b / gm1 + 0.5 * rho_b * vsq_b
+        e_s = B.p_static / gm1 + 0.5 * rho_l * (v_l * v_l).sum(1)
+        rho_r = np.where(back, rho_b, rho_l)
+        v_r = np.where(back[:, None], v_b, v_l)
+        e_r = np.where(back, e_b, np.where(sup, e_l, e_s))
+    elif f == SUB_IN_CHAR:                                # :471-588 total pressure / temperature, Riemann invariant from inside
+        nf = np.asarray(B.n_free[:nd], dtype=float)
+        c_l = np.sqrt(gamma * p_l / rho_l)
+        R_plus = vn_l + 2.0 * c_l / gm1
+        c_tot = gamma * R_ref * B.T_total
+        alpha = (n * nf).sum(1)
+        aa = 1.0 + 0.5 * gm1 * alpha * alpha
+        bb = -gm1 * alpha * R_plus
+        cc = 0.5 * gm1 * R_plus * R_plus - 2.0 * c_tot / gm1
+        dd = np.sqrt(np.maximum(bb * bb - 4.0 * aa * cc, 0.0))
+        V = np.maximum((-bb + dd) / (2.0 * aa), 0.0)
+        vsq = V * V
+        c_r = c_tot - 0.5 * gm1 * vsq
+        vsq = np.minimum(vsq / c_r, 1.0) * c_r
+        V = np.sqrt(vsq)
+        c_r = c_tot - 0.5 * gm1 * vsq
+        v_r = V[:, None] * nf
+        T_r = c_r / (gamma * R_ref)
+        p_r = B.p_total * (T_r / B.T_total) ** (gamma / gm1)
+        rho_r = p_r / (R_ref * T_r)
+        e_r = p_r / gm1 + 0.5 * rho_r * vsq
+    elif f == SUB_OUT_CHAR:                               # :593-640 fixed pressure, entropy and Riemann invariant from inside
+        c_l = np.sqrt(gamma * p_l / rho_l)
+        R_plus = vn_l + 2.0 * c_l / gm1
+        ent = p_l / rho_l ** gamma
+        p_r = B.p_static
+        rho_r = (p_r / ent) ** (1.0 / gamma)
+        c_r = np.sqrt(gamma * p_r / rho_r)
+        vn_r = R_plus - 2.0 * c_r / gm1
+        v_r = v_l + (vn_r - vn_l)[:, None] * n
+        e_r = p_r / gm1 + 0.5 * rho_r * (v_r * v_r).sum(1)
+    elif f == SUP_IN:                                     # :644-660
+        rho_r = np.full_like(rho_l, B.rho)
+        v_r = np.broadcast_to(vb, v_l.shape).copy()
+        e_r = B.p_static / gm1 + 0.5 * rho_r * (v_r * v_r).sum(1)
+    elif f == SUP_OUT:                                    # :664-670
+        rho_r, v_r, e_r = rho_l, v_l, e_l
+    elif f == SLIP_WALL:                                  # :674-701 mirrored (inviscid) / removed (viscous) normal velocity
+        rho_r = rho_l
+        v_r = v_l - (2.0 if sol_spec == 0 else 1.0) * vn_l[:, None] * n
+        e_r = p_l / gm1 + 0.5 * rho_r * (v_r * v_r).sum(1)
+    elif f in (ISOTHERM_WALL, ADIABAT_WALL):              # :705-863 (without wall model)
+        rho_r = rho_l
+        v_r = (2.0 * vb - v_l) if sol_spec == 0 else np.broadcast_to(vb, v_l.shape).copy()
+        vsq = (v_r * v_r).sum(1)
+        e_r = rho_r * (R_ref / gm1 * B.T_static) + 0.5 * rho_r * vsq if f == ISOTHERM_WALL else p_l / gm1 + 0.5 * rho_r * vsq
+    elif f == CHAR:                                       # :867-972 Riemann-invariant far field
+        vn_b = (vb * n).sum(1)
+        c_l = np.sqrt(gamma * p_l / rho_l)
+        c_b = np.sqrt(gamma * B.p_static / B.rho)
+        sup = np.abs(vn_l) / c_l >= 1
+        inflow = vn_l < 0
+        r_plus = np.where(inflow & sup, vn_b + 2.0 / gm1 * c_b, vn_l + 2.0 / gm1 * c_l)
+        r_minus = np.where(~inflow & sup, vn_l - 2.0 / gm1 * c_l, vn_b - 2.0 / gm1 * c_b)
+        c_star = 0.25 * gm1 * (r_plus - r_minus)
+        vn_star = 0.5 * (r_plus + r_minus)
+        one_over_s = np.where(inflow, B.rho ** gamma / B.p_static, rho_l ** gamma / p_l)
+        rho_r = (1.0 / gamma * (one_over_s * c_star * c_star)) ** (1.0 / gm1)
+        v_t = np.where(inflow[:, None], vb - vn_b[:, None] * n, v_l - vn_l[:, None] * n)
+        v_r = vn_star[:, None] * n + v_t
+        p_r = rho_r / gamma * c_star * c_star
+        e_r = p_r / gm1 + 0.5 * rho_r * (v_r * v_r).sum(1)
+    elif f == SLIP_WALL_DUAL:                             # :976-995
+        rho_r = rho_l
+        v_r = v_l - 2.0 * vn_l[:, None] * n
+        e_r = e_l
+    else:
+        raise ValueError("boundary kind %d is not restated" % f)
+    return np.concatenate([rho_r[:, None], rho_r[:, None] * v_r, e_r[:, None]], axis=1)
+
+
+def set_boundary_gradients(flag, u_r, g_l, n):
+    """bdy_inters::set_boundary_gradients (reference src/bdy_inters.cpp:1138-1189): g[q, field, dim]"""
+    nd = g_l.shape[-1]
+    if flag in (CHAR, SUP_IN, SUB_IN_SIMP, SUB_OUT_SIMP):
+        return np.zeros_like(g_l)
+    g = g_l.copy()
+    if flag == ADIABAT_WALL:  # remove the wall-normal gradient of the internal energy
+        rho = u_r[:, 0]
+        vsq = (u_r[:, 1:nd + 1] ** 2).sum(1)
+        inte = (u_r[:, nd + 1] - 0.5 * vsq / rho) / rho
+        grad_vel = (g[:, 1:nd + 1, :] - g[:, 0:1, :] * (u_r[:, 1:nd + 1] / rho[:, None])[:, :, None]) / rho[:, None, None]
+        s = inte[:, None] * g[:, 0, :] + (0.5 * vsq / (rho * rho))[:, None] * g[:, 0, :] + np.einsum("qi,qid->qd", u_r[:, 1:nd + 1], grad_vel)
+        grad_inte = g[:, nd + 1, :] - s
+        dn = (grad_inte * n).sum(1)
+        g[:, nd + 1, :] -= dn[:, None] * n
+    return g
+
 # ---- the per-stage sequence (reference src/solver.cpp:50-223) for one element type, interior interfaces -------------------
 class Oracle:
     def __init__(self, setup, prefix, inter_prefix, P):
@@ -188,6 +320,17 @@ class Oracle:
         self.idx_r = np.concatenate([np.asarray(setup[q + ".idx_r"]).ravel(order="F") for q in prefixes])
         self.u = [np.array(g("disu_upts_ic"), order="F"), np.zeros((self.nu, self.ne, self.nf), order="F")]
         self.div = np.zeros((self.nu, self.ne, self.nf), order="F")
+        # boundary interfaces (oracle/ref_dump.cpp dump_setup: 'bdy_<face type>.idx_l', '.boundary_id', '.bc_flags', '.bc_params', '.R_ref')
+        self.bdy = []  # (flat flux-point indices of one boundary's faces, BC)
+        for q in [x.replace("int_", "bdy_") for x in prefixes]:
+            if q + ".idx_l" not in setup:
+                continue
+            idx = np.asarray(setup[q + ".idx_l"])          # (fpt, inter)
+            bid = np.asarray(setup[q + ".boundary_id"]).ravel()
+            flags, rows = np.asarray(setup[q + ".bc_flags"]).ravel(), np.asarray(setup[q + ".bc_params"]).reshape((13, -1), order="F")
+            self.R_ref = float(np.asarray(setup[q + ".R_ref"]).ravel()[0])
+            for b in np.unique(bid):
+                self.bdy.append((idx[:, bid == b].ravel(order="F"), BC(flags[b], rows[:, b])))
 
     # operator product over all (ele, field) columns: the reference's column-major dgemm (src/funcs.cpp:49-124)
     @staticmethod
@@ -215,12 +358,22 @@ class Oracle:
         ntconf = np.zeros_like(uf)
         ntconf[self.idx_l] = fn * tdA[self.idx_l][:, None]
         ntconf[self.idx_r] = -fn * tdA[self.idx_r][:, None]
+        riemann = {0: rusanov_flux, 2: roeM_flux, 3: hllc_flux}[P.riemann_solve_type]
+        # bdy_inters::evaluate_boundaryConditions_invFlux (src/bdy_inters.cpp:213-338)
+        for bi, B in self.bdy:
+            ub_l, nb = uf[bi], nrm[bi]
+            ub_r = set_boundary_conditions(0, B, ub_l, nb, P.gamma, self.R_ref)
+            fnb = np.einsum("qkd,qd->qk", calc_invf(ub_l, P.gamma), nb) if B.flag == SLIP_WALL_DUAL else riemann(ub_l, ub_r, nb, P.gamma)
+            ntconf[bi] = fnb * tdA[bi][:, None]
         if P.viscous:
             beta = ldg_switched_beta(P.ldg_beta, n)[:, None]
             u_c = 0.5 * (u_l + u_r) - beta * (u_l - u_r)                          # inters::ldg_solution :615
             delta = np.zeros_like(uf)
             delta[self.idx_l] = u_c - u_l
             delta[self.idx_r] = u_c - u_r
+            for bi, B in self.bdy:                                                # boundary: u_c = u_r (ldg_solution, flux_spec 1)
+                ub_l, nb = uf[bi], nrm[bi]
+                delta[bi] = set_boundary_conditions(1 if B.flag in WALL_KINDS else 0, B, ub_l, nb, P.gamma, self.R_ref) - ub_l
             delta = delta.reshape((self.nfp, self.ne, self.nf), order="F")
             # eles::correct_gradient (:1890-2052)
             for d in range(nd):
@@ -242,6 +395,15 @@ class Oracle:
             fnv = np.einsum("qkd,qd->qk", f_c, n) - P.ldg_tau * (u_r - u_l)
             ntconf[self.idx_l] += fnv * tdA[self.idx_l][:, None]
             ntconf[self.idx_r] += -fnv * tdA[self.idx_r][:, None]
+            # bdy_inters::evaluate_boundaryConditions_viscFlux (src/bdy_inters.cpp:1024-1090): f_c = f_r (ldg_flux, flux_spec 1)
+            for bi, B in self.bdy:
+                if B.flag == SLIP_WALL:
+                    continue
+                ub_l, nb = uf[bi], nrm[bi]
+                ub_r = set_boundary_conditions(1, B, ub_l, nb, P.gamma, self.R_ref)
+                g_r = set_boundary_gradients(B.flag, ub_r, gf[bi], nb)
+                fnb = np.einsum("qkd,qd->qk", calc_visf(ub_r, g_r, P), nb) - P.ldg_tau * (ub_r - ub_l)
+                ntconf[bi] += fnb * tdA[bi][:, None]
         ntconf = ntconf.reshape((self.nfp, self.ne, self.nf), order="F")
         # calculate_corrected_divergence (:1738)
         self.div = div + self._apply(self.opp_3, ntconf - ntdisf)

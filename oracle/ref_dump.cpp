@@ -218,6 +218,20 @@ static void dump_setup(struct solution *S)
     vector<int> flags;
     for (int i = 0; i < run_input.bc_list.get_dim(0); i++) flags.push_back(run_input.bc_list(i).get_bc_flag());
     put_ivec(p + "bc_flags", flags);
+    // the boundary table as set_boundary_conditions reads it (run_input.bc_list, reference include/bc.h:50-58), one row per boundary:
+    // rho, velocity[3], p_static, T_static, p_total, T_total, mach, nx, ny, nz, use_wm
+    vector<double> bp;
+    const int nb = run_input.bc_list.get_dim(0);
+    for (int i = 0; i < nb; i++)
+    {
+      bc &b = run_input.bc_list(i);
+      bp.push_back(b.rho);
+      for (int k = 0; k < 3; k++) bp.push_back(b.velocity.get_dim(0) > k ? b.velocity(k) : 0.);
+      bp.push_back(b.p_static); bp.push_back(b.T_static); bp.push_back(b.p_total); bp.push_back(b.T_total); bp.push_back(b.mach);
+      bp.push_back(b.nx); bp.push_back(b.ny); bp.push_back(b.nz); bp.push_back((double)b.use_wm);
+    }
+    put_dvec(p + "bc_params", bp, {13, nb});
+    put_dvec(p + "R_ref", vector<double>(1, run_input.viscous ? run_input.R_ref : run_input.R_gas));
   }
 }
 
