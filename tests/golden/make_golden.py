@@ -50,6 +50,13 @@ GOLDEN.update({
         dict(_FREE, order=1, adv_type=0, riemann_solve_type=3, viscous=1, dt=1e-5, dx_cyclic=None, dy_cyclic=None, dz_cyclic=None, bc_Cyclic_type=None,
              bc_In_type="sub_in_char", bc_In_p_total=107200., bc_In_T_total=305.4, bc_In_nx=1., bc_In_ny=0., bc_In_nz=0., bc_Out_type="sub_out_char",
              bc_Out_p_static=100500., bc_Wall_type="adiabat_wall", bc_Top_type="slip_wall_dual", **_FORCE), 2),
+    # triangles (segment faces, dense operators): supersonic inflow / outflow, isothermal wall, moving adiabatic wall -- the boundary kinds of the
+    # shipped cylinder case (BASELINE config 2's origin)
+    "tribdy_p2_ns_supin_supout_isotherm_adiabat_rusanov": ("tri", (5, 4), dict(lengths=(3., 2.), origin=(0., 0.), bcs={"x-": "In", "x+": "Out", "y-": "Wall", "y+": "Top"}),
+        dict(order=2, adv_type=2, riemann_solve_type=0, viscous=1, ic_form=1, dt=2e-6, fix_vis=0, dx_cyclic=None, dy_cyclic=None, dz_cyclic=None, bc_Cyclic_type=None,
+             Mach_c_ic=1.8, nx_c_ic=1., ny_c_ic=0.02, nz_c_ic=0., T_c_ic=290., rho_c_ic=1.2, Mach_free_stream=1.8, rho_free_stream=1.2, T_free_stream=290.,
+             L_free_stream=1., bc_In_type="sup_in", bc_In_p_static=101000., bc_In_mach=1.8, bc_In_T_static=290., bc_In_nx=1., bc_In_ny=0., bc_Out_type="sup_out",
+             bc_Wall_type="isotherm_wall", bc_Wall_T_static=300., bc_Top_type="adiabat_wall", bc_Top_u=15., **_FORCE), 2),
     "quadbdy_p3_euler_subinsimp_suboutsimp_slipdual": ("quad", (6, 5), dict(lengths=(3., 2.), origin=(0., 0.), bcs={"x-": "In", "x+": "Out", "y-": "Wall", "y+": "Wall"}),
         dict(order=3, adv_type=2, riemann_solve_type=3, viscous=0, ic_form=1, dt=1e-5, dx_cyclic=None, dy_cyclic=None, dz_cyclic=None, bc_Cyclic_type=None,
              u_c_ic=100., v_c_ic=4., w_c_ic=0., p_c_ic=100000., rho_c_ic=1.2, bc_In_type="sub_in_simp", bc_In_rho=1.21, bc_In_u=102., bc_In_v=3., bc_In_w=0.,

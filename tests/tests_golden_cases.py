@@ -16,4 +16,5 @@ GOLDEN_CASES = {
     "hexbdy_p1_subinchar_suboutchar_adiabat_slipdual": ("hex", (3, 3, 2), dict(lengths=(1.5, 1., 1.), bcs={"x-": "In", "x+": "Out", "y-": "Wall", "y+": "Wall",
                                                                                                           "z-": "Wall", "z+": "Top"})),
     "quadbdy_p3_euler_subinsimp_suboutsimp_slipdual": ("quad", (6, 5), dict(lengths=(3., 2.), origin=(0., 0.), bcs={"x-": "In", "x+": "Out", "y-": "Wall", "y+": "Wall"})),
+    "tribdy_p2_ns_supin_supout_isotherm_adiabat_rusanov": ("tri", (5, 4), dict(lengths=(3., 2.), origin=(0., 0.), bcs={"x-": "In", "x+": "Out", "y-": "Wall", "y+": "Top"})),
 }
